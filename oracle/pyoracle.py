@@ -1,0 +1,171 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes wrapper of oracle/libqoracle.so (see qoracle.h).
+
+Same method names as q6_b200.engine.Qnb so parity tests call both sides alike.
+Importable only from tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from q6_b200.system import QSystem, qnb_system
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libqoracle.so")
+_PD = C.POINTER(C.c_double)
+_PI = C.POINTER(C.c_int32)
+_PL = C.POINTER(C.c_int64)
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "qoracle.c")
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < max(
+            os.path.getmtime(src), os.path.getmtime(os.path.join(_HERE, "qoracle.h")),
+            os.path.getmtime(os.path.join(_HERE, "..", "include", "qnb.h"))):
+        subprocess.check_call(["make", "-s", "-B", "-C", _HERE, "libqoracle.so"])
+    return LIB_PATH
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    build()
+    lib = C.CDLL(LIB_PATH)
+    H = C.c_void_p
+    lib.qo_last_error.restype = C.c_char_p
+    lib.qo_create.restype = H
+    lib.qo_create.argtypes = [C.POINTER(qnb_system)]
+    lib.qo_destroy.argtypes = [H]
+    lib.qo_update_box.argtypes = [H, _PD, _PD]
+    lib.qo_make_pair_lists.restype = C.c_int
+    lib.qo_make_pair_lists.argtypes = [H, _PD] + [C.c_double] * 7 + [_PL]
+    lib.qo_nonbond.restype = C.c_int
+    lib.qo_nonbond.argtypes = [H, _PD, _PD, C.c_int, _PD, _PD, _PD]
+    lib.qo_list_count.restype = C.c_int
+    lib.qo_list_count.argtypes = [H, C.c_int, C.c_int, _PL]
+    lib.qo_export_list.restype = C.c_int
+    lib.qo_export_list.argtypes = [H, C.c_int, C.c_int, _PI, _PD, C.c_int64]
+    lib.qo_export_lrf.restype = C.c_int
+    lib.qo_export_lrf.argtypes = [H, _PD]
+    lib.qo_make_qconn.restype = None
+    lib.qo_make_qconn.argtypes = [C.c_int, C.c_int, C.c_int, _PI, _PI, C.c_int, _PI, C.c_int, _PI, _PI, C.c_int,
+                                  _PI, _PI, _PI]
+    lib.qo_time_decomposed.restype = C.c_double
+    lib.qo_time_decomposed.argtypes = [C.POINTER(qnb_system), _PD, _PD, C.c_int, _PD, _PD, C.c_int, C.c_int,
+                                       C.c_int, _PD, _PD, _PD, _PD]
+    _lib = lib
+    return lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(_PD)
+
+
+class Oracle:
+    def __init__(self, qsys: QSystem):
+        self.lib = load()
+        self.sys = qsys
+        st, keep = qsys.as_struct()
+        self.h = self.lib.qo_create(C.byref(st))
+        if not self.h:
+            raise RuntimeError(self.lib.qo_last_error().decode())
+        if qsys.use_PBC:
+            self.update_box(qsys.boxlength)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.qo_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def update_box(self, boxlength, inv_boxl=None):
+        b = np.ascontiguousarray(boxlength, dtype=np.float64)
+        ib = np.ascontiguousarray(1.0 / b if inv_boxl is None else inv_boxl, dtype=np.float64)
+        self.lib.qo_update_box(self.h, _dp(b), _dp(ib))
+
+    def make_pair_lists(self, x, Rq, Rcq2, RcLRF2, Rcpp2, Rcpw2, Rcww2, RcLRF=None):
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+        if RcLRF is None:
+            RcLRF = float(np.sqrt(RcLRF2)) if RcLRF2 >= 0 else -1.0
+        counts = np.zeros(8, np.int64)
+        rc = self.lib.qo_make_pair_lists(self.h, _dp(x), Rq, Rcq2, RcLRF2, Rcpp2, Rcpw2, Rcww2, RcLRF,
+                                         counts.ctypes.data_as(_PL))
+        if rc:
+            raise RuntimeError(self.lib.qo_last_error().decode())
+        return counts
+
+    def pot_energy_nonbonds(self, x, lambdas, md=True, qq=True, d=None):
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+        lam = np.ascontiguousarray(lambdas, dtype=np.float64).reshape(-1)
+        if d is None:
+            d = np.zeros(3 * self.sys.natom)
+        E = np.zeros(7)
+        EQ = np.zeros(6 * self.sys.nstates)
+        flags = (1 if md else 0) | (2 if qq else 0)
+        self.lib.qo_nonbond(self.h, _dp(x), _dp(lam), flags, _dp(d.reshape(-1)), _dp(E), _dp(EQ))
+        return d.reshape(-1, 3), E, EQ.reshape(self.sys.nstates, 6)
+
+    def list_count(self, which, state=1):
+        n = C.c_int64()
+        self.lib.qo_list_count(self.h, which, state, C.byref(n))
+        return n.value
+
+    def export_list(self, which, state=1, params=True):
+        n = self.list_count(which, state)
+        ij = np.zeros((max(n, 1), 2), np.int32)
+        p = np.zeros((max(n, 1), 4))
+        self.lib.qo_export_list(self.h, which, state, ij.ctypes.data_as(_PI), _dp(p), n)
+        return ij[:n], (p[:n] if params else None)
+
+    def export_lrf(self):
+        out = np.zeros((self.sys.ncgp, 43))
+        self.lib.qo_export_lrf(self.h, _dp(out))
+        return out
+
+
+def make_qconn(nstates, nat_solute, nqat, iqseq, iqatom, bnd_solute, qbnd_ij, qbnd_cod, exspec_ij, exspec_flag):
+    """Literal find_bonded recursion (nonbondene.f90:3131); returns [iq][atom][state]."""
+    lib = load()
+    I = np.int32
+    iqseq = np.ascontiguousarray(iqseq, I)
+    iqatom = np.ascontiguousarray(iqatom, I)
+    bnd = np.ascontiguousarray(bnd_solute, I).reshape(-1, 3)
+    qb = np.ascontiguousarray(qbnd_ij, I).reshape(-1, 2)
+    qc = np.ascontiguousarray(np.asarray(qbnd_cod, I).reshape(-1, nstates).T)  # (bond,state) col-major
+    ex = np.ascontiguousarray(exspec_ij, I).reshape(-1, 2)
+    ef = np.ascontiguousarray(np.asarray(exspec_flag, I).reshape(-1, nstates).T)
+    out = np.zeros(nstates * nat_solute * nqat, I)
+    pi = lambda a: (a if a.size else np.zeros(1, I)).ctypes.data_as(_PI)
+    lib.qo_make_qconn(nstates, nat_solute, nqat, pi(iqseq), pi(iqatom), bnd.shape[0], pi(bnd), qb.shape[0], pi(qb),
+                      pi(qc), ex.shape[0], pi(ex), pi(ef), out.ctypes.data_as(_PI))
+    return out.reshape(nqat, nat_solute, nstates)
+
+
+def time_decomposed(qsys: QSystem, x, lambdas, cut7, nthreads, steps, md=True, qq=True, build_each=False):
+    """Qdyn6p-style decomposed CPU run; returns dict(seconds, list_seconds, d, E, EQ)."""
+    lib = load()
+    st, keep = qsys.as_struct()
+    x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+    lam = np.ascontiguousarray(lambdas, dtype=np.float64)
+    cut = np.ascontiguousarray(cut7, dtype=np.float64)
+    box = None
+    if qsys.use_PBC:
+        box = np.concatenate([qsys.boxlength, 1.0 / qsys.boxlength]).astype(np.float64)
+    d = np.zeros(3 * qsys.natom)
+    E = np.zeros(7)
+    EQ = np.zeros(6 * qsys.nstates)
+    ls = C.c_double()
+    flags = (1 if md else 0) | (2 if qq else 0)
+    sec = lib.qo_time_decomposed(C.byref(st), _dp(x), _dp(lam), flags, _dp(cut), _dp(box) if box is not None else None,
+                                 nthreads, steps, int(build_each), _dp(d), _dp(E), _dp(EQ),
+                                 C.cast(C.byref(ls), _PD))
+    if sec < 0:
+        raise RuntimeError(lib.qo_last_error().decode())
+    return dict(seconds=sec, list_seconds=ls.value, d=d.reshape(-1, 3), E=E, EQ=EQ.reshape(qsys.nstates, 6))

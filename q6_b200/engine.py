@@ -1,0 +1,227 @@
+"""ctypes binding of the C ABI (include/qnb.h) with the reference's procedure names.
+
+``Qnb.make_pair_lists`` and ``Qnb.pot_energy_nonbonds`` take the arguments of the
+Fortran procedures they replace (nonbondene.f90:749, potene.f90:320) and are what
+the parity tests call, so that a test reads like the reference's call sites.
+The shared library is the product; there is no Python or CPU fallback -- if
+``libqnb.so`` is missing or no GPU is usable, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .system import QSystem, qnb_system
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libqnb.so")
+
+QNB_FLAG_MD = 1
+QNB_FLAG_QQ = 2
+LIST_PP, LIST_PW, LIST_WW, LIST_QP, LIST_QW, LIST_QQ, LIST_QQP = range(7)
+LRF_STRIDE = 43
+E_COUNT = 7
+EQ_STRIDE = 6
+E_NAMES = ("pp.el", "pp.vdw", "pw.el", "pw.vdw", "ww.el", "ww.vdw", "LRF")
+EQ_NAMES = ("qq.el", "qq.vdw", "qp.el", "qp.vdw", "qw.el", "qw.vdw")
+
+_PD = C.POINTER(C.c_double)
+_PI = C.POINTER(C.c_int32)
+_PL = C.POINTER(C.c_int64)
+_PF = C.POINTER(C.c_float)
+
+
+class QnbError(RuntimeError):
+    """A non-zero return of the C ABI; the Fortran wrapper would call die()."""
+
+
+def bind(lib, prefix: str):
+    """Declare the argument types shared by libqnb (prefix 'qnb') and the oracle (prefix 'qo')."""
+    f = getattr(lib, f"{prefix}_last_error")
+    f.restype = C.c_char_p
+    f.argtypes = []
+    return lib
+
+
+_lib = None
+
+
+def load_library(path: str = LIB_PATH):
+    """dlopen libqnb.so and declare every entry point of include/qnb.h."""
+    global _lib
+    if _lib is not None and path == LIB_PATH:
+        return _lib
+    if not os.path.exists(path):
+        raise QnbError(f"{path} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(the CUDA library is the product; there is no CPU fallback)")
+    lib = C.CDLL(path)
+    H = C.c_void_p
+    lib.qnb_last_error.restype = C.c_char_p
+    lib.qnb_last_error.argtypes = []
+    lib.qnb_device_count.restype = C.c_int
+    lib.qnb_device_count.argtypes = []
+    lib.qnb_init.restype = C.c_int
+    lib.qnb_init.argtypes = [C.POINTER(qnb_system), C.c_int, C.POINTER(H)]
+    lib.qnb_update_box.restype = C.c_int
+    lib.qnb_update_box.argtypes = [H, _PD, _PD]
+    lib.qnb_build_lists.restype = C.c_int
+    lib.qnb_build_lists.argtypes = [H, _PD] + [C.c_double] * 7 + [_PL]
+    lib.qnb_nonbond.restype = C.c_int
+    lib.qnb_nonbond.argtypes = [H, _PD, _PD, C.c_int, _PD, _PD, _PD]
+    lib.qnb_list_count.restype = C.c_int
+    lib.qnb_list_count.argtypes = [H, C.c_int, C.c_int, _PL]
+    lib.qnb_export_list.restype = C.c_int
+    lib.qnb_export_list.argtypes = [H, C.c_int, C.c_int, _PI, _PD, C.c_int64]
+    lib.qnb_export_lrf.restype = C.c_int
+    lib.qnb_export_lrf.argtypes = [H, _PD]
+    lib.qnb_comm_unique_id.restype = C.c_int
+    lib.qnb_comm_unique_id.argtypes = [C.c_void_p]
+    lib.qnb_comm_init.restype = C.c_int
+    lib.qnb_comm_init.argtypes = [H, C.c_int, C.c_int, C.c_void_p]
+    lib.qnb_bench_nonbond.restype = C.c_int
+    lib.qnb_bench_nonbond.argtypes = [H, _PD, C.c_int, C.c_int, C.c_int, _PF]
+    lib.qnb_bench_build_lists.restype = C.c_int
+    lib.qnb_bench_build_lists.argtypes = [H, C.c_int, _PF]
+    lib.qnb_bench_kernels.restype = C.c_int
+    lib.qnb_bench_kernels.argtypes = [H, _PD, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int, _PF, C.c_int]
+    lib.qnb_launch_count.restype = C.c_int64
+    lib.qnb_launch_count.argtypes = [H]
+    lib.qnb_last_copy_bytes.restype = C.c_int
+    lib.qnb_last_copy_bytes.argtypes = [H, _PL, _PL]
+    lib.qnb_finalize.restype = C.c_int
+    lib.qnb_finalize.argtypes = [H]
+    if path == LIB_PATH:
+        _lib = lib
+    return lib
+
+
+def _dp(a: np.ndarray):
+    return a.ctypes.data_as(_PD)
+
+
+class Qnb:
+    """One handle = one GPU = one (shard of a) system."""
+
+    def __init__(self, qsys: QSystem, device: int = 0, lib=None):
+        self.lib = lib or load_library()
+        self.sys = qsys
+        if self.lib.qnb_device_count() <= 0:
+            raise QnbError("no usable CUDA device: " + self.lib.qnb_last_error().decode())
+        st, keep = qsys.as_struct()
+        h = C.c_void_p()
+        rc = self.lib.qnb_init(C.byref(st), device, C.byref(h))
+        del keep
+        if rc != 0:
+            raise QnbError(self.lib.qnb_last_error().decode())
+        self.h = h
+        if qsys.use_PBC:
+            self.update_box(qsys.boxlength)
+
+    # -- error plumbing
+    def _check(self, rc: int):
+        if rc != 0:
+            raise QnbError(self.lib.qnb_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.qnb_finalize(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- reference-named operations
+    def update_box(self, boxlength, inv_boxl=None):
+        b = np.ascontiguousarray(boxlength, dtype=np.float64)
+        ib = np.ascontiguousarray(1.0 / b if inv_boxl is None else inv_boxl, dtype=np.float64)
+        self._check(self.lib.qnb_update_box(self.h, _dp(b), _dp(ib)))
+
+    def make_pair_lists(self, x, Rq, Rcq2, RcLRF2, Rcpp2, Rcpw2, Rcww2, RcLRF=None):
+        """make_pair_lists(Rq,Rcq2,RcLRF2,Rcpp2,Rcpw2,Rcww2), nonbondene.f90:749."""
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+        assert x.size == 3 * self.sys.natom
+        if RcLRF is None:
+            RcLRF = float(np.sqrt(RcLRF2)) if RcLRF2 >= 0 else -1.0
+        counts = np.zeros(8, np.int64)
+        self._check(self.lib.qnb_build_lists(self.h, _dp(x), Rq, Rcq2, RcLRF2, Rcpp2, Rcpw2, Rcww2, RcLRF,
+                                             counts.ctypes.data_as(_PL)))
+        return counts
+
+    def pot_energy_nonbonds(self, x, lambdas, md=True, qq=True, d=None):
+        """pot_energy_nonbonds(E,EQ,md) (+ nonbond_qq/nonbond_qqp when qq): returns (d, E[7], EQ[nstates][6])."""
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+        lam = np.ascontiguousarray(lambdas, dtype=np.float64).reshape(-1)
+        assert lam.size == self.sys.nstates
+        if d is None:
+            d = np.zeros(3 * self.sys.natom)
+        else:
+            assert d.dtype == np.float64 and d.flags.c_contiguous
+        E = np.zeros(E_COUNT)
+        EQ = np.zeros(EQ_STRIDE * self.sys.nstates)
+        flags = (QNB_FLAG_MD if md else 0) | (QNB_FLAG_QQ if qq else 0)
+        self._check(self.lib.qnb_nonbond(self.h, _dp(x), _dp(lam), flags, _dp(d.reshape(-1)), _dp(E), _dp(EQ)))
+        return d.reshape(-1, 3), E, EQ.reshape(self.sys.nstates, EQ_STRIDE)
+
+    def list_count(self, which: int, state: int = 1) -> int:
+        n = C.c_int64()
+        self._check(self.lib.qnb_list_count(self.h, which, state, C.byref(n)))
+        return n.value
+
+    def export_list(self, which: int, state: int = 1, params: bool = True):
+        n = self.list_count(which, state)
+        ij = np.zeros((max(n, 1), 2), np.int32)
+        p = np.zeros((max(n, 1), 4)) if params else None
+        self._check(self.lib.qnb_export_list(self.h, which, state, ij.ctypes.data_as(_PI),
+                                             _dp(p) if params else None, n))
+        return ij[:n], (p[:n] if params else None)
+
+    def export_lrf(self):
+        out = np.zeros((self.sys.ncgp, LRF_STRIDE))
+        self._check(self.lib.qnb_export_lrf(self.h, _dp(out)))
+        return out
+
+    # -- multi-GPU
+    def unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        self._check(self.lib.qnb_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, rank: int, nranks: int, uid: bytes):
+        self._check(self.lib.qnb_comm_init(self.h, rank, nranks, C.c_char_p(uid)))
+
+    # -- measurement
+    def bench_nonbond(self, lambdas, steps: int, md=True, qq=True, flush_l2=False) -> float:
+        lam = np.ascontiguousarray(lambdas, dtype=np.float64)
+        ms = C.c_float()
+        flags = (QNB_FLAG_MD if md else 0) | (QNB_FLAG_QQ if qq else 0)
+        self._check(self.lib.qnb_bench_nonbond(self.h, _dp(lam), flags, steps, int(flush_l2), C.byref(ms)))
+        return ms.value
+
+    def bench_build_lists(self, reps: int) -> float:
+        ms = C.c_float()
+        self._check(self.lib.qnb_bench_build_lists(self.h, reps, C.byref(ms)))
+        return ms.value
+
+    def bench_kernels(self, lambdas, reps: int, md=True, qq=True, flush_l2=False) -> dict:
+        lam = np.ascontiguousarray(lambdas, dtype=np.float64)
+        names = C.create_string_buffer(4096)
+        ms = (C.c_float * 64)()
+        flags = (QNB_FLAG_MD if md else 0) | (QNB_FLAG_QQ if qq else 0)
+        n = self.lib.qnb_bench_kernels(self.h, _dp(lam), flags, reps, int(flush_l2), names, 4096, ms, 64)
+        if n < 0:
+            raise QnbError(self.lib.qnb_last_error().decode())
+        nm = names.value.decode().split("\n")[:n]
+        return {nm[i]: ms[i] for i in range(n)}
+
+    def launch_count(self) -> int:
+        return int(self.lib.qnb_launch_count(self.h))
+
+    def last_copy_bytes(self):
+        a, b = C.c_int64(), C.c_int64()
+        self._check(self.lib.qnb_last_copy_bytes(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
