@@ -1,0 +1,770 @@
+// qnb.cu -- C ABI (include/qnb.h) of the B200 nonbonded engine: device state, list build and
+// step orchestration.  Kernels live in qnb_lists.cuh / qnb_forces.cuh, host tables in qnb_tables.hpp.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/qnb.h"
+#include "qnb_forces.cuh"
+#include "qnb_kernels.cuh"
+#include "qnb_lists.cuh"
+#include "qnb_tables.hpp"
+
+namespace qnb {
+
+static thread_local std::string g_err;
+static int fail(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return 1;
+}
+#define CU(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// ---- minimal NCCL binding, resolved at run time from whichever libnccl the process already has
+struct ncclUniqueIdT { char internal[128]; };
+typedef void *ncclCommT;
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(ncclUniqueIdT *) = nullptr;
+    int (*CommInitRank)(ncclCommT *, int, ncclUniqueIdT, int) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, ncclCommT, cudaStream_t) = nullptr;
+    int (*CommDestroy)(ncclCommT) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool load() {
+        if (lib) return true;
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *n : names) {
+            lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (lib) break;
+        }
+        if (!lib) return false;
+        GetUniqueId = (int (*)(ncclUniqueIdT *))dlsym(lib, "ncclGetUniqueId");
+        CommInitRank = (int (*)(ncclCommT *, int, ncclUniqueIdT, int))dlsym(lib, "ncclCommInitRank");
+        AllReduce = (int (*)(const void *, void *, size_t, int, int, ncclCommT, cudaStream_t))dlsym(lib, "ncclAllReduce");
+        CommDestroy = (int (*)(ncclCommT))dlsym(lib, "ncclCommDestroy");
+        GetErrorString = (const char *(*)(int))dlsym(lib, "ncclGetErrorString");
+        return GetUniqueId && CommInitRank && AllReduce && CommDestroy;
+    }
+};
+static NcclApi g_nccl;
+constexpr int kNcclDouble = 8, kNcclSum = 0;
+
+template <typename T>
+struct DBuf {   // device buffer that only grows
+    T *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t n) {
+        if (n <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        size_t want = n + n / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+        if (e != cudaSuccess) { cap = 0; return fail("cudaMalloc(%zu bytes): %s", want * sizeof(T), cudaGetErrorString(e)); }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+template <typename T>
+static int upload(DBuf<T> &b, const std::vector<T> &v) {
+    if (b.ensure(std::max<size_t>(v.size(), 1))) return 1;
+    if (!v.empty()) CU(cudaMemcpy(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+}  // namespace qnb
+
+using namespace qnb;
+
+struct qnb_handle {
+    int device = 0;
+    HostTables T;
+    Dev D{};
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // static device tables
+    DBuf<double> crg;
+    DBuf<float> crgf, ljf;
+    DBuf<int> ctype, grp_of_atom, g_first, g_n, g_switch, g_atoms, g_nq, u_sw, u_grp, sp_off, sp_partner, gs_off,
+        gs_atoms, iqseq;
+    DBuf<uint8_t> is_q, excl, qbonded, u_excl, ljcode, sp_code;
+    DBuf<QPar4> qp_tab, qw_tab;
+    DBuf<QStatic> qstatic;
+    int n_qq = 0, n_qstatic = 0;
+    // per-step
+    DBuf<double> x, out /* grad[3n] | E[7] | EQ[6*nstates] */, lambda, lrf;
+    double *hx = nullptr, *hout = nullptr, *hlam = nullptr;   // pinned staging
+    size_t nout = 0;
+    // per-build
+    Cut cut{};
+    Grid grid{};
+    bool have_grid = false;
+    DBuf<double> upos;
+    DBuf<int> cell_of, cell_count, cell_start, cell_items, counts, row_tot, row_off, flag, pos, qp_list, qw_list,
+        qp_shift_atom;
+    DBuf<uint32_t> rows;
+    int nqp = 0, nqw = 0;
+    bool qp_done = false, qw_done = false, lists_built = false;
+    int64_t total_rows = 0;
+    int3 lrf_reach{1, 1, 1};
+    double box[3] = {0, 0, 0}, inv_box[3] = {0, 0, 0};
+    // comm
+    ncclCommT comm = nullptr;
+    int rank = 0, nranks = 1;
+    // stats
+    int64_t launches = 0, last_h2d = 0, last_d2h = 0;
+    DBuf<char> flush;
+    int last_flags = 0;
+};
+
+namespace qnb {
+
+#define LAUNCH(h, kernel, grid, block, smem, ...)                      \
+    do {                                                               \
+        kernel<<<(grid), (block), (smem), (h)->st>>>(__VA_ARGS__);     \
+        (h)->launches++;                                               \
+    } while (0)
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+static void refresh_dev(qnb_handle *h) {
+    for (int d = 0; d < 3; d++) { h->D.box[d] = h->box[d]; h->D.inv_box[d] = h->inv_box[d]; }
+}
+
+static int init_device(qnb_handle *h) {
+    HostTables &T = h->T;
+    const qnb_system &s = T.s;
+    Dev &D = h->D;
+    D.natom = s.natom; D.nat_solute = s.nat_solute; D.nwat = s.nwat; D.ncgp = s.ncgp; D.ncgp_solute = s.ncgp_solute;
+    D.nunit = T.nunit; D.nqat = s.nqat; D.nstates = s.nstates; D.nct = T.nct;
+    D.use_PBC = s.use_PBC != 0; D.use_LRF = s.use_LRF != 0; D.geometric = s.ivdw_rule == QNB_VDW_GEOMETRIC;
+    D.spc_water = (s.ivdw_rule == QNB_VDW_GEOMETRIC) && (s.solvent_type == QNB_SOLVENT_SPC);   // potene.f90:347
+    D.qswitch0 = s.qswitch - 1;
+    D.el14 = s.el14_scale; D.el14f = (float)s.el14_scale;
+    for (int d = 0; d < 3; d++) D.xpcent[d] = s.xpcent[d];
+    D.pp_s = s.pp_start; D.pp_e = s.pp_end; D.pw_s = s.pw_start; D.pw_e = s.pw_end; D.qp_s = s.qp_start; D.qp_e = s.qp_end;
+    D.ww_s = s.ww_start; D.ww_e = s.ww_end; D.qw_s = s.qw_start; D.qw_e = s.qw_end; D.at_s = s.natom_start; D.at_e = s.natom_end;
+
+    std::vector<float> crgf(T.crg.begin(), T.crg.end());
+    std::vector<float> ljf((size_t)T.nct * 6);
+    for (int t = 0; t < T.nct; t++)
+        for (int c = 0; c < 3; c++) { ljf[(t * 3 + c) * 2] = (float)T.lj_a[t * 3 + c]; ljf[(t * 3 + c) * 2 + 1] = (float)T.lj_b[t * 3 + c]; }
+    std::vector<int> g_nq(s.ncgp, 0);
+    for (int g = 0; g < s.ncgp; g++)
+        for (int k = 0; k < T.g_n[g]; k++) g_nq[g] += !T.is_q[T.g_atoms[T.g_first[g] + k]];
+    if (upload(h->crg, T.crg) || upload(h->crgf, crgf) || upload(h->ljf, ljf) || upload(h->ctype, T.ctype) ||
+        upload(h->grp_of_atom, T.grp_of_atom) || upload(h->g_first, T.g_first) || upload(h->g_n, T.g_n) ||
+        upload(h->g_switch, T.g_switch) || upload(h->g_atoms, T.g_atoms) || upload(h->g_nq, g_nq) ||
+        upload(h->u_sw, T.u_sw) || upload(h->u_grp, T.u_grp) || upload(h->sp_off, T.sp_off) ||
+        upload(h->sp_partner, T.sp_partner) || upload(h->gs_off, T.gs_off) || upload(h->gs_atoms, T.gs_atoms) ||
+        upload(h->iqseq, T.iqseq0) || upload(h->is_q, T.is_q) || upload(h->excl, T.excl) ||
+        upload(h->qbonded, T.qbonded) || upload(h->u_excl, T.u_excl) || upload(h->ljcode, T.ljcode) ||
+        upload(h->sp_code, T.sp_code))
+        return 1;
+    {
+        std::vector<QPar4> a(T.qp_tab.size()), b(T.qw_tab.size());
+        for (size_t k = 0; k < a.size(); k++) a[k] = QPar4{T.qp_tab[k].A, T.qp_tab[k].B, T.qp_tab[k].el, T.qp_tab[k].score};
+        for (size_t k = 0; k < b.size(); k++) b[k] = QPar4{T.qw_tab[k].A, T.qw_tab[k].B, T.qw_tab[k].el, T.qw_tab[k].score};
+        if (upload(h->qp_tab, a) || upload(h->qw_tab, b)) return 1;
+        std::vector<QStatic> qs;
+        for (const auto &e : T.qq_list) qs.push_back(QStatic{e.i, e.j, e.state, e.soft, QPar4{e.p.A, e.p.B, e.p.el, e.p.score}});
+        h->n_qq = (int)qs.size();
+        for (const auto &e : T.qqp_list) qs.push_back(QStatic{e.i, e.j, e.state, 0, QPar4{e.p.A, e.p.B, e.p.el, e.p.score}});
+        h->n_qstatic = (int)qs.size();
+        if (upload(h->qstatic, qs)) return 1;
+    }
+    D.crg = h->crg.p; D.crgf = h->crgf.p; D.ctype = h->ctype.p; D.is_q = h->is_q.p; D.excl = h->excl.p; D.qbonded = h->qbonded.p;
+    D.grp_of_atom = h->grp_of_atom.p; D.g_first = h->g_first.p; D.g_n = h->g_n.p; D.g_switch = h->g_switch.p;
+    D.g_atoms = h->g_atoms.p; D.g_nq = h->g_nq.p; D.u_sw = h->u_sw.p; D.u_grp = h->u_grp.p; D.u_excl = h->u_excl.p;
+    D.ljf = h->ljf.p; D.ljcode = h->ljcode.p; D.sp_off = h->sp_off.p; D.sp_partner = h->sp_partner.p; D.sp_code = h->sp_code.p;
+    D.gs_off = h->gs_off.p; D.gs_atoms = h->gs_atoms.p; D.iqseq = h->iqseq.p; D.qp_tab = h->qp_tab.p; D.qw_tab = h->qw_tab.p;
+    for (int a = 0; a < 3; a++) {
+        D.wq[a] = s.nwat > 0 ? (float)T.w_crg[a] : 0.f;
+        D.wqd[a] = s.nwat > 0 ? T.w_crg[a] : 0.0;
+        D.wct[a] = s.nwat > 0 ? T.w_ctype[a] : 0;
+        for (int b = 0; b < 3; b++) {
+            const QPar p = s.nwat > 0 ? T.ww_par[a * 3 + b] : QPar{};
+            D.wwA[a * 3 + b] = (float)p.A; D.wwB[a * 3 + b] = (float)p.B; D.wwQ[a * 3 + b] = (float)p.el; D.wwQd[a * 3 + b] = p.el;
+        }
+    }
+    const size_t n3 = 3 * (size_t)s.natom;
+    h->nout = n3 + QNB_E_COUNT + (size_t)QNB_EQ_STRIDE * s.nstates;
+    if (h->x.ensure(n3) || h->out.ensure(h->nout) || h->lambda.ensure(kMaxStates) ||
+        h->lrf.ensure((size_t)QNB_LRF_STRIDE * std::max(s.ncgp, 1)))
+        return 1;
+    CU(cudaMemset(h->lrf.p, 0, sizeof(double) * QNB_LRF_STRIDE * std::max(s.ncgp, 1)));
+    CU(cudaMallocHost(&h->hx, n3 * sizeof(double)));
+    CU(cudaMallocHost(&h->hout, h->nout * sizeof(double)));
+    CU(cudaMallocHost(&h->hlam, kMaxStates * sizeof(double)));
+    CU(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&h->ev0));
+    CU(cudaEventCreate(&h->ev1));
+    return 0;
+}
+
+// ------------------------------------------------------------------ list build
+static void make_grid(qnb_handle *h, const double *hx) {
+    const qnb_system &s = h->T.s;
+    Grid &G = h->grid;
+    double rcmax = std::sqrt(std::max({h->cut.rc2[0], h->cut.rc2[1], h->cut.rc2[2], 1.0})) * 1.0001;
+    const int nmax = 40;
+    if (s.use_PBC) {
+        G.periodic = 1;
+        for (int d = 0; d < 3; d++) {
+            int n = (int)std::floor(h->box[d] / rcmax);
+            n = std::max(1, std::min(n, nmax));
+            G.n[d] = n;
+            G.org[d] = 0;
+            G.inv_box[d] = h->inv_box[d];
+            G.inv_cell[d] = n / h->box[d];
+        }
+    } else {
+        G.periodic = 0;
+        // bounding box of the switch atoms at the first build, padded; later drift is absorbed by clamping
+        if (!h->have_grid) {
+            double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+            for (int u = 0; u < h->T.nunit; u++)
+                for (int d = 0; d < 3; d++) {
+                    double v = hx[3 * h->T.u_sw[u] + d];
+                    lo[d] = std::min(lo[d], v); hi[d] = std::max(hi[d], v);
+                }
+            for (int d = 0; d < 3; d++) { G.org[d] = lo[d] - 2.0; G.inv_box[d] = hi[d] + 2.0 - G.org[d]; /* extent kept here */ }
+        }
+        for (int d = 0; d < 3; d++) {
+            const double ext = G.inv_box[d];
+            double cell = std::max(rcmax, ext / nmax);
+            G.n[d] = std::max(1, (int)std::floor(ext / cell) + 1);
+            G.inv_cell[d] = 1.0 / cell;
+        }
+    }
+    G.ncell = G.n[0] * G.n[1] * G.n[2];
+    h->have_grid = true;
+    // LRF reach in cells
+    const bool all = h->cut.lrf_all[0] || h->cut.lrf_all[1] || h->cut.lrf_all[2];
+    const double rl = std::sqrt(std::max(h->cut.rclrf2, 0.0));
+    int r[3];
+    for (int d = 0; d < 3; d++) {
+        double m = std::ceil(rl * G.inv_cell[d] * 1.0001) + 1;
+        r[d] = (all || m > G.n[d]) ? G.n[d] : (int)m;
+    }
+    h->lrf_reach = make_int3(r[0], r[1], r[2]);
+}
+
+static int run_exclusive_scan(qnb_handle *h, const int *in, int *out, int n) {
+    LAUNCH(h, k_exclusive_scan, 1, 1024, 0, in, out, n);
+    return 0;
+}
+
+static int build_device(qnb_handle *h, const double *hx_for_grid) {
+    const Dev &D = h->D;
+    const int nu = D.nunit;
+    make_grid(h, hx_for_grid);
+    const Grid G = h->grid;
+    if (h->upos.ensure(3 * (size_t)std::max(nu, 1)) || h->cell_of.ensure(std::max(nu, 1)) ||
+        h->cell_count.ensure(G.ncell + 1) || h->cell_start.ensure(G.ncell + 2) || h->cell_items.ensure(std::max(nu, 1)) ||
+        h->counts.ensure(3 * (size_t)std::max(nu, 1)) || h->row_tot.ensure(std::max(nu, 1) + 1) ||
+        h->row_off.ensure(std::max(nu, 1) + 2) ||
+        h->flag.ensure(std::max({D.natom, D.nwat, 1}) + 1) || h->pos.ensure(std::max({D.natom, D.nwat, 1}) + 2) ||
+        h->qp_list.ensure(std::max(D.nat_solute, 1)) || h->qw_list.ensure(std::max(D.nwat, 1)) ||
+        h->qp_shift_atom.ensure(std::max(D.ncgp_solute, 1)))
+        return 1;
+    const bool md_lists = true;
+    if (nu > 0 && md_lists) {
+        CU(cudaMemsetAsync(h->cell_count.p, 0, sizeof(int) * (G.ncell + 1), h->st));
+        LAUNCH(h, k_bin_units, cdiv(nu, 256), 256, 0, D, G, h->x.p, h->upos.p, h->cell_of.p, h->cell_count.p);
+        run_exclusive_scan(h, h->cell_count.p, h->cell_start.p, G.ncell);
+        CU(cudaMemsetAsync(h->cell_count.p, 0, sizeof(int) * (G.ncell + 1), h->st));
+        LAUNCH(h, k_cell_fill, cdiv(nu, 256), 256, 0, nu, h->cell_of.p, h->cell_start.p, h->cell_count.p, h->cell_items.p);
+        LAUNCH(h, k_cell_sort, cdiv(G.ncell, 128), 128, 0, G.ncell, h->cell_start.p, h->cell_items.p);
+        LAUNCH(h, k_build_rows<false>, cdiv(nu * 32, 256), 256, 0, D, h->cut, G, h->upos.p, h->cell_of.p, h->cell_start.p,
+               h->cell_items.p, h->counts.p, (const int *)nullptr, (uint32_t *)nullptr);
+        LAUNCH(h, k_row_totals, cdiv(nu, 256), 256, 0, nu, h->counts.p, h->row_tot.p);
+        run_exclusive_scan(h, h->row_tot.p, h->row_off.p, nu);
+        int total = 0;
+        CU(cudaMemcpyAsync(&total, h->row_off.p + nu, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+        CU(cudaStreamSynchronize(h->st));
+        h->total_rows = total;
+        if (h->rows.ensure((size_t)std::max(total, 1))) return 1;
+        LAUNCH(h, k_build_rows<true>, cdiv(nu * 32, 256), 256, 0, D, h->cut, G, h->upos.p, h->cell_of.p, h->cell_start.p,
+               h->cell_items.p, h->counts.p, h->row_off.p, h->rows.p);
+    }
+    // Q-atom partner lists: built once when the cut-off covers everything (nbqplist L3678, nbqwlist L3889,
+    // nbqplist_box L3780, nbqwlist_box L3972)
+    const double rex2 = h->T.s.rexcl_o * h->T.s.rexcl_o;
+    if (D.nqat > 0) {
+        const bool skip_qp = h->qp_done && (D.use_PBC ? (h->cut.Rq < 0.0) : (h->cut.rcq2 > rex2));
+        const bool skip_qw = h->qw_done && (D.use_PBC ? (h->cut.Rq < 0.0) : (h->cut.rcq2 > rex2));
+        if (!skip_qp && D.ncgp_solute > 0) {
+            LAUNCH(h, k_qp_flags, cdiv(D.ncgp_solute, 128), 128, 0, D, h->cut, h->x.p, h->flag.p, h->qp_shift_atom.p);
+            run_exclusive_scan(h, h->flag.p, h->pos.p, D.nat_solute);
+            LAUNCH(h, k_compact, cdiv(D.nat_solute, 256), 256, 0, D.nat_solute, h->flag.p, h->pos.p, h->qp_list.p);
+            CU(cudaMemcpyAsync(&h->nqp, h->pos.p + D.nat_solute, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+            CU(cudaStreamSynchronize(h->st));
+            h->qp_done = true;
+        }
+        if (!skip_qw && D.nwat > 0) {
+            LAUNCH(h, k_qw_flags, cdiv(D.nwat, 128), 128, 0, D, h->cut, h->x.p, h->flag.p);
+            run_exclusive_scan(h, h->flag.p, h->pos.p, D.nwat);
+            LAUNCH(h, k_compact, cdiv(D.nwat, 256), 256, 0, D.nwat, h->flag.p, h->pos.p, h->qw_list.p);
+            CU(cudaMemcpyAsync(&h->nqw, h->pos.p + D.nwat, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+            CU(cudaStreamSynchronize(h->st));
+            h->qw_done = true;
+        }
+    }
+    // LRF: cgp_centers + lrf_update over every pair that falls in the LRF branch
+    if (D.use_LRF && D.ncgp > 0) {
+        LAUNCH(h, k_cgp_centers, cdiv(D.ncgp, 128), 128, 0, D, h->x.p, h->lrf.p);
+        if (nu > 0)
+            LAUNCH(h, k_lrf_accumulate, cdiv(nu * 32, 256), 256, 0, D, h->cut, G, h->lrf_reach, h->x.p, h->upos.p,
+                   h->cell_of.p, h->cell_start.p, h->cell_items.p, h->lrf.p);
+        if (h->comm) {
+            // lrf_gather (nonbondene.f90:616-623): sum the moments, keep cgp_cent (identical on every rank).
+            // cgp_cent is divided by nranks after the sum so one all-reduce serves both.
+            int rc = g_nccl.AllReduce(h->lrf.p, h->lrf.p, (size_t)QNB_LRF_STRIDE * D.ncgp, kNcclDouble, kNcclSum, h->comm, h->st);
+            if (rc) return fail("ncclAllReduce(lrf): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
+            // restore the centres (recomputed: bit-identical to the single-rank value)
+            LAUNCH(h, k_cgp_centers_only, cdiv(D.ncgp, 128), 128, 0, D, h->x.p, h->lrf.p);
+        }
+    }
+    CU(cudaStreamSynchronize(h->st));
+    CU(cudaGetLastError());
+    h->lists_built = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------ one nonbonded evaluation on device
+enum StepKernel { K_WATER = 0, K_SOLUTE, K_QPARTNER, K_QATOM, K_QSTATIC, K_LRF, K_COUNT };
+static const char *kStepKernelNames[K_COUNT] = {"k_water_force", "k_solute_force", "k_q_partner", "k_q_atom",
+                                                "k_qq_static", "k_lrf_taylor"};
+
+static bool step_kernel_active(const qnb_handle *h, int k, int flags) {
+    const Dev &D = h->D;
+    const bool md = flags & QNB_FLAG_MD;
+    switch (k) {
+    case K_WATER: return md && D.nwat > 0;
+    case K_SOLUTE: return md && D.ncgp_solute > 0;
+    case K_QPARTNER: return D.nqat > 0 && (h->nqp + h->nqw) > 0;
+    case K_QATOM: return D.nqat > 0 && (h->nqp + h->nqw) > 0;
+    case K_QSTATIC: return (flags & QNB_FLAG_QQ) && h->T.s.is_master && h->n_qstatic > 0;
+    case K_LRF: return md && D.use_LRF;
+    }
+    return false;
+}
+
+static void launch_step_kernel(qnb_handle *h, int k) {
+    const Dev &D = h->D;
+    double *grad = h->out.p, *E = h->out.p + 3 * (size_t)D.natom, *EQ = E + QNB_E_COUNT;
+    const bool pbc = D.use_PBC, spc = D.spc_water, geom = D.geometric;
+    switch (k) {
+    case K_WATER: {
+        const int grid = cdiv(D.nwat * 32, 128);
+#define WCASE(P, S, G) LAUNCH(h, (k_water_force<P, S, G>), grid, 128, 0, D, h->x.p, h->row_off.p, h->counts.p, h->rows.p, grad, E)
+        if (pbc) { if (spc) WCASE(true, true, true); else if (geom) WCASE(true, false, true); else WCASE(true, false, false); }
+        else { if (spc) WCASE(false, true, true); else if (geom) WCASE(false, false, true); else WCASE(false, false, false); }
+#undef WCASE
+        break;
+    }
+    case K_SOLUTE: {
+        const int grid = cdiv(D.ncgp_solute * 32, 128);
+#define SCASE(P, G) LAUNCH(h, (k_solute_force<P, G>), grid, 128, 0, D, h->x.p, h->row_off.p, h->counts.p, h->rows.p, grad, E)
+        if (pbc) { if (geom) SCASE(true, true); else SCASE(true, false); }
+        else { if (geom) SCASE(false, true); else SCASE(false, false); }
+#undef SCASE
+        break;
+    }
+    case K_QPARTNER: {
+        const int n = h->nqp + h->nqw;
+        const size_t sm = sizeof(double) * (3 * (size_t)D.nqat + D.nstates);
+        if (pbc) LAUNCH(h, k_q_partner<true>, cdiv(n, 128), 128, sm, D, h->x.p, h->lambda.p, h->nqp, h->qp_list.p, h->qp_shift_atom.p, h->nqw, h->qw_list.p, grad);
+        else LAUNCH(h, k_q_partner<false>, cdiv(n, 128), 128, sm, D, h->x.p, h->lambda.p, h->nqp, h->qp_list.p, h->qp_shift_atom.p, h->nqw, h->qw_list.p, grad);
+        break;
+    }
+    case K_QATOM:
+        if (pbc) LAUNCH(h, k_q_atom<true>, D.nqat, 128, 0, D, h->x.p, h->lambda.p, h->nqp, h->qp_list.p, h->qp_shift_atom.p, h->nqw, h->qw_list.p, grad, EQ);
+        else LAUNCH(h, k_q_atom<false>, D.nqat, 128, 0, D, h->x.p, h->lambda.p, h->nqp, h->qp_list.p, h->qp_shift_atom.p, h->nqw, h->qw_list.p, grad, EQ);
+        break;
+    case K_QSTATIC:
+        LAUNCH(h, k_qq_static, cdiv(h->n_qstatic, 128), 128, 0, h->n_qstatic, h->n_qq, h->qstatic.p, h->x.p, h->lambda.p, grad, EQ);
+        break;
+    case K_LRF:
+        LAUNCH(h, k_lrf_taylor, cdiv(D.natom, 128), 128, 0, D, h->x.p, h->lrf.p, grad, E);
+        break;
+    }
+}
+
+static int step_device(qnb_handle *h, int flags) {
+    CU(cudaMemsetAsync(h->out.p, 0, h->nout * sizeof(double), h->st));
+    for (int k = 0; k < K_COUNT; k++)
+        if (step_kernel_active(h, k, flags)) launch_step_kernel(h, k);
+    if (h->comm) {
+        // gather_nonbond + serial sum on the master (potene.f90:195-222) as one all-reduce over [d | E | EQ]
+        int rc = g_nccl.AllReduce(h->out.p, h->out.p, h->nout, kNcclDouble, kNcclSum, h->comm, h->st);
+        if (rc) return fail("ncclAllReduce(forces): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
+    }
+    return 0;
+}
+
+}  // namespace qnb
+
+// =============================================================================== C ABI
+extern "C" {
+
+const char *qnb_last_error(void) { return g_err.c_str(); }
+
+int qnb_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { fail("cudaGetDeviceCount: %s", cudaGetErrorString(e)); return 0; }
+    return n;
+}
+
+int qnb_init(const qnb_system *sys, int device, qnb_handle **out) {
+    if (!sys || !out) return fail("qnb_init: null argument");
+    if (sys->abi_version != QNB_ABI_VERSION) return fail("qnb_init: abi_version %d, library is %d", sys->abi_version, QNB_ABI_VERSION);
+    int n = qnb_device_count();
+    if (n <= 0) return fail("qnb_init: no CUDA device (%s); this library has no CPU path", g_err.c_str());
+    if (device < 0 || device >= n) return fail("qnb_init: device %d out of range (0..%d)", device, n - 1);
+    CU(cudaSetDevice(device));
+    qnb_handle *h = new qnb_handle();
+    h->device = device;
+    if (!h->T.build(sys)) { fail("qnb_init: %s", h->T.error.c_str()); delete h; return 1; }
+    if (init_device(h)) { delete h; return 1; }
+    *out = h;
+    return 0;
+}
+
+int qnb_update_box(qnb_handle *h, const double boxlength[3], const double inv_boxl[3]) {
+    if (!h) return fail("null handle");
+    for (int d = 0; d < 3; d++) { h->box[d] = boxlength[d]; h->inv_box[d] = inv_boxl[d]; }
+    refresh_dev(h);
+    return 0;
+}
+
+int qnb_build_lists(qnb_handle *h, const double *x, double Rq, double Rcq2, double RcLRF2, double Rcpp2, double Rcpw2,
+                    double Rcww2, double RcLRF, int64_t counts_out[8]) {
+    if (!h || !x) return fail("qnb_build_lists: null argument");
+    CU(cudaSetDevice(h->device));
+    const qnb_system &s = h->T.s;
+    if (s.use_PBC && !(h->box[0] > 0 && h->box[1] > 0 && h->box[2] > 0)) return fail("qnb_build_lists: periodic system without a box (call qnb_update_box)");
+    Cut &C = h->cut;
+    C.rc2[0] = Rcpp2; C.rc2[1] = Rcpw2; C.rc2[2] = Rcww2;
+    C.rclrf2 = RcLRF2; C.rcq2 = Rcq2; C.Rq = Rq;
+    // "no LRF cut-off" sentinels of the box builders: pp compares its squared argument with -1
+    // (nonbondene.f90:2035), pw/ww compare the global RcLRF (L3066, L4497)
+    C.lrf_all[0] = s.use_PBC && (RcLRF2 == -1.0);
+    C.lrf_all[1] = C.lrf_all[2] = s.use_PBC && (RcLRF == -1.0);
+    const size_t n3 = 3 * (size_t)s.natom;
+    memcpy(h->hx, x, n3 * sizeof(double));
+    CU(cudaMemcpyAsync(h->x.p, h->hx, n3 * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    if (build_device(h, x)) return 1;
+    if (counts_out) {
+        for (int k = 0; k < 8; k++) counts_out[k] = 0;
+        int64_t n;
+        for (int w = 0; w < 5; w++) { if (qnb_list_count(h, w, 1, &n)) return 1; counts_out[w] = n; }
+    }
+    return 0;
+}
+
+int qnb_nonbond(qnb_handle *h, const double *x, const double *lambda, int flags, double *d, double *E_out, double *EQ_out) {
+    if (!h || !x || !lambda || !d || !E_out || !EQ_out) return fail("qnb_nonbond: null argument");
+    if (!h->lists_built) return fail("qnb_nonbond: pair lists have not been built (call qnb_build_lists)");
+    CU(cudaSetDevice(h->device));
+    const qnb_system &s = h->T.s;
+    const size_t n3 = 3 * (size_t)s.natom;
+    memcpy(h->hx, x, n3 * sizeof(double));
+    for (int k = 0; k < s.nstates; k++) h->hlam[k] = lambda[k];
+    CU(cudaMemcpyAsync(h->x.p, h->hx, n3 * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    CU(cudaMemcpyAsync(h->lambda.p, h->hlam, s.nstates * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    h->last_flags = flags;
+    if (step_device(h, flags)) return 1;
+    CU(cudaMemcpyAsync(h->hout, h->out.p, h->nout * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    CU(cudaGetLastError());
+    h->last_h2d = (int64_t)((n3 + s.nstates) * sizeof(double));
+    h->last_d2h = (int64_t)(h->nout * sizeof(double));
+    for (size_t k = 0; k < n3; k++) d[k] += h->hout[k];
+    for (int k = 0; k < QNB_E_COUNT; k++) E_out[k] = h->hout[n3 + k];
+    for (int k = 0; k < QNB_EQ_STRIDE * s.nstates; k++) EQ_out[k] = h->hout[n3 + QNB_E_COUNT + k];
+    return 0;
+}
+
+// ---- list export: expansion of the device rows into the reference's explicit entries (host side)
+static int export_impl(qnb_handle *h, int which, int state, int32_t *ij, double *params, int64_t capacity, int64_t *count) {
+    const HostTables &T = h->T;
+    const qnb_system &s = T.s;
+    const int nst = s.nstates;
+    int64_t n = 0;
+    auto emit = [&](int i1, int j1, const QPar &p) -> bool {
+        if (ij) {
+            if (n >= capacity) return false;
+            ij[2 * n] = i1; ij[2 * n + 1] = j1;
+            if (params) { params[4 * n] = p.A; params[4 * n + 1] = p.B; params[4 * n + 2] = p.el; params[4 * n + 3] = p.score; }
+        }
+        n++;
+        return true;
+    };
+    if (state < 1 || state > nst) return fail("state %d out of range", state);
+    if (which == QNB_LIST_QQ || which == QNB_LIST_QQP) {
+        if (s.is_master)
+            for (const auto &e : (which == QNB_LIST_QQ ? T.qq_list : T.qqp_list))
+                if (e.state == state - 1)
+                    if (!emit(e.iq, which == QNB_LIST_QQ ? e.jq : e.j + 1, e.p)) return fail("export capacity too small");
+        *count = n;
+        return 0;
+    }
+    if (!h->lists_built) return fail("pair lists have not been built");
+    CU(cudaSetDevice(h->device));
+    if (which == QNB_LIST_QP || which == QNB_LIST_QW) {
+        if (s.nqat > 0) {
+            const int m = which == QNB_LIST_QP ? h->nqp : h->nqw;
+            std::vector<int> lst(std::max(m, 1));
+            if (m) CU(cudaMemcpy(lst.data(), which == QNB_LIST_QP ? h->qp_list.p : h->qw_list.p, sizeof(int) * m, cudaMemcpyDeviceToHost));
+            for (int k = 0; k < m; k++)
+                for (int q = 1; q <= s.nqat; q++) {
+                    if (which == QNB_LIST_QP) {
+                        const QPar &p = T.qp_tab[((size_t)(q - 1) * nst + (state - 1)) * s.nat_solute + lst[k]];
+                        if (!emit(q, lst[k] + 1, p)) return fail("export capacity too small");
+                    } else
+                        for (int site = 0; site < s.solv_atom; site++) {
+                            const QPar &p = T.qw_tab[((size_t)(q - 1) * nst + (state - 1)) * s.solv_atom + site];
+                            if (!emit(q, s.nat_solute + s.solv_atom * lst[k] + site + 1, p)) return fail("export capacity too small");
+                        }
+                }
+        }
+        *count = n;
+        return 0;
+    }
+    const int nu = T.nunit;
+    std::vector<int> counts(3 * (size_t)std::max(nu, 1)), off(std::max(nu, 1) + 1);
+    std::vector<uint32_t> rows((size_t)std::max<int64_t>(h->total_rows, 1));
+    if (nu) {
+        CU(cudaMemcpy(counts.data(), h->counts.p, sizeof(int) * 3 * nu, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(off.data(), h->row_off.p, sizeof(int) * (nu + 1), cudaMemcpyDeviceToHost));
+        if (h->total_rows) CU(cudaMemcpy(rows.data(), h->rows.p, sizeof(uint32_t) * h->total_rows, cudaMemcpyDeviceToHost));
+    }
+    const int ns = s.ncgp_solute, sa = s.solv_atom;
+    if (which == QNB_LIST_WW) {
+        for (int u = ns; u < nu; u++) {
+            const int iw = u - ns;
+            for (int k = 0; k < counts[3 * u]; k++) {
+                const int jw = (int)(rows[off[u] + k] & kIdMask);
+                for (int la = 0; la < sa; la++)
+                    for (int ka = 0; ka < sa; ka++)
+                        if (!emit(s.nat_solute + sa * iw + la + 1, s.nat_solute + sa * jw + ka + 1, T.ww_par[la * sa + ka]))
+                            return fail("export capacity too small");
+            }
+        }
+    } else if (which == QNB_LIST_PW) {
+        for (int g = 0; g < ns; g++) {
+            const uint32_t *rb = rows.data() + off[g] + counts[3 * g] + counts[3 * g + 1];
+            for (int k = 0; k < counts[3 * g + 2]; k++) {
+                const int jw = (int)(rb[k] & kIdMask);
+                for (int m = 0; m < T.g_n[g]; m++) {
+                    const int i = T.g_atoms[T.g_first[g] + m];
+                    if (T.is_q[i]) continue;
+                    for (int site = 0; site < sa; site++)
+                        if (!emit(i + 1, s.nat_solute + sa * jw + site + 1, T.pw_params(i, site))) return fail("export capacity too small");
+                }
+            }
+        }
+    } else if (which == QNB_LIST_PP) {
+        for (int g = 0; g < ns; g++) {
+            const uint32_t *ra = rows.data() + off[g];
+            for (int m = 0; m < T.g_n[g]; m++) {
+                const int i = T.g_atoms[T.g_first[g] + m];
+                if (T.is_q[i]) continue;
+                for (int k = 0; k < counts[3 * g]; k++) {
+                    const int j = (int)(ra[k] & kIdMask);
+                    if (T.grp_of_atom[j] == g && i >= j) continue;   // count once inside a group (L1874)
+                    QPar p;
+                    bool set;
+                    if (!T.pp_params(i, j, p, set) || !set) continue;   // pp_map == 0 or .not. %set (L1876-1877)
+                    if (!emit(i + 1, j + 1, p)) return fail("export capacity too small");
+                }
+            }
+        }
+    } else return fail("unknown list %d", which);
+    *count = n;
+    return 0;
+}
+
+int qnb_list_count(qnb_handle *h, int which, int state, int64_t *n) {
+    if (!h || !n) return fail("null argument");
+    return export_impl(h, which, state, nullptr, nullptr, 0, n);
+}
+
+int qnb_export_list(qnb_handle *h, int which, int state, int32_t *ij, double *params, int64_t capacity) {
+    if (!h || !ij) return fail("null argument");
+    int64_t n;
+    return export_impl(h, which, state, ij, params, capacity, &n);
+}
+
+int qnb_export_lrf(qnb_handle *h, double *lrf) {
+    if (!h || !lrf) return fail("null argument");
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpy(lrf, h->lrf.p, sizeof(double) * QNB_LRF_STRIDE * h->T.s.ncgp, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int qnb_comm_unique_id(void *id128) {
+    if (!g_nccl.load()) return fail("libnccl.so.2 not found: %s", dlerror());
+    ncclUniqueIdT id;
+    int rc = g_nccl.GetUniqueId(&id);
+    if (rc) return fail("ncclGetUniqueId failed (%d)", rc);
+    memcpy(id128, &id, 128);
+    return 0;
+}
+
+int qnb_comm_init(qnb_handle *h, int rank, int nranks, const void *id128) {
+    if (!h || !id128) return fail("null argument");
+    if (!g_nccl.load()) return fail("libnccl.so.2 not found: %s", dlerror());
+    CU(cudaSetDevice(h->device));
+    ncclUniqueIdT id;
+    memcpy(&id, id128, 128);
+    int rc = g_nccl.CommInitRank(&h->comm, nranks, id, rank);
+    if (rc) return fail("ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
+    h->rank = rank; h->nranks = nranks;
+    return 0;
+}
+
+static int flush_l2(qnb_handle *h) {
+    const size_t bytes = 256u << 20;   // > 126 MB L2
+    if (h->flush.ensure(bytes)) return 1;
+    CU(cudaMemsetAsync(h->flush.p, 1, bytes, h->st));
+    return 0;
+}
+
+int qnb_bench_nonbond(qnb_handle *h, const double *lambda, int flags, int steps, int do_flush, float *ms_out) {
+    if (!h || !lambda || !ms_out) return fail("null argument");
+    if (!h->lists_built) return fail("pair lists have not been built");
+    CU(cudaSetDevice(h->device));
+    for (int k = 0; k < h->T.s.nstates; k++) h->hlam[k] = lambda[k];
+    CU(cudaMemcpyAsync(h->lambda.p, h->hlam, h->T.s.nstates * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    float total = 0.f;
+    if (do_flush) {
+        for (int k = 0; k < steps; k++) {
+            if (flush_l2(h)) return 1;
+            CU(cudaEventRecord(h->ev0, h->st));
+            if (step_device(h, flags)) return 1;
+            CU(cudaEventRecord(h->ev1, h->st));
+            CU(cudaEventSynchronize(h->ev1));
+            float ms;
+            CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+            total += ms;
+        }
+    } else {
+        CU(cudaStreamSynchronize(h->st));
+        CU(cudaEventRecord(h->ev0, h->st));
+        for (int k = 0; k < steps; k++)
+            if (step_device(h, flags)) return 1;
+        CU(cudaEventRecord(h->ev1, h->st));
+        CU(cudaEventSynchronize(h->ev1));
+        CU(cudaEventElapsedTime(&total, h->ev0, h->ev1));
+    }
+    CU(cudaGetLastError());
+    *ms_out = total;
+    return 0;
+}
+
+int qnb_bench_build_lists(qnb_handle *h, int reps, float *ms_out) {
+    if (!h || !ms_out) return fail("null argument");
+    if (!h->lists_built) return fail("pair lists have not been built");
+    CU(cudaSetDevice(h->device));
+    float total = 0.f;
+    for (int k = 0; k < reps; k++) {
+        h->qp_done = h->qw_done = false;
+        CU(cudaEventRecord(h->ev0, h->st));
+        if (build_device(h, h->hx)) return 1;
+        CU(cudaEventRecord(h->ev1, h->st));
+        CU(cudaEventSynchronize(h->ev1));
+        float ms;
+        CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        total += ms;
+    }
+    *ms_out = total;
+    return 0;
+}
+
+int qnb_bench_kernels(qnb_handle *h, const double *lambda, int flags, int reps, int do_flush, char *names_out,
+                      int names_cap, float *ms_out, int ms_cap) {
+    if (!h || !lambda || !names_out || !ms_out) { fail("null argument"); return -1; }
+    if (!h->lists_built) { fail("pair lists have not been built"); return -1; }
+    if (cudaSetDevice(h->device) != cudaSuccess) { fail("cudaSetDevice"); return -1; }
+    for (int k = 0; k < h->T.s.nstates; k++) h->hlam[k] = lambda[k];
+    cudaMemcpyAsync(h->lambda.p, h->hlam, h->T.s.nstates * sizeof(double), cudaMemcpyHostToDevice, h->st);
+    std::string names;
+    int n = 0;
+    for (int k = 0; k < K_COUNT; k++) {
+        if (!step_kernel_active(h, k, flags)) continue;
+        if (n >= ms_cap) break;
+        float total = 0.f;
+        for (int r = 0; r < reps + 1; r++) {   // first repetition is warm-up
+            cudaMemsetAsync(h->out.p, 0, h->nout * sizeof(double), h->st);
+            if (do_flush && flush_l2(h)) return -1;
+            cudaEventRecord(h->ev0, h->st);
+            launch_step_kernel(h, k);
+            cudaEventRecord(h->ev1, h->st);
+            cudaEventSynchronize(h->ev1);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+            if (r > 0) total += ms;
+        }
+        ms_out[n++] = total / reps;
+        if (!names.empty()) names += "\n";
+        names += kStepKernelNames[k];
+    }
+    if (cudaGetLastError() != cudaSuccess) { fail("kernel launch failed"); return -1; }
+    snprintf(names_out, names_cap, "%s", names.c_str());
+    return n;
+}
+
+int64_t qnb_launch_count(qnb_handle *h) { return h ? h->launches : 0; }
+
+int qnb_last_copy_bytes(qnb_handle *h, int64_t *h2d, int64_t *d2h) {
+    if (!h) return fail("null handle");
+    if (h2d) *h2d = h->last_h2d;
+    if (d2h) *d2h = h->last_d2h;
+    return 0;
+}
+
+int qnb_finalize(qnb_handle *h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    if (h->st) cudaStreamSynchronize(h->st);
+    h->crg.release(); h->crgf.release(); h->ljf.release(); h->ctype.release(); h->grp_of_atom.release();
+    h->g_first.release(); h->g_n.release(); h->g_switch.release(); h->g_atoms.release(); h->g_nq.release();
+    h->u_sw.release(); h->u_grp.release(); h->sp_off.release(); h->sp_partner.release(); h->gs_off.release();
+    h->gs_atoms.release(); h->iqseq.release(); h->is_q.release(); h->excl.release(); h->qbonded.release();
+    h->u_excl.release(); h->ljcode.release(); h->sp_code.release(); h->qp_tab.release(); h->qw_tab.release();
+    h->qstatic.release(); h->x.release(); h->out.release(); h->lambda.release(); h->lrf.release(); h->upos.release();
+    h->cell_of.release(); h->cell_count.release(); h->cell_start.release(); h->cell_items.release(); h->counts.release();
+    h->row_tot.release(); h->row_off.release(); h->flag.release(); h->pos.release(); h->qp_list.release();
+    h->qw_list.release(); h->qp_shift_atom.release(); h->rows.release(); h->flush.release();
+    if (h->hx) cudaFreeHost(h->hx);
+    if (h->hout) cudaFreeHost(h->hout);
+    if (h->hlam) cudaFreeHost(h->hlam);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->st) cudaStreamDestroy(h->st);
+    delete h;
+    return 0;
+}
+
+}  // extern "C"

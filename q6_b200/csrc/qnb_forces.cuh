@@ -1,0 +1,584 @@
+// qnb_forces.cuh -- nonbonded force/energy kernels over the unit rows.
+//
+// Replaces nonbond_pp/_box, nonbond_pw/_box, nonbond_ww/_box, nonbond_ww_spc/_box (nbe, nbe_b, nbe_spc,
+// nbe_spcb), nonbond_qp/_box, nonbond_qw/_box, nonbond_qw_spc/_box (nbe_qx, nbe_qspc), nonbond_qq,
+// nonbond_qqp (nbe_qq) and lrf_taylor (nonbondene.f90:507-571, 4694-6077; nonbonded.f90:45-291).
+//
+// "d" is the reference's gradient array (globals.f90:347): d(i) -= vec*dv, d(j) += vec*dv with
+// vec = x(j)-x(i) [+ periodic shift] and dv = (1/r) dV/dr.  Every kernel below accumulates the gradient of
+// the atoms of ITS OWN unit only (full rows), so from atom a with partner b it always adds -vec(a->b)*dv.
+#pragma once
+#include "qnb_kernels.cuh"
+
+namespace qnb {
+
+// FP32 LJ parameters of a pair from per-type tables (precompute_set_values_*: simprep.f90:3326-3342)
+template <bool GEOM>
+__device__ __forceinline__ void lj_pair(const float *__restrict__ ljf, int cta, int ctb, int code, float &A, float &B) {
+    const float2 pa = *reinterpret_cast<const float2 *>(ljf + (cta * 3 + code - 1) * 2);
+    const float2 pb = *reinterpret_cast<const float2 *>(ljf + (ctb * 3 + code - 1) * 2);
+    if (GEOM) {
+        A = pa.x * pb.x;
+        B = pa.y * pb.y;
+    } else {
+        float t = pa.x + pb.x;
+        t = t * t;
+        t = t * t * t;
+        const float e = pa.y * pb.y;
+        A = t * t * e;
+        B = 2.0f * t * e;
+    }
+}
+
+// One FP32 pair (nbe, nonbonded.f90:45-75): returns dv; accumulates LJ energy when asked.
+template <bool LJ, bool ENERGY>
+__device__ __forceinline__ float pair_f32(float dx, float dy, float dz, float qq, float A, float B, float &rinv_out,
+                                          float &evdw) {
+    const float r2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+    const float rinv = rsqrtf(r2);
+    const float rinv2 = rinv * rinv;
+    rinv_out = rinv;
+    const float vel = qq * rinv;
+    float t = -vel;
+    if (LJ) {
+        const float r6 = rinv2 * rinv2 * rinv2;
+        const float va = A * r6 * r6, vb = B * r6;
+        t = fmaf(6.0f, vb, fmaf(-12.0f, va, t));
+        if (ENERGY) evdw += va - vb;
+    }
+    return rinv2 * t;
+}
+
+// FP64 Coulomb energy of one pair: elec / r with r from FP64 coordinates
+__device__ __forceinline__ double coulomb_f64(double dx, double dy, double dz, double qq, float rinv_seed) {
+    const double r2 = fma(dx, dx, fma(dy, dy, dz * dz));
+    return qq * rsqrt_refine(r2, rinv_seed);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Water rows: ww (3x3 site tile) + the water side of pw.  One warp per water molecule.
+template <bool PBC, bool SPC, bool GEOM>
+__global__ void __launch_bounds__(128)
+k_water_force(Dev D, const double *__restrict__ x, const int *__restrict__ row_off, const int *__restrict__ counts,
+              const uint32_t *__restrict__ rows, double *__restrict__ grad, double *__restrict__ E) {
+    const int lane = threadIdx.x & 31;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= D.nwat) return;
+    const int u = D.ncgp_solute + w;
+    const int nown = counts[3 * u], nmir = counts[3 * u + 1], nb = counts[3 * u + 2];
+    if (nown + nmir + nb == 0) return;
+    const uint32_t *row = rows + row_off[u];
+    const int i0 = D.nat_solute + 3 * w;
+    const double ox = x[3 * i0], oy = x[3 * i0 + 1], oz = x[3 * i0 + 2];
+    double sd[3][3];   // site offsets from the row origin (own oxygen)
+    float sf[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        sd[a][0] = x[3 * (i0 + a)] - ox; sd[a][1] = x[3 * (i0 + a) + 1] - oy; sd[a][2] = x[3 * (i0 + a) + 2] - oz;
+        sf[a][0] = (float)sd[a][0]; sf[a][1] = (float)sd[a][1]; sf[a][2] = (float)sd[a][2];
+    }
+    float g[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) g[a][0] = g[a][1] = g[a][2] = 0.f;
+    float evdw = 0.f;
+    double eel = 0.0;
+
+    // ---- water-water: A_own (with energies) then A_mir (forces only)
+    for (int k = lane; k < nown + nmir; k += 32) {
+        const bool own = k < nown;
+        const int jw = (int)(row[k] & kIdMask);
+        const int j0 = D.nat_solute + 3 * jw;
+        double ud[3][3];
+        {
+            double shx = 0, shy = 0, shz = 0;
+            const double jx = x[3 * j0], jy = x[3 * j0 + 1], jz = x[3 * j0 + 2];
+            if (PBC) {
+                // one shift per molecule pair from the O-O vector (nonbond_ww_spc_box L6016-6017)
+                shx = pshift(ox - jx, D.box[0], D.inv_box[0]);
+                shy = pshift(oy - jy, D.box[1], D.inv_box[1]);
+                shz = pshift(oz - jz, D.box[2], D.inv_box[2]);
+            }
+#pragma unroll
+            for (int b = 0; b < 3; b++) {
+                ud[b][0] = (x[3 * (j0 + b)] - ox) + shx;
+                ud[b][1] = (x[3 * (j0 + b) + 1] - oy) + shy;
+                ud[b][2] = (x[3 * (j0 + b) + 2] - oz) + shz;
+            }
+        }
+        float uf[3][3];
+#pragma unroll
+        for (int b = 0; b < 3; b++) { uf[b][0] = (float)ud[b][0]; uf[b][1] = (float)ud[b][1]; uf[b][2] = (float)ud[b][2]; }
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+#pragma unroll
+            for (int b = 0; b < 3; b++) {
+                const float dx = uf[b][0] - sf[a][0], dy = uf[b][1] - sf[a][1], dz = uf[b][2] - sf[a][2];
+                float rinv, ev = 0.f, dv;
+                const bool lj = !SPC || (a == 0 && b == 0);   // nonbond_ww_spc: only the first pair carries LJ
+                if (lj) dv = pair_f32<true, true>(dx, dy, dz, D.wwQ[a * 3 + b], D.wwA[a * 3 + b], D.wwB[a * 3 + b], rinv, ev);
+                else dv = pair_f32<false, false>(dx, dy, dz, D.wwQ[a * 3 + b], 0.f, 0.f, rinv, ev);
+                g[a][0] = fmaf(-dx, dv, g[a][0]); g[a][1] = fmaf(-dy, dv, g[a][1]); g[a][2] = fmaf(-dz, dv, g[a][2]);
+                if (own) {
+                    evdw += ev;
+                    eel += coulomb_f64(ud[b][0] - sd[a][0], ud[b][1] - sd[a][1], ud[b][2] - sd[a][2], D.wwQd[a * 3 + b], rinv);
+                }
+            }
+        }
+    }
+    // ---- solute atoms acting on this water (pw, water side: gradient only)
+    const uint32_t *rowb = row + nown + nmir;
+    for (int k = lane; k < nb; k += 32) {
+        const int b = (int)(rowb[k] & kIdMask);
+        double ux = x[3 * b] - ox, uy = x[3 * b + 1] - oy, uz = x[3 * b + 2] - oz;
+        if (PBC) {
+            // nonbond_pw_box: shift = boxlength*nint((x(solute switch)-x(water O))*inv_boxl), vec = x(j)-x(i)+shift
+            // for i = solute atom, j = water atom; seen from the water: vec(a->b) = x(b)-x(a)-shift
+            const int sw = D.g_switch[D.grp_of_atom[b]];
+            ux -= pshift(x[3 * sw] - ox, D.box[0], D.inv_box[0]);
+            uy -= pshift(x[3 * sw + 1] - oy, D.box[1], D.inv_box[1]);
+            uz -= pshift(x[3 * sw + 2] - oz, D.box[2], D.inv_box[2]);
+        }
+        const float ufx = (float)ux, ufy = (float)uy, ufz = (float)uz;
+        const float qb = D.crgf[b];
+        const int ctb = D.ctype[b];
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            const int code = D.ljcode[ctb * D.nct + D.wct[a]];
+            float A, B, rinv, ev = 0.f;
+            lj_pair<GEOM>(D.ljf, D.wct[a], ctb, code, A, B);
+            const float dx = ufx - sf[a][0], dy = ufy - sf[a][1], dz = ufz - sf[a][2];
+            const float dv = pair_f32<true, false>(dx, dy, dz, D.wq[a] * qb, A, B, rinv, ev);
+            g[a][0] = fmaf(-dx, dv, g[a][0]); g[a][1] = fmaf(-dy, dv, g[a][1]); g[a][2] = fmaf(-dz, dv, g[a][2]);
+        }
+    }
+    // ---- FP64 cross-lane reduction, one writer per atom
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const double s = warp_sum((double)g[a][c]);
+            if (lane == 0) grad[3 * (i0 + a) + c] += s;
+        }
+    const double sv = warp_sum((double)evdw), se = warp_sum(eel);
+    if (lane == 0 && (nown > 0)) {
+        atomicAdd(&E[QNB_E_WW_VDW], sv);
+        atomicAdd(&E[QNB_E_WW_EL], se);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Solute rows: pp + the solute (owner) side of pw.  One warp per charge group, i-atoms in register
+// tiles of four.
+constexpr int kITile = 4;
+
+__device__ __forceinline__ int special_code(const Dev &D, int a, int b) {
+    // -1: ordinary pair; kPairExcluded(0): skip; 3: 1-4 pair
+    int lo = D.sp_off[a], hi = D.sp_off[a + 1];
+    while (lo < hi) {
+        const int m = (lo + hi) >> 1;
+        if (D.sp_partner[m] < b) lo = m + 1; else hi = m;
+    }
+    if (lo < D.sp_off[a + 1] && D.sp_partner[lo] == b) return (int)D.sp_code[lo];
+    return -1;
+}
+
+template <bool PBC, bool GEOM>
+__global__ void __launch_bounds__(128)
+k_solute_force(Dev D, const double *__restrict__ x, const int *__restrict__ row_off, const int *__restrict__ counts,
+               const uint32_t *__restrict__ rows, double *__restrict__ grad, double *__restrict__ E) {
+    const int lane = threadIdx.x & 31;
+    const int gidx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (gidx >= D.ncgp_solute) return;
+    const int nown = counts[3 * gidx], nmir = counts[3 * gidx + 1], nb = counts[3 * gidx + 2];
+    if (nown + nmir + nb == 0) return;
+    const uint32_t *row = rows + row_off[gidx];
+    const int gf = D.g_first[gidx], gn = D.g_n[gidx];
+    const int sw = D.g_switch[gidx];
+    const double ox = x[3 * sw], oy = x[3 * sw + 1], oz = x[3 * sw + 2];   // row origin = switch atom
+    double e_pp_el = 0.0, e_pw_el = 0.0;
+    float e_pp_vdw = 0.f, e_pw_vdw = 0.f;
+
+    int kscan = 0;   // position in the group's atom list
+    while (kscan < gn) {
+        // next tile of up to four non-Q atoms
+        int ai[kITile], cti[kITile];
+        float sf[kITile][3], qf[kITile];
+        double sd[kITile][3], qd[kITile];
+        int nt = 0;
+#pragma unroll
+        for (int t = 0; t < kITile; t++) { ai[t] = -1; cti[t] = 0; qf[t] = 0.f; qd[t] = 0.0;
+            sf[t][0] = sf[t][1] = sf[t][2] = 0.f; sd[t][0] = sd[t][1] = sd[t][2] = 0.0; }
+#pragma unroll
+        for (int t = 0; t < kITile; t++) {
+            while (kscan < gn && D.is_q[D.g_atoms[gf + kscan]]) kscan++;
+            if (kscan < gn) {
+                const int a = D.g_atoms[gf + kscan++];
+                ai[t] = a; cti[t] = D.ctype[a]; qd[t] = D.crg[a]; qf[t] = (float)qd[t];
+                sd[t][0] = x[3 * a] - ox; sd[t][1] = x[3 * a + 1] - oy; sd[t][2] = x[3 * a + 2] - oz;
+                sf[t][0] = (float)sd[t][0]; sf[t][1] = (float)sd[t][1]; sf[t][2] = (float)sd[t][2];
+                nt = t + 1;
+            }
+        }
+        if (nt == 0) break;
+        float g[kITile][3];
+#pragma unroll
+        for (int t = 0; t < kITile; t++) g[t][0] = g[t][1] = g[t][2] = 0.f;
+
+        // ---- solute-solute partner atoms
+        for (int k = lane; k < nown + nmir; k += 32) {
+            const uint32_t e = row[k];
+            const bool own = k < nown;
+            const int b = (int)(e & kIdMask);
+            const bool special = (e & kSpecialBit) != 0;
+            const int gb = D.grp_of_atom[b];
+            double ux = x[3 * b] - ox, uy = x[3 * b + 1] - oy, uz = x[3 * b + 2] - oz;
+            if (PBC) {
+                // nonbond_pp_box L4791-4801: shift = boxlength*nint((x(sw_i)-x(sw_j))*inv_boxl)
+                const int swb = D.g_switch[gb];
+                ux += pshift(ox - x[3 * swb], D.box[0], D.inv_box[0]);
+                uy += pshift(oy - x[3 * swb + 1], D.box[1], D.inv_box[1]);
+                uz += pshift(oz - x[3 * swb + 2], D.box[2], D.inv_box[2]);
+            }
+            const float ufx = (float)ux, ufy = (float)uy, ufz = (float)uz;
+            const float qb = D.crgf[b];
+            const double qbd = D.crg[b];
+            const int ctb = D.ctype[b];
+            const bool same = gb == gidx;
+#pragma unroll
+            for (int t = 0; t < kITile; t++) {
+                if (t < nt) {
+                    const int a = ai[t];
+                    int code = D.ljcode[cti[t] * D.nct + ctb];
+                    bool skip = false, i14 = false;
+                    if (special) {
+                        if (a == b) skip = true;
+                        else {
+                            const int sc = special_code(D, a, b);
+                            if (sc == 0) skip = true;
+                            else if (sc == 3) { code = 3; i14 = true; }
+                        }
+                    }
+                    if (!skip) {
+                        float A, B, rinv, ev = 0.f;
+                        lj_pair<GEOM>(D.ljf, cti[t], ctb, code, A, B);
+                        const float qq = i14 ? qf[t] * qb * D.el14f : qf[t] * qb;
+                        const float dx = ufx - sf[t][0], dy = ufy - sf[t][1], dz = ufz - sf[t][2];
+                        const float dv = pair_f32<true, true>(dx, dy, dz, qq, A, B, rinv, ev);
+                        g[t][0] = fmaf(-dx, dv, g[t][0]); g[t][1] = fmaf(-dy, dv, g[t][1]); g[t][2] = fmaf(-dz, dv, g[t][2]);
+                        // energy once per pair: on the owner side; inside one group on the lower atom (i<j, L1874)
+                        if (own && (!same || a < b)) {
+                            e_pp_vdw += ev;
+                            const double qqd = i14 ? qd[t] * qbd * D.el14 : qd[t] * qbd;
+                            e_pp_el += coulomb_f64(ux - sd[t][0], uy - sd[t][1], uz - sd[t][2], qqd, rinv);
+                        }
+                    }
+                }
+            }
+        }
+        // ---- solute-water: this side owns the pair, all three water atoms with full LJ (nbe)
+        const uint32_t *rowb = row + nown + nmir;
+        for (int k = lane; k < nb; k += 32) {
+            const int jw = (int)(rowb[k] & kIdMask);
+            const int j0 = D.nat_solute + 3 * jw;
+            double shx = 0, shy = 0, shz = 0;
+            if (PBC) {
+                shx = pshift(ox - x[3 * j0], D.box[0], D.inv_box[0]);
+                shy = pshift(oy - x[3 * j0 + 1], D.box[1], D.inv_box[1]);
+                shz = pshift(oz - x[3 * j0 + 2], D.box[2], D.inv_box[2]);
+            }
+#pragma unroll
+            for (int s = 0; s < 3; s++) {
+                const double ux = (x[3 * (j0 + s)] - ox) + shx, uy = (x[3 * (j0 + s) + 1] - oy) + shy,
+                             uz = (x[3 * (j0 + s) + 2] - oz) + shz;
+                const float ufx = (float)ux, ufy = (float)uy, ufz = (float)uz;
+                const int ctb = D.wct[s];
+#pragma unroll
+                for (int t = 0; t < kITile; t++) {
+                    if (t < nt) {
+                        const int code = D.ljcode[cti[t] * D.nct + ctb];
+                        float A, B, rinv, ev = 0.f;
+                        lj_pair<GEOM>(D.ljf, cti[t], ctb, code, A, B);
+                        const float dx = ufx - sf[t][0], dy = ufy - sf[t][1], dz = ufz - sf[t][2];
+                        const float dv = pair_f32<true, true>(dx, dy, dz, qf[t] * D.wq[s], A, B, rinv, ev);
+                        g[t][0] = fmaf(-dx, dv, g[t][0]); g[t][1] = fmaf(-dy, dv, g[t][1]); g[t][2] = fmaf(-dz, dv, g[t][2]);
+                        e_pw_vdw += ev;
+                        e_pw_el += coulomb_f64(ux - sd[t][0], uy - sd[t][1], uz - sd[t][2], qd[t] * D.wqd[s], rinv);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < kITile; t++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const double s = warp_sum((double)g[t][c]);
+                if (lane == 0 && t < nt) grad[3 * ai[t] + c] += s;
+            }
+    }
+    const double s1 = warp_sum(e_pp_el), s2 = warp_sum((double)e_pp_vdw), s3 = warp_sum(e_pw_el),
+                 s4 = warp_sum((double)e_pw_vdw);
+    if (lane == 0) {
+        if (nown > 0) { atomicAdd(&E[QNB_E_PP_EL], s1); atomicAdd(&E[QNB_E_PP_VDW], s2); }
+        if (nb > 0) { atomicAdd(&E[QNB_E_PW_EL], s3); atomicAdd(&E[QNB_E_PW_VDW], s4); }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Q-atom kernels, FP64.  nbe_qx (nonbonded.f90:200-222) for one state.
+struct QxOut { double vel, vvdw, dv; };
+__device__ __forceinline__ QxOut qx_eval(double r2inv, double rinv, const QPar4 &p, double lambda) {
+    QxOut o;
+    const double r6 = r2inv * r2inv * r2inv;          // dist%r6 = 1/r^6
+    const double r6_hc = 1.0 / r6;                    // r^6
+    const double r6s = 1.0 / (r6_hc + p.score);       // softcore
+    const double r12 = r6s * r6s;
+    o.vel = p.el * rinv;
+    const double va = p.A * r12, vb = p.B * r6s;
+    o.vvdw = va - vb;
+    o.dv = r2inv * (-o.vel - (12.0 * va - 6.0 * vb) * r6s * r6_hc) * lambda;
+    return o;
+}
+
+// Gradient on the PARTNER atoms of the Q-atoms (nonbond_qp/_box, nonbond_qw(_spc)/_box seen from atom j).
+// One thread per listed solute atom, then one thread per listed water molecule.
+template <bool PBC>
+__global__ void __launch_bounds__(128)
+k_q_partner(Dev D, const double *__restrict__ x, const double *__restrict__ lambda, int nqp,
+            const int *__restrict__ qp_list, const int *__restrict__ qp_shift_atom, int nqw,
+            const int *__restrict__ qw_list, double *__restrict__ grad) {
+    extern __shared__ double sh[];
+    double *xq = sh;                 // [nqat][3]
+    double *lam = sh + 3 * D.nqat;   // [nstates]
+    for (int k = threadIdx.x; k < D.nqat; k += blockDim.x) {
+        const int a = D.iqseq[k];
+        xq[3 * k] = x[3 * a]; xq[3 * k + 1] = x[3 * a + 1]; xq[3 * k + 2] = x[3 * a + 2];
+    }
+    for (int k = threadIdx.x; k < D.nstates; k += blockDim.x) lam[k] = lambda[k];
+    __syncthreads();
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nst = D.nstates;
+    if (p < nqp) {
+        const int j = qp_list[p];
+        const double jx = x[3 * j], jy = x[3 * j + 1], jz = x[3 * j + 2];
+        double shx = 0, shy = 0, shz = 0;
+        if (PBC) {
+            // nonbond_qp_box L5275-5278: nbqp_cgp%shift = boxlength*nint((x(ia)-x(qswitch))*inv_boxl) with ia the
+            // group's first atom inside Rcq; vec = shift - (x(i)-x(j)).  No registered pair (Rq<0) -> zero shift.
+            const int ref = qp_shift_atom[D.grp_of_atom[j]];
+            if (ref >= 0) {
+                const int qs = D.qswitch0;
+                shx = pshift(x[3 * ref] - x[3 * qs], D.box[0], D.inv_box[0]);
+                shy = pshift(x[3 * ref + 1] - x[3 * qs + 1], D.box[1], D.inv_box[1]);
+                shz = pshift(x[3 * ref + 2] - x[3 * qs + 2], D.box[2], D.inv_box[2]);
+            }
+        }
+        double gx = 0, gy = 0, gz = 0;
+        for (int q = 0; q < D.nqat; q++) {
+            const double vx = shx - (xq[3 * q] - jx), vy = shy - (xq[3 * q + 1] - jy), vz = shz - (xq[3 * q + 2] - jz);
+            const double r2inv = 1.0 / (vx * vx + vy * vy + vz * vz), rinv = sqrt(r2inv);
+            double dv = 0;
+            for (int s = 0; s < nst; s++) {
+                const QPar4 pr = D.qp_tab[(size_t)(q * nst + s) * D.nat_solute + j];
+                dv += qx_eval(r2inv, rinv, pr, lam[s]).dv;
+            }
+            gx += vx * dv; gy += vy * dv; gz += vz * dv;   // d(j) += vec*dv
+        }
+        grad[3 * j] += gx; grad[3 * j + 1] += gy; grad[3 * j + 2] += gz;
+    } else if (p < nqp + nqw) {
+        const int w = qw_list[p - nqp];
+        const int j0 = D.nat_solute + 3 * w;
+        double xs[3][3];
+#pragma unroll
+        for (int s = 0; s < 3; s++) { xs[s][0] = x[3 * (j0 + s)]; xs[s][1] = x[3 * (j0 + s) + 1]; xs[s][2] = x[3 * (j0 + s) + 2]; }
+        double sh3[3][3];
+#pragma unroll
+        for (int s = 0; s < 3; s++) sh3[s][0] = sh3[s][1] = sh3[s][2] = 0.0;
+        if (PBC) {
+            const int qs = D.qswitch0;
+#pragma unroll
+            for (int s = 0; s < 3; s++) {
+                // spc: one shift from x(qswitch)-x(O) (L5818-5820); general: per atom j (L5470-5472)
+                const int r = D.spc_water ? 0 : s;
+                sh3[s][0] = pshift(x[3 * qs] - xs[r][0], D.box[0], D.inv_box[0]);
+                sh3[s][1] = pshift(x[3 * qs + 1] - xs[r][1], D.box[1], D.inv_box[1]);
+                sh3[s][2] = pshift(x[3 * qs + 2] - xs[r][2], D.box[2], D.inv_box[2]);
+            }
+        }
+        double g[3][3];
+#pragma unroll
+        for (int s = 0; s < 3; s++) g[s][0] = g[s][1] = g[s][2] = 0.0;
+        for (int q = 0; q < D.nqat; q++) {
+#pragma unroll
+            for (int s = 0; s < 3; s++) {
+                const double vx = sh3[s][0] - (xq[3 * q] - xs[s][0]), vy = sh3[s][1] - (xq[3 * q + 1] - xs[s][1]),
+                             vz = sh3[s][2] - (xq[3 * q + 2] - xs[s][2]);
+                const double r2inv = 1.0 / (vx * vx + vy * vy + vz * vz), rinv = sqrt(r2inv);
+                double dv = 0;
+                for (int st = 0; st < nst; st++) {
+                    const QPar4 pr = D.qw_tab[(size_t)(q * nst + st) * 3 + s];
+                    if (D.spc_water && s > 0) dv += -r2inv * (pr.el * rinv) * lam[st];   // nbe_qspc
+                    else dv += qx_eval(r2inv, rinv, pr, lam[st]).dv;
+                }
+                g[s][0] += vx * dv; g[s][1] += vy * dv; g[s][2] += vz * dv;
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < 3; s++) { grad[3 * (j0 + s)] += g[s][0]; grad[3 * (j0 + s) + 1] += g[s][1]; grad[3 * (j0 + s) + 2] += g[s][2]; }
+    }
+}
+
+// Gradient on the Q-atoms and the per-state energies EQ(:)%qp, EQ(:)%qw.  One block per Q-atom.
+template <bool PBC>
+__global__ void __launch_bounds__(128)
+k_q_atom(Dev D, const double *__restrict__ x, const double *__restrict__ lambda, int nqp,
+         const int *__restrict__ qp_list, const int *__restrict__ qp_shift_atom, int nqw,
+         const int *__restrict__ qw_list, double *__restrict__ grad, double *__restrict__ EQ) {
+    __shared__ double red[4][3 + 4 * kMaxStatesDev];
+    const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int nst = D.nstates;
+    const int iat = D.iqseq[q];
+    const double qx = x[3 * iat], qy = x[3 * iat + 1], qz = x[3 * iat + 2];
+    double lam[kMaxStatesDev], eel[kMaxStatesDev], evdw[kMaxStatesDev], wel[kMaxStatesDev], wvdw[kMaxStatesDev];
+#pragma unroll
+    for (int s = 0; s < kMaxStatesDev; s++) { lam[s] = s < nst ? lambda[s] : 0.0; eel[s] = evdw[s] = wel[s] = wvdw[s] = 0.0; }
+    double gx = 0, gy = 0, gz = 0;
+    for (int p = tid; p < nqp; p += blockDim.x) {
+        const int j = qp_list[p];
+        double vx = x[3 * j] - qx, vy = x[3 * j + 1] - qy, vz = x[3 * j + 2] - qz;
+        if (PBC) {
+            const int ref = qp_shift_atom[D.grp_of_atom[j]];
+            if (ref >= 0) {
+                const int qs = D.qswitch0;
+                vx += pshift(x[3 * ref] - x[3 * qs], D.box[0], D.inv_box[0]);
+                vy += pshift(x[3 * ref + 1] - x[3 * qs + 1], D.box[1], D.inv_box[1]);
+                vz += pshift(x[3 * ref + 2] - x[3 * qs + 2], D.box[2], D.inv_box[2]);
+            }
+        }
+        const double r2inv = 1.0 / (vx * vx + vy * vy + vz * vz), rinv = sqrt(r2inv);
+        double dv = 0;
+#pragma unroll
+        for (int s = 0; s < kMaxStatesDev; s++)
+            if (s < nst) {
+                const QxOut o = qx_eval(r2inv, rinv, D.qp_tab[(size_t)(q * nst + s) * D.nat_solute + j], lam[s]);
+                eel[s] += o.vel; evdw[s] += o.vvdw; dv += o.dv;
+            }
+        gx -= vx * dv; gy -= vy * dv; gz -= vz * dv;   // d(i) -= vec*dv
+    }
+    for (int p = tid; p < nqw; p += blockDim.x) {
+        const int j0 = D.nat_solute + 3 * qw_list[p];
+        double shx = 0, shy = 0, shz = 0;
+#pragma unroll
+        for (int site = 0; site < 3; site++) {
+            const double jx = x[3 * (j0 + site)], jy = x[3 * (j0 + site) + 1], jz = x[3 * (j0 + site) + 2];
+            if (PBC && (site == 0 || !D.spc_water)) {
+                const int qs = D.qswitch0;
+                shx = pshift(x[3 * qs] - jx, D.box[0], D.inv_box[0]);
+                shy = pshift(x[3 * qs + 1] - jy, D.box[1], D.inv_box[1]);
+                shz = pshift(x[3 * qs + 2] - jz, D.box[2], D.inv_box[2]);
+            }
+            const double vx = shx - (qx - jx), vy = shy - (qy - jy), vz = shz - (qz - jz);
+            const double r2inv = 1.0 / (vx * vx + vy * vy + vz * vz), rinv = sqrt(r2inv);
+            double dv = 0;
+#pragma unroll
+            for (int s = 0; s < kMaxStatesDev; s++)
+                if (s < nst) {
+                    const QPar4 pr = D.qw_tab[(size_t)(q * nst + s) * 3 + site];
+                    if (D.spc_water && site > 0) {
+                        const double vel = pr.el * rinv;   // nbe_qspc
+                        wel[s] += vel; dv += -r2inv * vel * lam[s];
+                    } else {
+                        const QxOut o = qx_eval(r2inv, rinv, pr, lam[s]);
+                        wel[s] += o.vel; wvdw[s] += o.vvdw; dv += o.dv;
+                    }
+                }
+            gx -= vx * dv; gy -= vy * dv; gz -= vz * dv;
+        }
+    }
+    // block reduction
+    gx = warp_sum(gx); gy = warp_sum(gy); gz = warp_sum(gz);
+#pragma unroll
+    for (int s = 0; s < kMaxStatesDev; s++)
+        if (s < nst) { eel[s] = warp_sum(eel[s]); evdw[s] = warp_sum(evdw[s]); wel[s] = warp_sum(wel[s]); wvdw[s] = warp_sum(wvdw[s]); }
+    if (lane == 0) {
+        red[wid][0] = gx; red[wid][1] = gy; red[wid][2] = gz;
+#pragma unroll
+        for (int s = 0; s < kMaxStatesDev; s++)
+            if (s < nst) { red[wid][3 + 4 * s] = eel[s]; red[wid][4 + 4 * s] = evdw[s]; red[wid][5 + 4 * s] = wel[s]; red[wid][6 + 4 * s] = wvdw[s]; }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const int nw = blockDim.x >> 5;
+        double a[3] = {0, 0, 0};
+        for (int k = 0; k < nw; k++) { a[0] += red[k][0]; a[1] += red[k][1]; a[2] += red[k][2]; }
+        grad[3 * iat] += a[0]; grad[3 * iat + 1] += a[1]; grad[3 * iat + 2] += a[2];
+        for (int s = 0; s < nst; s++) {
+            double e[4] = {0, 0, 0, 0};
+            for (int k = 0; k < nw; k++) for (int c = 0; c < 4; c++) e[c] += red[k][3 + 4 * s + c];
+            atomicAdd(&EQ[QNB_EQ_STRIDE * s + 2], e[0]); atomicAdd(&EQ[QNB_EQ_STRIDE * s + 3], e[1]);
+            atomicAdd(&EQ[QNB_EQ_STRIDE * s + 4], e[2]); atomicAdd(&EQ[QNB_EQ_STRIDE * s + 5], e[3]);
+        }
+    }
+}
+
+// Static lists nbqq / nbqqp (nonbond_qq L5013, nonbond_qqp L5085): one thread per (pair,state) entry.
+struct QStatic { int i, j, state, soft; QPar4 p; };
+__global__ void k_qq_static(int n, int nqq, const QStatic *__restrict__ lst, const double *__restrict__ x,
+                            const double *__restrict__ lambda, double *__restrict__ grad, double *__restrict__ EQ) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const QStatic e = lst[k];
+    const double vx = x[3 * e.j] - x[3 * e.i], vy = x[3 * e.j + 1] - x[3 * e.i + 1], vz = x[3 * e.j + 2] - x[3 * e.i + 2];
+    const double r2inv = 1.0 / (vx * vx + vy * vy + vz * vz), rinv = sqrt(r2inv);
+    const double lam = lambda[e.state];
+    double vel, vvdw, dv;
+    if (e.soft) {
+        // nbe_qq soft pair: V_a = A*exp(-B*r), code "-nb%vdWB/r" with r holding 1/r (nonbonded.f90:140-143)
+        vel = e.p.el * rinv;
+        const double va = e.p.A * exp(-e.p.B / rinv);
+        vvdw = va;
+        dv = r2inv * (-vel - e.p.B * va / rinv) * lam;
+    } else {
+        const QxOut o = qx_eval(r2inv, rinv, e.p, lam);
+        vel = o.vel; vvdw = o.vvdw; dv = o.dv;
+    }
+    atomicAdd(&grad[3 * e.i], -vx * dv); atomicAdd(&grad[3 * e.i + 1], -vy * dv); atomicAdd(&grad[3 * e.i + 2], -vz * dv);
+    atomicAdd(&grad[3 * e.j], vx * dv); atomicAdd(&grad[3 * e.j + 1], vy * dv); atomicAdd(&grad[3 * e.j + 2], vz * dv);
+    const int o = (k < nqq) ? 0 : 2;   // nbqq -> EQ%qq, nbqqp -> EQ%qp (potene.f90:176-177)
+    atomicAdd(&EQ[QNB_EQ_STRIDE * e.state + o], vel);
+    atomicAdd(&EQ[QNB_EQ_STRIDE * e.state + o + 1], vvdw);
+}
+
+// lrf_taylor (nonbondene.f90:507-571)
+__global__ void k_lrf_taylor(Dev D, const double *__restrict__ x, const double *__restrict__ lrf,
+                             double *__restrict__ grad, double *__restrict__ E) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double e = 0.0;
+    if (i < D.natom && i + 1 >= D.at_s && i + 1 <= D.at_e && !D.is_q[i] && (D.use_PBC || !D.excl[i])) {
+        const double *l = lrf + (size_t)QNB_LRF_STRIDE * D.grp_of_atom[i];
+        const double dx = l[0] - x[3 * i], dy = l[1] - x[3 * i + 1], dz = l[2] - x[3 * i + 2];
+        const double *p1 = l + 4, *p2 = l + 7, *p3 = l + 16;
+        // potential
+        const double t0 = dx * p2[0] + dy * p2[1] + dz * p2[2];
+        const double t1 = dx * p2[3] + dy * p2[4] + dz * p2[5];
+        const double t2 = dx * p2[6] + dy * p2[7] + dz * p2[8];
+        const double V = l[3] + (dx * p1[0] + dy * p1[1] + dz * p1[2]) + 0.5 * (dx * t0 + dy * t1 + dz * t2);
+        const double q = D.crg[i];
+        e = 0.5 * q * V;
+        // field
+        double df[3];
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            const double *r = p3 + 9 * a;
+            const double u0 = dx * r[0] + dy * r[1] + dz * r[2];
+            const double u1 = dx * r[3] + dy * r[4] + dz * r[5];
+            const double u2 = dx * r[6] + dy * r[7] + dz * r[8];
+            const double d2 = (a == 0) ? t0 : (a == 1) ? t1 : t2;
+            df[a] = p1[a] + d2 + 0.5 * (dx * u0 + dy * u1 + dz * u2);
+        }
+        grad[3 * i] -= df[0] * q; grad[3 * i + 1] -= df[1] * q; grad[3 * i + 2] -= df[2] * q;
+    }
+    e = warp_sum(e);
+    if ((threadIdx.x & 31) == 0 && e != 0.0) atomicAdd(&E[QNB_E_LRF], e);
+}
+
+}  // namespace qnb

@@ -1,0 +1,157 @@
+// qnb_kernels.cuh -- sm_100a kernels of the Qdyn6 nonbonded path.
+//
+// Design (DESIGN.md has the long form):
+//  * "units" = solute charge groups [0,ncgp_solute) followed by water molecules.  Pair lists
+//    are held at unit level as FULL (symmetric) neighbour rows: every unit owns a row with
+//    all partners it has a listed pair with, so each force kernel accumulates forces only
+//    on the atoms of its own unit -- no scatter atomics, deterministic.  The reference's
+//    half list (checkerboard rule, nonbondene.f90:1855) survives as the "owner" bit of an
+//    entry: the side that the reference would hold the pair on computes its energy, and
+//    qnb_export_list() expands exactly those entries.
+//  * cut-off tests are FP64 on switch atoms, literally the reference's expression, so lists
+//    are exact.  Pair forces are FP32 on coordinates taken relative to the row's own origin
+//    (FP64 subtraction first), LJ energies FP32 with FP64 accumulation, Coulomb ENERGIES in
+//    FP64 (rsqrt seed + one Halley step) because neutral-group sums cancel to ~1e-7 of their
+//    terms and the parity bar is 1e-6 on the net value.
+//  * Q-atom kernels (per-state, softcore, lambda-weighted) and LRF are FP64 throughout.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace qnb {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kMaxStatesDev = 8;
+constexpr uint32_t kOwnerBit = 0x80000000u;    // this row's unit is the reference's "i" side of the pair
+constexpr uint32_t kSpecialBit = 0x40000000u;  // solute partner atom with an excluded/1-4/self relation
+constexpr uint32_t kIdMask = 0x3fffffffu;
+
+struct QPar4 { double A, B, el, score; };
+
+struct Grid {
+    double org[3];
+    double inv_cell[3];
+    double inv_box[3];   // periodic: 1/L
+    int n[3];
+    int ncell;
+    int periodic;
+};
+
+// Static device tables + per-build state.  Passed by value to kernels.
+struct Dev {
+    int natom, nat_solute, nwat, ncgp, ncgp_solute, nunit, nqat, nstates, nct;
+    int use_PBC, use_LRF, geometric, spc_water, qswitch0;
+    double el14;
+    float el14f;
+    double box[3], inv_box[3];
+    double xpcent[3];
+    // shard (1-based inclusive, as calculation_assignment)
+    int pp_s, pp_e, pw_s, pw_e, qp_s, qp_e, ww_s, ww_e, qw_s, qw_e, at_s, at_e;
+    // atoms
+    const double *crg;          // [natom]
+    const float *crgf;          // [natom]
+    const int *ctype;           // [natom]
+    const uint8_t *is_q, *excl, *qbonded;
+    const int *grp_of_atom;
+    // groups
+    const int *g_first, *g_n, *g_switch, *g_atoms, *g_nq;   // g_nq: non-Q atoms per group
+    // units
+    const int *u_sw, *u_grp;
+    const uint8_t *u_excl;
+    // LJ tables
+    const float *ljf;           // [nct][3][2] (a,b) by code
+    const uint8_t *ljcode;      // [nct][nct]
+    // specials
+    const int *sp_off, *sp_partner;
+    const uint8_t *sp_code;
+    const int *gs_off, *gs_atoms;
+    // water sites
+    float wq[3];                // site charges
+    double wqd[3];
+    int wct[3];
+    float wwA[9], wwB[9], wwQ[9];
+    double wwQd[9];
+    // solute non-Q atom compaction (rows of the solute kernel are per group)
+    // Q
+    const int *iqseq;           // [nqat]
+    const QPar4 *qp_tab;        // [(iq*nstates+s)][nat_solute]
+    const QPar4 *qw_tab;        // [(iq*nstates+s)][3]
+};
+
+struct Cut {
+    double rc2[3];      // pp, pw, ww
+    double rclrf2;
+    int lrf_all[3];     // "no LRF cut-off" sentinel per class (box builders)
+    double rcq2;
+    double Rq;
+};
+
+// ------------------------------------------------------------------ small device helpers
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(kFull, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+// boxlength*q_nint(shift*inv_boxl): round() = half away from zero = Fortran nint
+__device__ __forceinline__ double pshift(double v, double L, double invL) {
+    return __dmul_rn(L, round(__dmul_rn(v, invL)));
+}
+// qvec_square without contraction: (x*x + y*y) + z*z
+__device__ __forceinline__ double sq3(double x, double y, double z) {
+    return __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z));
+}
+
+// 1/sqrt(r2) in FP64 from an FP32 seed: one Halley step, relative error ~ seed_err^3
+__device__ __forceinline__ double rsqrt_refine(double r2, float seed) {
+    double y = (double)seed;
+    double e = fma(-r2 * y, y, 1.0);
+    double t = fma(0.375, e, 0.5) * e;
+    return fma(y, t, y);
+}
+
+// class of a unit pair and the reference's owner side.  Units: [0,ns) solute groups, then waters.
+// returns class 0 pp, 1 pw, 2 ww; owner_is_u: the reference lists the pair while looping i = u.
+__device__ __forceinline__ int pair_class(int u, int v, int ns, bool &owner_is_u) {
+    const bool us = u < ns, vs = v < ns;
+    if (us != vs) { owner_is_u = us; return 1; }            // pw: the solute group is always "i" (L2864)
+    const int a = us ? u + 1 : u - ns + 1, b = us ? v + 1 : v - ns + 1;   // 1-based group / water numbers
+    if (a == b) owner_is_u = true;
+    else {
+        // kept while looping ig=a iff not ((a>b and even sum) or (a<b and odd sum)) (L1855-1857)
+        const bool even = ((a + b) & 1) == 0;
+        owner_is_u = (a > b) ? !even : even;
+    }
+    return us ? 0 : 2;
+}
+__device__ __forceinline__ bool in_shard(const Dev &D, int cls, int owner_unit) {
+    if (cls == 2) { int w = owner_unit - D.ncgp_solute + 1; return w >= D.ww_s && w <= D.ww_e; }
+    int g = owner_unit + 1;
+    return cls == 0 ? (g >= D.pp_s && g <= D.pp_e) : (g >= D.pw_s && g <= D.pw_e);
+}
+// squared switch-atom distance exactly as the builders compute it
+__device__ __forceinline__ double unit_r2(const Dev &D, const double *pu, const double *pv) {
+    // Explicitly rounded operations: no FMA contraction, so r2 is bit-identical to the reference's
+    // a%x**2 + a%y**2 + a%z**2 (math.f90:206) and borderline pairs fall on the same side.
+    double dx, dy, dz;
+    if (!D.use_PBC) {
+        // q_dist4(x(is),x(ja)) = |x(ja)-x(is)|^2 (math.f90:254)
+        dx = __dsub_rn(pv[0], pu[0]); dy = __dsub_rn(pv[1], pu[1]); dz = __dsub_rn(pv[2], pu[2]);
+    } else {
+        // shift = x(is)-x(ja); r2 = q_dist4(shift, boxlength*q_nint(shift*inv_boxl)) (L1991-1992)
+        double sx = __dsub_rn(pu[0], pv[0]), sy = __dsub_rn(pu[1], pv[1]), sz = __dsub_rn(pu[2], pv[2]);
+        dx = __dsub_rn(pshift(sx, D.box[0], D.inv_box[0]), sx);
+        dy = __dsub_rn(pshift(sy, D.box[1], D.inv_box[1]), sy);
+        dz = __dsub_rn(pshift(sz, D.box[2], D.inv_box[2]), sz);
+    }
+    return sq3(dx, dy, dz);
+}
+
+}  // namespace qnb

@@ -1,0 +1,439 @@
+// qnb_lists.cuh -- pair-list generation: cell binning of switch atoms, warp-ballot/scan
+// compaction into per-unit neighbour rows, Q-atom partner lists, LRF multipole accumulation.
+//
+// Replaces nbpplist/nbpwlist/nbwwlist(_box)(_lrf), nbqplist(_box), nbqwlist(_box), cgp_centers and
+// lrf_update (nonbondene.f90:43-78, 628-725, 1520-2055, 2622-3085, 3647-4025, 4079-4515).  The
+// reference tests all ncgp^2 switch-atom pairs; here switch atoms are binned into cells of edge
+// >= the largest cut-off and only the 27 surrounding cells are tested -- with the reference's own
+// FP64 expression, so the resulting set of pairs is identical.
+#pragma once
+#include "qnb_kernels.cuh"
+
+namespace qnb {
+
+// ---------------------------------------------------------------- cells
+__device__ __forceinline__ int cell_coord(const Grid &G, double x, int d) {
+    int c;
+    if (G.periodic) {
+        double f = x * G.inv_box[d];
+        f -= floor(f);
+        c = (int)(f * (double)G.n[d]);
+    } else {
+        c = (int)floor((x - G.org[d]) * G.inv_cell[d]);
+    }
+    return min(max(c, 0), G.n[d] - 1);   // clamping is monotone: neighbours stay within +-1 cell
+}
+
+// upos[u] = x(switch atom of u); cell_of[u]; histogram
+__global__ void k_bin_units(Dev D, Grid G, const double *__restrict__ x, double *__restrict__ upos,
+                            int *__restrict__ cell_of, int *__restrict__ cell_count) {
+    int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= D.nunit) return;
+    int a = D.u_sw[u];
+    double px = x[3 * a], py = x[3 * a + 1], pz = x[3 * a + 2];
+    upos[3 * u] = px; upos[3 * u + 1] = py; upos[3 * u + 2] = pz;
+    int c = (cell_coord(G, pz, 2) * G.n[1] + cell_coord(G, py, 1)) * G.n[0] + cell_coord(G, px, 0);
+    cell_of[u] = c;
+    atomicAdd(&cell_count[c], 1);
+}
+
+// single-block exclusive scan: out[i] = sum_{k<i} in[k], out[n] = total
+__global__ void k_exclusive_scan(const int *__restrict__ in, int *__restrict__ out, int n) {
+    __shared__ int warp_off[32];
+    __shared__ int block_total;
+    __shared__ int carry;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int i = base + tid;
+        const int v = i < n ? in[i] : 0;
+        const int inc = warp_incl_scan(v, lane);
+        if (lane == 31) warp_off[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            const int t = lane < nw ? warp_off[lane] : 0;
+            const int ti = warp_incl_scan(t, lane);
+            warp_off[lane] = ti - t;
+            if (lane == 31) block_total = ti;
+        }
+        __syncthreads();
+        if (i < n) out[i] = carry + warp_off[wid] + inc - v;
+        __syncthreads();
+        if (tid == 0) carry += block_total;
+        __syncthreads();
+    }
+    if (tid == 0) out[n] = carry;
+}
+
+__global__ void k_cell_fill(int nunit, const int *__restrict__ cell_of, const int *__restrict__ cell_start,
+                            int *__restrict__ cell_cursor, int *__restrict__ cell_items) {
+    int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= nunit) return;
+    int c = cell_of[u];
+    int p = atomicAdd(&cell_cursor[c], 1);
+    cell_items[cell_start[c] + p] = u;
+}
+
+// order items inside each cell by unit number so that rows come out in a run-independent order
+__global__ void k_cell_sort(int ncell, const int *__restrict__ cell_start, int *__restrict__ cell_items) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncell) return;
+    int lo = cell_start[c], hi = cell_start[c + 1];
+    for (int i = lo + 1; i < hi; i++) {
+        int v = cell_items[i], j = i - 1;
+        while (j >= lo && cell_items[j] > v) { cell_items[j + 1] = cell_items[j]; j--; }
+        cell_items[j + 1] = v;
+    }
+}
+
+// range of cells along one dimension around c with reach m
+struct DimRange { int start, count; };
+__device__ __forceinline__ DimRange dim_range(int c, int m, int n, int periodic) {
+    DimRange r;
+    if (!periodic) {
+        r.start = max(0, c - m);
+        r.count = min(n - 1, c + m) - r.start + 1;
+    } else if (2 * m + 1 >= n) {
+        r.start = 0; r.count = n;
+    } else {
+        r.start = c - m; r.count = 2 * m + 1;   // wrapped by the caller
+    }
+    return r;
+}
+// up to two contiguous x-segments [lo,hi) of cells
+struct XSeg { int lo[2], hi[2], n; };
+__device__ __forceinline__ XSeg x_segments(int c, int m, int n, int periodic) {
+    XSeg s;
+    s.n = 1; s.lo[1] = s.hi[1] = 0;
+    if (!periodic) { s.lo[0] = max(0, c - m); s.hi[0] = min(n - 1, c + m) + 1; }
+    else if (2 * m + 1 >= n) { s.lo[0] = 0; s.hi[0] = n; }
+    else {
+        int a = c - m, b = c + m;
+        if (a < 0) { s.lo[0] = a + n; s.hi[0] = n; s.lo[1] = 0; s.hi[1] = b + 1; s.n = 2; }
+        else if (b >= n) { s.lo[0] = a; s.hi[0] = n; s.lo[1] = 0; s.hi[1] = b - n + 1; s.n = 2; }
+        else { s.lo[0] = a; s.hi[0] = b + 1; }
+    }
+    return s;
+}
+
+// ---------------------------------------------------------------- neighbour rows
+//
+// Row of unit u: [ A_own | A_mir | B ]
+//   water  u: A = partner waters (ww),                      B = partner solute ATOMS (pw, forces only)
+//   solute u: A = partner solute ATOMS (pp, non-Q, flagged), B = partner waters (pw, owner side)
+// A_own holds the pairs the reference lists while looping i = u (owner side), A_mir the rest.
+// counts[3*u + {0,1,2}] = |A_own|, |A_mir|, |B|.
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+k_build_rows(Dev D, Cut C, Grid G, const double *__restrict__ upos, const int *__restrict__ cell_of,
+             const int *__restrict__ cell_start, const int *__restrict__ cell_items, int *__restrict__ counts,
+             const int *__restrict__ row_off, uint32_t *__restrict__ rows) {
+    const int lane = threadIdx.x & 31;
+    const int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (u >= D.nunit) return;
+    const int ns = D.ncgp_solute;
+    const bool u_sol = u < ns;
+    int n_own = 0, n_mir = 0, n_b = 0;      // warp-uniform cursors
+    int base_own = 0, base_mir = 0, base_b = 0;
+    if (FILL) {
+        base_own = row_off[u];
+        base_mir = base_own + counts[3 * u];
+        base_b = base_mir + counts[3 * u + 1];
+    }
+    if (!D.u_excl[u]) {
+        const double pu[3] = {upos[3 * u], upos[3 * u + 1], upos[3 * u + 2]};
+        const int cu = cell_of[u];
+        const int cx = cu % G.n[0], cy = (cu / G.n[0]) % G.n[1], cz = cu / (G.n[0] * G.n[1]);
+        const DimRange rz = dim_range(cz, 1, G.n[2], G.periodic), ry = dim_range(cy, 1, G.n[1], G.periodic);
+        const XSeg xs = x_segments(cx, 1, G.n[0], G.periodic);
+        const int gs_lo = u_sol ? D.gs_off[u] : 0, gs_hi = u_sol ? D.gs_off[u + 1] : 0;
+        for (int iz = 0; iz < rz.count; iz++) {
+            int z = rz.start + iz; z = (z % G.n[2] + G.n[2]) % G.n[2];
+            for (int iy = 0; iy < ry.count; iy++) {
+                int y = ry.start + iy; y = (y % G.n[1] + G.n[1]) % G.n[1];
+                const int rowbase = (z * G.n[1] + y) * G.n[0];
+                for (int sgi = 0; sgi < xs.n; sgi++) {
+                    const int lo = cell_start[rowbase + xs.lo[sgi]], hi = cell_start[rowbase + xs.hi[sgi]];
+                    for (int base = lo; base < hi; base += 32) {
+                        const int idx = base + lane;
+                        int v = idx < hi ? cell_items[idx] : -1;
+                        bool pass = false, owner_is_u = false;
+                        int cls = 0;
+                        if (v >= 0 && !D.u_excl[v]) {
+                            cls = pair_class(u, v, ns, owner_is_u);
+                            if (!(cls == 2 && u == v) && in_shard(D, cls, owner_is_u ? u : v)) {
+                                const double pv[3] = {upos[3 * v], upos[3 * v + 1], upos[3 * v + 2]};
+                                // owner orientation (is = owner's switch atom); the value is the same either way
+                                double r2 = owner_is_u ? unit_r2(D, pu, pv) : unit_r2(D, pv, pu);
+                                pass = r2 <= C.rc2[cls];
+                            }
+                        }
+                        // entries emitted by this lane, by segment
+                        const bool v_sol = v >= 0 && v < ns;
+                        int c_own = 0, c_mir = 0, c_b = 0;
+                        if (pass) {
+                            if (u_sol) {
+                                if (v_sol) { if (owner_is_u) c_own = D.g_nq[v]; else c_mir = D.g_nq[v]; }
+                                else c_b = 1;
+                            } else {
+                                if (v_sol) c_b = D.g_nq[v];
+                                else { if (owner_is_u) c_own = 1; else c_mir = 1; }
+                            }
+                        }
+                        const int s_own = warp_incl_scan(c_own, lane), s_mir = warp_incl_scan(c_mir, lane),
+                                  s_b = warp_incl_scan(c_b, lane);
+                        if (FILL && pass) {
+                            int p_own = base_own + n_own + s_own - c_own;
+                            int p_mir = base_mir + n_mir + s_mir - c_mir;
+                            int p_b = base_b + n_b + s_b - c_b;
+                            if (v_sol) {
+                                // flatten the group's non-Q atoms
+                                const int gf = D.g_first[v], gn = D.g_n[v];
+                                uint32_t flag = (u_sol && owner_is_u) ? kOwnerBit : 0u;
+                                int p = u_sol ? (owner_is_u ? p_own : p_mir) : p_b;
+                                for (int k = 0; k < gn; k++) {
+                                    int b = D.g_atoms[gf + k];
+                                    if (D.is_q[b]) continue;
+                                    uint32_t e = (uint32_t)b | flag;
+                                    if (u_sol) {
+                                        // special if b relates to any atom of group u (excluded / 1-4 / same group)
+                                        int l = gs_lo, h = gs_hi;
+                                        while (l < h) { int m = (l + h) >> 1; if (D.gs_atoms[m] < b) l = m + 1; else h = m; }
+                                        if (l < gs_hi && D.gs_atoms[l] == b) e |= kSpecialBit;
+                                    }
+                                    rows[p++] = e;
+                                }
+                            } else {
+                                const uint32_t w = (uint32_t)(v - ns);
+                                if (u_sol) rows[p_b] = w | kOwnerBit;
+                                else if (owner_is_u) rows[p_own] = w | kOwnerBit;
+                                else rows[p_mir] = w;
+                            }
+                        }
+                        n_own += __shfl_sync(kFull, s_own, 31);
+                        n_mir += __shfl_sync(kFull, s_mir, 31);
+                        n_b += __shfl_sync(kFull, s_b, 31);
+                    }
+                }
+            }
+        }
+    }
+    if (!FILL && lane == 0) {
+        counts[3 * u] = n_own; counts[3 * u + 1] = n_mir; counts[3 * u + 2] = n_b;
+    }
+}
+
+__global__ void k_row_totals(int nunit, const int *__restrict__ counts, int *__restrict__ tot) {
+    int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u < nunit) tot[u] = counts[3 * u] + counts[3 * u + 1] + counts[3 * u + 2];
+}
+
+// ---------------------------------------------------------------- Q-atom partner lists
+// nbqplist / nbqplist_box (L3647-3859): flag solute atoms that pair with every Q-atom; for the box the
+// group's reference atom for the periodic shift (first atom found inside Rcq) is kept per group.
+__global__ void k_qp_flags(Dev D, Cut C, const double *__restrict__ x, int *__restrict__ flag,
+                           int *__restrict__ qp_shift_atom) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= D.ncgp_solute) return;
+    const int gf = D.g_first[g], gn = D.g_n[g];
+    bool inside = false;
+    int ref = -1;
+    if (g + 1 >= D.qp_s && g + 1 <= D.qp_e) {
+        if (!D.use_PBC) {
+            int ia = D.g_switch[g];
+            if (!D.excl[ia]) {
+                // r2 = q_dist4(x(ia),xpcent); skip if r2 > rcut2 (L3707-3710)
+                double r2 = sq3(__dsub_rn(D.xpcent[0], x[3 * ia]), __dsub_rn(D.xpcent[1], x[3 * ia + 1]),
+                                __dsub_rn(D.xpcent[2], x[3 * ia + 2]));
+                inside = !(r2 > C.rcq2);
+            }
+        } else if (C.Rq < 0.0) {
+            inside = true;   // no cut-off: every group, no registered reference atom (zero shift)
+        } else {
+            const int qs = D.qswitch0;
+            for (int k = 0; k < gn && !inside; k++) {
+                int i = D.g_atoms[gf + k];
+                double sx = __dsub_rn(x[3 * i], x[3 * qs]), sy = __dsub_rn(x[3 * i + 1], x[3 * qs + 1]),
+                       sz = __dsub_rn(x[3 * i + 2], x[3 * qs + 2]);
+                double r2 = sq3(__dsub_rn(pshift(sx, D.box[0], D.inv_box[0]), sx),
+                                __dsub_rn(pshift(sy, D.box[1], D.inv_box[1]), sy),
+                                __dsub_rn(pshift(sz, D.box[2], D.inv_box[2]), sz));
+                if (r2 <= C.rcq2) { inside = true; ref = i; }
+            }
+        }
+    }
+    qp_shift_atom[g] = ref;
+    for (int k = 0; k < gn; k++) {
+        int i = D.g_atoms[gf + k];
+        // "check if already on qq list": any(qconn(:,i,:) <= 3) also covers the Q-atoms themselves
+        flag[i] = (inside && i < D.nat_solute && !D.qbonded[i]) ? 1 : 0;
+    }
+}
+// nbqwlist / nbqwlist_box (L3862-4025)
+__global__ void k_qw_flags(Dev D, Cut C, const double *__restrict__ x, int *__restrict__ flag) {
+    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= D.nwat) return;
+    int ia = D.nat_solute + 3 * w;
+    bool inside = false;
+    if (w + 1 >= D.qw_s && w + 1 <= D.qw_e) {
+        if (!D.use_PBC) {
+            if (!D.excl[ia]) {
+                double r2 = sq3(__dsub_rn(D.xpcent[0], x[3 * ia]), __dsub_rn(D.xpcent[1], x[3 * ia + 1]),
+                                __dsub_rn(D.xpcent[2], x[3 * ia + 2]));
+                inside = r2 <= C.rcq2;
+            }
+        } else if (C.Rq > 0.0) {
+            const int qs = D.qswitch0;
+            double sx = __dsub_rn(x[3 * ia], x[3 * qs]), sy = __dsub_rn(x[3 * ia + 1], x[3 * qs + 1]),
+                   sz = __dsub_rn(x[3 * ia + 2], x[3 * qs + 2]);
+            double r2 = sq3(__dsub_rn(pshift(sx, D.box[0], D.inv_box[0]), sx),
+                            __dsub_rn(pshift(sy, D.box[1], D.inv_box[1]), sy),
+                            __dsub_rn(pshift(sz, D.box[2], D.inv_box[2]), sz));
+            inside = (r2 <= C.rcq2);
+        } else {
+            // Rq <= 0: r2 = one; listed if (r2 <= rcut2) .or. (Rq < zero) (L3996-4003)
+            inside = (1.0 <= C.rcq2) || (C.Rq < 0.0);
+        }
+    }
+    flag[w] = inside ? 1 : 0;
+}
+__global__ void k_compact(int n, const int *__restrict__ flag, const int *__restrict__ pos, int *__restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flag[i]) out[pos[i]] = i;
+}
+
+// ---------------------------------------------------------------- LRF
+// lrf layout per group: 43 doubles = cgp_cent(3) phi0 phi1(3) phi2(3x3) phi3(9x3)  (LRF_TYPE, globals.f90:503)
+
+// cgp_centers (nonbondene.f90:43-78)
+__global__ void k_cgp_centers(Dev D, const double *__restrict__ x, double *__restrict__ lrf) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= D.ncgp) return;
+    double cx = 0, cy = 0, cz = 0;
+    const int gf = D.g_first[g], gn = D.g_n[g];
+    for (int k = 0; k < gn; k++) {
+        int a = D.g_atoms[gf + k];
+        cx = __dadd_rn(cx, x[3 * a]); cy = __dadd_rn(cy, x[3 * a + 1]); cz = __dadd_rn(cz, x[3 * a + 2]);
+    }
+    double *l = lrf + (size_t)QNB_LRF_STRIDE * g;
+    const double n = (double)gn;
+    l[0] = cx / n; l[1] = cy / n; l[2] = cz / n;
+    for (int k = 3; k < QNB_LRF_STRIDE; k++) l[k] = 0.0;
+}
+
+// centres only (after the multi-GPU sum of the moments, lrf_add keeps cgp_cent: nonbondene.f90:582)
+__global__ void k_cgp_centers_only(Dev D, const double *__restrict__ x, double *__restrict__ lrf) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= D.ncgp) return;
+    double cx = 0, cy = 0, cz = 0;
+    const int gf = D.g_first[g], gn = D.g_n[g];
+    for (int k = 0; k < gn; k++) {
+        int a = D.g_atoms[gf + k];
+        cx = __dadd_rn(cx, x[3 * a]); cy = __dadd_rn(cy, x[3 * a + 1]); cz = __dadd_rn(cz, x[3 * a + 2]);
+    }
+    double *l = lrf + (size_t)QNB_LRF_STRIDE * g;
+    const double n = (double)gn;
+    l[0] = cx / n; l[1] = cy / n; l[2] = cz / n;
+}
+
+// lrf_update (nonbondene.f90:628-725), gathered per TARGET group: the warp of target unit t sums the
+// contribution of every source atom whose unit pair (t,s) the reference sends through the LRF branch
+// (outside the class cut-off, inside RcLRF, pair owned by this shard).  20 unique moments are
+// accumulated (phi2 and phi3 are symmetric) and expanded on write.
+__global__ void __launch_bounds__(256)
+k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x, const double *__restrict__ upos,
+                 const int *__restrict__ cell_of, const int *__restrict__ cell_start,
+                 const int *__restrict__ cell_items, double *__restrict__ lrf) {
+    const int lane = threadIdx.x & 31;
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (t >= D.nunit) return;
+    if (D.u_excl[t]) return;
+    const int ns = D.ncgp_solute;
+    const int gt = D.u_grp[t];
+    double *lt = lrf + (size_t)QNB_LRF_STRIDE * gt;
+    const double cx_ = lt[0], cy_ = lt[1], cz_ = lt[2];
+    const double pt[3] = {upos[3 * t], upos[3 * t + 1], upos[3 * t + 2]};
+    double m[20];
+#pragma unroll
+    for (int k = 0; k < 20; k++) m[k] = 0.0;
+    const int cu = cell_of[t];
+    const int cx = cu % G.n[0], cy = (cu / G.n[0]) % G.n[1], cz = cu / (G.n[0] * G.n[1]);
+    const DimRange rz = dim_range(cz, reach.z, G.n[2], G.periodic), ry = dim_range(cy, reach.y, G.n[1], G.periodic);
+    const XSeg xs = x_segments(cx, reach.x, G.n[0], G.periodic);
+    for (int iz = 0; iz < rz.count; iz++) {
+        int z = rz.start + iz; z = (z % G.n[2] + G.n[2]) % G.n[2];
+        for (int iy = 0; iy < ry.count; iy++) {
+            int y = ry.start + iy; y = (y % G.n[1] + G.n[1]) % G.n[1];
+            const int rowbase = (z * G.n[1] + y) * G.n[0];
+            for (int sgi = 0; sgi < xs.n; sgi++) {
+                const int lo = cell_start[rowbase + xs.lo[sgi]], hi = cell_start[rowbase + xs.hi[sgi]];
+                for (int idx = lo + lane; idx < hi; idx += 32) {
+                    const int s = cell_items[idx];
+                    if (s == t || D.u_excl[s]) continue;
+                    bool owner_is_t;
+                    const int cls = pair_class(t, s, ns, owner_is_t);
+                    if (!in_shard(D, cls, owner_is_t ? t : s)) continue;
+                    const double ps[3] = {upos[3 * s], upos[3 * s + 1], upos[3 * s + 2]};
+                    const double r2u = owner_is_t ? unit_r2(D, pt, ps) : unit_r2(D, ps, pt);
+                    if (r2u <= C.rc2[cls]) continue;                       // listed pair, not LRF
+                    if (!(r2u <= C.rclrf2 || C.lrf_all[cls])) continue;    // beyond the LRF cut-off
+                    // lrf_update(group1 = source, group2 = target)
+                    const int gsrc = D.u_grp[s];
+                    double shx = 0, shy = 0, shz = 0;
+                    if (D.use_PBC) {
+                        const int isw = D.g_switch[gsrc];
+                        shx = pshift(x[3 * isw] - cx_, D.box[0], D.inv_box[0]);
+                        shy = pshift(x[3 * isw + 1] - cy_, D.box[1], D.inv_box[1]);
+                        shz = pshift(x[3 * isw + 2] - cz_, D.box[2], D.inv_box[2]);
+                    }
+                    const int gf = D.g_first[gsrc], gn = D.g_n[gsrc];
+                    for (int k = 0; k < gn; k++) {
+                        const int i = D.g_atoms[gf + k];
+                        if (D.is_q[i]) continue;
+                        const double dx = x[3 * i] - cx_ - shx, dy = x[3 * i + 1] - cy_ - shy, dz = x[3 * i + 2] - cz_ - shz;
+                        const double r2 = dx * dx + dy * dy + dz * dz;
+                        const double f0 = D.crg[i] / (r2 * sqrt(r2));
+                        const double f1 = 3.0 * f0 / r2;
+                        const double f2 = -f1 / r2;
+                        m[0] += f0 * r2;
+                        m[1] -= dx * f0; m[2] -= dy * f0; m[3] -= dz * f0;
+                        // phi2: xx xy xz yy yz zz
+                        m[4] += f1 * dx * dx - f0; m[5] += f1 * dx * dy; m[6] += f1 * dx * dz;
+                        m[7] += f1 * dy * dy - f0; m[8] += f1 * dy * dz; m[9] += f1 * dz * dz - f0;
+                        // phi3: xxx xxy xxz xyy xyz xzz yyy yyz yzz zzz
+                        const double g5 = 5.0 * f2, gr = f2 * r2;
+                        m[10] += g5 * dx * dx * dx - 3.0 * gr * dx;
+                        m[11] += g5 * dx * dx * dy - gr * dy;
+                        m[12] += g5 * dx * dx * dz - gr * dz;
+                        m[13] += g5 * dx * dy * dy - gr * dx;
+                        m[14] += g5 * dx * dy * dz;
+                        m[15] += g5 * dx * dz * dz - gr * dx;
+                        m[16] += g5 * dy * dy * dy - 3.0 * gr * dy;
+                        m[17] += g5 * dy * dy * dz - gr * dz;
+                        m[18] += g5 * dy * dz * dz - gr * dy;
+                        m[19] += g5 * dz * dz * dz - 3.0 * gr * dz;
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 20; k++) m[k] = warp_sum(m[k]);
+    if (lane == 0) {
+        lt[3] = m[0];
+        lt[4] = m[1]; lt[5] = m[2]; lt[6] = m[3];
+        // phi2(a)%b
+        lt[7] = m[4]; lt[8] = m[5]; lt[9] = m[6];
+        lt[10] = m[5]; lt[11] = m[7]; lt[12] = m[8];
+        lt[13] = m[6]; lt[14] = m[8]; lt[15] = m[9];
+        // phi3(3*(n-1)+j)%k = T[n][j][k]
+        const int ix[27] = {10, 11, 12, 11, 13, 14, 12, 14, 15,    // n = x: (xx*, xy*, xz*)
+                            11, 13, 14, 13, 16, 17, 14, 17, 18,    // n = y
+                            12, 14, 15, 14, 17, 18, 15, 18, 19};   // n = z
+#pragma unroll
+        for (int k = 0; k < 27; k++) lt[16 + k] = m[ix[k]];
+    }
+}
+
+}  // namespace qnb

@@ -126,6 +126,40 @@ class QSystem:
     # topology coordinates (convenience for tests/bench)
     xtop: np.ndarray = None
 
+    _SCALARS = ("natom", "nat_solute", "nwat", "solv_atom", "ncgp", "ncgp_solute", "nqat", "nstates", "qswitch",
+                "natyps", "num_atyp", "max_nbr_range", "nqlib", "iuse_switch_atom", "use_PBC", "use_LRF", "ivdw_rule",
+                "solvent_type", "qvdw_flag", "qq_use_library_charges", "ntors_gt_solute", "el14_scale", "rexcl_o")
+    _ARRAYS = ("xpcent", "boxlength", "cgp", "cgpatom", "excl", "iqatom", "iqseq", "iac", "crg", "iaclib", "ljcod",
+               "listex", "list14", "listexlong", "list14long", "qcrg", "qiac", "qavdw", "qbvdw", "sc_lookup",
+               "iqexpnb", "jqexpnb", "el_scale_iq", "el_scale_jq", "el_scale", "qconn", "xtop")
+
+    def save(self, path: str) -> None:
+        """Fixture file: every table of the system (compressed npz)."""
+        d = {k: np.asarray(getattr(self, k)) for k in self._SCALARS}
+        for k in self._ARRAYS:
+            v = getattr(self, k)
+            d[k] = np.zeros(0) if v is None else np.asarray(v)
+        # the exclusion bit tables are sparse: store packed
+        d["listex"] = np.packbits(np.asarray(self.listex, np.uint8).reshape(-1))
+        d["list14"] = np.packbits(np.asarray(self.list14, np.uint8).reshape(-1))
+        d["qconn"] = np.asarray(self.qconn, np.int8)
+        np.savez_compressed(path, **d)
+
+    @staticmethod
+    def load(path: str) -> "QSystem":
+        z = np.load(path)
+        q = QSystem()
+        for k in QSystem._SCALARS:
+            v = z[k]
+            setattr(q, k, float(v) if k in ("el14_scale", "rexcl_o") else int(v))
+        for k in QSystem._ARRAYS:
+            setattr(q, k, z[k])
+        n = q.nat_solute * q.max_nbr_range
+        q.listex = np.unpackbits(z["listex"])[:n].astype(np.int32).reshape(q.nat_solute, q.max_nbr_range)
+        q.list14 = np.unpackbits(z["list14"])[:n].astype(np.int32).reshape(q.nat_solute, q.max_nbr_range)
+        q.qconn = z["qconn"].astype(np.int32)
+        return q.full_shard()
+
     def full_shard(self) -> "QSystem":
         """calculation_assignment for numnodes == 1 (nonbondene.f90:126-152)."""
         self.pp = self.pw = self.qp = (1, self.ncgp_solute)

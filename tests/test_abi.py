@@ -1,0 +1,66 @@
+"""The C-ABI library loads and exports every symbol include/qnb.h declares (no compute without a GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "qnb.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(qnb_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_header_symbols_exported():
+    from q6_b200 import engine
+    lib = engine.load_library()
+    names = _declared()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), f"libqnb.so does not export {n}"
+
+
+def test_struct_layout_matches_header():
+    """ctypes image of qnb_system has the header's field order (names parsed from the header)."""
+    from q6_b200.system import qnb_system
+    text = open(os.path.join(ROOT, "include", "qnb.h")).read()
+    start = text.index("typedef struct qnb_system {") + len("typedef struct qnb_system {")
+    body = text[start:text.index("} qnb_system;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        m = re.match(r"(?:const\s+)?(int32_t|double)\s*(.*)$", decl, flags=re.S)
+        if not m:
+            continue
+        for nm in m.group(2).split(","):
+            nm = nm.strip().lstrip("*").strip()
+            nm = re.sub(r"\[.*\]", "", nm)
+            if nm:
+                fields.append(nm)
+    assert fields == [f[0] for f in qnb_system._fields_]
+
+
+def test_no_gpu_fails_loudly():
+    """Without a CUDA device construction raises; there is no CPU fallback."""
+    from q6_b200 import engine, synth
+    lib = engine.load_library()
+    if lib.qnb_device_count() > 0:
+        pytest.skip("a GPU is present")
+    q = synth.solvated_sphere(10.0, 5.0, 4, 1, 3)
+    with pytest.raises(engine.QnbError):
+        engine.Qnb(q)
+
+
+def test_product_does_not_import_oracle():
+    """The shipped package never references oracle/ (only tests, smoke() and bench's CPU legs may)."""
+    pkg = os.path.join(ROOT, "q6_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".cpp")):
+                src = open(os.path.join(dp, f), errors="replace").read()
+                assert "qoracle" not in src and "pyoracle" not in src and "oracle/" not in src, f

@@ -1,0 +1,168 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle -- the first gate.
+
+Bars (BASELINE.json north_star): pair lists equal as sorted sets (bit-exact indices, parameters to
+FP64 round-off), gradient <= 1e-5 relative RMS, every energy term <= 1e-6 relative.
+"""
+import numpy as np
+import pytest
+
+import common
+from common import (ENERGY_REL, FORCE_REL_RMS, LIST_NAMES, assert_energy, golden_system, rel_rms, small_systems,
+                    sorted_pairs, sorted_pairs_with_params)
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_lists(g, o, nstates):
+    for which, nm in enumerate(LIST_NAMES):
+        for st in range(1, nstates + 1 if which >= 3 else 2):
+            gi, gp = g.export_list(which, st)
+            oi, op = o.export_list(which, st)
+            assert len(gi) == len(oi), f"nb{nm} state {st}: {len(gi)} entries, oracle {len(oi)}"
+            gk, gpp = sorted_pairs_with_params(gi, gp)
+            ok, opp = sorted_pairs_with_params(oi, op)
+            assert np.array_equal(gk, ok), f"nb{nm} state {st}: pair sets differ"
+            if len(gk):
+                assert np.allclose(gpp, opp, rtol=1e-13, atol=1e-300), f"nb{nm} state {st}: parameters differ"
+
+
+def _check_step(g, o, q, x, lam, md=True, qq=True):
+    dg, Eg, EQg = g.pot_energy_nonbonds(x, lam, md=md, qq=qq)
+    do, Eo, EQo = o.pot_energy_nonbonds(x, lam, md=md, qq=qq)
+    r = rel_rms(dg, do)
+    assert r <= FORCE_REL_RMS, f"gradient relative RMS {r:.3e}"
+    for k, nm in enumerate(("pp.el", "pp.vdw", "pw.el", "pw.vdw", "ww.el", "ww.vdw", "LRF")):
+        assert_energy(nm, Eg[k], Eo[k])
+    for s in range(q.nstates):
+        for k, nm in enumerate(("qq.el", "qq.vdw", "qp.el", "qp.vdw", "qw.el", "qw.vdw")):
+            assert_energy(f"state {s + 1} {nm}", EQg[s, k], EQo[s, k])
+    return r
+
+
+def _run_case(q, cuts, lam, check_lists=True):
+    from oracle.pyoracle import Oracle
+    from q6_b200.engine import Qnb
+    g, o = Qnb(q), Oracle(q)
+    try:
+        x = q.xtop
+        cg = g.make_pair_lists(x, **cuts)
+        co = o.make_pair_lists(x, **cuts)
+        assert np.array_equal(cg[:5], co[:5]), f"list sizes {cg[:5]} vs oracle {co[:5]}"
+        if check_lists:
+            _check_lists(g, o, q.nstates)
+        if q.use_LRF:
+            lg, lo = g.export_lrf(), o.export_lrf()
+            scale = np.abs(lo).max(axis=0) + 1e-300
+            assert np.all(np.abs(lg - lo) <= 1e-9 * scale + 1e-12), "LRF moments differ"
+        r = _check_step(g, o, q, x, lam)
+        # a second evaluation at moved coordinates with the SAME lists (what happens between list updates)
+        rng = np.random.default_rng(5)
+        x2 = x + rng.normal(0, 0.02, x.shape)
+        _check_step(g, o, q, x2, lam)
+        # Q-only evaluation (pot_energy(...,.false.) as called by QCP)
+        _check_step(g, o, q, x2, lam, md=False)
+        return r
+    finally:
+        g.close()
+        o.close()
+
+
+@pytest.mark.parametrize("case", small_systems(), ids=lambda c: c[0])
+def test_synthetic_small(case):
+    name, q, cuts, lam = case
+    _run_case(q, cuts, np.array(lam))
+
+
+@pytest.mark.parametrize("name", ["c1_sph", "c1_pbc", "c4_evb"])
+def test_reference_fixtures(name):
+    """The reference's own shipped systems (tests/basic_tests, tests/exclude_tests) at topology coordinates,
+    against the live oracle and against the committed oracle results."""
+    from q6_b200.engine import Qnb
+    q, cuts, lam, z = golden_system(name)
+    _run_case(q, cuts, lam)
+    g = Qnb(q)
+    try:
+        c = g.make_pair_lists(q.xtop, **cuts)
+        assert np.array_equal(c[:5], z["counts"][:5])
+        d, E, EQ = g.pot_energy_nonbonds(q.xtop, lam)
+        assert rel_rms(d, z["d"]) <= FORCE_REL_RMS
+        for k in range(7):
+            assert_energy(f"E[{k}]", E[k], z["E"][k])
+        assert_energy("EQ", EQ, z["EQ"])
+    finally:
+        g.close()
+
+
+def test_golden_scalars_c1():
+    """tests/basic_tests step-0 goldens reachable from topology coordinates: 56 402 water pairs,
+    E%ww%vdw = -413.17 (SPH_leap-frog_berendsen_benchmark.en row 1)."""
+    from q6_b200.engine import Qnb
+    q, cuts, lam, z = golden_system("c1_sph")
+    g = Qnb(q)
+    try:
+        c = g.make_pair_lists(q.xtop, **cuts)
+        assert c[2] == 56402 * 9
+        d, E, EQ = g.pot_energy_nonbonds(q.xtop, lam)
+        assert round(E[5], 2) == -413.17
+    finally:
+        g.close()
+
+
+@pytest.mark.parametrize("name", ["C2", "C3", "C4s"])
+def test_baseline_configs(name):
+    """The BASELINE.json configurations at full size (synthetic systems of the named shapes)."""
+    from q6_b200 import synth
+    q, cuts, lam = synth.config(name)
+    _run_case(q, cuts, lam, check_lists=True)
+
+
+def test_list_rebuild_after_motion():
+    """Lists rebuilt at moved coordinates equal the oracle's; once-only Q lists stay (nbqplist L3678)."""
+    from oracle.pyoracle import Oracle
+    from q6_b200 import synth
+    from q6_b200.engine import Qnb
+    q = synth.solvated_sphere(16.0, 9.0, 20, 2, 31, fep="evb")
+    cuts = common.sph_cuts(8.0)
+    g, o = Qnb(q), Oracle(q)
+    rng = np.random.default_rng(1)
+    x = q.xtop.copy()
+    for it in range(3):
+        cg, co = g.make_pair_lists(x, **cuts), o.make_pair_lists(x, **cuts)
+        assert np.array_equal(cg[:5], co[:5])
+        for which in range(5):
+            assert np.array_equal(sorted_pairs(g.export_list(which)[0]), sorted_pairs(o.export_list(which)[0]))
+        _check_step(g, o, q, x, np.array([0.5, 0.5]))
+        x = x + rng.normal(0, 0.15, x.shape)
+    g.close()
+
+
+def test_properties_water_box_full_size():
+    """C5 (98 304 atoms, PBC) through size-independent properties: the gradient sums to zero (Newton's third
+    law over every listed pair), the pair count is symmetric, and a rigid translation by a lattice vector of
+    the box leaves energies unchanged."""
+    from q6_b200 import synth
+    from q6_b200.engine import Qnb
+    q, cuts, lam = synth.config("C5")
+    g = Qnb(q)
+    try:
+        c = g.make_pair_lists(q.xtop, **cuts)
+        assert c[2] % 9 == 0 and c[2] > 0
+        d, E, EQ = g.pot_energy_nonbonds(q.xtop, lam)
+        # ww gradient alone cancels pairwise; LRF (a field expansion) does not, so compare without it
+        scale = np.abs(d).sum() / d.size
+        q2 = synth.water_box(32, 20261018)
+        q2.use_LRF = 0
+        g2 = Qnb(q2)
+        g2.make_pair_lists(q2.xtop, **cuts)
+        d2, E2, _ = g2.pot_energy_nonbonds(q2.xtop, lam)
+        assert np.abs(d2.sum(axis=0)).max() <= 1e-6 * scale * d2.shape[0] ** 0.5
+        assert_energy("ww.el", E2[4], E[4])
+        assert_energy("ww.vdw", E2[5], E[5])
+        xs = q2.xtop + q2.boxlength[None, :] * np.array([1.0, -2.0, 3.0])[None, :]
+        g2.make_pair_lists(xs, **cuts)
+        d3, E3, _ = g2.pot_energy_nonbonds(xs, lam)
+        assert_energy("ww.el shifted", E3[4], E2[4], tol=1e-6)
+        assert_energy("ww.vdw shifted", E3[5], E2[5], tol=1e-6)
+        g2.close()
+    finally:
+        g.close()
