@@ -210,6 +210,12 @@ int qnb_comm_init(qnb_handle *h, int rank, int nranks, const void *id128);
  * ms_out = CUDA-event time of the whole loop on the handle's stream. */
 int qnb_bench_nonbond(qnb_handle *h, const double *lambda, int flags, int steps, int flush_l2, float *ms_out);
 int qnb_bench_build_lists(qnb_handle *h, int reps, float *ms_out);
+/* md_run's loop on device-resident coordinates: a list rebuild every nbcycle steps (md.f90:1661) plus one
+ * nonbonded evaluation per step; ms_out = CUDA-event time of the loop. */
+int qnb_bench_md(qnb_handle *h, const double *lambda, int flags, int steps, int nbcycle, float *ms_out);
+/* Sustained FMA throughput of the FP32 (which=0) / FP64 (which=1) pipe in TFLOP/s: the measured roofline
+ * denominator of the force kernels (MEASURED_PEAKS.json holds only HBM and bf16 tensor figures). */
+int qnb_bench_peak(int device, int which, float *tflops_out);
 /* Per-kernel CUDA-event time (ms, averaged over reps) of the kernels of the last step:
  * names_out: '\n'-separated list; returns number of kernels. */
 int qnb_bench_kernels(qnb_handle *h, const double *lambda, int flags, int reps, int flush_l2,

@@ -99,7 +99,7 @@ struct qnb_handle {
     cudaStream_t st = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // static device tables
-    DBuf<double> crg;
+    DBuf<double> crg, ljd;
     DBuf<float> crgf, ljf;
     DBuf<int> ctype, grp_of_atom, g_first, g_n, g_switch, g_atoms, g_nq, u_sw, u_grp, sp_off, sp_partner, gs_off,
         gs_atoms, iqseq;
@@ -165,10 +165,13 @@ static int init_device(qnb_handle *h) {
     std::vector<float> ljf((size_t)T.nct * 6);
     for (int t = 0; t < T.nct; t++)
         for (int c = 0; c < 3; c++) { ljf[(t * 3 + c) * 2] = (float)T.lj_a[t * 3 + c]; ljf[(t * 3 + c) * 2 + 1] = (float)T.lj_b[t * 3 + c]; }
+    std::vector<double> ljd(ljf.begin(), ljf.end());
+    for (int t = 0; t < T.nct; t++)
+        for (int c = 0; c < 3; c++) { ljd[(t * 3 + c) * 2] = T.lj_a[t * 3 + c]; ljd[(t * 3 + c) * 2 + 1] = T.lj_b[t * 3 + c]; }
     std::vector<int> g_nq(s.ncgp, 0);
     for (int g = 0; g < s.ncgp; g++)
         for (int k = 0; k < T.g_n[g]; k++) g_nq[g] += !T.is_q[T.g_atoms[T.g_first[g] + k]];
-    if (upload(h->crg, T.crg) || upload(h->crgf, crgf) || upload(h->ljf, ljf) || upload(h->ctype, T.ctype) ||
+    if (upload(h->crg, T.crg) || upload(h->crgf, crgf) || upload(h->ljf, ljf) || upload(h->ljd, ljd) || upload(h->ctype, T.ctype) ||
         upload(h->grp_of_atom, T.grp_of_atom) || upload(h->g_first, T.g_first) || upload(h->g_n, T.g_n) ||
         upload(h->g_switch, T.g_switch) || upload(h->g_atoms, T.g_atoms) || upload(h->g_nq, g_nq) ||
         upload(h->u_sw, T.u_sw) || upload(h->u_grp, T.u_grp) || upload(h->sp_off, T.sp_off) ||
@@ -192,7 +195,7 @@ static int init_device(qnb_handle *h) {
     D.crg = h->crg.p; D.crgf = h->crgf.p; D.ctype = h->ctype.p; D.is_q = h->is_q.p; D.excl = h->excl.p; D.qbonded = h->qbonded.p;
     D.grp_of_atom = h->grp_of_atom.p; D.g_first = h->g_first.p; D.g_n = h->g_n.p; D.g_switch = h->g_switch.p;
     D.g_atoms = h->g_atoms.p; D.g_nq = h->g_nq.p; D.u_sw = h->u_sw.p; D.u_grp = h->u_grp.p; D.u_excl = h->u_excl.p;
-    D.ljf = h->ljf.p; D.ljcode = h->ljcode.p; D.sp_off = h->sp_off.p; D.sp_partner = h->sp_partner.p; D.sp_code = h->sp_code.p;
+    D.ljf = h->ljf.p; D.ljd = h->ljd.p; D.ljcode = h->ljcode.p; D.sp_off = h->sp_off.p; D.sp_partner = h->sp_partner.p; D.sp_code = h->sp_code.p;
     D.gs_off = h->gs_off.p; D.gs_atoms = h->gs_atoms.p; D.iqseq = h->iqseq.p; D.qp_tab = h->qp_tab.p; D.qw_tab = h->qw_tab.p;
     for (int a = 0; a < 3; a++) {
         D.wq[a] = s.nwat > 0 ? (float)T.w_crg[a] : 0.f;
@@ -200,7 +203,7 @@ static int init_device(qnb_handle *h) {
         D.wct[a] = s.nwat > 0 ? T.w_ctype[a] : 0;
         for (int b = 0; b < 3; b++) {
             const QPar p = s.nwat > 0 ? T.ww_par[a * 3 + b] : QPar{};
-            D.wwA[a * 3 + b] = (float)p.A; D.wwB[a * 3 + b] = (float)p.B; D.wwQ[a * 3 + b] = (float)p.el; D.wwQd[a * 3 + b] = p.el;
+            D.wwA[a * 3 + b] = (float)p.A; D.wwB[a * 3 + b] = (float)p.B; D.wwQ[a * 3 + b] = (float)p.el; D.wwQd[a * 3 + b] = p.el; D.wwAd[a * 3 + b] = p.A; D.wwBd[a * 3 + b] = p.B;
         }
     }
     const size_t n3 = 3 * (size_t)s.natom;
@@ -418,6 +421,24 @@ static int step_device(qnb_handle *h, int flags) {
         if (rc) return fail("ncclAllReduce(forces): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
     }
     return 0;
+}
+
+}  // namespace qnb
+
+namespace qnb {
+template <typename T>
+__global__ void __launch_bounds__(256) k_fma_peak(T *out, int iters, T a, T b) {
+    T v[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = (T)(threadIdx.x + k);
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = v[k] * a + b;
+    }
+    T s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += v[k];
+    if (s == (T)123456789) out[0] = s;   // never true: keeps the chain alive
 }
 
 }  // namespace qnb
@@ -643,6 +664,61 @@ int qnb_comm_init(qnb_handle *h, int rank, int nranks, const void *id128) {
     return 0;
 }
 
+// ---- pipe peaks measured on the spot (the roofline denominators of the force kernels)
+int qnb_bench_peak(int device, int which, float *tflops_out) {
+    if (!tflops_out) return fail("null argument");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 14;
+    void *buf;
+    CU(cudaMalloc(&buf, 64));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    float best = 0.f;
+    for (int rep = 0; rep < 6; rep++) {
+        CU(cudaEventRecord(e0));
+        if (which == 0) k_fma_peak<float><<<blocks, threads>>>((float *)buf, iters, 1.0001f, 0.5f);
+        else k_fma_peak<double><<<blocks, threads>>>((double *)buf, iters, 1.0001, 0.5);
+        CU(cudaEventRecord(e1));
+        CU(cudaEventSynchronize(e1));
+        float ms;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        const double flop = 2.0 * 8.0 * iters * (double)blocks * threads;
+        const float tf = (float)(flop / (ms * 1e-3) / 1e12);
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf);
+    CU(cudaGetLastError());
+    *tflops_out = best;
+    return 0;
+}
+
+// md_run's inner loop on device-resident coordinates: lists every nbcycle steps (md.f90:1661), one nonbonded
+// evaluation per step; CUDA-event time of the whole loop.
+int qnb_bench_md(qnb_handle *h, const double *lambda, int flags, int steps, int nbcycle, float *ms_out) {
+    if (!h || !lambda || !ms_out) return fail("null argument");
+    if (!h->lists_built) return fail("pair lists have not been built");
+    CU(cudaSetDevice(h->device));
+    for (int k = 0; k < h->T.s.nstates; k++) h->hlam[k] = lambda[k];
+    CU(cudaMemcpyAsync(h->lambda.p, h->hlam, h->T.s.nstates * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    CU(cudaEventRecord(h->ev0, h->st));
+    for (int k = 0; k < steps; k++) {
+        if (nbcycle > 0 && k % nbcycle == 0) {
+            h->qp_done = h->qw_done = false;
+            if (build_device(h, h->hx)) return 1;
+        }
+        if (step_device(h, flags)) return 1;
+    }
+    CU(cudaEventRecord(h->ev1, h->st));
+    CU(cudaEventSynchronize(h->ev1));
+    CU(cudaEventElapsedTime(ms_out, h->ev0, h->ev1));
+    CU(cudaGetLastError());
+    return 0;
+}
+
 static int flush_l2(qnb_handle *h) {
     const size_t bytes = 256u << 20;   // > 126 MB L2
     if (h->flush.ensure(bytes)) return 1;
@@ -748,7 +824,7 @@ int qnb_finalize(qnb_handle *h) {
     cudaSetDevice(h->device);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     if (h->st) cudaStreamSynchronize(h->st);
-    h->crg.release(); h->crgf.release(); h->ljf.release(); h->ctype.release(); h->grp_of_atom.release();
+    h->crg.release(); h->ljd.release(); h->crgf.release(); h->ljf.release(); h->ctype.release(); h->grp_of_atom.release();
     h->g_first.release(); h->g_n.release(); h->g_switch.release(); h->g_atoms.release(); h->g_nq.release();
     h->u_sw.release(); h->u_grp.release(); h->sp_off.release(); h->sp_partner.release(); h->gs_off.release();
     h->gs_atoms.release(); h->iqseq.release(); h->is_q.release(); h->excl.release(); h->qbonded.release();

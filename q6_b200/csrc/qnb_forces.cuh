@@ -54,6 +54,32 @@ __device__ __forceinline__ double coulomb_f64(double dx, double dy, double dz, d
     const double r2 = fma(dx, dx, fma(dy, dy, dz * dz));
     return qq * rsqrt_refine(r2, rinv_seed);
 }
+// FP64 Coulomb + LJ energies of one pair (clashing start structures carry LJ terms of 1e3..1e5 kcal/mol whose
+// FP32 rounding alone would exceed 1e-6 of the net Vvdw)
+__device__ __forceinline__ void energy_f64(double dx, double dy, double dz, double qq, double A, double B,
+                                           float rinv_seed, double &eel, double &evdw) {
+    const double r2 = fma(dx, dx, fma(dy, dy, dz * dz));
+    const double y = rsqrt_refine(r2, rinv_seed);
+    eel = fma(qq, y, eel);
+    const double y2 = y * y, r6 = y2 * y2 * y2;
+    evdw += fma(A * r6, r6, -B * r6);
+}
+template <bool GEOM>
+__device__ __forceinline__ void lj_pair_f64(const double *__restrict__ ljd, int cta, int ctb, int code, double &A, double &B) {
+    const double2 pa = *reinterpret_cast<const double2 *>(ljd + (cta * 3 + code - 1) * 2);
+    const double2 pb = *reinterpret_cast<const double2 *>(ljd + (ctb * 3 + code - 1) * 2);
+    if (GEOM) {
+        A = pa.x * pb.x;
+        B = pa.y * pb.y;
+    } else {
+        double t = pa.x + pb.x;
+        t = t * t;
+        t = t * t * t;
+        const double e = pa.y * pb.y;
+        A = t * t * e;
+        B = 2.0 * t * e;
+    }
+}
 
 // ------------------------------------------------------------------------------------------------
 // Water rows: ww (3x3 site tile) + the water side of pw.  One warp per water molecule.
@@ -80,8 +106,7 @@ k_water_force(Dev D, const double *__restrict__ x, const int *__restrict__ row_o
     float g[3][3];
 #pragma unroll
     for (int a = 0; a < 3; a++) g[a][0] = g[a][1] = g[a][2] = 0.f;
-    float evdw = 0.f;
-    double eel = 0.0;
+    double evdw = 0.0, eel = 0.0;
 
     // ---- water-water: A_own (with energies) then A_mir (forces only)
     for (int k = lane; k < nown + nmir; k += 32) {
@@ -115,12 +140,13 @@ k_water_force(Dev D, const double *__restrict__ x, const int *__restrict__ row_o
                 const float dx = uf[b][0] - sf[a][0], dy = uf[b][1] - sf[a][1], dz = uf[b][2] - sf[a][2];
                 float rinv, ev = 0.f, dv;
                 const bool lj = !SPC || (a == 0 && b == 0);   // nonbond_ww_spc: only the first pair carries LJ
-                if (lj) dv = pair_f32<true, true>(dx, dy, dz, D.wwQ[a * 3 + b], D.wwA[a * 3 + b], D.wwB[a * 3 + b], rinv, ev);
+                if (lj) dv = pair_f32<true, false>(dx, dy, dz, D.wwQ[a * 3 + b], D.wwA[a * 3 + b], D.wwB[a * 3 + b], rinv, ev);
                 else dv = pair_f32<false, false>(dx, dy, dz, D.wwQ[a * 3 + b], 0.f, 0.f, rinv, ev);
                 g[a][0] = fmaf(-dx, dv, g[a][0]); g[a][1] = fmaf(-dy, dv, g[a][1]); g[a][2] = fmaf(-dz, dv, g[a][2]);
                 if (own) {
-                    evdw += ev;
-                    eel += coulomb_f64(ud[b][0] - sd[a][0], ud[b][1] - sd[a][1], ud[b][2] - sd[a][2], D.wwQd[a * 3 + b], rinv);
+                    if (lj) energy_f64(ud[b][0] - sd[a][0], ud[b][1] - sd[a][1], ud[b][2] - sd[a][2], D.wwQd[a * 3 + b],
+                                       D.wwAd[a * 3 + b], D.wwBd[a * 3 + b], rinv, eel, evdw);
+                    else eel += coulomb_f64(ud[b][0] - sd[a][0], ud[b][1] - sd[a][1], ud[b][2] - sd[a][2], D.wwQd[a * 3 + b], rinv);
                 }
             }
         }
@@ -159,7 +185,7 @@ k_water_force(Dev D, const double *__restrict__ x, const int *__restrict__ row_o
             const double s = warp_sum((double)g[a][c]);
             if (lane == 0) grad[3 * (i0 + a) + c] += s;
         }
-    const double sv = warp_sum((double)evdw), se = warp_sum(eel);
+    const double sv = warp_sum(evdw), se = warp_sum(eel);
     if (lane == 0 && (nown > 0)) {
         atomicAdd(&E[QNB_E_WW_VDW], sv);
         atomicAdd(&E[QNB_E_WW_EL], se);
@@ -195,8 +221,7 @@ k_solute_force(Dev D, const double *__restrict__ x, const int *__restrict__ row_
     const int gf = D.g_first[gidx], gn = D.g_n[gidx];
     const int sw = D.g_switch[gidx];
     const double ox = x[3 * sw], oy = x[3 * sw + 1], oz = x[3 * sw + 2];   // row origin = switch atom
-    double e_pp_el = 0.0, e_pw_el = 0.0;
-    float e_pp_vdw = 0.f, e_pw_vdw = 0.f;
+    double e_pp_el = 0.0, e_pw_el = 0.0, e_pp_vdw = 0.0, e_pw_vdw = 0.0;
 
     int kscan = 0;   // position in the group's atom list
     while (kscan < gn) {
@@ -263,13 +288,14 @@ k_solute_force(Dev D, const double *__restrict__ x, const int *__restrict__ row_
                         lj_pair<GEOM>(D.ljf, cti[t], ctb, code, A, B);
                         const float qq = i14 ? qf[t] * qb * D.el14f : qf[t] * qb;
                         const float dx = ufx - sf[t][0], dy = ufy - sf[t][1], dz = ufz - sf[t][2];
-                        const float dv = pair_f32<true, true>(dx, dy, dz, qq, A, B, rinv, ev);
+                        const float dv = pair_f32<true, false>(dx, dy, dz, qq, A, B, rinv, ev);
                         g[t][0] = fmaf(-dx, dv, g[t][0]); g[t][1] = fmaf(-dy, dv, g[t][1]); g[t][2] = fmaf(-dz, dv, g[t][2]);
                         // energy once per pair: on the owner side; inside one group on the lower atom (i<j, L1874)
                         if (own && (!same || a < b)) {
-                            e_pp_vdw += ev;
                             const double qqd = i14 ? qd[t] * qbd * D.el14 : qd[t] * qbd;
-                            e_pp_el += coulomb_f64(ux - sd[t][0], uy - sd[t][1], uz - sd[t][2], qqd, rinv);
+                            double Ad, Bd;
+                            lj_pair_f64<GEOM>(D.ljd, cti[t], ctb, code, Ad, Bd);
+                            energy_f64(ux - sd[t][0], uy - sd[t][1], uz - sd[t][2], qqd, Ad, Bd, rinv, e_pp_el, e_pp_vdw);
                         }
                     }
                 }
@@ -299,10 +325,11 @@ k_solute_force(Dev D, const double *__restrict__ x, const int *__restrict__ row_
                         float A, B, rinv, ev = 0.f;
                         lj_pair<GEOM>(D.ljf, cti[t], ctb, code, A, B);
                         const float dx = ufx - sf[t][0], dy = ufy - sf[t][1], dz = ufz - sf[t][2];
-                        const float dv = pair_f32<true, true>(dx, dy, dz, qf[t] * D.wq[s], A, B, rinv, ev);
+                        const float dv = pair_f32<true, false>(dx, dy, dz, qf[t] * D.wq[s], A, B, rinv, ev);
                         g[t][0] = fmaf(-dx, dv, g[t][0]); g[t][1] = fmaf(-dy, dv, g[t][1]); g[t][2] = fmaf(-dz, dv, g[t][2]);
-                        e_pw_vdw += ev;
-                        e_pw_el += coulomb_f64(ux - sd[t][0], uy - sd[t][1], uz - sd[t][2], qd[t] * D.wqd[s], rinv);
+                        double Ad, Bd;
+                        lj_pair_f64<GEOM>(D.ljd, cti[t], ctb, code, Ad, Bd);
+                        energy_f64(ux - sd[t][0], uy - sd[t][1], uz - sd[t][2], qd[t] * D.wqd[s], Ad, Bd, rinv, e_pw_el, e_pw_vdw);
                     }
                 }
             }
@@ -315,8 +342,7 @@ k_solute_force(Dev D, const double *__restrict__ x, const int *__restrict__ row_
                 if (lane == 0 && t < nt) grad[3 * ai[t] + c] += s;
             }
     }
-    const double s1 = warp_sum(e_pp_el), s2 = warp_sum((double)e_pp_vdw), s3 = warp_sum(e_pw_el),
-                 s4 = warp_sum((double)e_pw_vdw);
+    const double s1 = warp_sum(e_pp_el), s2 = warp_sum(e_pp_vdw), s3 = warp_sum(e_pw_el), s4 = warp_sum(e_pw_vdw);
     if (lane == 0) {
         if (nown > 0) { atomicAdd(&E[QNB_E_PP_EL], s1); atomicAdd(&E[QNB_E_PP_VDW], s2); }
         if (nb > 0) { atomicAdd(&E[QNB_E_PW_EL], s3); atomicAdd(&E[QNB_E_PW_VDW], s4); }

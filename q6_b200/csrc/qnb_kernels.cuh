@@ -60,6 +60,7 @@ struct Dev {
     const uint8_t *u_excl;
     // LJ tables
     const float *ljf;           // [nct][3][2] (a,b) by code
+    const double *ljd;          // same in FP64 (energies)
     const uint8_t *ljcode;      // [nct][nct]
     // specials
     const int *sp_off, *sp_partner;
@@ -70,7 +71,7 @@ struct Dev {
     double wqd[3];
     int wct[3];
     float wwA[9], wwB[9], wwQ[9];
-    double wwQd[9];
+    double wwQd[9], wwAd[9], wwBd[9];
     // solute non-Q atom compaction (rows of the solute kernel are per group)
     // Q
     const int *iqseq;           // [nqat]

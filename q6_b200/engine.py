@@ -84,6 +84,10 @@ def load_library(path: str = LIB_PATH):
     lib.qnb_bench_nonbond.argtypes = [H, _PD, C.c_int, C.c_int, C.c_int, _PF]
     lib.qnb_bench_build_lists.restype = C.c_int
     lib.qnb_bench_build_lists.argtypes = [H, C.c_int, _PF]
+    lib.qnb_bench_md.restype = C.c_int
+    lib.qnb_bench_md.argtypes = [H, _PD, C.c_int, C.c_int, C.c_int, _PF]
+    lib.qnb_bench_peak.restype = C.c_int
+    lib.qnb_bench_peak.argtypes = [C.c_int, C.c_int, _PF]
     lib.qnb_bench_kernels.restype = C.c_int
     lib.qnb_bench_kernels.argtypes = [H, _PD, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int, _PF, C.c_int]
     lib.qnb_launch_count.restype = C.c_int64
@@ -202,6 +206,13 @@ class Qnb:
         self._check(self.lib.qnb_bench_nonbond(self.h, _dp(lam), flags, steps, int(flush_l2), C.byref(ms)))
         return ms.value
 
+    def bench_md(self, lambdas, steps: int, nbcycle: int, md=True, qq=True) -> float:
+        lam = np.ascontiguousarray(lambdas, dtype=np.float64)
+        ms = C.c_float()
+        flags = (QNB_FLAG_MD if md else 0) | (QNB_FLAG_QQ if qq else 0)
+        self._check(self.lib.qnb_bench_md(self.h, _dp(lam), flags, steps, nbcycle, C.byref(ms)))
+        return ms.value
+
     def bench_build_lists(self, reps: int) -> float:
         ms = C.c_float()
         self._check(self.lib.qnb_bench_build_lists(self.h, reps, C.byref(ms)))
@@ -225,3 +236,12 @@ class Qnb:
         a, b = C.c_int64(), C.c_int64()
         self._check(self.lib.qnb_last_copy_bytes(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+
+def bench_peak(which: int, device: int = 0) -> float:
+    """Measured FMA throughput (TFLOP/s) of the FP32 (0) or FP64 (1) pipe."""
+    lib = load_library()
+    tf = C.c_float()
+    if lib.qnb_bench_peak(device, which, C.byref(tf)) != 0:
+        raise QnbError(lib.qnb_last_error().decode())
+    return tf.value
