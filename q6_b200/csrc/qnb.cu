@@ -12,8 +12,8 @@
 #include <vector>
 
 #include "../../include/qnb.h"
-#include "qnb_forces.cuh"
 #include "qnb_kernels.cuh"
+#include "qnb_forces.cuh"
 #include "qnb_lists.cuh"
 #include "qnb_tables.hpp"
 
@@ -96,8 +96,11 @@ struct qnb_handle {
     int device = 0;
     HostTables T;
     Dev D{};
-    cudaStream_t st = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t st = nullptr, aux[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+    cudaGraphExec_t graph[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};   // [with copies][flags]
+    bool use_graph = true;
+    int graph_launches[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
     // static device tables
     DBuf<double> crg, ljd;
     DBuf<float> crgf, ljf;
@@ -119,6 +122,8 @@ struct qnb_handle {
     DBuf<int> cell_of, cell_count, cell_start, cell_items, counts, row_tot, row_off, flag, pos, qp_list, qw_list,
         qp_shift_atom;
     DBuf<uint32_t> rows;
+    DBuf<double4> item_pos, src;
+    DBuf<int> cell_unsorted, item_nq, src_off;
     int nqp = 0, nqw = 0;
     bool qp_done = false, qw_done = false, lists_built = false;
     int64_t total_rows = 0;
@@ -135,11 +140,12 @@ struct qnb_handle {
 
 namespace qnb {
 
-#define LAUNCH(h, kernel, grid, block, smem, ...)                      \
+#define LAUNCH_ON(h, stream, kernel, grid, block, smem, ...)            \
     do {                                                               \
-        kernel<<<(grid), (block), (smem), (h)->st>>>(__VA_ARGS__);     \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);    \
         (h)->launches++;                                               \
     } while (0)
+#define LAUNCH(h, kernel, grid, block, smem, ...) LAUNCH_ON(h, (h)->st, kernel, grid, block, smem, __VA_ARGS__)
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
@@ -216,12 +222,24 @@ static int init_device(qnb_handle *h) {
     CU(cudaMallocHost(&h->hout, h->nout * sizeof(double)));
     CU(cudaMallocHost(&h->hlam, kMaxStates * sizeof(double)));
     CU(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+    for (int k = 0; k < 3; k++) {
+        CU(cudaStreamCreateWithFlags(&h->aux[k], cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&h->ev_join[k], cudaEventDisableTiming));
+    }
+    CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     CU(cudaEventCreate(&h->ev0));
     CU(cudaEventCreate(&h->ev1));
+    if (const char *e = getenv("QNB_NO_GRAPH")) h->use_graph = !(e[0] == '1');
     return 0;
 }
 
 // ------------------------------------------------------------------ list build
+static void drop_graphs(qnb_handle *h) {
+    for (int c = 0; c < 2; c++)
+        for (int f = 0; f < 4; f++)
+            if (h->graph[c][f]) { cudaGraphExecDestroy(h->graph[c][f]); h->graph[c][f] = nullptr; }
+}
+
 static void make_grid(qnb_handle *h, const double *hx) {
     const qnb_system &s = h->T.s;
     Grid &G = h->grid;
@@ -276,6 +294,7 @@ static int run_exclusive_scan(qnb_handle *h, const int *in, int *out, int n) {
 
 static int build_device(qnb_handle *h, const double *hx_for_grid) {
     const Dev &D = h->D;
+    drop_graphs(h);   // row pointers, counts and list sizes are baked into the captured launches
     const int nu = D.nunit;
     make_grid(h, hx_for_grid);
     const Grid G = h->grid;
@@ -285,7 +304,9 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
         h->row_off.ensure(std::max(nu, 1) + 2) ||
         h->flag.ensure(std::max({D.natom, D.nwat, 1}) + 1) || h->pos.ensure(std::max({D.natom, D.nwat, 1}) + 2) ||
         h->qp_list.ensure(std::max(D.nat_solute, 1)) || h->qw_list.ensure(std::max(D.nwat, 1)) ||
-        h->qp_shift_atom.ensure(std::max(D.ncgp_solute, 1)))
+        h->qp_shift_atom.ensure(std::max(D.ncgp_solute, 1)) || h->item_pos.ensure(std::max(nu, 1)) ||
+        h->src.ensure(std::max(D.natom, 1)) || h->cell_unsorted.ensure(std::max(nu, 1)) ||
+        h->item_nq.ensure(std::max(nu, 1) + 1) || h->src_off.ensure(std::max(nu, 1) + 2))
         return 1;
     const bool md_lists = true;
     if (nu > 0 && md_lists) {
@@ -293,10 +314,11 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
         LAUNCH(h, k_bin_units, cdiv(nu, 256), 256, 0, D, G, h->x.p, h->upos.p, h->cell_of.p, h->cell_count.p);
         run_exclusive_scan(h, h->cell_count.p, h->cell_start.p, G.ncell);
         CU(cudaMemsetAsync(h->cell_count.p, 0, sizeof(int) * (G.ncell + 1), h->st));
-        LAUNCH(h, k_cell_fill, cdiv(nu, 256), 256, 0, nu, h->cell_of.p, h->cell_start.p, h->cell_count.p, h->cell_items.p);
-        LAUNCH(h, k_cell_sort, cdiv(G.ncell, 128), 128, 0, G.ncell, h->cell_start.p, h->cell_items.p);
+        LAUNCH(h, k_cell_fill, cdiv(nu, 256), 256, 0, nu, h->cell_of.p, h->cell_start.p, h->cell_count.p, h->cell_unsorted.p);
+        LAUNCH(h, k_cell_sort, G.ncell, 64, 0, G.ncell, h->cell_start.p, h->cell_unsorted.p, h->cell_items.p);
+        LAUNCH(h, k_pack_items, cdiv(nu, 256), 256, 0, D, h->upos.p, h->cell_items.p, h->item_pos.p, h->item_nq.p);
         LAUNCH(h, k_build_rows<false>, cdiv(nu * 32, 256), 256, 0, D, h->cut, G, h->upos.p, h->cell_of.p, h->cell_start.p,
-               h->cell_items.p, h->counts.p, (const int *)nullptr, (uint32_t *)nullptr);
+               h->item_pos.p, h->counts.p, (const int *)nullptr, (uint32_t *)nullptr);
         LAUNCH(h, k_row_totals, cdiv(nu, 256), 256, 0, nu, h->counts.p, h->row_tot.p);
         run_exclusive_scan(h, h->row_tot.p, h->row_off.p, nu);
         int total = 0;
@@ -305,7 +327,7 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
         h->total_rows = total;
         if (h->rows.ensure((size_t)std::max(total, 1))) return 1;
         LAUNCH(h, k_build_rows<true>, cdiv(nu * 32, 256), 256, 0, D, h->cut, G, h->upos.p, h->cell_of.p, h->cell_start.p,
-               h->cell_items.p, h->counts.p, h->row_off.p, h->rows.p);
+               h->item_pos.p, h->counts.p, h->row_off.p, h->rows.p);
     }
     // Q-atom partner lists: built once when the cut-off covers everything (nbqplist L3678, nbqwlist L3889,
     // nbqplist_box L3780, nbqwlist_box L3972)
@@ -333,9 +355,12 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
     // LRF: cgp_centers + lrf_update over every pair that falls in the LRF branch
     if (D.use_LRF && D.ncgp > 0) {
         LAUNCH(h, k_cgp_centers, cdiv(D.ncgp, 128), 128, 0, D, h->x.p, h->lrf.p);
-        if (nu > 0)
+        if (nu > 0) {
+            run_exclusive_scan(h, h->item_nq.p, h->src_off.p, nu);
+            LAUNCH(h, k_pack_sources, cdiv(nu, 128), 128, 0, D, h->x.p, h->cell_items.p, h->src_off.p, h->src.p);
             LAUNCH(h, k_lrf_accumulate, cdiv(nu * 32, 256), 256, 0, D, h->cut, G, h->lrf_reach, h->x.p, h->upos.p,
-                   h->cell_of.p, h->cell_start.p, h->cell_items.p, h->lrf.p);
+                   h->cell_of.p, h->cell_start.p, h->item_pos.p, h->src_off.p, h->src.p, h->lrf.p);
+        }
         if (h->comm) {
             // lrf_gather (nonbondene.f90:616-623): sum the moments, keep cgp_cent (identical on every rank).
             // cgp_cent is divided by nranks after the sum so one all-reduce serves both.
@@ -370,14 +395,14 @@ static bool step_kernel_active(const qnb_handle *h, int k, int flags) {
     return false;
 }
 
-static void launch_step_kernel(qnb_handle *h, int k) {
+static void launch_step_kernel(qnb_handle *h, int k, cudaStream_t cs) {
     const Dev &D = h->D;
     double *grad = h->out.p, *E = h->out.p + 3 * (size_t)D.natom, *EQ = E + QNB_E_COUNT;
     const bool pbc = D.use_PBC, spc = D.spc_water, geom = D.geometric;
     switch (k) {
     case K_WATER: {
         const int grid = cdiv(D.nwat * 32, 128);
-#define WCASE(P, S, G) LAUNCH(h, (k_water_force<P, S, G>), grid, 128, 0, D, h->x.p, h->row_off.p, h->counts.p, h->rows.p, grad, E)
+#define WCASE(P, S, G) LAUNCH_ON(h, cs, (k_water_force<P, S, G>), grid, 128, 0, D, h->x.p, h->row_off.p, h->counts.p, h->rows.p, grad, E)
         if (pbc) { if (spc) WCASE(true, true, true); else if (geom) WCASE(true, false, true); else WCASE(true, false, false); }
         else { if (spc) WCASE(false, true, true); else if (geom) WCASE(false, false, true); else WCASE(false, false, false); }
 #undef WCASE
@@ -385,41 +410,104 @@ static void launch_step_kernel(qnb_handle *h, int k) {
     }
     case K_SOLUTE: {
         const int grid = cdiv(D.ncgp_solute * 32, 128);
-#define SCASE(P, G) LAUNCH(h, (k_solute_force<P, G>), grid, 128, 0, D, h->x.p, h->row_off.p, h->counts.p, h->rows.p, grad, E)
+#define SCASE(P, G) LAUNCH_ON(h, cs, (k_solute_force<P, G>), grid, 128, 0, D, h->x.p, h->row_off.p, h->counts.p, h->rows.p, grad, E)
         if (pbc) { if (geom) SCASE(true, true); else SCASE(true, false); }
         else { if (geom) SCASE(false, true); else SCASE(false, false); }
 #undef SCASE
         break;
     }
     case K_QPARTNER: {
-        const int n = h->nqp + h->nqw;
+        const int n = h->nqp + 3 * h->nqw;
         const size_t sm = sizeof(double) * (3 * (size_t)D.nqat + D.nstates);
-        if (pbc) LAUNCH(h, k_q_partner<true>, cdiv(n, 128), 128, sm, D, h->x.p, h->lambda.p, h->nqp, h->qp_list.p, h->qp_shift_atom.p, h->nqw, h->qw_list.p, grad);
-        else LAUNCH(h, k_q_partner<false>, cdiv(n, 128), 128, sm, D, h->x.p, h->lambda.p, h->nqp, h->qp_list.p, h->qp_shift_atom.p, h->nqw, h->qw_list.p, grad);
+        if (pbc) LAUNCH_ON(h, cs, k_q_partner<true>, cdiv(n, 128), 128, sm, D, h->x.p, h->lambda.p, h->nqp, h->qp_list.p, h->qp_shift_atom.p, h->nqw, h->qw_list.p, grad);
+        else LAUNCH_ON(h, cs, k_q_partner<false>, cdiv(n, 128), 128, sm, D, h->x.p, h->lambda.p, h->nqp, h->qp_list.p, h->qp_shift_atom.p, h->nqw, h->qw_list.p, grad);
         break;
     }
-    case K_QATOM:
-        if (pbc) LAUNCH(h, k_q_atom<true>, D.nqat, 128, 0, D, h->x.p, h->lambda.p, h->nqp, h->qp_list.p, h->qp_shift_atom.p, h->nqw, h->qw_list.p, grad, EQ);
-        else LAUNCH(h, k_q_atom<false>, D.nqat, 128, 0, D, h->x.p, h->lambda.p, h->nqp, h->qp_list.p, h->qp_shift_atom.p, h->nqw, h->qw_list.p, grad, EQ);
+    case K_QATOM: {
+        const int nsite = h->nqp + 3 * h->nqw;
+        const int slices = std::max(1, std::min(cdiv(nsite, 128), cdiv(4 * 148, std::max(D.nqat, 1))));
+        const dim3 qgrid(D.nqat, slices);
+#define QCASE(P, N) LAUNCH_ON(h, cs, (k_q_atom<P, N>), qgrid, 128, 0, D, h->x.p, h->lambda.p, h->nqp, h->qp_list.p, h->qp_shift_atom.p, h->nqw, h->qw_list.p, grad, EQ)
+        const int ns = D.nstates;
+        if (pbc) { if (ns <= 1) QCASE(true, 1); else if (ns <= 2) QCASE(true, 2); else if (ns <= 4) QCASE(true, 4); else QCASE(true, 8); }
+        else { if (ns <= 1) QCASE(false, 1); else if (ns <= 2) QCASE(false, 2); else if (ns <= 4) QCASE(false, 4); else QCASE(false, 8); }
+#undef QCASE
         break;
+    }
     case K_QSTATIC:
-        LAUNCH(h, k_qq_static, cdiv(h->n_qstatic, 128), 128, 0, h->n_qstatic, h->n_qq, h->qstatic.p, h->x.p, h->lambda.p, grad, EQ);
+        LAUNCH_ON(h, cs, k_qq_static, cdiv(h->n_qstatic, 128), 128, 0, h->n_qstatic, h->n_qq, h->qstatic.p, h->x.p, h->lambda.p, grad, EQ);
         break;
     case K_LRF:
-        LAUNCH(h, k_lrf_taylor, cdiv(D.natom, 128), 128, 0, D, h->x.p, h->lrf.p, grad, E);
+        LAUNCH_ON(h, cs, k_lrf_taylor, cdiv(D.natom, 128), 128, 0, D, h->x.p, h->lrf.p, grad, E);
         break;
     }
 }
 
-static int step_device(qnb_handle *h, int flags) {
+// The kernels of one evaluation are independent (they only meet in atomicAdd on grad/E), so they are issued on
+// four streams between a fork and a join event: at 12k atoms no single kernel fills 148 SMs.
+static const int kStreamOf[K_COUNT] = {0, 1, 2, 2, -1, -1};   // aux stream index, -1 = main stream
+
+static int issue_step(qnb_handle *h, int flags) {
     CU(cudaMemsetAsync(h->out.p, 0, h->nout * sizeof(double), h->st));
-    for (int k = 0; k < K_COUNT; k++)
-        if (step_kernel_active(h, k, flags)) launch_step_kernel(h, k);
+    CU(cudaEventRecord(h->ev_fork, h->st));
+    bool used[3] = {false, false, false};
+    for (int k = 0; k < K_COUNT; k++) {
+        if (!step_kernel_active(h, k, flags)) continue;
+        const int si = kStreamOf[k];
+        cudaStream_t cs = si < 0 ? h->st : h->aux[si];
+        if (si >= 0 && !used[si]) { CU(cudaStreamWaitEvent(cs, h->ev_fork, 0)); used[si] = true; }
+        launch_step_kernel(h, k, cs);
+    }
+    for (int k = 0; k < 3; k++)
+        if (used[k]) {
+            CU(cudaEventRecord(h->ev_join[k], h->aux[k]));
+            CU(cudaStreamWaitEvent(h->st, h->ev_join[k], 0));
+        }
+    return 0;
+}
+
+// One evaluation on the device.  with_copies: pinned x -> device before, [grad|E|EQ] -> pinned after.
+// Captured once per list build into a CUDA graph (one launch per MD step instead of ~10 API calls).
+static int step_device(qnb_handle *h, int flags, bool with_copies = false) {
+    const size_t n3 = 3 * (size_t)h->T.s.natom;
+    const bool graphable = h->use_graph && !h->comm;
+    flags &= 3;
+    if (graphable) {
+        cudaGraphExec_t &ge = h->graph[with_copies ? 1 : 0][flags];
+        if (!ge) {
+            cudaGraph_t g = nullptr;
+            const int64_t l0 = h->launches;
+            CU(cudaStreamBeginCapture(h->st, cudaStreamCaptureModeThreadLocal));
+            int rc = 0;
+            if (with_copies) {
+                rc |= cudaMemcpyAsync(h->x.p, h->hx, n3 * sizeof(double), cudaMemcpyHostToDevice, h->st) != cudaSuccess;
+                rc |= cudaMemcpyAsync(h->lambda.p, h->hlam, kMaxStates * sizeof(double), cudaMemcpyHostToDevice, h->st) != cudaSuccess;
+            }
+            rc |= issue_step(h, flags);
+            if (with_copies) rc |= cudaMemcpyAsync(h->hout, h->out.p, h->nout * sizeof(double), cudaMemcpyDeviceToHost, h->st) != cudaSuccess;
+            cudaError_t ce = cudaStreamEndCapture(h->st, &g);
+            h->graph_launches[with_copies ? 1 : 0][flags] = (int)(h->launches - l0);
+            h->launches = l0;
+            if (rc || ce != cudaSuccess || !g) return fail("CUDA graph capture of the step failed: %s", cudaGetErrorString(ce));
+            ce = cudaGraphInstantiate(&ge, g, 0);
+            cudaGraphDestroy(g);
+            if (ce != cudaSuccess) return fail("cudaGraphInstantiate: %s", cudaGetErrorString(ce));
+        }
+        CU(cudaGraphLaunch(ge, h->st));
+        h->launches += h->graph_launches[with_copies ? 1 : 0][flags];
+        return 0;
+    }
+    if (with_copies) {
+        CU(cudaMemcpyAsync(h->x.p, h->hx, n3 * sizeof(double), cudaMemcpyHostToDevice, h->st));
+        CU(cudaMemcpyAsync(h->lambda.p, h->hlam, kMaxStates * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    }
+    if (issue_step(h, flags)) return 1;
     if (h->comm) {
         // gather_nonbond + serial sum on the master (potene.f90:195-222) as one all-reduce over [d | E | EQ]
         int rc = g_nccl.AllReduce(h->out.p, h->out.p, h->nout, kNcclDouble, kNcclSum, h->comm, h->st);
         if (rc) return fail("ncclAllReduce(forces): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
     }
+    if (with_copies) CU(cudaMemcpyAsync(h->hout, h->out.p, h->nout * sizeof(double), cudaMemcpyDeviceToHost, h->st));
     return 0;
 }
 
@@ -474,6 +562,7 @@ int qnb_update_box(qnb_handle *h, const double boxlength[3], const double inv_bo
     if (!h) return fail("null handle");
     for (int d = 0; d < 3; d++) { h->box[d] = boxlength[d]; h->inv_box[d] = inv_boxl[d]; }
     refresh_dev(h);
+    drop_graphs(h);
     return 0;
 }
 
@@ -510,11 +599,8 @@ int qnb_nonbond(qnb_handle *h, const double *x, const double *lambda, int flags,
     const size_t n3 = 3 * (size_t)s.natom;
     memcpy(h->hx, x, n3 * sizeof(double));
     for (int k = 0; k < s.nstates; k++) h->hlam[k] = lambda[k];
-    CU(cudaMemcpyAsync(h->x.p, h->hx, n3 * sizeof(double), cudaMemcpyHostToDevice, h->st));
-    CU(cudaMemcpyAsync(h->lambda.p, h->hlam, s.nstates * sizeof(double), cudaMemcpyHostToDevice, h->st));
     h->last_flags = flags;
-    if (step_device(h, flags)) return 1;
-    CU(cudaMemcpyAsync(h->hout, h->out.p, h->nout * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    if (step_device(h, flags, true)) return 1;
     CU(cudaStreamSynchronize(h->st));
     CU(cudaGetLastError());
     h->last_h2d = (int64_t)((n3 + s.nstates) * sizeof(double));
@@ -794,7 +880,7 @@ int qnb_bench_kernels(qnb_handle *h, const double *lambda, int flags, int reps, 
             cudaMemsetAsync(h->out.p, 0, h->nout * sizeof(double), h->st);
             if (do_flush && flush_l2(h)) return -1;
             cudaEventRecord(h->ev0, h->st);
-            launch_step_kernel(h, k);
+            launch_step_kernel(h, k, h->st);
             cudaEventRecord(h->ev1, h->st);
             cudaEventSynchronize(h->ev1);
             float ms = 0;
@@ -824,6 +910,9 @@ int qnb_finalize(qnb_handle *h) {
     cudaSetDevice(h->device);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     if (h->st) cudaStreamSynchronize(h->st);
+    drop_graphs(h);
+    for (int k = 0; k < 3; k++) { if (h->aux[k]) cudaStreamDestroy(h->aux[k]); if (h->ev_join[k]) cudaEventDestroy(h->ev_join[k]); }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     h->crg.release(); h->ljd.release(); h->crgf.release(); h->ljf.release(); h->ctype.release(); h->grp_of_atom.release();
     h->g_first.release(); h->g_n.release(); h->g_switch.release(); h->g_atoms.release(); h->g_nq.release();
     h->u_sw.release(); h->u_grp.release(); h->sp_off.release(); h->sp_partner.release(); h->gs_off.release();
@@ -833,6 +922,7 @@ int qnb_finalize(qnb_handle *h) {
     h->cell_of.release(); h->cell_count.release(); h->cell_start.release(); h->cell_items.release(); h->counts.release();
     h->row_tot.release(); h->row_off.release(); h->flag.release(); h->pos.release(); h->qp_list.release();
     h->qw_list.release(); h->qp_shift_atom.release(); h->rows.release(); h->flush.release();
+    h->item_pos.release(); h->src.release(); h->cell_unsorted.release(); h->item_nq.release(); h->src_off.release();
     if (h->hx) cudaFreeHost(h->hx);
     if (h->hout) cudaFreeHost(h->hout);
     if (h->hlam) cudaFreeHost(h->hlam);

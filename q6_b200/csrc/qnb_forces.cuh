@@ -7,6 +7,7 @@
 // "d" is the reference's gradient array (globals.f90:347): d(i) -= vec*dv, d(j) += vec*dv with
 // vec = x(j)-x(i) [+ periodic shift] and dv = (1/r) dV/dr.  Every kernel below accumulates the gradient of
 // the atoms of ITS OWN unit only (full rows), so from atom a with partner b it always adds -vec(a->b)*dv.
+// The kernels of one step run concurrently on several streams, hence the (uncontended) FP64 atomicAdd on grad.
 #pragma once
 #include "qnb_kernels.cuh"
 
@@ -183,7 +184,7 @@ k_water_force(Dev D, const double *__restrict__ x, const int *__restrict__ row_o
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             const double s = warp_sum((double)g[a][c]);
-            if (lane == 0) grad[3 * (i0 + a) + c] += s;
+            if (lane == 0) atomicAdd(&grad[3 * (i0 + a) + c], s);
         }
     const double sv = warp_sum(evdw), se = warp_sum(eel);
     if (lane == 0 && (nown > 0)) {
@@ -339,7 +340,7 @@ k_solute_force(Dev D, const double *__restrict__ x, const int *__restrict__ row_
 #pragma unroll
             for (int c = 0; c < 3; c++) {
                 const double s = warp_sum((double)g[t][c]);
-                if (lane == 0 && t < nt) grad[3 * ai[t] + c] += s;
+                if (lane == 0 && t < nt) atomicAdd(&grad[3 * ai[t] + c], s);
             }
     }
     const double s1 = warp_sum(e_pp_el), s2 = warp_sum(e_pp_vdw), s3 = warp_sum(e_pw_el), s4 = warp_sum(e_pw_vdw);
@@ -350,13 +351,21 @@ k_solute_force(Dev D, const double *__restrict__ x, const int *__restrict__ row_
 }
 
 // ------------------------------------------------------------------------------------------------
-// Q-atom kernels, FP64.  nbe_qx (nonbonded.f90:200-222) for one state.
+// Q-atom kernels, FP64 throughout (per-state energies are FEP observables), written without divisions:
+// 1/r from an FP32 rsqrt seed + Halley step, 1/(r^6+alpha) from an FP32 reciprocal seed + two Newton steps.
 struct QxOut { double vel, vvdw, dv; };
-__device__ __forceinline__ QxOut qx_eval(double r2inv, double rinv, const QPar4 &p, double lambda) {
+__device__ __forceinline__ double rcp_refine(double d) {
+    double z = (double)__frcp_rn((float)d);
+    z = z * fma(-d, z, 2.0);
+    z = z * fma(-d, z, 2.0);
+    return z;
+}
+// nbe_qx (nonbonded.f90:200-222) for one state; r2 = |vec|^2, rinv = 1/r
+__device__ __forceinline__ QxOut qx_eval(double r2, double rinv, const QPar4 &p, double lambda) {
     QxOut o;
-    const double r6 = r2inv * r2inv * r2inv;          // dist%r6 = 1/r^6
-    const double r6_hc = 1.0 / r6;                    // r^6
-    const double r6s = 1.0 / (r6_hc + p.score);       // softcore
+    const double r2inv = rinv * rinv;
+    const double r6_hc = r2 * r2 * r2;                 // 1/dist%r6 = r^6
+    const double r6s = rcp_refine(r6_hc + p.score);    // softcore: 1/(r^6 + alpha)
     const double r12 = r6s * r6s;
     o.vel = p.el * rinv;
     const double va = p.A * r12, vb = p.B * r6s;
@@ -365,8 +374,36 @@ __device__ __forceinline__ QxOut qx_eval(double r2inv, double rinv, const QPar4 
     return o;
 }
 
-// Gradient on the PARTNER atoms of the Q-atoms (nonbond_qp/_box, nonbond_qw(_spc)/_box seen from atom j).
-// One thread per listed solute atom, then one thread per listed water molecule.
+// Partner site p of the Q lists: [0,nqp) listed solute atoms, then 3 sites per listed water.
+struct QSite { int atom; int site; bool water; };
+__device__ __forceinline__ QSite q_site(const Dev &D, int p, int nqp, const int *qp_list, const int *qw_list) {
+    QSite s;
+    if (p < nqp) { s.atom = qp_list[p]; s.site = 0; s.water = false; }
+    else { const int k = p - nqp; s.site = k % 3; s.atom = D.nat_solute + 3 * qw_list[k / 3] + s.site; s.water = true; }
+    return s;
+}
+// periodic shift of the Q -> partner vector (vec = shift - (x(i) - x(j)))
+template <bool PBC>
+__device__ __forceinline__ void q_shift(const Dev &D, const double *__restrict__ x, const QSite &s,
+                                        const int *__restrict__ qp_shift_atom, double sh[3]) {
+    sh[0] = sh[1] = sh[2] = 0.0;
+    if (!PBC) return;
+    const int qs = D.qswitch0;
+    if (!s.water) {
+        // nonbond_qp_box L5275-5278: boxlength*nint((x(ia)-x(qswitch))*inv_boxl), ia = the group's first atom inside Rcq;
+        // no registered pair (Rq<0) -> zero shift
+        const int ref = qp_shift_atom[D.grp_of_atom[s.atom]];
+        if (ref >= 0)
+            for (int c = 0; c < 3; c++) sh[c] = pshift(x[3 * ref + c] - x[3 * qs + c], D.box[c], D.inv_box[c]);
+    } else {
+        // spc: one shift per molecule from x(qswitch)-x(O) (L5818-5820); general: per atom j (L5470-5472)
+        const int r = D.spc_water ? s.atom - s.site : s.atom;
+        for (int c = 0; c < 3; c++) sh[c] = pshift(x[3 * qs + c] - x[3 * r + c], D.box[c], D.inv_box[c]);
+    }
+}
+
+// Gradient on the PARTNER atoms (nonbond_qp/_box, nonbond_qw(_spc)/_box seen from atom j): one thread per
+// partner site, all Q-atoms looped from shared memory.
 template <bool PBC>
 __global__ void __launch_bounds__(128)
 k_q_partner(Dev D, const double *__restrict__ x, const double *__restrict__ lambda, int nqp,
@@ -382,166 +419,89 @@ k_q_partner(Dev D, const double *__restrict__ x, const double *__restrict__ lamb
     for (int k = threadIdx.x; k < D.nstates; k += blockDim.x) lam[k] = lambda[k];
     __syncthreads();
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nqp + 3 * nqw) return;
     const int nst = D.nstates;
-    if (p < nqp) {
-        const int j = qp_list[p];
-        const double jx = x[3 * j], jy = x[3 * j + 1], jz = x[3 * j + 2];
-        double shx = 0, shy = 0, shz = 0;
-        if (PBC) {
-            // nonbond_qp_box L5275-5278: nbqp_cgp%shift = boxlength*nint((x(ia)-x(qswitch))*inv_boxl) with ia the
-            // group's first atom inside Rcq; vec = shift - (x(i)-x(j)).  No registered pair (Rq<0) -> zero shift.
-            const int ref = qp_shift_atom[D.grp_of_atom[j]];
-            if (ref >= 0) {
-                const int qs = D.qswitch0;
-                shx = pshift(x[3 * ref] - x[3 * qs], D.box[0], D.inv_box[0]);
-                shy = pshift(x[3 * ref + 1] - x[3 * qs + 1], D.box[1], D.inv_box[1]);
-                shz = pshift(x[3 * ref + 2] - x[3 * qs + 2], D.box[2], D.inv_box[2]);
-            }
+    const QSite s = q_site(D, p, nqp, qp_list, qw_list);
+    const double jx = x[3 * s.atom], jy = x[3 * s.atom + 1], jz = x[3 * s.atom + 2];
+    double shf[3];
+    q_shift<PBC>(D, x, s, qp_shift_atom, shf);
+    const bool coul_only = s.water && D.spc_water && s.site > 0;   // nbe_qspc
+    double gx = 0, gy = 0, gz = 0;
+    for (int q = 0; q < D.nqat; q++) {
+        const double vx = shf[0] - (xq[3 * q] - jx), vy = shf[1] - (xq[3 * q + 1] - jy), vz = shf[2] - (xq[3 * q + 2] - jz);
+        const double r2 = vx * vx + vy * vy + vz * vz, rinv = rinv_f64(r2);
+        double dv = 0;
+        for (int st = 0; st < nst; st++) {
+            const QPar4 pr = s.water ? D.qw_tab[(size_t)(q * nst + st) * 3 + s.site]
+                                     : D.qp_tab[(size_t)(q * nst + st) * D.nat_solute + s.atom];
+            if (coul_only) dv += -(rinv * rinv) * (pr.el * rinv) * lam[st];
+            else dv += qx_eval(r2, rinv, pr, lam[st]).dv;
         }
-        double gx = 0, gy = 0, gz = 0;
-        for (int q = 0; q < D.nqat; q++) {
-            const double vx = shx - (xq[3 * q] - jx), vy = shy - (xq[3 * q + 1] - jy), vz = shz - (xq[3 * q + 2] - jz);
-            const double r2inv = 1.0 / (vx * vx + vy * vy + vz * vz), rinv = sqrt(r2inv);
-            double dv = 0;
-            for (int s = 0; s < nst; s++) {
-                const QPar4 pr = D.qp_tab[(size_t)(q * nst + s) * D.nat_solute + j];
-                dv += qx_eval(r2inv, rinv, pr, lam[s]).dv;
-            }
-            gx += vx * dv; gy += vy * dv; gz += vz * dv;   // d(j) += vec*dv
-        }
-        grad[3 * j] += gx; grad[3 * j + 1] += gy; grad[3 * j + 2] += gz;
-    } else if (p < nqp + nqw) {
-        const int w = qw_list[p - nqp];
-        const int j0 = D.nat_solute + 3 * w;
-        double xs[3][3];
-#pragma unroll
-        for (int s = 0; s < 3; s++) { xs[s][0] = x[3 * (j0 + s)]; xs[s][1] = x[3 * (j0 + s) + 1]; xs[s][2] = x[3 * (j0 + s) + 2]; }
-        double sh3[3][3];
-#pragma unroll
-        for (int s = 0; s < 3; s++) sh3[s][0] = sh3[s][1] = sh3[s][2] = 0.0;
-        if (PBC) {
-            const int qs = D.qswitch0;
-#pragma unroll
-            for (int s = 0; s < 3; s++) {
-                // spc: one shift from x(qswitch)-x(O) (L5818-5820); general: per atom j (L5470-5472)
-                const int r = D.spc_water ? 0 : s;
-                sh3[s][0] = pshift(x[3 * qs] - xs[r][0], D.box[0], D.inv_box[0]);
-                sh3[s][1] = pshift(x[3 * qs + 1] - xs[r][1], D.box[1], D.inv_box[1]);
-                sh3[s][2] = pshift(x[3 * qs + 2] - xs[r][2], D.box[2], D.inv_box[2]);
-            }
-        }
-        double g[3][3];
-#pragma unroll
-        for (int s = 0; s < 3; s++) g[s][0] = g[s][1] = g[s][2] = 0.0;
-        for (int q = 0; q < D.nqat; q++) {
-#pragma unroll
-            for (int s = 0; s < 3; s++) {
-                const double vx = sh3[s][0] - (xq[3 * q] - xs[s][0]), vy = sh3[s][1] - (xq[3 * q + 1] - xs[s][1]),
-                             vz = sh3[s][2] - (xq[3 * q + 2] - xs[s][2]);
-                const double r2inv = 1.0 / (vx * vx + vy * vy + vz * vz), rinv = sqrt(r2inv);
-                double dv = 0;
-                for (int st = 0; st < nst; st++) {
-                    const QPar4 pr = D.qw_tab[(size_t)(q * nst + st) * 3 + s];
-                    if (D.spc_water && s > 0) dv += -r2inv * (pr.el * rinv) * lam[st];   // nbe_qspc
-                    else dv += qx_eval(r2inv, rinv, pr, lam[st]).dv;
-                }
-                g[s][0] += vx * dv; g[s][1] += vy * dv; g[s][2] += vz * dv;
-            }
-        }
-#pragma unroll
-        for (int s = 0; s < 3; s++) { grad[3 * (j0 + s)] += g[s][0]; grad[3 * (j0 + s) + 1] += g[s][1]; grad[3 * (j0 + s) + 2] += g[s][2]; }
+        gx += vx * dv; gy += vy * dv; gz += vz * dv;   // d(j) += vec*dv
     }
+    atomicAdd(&grad[3 * s.atom], gx); atomicAdd(&grad[3 * s.atom + 1], gy); atomicAdd(&grad[3 * s.atom + 2], gz);
 }
 
-// Gradient on the Q-atoms and the per-state energies EQ(:)%qp, EQ(:)%qw.  One block per Q-atom.
-template <bool PBC>
+// Gradient on the Q-atoms and the per-state energies EQ(:)%qp, EQ(:)%qw.  Block (q, slice): the partner sites
+// are dealt round-robin to gridDim.y slices so that a few dozen Q-atoms still fill the machine.
+template <bool PBC, int NS>
 __global__ void __launch_bounds__(128)
 k_q_atom(Dev D, const double *__restrict__ x, const double *__restrict__ lambda, int nqp,
          const int *__restrict__ qp_list, const int *__restrict__ qp_shift_atom, int nqw,
          const int *__restrict__ qw_list, double *__restrict__ grad, double *__restrict__ EQ) {
-    __shared__ double red[4][3 + 4 * kMaxStatesDev];
+    __shared__ double red[4][3 + 4 * NS];
     const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int nst = D.nstates;
     const int iat = D.iqseq[q];
     const double qx = x[3 * iat], qy = x[3 * iat + 1], qz = x[3 * iat + 2];
-    double lam[kMaxStatesDev], eel[kMaxStatesDev], evdw[kMaxStatesDev], wel[kMaxStatesDev], wvdw[kMaxStatesDev];
+    double lam[NS], eel[NS], evdw[NS], wel[NS], wvdw[NS];
 #pragma unroll
-    for (int s = 0; s < kMaxStatesDev; s++) { lam[s] = s < nst ? lambda[s] : 0.0; eel[s] = evdw[s] = wel[s] = wvdw[s] = 0.0; }
+    for (int s = 0; s < NS; s++) { lam[s] = s < nst ? lambda[s] : 0.0; eel[s] = evdw[s] = wel[s] = wvdw[s] = 0.0; }
     double gx = 0, gy = 0, gz = 0;
-    for (int p = tid; p < nqp; p += blockDim.x) {
-        const int j = qp_list[p];
-        double vx = x[3 * j] - qx, vy = x[3 * j + 1] - qy, vz = x[3 * j + 2] - qz;
-        if (PBC) {
-            const int ref = qp_shift_atom[D.grp_of_atom[j]];
-            if (ref >= 0) {
-                const int qs = D.qswitch0;
-                vx += pshift(x[3 * ref] - x[3 * qs], D.box[0], D.inv_box[0]);
-                vy += pshift(x[3 * ref + 1] - x[3 * qs + 1], D.box[1], D.inv_box[1]);
-                vz += pshift(x[3 * ref + 2] - x[3 * qs + 2], D.box[2], D.inv_box[2]);
-            }
-        }
-        const double r2inv = 1.0 / (vx * vx + vy * vy + vz * vz), rinv = sqrt(r2inv);
+    const int nsite = nqp + 3 * nqw;
+    for (int p = blockIdx.y * blockDim.x + tid; p < nsite; p += gridDim.y * blockDim.x) {
+        const QSite s = q_site(D, p, nqp, qp_list, qw_list);
+        double shf[3];
+        q_shift<PBC>(D, x, s, qp_shift_atom, shf);
+        const double vx = shf[0] - (qx - x[3 * s.atom]), vy = shf[1] - (qy - x[3 * s.atom + 1]), vz = shf[2] - (qz - x[3 * s.atom + 2]);
+        const double r2 = vx * vx + vy * vy + vz * vz, rinv = rinv_f64(r2);
+        const bool coul_only = s.water && D.spc_water && s.site > 0;
         double dv = 0;
 #pragma unroll
-        for (int s = 0; s < kMaxStatesDev; s++)
-            if (s < nst) {
-                const QxOut o = qx_eval(r2inv, rinv, D.qp_tab[(size_t)(q * nst + s) * D.nat_solute + j], lam[s]);
-                eel[s] += o.vel; evdw[s] += o.vvdw; dv += o.dv;
+        for (int st = 0; st < NS; st++)
+            if (st < nst) {
+                const QPar4 pr = s.water ? D.qw_tab[(size_t)(q * nst + st) * 3 + s.site]
+                                         : D.qp_tab[(size_t)(q * nst + st) * D.nat_solute + s.atom];
+                if (coul_only) {
+                    const double vel = pr.el * rinv;
+                    wel[st] += vel; dv += -(rinv * rinv) * vel * lam[st];
+                } else {
+                    const QxOut o = qx_eval(r2, rinv, pr, lam[st]);
+                    if (s.water) { wel[st] += o.vel; wvdw[st] += o.vvdw; } else { eel[st] += o.vel; evdw[st] += o.vvdw; }
+                    dv += o.dv;
+                }
             }
         gx -= vx * dv; gy -= vy * dv; gz -= vz * dv;   // d(i) -= vec*dv
     }
-    for (int p = tid; p < nqw; p += blockDim.x) {
-        const int j0 = D.nat_solute + 3 * qw_list[p];
-        double shx = 0, shy = 0, shz = 0;
-#pragma unroll
-        for (int site = 0; site < 3; site++) {
-            const double jx = x[3 * (j0 + site)], jy = x[3 * (j0 + site) + 1], jz = x[3 * (j0 + site) + 2];
-            if (PBC && (site == 0 || !D.spc_water)) {
-                const int qs = D.qswitch0;
-                shx = pshift(x[3 * qs] - jx, D.box[0], D.inv_box[0]);
-                shy = pshift(x[3 * qs + 1] - jy, D.box[1], D.inv_box[1]);
-                shz = pshift(x[3 * qs + 2] - jz, D.box[2], D.inv_box[2]);
-            }
-            const double vx = shx - (qx - jx), vy = shy - (qy - jy), vz = shz - (qz - jz);
-            const double r2inv = 1.0 / (vx * vx + vy * vy + vz * vz), rinv = sqrt(r2inv);
-            double dv = 0;
-#pragma unroll
-            for (int s = 0; s < kMaxStatesDev; s++)
-                if (s < nst) {
-                    const QPar4 pr = D.qw_tab[(size_t)(q * nst + s) * 3 + site];
-                    if (D.spc_water && site > 0) {
-                        const double vel = pr.el * rinv;   // nbe_qspc
-                        wel[s] += vel; dv += -r2inv * vel * lam[s];
-                    } else {
-                        const QxOut o = qx_eval(r2inv, rinv, pr, lam[s]);
-                        wel[s] += o.vel; wvdw[s] += o.vvdw; dv += o.dv;
-                    }
-                }
-            gx -= vx * dv; gy -= vy * dv; gz -= vz * dv;
-        }
-    }
-    // block reduction
     gx = warp_sum(gx); gy = warp_sum(gy); gz = warp_sum(gz);
 #pragma unroll
-    for (int s = 0; s < kMaxStatesDev; s++)
+    for (int s = 0; s < NS; s++)
         if (s < nst) { eel[s] = warp_sum(eel[s]); evdw[s] = warp_sum(evdw[s]); wel[s] = warp_sum(wel[s]); wvdw[s] = warp_sum(wvdw[s]); }
     if (lane == 0) {
         red[wid][0] = gx; red[wid][1] = gy; red[wid][2] = gz;
 #pragma unroll
-        for (int s = 0; s < kMaxStatesDev; s++)
+        for (int s = 0; s < NS; s++)
             if (s < nst) { red[wid][3 + 4 * s] = eel[s]; red[wid][4 + 4 * s] = evdw[s]; red[wid][5 + 4 * s] = wel[s]; red[wid][6 + 4 * s] = wvdw[s]; }
     }
     __syncthreads();
-    if (tid == 0) {
+    if (tid < 3 + 4 * nst) {
         const int nw = blockDim.x >> 5;
-        double a[3] = {0, 0, 0};
-        for (int k = 0; k < nw; k++) { a[0] += red[k][0]; a[1] += red[k][1]; a[2] += red[k][2]; }
-        grad[3 * iat] += a[0]; grad[3 * iat + 1] += a[1]; grad[3 * iat + 2] += a[2];
-        for (int s = 0; s < nst; s++) {
-            double e[4] = {0, 0, 0, 0};
-            for (int k = 0; k < nw; k++) for (int c = 0; c < 4; c++) e[c] += red[k][3 + 4 * s + c];
-            atomicAdd(&EQ[QNB_EQ_STRIDE * s + 2], e[0]); atomicAdd(&EQ[QNB_EQ_STRIDE * s + 3], e[1]);
-            atomicAdd(&EQ[QNB_EQ_STRIDE * s + 4], e[2]); atomicAdd(&EQ[QNB_EQ_STRIDE * s + 5], e[3]);
+        double a = 0;
+        for (int k = 0; k < nw; k++) a += red[k][tid];
+        if (tid < 3) atomicAdd(&grad[3 * iat + tid], a);
+        else {
+            const int s = (tid - 3) >> 2, c = (tid - 3) & 3;
+            atomicAdd(&EQ[QNB_EQ_STRIDE * s + 2 + c], a);
         }
     }
 }
@@ -554,17 +514,18 @@ __global__ void k_qq_static(int n, int nqq, const QStatic *__restrict__ lst, con
     if (k >= n) return;
     const QStatic e = lst[k];
     const double vx = x[3 * e.j] - x[3 * e.i], vy = x[3 * e.j + 1] - x[3 * e.i + 1], vz = x[3 * e.j + 2] - x[3 * e.i + 2];
-    const double r2inv = 1.0 / (vx * vx + vy * vy + vz * vz), rinv = sqrt(r2inv);
+    const double r2 = vx * vx + vy * vy + vz * vz, rinv = rinv_f64(r2), r2inv = rinv * rinv;
     const double lam = lambda[e.state];
     double vel, vvdw, dv;
     if (e.soft) {
         // nbe_qq soft pair: V_a = A*exp(-B*r), code "-nb%vdWB/r" with r holding 1/r (nonbonded.f90:140-143)
+        const double r = r2 * rinv;
         vel = e.p.el * rinv;
-        const double va = e.p.A * exp(-e.p.B / rinv);
+        const double va = e.p.A * exp(-e.p.B * r);
         vvdw = va;
-        dv = r2inv * (-vel - e.p.B * va / rinv) * lam;
+        dv = r2inv * (-vel - e.p.B * va * r) * lam;
     } else {
-        const QxOut o = qx_eval(r2inv, rinv, e.p, lam);
+        const QxOut o = qx_eval(r2, rinv, e.p, lam);
         vel = o.vel; vvdw = o.vvdw; dv = o.dv;
     }
     atomicAdd(&grad[3 * e.i], -vx * dv); atomicAdd(&grad[3 * e.i + 1], -vy * dv); atomicAdd(&grad[3 * e.i + 2], -vz * dv);
@@ -601,7 +562,7 @@ __global__ void k_lrf_taylor(Dev D, const double *__restrict__ x, const double *
             const double d2 = (a == 0) ? t0 : (a == 1) ? t1 : t2;
             df[a] = p1[a] + d2 + 0.5 * (dx * u0 + dy * u1 + dz * u2);
         }
-        grad[3 * i] -= df[0] * q; grad[3 * i + 1] -= df[1] * q; grad[3 * i + 2] -= df[2] * q;
+        atomicAdd(&grad[3 * i], -df[0] * q); atomicAdd(&grad[3 * i + 1], -df[1] * q); atomicAdd(&grad[3 * i + 2], -df[2] * q);
     }
     e = warp_sum(e);
     if ((threadIdx.x & 31) == 0 && e != 0.0) atomicAdd(&E[QNB_E_LRF], e);

@@ -118,6 +118,8 @@ __device__ __forceinline__ double rsqrt_refine(double r2, float seed) {
     return fma(y, t, y);
 }
 
+__device__ __forceinline__ double rinv_f64(double r2) { return rsqrt_refine(r2, rsqrtf((float)r2)); }
+
 // class of a unit pair and the reference's owner side.  Units: [0,ns) solute groups, then waters.
 // returns class 0 pp, 1 pw, 2 ww; owner_is_u: the reference lists the pair while looping i = u.
 __device__ __forceinline__ int pair_class(int u, int v, int ns, bool &owner_is_u) {

@@ -75,15 +75,42 @@ __global__ void k_cell_fill(int nunit, const int *__restrict__ cell_of, const in
     cell_items[cell_start[c] + p] = u;
 }
 
-// order items inside each cell by unit number so that rows come out in a run-independent order
-__global__ void k_cell_sort(int ncell, const int *__restrict__ cell_start, int *__restrict__ cell_items) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= ncell) return;
-    int lo = cell_start[c], hi = cell_start[c + 1];
-    for (int i = lo + 1; i < hi; i++) {
-        int v = cell_items[i], j = i - 1;
-        while (j >= lo && cell_items[j] > v) { cell_items[j + 1] = cell_items[j]; j--; }
-        cell_items[j + 1] = v;
+// order items inside each cell by unit number so that rows come out in a run-independent order:
+// one block per cell, rank of an item = number of smaller unit ids in the same cell
+__global__ void k_cell_sort(int ncell, const int *__restrict__ cell_start, const int *__restrict__ unsorted,
+                            int *__restrict__ cell_items) {
+    const int c = blockIdx.x;
+    const int lo = cell_start[c], hi = cell_start[c + 1];
+    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const int v = unsorted[i];
+        int rank = 0;
+        for (int j = lo; j < hi; j++) rank += unsorted[j] < v;
+        cell_items[lo + rank] = v;
+    }
+}
+
+// cell-ordered copies of what the pair searches read: switch-atom position + unit id, and the number of
+// LRF source atoms (non-Q atoms of the unit's charge group)
+__global__ void k_pack_items(Dev D, const double *__restrict__ upos, const int *__restrict__ cell_items,
+                             double4 *__restrict__ item_pos, int *__restrict__ item_nq) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= D.nunit) return;
+    const int u = cell_items[idx];
+    item_pos[idx] = make_double4(upos[3 * u], upos[3 * u + 1], upos[3 * u + 2], __longlong_as_double((long long)u));
+    item_nq[idx] = D.u_excl[u] ? 0 : D.g_nq[D.u_grp[u]];
+}
+__global__ void k_pack_sources(Dev D, const double *__restrict__ x, const int *__restrict__ cell_items,
+                               const int *__restrict__ src_off, double4 *__restrict__ src) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= D.nunit) return;
+    const int u = cell_items[idx];
+    if (D.u_excl[u]) return;
+    const int g = D.u_grp[u], gf = D.g_first[g], gn = D.g_n[g];
+    int p = src_off[idx];
+    for (int k = 0; k < gn; k++) {
+        const int i = D.g_atoms[gf + k];
+        if (D.is_q[i]) continue;
+        src[p++] = make_double4(x[3 * i], x[3 * i + 1], x[3 * i + 2], D.crg[i]);
     }
 }
 
@@ -127,7 +154,7 @@ __device__ __forceinline__ XSeg x_segments(int c, int m, int n, int periodic) {
 template <bool FILL>
 __global__ void __launch_bounds__(256)
 k_build_rows(Dev D, Cut C, Grid G, const double *__restrict__ upos, const int *__restrict__ cell_of,
-             const int *__restrict__ cell_start, const int *__restrict__ cell_items, int *__restrict__ counts,
+             const int *__restrict__ cell_start, const double4 *__restrict__ item_pos, int *__restrict__ counts,
              const int *__restrict__ row_off, uint32_t *__restrict__ rows) {
     const int lane = threadIdx.x & 31;
     const int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -157,13 +184,15 @@ k_build_rows(Dev D, Cut C, Grid G, const double *__restrict__ upos, const int *_
                     const int lo = cell_start[rowbase + xs.lo[sgi]], hi = cell_start[rowbase + xs.hi[sgi]];
                     for (int base = lo; base < hi; base += 32) {
                         const int idx = base + lane;
-                        int v = idx < hi ? cell_items[idx] : -1;
+                        double4 ip = make_double4(0, 0, 0, 0);
+                        int v = -1;
+                        if (idx < hi) { ip = item_pos[idx]; v = (int)__double_as_longlong(ip.w); }
                         bool pass = false, owner_is_u = false;
                         int cls = 0;
                         if (v >= 0 && !D.u_excl[v]) {
                             cls = pair_class(u, v, ns, owner_is_u);
                             if (!(cls == 2 && u == v) && in_shard(D, cls, owner_is_u ? u : v)) {
-                                const double pv[3] = {upos[3 * v], upos[3 * v + 1], upos[3 * v + 2]};
+                                const double pv[3] = {ip.x, ip.y, ip.z};
                                 // owner orientation (is = owner's switch atom); the value is the same either way
                                 double r2 = owner_is_u ? unit_r2(D, pu, pv) : unit_r2(D, pv, pu);
                                 pass = r2 <= C.rc2[cls];
@@ -340,11 +369,13 @@ __global__ void k_cgp_centers_only(Dev D, const double *__restrict__ x, double *
 // lrf_update (nonbondene.f90:628-725), gathered per TARGET group: the warp of target unit t sums the
 // contribution of every source atom whose unit pair (t,s) the reference sends through the LRF branch
 // (outside the class cut-off, inside RcLRF, pair owned by this shard).  20 unique moments are
-// accumulated (phi2 and phi3 are symmetric) and expanded on write.
+// accumulated (phi2 and phi3 are symmetric) and expanded on write.  FP64, no divisions:
+// field0 = q/r^3, field1 = 3 field0/r^2, field2 = -field1/r^2 from 1/r (rsqrt seed + Halley step).
 __global__ void __launch_bounds__(256)
 k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x, const double *__restrict__ upos,
                  const int *__restrict__ cell_of, const int *__restrict__ cell_start,
-                 const int *__restrict__ cell_items, double *__restrict__ lrf) {
+                 const double4 *__restrict__ item_pos, const int *__restrict__ src_off,
+                 const double4 *__restrict__ src, double *__restrict__ lrf) {
     const int lane = threadIdx.x & 31;
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (t >= D.nunit) return;
@@ -369,50 +400,55 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
             for (int sgi = 0; sgi < xs.n; sgi++) {
                 const int lo = cell_start[rowbase + xs.lo[sgi]], hi = cell_start[rowbase + xs.hi[sgi]];
                 for (int idx = lo + lane; idx < hi; idx += 32) {
-                    const int s = cell_items[idx];
-                    if (s == t || D.u_excl[s]) continue;
+                    const double4 ip = item_pos[idx];
+                    const int s = (int)__double_as_longlong(ip.w);
+                    const int a0 = src_off[idx], a1 = src_off[idx + 1];   // empty for excluded units
+                    if (s == t || a0 == a1) continue;
                     bool owner_is_t;
                     const int cls = pair_class(t, s, ns, owner_is_t);
                     if (!in_shard(D, cls, owner_is_t ? t : s)) continue;
-                    const double ps[3] = {upos[3 * s], upos[3 * s + 1], upos[3 * s + 2]};
+                    const double ps[3] = {ip.x, ip.y, ip.z};
                     const double r2u = owner_is_t ? unit_r2(D, pt, ps) : unit_r2(D, ps, pt);
                     if (r2u <= C.rc2[cls]) continue;                       // listed pair, not LRF
                     if (!(r2u <= C.rclrf2 || C.lrf_all[cls])) continue;    // beyond the LRF cut-off
                     // lrf_update(group1 = source, group2 = target)
-                    const int gsrc = D.u_grp[s];
                     double shx = 0, shy = 0, shz = 0;
                     if (D.use_PBC) {
-                        const int isw = D.g_switch[gsrc];
+                        // shift = boxlength*nint((x(cgp(group1)%iswitch) - lrf(group2)%cgp_cent)*inv_boxl)
+                        const int isw = D.g_switch[D.u_grp[s]];
                         shx = pshift(x[3 * isw] - cx_, D.box[0], D.inv_box[0]);
                         shy = pshift(x[3 * isw + 1] - cy_, D.box[1], D.inv_box[1]);
                         shz = pshift(x[3 * isw + 2] - cz_, D.box[2], D.inv_box[2]);
                     }
-                    const int gf = D.g_first[gsrc], gn = D.g_n[gsrc];
-                    for (int k = 0; k < gn; k++) {
-                        const int i = D.g_atoms[gf + k];
-                        if (D.is_q[i]) continue;
-                        const double dx = x[3 * i] - cx_ - shx, dy = x[3 * i + 1] - cy_ - shy, dz = x[3 * i + 2] - cz_ - shz;
+                    for (int k = a0; k < a1; k++) {
+                        const double4 sa = src[k];
+                        const double dx = sa.x - cx_ - shx, dy = sa.y - cy_ - shy, dz = sa.z - cz_ - shz;
                         const double r2 = dx * dx + dy * dy + dz * dz;
-                        const double f0 = D.crg[i] / (r2 * sqrt(r2));
-                        const double f1 = 3.0 * f0 / r2;
-                        const double f2 = -f1 / r2;
-                        m[0] += f0 * r2;
+                        const double ri = rinv_f64(r2), ri2 = ri * ri;
+                        const double f0 = sa.w * ri * ri2;
+                        const double f1 = 3.0 * f0 * ri2;
+                        const double f2 = -f1 * ri2;
+                        m[0] += sa.w * ri;                                 // field0*r2
                         m[1] -= dx * f0; m[2] -= dy * f0; m[3] -= dz * f0;
+                        const double tx = f1 * dx, ty = f1 * dy, tz = f1 * dz;
                         // phi2: xx xy xz yy yz zz
-                        m[4] += f1 * dx * dx - f0; m[5] += f1 * dx * dy; m[6] += f1 * dx * dz;
-                        m[7] += f1 * dy * dy - f0; m[8] += f1 * dy * dz; m[9] += f1 * dz * dz - f0;
+                        m[4] += tx * dx - f0; m[5] += tx * dy; m[6] += tx * dz;
+                        m[7] += ty * dy - f0; m[8] += ty * dz; m[9] += tz * dz - f0;
                         // phi3: xxx xxy xxz xyy xyz xzz yyy yyz yzz zzz
                         const double g5 = 5.0 * f2, gr = f2 * r2;
-                        m[10] += g5 * dx * dx * dx - 3.0 * gr * dx;
-                        m[11] += g5 * dx * dx * dy - gr * dy;
-                        m[12] += g5 * dx * dx * dz - gr * dz;
-                        m[13] += g5 * dx * dy * dy - gr * dx;
-                        m[14] += g5 * dx * dy * dz;
-                        m[15] += g5 * dx * dz * dz - gr * dx;
-                        m[16] += g5 * dy * dy * dy - 3.0 * gr * dy;
-                        m[17] += g5 * dy * dy * dz - gr * dz;
-                        m[18] += g5 * dy * dz * dz - gr * dy;
-                        m[19] += g5 * dz * dz * dz - 3.0 * gr * dz;
+                        const double ax = g5 * dx, ay = g5 * dy, az = g5 * dz;
+                        const double axx = ax * dx, axy = ax * dy, axz = ax * dz, ayy = ay * dy, ayz = ay * dz, azz = az * dz;
+                        const double gx = gr * dx, gy = gr * dy, gz = gr * dz;
+                        m[10] += axx * dx - 3.0 * gx;
+                        m[11] += axx * dy - gy;
+                        m[12] += axx * dz - gz;
+                        m[13] += axy * dy - gx;
+                        m[14] += axy * dz;
+                        m[15] += axz * dz - gx;
+                        m[16] += ayy * dy - 3.0 * gy;
+                        m[17] += ayy * dz - gz;
+                        m[18] += ayz * dz - gy;
+                        m[19] += azz * dz - 3.0 * gz;
                     }
                 }
             }
