@@ -419,8 +419,9 @@ static void launch_step_kernel(qnb_handle *h, int k, cudaStream_t cs) {
     case K_QPARTNER: {
         const int n = h->nqp + 3 * h->nqw;
         const size_t sm = sizeof(double) * (3 * (size_t)D.nqat + D.nstates);
-        if (pbc) LAUNCH_ON(h, cs, k_q_partner<true>, cdiv(n, 128), 128, sm, D, h->x.p, h->lambda.p, h->nqp, h->qp_list.p, h->qp_shift_atom.p, h->nqw, h->qw_list.p, grad);
-        else LAUNCH_ON(h, cs, k_q_partner<false>, cdiv(n, 128), 128, sm, D, h->x.p, h->lambda.p, h->nqp, h->qp_list.p, h->qp_shift_atom.p, h->nqw, h->qw_list.p, grad);
+        const dim3 pgrid(cdiv(n, 128), std::max(1, std::min(D.nqat, cdiv(6 * 148, cdiv(n, 128)))));
+        if (pbc) LAUNCH_ON(h, cs, k_q_partner<true>, pgrid, 128, sm, D, h->x.p, h->lambda.p, h->nqp, h->qp_list.p, h->qp_shift_atom.p, h->nqw, h->qw_list.p, grad);
+        else LAUNCH_ON(h, cs, k_q_partner<false>, pgrid, 128, sm, D, h->x.p, h->lambda.p, h->nqp, h->qp_list.p, h->qp_shift_atom.p, h->nqw, h->qw_list.p, grad);
         break;
     }
     case K_QATOM: {

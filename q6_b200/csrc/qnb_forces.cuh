@@ -427,7 +427,11 @@ k_q_partner(Dev D, const double *__restrict__ x, const double *__restrict__ lamb
     q_shift<PBC>(D, x, s, qp_shift_atom, shf);
     const bool coul_only = s.water && D.spc_water && s.site > 0;   // nbe_qspc
     double gx = 0, gy = 0, gz = 0;
-    for (int q = 0; q < D.nqat; q++) {
+    // the Q-atoms are dealt to gridDim.y blocks so that the few thousand partner sites still fill the machine
+    const int qchunk = (D.nqat + gridDim.y - 1) / gridDim.y;
+    const int q0 = blockIdx.y * qchunk, q1 = min(D.nqat, q0 + qchunk);
+#pragma unroll 2
+    for (int q = q0; q < q1; q++) {
         const double vx = shf[0] - (xq[3 * q] - jx), vy = shf[1] - (xq[3 * q + 1] - jy), vz = shf[2] - (xq[3 * q + 2] - jz);
         const double r2 = vx * vx + vy * vy + vz * vz, rinv = rinv_f64(r2);
         double dv = 0;

@@ -145,16 +145,19 @@ class Qnb:
         ib = np.ascontiguousarray(1.0 / b if inv_boxl is None else inv_boxl, dtype=np.float64)
         self._check(self.lib.qnb_update_box(self.h, _dp(b), _dp(ib)))
 
-    def make_pair_lists(self, x, Rq, Rcq2, RcLRF2, Rcpp2, Rcpw2, Rcww2, RcLRF=None):
-        """make_pair_lists(Rq,Rcq2,RcLRF2,Rcpp2,Rcpw2,Rcww2), nonbondene.f90:749."""
+    def make_pair_lists(self, x, Rq, Rcq2, RcLRF2, Rcpp2, Rcpw2, Rcww2, RcLRF=None, counts=True):
+        """make_pair_lists(Rq,Rcq2,RcLRF2,Rcpp2,Rcpw2,Rcww2), nonbondene.f90:749.
+
+        counts=True also returns nbpp_pair..nbqw_pair as the reference would log them under -DDUMP
+        (md.f90:1693-1695); the exact nbpp count needs a host-side expansion, so production loops pass False."""
         x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
         assert x.size == 3 * self.sys.natom
         if RcLRF is None:
             RcLRF = float(np.sqrt(RcLRF2)) if RcLRF2 >= 0 else -1.0
-        counts = np.zeros(8, np.int64)
+        out = np.zeros(8, np.int64) if counts else None
         self._check(self.lib.qnb_build_lists(self.h, _dp(x), Rq, Rcq2, RcLRF2, Rcpp2, Rcpw2, Rcww2, RcLRF,
-                                             counts.ctypes.data_as(_PL)))
-        return counts
+                                             out.ctypes.data_as(_PL) if counts else None))
+        return out
 
     def pot_energy_nonbonds(self, x, lambdas, md=True, qq=True, d=None):
         """pot_energy_nonbonds(E,EQ,md) (+ nonbond_qq/nonbond_qqp when qq): returns (d, E[7], EQ[nstates][6])."""
