@@ -1,0 +1,93 @@
+! qnb_mod.f90 -- ISO_C_BINDING interface to libqnb.so (include/qnb.h) for Qdyn6.
+!
+! NOT COMPILED IN THIS REPOSITORY'S IMAGE (no Fortran compiler is installed there); it is the
+! binding a Q6 maintainer adds to src/ and lists in the makefile before nonbondene.f90.
+! Every interface below mirrors one prototype of include/qnb.h.
+module QNB
+use, intrinsic :: iso_c_binding
+implicit none
+
+integer(c_int), parameter :: QNB_ABI_VERSION = 1
+integer(c_int), parameter :: QNB_FLAG_MD = 1, QNB_FLAG_QQ = 2
+
+! struct qnb_system (include/qnb.h) -- field order and types must match exactly
+type, bind(c) :: qnb_system
+    integer(c_int32_t) :: abi_version
+    integer(c_int32_t) :: natom, nat_solute, nwat, solv_atom, ncgp, ncgp_solute, nqat, nstates, qswitch
+    integer(c_int32_t) :: natyps, num_atyp, max_nbr_range, nexlong, n14long, nqlib, nqexpnb, nel_scale
+    integer(c_int32_t) :: iuse_switch_atom, use_PBC, use_LRF, ivdw_rule, solvent_type, qvdw_flag
+    integer(c_int32_t) :: qq_use_library_charges, ntors_gt_solute
+    real(c_double)     :: el14_scale
+    real(c_double)     :: xpcent(3)
+    real(c_double)     :: rexcl_o
+    type(c_ptr) :: cgp, cgpatom, excl, iqatom, iqseq, iac, crg, iaclib, ljcod, listex, list14, listexlong, list14long
+    type(c_ptr) :: qcrg, qiac, qavdw, qbvdw, sc_lookup, iqexpnb, jqexpnb, el_scale_iq, el_scale_jq, el_scale, qconn
+    integer(c_int32_t) :: pp_start, pp_end, pw_start, pw_end, qp_start, qp_end, ww_start, ww_end, qw_start, qw_end
+    integer(c_int32_t) :: natom_start, natom_end, is_master
+end type qnb_system
+
+interface
+    function qnb_last_error() bind(c, name='qnb_last_error') result(msg)
+        import :: c_ptr
+        type(c_ptr) :: msg
+    end function
+    function qnb_init(sys, device, handle) bind(c, name='qnb_init') result(rc)
+        import :: c_int, c_ptr, qnb_system
+        type(qnb_system), intent(in) :: sys
+        integer(c_int), value :: device
+        type(c_ptr), intent(out) :: handle
+        integer(c_int) :: rc
+    end function
+    function qnb_update_box(handle, boxlength, inv_boxl) bind(c, name='qnb_update_box') result(rc)
+        import :: c_int, c_ptr, c_double
+        type(c_ptr), value :: handle
+        real(c_double), intent(in) :: boxlength(3), inv_boxl(3)
+        integer(c_int) :: rc
+    end function
+    function qnb_build_lists(handle, x, Rq, Rcq2, RcLRF2, Rcpp2, Rcpw2, Rcww2, RcLRF, counts) &
+            bind(c, name='qnb_build_lists') result(rc)
+        import :: c_int, c_ptr, c_double
+        type(c_ptr), value :: handle
+        real(c_double), intent(in) :: x(*)                ! TYPE(qr_vec) x(natom) == 3*natom doubles
+        real(c_double), value :: Rq, Rcq2, RcLRF2, Rcpp2, Rcpw2, Rcww2, RcLRF
+        type(c_ptr), value :: counts                      ! c_null_ptr or int64(8)
+        integer(c_int) :: rc
+    end function
+    function qnb_nonbond(handle, x, lambda, flags, d, E_out, EQ_out) bind(c, name='qnb_nonbond') result(rc)
+        import :: c_int, c_ptr, c_double
+        type(c_ptr), value :: handle
+        real(c_double), intent(in) :: x(*), lambda(*)
+        integer(c_int), value :: flags
+        real(c_double), intent(inout) :: d(*)             ! added to
+        real(c_double), intent(out) :: E_out(7), EQ_out(*) ! 6*nstates
+        integer(c_int) :: rc
+    end function
+    function qnb_export_lrf(handle, lrf) bind(c, name='qnb_export_lrf') result(rc)
+        import :: c_int, c_ptr, c_double
+        type(c_ptr), value :: handle
+        real(c_double), intent(out) :: lrf(*)             ! 43*ncgp, LRF_TYPE order
+        integer(c_int) :: rc
+    end function
+    function qnb_comm_unique_id(id128) bind(c, name='qnb_comm_unique_id') result(rc)
+        import :: c_int, c_char
+        character(kind=c_char), intent(out) :: id128(128)
+        integer(c_int) :: rc
+    end function
+    function qnb_comm_init(handle, rank, nranks, id128) bind(c, name='qnb_comm_init') result(rc)
+        import :: c_int, c_ptr, c_char
+        type(c_ptr), value :: handle
+        integer(c_int), value :: rank, nranks
+        character(kind=c_char), intent(in) :: id128(128)
+        integer(c_int) :: rc
+    end function
+    function qnb_finalize(handle) bind(c, name='qnb_finalize') result(rc)
+        import :: c_int, c_ptr
+        type(c_ptr), value :: handle
+        integer(c_int) :: rc
+    end function
+end interface
+
+type(c_ptr), save :: qnb_handle = c_null_ptr
+real(c_double), allocatable, save :: qnb_EQ(:)     ! 6*nstates of the last qnb_nonbond (qq terms are added later)
+
+end module QNB

@@ -1,0 +1,149 @@
+"""The CPU oracle against the reference's own golden values and the committed fixtures (no GPU).
+
+Pinning: the reference cannot be built here, so its shipped test inputs are the anchor:
+tests/basic_tests/prep_SPH at topology coordinates must give 56 402 water pairs inside 10 A and
+E%ww%vdw = -413.17 (SPH_leap-frog_berendsen_benchmark.en row 1: lower == upper bound); the H-dependent
+step-0 numbers (EL -7.30, Q-surr. 3.12 / 139.43) are taken after the initial SHAKE and are reproduced from
+raw topology coordinates only to ~0.2 kcal/mol.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import common
+from common import golden_system, rel_rms, sorted_pairs
+
+
+def test_sph_golden_scalars():
+    from oracle.pyoracle import Oracle
+    q, cuts, lam, z = golden_system("c1_sph")
+    o = Oracle(q)
+    c = o.make_pair_lists(q.xtop, **cuts)
+    assert c[2] == 56402 * 9                      # water pairs inside 10 A
+    assert c[4] == 46 * 3 * 1117                  # nbqw: every water x every Q-atom (Rcq = 99)
+    d, E, EQ = o.pot_energy_nonbonds(q.xtop, lam)
+    assert round(E[5], 2) == -413.17              # E%ww%vdw, benchmark.en row 1 "VdW"
+    assert abs(E[4] - (-7.30)) < 0.25             # EL, post-SHAKE value
+    assert abs((EQ[0, 2] + EQ[0, 4]) - 3.12) < 0.25 and abs((EQ[0, 3] + EQ[0, 5]) - 139.43) < 0.25   # Q-surr.
+
+
+def test_pbc_golden_scalars():
+    """eval_test.sh:101: step-0 Q-surr. = -31.30 / 228.64 for the PBC test (post-SHAKE)."""
+    from oracle.pyoracle import Oracle
+    q, cuts, lam, z = golden_system("c1_pbc")
+    o = Oracle(q)
+    o.make_pair_lists(q.xtop, **cuts)
+    d, E, EQ = o.pot_energy_nonbonds(q.xtop, lam)
+    assert abs((EQ[0, 2] + EQ[0, 4]) - (-31.30)) < 0.6
+    assert abs((EQ[0, 3] + EQ[0, 5]) - 228.64) < 0.6
+
+
+@pytest.mark.parametrize("name", ["c1_sph", "c1_pbc", "c4_evb"])
+def test_oracle_matches_committed_results(name):
+    from oracle.pyoracle import Oracle
+    import sys
+    sys.path.insert(0, common.GOLDEN)
+    from make_golden import list_checksum
+    q, cuts, lam, z = golden_system(name)
+    o = Oracle(q)
+    c = o.make_pair_lists(q.xtop, **cuts)
+    assert np.array_equal(c, z["counts"])
+    d, E, EQ = o.pot_energy_nonbonds(q.xtop, lam)
+    assert np.allclose(E, z["E"], rtol=1e-12, atol=1e-9)
+    assert np.allclose(EQ, z["EQ"], rtol=1e-12, atol=1e-9)
+    assert rel_rms(d, z["d"]) < 1e-13
+    assert np.allclose(o.export_lrf(), z["lrf"], rtol=1e-11, atol=1e-12)
+    for which, nm in enumerate(common.LIST_NAMES):
+        ij, _ = o.export_list(which, 1)
+        assert np.array_equal(list_checksum(ij), z[f"sum_{nm}"]), nm
+
+
+def test_finite_difference_gradient():
+    """-dE/dx of the oracle's energies equals its gradient (no LRF: the Taylor term is a frozen field)."""
+    from oracle.pyoracle import Oracle
+    from q6_b200 import synth
+    q = synth.solvated_sphere(13.0, 7.0, 12, 2, 41, fep="evb")
+    q.use_LRF = 0
+    lam = np.array([0.3, 0.7])
+    o = Oracle(q)
+    x = q.xtop
+    o.make_pair_lists(x, **common.sph_cuts(8.0))
+    d, E, EQ = o.pot_energy_nonbonds(x, lam)
+
+    def etot(xx):
+        _, E1, EQ1 = o.pot_energy_nonbonds(xx, lam)
+        return E1.sum() + (EQ1 * lam[:, None]).sum()
+    worst = 0.0
+    for a in (0, 3, 11, 12, 40, q.nat_solute + 1, q.natom - 1):
+        for c in range(3):
+            h = 1e-5
+            xp, xm = x.copy(), x.copy()
+            xp[a, c] += h
+            xm[a, c] -= h
+            fd = (etot(xp) - etot(xm)) / (2 * h)
+            worst = max(worst, abs(fd - d[a, c]) / max(1.0, abs(d[a, c])))
+    assert worst < 1e-6
+
+
+def test_lrf_converges_to_explicit_coulomb():
+    """LRF self-consistency: for a well separated pair of neutral groups the third-order expansion at the
+    group centre reproduces the explicit Coulomb interaction energy of the far atoms."""
+    from oracle.pyoracle import Oracle
+    from q6_b200 import synth
+    q = synth.water_box(2, 3, jitter=0.0)
+    # keep two waters only
+    q.natom, q.nwat, q.ncgp = 6, 2, 2
+    q.cgp, q.cgpatom = q.cgp[:2], q.cgpatom[:6]
+    for k in ("iac", "crg", "excl", "iqatom"):
+        setattr(q, k, getattr(q, k)[:6])
+    q.use_PBC, q.use_LRF = 0, 1
+    q.xpcent = np.zeros(3)
+    q.rexcl_o = 100.0
+    q.full_shard()
+    x = q.xtop[:6].copy()
+    x[3:6] += np.array([25.0, 3.0, -2.0]) - (x[3] - x[0])      # second water 25 A away
+    o = Oracle(q)
+    o.make_pair_lists(x, Rq=1.0, Rcq2=1.0, RcLRF2=50.0 ** 2, Rcpp2=100.0, Rcpw2=100.0, Rcww2=100.0, RcLRF=50.0)
+    d, E, EQ = o.pot_energy_nonbonds(x, [1.0])
+    assert E[4] == 0.0 and E[5] == 0.0                          # nothing inside the cut-off
+    qq = q.crg[:6]
+    explicit = sum(qq[a] * qq[3 + b] / np.linalg.norm(x[a] - x[3 + b]) for a in range(3) for b in range(3))
+    # third-order Taylor expansion about the group centre: error O((d/r)^4) of a dipole-dipole term
+    assert abs(E[6] - explicit) < 5e-3 * abs(explicit) + 1e-8
+
+
+def test_make_qconn_host_port_matches_literal_recursion():
+    from oracle import pyoracle
+    from q6_b200.system import make_qconn
+    rng = np.random.default_rng(3)
+    nat, nq, ns = 60, 7, 2
+    iqseq = np.array([5, 6, 7, 20, 21, 40, 58], np.int32)
+    iqatom = np.zeros(nat, np.int32)
+    iqatom[iqseq - 1] = np.arange(1, nq + 1)
+    bonds = [(i, i + 1, 1 if i % 9 else 0) for i in range(1, nat)] + [(3, 30, 1), (10, 50, 1), (21, 45, -1)]
+    bnd = np.array(bonds, np.int32)
+    qb = np.array([[7, 25], [20, 58], [6, 40]], np.int32)
+    qc = np.array([[1, 0], [0, 2], [3, 3]], np.int32)
+    ex = np.array([[5, 9], [33, 21]], np.int32)
+    ef = np.array([[1, 1], [0, 1]], np.int32)
+    a = make_qconn(ns, nat, nq, iqseq, iqatom, bnd, qb, qc, ex, ef)
+    b = pyoracle.make_qconn(ns, nat, nq, iqseq, iqatom, bnd, qb, qc, ex, ef)
+    assert np.array_equal(a, b)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/tests"), reason="reference tree not mounted")
+def test_fixture_files_reparse_identically():
+    """The committed *_system.npz are what the readers produce from the reference's shipped files."""
+    from q6_b200.fep import load_fep
+    from q6_b200.system import build_system
+    from q6_b200.topo import topo_read
+    R = "/root/reference/tests/basic_tests/prep_SPH/"
+    t = topo_read(R + "lig_w.top")
+    assert (t.nat_pro, t.nat_solute, t.nwat, t.ncgp, t.ncgp_solute, t.natyps) == (3397, 46, 1117, 1150, 33, 93)
+    f = load_fep(R + "lig_w.fep", t)
+    assert (f.nqat, f.nstates) == (46, 1)
+    q = build_system(t, f)
+    g, _, _, _ = golden_system("c1_sph")
+    for k in ("crg", "iac", "cgp", "cgpatom", "listex", "list14", "qconn", "qcrg", "xtop"):
+        assert np.array_equal(np.asarray(getattr(q, k)), np.asarray(getattr(g, k))), k
