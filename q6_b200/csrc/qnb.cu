@@ -114,6 +114,7 @@ struct qnb_handle {
     DBuf<double> x, out /* grad[3n] | E[7] | EQ[6*nstates] */, lambda, lrf;
     double *hx = nullptr, *hout = nullptr, *hlam = nullptr;   // pinned staging
     size_t nout = 0;
+    int nE = 0;   // energies per slot: E[7] | EQ[6*nstates]; the output buffer holds kESlots partial copies
     // per-build
     Cut cut{};
     Grid grid{};
@@ -213,7 +214,8 @@ static int init_device(qnb_handle *h) {
         }
     }
     const size_t n3 = 3 * (size_t)s.natom;
-    h->nout = n3 + QNB_E_COUNT + (size_t)QNB_EQ_STRIDE * s.nstates;
+    h->nE = QNB_E_COUNT + QNB_EQ_STRIDE * s.nstates;
+    h->nout = n3 + (size_t)kESlots * h->nE;
     if (h->x.ensure(n3) || h->out.ensure(h->nout) || h->lambda.ensure(kMaxStates) ||
         h->lrf.ensure((size_t)QNB_LRF_STRIDE * std::max(s.ncgp, 1)))
         return 1;
@@ -358,7 +360,7 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
         if (nu > 0) {
             run_exclusive_scan(h, h->item_nq.p, h->src_off.p, nu);
             LAUNCH(h, k_pack_sources, cdiv(nu, 128), 128, 0, D, h->x.p, h->cell_items.p, h->src_off.p, h->src.p);
-            LAUNCH(h, k_lrf_accumulate, cdiv(nu * 32, 256), 256, 0, D, h->cut, G, h->lrf_reach, h->x.p, h->upos.p,
+            LAUNCH(h, k_lrf_accumulate, nu, 32 * kRowWarps, 0, D, h->cut, G, h->lrf_reach, h->x.p, h->upos.p,
                    h->cell_of.p, h->cell_start.p, h->item_pos.p, h->src_off.p, h->src.p, h->lrf.p);
         }
         if (h->comm) {
@@ -397,20 +399,21 @@ static bool step_kernel_active(const qnb_handle *h, int k, int flags) {
 
 static void launch_step_kernel(qnb_handle *h, int k, cudaStream_t cs) {
     const Dev &D = h->D;
-    double *grad = h->out.p, *E = h->out.p + 3 * (size_t)D.natom, *EQ = E + QNB_E_COUNT;
+    double *grad = h->out.p, *E = h->out.p + 3 * (size_t)D.natom;
+    const int nE = h->nE;
     const bool pbc = D.use_PBC, spc = D.spc_water, geom = D.geometric;
     switch (k) {
     case K_WATER: {
-        const int grid = cdiv(D.nwat * 32, 128);
-#define WCASE(P, S, G) LAUNCH_ON(h, cs, (k_water_force<P, S, G>), grid, 128, 0, D, h->x.p, h->row_off.p, h->counts.p, h->rows.p, grad, E)
+        const int grid = D.nwat;
+#define WCASE(P, S, G) LAUNCH_ON(h, cs, (k_water_force<P, S, G>), grid, 32 * kRowWarps, 0, D, h->x.p, h->row_off.p, h->counts.p, h->rows.p, grad, E, nE)
         if (pbc) { if (spc) WCASE(true, true, true); else if (geom) WCASE(true, false, true); else WCASE(true, false, false); }
         else { if (spc) WCASE(false, true, true); else if (geom) WCASE(false, false, true); else WCASE(false, false, false); }
 #undef WCASE
         break;
     }
     case K_SOLUTE: {
-        const int grid = cdiv(D.ncgp_solute * 32, 128);
-#define SCASE(P, G) LAUNCH_ON(h, cs, (k_solute_force<P, G>), grid, 128, 0, D, h->x.p, h->row_off.p, h->counts.p, h->rows.p, grad, E)
+        const int grid = D.ncgp_solute;
+#define SCASE(P, G) LAUNCH_ON(h, cs, (k_solute_force<P, G>), grid, 32 * kRowWarps, 0, D, h->x.p, h->row_off.p, h->counts.p, h->rows.p, grad, E, nE)
         if (pbc) { if (geom) SCASE(true, true); else SCASE(true, false); }
         else { if (geom) SCASE(false, true); else SCASE(false, false); }
 #undef SCASE
@@ -428,7 +431,7 @@ static void launch_step_kernel(qnb_handle *h, int k, cudaStream_t cs) {
         const int nsite = h->nqp + 3 * h->nqw;
         const int slices = std::max(1, std::min(cdiv(nsite, 128), cdiv(4 * 148, std::max(D.nqat, 1))));
         const dim3 qgrid(D.nqat, slices);
-#define QCASE(P, N) LAUNCH_ON(h, cs, (k_q_atom<P, N>), qgrid, 128, 0, D, h->x.p, h->lambda.p, h->nqp, h->qp_list.p, h->qp_shift_atom.p, h->nqw, h->qw_list.p, grad, EQ)
+#define QCASE(P, N) LAUNCH_ON(h, cs, (k_q_atom<P, N>), qgrid, 128, 0, D, h->x.p, h->lambda.p, h->nqp, h->qp_list.p, h->qp_shift_atom.p, h->nqw, h->qw_list.p, grad, E, nE)
         const int ns = D.nstates;
         if (pbc) { if (ns <= 1) QCASE(true, 1); else if (ns <= 2) QCASE(true, 2); else if (ns <= 4) QCASE(true, 4); else QCASE(true, 8); }
         else { if (ns <= 1) QCASE(false, 1); else if (ns <= 2) QCASE(false, 2); else if (ns <= 4) QCASE(false, 4); else QCASE(false, 8); }
@@ -436,10 +439,10 @@ static void launch_step_kernel(qnb_handle *h, int k, cudaStream_t cs) {
         break;
     }
     case K_QSTATIC:
-        LAUNCH_ON(h, cs, k_qq_static, cdiv(h->n_qstatic, 128), 128, 0, h->n_qstatic, h->n_qq, h->qstatic.p, h->x.p, h->lambda.p, grad, EQ);
+        LAUNCH_ON(h, cs, k_qq_static, cdiv(h->n_qstatic, 128), 128, 0, h->n_qstatic, h->n_qq, h->qstatic.p, h->x.p, h->lambda.p, grad, E, nE);
         break;
     case K_LRF:
-        LAUNCH_ON(h, cs, k_lrf_taylor, cdiv(D.natom, 128), 128, 0, D, h->x.p, h->lrf.p, grad, E);
+        LAUNCH_ON(h, cs, k_lrf_taylor, cdiv(D.natom, 128), 128, 0, D, h->x.p, h->lrf.p, grad, E, nE);
         break;
     }
 }
@@ -607,8 +610,11 @@ int qnb_nonbond(qnb_handle *h, const double *x, const double *lambda, int flags,
     h->last_h2d = (int64_t)((n3 + s.nstates) * sizeof(double));
     h->last_d2h = (int64_t)(h->nout * sizeof(double));
     for (size_t k = 0; k < n3; k++) d[k] += h->hout[k];
-    for (int k = 0; k < QNB_E_COUNT; k++) E_out[k] = h->hout[n3 + k];
-    for (int k = 0; k < QNB_EQ_STRIDE * s.nstates; k++) EQ_out[k] = h->hout[n3 + QNB_E_COUNT + k];
+    for (int k = 0; k < h->nE; k++) {
+        double e = 0;   // fixed-order sum of the partial accumulators
+        for (int sl = 0; sl < kESlots; sl++) e += h->hout[n3 + (size_t)sl * h->nE + k];
+        if (k < QNB_E_COUNT) E_out[k] = e; else EQ_out[k - QNB_E_COUNT] = e;
+    }
     return 0;
 }
 

@@ -83,14 +83,16 @@ __device__ __forceinline__ void lj_pair_f64(const double *__restrict__ ljd, int 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Water rows: ww (3x3 site tile) + the water side of pw.  One warp per water molecule.
+// Water rows: ww (3x3 site tile) + the water side of pw.  One block of kRowWarps warps per water molecule: the
+// row is dealt to the warps in chunks of 32 entries, so that a 12k-atom system still puts >12k warps in flight
+// (the kernel is latency-bound, not throughput-bound, at that size).
 template <bool PBC, bool SPC, bool GEOM>
 __global__ void __launch_bounds__(128)
 k_water_force(Dev D, const double *__restrict__ x, const int *__restrict__ row_off, const int *__restrict__ counts,
-              const uint32_t *__restrict__ rows, double *__restrict__ grad, double *__restrict__ E) {
+              const uint32_t *__restrict__ rows, double *__restrict__ grad, double *__restrict__ Eslots, int nE) {
     const int lane = threadIdx.x & 31;
-    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (w >= D.nwat) return;
+    const int w = blockIdx.x, wid = threadIdx.x >> 5;
+    const int kstart = wid * 32 + lane, kstep = kRowWarps * 32;
     const int u = D.ncgp_solute + w;
     const int nown = counts[3 * u], nmir = counts[3 * u + 1], nb = counts[3 * u + 2];
     if (nown + nmir + nb == 0) return;
@@ -110,7 +112,7 @@ k_water_force(Dev D, const double *__restrict__ x, const int *__restrict__ row_o
     double evdw = 0.0, eel = 0.0;
 
     // ---- water-water: A_own (with energies) then A_mir (forces only)
-    for (int k = lane; k < nown + nmir; k += 32) {
+    for (int k = kstart; k < nown + nmir; k += kstep) {
         const bool own = k < nown;
         const int jw = (int)(row[k] & kIdMask);
         const int j0 = D.nat_solute + 3 * jw;
@@ -154,7 +156,7 @@ k_water_force(Dev D, const double *__restrict__ x, const int *__restrict__ row_o
     }
     // ---- solute atoms acting on this water (pw, water side: gradient only)
     const uint32_t *rowb = row + nown + nmir;
-    for (int k = lane; k < nb; k += 32) {
+    for (int k = kstart; k < nb; k += kstep) {
         const int b = (int)(rowb[k] & kIdMask);
         double ux = x[3 * b] - ox, uy = x[3 * b + 1] - oy, uz = x[3 * b + 2] - oz;
         if (PBC) {
@@ -178,18 +180,27 @@ k_water_force(Dev D, const double *__restrict__ x, const int *__restrict__ row_o
             g[a][0] = fmaf(-dx, dv, g[a][0]); g[a][1] = fmaf(-dy, dv, g[a][1]); g[a][2] = fmaf(-dz, dv, g[a][2]);
         }
     }
-    // ---- FP64 cross-lane reduction, one writer per atom
+    // ---- FP64 reduction: lanes (shuffles), then warps (shared memory), one FP64 atomicAdd per component
+    __shared__ double red[kRowWarps][11];
 #pragma unroll
     for (int a = 0; a < 3; a++)
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             const double s = warp_sum((double)g[a][c]);
-            if (lane == 0) atomicAdd(&grad[3 * (i0 + a) + c], s);
+            if (lane == 0) red[wid][a * 3 + c] = s;
         }
     const double sv = warp_sum(evdw), se = warp_sum(eel);
-    if (lane == 0 && (nown > 0)) {
-        atomicAdd(&E[QNB_E_WW_VDW], sv);
-        atomicAdd(&E[QNB_E_WW_EL], se);
+    if (lane == 0) { red[wid][9] = sv; red[wid][10] = se; }
+    __syncthreads();
+    if (threadIdx.x < 11) {
+        double s = 0;
+#pragma unroll
+        for (int k = 0; k < kRowWarps; k++) s += red[k][threadIdx.x];
+        if (threadIdx.x < 9) atomicAdd(&grad[3 * i0 + threadIdx.x], s);
+        else if (nown > 0) {
+            double *E = Eslots + (size_t)(blockIdx.x & (kESlots - 1)) * nE;
+            atomicAdd(&E[threadIdx.x == 9 ? QNB_E_WW_VDW : QNB_E_WW_EL], s);
+        }
     }
 }
 
@@ -212,12 +223,13 @@ __device__ __forceinline__ int special_code(const Dev &D, int a, int b) {
 template <bool PBC, bool GEOM>
 __global__ void __launch_bounds__(128)
 k_solute_force(Dev D, const double *__restrict__ x, const int *__restrict__ row_off, const int *__restrict__ counts,
-               const uint32_t *__restrict__ rows, double *__restrict__ grad, double *__restrict__ E) {
+               const uint32_t *__restrict__ rows, double *__restrict__ grad, double *__restrict__ Eslots, int nE) {
     const int lane = threadIdx.x & 31;
-    const int gidx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (gidx >= D.ncgp_solute) return;
+    const int gidx = blockIdx.x, wid = threadIdx.x >> 5;
+    const int kstart = wid * 32 + lane, kstep = kRowWarps * 32;
+    __shared__ double red[kRowWarps][3 * kITile];
     const int nown = counts[3 * gidx], nmir = counts[3 * gidx + 1], nb = counts[3 * gidx + 2];
-    if (nown + nmir + nb == 0) return;
+    if (nown + nmir + nb == 0) return;   // block-uniform
     const uint32_t *row = rows + row_off[gidx];
     const int gf = D.g_first[gidx], gn = D.g_n[gidx];
     const int sw = D.g_switch[gidx];
@@ -251,7 +263,7 @@ k_solute_force(Dev D, const double *__restrict__ x, const int *__restrict__ row_
         for (int t = 0; t < kITile; t++) g[t][0] = g[t][1] = g[t][2] = 0.f;
 
         // ---- solute-solute partner atoms
-        for (int k = lane; k < nown + nmir; k += 32) {
+        for (int k = kstart; k < nown + nmir; k += kstep) {
             const uint32_t e = row[k];
             const bool own = k < nown;
             const int b = (int)(e & kIdMask);
@@ -304,7 +316,7 @@ k_solute_force(Dev D, const double *__restrict__ x, const int *__restrict__ row_
         }
         // ---- solute-water: this side owns the pair, all three water atoms with full LJ (nbe)
         const uint32_t *rowb = row + nown + nmir;
-        for (int k = lane; k < nb; k += 32) {
+        for (int k = kstart; k < nb; k += kstep) {
             const int jw = (int)(rowb[k] & kIdMask);
             const int j0 = D.nat_solute + 3 * jw;
             double shx = 0, shy = 0, shz = 0;
@@ -340,13 +352,31 @@ k_solute_force(Dev D, const double *__restrict__ x, const int *__restrict__ row_
 #pragma unroll
             for (int c = 0; c < 3; c++) {
                 const double s = warp_sum((double)g[t][c]);
-                if (lane == 0 && t < nt) atomicAdd(&grad[3 * ai[t] + c], s);
+                if (lane == 0) red[wid][t * 3 + c] = s;
             }
+        __syncthreads();
+        if (threadIdx.x < 3 * kITile) {
+            const int t = threadIdx.x / 3;
+            double s = 0;
+#pragma unroll
+            for (int k = 0; k < kRowWarps; k++) s += red[k][threadIdx.x];
+            int at = -1;   // ai[] is a register array: select without dynamic indexing
+#pragma unroll
+            for (int tt = 0; tt < kITile; tt++) if (tt == t) at = ai[tt];
+            if (t < nt) atomicAdd(&grad[3 * at + (threadIdx.x - 3 * t)], s);
+        }
+        __syncthreads();
     }
     const double s1 = warp_sum(e_pp_el), s2 = warp_sum(e_pp_vdw), s3 = warp_sum(e_pw_el), s4 = warp_sum(e_pw_vdw);
-    if (lane == 0) {
-        if (nown > 0) { atomicAdd(&E[QNB_E_PP_EL], s1); atomicAdd(&E[QNB_E_PP_VDW], s2); }
-        if (nb > 0) { atomicAdd(&E[QNB_E_PW_EL], s3); atomicAdd(&E[QNB_E_PW_VDW], s4); }
+    if (lane == 0) { red[wid][0] = s1; red[wid][1] = s2; red[wid][2] = s3; red[wid][3] = s4; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double s = 0;
+#pragma unroll
+        for (int k = 0; k < kRowWarps; k++) s += red[k][threadIdx.x];
+        double *E = Eslots + (size_t)(blockIdx.x & (kESlots - 1)) * nE;
+        const int idx[4] = {QNB_E_PP_EL, QNB_E_PP_VDW, QNB_E_PW_EL, QNB_E_PW_VDW};
+        if ((threadIdx.x < 2 && nown > 0) || (threadIdx.x >= 2 && nb > 0)) atomicAdd(&E[idx[threadIdx.x]], s);
     }
 }
 
@@ -452,8 +482,9 @@ template <bool PBC, int NS>
 __global__ void __launch_bounds__(128)
 k_q_atom(Dev D, const double *__restrict__ x, const double *__restrict__ lambda, int nqp,
          const int *__restrict__ qp_list, const int *__restrict__ qp_shift_atom, int nqw,
-         const int *__restrict__ qw_list, double *__restrict__ grad, double *__restrict__ EQ) {
+         const int *__restrict__ qw_list, double *__restrict__ grad, double *__restrict__ Eslots, int nE) {
     __shared__ double red[4][3 + 4 * NS];
+    double *EQ = Eslots + (size_t)((blockIdx.x + blockIdx.y) & (kESlots - 1)) * nE + QNB_E_COUNT;
     const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int nst = D.nstates;
     const int iat = D.iqseq[q];
@@ -513,8 +544,9 @@ k_q_atom(Dev D, const double *__restrict__ x, const double *__restrict__ lambda,
 // Static lists nbqq / nbqqp (nonbond_qq L5013, nonbond_qqp L5085): one thread per (pair,state) entry.
 struct QStatic { int i, j, state, soft; QPar4 p; };
 __global__ void k_qq_static(int n, int nqq, const QStatic *__restrict__ lst, const double *__restrict__ x,
-                            const double *__restrict__ lambda, double *__restrict__ grad, double *__restrict__ EQ) {
+                            const double *__restrict__ lambda, double *__restrict__ grad, double *__restrict__ Eslots, int nE) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    double *EQ = Eslots + (size_t)(k & (kESlots - 1)) * nE + QNB_E_COUNT;
     if (k >= n) return;
     const QStatic e = lst[k];
     const double vx = x[3 * e.j] - x[3 * e.i], vy = x[3 * e.j + 1] - x[3 * e.i + 1], vz = x[3 * e.j + 2] - x[3 * e.i + 2];
@@ -541,8 +573,9 @@ __global__ void k_qq_static(int n, int nqq, const QStatic *__restrict__ lst, con
 
 // lrf_taylor (nonbondene.f90:507-571)
 __global__ void k_lrf_taylor(Dev D, const double *__restrict__ x, const double *__restrict__ lrf,
-                             double *__restrict__ grad, double *__restrict__ E) {
+                             double *__restrict__ grad, double *__restrict__ Eslots, int nE) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double *E = Eslots + (size_t)(blockIdx.x & (kESlots - 1)) * nE;
     double e = 0.0;
     if (i < D.natom && i + 1 >= D.at_s && i + 1 <= D.at_e && !D.is_q[i] && (D.use_PBC || !D.excl[i])) {
         const double *l = lrf + (size_t)QNB_LRF_STRIDE * D.grp_of_atom[i];

@@ -22,6 +22,8 @@ namespace qnb {
 
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kMaxStatesDev = 8;
+constexpr int kRowWarps = 4;    // warps (of one block) that share a unit's row in the force kernels
+constexpr int kESlots = 32;     // energy accumulators are replicated to keep same-address atomics rare
 constexpr uint32_t kOwnerBit = 0x80000000u;    // this row's unit is the reference's "i" side of the pair
 constexpr uint32_t kSpecialBit = 0x40000000u;  // solute partner atom with an excluded/1-4/self relation
 constexpr uint32_t kIdMask = 0x3fffffffu;

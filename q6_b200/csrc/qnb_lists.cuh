@@ -366,109 +366,123 @@ __global__ void k_cgp_centers_only(Dev D, const double *__restrict__ x, double *
     l[0] = cx / n; l[1] = cy / n; l[2] = cz / n;
 }
 
+__constant__ int kLrfExpand[40] = {0, 1, 2, 3,
+                                   4, 5, 6, 5, 7, 8, 6, 8, 9,
+                                   10, 11, 12, 11, 13, 14, 12, 14, 15,    // n = x: (xx*, xy*, xz*)
+                                   11, 13, 14, 13, 16, 17, 14, 17, 18,    // n = y
+                                   12, 14, 15, 14, 17, 18, 15, 18, 19};   // n = z
+
 // lrf_update (nonbondene.f90:628-725), gathered per TARGET group: the warp of target unit t sums the
 // contribution of every source atom whose unit pair (t,s) the reference sends through the LRF branch
 // (outside the class cut-off, inside RcLRF, pair owned by this shard).  20 unique moments are
 // accumulated (phi2 and phi3 are symmetric) and expanded on write.  FP64, no divisions:
 // field0 = q/r^3, field1 = 3 field0/r^2, field2 = -field1/r^2 from 1/r (rsqrt seed + Halley step).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * kRowWarps)
 k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x, const double *__restrict__ upos,
                  const int *__restrict__ cell_of, const int *__restrict__ cell_start,
                  const double4 *__restrict__ item_pos, const int *__restrict__ src_off,
                  const double4 *__restrict__ src, double *__restrict__ lrf) {
-    const int lane = threadIdx.x & 31;
-    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (t >= D.nunit) return;
-    if (D.u_excl[t]) return;
+    // one block (kRowWarps warps) per target unit; the cell rows inside the LRF reach are dealt to the warps
+    __shared__ double red[kRowWarps][20];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int t = blockIdx.x;
+    if (D.u_excl[t]) return;   // block-uniform
     const int ns = D.ncgp_solute;
     const int gt = D.u_grp[t];
     double *lt = lrf + (size_t)QNB_LRF_STRIDE * gt;
     const double cx_ = lt[0], cy_ = lt[1], cz_ = lt[2];
     const double pt[3] = {upos[3 * t], upos[3 * t + 1], upos[3 * t + 2]};
-    double m[20];
+    // phi0, phi1, phi2 in FP64.  phi3 enters the field only as 1/2 dr.phi3.dr with |dr| ~ 1 A against r >= Rc, a
+    // (dr/r)^2 ~ 1e-2 correction to phi1, so it is formed and summed in FP32 (relative error ~1e-6 of itself).
+    double m[10];
+    float h[10];
 #pragma unroll
-    for (int k = 0; k < 20; k++) m[k] = 0.0;
+    for (int k = 0; k < 10; k++) { m[k] = 0.0; h[k] = 0.f; }
     const int cu = cell_of[t];
     const int cx = cu % G.n[0], cy = (cu / G.n[0]) % G.n[1], cz = cu / (G.n[0] * G.n[1]);
     const DimRange rz = dim_range(cz, reach.z, G.n[2], G.periodic), ry = dim_range(cy, reach.y, G.n[1], G.periodic);
     const XSeg xs = x_segments(cx, reach.x, G.n[0], G.periodic);
-    for (int iz = 0; iz < rz.count; iz++) {
+    const int nrow = rz.count * ry.count * xs.n;
+    for (int r = wid; r < nrow; r += kRowWarps) {
+        const int sgi = r % xs.n, iy = (r / xs.n) % ry.count, iz = r / (xs.n * ry.count);
         int z = rz.start + iz; z = (z % G.n[2] + G.n[2]) % G.n[2];
-        for (int iy = 0; iy < ry.count; iy++) {
-            int y = ry.start + iy; y = (y % G.n[1] + G.n[1]) % G.n[1];
-            const int rowbase = (z * G.n[1] + y) * G.n[0];
-            for (int sgi = 0; sgi < xs.n; sgi++) {
-                const int lo = cell_start[rowbase + xs.lo[sgi]], hi = cell_start[rowbase + xs.hi[sgi]];
-                for (int idx = lo + lane; idx < hi; idx += 32) {
-                    const double4 ip = item_pos[idx];
-                    const int s = (int)__double_as_longlong(ip.w);
-                    const int a0 = src_off[idx], a1 = src_off[idx + 1];   // empty for excluded units
-                    if (s == t || a0 == a1) continue;
-                    bool owner_is_t;
-                    const int cls = pair_class(t, s, ns, owner_is_t);
-                    if (!in_shard(D, cls, owner_is_t ? t : s)) continue;
-                    const double ps[3] = {ip.x, ip.y, ip.z};
-                    const double r2u = owner_is_t ? unit_r2(D, pt, ps) : unit_r2(D, ps, pt);
-                    if (r2u <= C.rc2[cls]) continue;                       // listed pair, not LRF
-                    if (!(r2u <= C.rclrf2 || C.lrf_all[cls])) continue;    // beyond the LRF cut-off
-                    // lrf_update(group1 = source, group2 = target)
-                    double shx = 0, shy = 0, shz = 0;
-                    if (D.use_PBC) {
-                        // shift = boxlength*nint((x(cgp(group1)%iswitch) - lrf(group2)%cgp_cent)*inv_boxl)
-                        const int isw = D.g_switch[D.u_grp[s]];
-                        shx = pshift(x[3 * isw] - cx_, D.box[0], D.inv_box[0]);
-                        shy = pshift(x[3 * isw + 1] - cy_, D.box[1], D.inv_box[1]);
-                        shz = pshift(x[3 * isw + 2] - cz_, D.box[2], D.inv_box[2]);
-                    }
-                    for (int k = a0; k < a1; k++) {
-                        const double4 sa = src[k];
-                        const double dx = sa.x - cx_ - shx, dy = sa.y - cy_ - shy, dz = sa.z - cz_ - shz;
-                        const double r2 = dx * dx + dy * dy + dz * dz;
-                        const double ri = rinv_f64(r2), ri2 = ri * ri;
-                        const double f0 = sa.w * ri * ri2;
-                        const double f1 = 3.0 * f0 * ri2;
-                        const double f2 = -f1 * ri2;
-                        m[0] += sa.w * ri;                                 // field0*r2
-                        m[1] -= dx * f0; m[2] -= dy * f0; m[3] -= dz * f0;
-                        const double tx = f1 * dx, ty = f1 * dy, tz = f1 * dz;
-                        // phi2: xx xy xz yy yz zz
-                        m[4] += tx * dx - f0; m[5] += tx * dy; m[6] += tx * dz;
-                        m[7] += ty * dy - f0; m[8] += ty * dz; m[9] += tz * dz - f0;
-                        // phi3: xxx xxy xxz xyy xyz xzz yyy yyz yzz zzz
-                        const double g5 = 5.0 * f2, gr = f2 * r2;
-                        const double ax = g5 * dx, ay = g5 * dy, az = g5 * dz;
-                        const double axx = ax * dx, axy = ax * dy, axz = ax * dz, ayy = ay * dy, ayz = ay * dz, azz = az * dz;
-                        const double gx = gr * dx, gy = gr * dy, gz = gr * dz;
-                        m[10] += axx * dx - 3.0 * gx;
-                        m[11] += axx * dy - gy;
-                        m[12] += axx * dz - gz;
-                        m[13] += axy * dy - gx;
-                        m[14] += axy * dz;
-                        m[15] += axz * dz - gx;
-                        m[16] += ayy * dy - 3.0 * gy;
-                        m[17] += ayy * dz - gz;
-                        m[18] += ayz * dz - gy;
-                        m[19] += azz * dz - 3.0 * gz;
-                    }
-                }
+        int y = ry.start + iy; y = (y % G.n[1] + G.n[1]) % G.n[1];
+        const int rowbase = (z * G.n[1] + y) * G.n[0];
+        const int lo = cell_start[rowbase + (sgi == 0 ? xs.lo[0] : xs.lo[1])];
+        const int hi = cell_start[rowbase + (sgi == 0 ? xs.hi[0] : xs.hi[1])];
+        for (int idx = lo + lane; idx < hi; idx += 32) {
+            const double4 ip = item_pos[idx];
+            const int s = (int)__double_as_longlong(ip.w);
+            const int a0 = src_off[idx], a1 = src_off[idx + 1];   // empty for excluded units
+            if (s == t || a0 == a1) continue;
+            bool owner_is_t;
+            const int cls = pair_class(t, s, ns, owner_is_t);
+            if (!in_shard(D, cls, owner_is_t ? t : s)) continue;
+            const double ps[3] = {ip.x, ip.y, ip.z};
+            const double r2u = owner_is_t ? unit_r2(D, pt, ps) : unit_r2(D, ps, pt);
+            if (r2u <= C.rc2[cls]) continue;                       // listed pair, not LRF
+            if (!(r2u <= C.rclrf2 || C.lrf_all[cls])) continue;    // beyond the LRF cut-off
+            // lrf_update(group1 = source, group2 = target): dr = x(i) - cgp_cent(target) - shift
+            double ox = cx_, oy = cy_, oz = cz_;
+            if (D.use_PBC) {
+                // shift = boxlength*nint((x(cgp(group1)%iswitch) - lrf(group2)%cgp_cent)*inv_boxl)
+                const int isw = D.g_switch[D.u_grp[s]];
+                ox += pshift(x[3 * isw] - cx_, D.box[0], D.inv_box[0]);
+                oy += pshift(x[3 * isw + 1] - cy_, D.box[1], D.inv_box[1]);
+                oz += pshift(x[3 * isw + 2] - cz_, D.box[2], D.inv_box[2]);
+            }
+            for (int k = a0; k < a1; k++) {
+                const double4 sa = src[k];
+                const double dx = sa.x - ox, dy = sa.y - oy, dz = sa.z - oz;
+                const double r2 = dx * dx + dy * dy + dz * dz;
+                const float rif = rsqrtf((float)r2);
+                const double ri = rsqrt_refine(r2, rif), ri2 = ri * ri;
+                const double f0 = sa.w * ri * ri2;      // field0 = q/r^3
+                const double f1 = 3.0 * f0 * ri2;       // field1 = 3 field0/r^2
+                m[0] += sa.w * ri;                      // phi0 += field0*r2
+                m[1] -= dx * f0; m[2] -= dy * f0; m[3] -= dz * f0;
+                const double tx = f1 * dx, ty = f1 * dy, tz = f1 * dz;
+                // phi2: xx xy xz yy yz zz
+                m[4] += tx * dx - f0; m[5] += tx * dy; m[6] += tx * dz;
+                m[7] += ty * dy - f0; m[8] += ty * dz; m[9] += tz * dz - f0;
+                // phi3 (FP32): field2 = -field1/r^2 = -3 q / r^7; xxx xxy xxz xyy xyz xzz yyy yyz yzz zzz
+                const float fx = (float)dx, fy = (float)dy, fz = (float)dz;
+                const float rif2 = rif * rif, rif4 = rif2 * rif2;
+                const float f2 = -3.0f * (float)sa.w * rif * rif2 * rif4;
+                const float g5 = 5.0f * f2, gr = f2 * (fx * fx + fy * fy + fz * fz);
+                const float ax = g5 * fx, ay = g5 * fy, az = g5 * fz;
+                const float axx = ax * fx, axy = ax * fy, axz = ax * fz, ayy = ay * fy, ayz = ay * fz, azz = az * fz;
+                const float gx = gr * fx, gy = gr * fy, gz = gr * fz;
+                h[0] += axx * fx - 3.0f * gx;
+                h[1] += axx * fy - gy;
+                h[2] += axx * fz - gz;
+                h[3] += axy * fy - gx;
+                h[4] += axy * fz;
+                h[5] += axz * fz - gx;
+                h[6] += ayy * fy - 3.0f * gy;
+                h[7] += ayy * fz - gz;
+                h[8] += ayz * fz - gy;
+                h[9] += azz * fz - 3.0f * gz;
             }
         }
     }
 #pragma unroll
-    for (int k = 0; k < 20; k++) m[k] = warp_sum(m[k]);
-    if (lane == 0) {
-        lt[3] = m[0];
-        lt[4] = m[1]; lt[5] = m[2]; lt[6] = m[3];
-        // phi2(a)%b
-        lt[7] = m[4]; lt[8] = m[5]; lt[9] = m[6];
-        lt[10] = m[5]; lt[11] = m[7]; lt[12] = m[8];
-        lt[13] = m[6]; lt[14] = m[8]; lt[15] = m[9];
-        // phi3(3*(n-1)+j)%k = T[n][j][k]
-        const int ix[27] = {10, 11, 12, 11, 13, 14, 12, 14, 15,    // n = x: (xx*, xy*, xz*)
-                            11, 13, 14, 13, 16, 17, 14, 17, 18,    // n = y
-                            12, 14, 15, 14, 17, 18, 15, 18, 19};   // n = z
+    for (int k = 0; k < 10; k++) {
+        const double a = warp_sum(m[k]), bsum = warp_sum((double)h[k]);
+        if (lane == 0) { red[wid][k] = a; red[wid][10 + k] = bsum; }
+    }
+    __syncthreads();
+    __shared__ double mm[20];
+    if (threadIdx.x < 20) {
+        double a = 0;
 #pragma unroll
-        for (int k = 0; k < 27; k++) lt[16 + k] = m[ix[k]];
+        for (int k = 0; k < kRowWarps; k++) a += red[k][threadIdx.x];
+        mm[threadIdx.x] = a;
+    }
+    __syncthreads();
+    if (threadIdx.x < 40) {
+        // LRF_TYPE order after cgp_cent: phi0, phi1(3), phi2(a)%b (9), phi3(3*(n-1)+j)%k (27) from the unique moments
+        lt[3 + threadIdx.x] = mm[kLrfExpand[threadIdx.x]];
     }
 }
 
