@@ -392,12 +392,16 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
     double *lt = lrf + (size_t)QNB_LRF_STRIDE * gt;
     const double cx_ = lt[0], cy_ = lt[1], cz_ = lt[2];
     const double pt[3] = {upos[3 * t], upos[3 * t + 1], upos[3 * t + 2]};
-    // phi0, phi1, phi2 in FP64.  phi3 enters the field only as 1/2 dr.phi3.dr with |dr| ~ 1 A against r >= Rc, a
-    // (dr/r)^2 ~ 1e-2 correction to phi1, so it is formed and summed in FP32 (relative error ~1e-6 of itself).
-    double m[10];
-    float h[10];
+    // phi0 and phi1 in FP64.  phi2 and phi3 enter potential and field only through dr.phi2.dr, phi2.dr and
+    // dr.phi3.dr with |dr| ~ 1 A (atom to group centre) against r >= Rc: corrections of relative size dr/r ~ 0.1 and
+    // (dr/r)^2 ~ 0.01 to the phi1 terms, so they are formed and summed in FP32 (relative error ~1e-6 of
+    // themselves, <= 1e-7 of the LRF energy and field).
+    double m[4];
+    float h[16];
 #pragma unroll
-    for (int k = 0; k < 10; k++) { m[k] = 0.0; h[k] = 0.f; }
+    for (int k = 0; k < 4; k++) m[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) h[k] = 0.f;
     const int cu = cell_of[t];
     const int cx = cu % G.n[0], cy = (cu / G.n[0]) % G.n[1], cz = cu / (G.n[0] * G.n[1]);
     const DimRange rz = dim_range(cz, reach.z, G.n[2], G.periodic), ry = dim_range(cy, reach.y, G.n[1], G.periodic);
@@ -438,17 +442,16 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
                 const float rif = rsqrtf((float)r2);
                 const double ri = rsqrt_refine(r2, rif), ri2 = ri * ri;
                 const double f0 = sa.w * ri * ri2;      // field0 = q/r^3
-                const double f1 = 3.0 * f0 * ri2;       // field1 = 3 field0/r^2
                 m[0] += sa.w * ri;                      // phi0 += field0*r2
                 m[1] -= dx * f0; m[2] -= dy * f0; m[3] -= dz * f0;
-                const double tx = f1 * dx, ty = f1 * dy, tz = f1 * dz;
-                // phi2: xx xy xz yy yz zz
-                m[4] += tx * dx - f0; m[5] += tx * dy; m[6] += tx * dz;
-                m[7] += ty * dy - f0; m[8] += ty * dz; m[9] += tz * dz - f0;
-                // phi3 (FP32): field2 = -field1/r^2 = -3 q / r^7; xxx xxy xxz xyy xyz xzz yyy yyz yzz zzz
-                const float fx = (float)dx, fy = (float)dy, fz = (float)dz;
-                const float rif2 = rif * rif, rif4 = rif2 * rif2;
-                const float f2 = -3.0f * (float)sa.w * rif * rif2 * rif4;
+                // phi2 (FP32): field1 = 3 q/r^5; xx xy xz yy yz zz
+                const float fx = (float)dx, fy = (float)dy, fz = (float)dz, qf = (float)sa.w;
+                const float rif2 = rif * rif, f0f = qf * rif * rif2, f1f = 3.0f * f0f * rif2;
+                const float tx = f1f * fx, ty = f1f * fy, tz = f1f * fz;
+                h[10] += tx * fx - f0f; h[11] += tx * fy; h[12] += tx * fz;
+                h[13] += ty * fy - f0f; h[14] += ty * fz; h[15] += tz * fz - f0f;
+                // phi3 (FP32): field2 = -field1/r^2 = -3 q/r^7; xxx xxy xxz xyy xyz xzz yyy yyz yzz zzz
+                const float f2 = -f1f * rif2;
                 const float g5 = 5.0f * f2, gr = f2 * (fx * fx + fy * fy + fz * fz);
                 const float ax = g5 * fx, ay = g5 * fy, az = g5 * fz;
                 const float axx = ax * fx, axy = ax * fy, axz = ax * fz, ayy = ay * fy, ayz = ay * fz, azz = az * fz;
@@ -466,11 +469,13 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
             }
         }
     }
+    // red[.][0..3] = phi0, phi1; [4..9] = phi2 unique; [10..19] = phi3 unique
 #pragma unroll
-    for (int k = 0; k < 10; k++) {
-        const double a = warp_sum(m[k]), bsum = warp_sum((double)h[k]);
-        if (lane == 0) { red[wid][k] = a; red[wid][10 + k] = bsum; }
-    }
+    for (int k = 0; k < 4; k++) { const double a = warp_sum(m[k]); if (lane == 0) red[wid][k] = a; }
+#pragma unroll
+    for (int k = 0; k < 6; k++) { const double a = warp_sum((double)h[10 + k]); if (lane == 0) red[wid][4 + k] = a; }
+#pragma unroll
+    for (int k = 0; k < 10; k++) { const double a = warp_sum((double)h[k]); if (lane == 0) red[wid][10 + k] = a; }
     __syncthreads();
     __shared__ double mm[20];
     if (threadIdx.x < 20) {
