@@ -202,6 +202,7 @@ def main():
         _, E, EQ = g.pot_energy_nonbonds(x, lam, d=d)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
+    host_breakdown = g.last_timing()
     h2d, d2h = g.last_copy_bytes()
     h2d_step = h2d + (3 * q.natom * 8) / NBCYCLE   # + the list build's coordinate upload, amortised
     if proc is not None:
@@ -263,7 +264,8 @@ def main():
                 "ns_per_day_device_resident": 86400.0 / t_step * DT_FS * 1e-6,
                 "fep_windows_per_hour": world * 3600.0 / (STEPS_PER_WINDOW * e2e_step),
                 "e2e": {"value": npairs * world / e2e_step, "unit": "pairs/s", "ms_per_step": e2e_step * 1e3,
-                        "h2d_bytes_per_step": int(h2d_step), "d2h_bytes_per_step": int(d2h)},
+                        "h2d_bytes_per_step": int(h2d_step), "d2h_bytes_per_step": int(d2h),
+                        "host_breakdown_last_call_us": {k: round(v * 1e6, 1) for k, v in host_breakdown.items()}},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1

@@ -222,6 +222,9 @@ int qnb_bench_kernels(qnb_handle *h, const double *lambda, int flags, int reps, 
                       char *names_out, int names_cap, float *ms_out, int ms_cap);
 /* Kernel launches issued by this handle since creation. */
 int64_t qnb_launch_count(qnb_handle *h);
+/* Host-side seconds of the last qnb_nonbond: staging x into pinned memory, issuing the step (graph launch),
+ * waiting for the device (H2D + kernels + D2H), adding d / summing energies. */
+int qnb_last_timing(qnb_handle *h, double out[4]);
 /* Bytes copied host->device / device->host by the last qnb_nonbond call. */
 int qnb_last_copy_bytes(qnb_handle *h, int64_t *h2d, int64_t *d2h);
 

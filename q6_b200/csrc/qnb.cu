@@ -4,6 +4,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -124,7 +125,10 @@ struct qnb_handle {
         qp_shift_atom;
     DBuf<uint32_t> rows;
     DBuf<double4> item_pos, src;
-    DBuf<int> cell_unsorted, item_nq, src_off;
+    DBuf<int> cell_unsorted, item_nq, src_off, pk_atom, pk_ct;
+    DBuf<float> pk_q;
+    DBuf<double> pk_qd, px, py, pz;
+    int npk = 0;   // packed atoms: non-Q atoms of non-excluded units in cell order
     int nqp = 0, nqw = 0;
     bool qp_done = false, qw_done = false, lists_built = false;
     int64_t total_rows = 0;
@@ -135,6 +139,7 @@ struct qnb_handle {
     int rank = 0, nranks = 1;
     // stats
     int64_t launches = 0, last_h2d = 0, last_d2h = 0;
+    double t_stage_in = 0, t_issue = 0, t_wait = 0, t_add_out = 0;   // host-side seconds of the last qnb_nonbond
     DBuf<char> flush;
     int last_flags = 0;
 };
@@ -308,7 +313,10 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
         h->qp_list.ensure(std::max(D.nat_solute, 1)) || h->qw_list.ensure(std::max(D.nwat, 1)) ||
         h->qp_shift_atom.ensure(std::max(D.ncgp_solute, 1)) || h->item_pos.ensure(std::max(nu, 1)) ||
         h->src.ensure(std::max(D.natom, 1)) || h->cell_unsorted.ensure(std::max(nu, 1)) ||
-        h->item_nq.ensure(std::max(nu, 1) + 1) || h->src_off.ensure(std::max(nu, 1) + 2))
+        h->item_nq.ensure(std::max(nu, 1) + 1) || h->src_off.ensure(std::max(nu, 1) + 2) ||
+        h->pk_atom.ensure(std::max(D.natom, 1)) || h->pk_ct.ensure(std::max(D.natom, 1)) || h->pk_q.ensure(std::max(D.natom, 1)) ||
+        h->pk_qd.ensure(std::max(D.natom, 1)) || h->px.ensure(std::max(D.natom, 1)) || h->py.ensure(std::max(D.natom, 1)) ||
+        h->pz.ensure(std::max(D.natom, 1)))
         return 1;
     const bool md_lists = true;
     if (nu > 0 && md_lists) {
@@ -319,17 +327,21 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
         LAUNCH(h, k_cell_fill, cdiv(nu, 256), 256, 0, nu, h->cell_of.p, h->cell_start.p, h->cell_count.p, h->cell_unsorted.p);
         LAUNCH(h, k_cell_sort, G.ncell, 64, 0, G.ncell, h->cell_start.p, h->cell_unsorted.p, h->cell_items.p);
         LAUNCH(h, k_pack_items, cdiv(nu, 256), 256, 0, D, h->upos.p, h->cell_items.p, h->item_pos.p, h->item_nq.p);
+        run_exclusive_scan(h, h->item_nq.p, h->src_off.p, nu);
+        LAUNCH(h, k_pack_atoms, cdiv(nu, 128), 128, 0, D, h->cell_items.p, h->src_off.p, h->pk_atom.p, h->pk_q.p, h->pk_qd.p, h->pk_ct.p);
         LAUNCH(h, k_build_rows<false>, cdiv(nu * 32, 256), 256, 0, D, h->cut, G, h->upos.p, h->cell_of.p, h->cell_start.p,
-               h->item_pos.p, h->counts.p, (const int *)nullptr, (uint32_t *)nullptr);
+               h->item_pos.p, h->src_off.p, h->counts.p, (const int *)nullptr, (uint32_t *)nullptr);
         LAUNCH(h, k_row_totals, cdiv(nu, 256), 256, 0, nu, h->counts.p, h->row_tot.p);
         run_exclusive_scan(h, h->row_tot.p, h->row_off.p, nu);
-        int total = 0;
+        int total = 0, npk = 0;
         CU(cudaMemcpyAsync(&total, h->row_off.p + nu, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+        CU(cudaMemcpyAsync(&npk, h->src_off.p + nu, sizeof(int), cudaMemcpyDeviceToHost, h->st));
         CU(cudaStreamSynchronize(h->st));
         h->total_rows = total;
+        h->npk = npk;
         if (h->rows.ensure((size_t)std::max(total, 1))) return 1;
         LAUNCH(h, k_build_rows<true>, cdiv(nu * 32, 256), 256, 0, D, h->cut, G, h->upos.p, h->cell_of.p, h->cell_start.p,
-               h->item_pos.p, h->counts.p, h->row_off.p, h->rows.p);
+               h->item_pos.p, h->src_off.p, h->counts.p, h->row_off.p, h->rows.p);
     }
     // Q-atom partner lists: built once when the cut-off covers everything (nbqplist L3678, nbqwlist L3889,
     // nbqplist_box L3780, nbqwlist_box L3972)
@@ -358,8 +370,7 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
     if (D.use_LRF && D.ncgp > 0) {
         LAUNCH(h, k_cgp_centers, cdiv(D.ncgp, 128), 128, 0, D, h->x.p, h->lrf.p);
         if (nu > 0) {
-            run_exclusive_scan(h, h->item_nq.p, h->src_off.p, nu);
-            LAUNCH(h, k_pack_sources, cdiv(nu, 128), 128, 0, D, h->x.p, h->cell_items.p, h->src_off.p, h->src.p);
+            if (h->npk > 0) LAUNCH(h, k_pack_sources, cdiv(h->npk, 256), 256, 0, h->npk, h->pk_atom.p, h->x.p, h->crg.p, h->src.p);
             LAUNCH(h, k_lrf_accumulate, nu, 32 * kRowWarps, 0, D, h->cut, G, h->lrf_reach, h->x.p, h->upos.p,
                    h->cell_of.p, h->cell_start.p, h->item_pos.p, h->src_off.p, h->src.p, h->lrf.p);
         }
@@ -405,7 +416,7 @@ static void launch_step_kernel(qnb_handle *h, int k, cudaStream_t cs) {
     switch (k) {
     case K_WATER: {
         const int grid = D.nwat;
-#define WCASE(P, S, G) LAUNCH_ON(h, cs, (k_water_force<P, S, G>), grid, 32 * kRowWarps, 0, D, h->x.p, h->row_off.p, h->counts.p, h->rows.p, grad, E, nE)
+#define WCASE(P, S, G) LAUNCH_ON(h, cs, (k_water_force<P, S, G>), grid, 32 * kRowWarps, 0, D, h->x.p, h->px.p, h->py.p, h->pz.p, h->pk_q.p, h->pk_ct.p, h->pk_atom.p, h->row_off.p, h->counts.p, h->rows.p, grad, E, nE)
         if (pbc) { if (spc) WCASE(true, true, true); else if (geom) WCASE(true, false, true); else WCASE(true, false, false); }
         else { if (spc) WCASE(false, true, true); else if (geom) WCASE(false, false, true); else WCASE(false, false, false); }
 #undef WCASE
@@ -413,7 +424,7 @@ static void launch_step_kernel(qnb_handle *h, int k, cudaStream_t cs) {
     }
     case K_SOLUTE: {
         const int grid = D.ncgp_solute;
-#define SCASE(P, G) LAUNCH_ON(h, cs, (k_solute_force<P, G>), grid, 32 * kRowWarps, 0, D, h->x.p, h->row_off.p, h->counts.p, h->rows.p, grad, E, nE)
+#define SCASE(P, G) LAUNCH_ON(h, cs, (k_solute_force<P, G>), grid, 32 * kRowWarps, 0, D, h->x.p, h->px.p, h->py.p, h->pz.p, h->pk_q.p, h->pk_qd.p, h->pk_ct.p, h->pk_atom.p, h->row_off.p, h->counts.p, h->rows.p, grad, E, nE)
         if (pbc) { if (geom) SCASE(true, true); else SCASE(true, false); }
         else { if (geom) SCASE(false, true); else SCASE(false, false); }
 #undef SCASE
@@ -453,6 +464,8 @@ static const int kStreamOf[K_COUNT] = {0, 1, 2, 2, -1, -1};   // aux stream inde
 
 static int issue_step(qnb_handle *h, int flags) {
     CU(cudaMemsetAsync(h->out.p, 0, h->nout * sizeof(double), h->st));
+    if ((flags & QNB_FLAG_MD) && h->npk > 0)
+        LAUNCH(h, k_pack_coords, cdiv(h->npk, 256), 256, 0, h->npk, h->pk_atom.p, h->x.p, h->px.p, h->py.p, h->pz.p);
     CU(cudaEventRecord(h->ev_fork, h->st));
     bool used[3] = {false, false, false};
     for (int k = 0; k < K_COUNT; k++) {
@@ -601,12 +614,17 @@ int qnb_nonbond(qnb_handle *h, const double *x, const double *lambda, int flags,
     CU(cudaSetDevice(h->device));
     const qnb_system &s = h->T.s;
     const size_t n3 = 3 * (size_t)s.natom;
+    using clk = std::chrono::steady_clock;
+    const auto t0 = clk::now();
     memcpy(h->hx, x, n3 * sizeof(double));
     for (int k = 0; k < s.nstates; k++) h->hlam[k] = lambda[k];
     h->last_flags = flags;
+    const auto t1 = clk::now();
     if (step_device(h, flags, true)) return 1;
+    const auto t2 = clk::now();
     CU(cudaStreamSynchronize(h->st));
     CU(cudaGetLastError());
+    const auto t3 = clk::now();
     h->last_h2d = (int64_t)((n3 + s.nstates) * sizeof(double));
     h->last_d2h = (int64_t)(h->nout * sizeof(double));
     for (size_t k = 0; k < n3; k++) d[k] += h->hout[k];
@@ -615,6 +633,15 @@ int qnb_nonbond(qnb_handle *h, const double *x, const double *lambda, int flags,
         for (int sl = 0; sl < kESlots; sl++) e += h->hout[n3 + (size_t)sl * h->nE + k];
         if (k < QNB_E_COUNT) E_out[k] = e; else EQ_out[k - QNB_E_COUNT] = e;
     }
+    const auto t4 = clk::now();
+    auto sec = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+    h->t_stage_in = sec(t0, t1); h->t_issue = sec(t1, t2); h->t_wait = sec(t2, t3); h->t_add_out = sec(t3, t4);
+    return 0;
+}
+
+int qnb_last_timing(qnb_handle *h, double out[4]) {
+    if (!h || !out) return fail("null argument");
+    out[0] = h->t_stage_in; out[1] = h->t_issue; out[2] = h->t_wait; out[3] = h->t_add_out;
     return 0;
 }
 
@@ -673,11 +700,13 @@ static int export_impl(qnb_handle *h, int which, int state, int32_t *ij, double 
         if (h->total_rows) CU(cudaMemcpy(rows.data(), h->rows.p, sizeof(uint32_t) * h->total_rows, cudaMemcpyDeviceToHost));
     }
     const int ns = s.ncgp_solute, sa = s.solv_atom;
+    std::vector<int> pk(std::max(h->npk, 1));   // row entries are packed atom indices
+    if (h->npk) CU(cudaMemcpy(pk.data(), h->pk_atom.p, sizeof(int) * h->npk, cudaMemcpyDeviceToHost));
     if (which == QNB_LIST_WW) {
         for (int u = ns; u < nu; u++) {
             const int iw = u - ns;
             for (int k = 0; k < counts[3 * u]; k++) {
-                const int jw = (int)(rows[off[u] + k] & kIdMask);
+                const int jw = (pk[rows[off[u] + k] & kIdMask] - s.nat_solute) / sa;
                 for (int la = 0; la < sa; la++)
                     for (int ka = 0; ka < sa; ka++)
                         if (!emit(s.nat_solute + sa * iw + la + 1, s.nat_solute + sa * jw + ka + 1, T.ww_par[la * sa + ka]))
@@ -688,7 +717,7 @@ static int export_impl(qnb_handle *h, int which, int state, int32_t *ij, double 
         for (int g = 0; g < ns; g++) {
             const uint32_t *rb = rows.data() + off[g] + counts[3 * g] + counts[3 * g + 1];
             for (int k = 0; k < counts[3 * g + 2]; k++) {
-                const int jw = (int)(rb[k] & kIdMask);
+                const int jw = (pk[rb[k] & kIdMask] - s.nat_solute) / sa;
                 for (int m = 0; m < T.g_n[g]; m++) {
                     const int i = T.g_atoms[T.g_first[g] + m];
                     if (T.is_q[i]) continue;
@@ -704,7 +733,7 @@ static int export_impl(qnb_handle *h, int which, int state, int32_t *ij, double 
                 const int i = T.g_atoms[T.g_first[g] + m];
                 if (T.is_q[i]) continue;
                 for (int k = 0; k < counts[3 * g]; k++) {
-                    const int j = (int)(ra[k] & kIdMask);
+                    const int j = pk[ra[k] & kIdMask];
                     if (T.grp_of_atom[j] == g && i >= j) continue;   // count once inside a group (L1874)
                     QPar p;
                     bool set;
@@ -879,6 +908,7 @@ int qnb_bench_kernels(qnb_handle *h, const double *lambda, int flags, int reps, 
     cudaMemcpyAsync(h->lambda.p, h->hlam, h->T.s.nstates * sizeof(double), cudaMemcpyHostToDevice, h->st);
     std::string names;
     int n = 0;
+    if (h->npk > 0) LAUNCH(h, k_pack_coords, cdiv(h->npk, 256), 256, 0, h->npk, h->pk_atom.p, h->x.p, h->px.p, h->py.p, h->pz.p);
     for (int k = 0; k < K_COUNT; k++) {
         if (!step_kernel_active(h, k, flags)) continue;
         if (n >= ms_cap) break;
@@ -929,6 +959,7 @@ int qnb_finalize(qnb_handle *h) {
     h->cell_of.release(); h->cell_count.release(); h->cell_start.release(); h->cell_items.release(); h->counts.release();
     h->row_tot.release(); h->row_off.release(); h->flag.release(); h->pos.release(); h->qp_list.release();
     h->qw_list.release(); h->qp_shift_atom.release(); h->rows.release(); h->flush.release();
+    h->pk_atom.release(); h->pk_ct.release(); h->pk_q.release(); h->pk_qd.release(); h->px.release(); h->py.release(); h->pz.release();
     h->item_pos.release(); h->src.release(); h->cell_unsorted.release(); h->item_nq.release(); h->src_off.release();
     if (h->hx) cudaFreeHost(h->hx);
     if (h->hout) cudaFreeHost(h->hout);

@@ -88,7 +88,9 @@ __device__ __forceinline__ void lj_pair_f64(const double *__restrict__ ljd, int 
 // (the kernel is latency-bound, not throughput-bound, at that size).
 template <bool PBC, bool SPC, bool GEOM>
 __global__ void __launch_bounds__(128)
-k_water_force(Dev D, const double *__restrict__ x, const int *__restrict__ row_off, const int *__restrict__ counts,
+k_water_force(Dev D, const double *__restrict__ x, const double *__restrict__ px, const double *__restrict__ py,
+              const double *__restrict__ pz, const float *__restrict__ pk_q, const int *__restrict__ pk_ct,
+              const int *__restrict__ pk_atom, const int *__restrict__ row_off, const int *__restrict__ counts,
               const uint32_t *__restrict__ rows, double *__restrict__ grad, double *__restrict__ Eslots, int nE) {
     const int lane = threadIdx.x & 31;
     const int w = blockIdx.x, wid = threadIdx.x >> 5;
@@ -114,23 +116,21 @@ k_water_force(Dev D, const double *__restrict__ x, const int *__restrict__ row_o
     // ---- water-water: A_own (with energies) then A_mir (forces only)
     for (int k = kstart; k < nown + nmir; k += kstep) {
         const bool own = k < nown;
-        const int jw = (int)(row[k] & kIdMask);
-        const int j0 = D.nat_solute + 3 * jw;
+        const int p0 = (int)(row[k] & kIdMask);   // packed index of the partner's oxygen
         double ud[3][3];
         {
             double shx = 0, shy = 0, shz = 0;
-            const double jx = x[3 * j0], jy = x[3 * j0 + 1], jz = x[3 * j0 + 2];
             if (PBC) {
                 // one shift per molecule pair from the O-O vector (nonbond_ww_spc_box L6016-6017)
-                shx = pshift(ox - jx, D.box[0], D.inv_box[0]);
-                shy = pshift(oy - jy, D.box[1], D.inv_box[1]);
-                shz = pshift(oz - jz, D.box[2], D.inv_box[2]);
+                shx = pshift(ox - px[p0], D.box[0], D.inv_box[0]);
+                shy = pshift(oy - py[p0], D.box[1], D.inv_box[1]);
+                shz = pshift(oz - pz[p0], D.box[2], D.inv_box[2]);
             }
 #pragma unroll
             for (int b = 0; b < 3; b++) {
-                ud[b][0] = (x[3 * (j0 + b)] - ox) + shx;
-                ud[b][1] = (x[3 * (j0 + b) + 1] - oy) + shy;
-                ud[b][2] = (x[3 * (j0 + b) + 2] - oz) + shz;
+                ud[b][0] = (px[p0 + b] - ox) + shx;
+                ud[b][1] = (py[p0 + b] - oy) + shy;
+                ud[b][2] = (pz[p0 + b] - oz) + shz;
             }
         }
         float uf[3][3];
@@ -157,19 +157,19 @@ k_water_force(Dev D, const double *__restrict__ x, const int *__restrict__ row_o
     // ---- solute atoms acting on this water (pw, water side: gradient only)
     const uint32_t *rowb = row + nown + nmir;
     for (int k = kstart; k < nb; k += kstep) {
-        const int b = (int)(rowb[k] & kIdMask);
-        double ux = x[3 * b] - ox, uy = x[3 * b + 1] - oy, uz = x[3 * b + 2] - oz;
+        const int pb = (int)(rowb[k] & kIdMask);
+        double ux = px[pb] - ox, uy = py[pb] - oy, uz = pz[pb] - oz;
         if (PBC) {
             // nonbond_pw_box: shift = boxlength*nint((x(solute switch)-x(water O))*inv_boxl), vec = x(j)-x(i)+shift
             // for i = solute atom, j = water atom; seen from the water: vec(a->b) = x(b)-x(a)-shift
-            const int sw = D.g_switch[D.grp_of_atom[b]];
+            const int sw = D.g_switch[D.grp_of_atom[pk_atom[pb]]];
             ux -= pshift(x[3 * sw] - ox, D.box[0], D.inv_box[0]);
             uy -= pshift(x[3 * sw + 1] - oy, D.box[1], D.inv_box[1]);
             uz -= pshift(x[3 * sw + 2] - oz, D.box[2], D.inv_box[2]);
         }
         const float ufx = (float)ux, ufy = (float)uy, ufz = (float)uz;
-        const float qb = D.crgf[b];
-        const int ctb = D.ctype[b];
+        const float qb = pk_q[pb];
+        const int ctb = pk_ct[pb];
 #pragma unroll
         for (int a = 0; a < 3; a++) {
             const int code = D.ljcode[ctb * D.nct + D.wct[a]];
@@ -222,8 +222,11 @@ __device__ __forceinline__ int special_code(const Dev &D, int a, int b) {
 
 template <bool PBC, bool GEOM>
 __global__ void __launch_bounds__(128)
-k_solute_force(Dev D, const double *__restrict__ x, const int *__restrict__ row_off, const int *__restrict__ counts,
-               const uint32_t *__restrict__ rows, double *__restrict__ grad, double *__restrict__ Eslots, int nE) {
+k_solute_force(Dev D, const double *__restrict__ x, const double *__restrict__ px, const double *__restrict__ py,
+               const double *__restrict__ pz, const float *__restrict__ pk_q, const double *__restrict__ pk_qd,
+               const int *__restrict__ pk_ct, const int *__restrict__ pk_atom, const int *__restrict__ row_off,
+               const int *__restrict__ counts, const uint32_t *__restrict__ rows, double *__restrict__ grad,
+               double *__restrict__ Eslots, int nE) {
     const int lane = threadIdx.x & 31;
     const int gidx = blockIdx.x, wid = threadIdx.x >> 5;
     const int kstart = wid * 32 + lane, kstep = kRowWarps * 32;
@@ -266,10 +269,11 @@ k_solute_force(Dev D, const double *__restrict__ x, const int *__restrict__ row_
         for (int k = kstart; k < nown + nmir; k += kstep) {
             const uint32_t e = row[k];
             const bool own = k < nown;
-            const int b = (int)(e & kIdMask);
+            const int pb = (int)(e & kIdMask);
             const bool special = (e & kSpecialBit) != 0;
-            const int gb = D.grp_of_atom[b];
-            double ux = x[3 * b] - ox, uy = x[3 * b + 1] - oy, uz = x[3 * b + 2] - oz;
+            double ux = px[pb] - ox, uy = py[pb] - oy, uz = pz[pb] - oz;
+            int b = -1, gb = -1;       // atom id / group of the partner: only the special and periodic paths need them
+            if (special || PBC) { b = pk_atom[pb]; gb = D.grp_of_atom[b]; }
             if (PBC) {
                 // nonbond_pp_box L4791-4801: shift = boxlength*nint((x(sw_i)-x(sw_j))*inv_boxl)
                 const int swb = D.g_switch[gb];
@@ -278,10 +282,10 @@ k_solute_force(Dev D, const double *__restrict__ x, const int *__restrict__ row_
                 uz += pshift(oz - x[3 * swb + 2], D.box[2], D.inv_box[2]);
             }
             const float ufx = (float)ux, ufy = (float)uy, ufz = (float)uz;
-            const float qb = D.crgf[b];
-            const double qbd = D.crg[b];
-            const int ctb = D.ctype[b];
-            const bool same = gb == gidx;
+            const float qb = pk_q[pb];
+            const double qbd = pk_qd[pb];
+            const int ctb = pk_ct[pb];
+            const bool same = special && gb == gidx;   // own-group partners are always flagged special
 #pragma unroll
             for (int t = 0; t < kITile; t++) {
                 if (t < nt) {
@@ -317,18 +321,16 @@ k_solute_force(Dev D, const double *__restrict__ x, const int *__restrict__ row_
         // ---- solute-water: this side owns the pair, all three water atoms with full LJ (nbe)
         const uint32_t *rowb = row + nown + nmir;
         for (int k = kstart; k < nb; k += kstep) {
-            const int jw = (int)(rowb[k] & kIdMask);
-            const int j0 = D.nat_solute + 3 * jw;
+            const int p0 = (int)(rowb[k] & kIdMask);   // packed index of the water's oxygen
             double shx = 0, shy = 0, shz = 0;
             if (PBC) {
-                shx = pshift(ox - x[3 * j0], D.box[0], D.inv_box[0]);
-                shy = pshift(oy - x[3 * j0 + 1], D.box[1], D.inv_box[1]);
-                shz = pshift(oz - x[3 * j0 + 2], D.box[2], D.inv_box[2]);
+                shx = pshift(ox - px[p0], D.box[0], D.inv_box[0]);
+                shy = pshift(oy - py[p0], D.box[1], D.inv_box[1]);
+                shz = pshift(oz - pz[p0], D.box[2], D.inv_box[2]);
             }
 #pragma unroll
             for (int s = 0; s < 3; s++) {
-                const double ux = (x[3 * (j0 + s)] - ox) + shx, uy = (x[3 * (j0 + s) + 1] - oy) + shy,
-                             uz = (x[3 * (j0 + s) + 2] - oz) + shz;
+                const double ux = (px[p0 + s] - ox) + shx, uy = (py[p0 + s] - oy) + shy, uz = (pz[p0 + s] - oz) + shz;
                 const float ufx = (float)ux, ufy = (float)uy, ufz = (float)uz;
                 const int ctb = D.wct[s];
 #pragma unroll

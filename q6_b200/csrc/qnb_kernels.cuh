@@ -87,6 +87,10 @@ struct Cut {
     int lrf_all[3];     // "no LRF cut-off" sentinel per class (box builders)
     double rcq2;
     double Rq;
+    // kernel parameters live in constant memory: select by class without dynamic indexing (which would force a
+    // local-memory copy of the struct)
+    __host__ __device__ double rc2_of(int cls) const { return cls == 0 ? rc2[0] : cls == 1 ? rc2[1] : rc2[2]; }
+    __host__ __device__ int lrf_all_of(int cls) const { return cls == 0 ? lrf_all[0] : cls == 1 ? lrf_all[1] : lrf_all[2]; }
 };
 
 // ------------------------------------------------------------------ small device helpers

@@ -99,8 +99,12 @@ __global__ void k_pack_items(Dev D, const double *__restrict__ upos, const int *
     item_pos[idx] = make_double4(upos[3 * u], upos[3 * u + 1], upos[3 * u + 2], __longlong_as_double((long long)u));
     item_nq[idx] = D.u_excl[u] ? 0 : D.g_nq[D.u_grp[u]];
 }
-__global__ void k_pack_sources(Dev D, const double *__restrict__ x, const int *__restrict__ cell_items,
-                               const int *__restrict__ src_off, double4 *__restrict__ src) {
+// Packed atoms: the non-Q atoms of every non-excluded unit, in cell order of the units.  Row entries are indices
+// into this order, so the lanes of a warp (consecutive row entries = neighbouring units of one cell) read
+// neighbouring records instead of gathering all over the coordinate array.
+__global__ void k_pack_atoms(Dev D, const int *__restrict__ cell_items, const int *__restrict__ src_off,
+                             int *__restrict__ pk_atom, float *__restrict__ pk_q, double *__restrict__ pk_qd,
+                             int *__restrict__ pk_ct) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= D.nunit) return;
     const int u = cell_items[idx];
@@ -110,8 +114,25 @@ __global__ void k_pack_sources(Dev D, const double *__restrict__ x, const int *_
     for (int k = 0; k < gn; k++) {
         const int i = D.g_atoms[gf + k];
         if (D.is_q[i]) continue;
-        src[p++] = make_double4(x[3 * i], x[3 * i + 1], x[3 * i + 2], D.crg[i]);
+        pk_atom[p] = i; pk_q[p] = D.crgf[i]; pk_qd[p] = D.crg[i]; pk_ct[p] = D.ctype[i];
+        p++;
     }
+}
+// per list build: LRF source records (x,y,z,q) in packed order
+__global__ void k_pack_sources(int npk, const int *__restrict__ pk_atom, const double *__restrict__ x,
+                               const double *__restrict__ crg, double4 *__restrict__ src) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npk) return;
+    const int i = pk_atom[p];
+    src[p] = make_double4(x[3 * i], x[3 * i + 1], x[3 * i + 2], crg[i]);
+}
+// per step: coordinates in packed order, structure of arrays
+__global__ void k_pack_coords(int npk, const int *__restrict__ pk_atom, const double *__restrict__ x,
+                              double *__restrict__ px, double *__restrict__ py, double *__restrict__ pz) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npk) return;
+    const int i = pk_atom[p];
+    px[p] = x[3 * i]; py[p] = x[3 * i + 1]; pz[p] = x[3 * i + 2];
 }
 
 // range of cells along one dimension around c with reach m
@@ -154,8 +175,9 @@ __device__ __forceinline__ XSeg x_segments(int c, int m, int n, int periodic) {
 template <bool FILL>
 __global__ void __launch_bounds__(256)
 k_build_rows(Dev D, Cut C, Grid G, const double *__restrict__ upos, const int *__restrict__ cell_of,
-             const int *__restrict__ cell_start, const double4 *__restrict__ item_pos, int *__restrict__ counts,
-             const int *__restrict__ row_off, uint32_t *__restrict__ rows) {
+             const int *__restrict__ cell_start, const double4 *__restrict__ item_pos,
+             const int *__restrict__ src_off, int *__restrict__ counts, const int *__restrict__ row_off,
+             uint32_t *__restrict__ rows) {
     const int lane = threadIdx.x & 31;
     const int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (u >= D.nunit) return;
@@ -195,7 +217,7 @@ k_build_rows(Dev D, Cut C, Grid G, const double *__restrict__ upos, const int *_
                                 const double pv[3] = {ip.x, ip.y, ip.z};
                                 // owner orientation (is = owner's switch atom); the value is the same either way
                                 double r2 = owner_is_u ? unit_r2(D, pu, pv) : unit_r2(D, pv, pu);
-                                pass = r2 <= C.rc2[cls];
+                                pass = r2 <= C.rc2_of(cls);
                             }
                         }
                         // entries emitted by this lane, by segment
@@ -216,15 +238,17 @@ k_build_rows(Dev D, Cut C, Grid G, const double *__restrict__ upos, const int *_
                             int p_own = base_own + n_own + s_own - c_own;
                             int p_mir = base_mir + n_mir + s_mir - c_mir;
                             int p_b = base_b + n_b + s_b - c_b;
+                            const uint32_t pk0 = (uint32_t)src_off[idx];   // first packed atom of unit v
                             if (v_sol) {
-                                // flatten the group's non-Q atoms
+                                // flatten the group's non-Q atoms (entries = packed atom indices)
                                 const int gf = D.g_first[v], gn = D.g_n[v];
                                 uint32_t flag = (u_sol && owner_is_u) ? kOwnerBit : 0u;
                                 int p = u_sol ? (owner_is_u ? p_own : p_mir) : p_b;
+                                uint32_t pk = pk0;
                                 for (int k = 0; k < gn; k++) {
                                     int b = D.g_atoms[gf + k];
                                     if (D.is_q[b]) continue;
-                                    uint32_t e = (uint32_t)b | flag;
+                                    uint32_t e = (pk++) | flag;
                                     if (u_sol) {
                                         // special if b relates to any atom of group u (excluded / 1-4 / same group)
                                         int l = gs_lo, h = gs_hi;
@@ -234,10 +258,10 @@ k_build_rows(Dev D, Cut C, Grid G, const double *__restrict__ upos, const int *_
                                     rows[p++] = e;
                                 }
                             } else {
-                                const uint32_t w = (uint32_t)(v - ns);
-                                if (u_sol) rows[p_b] = w | kOwnerBit;
-                                else if (owner_is_u) rows[p_own] = w | kOwnerBit;
-                                else rows[p_mir] = w;
+                                // a water partner is named by the packed index of its first atom (O)
+                                if (u_sol) rows[p_b] = pk0 | kOwnerBit;
+                                else if (owner_is_u) rows[p_own] = pk0 | kOwnerBit;
+                                else rows[p_mir] = pk0;
                             }
                         }
                         n_own += __shfl_sync(kFull, s_own, 31);
@@ -424,8 +448,8 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
             if (!in_shard(D, cls, owner_is_t ? t : s)) continue;
             const double ps[3] = {ip.x, ip.y, ip.z};
             const double r2u = owner_is_t ? unit_r2(D, pt, ps) : unit_r2(D, ps, pt);
-            if (r2u <= C.rc2[cls]) continue;                       // listed pair, not LRF
-            if (!(r2u <= C.rclrf2 || C.lrf_all[cls])) continue;    // beyond the LRF cut-off
+            if (r2u <= C.rc2_of(cls)) continue;                      // listed pair, not LRF
+            if (!(r2u <= C.rclrf2 || C.lrf_all_of(cls))) continue;   // beyond the LRF cut-off
             // lrf_update(group1 = source, group2 = target): dr = x(i) - cgp_cent(target) - shift
             double ox = cx_, oy = cy_, oz = cz_;
             if (D.use_PBC) {

@@ -92,6 +92,8 @@ def load_library(path: str = LIB_PATH):
     lib.qnb_bench_kernels.argtypes = [H, _PD, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int, _PF, C.c_int]
     lib.qnb_launch_count.restype = C.c_int64
     lib.qnb_launch_count.argtypes = [H]
+    lib.qnb_last_timing.restype = C.c_int
+    lib.qnb_last_timing.argtypes = [H, _PD]
     lib.qnb_last_copy_bytes.restype = C.c_int
     lib.qnb_last_copy_bytes.argtypes = [H, _PL, _PL]
     lib.qnb_finalize.restype = C.c_int
@@ -234,6 +236,11 @@ class Qnb:
 
     def launch_count(self) -> int:
         return int(self.lib.qnb_launch_count(self.h))
+
+    def last_timing(self) -> dict:
+        t = np.zeros(4)
+        self._check(self.lib.qnb_last_timing(self.h, _dp(t)))
+        return dict(zip(("stage_in_s", "issue_s", "device_wait_s", "add_out_s"), t.tolist()))
 
     def last_copy_bytes(self):
         a, b = C.c_int64(), C.c_int64()

@@ -53,7 +53,9 @@ def _run_case(q, cuts, lam, check_lists=True):
         if q.use_LRF:
             lg, lo = g.export_lrf(), o.export_lrf()
             scale = np.abs(lo).max(axis=0) + 1e-300
-            assert np.all(np.abs(lg - lo) <= 1e-9 * scale + 1e-12), "LRF moments differ"
+            # centres, phi0, phi1 are FP64 on the GPU; phi2/phi3 (higher-order corrections) are summed in FP32
+            tol = np.where(np.arange(43) < 7, 1e-9, 2e-5)
+            assert np.all(np.abs(lg - lo) <= tol * scale + 1e-12), "LRF moments differ"
         r = _check_step(g, o, q, x, lam)
         # a second evaluation at moved coordinates with the SAME lists (what happens between list updates)
         rng = np.random.default_rng(5)
