@@ -93,12 +93,14 @@ static int upload(DBuf<T> &b, const std::vector<T> &v) {
 
 using namespace qnb;
 
+constexpr int kAux = 5;   // auxiliary streams: the kernels of one evaluation run concurrently
+
 struct qnb_handle {
-    int device = 0;
+    int device = 0, nsm = 148;
     HostTables T;
     Dev D{};
-    cudaStream_t st = nullptr, aux[3] = {nullptr, nullptr, nullptr};
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+    cudaStream_t st = nullptr, aux[kAux] = {};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join[kAux] = {};
     cudaGraphExec_t graph[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};   // [with copies][flags]
     bool use_graph = true;
     int graph_launches[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
@@ -129,6 +131,10 @@ struct qnb_handle {
     DBuf<float> pk_q;
     DBuf<double> pk_qd, px, py, pz;
     int npk = 0;   // packed atoms: non-Q atoms of non-excluded units in cell order
+    DBuf<int> nch, choff;
+    DBuf<int2> wdesc;
+    DBuf<uint32_t> wrow;
+    int nwchunk = 0;   // water-row chunks
     int nqp = 0, nqw = 0;
     bool qp_done = false, qw_done = false, lists_built = false;
     int64_t total_rows = 0;
@@ -228,8 +234,13 @@ static int init_device(qnb_handle *h) {
     CU(cudaMallocHost(&h->hx, n3 * sizeof(double)));
     CU(cudaMallocHost(&h->hout, h->nout * sizeof(double)));
     CU(cudaMallocHost(&h->hlam, kMaxStates * sizeof(double)));
+    {
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, h->device));
+        h->nsm = prop.multiProcessorCount;
+    }
     CU(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
-    for (int k = 0; k < 3; k++) {
+    for (int k = 0; k < kAux; k++) {
         CU(cudaStreamCreateWithFlags(&h->aux[k], cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&h->ev_join[k], cudaEventDisableTiming));
     }
@@ -342,6 +353,20 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
         if (h->rows.ensure((size_t)std::max(total, 1))) return 1;
         LAUNCH(h, k_build_rows<true>, cdiv(nu * 32, 256), 256, 0, D, h->cut, G, h->upos.p, h->cell_of.p, h->cell_start.p,
                h->item_pos.p, h->src_off.p, h->counts.p, h->row_off.p, h->rows.p);
+        // chunked copy of the water rows for the streaming force kernel
+        h->nwchunk = 0;
+        if (D.nwat > 0) {
+            if (h->nch.ensure(D.nwat + 1) || h->choff.ensure(D.nwat + 2)) return 1;
+            LAUNCH(h, k_chunk_count, cdiv(D.nwat, 256), 256, 0, D.ncgp_solute, D.nwat, h->counts.p, h->nch.p);
+            run_exclusive_scan(h, h->nch.p, h->choff.p, D.nwat);
+            CU(cudaMemcpyAsync(&h->nwchunk, h->choff.p + D.nwat, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+            CU(cudaStreamSynchronize(h->st));
+            if (h->nwchunk > 0) {
+                if (h->wdesc.ensure(h->nwchunk) || h->wrow.ensure((size_t)h->nwchunk * 32)) return 1;
+                LAUNCH(h, k_chunk_fill, cdiv(D.nwat * 32, 256), 256, 0, D.ncgp_solute, D.nwat, h->counts.p, h->row_off.p,
+                       h->rows.p, h->choff.p, h->wdesc.p, h->wrow.p);
+            }
+        }
     }
     // Q-atom partner lists: built once when the cut-off covers everything (nbqplist L3678, nbqwlist L3889,
     // nbqplist_box L3780, nbqwlist_box L3972)
@@ -398,7 +423,7 @@ static bool step_kernel_active(const qnb_handle *h, int k, int flags) {
     const Dev &D = h->D;
     const bool md = flags & QNB_FLAG_MD;
     switch (k) {
-    case K_WATER: return md && D.nwat > 0;
+    case K_WATER: return md && D.nwat > 0 && h->nwchunk > 0;
     case K_SOLUTE: return md && D.ncgp_solute > 0;
     case K_QPARTNER: return D.nqat > 0 && (h->nqp + h->nqw) > 0;
     case K_QATOM: return D.nqat > 0 && (h->nqp + h->nqw) > 0;
@@ -415,8 +440,9 @@ static void launch_step_kernel(qnb_handle *h, int k, cudaStream_t cs) {
     const bool pbc = D.use_PBC, spc = D.spc_water, geom = D.geometric;
     switch (k) {
     case K_WATER: {
-        const int grid = D.nwat;
-#define WCASE(P, S, G) LAUNCH_ON(h, cs, (k_water_force<P, S, G>), grid, 32 * kRowWarps, 0, D, h->x.p, h->px.p, h->py.p, h->pz.p, h->pk_q.p, h->pk_ct.p, h->pk_atom.p, h->row_off.p, h->counts.p, h->rows.p, grad, E, nE)
+        // persistent: at most 3 blocks of 4 warps per SM, at least ~4 chunks per warp
+        const int grid = std::max(1, std::min(3 * h->nsm, cdiv(h->nwchunk, 4 * 4)));
+#define WCASE(P, S, G) LAUNCH_ON(h, cs, (k_water_force<P, S, G>), grid, 128, 0, D, h->x.p, h->px.p, h->py.p, h->pz.p, h->pk_q.p, h->pk_ct.p, h->pk_atom.p, h->nwchunk, h->wdesc.p, h->wrow.p, grad, E, nE)
         if (pbc) { if (spc) WCASE(true, true, true); else if (geom) WCASE(true, false, true); else WCASE(true, false, false); }
         else { if (spc) WCASE(false, true, true); else if (geom) WCASE(false, false, true); else WCASE(false, false, false); }
 #undef WCASE
@@ -460,14 +486,14 @@ static void launch_step_kernel(qnb_handle *h, int k, cudaStream_t cs) {
 
 // The kernels of one evaluation are independent (they only meet in atomicAdd on grad/E), so they are issued on
 // four streams between a fork and a join event: at 12k atoms no single kernel fills 148 SMs.
-static const int kStreamOf[K_COUNT] = {0, 1, 2, 2, -1, -1};   // aux stream index, -1 = main stream
+static const int kStreamOf[K_COUNT] = {0, 1, 2, 3, 4, -1};   // aux stream index, -1 = main stream
 
 static int issue_step(qnb_handle *h, int flags) {
     CU(cudaMemsetAsync(h->out.p, 0, h->nout * sizeof(double), h->st));
     if ((flags & QNB_FLAG_MD) && h->npk > 0)
         LAUNCH(h, k_pack_coords, cdiv(h->npk, 256), 256, 0, h->npk, h->pk_atom.p, h->x.p, h->px.p, h->py.p, h->pz.p);
     CU(cudaEventRecord(h->ev_fork, h->st));
-    bool used[3] = {false, false, false};
+    bool used[kAux] = {};
     for (int k = 0; k < K_COUNT; k++) {
         if (!step_kernel_active(h, k, flags)) continue;
         const int si = kStreamOf[k];
@@ -475,7 +501,7 @@ static int issue_step(qnb_handle *h, int flags) {
         if (si >= 0 && !used[si]) { CU(cudaStreamWaitEvent(cs, h->ev_fork, 0)); used[si] = true; }
         launch_step_kernel(h, k, cs);
     }
-    for (int k = 0; k < 3; k++)
+    for (int k = 0; k < kAux; k++)
         if (used[k]) {
             CU(cudaEventRecord(h->ev_join[k], h->aux[k]));
             CU(cudaStreamWaitEvent(h->st, h->ev_join[k], 0));
@@ -948,7 +974,7 @@ int qnb_finalize(qnb_handle *h) {
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     if (h->st) cudaStreamSynchronize(h->st);
     drop_graphs(h);
-    for (int k = 0; k < 3; k++) { if (h->aux[k]) cudaStreamDestroy(h->aux[k]); if (h->ev_join[k]) cudaEventDestroy(h->ev_join[k]); }
+    for (int k = 0; k < kAux; k++) { if (h->aux[k]) cudaStreamDestroy(h->aux[k]); if (h->ev_join[k]) cudaEventDestroy(h->ev_join[k]); }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     h->crg.release(); h->ljd.release(); h->crgf.release(); h->ljf.release(); h->ctype.release(); h->grp_of_atom.release();
     h->g_first.release(); h->g_n.release(); h->g_switch.release(); h->g_atoms.release(); h->g_nq.release();
@@ -960,6 +986,7 @@ int qnb_finalize(qnb_handle *h) {
     h->row_tot.release(); h->row_off.release(); h->flag.release(); h->pos.release(); h->qp_list.release();
     h->qw_list.release(); h->qp_shift_atom.release(); h->rows.release(); h->flush.release();
     h->pk_atom.release(); h->pk_ct.release(); h->pk_q.release(); h->pk_qd.release(); h->px.release(); h->py.release(); h->pz.release();
+    h->nch.release(); h->choff.release(); h->wdesc.release(); h->wrow.release();
     h->item_pos.release(); h->src.release(); h->cell_unsorted.release(); h->item_nq.release(); h->src_off.release();
     if (h->hx) cudaFreeHost(h->hx);
     if (h->hout) cudaFreeHost(h->hout);

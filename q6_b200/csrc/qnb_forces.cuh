@@ -83,124 +83,172 @@ __device__ __forceinline__ void lj_pair_f64(const double *__restrict__ ljd, int 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Water rows: ww (3x3 site tile) + the water side of pw.  One block of kRowWarps warps per water molecule: the
-// row is dealt to the warps in chunks of 32 entries, so that a 12k-atom system still puts >12k warps in flight
-// (the kernel is latency-bound, not throughput-bound, at that size).
+// Water rows: ww (3x3 site tile) + the water side of pw.
+//
+// The rows are re-laid out at list-build time into CHUNKS of 32 entries (k_chunk_*: one descriptor {unit, kind}
+// and 32 padded entries per chunk).  The kernel is persistent: every warp owns a contiguous range of chunks and
+// runs a three-stage software pipeline over it -- descriptor+entry of chunk c+2 and partner coordinates of chunk
+// c+1 are in flight while chunk c is computed -- because at 12k atoms the work is latency-bound (three dependent
+// L2 round trips per chunk against ~500 issue cycles of arithmetic).  Gradients of the current water are kept in
+// registers across its chunks and flushed (FP64 shuffle reduction + 9 atomicAdd) when the water changes.
+constexpr int kChunkOwn = 0, kChunkMir = 1, kChunkB = 2;
+constexpr uint32_t kPadEntry = 0xffffffffu;
+
+struct WaterTile {          // own molecule of the row being processed
+    double o[3];            // row origin: own oxygen
+    double sd[3][3];        // site offsets from the origin, FP64 (energies)
+    float sf[3][3];         // same, FP32 (forces)
+    float g[3][3];          // gradient accumulators
+};
+
+template <bool PBC, bool SPC>
+__device__ __forceinline__ void ww_chunk(const Dev &D, WaterTile &T, bool own, bool valid, const double (&pj)[9],
+                                         double &eel, double &evdw) {
+    if (!valid) return;
+    // pj = x,y,z of the partner's three sites (SoA order: x0 x1 x2 y0 y1 y2 z0 z1 z2)
+    double shx = 0, shy = 0, shz = 0;
+    if (PBC) {
+        // one shift per molecule pair from the O-O vector (nonbond_ww_spc_box L6016-6017)
+        shx = pshift(T.o[0] - pj[0], D.box[0], D.inv_box[0]);
+        shy = pshift(T.o[1] - pj[3], D.box[1], D.inv_box[1]);
+        shz = pshift(T.o[2] - pj[6], D.box[2], D.inv_box[2]);
+    }
+    double ud[3][3];
+    float uf[3][3];
+#pragma unroll
+    for (int b = 0; b < 3; b++) {
+        ud[b][0] = (pj[b] - T.o[0]) + shx; ud[b][1] = (pj[3 + b] - T.o[1]) + shy; ud[b][2] = (pj[6 + b] - T.o[2]) + shz;
+        uf[b][0] = (float)ud[b][0]; uf[b][1] = (float)ud[b][1]; uf[b][2] = (float)ud[b][2];
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+#pragma unroll
+        for (int b = 0; b < 3; b++) {
+            const float dx = uf[b][0] - T.sf[a][0], dy = uf[b][1] - T.sf[a][1], dz = uf[b][2] - T.sf[a][2];
+            float rinv, ev = 0.f, dv;
+            const bool lj = !SPC || (a == 0 && b == 0);   // nonbond_ww_spc: only the first pair carries LJ
+            if (lj) dv = pair_f32<true, false>(dx, dy, dz, D.wwQ[a * 3 + b], D.wwA[a * 3 + b], D.wwB[a * 3 + b], rinv, ev);
+            else dv = pair_f32<false, false>(dx, dy, dz, D.wwQ[a * 3 + b], 0.f, 0.f, rinv, ev);
+            T.g[a][0] = fmaf(-dx, dv, T.g[a][0]); T.g[a][1] = fmaf(-dy, dv, T.g[a][1]); T.g[a][2] = fmaf(-dz, dv, T.g[a][2]);
+            if (own) {
+                if (lj) energy_f64(ud[b][0] - T.sd[a][0], ud[b][1] - T.sd[a][1], ud[b][2] - T.sd[a][2], D.wwQd[a * 3 + b],
+                                   D.wwAd[a * 3 + b], D.wwBd[a * 3 + b], rinv, eel, evdw);
+                else eel += coulomb_f64(ud[b][0] - T.sd[a][0], ud[b][1] - T.sd[a][1], ud[b][2] - T.sd[a][2], D.wwQd[a * 3 + b], rinv);
+            }
+        }
+    }
+}
+
+// solute atom acting on the own water (pw, water side: gradient only)
+template <bool PBC, bool GEOM>
+__device__ __forceinline__ void wp_chunk(const Dev &D, WaterTile &T, bool valid, const double (&pj)[9], float qb, int ctb,
+                                         int pb, const double *__restrict__ x, const int *__restrict__ pk_atom) {
+    if (!valid) return;
+    double ux = pj[0] - T.o[0], uy = pj[3] - T.o[1], uz = pj[6] - T.o[2];
+    if (PBC) {
+        // nonbond_pw_box: shift = boxlength*nint((x(solute switch)-x(water O))*inv_boxl), vec = x(j)-x(i)+shift
+        // for i = solute atom, j = water atom; seen from the water: vec(a->b) = x(b)-x(a)-shift
+        const int sw = D.g_switch[D.grp_of_atom[pk_atom[pb]]];
+        ux -= pshift(x[3 * sw] - T.o[0], D.box[0], D.inv_box[0]);
+        uy -= pshift(x[3 * sw + 1] - T.o[1], D.box[1], D.inv_box[1]);
+        uz -= pshift(x[3 * sw + 2] - T.o[2], D.box[2], D.inv_box[2]);
+    }
+    const float ufx = (float)ux, ufy = (float)uy, ufz = (float)uz;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const int code = D.ljcode[ctb * D.nct + D.wct[a]];
+        float A, B, rinv, ev = 0.f;
+        lj_pair<GEOM>(D.ljf, D.wct[a], ctb, code, A, B);
+        const float dx = ufx - T.sf[a][0], dy = ufy - T.sf[a][1], dz = ufz - T.sf[a][2];
+        const float dv = pair_f32<true, false>(dx, dy, dz, D.wq[a] * qb, A, B, rinv, ev);
+        T.g[a][0] = fmaf(-dx, dv, T.g[a][0]); T.g[a][1] = fmaf(-dy, dv, T.g[a][1]); T.g[a][2] = fmaf(-dz, dv, T.g[a][2]);
+    }
+}
+
 template <bool PBC, bool SPC, bool GEOM>
 __global__ void __launch_bounds__(128)
 k_water_force(Dev D, const double *__restrict__ x, const double *__restrict__ px, const double *__restrict__ py,
               const double *__restrict__ pz, const float *__restrict__ pk_q, const int *__restrict__ pk_ct,
-              const int *__restrict__ pk_atom, const int *__restrict__ row_off, const int *__restrict__ counts,
-              const uint32_t *__restrict__ rows, double *__restrict__ grad, double *__restrict__ Eslots, int nE) {
+              const int *__restrict__ pk_atom, int nchunk, const int2 *__restrict__ cdesc,
+              const uint32_t *__restrict__ crow, double *__restrict__ grad, double *__restrict__ Eslots, int nE) {
     const int lane = threadIdx.x & 31;
-    const int w = blockIdx.x, wid = threadIdx.x >> 5;
-    const int kstart = wid * 32 + lane, kstep = kRowWarps * 32;
-    const int u = D.ncgp_solute + w;
-    const int nown = counts[3 * u], nmir = counts[3 * u + 1], nb = counts[3 * u + 2];
-    if (nown + nmir + nb == 0) return;
-    const uint32_t *row = rows + row_off[u];
-    const int i0 = D.nat_solute + 3 * w;
-    const double ox = x[3 * i0], oy = x[3 * i0 + 1], oz = x[3 * i0 + 2];
-    double sd[3][3];   // site offsets from the row origin (own oxygen)
-    float sf[3][3];
-#pragma unroll
-    for (int a = 0; a < 3; a++) {
-        sd[a][0] = x[3 * (i0 + a)] - ox; sd[a][1] = x[3 * (i0 + a) + 1] - oy; sd[a][2] = x[3 * (i0 + a) + 2] - oz;
-        sf[a][0] = (float)sd[a][0]; sf[a][1] = (float)sd[a][1]; sf[a][2] = (float)sd[a][2];
-    }
-    float g[3][3];
-#pragma unroll
-    for (int a = 0; a < 3; a++) g[a][0] = g[a][1] = g[a][2] = 0.f;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
+    const int per = (nchunk + nwarp - 1) / nwarp;
+    const int c0 = gw * per, c1 = min(nchunk, c0 + per);
+    if (c0 >= c1) return;
+    WaterTile T;
+    int cur_w = -1;
     double evdw = 0.0, eel = 0.0;
 
-    // ---- water-water: A_own (with energies) then A_mir (forces only)
-    for (int k = kstart; k < nown + nmir; k += kstep) {
-        const bool own = k < nown;
-        const int p0 = (int)(row[k] & kIdMask);   // packed index of the partner's oxygen
-        double ud[3][3];
-        {
-            double shx = 0, shy = 0, shz = 0;
-            if (PBC) {
-                // one shift per molecule pair from the O-O vector (nonbond_ww_spc_box L6016-6017)
-                shx = pshift(ox - px[p0], D.box[0], D.inv_box[0]);
-                shy = pshift(oy - py[p0], D.box[1], D.inv_box[1]);
-                shz = pshift(oz - pz[p0], D.box[2], D.inv_box[2]);
-            }
+    auto flush = [&]() {
+        if (cur_w < 0) return;
+        const int i0 = D.nat_solute + 3 * cur_w;
+        double s[9];
 #pragma unroll
-            for (int b = 0; b < 3; b++) {
-                ud[b][0] = (px[p0 + b] - ox) + shx;
-                ud[b][1] = (py[p0 + b] - oy) + shy;
-                ud[b][2] = (pz[p0 + b] - oz) + shz;
-            }
+        for (int k = 0; k < 9; k++) s[k] = warp_sum((double)T.g[k / 3][k % 3]);
+        double mine = 0;
+#pragma unroll
+        for (int k = 0; k < 9; k++) if (lane == k) mine = s[k];
+        if (lane < 9) atomicAdd(&grad[3 * i0 + lane], mine);
+    };
+    // stage A: descriptor + entry; stage B: partner coordinates
+    auto load_a = [&](int c, int2 &d, uint32_t &e) {
+        d = cdesc[c];
+        e = crow[(size_t)c * 32 + lane];
+    };
+    auto load_b = [&](const int2 &d, uint32_t e, double (&pj)[9], float &qb, int &ctb) {
+        if (e == kPadEntry) return;
+        const int p = (int)(e & kIdMask);
+        if (d.y == kChunkB) {
+            pj[0] = px[p]; pj[3] = py[p]; pj[6] = pz[p];
+            qb = pk_q[p]; ctb = pk_ct[p];
+        } else {
+#pragma unroll
+            for (int b = 0; b < 3; b++) { pj[b] = px[p + b]; pj[3 + b] = py[p + b]; pj[6 + b] = pz[p + b]; }
         }
-        float uf[3][3];
+    };
+    int2 d0, d1 = make_int2(-1, 0), d2 = make_int2(-1, 0);
+    uint32_t e0, e1 = kPadEntry, e2 = kPadEntry;
+    double p0[9], p1[9];
+    float q0 = 0.f, q1 = 0.f;
+    int ct0 = 0, ct1 = 0;
 #pragma unroll
-        for (int b = 0; b < 3; b++) { uf[b][0] = (float)ud[b][0]; uf[b][1] = (float)ud[b][1]; uf[b][2] = (float)ud[b][2]; }
+    for (int k = 0; k < 9; k++) { p0[k] = 0.0; p1[k] = 0.0; }
+    load_a(c0, d0, e0);
+    if (c0 + 1 < c1) load_a(c0 + 1, d1, e1);
+    load_b(d0, e0, p0, q0, ct0);
+    for (int c = c0; c < c1; c++) {
+        if (c + 2 < c1) load_a(c + 2, d2, e2);
+        if (c + 1 < c1) load_b(d1, e1, p1, q1, ct1);
+        if (d0.x != cur_w) {
+            flush();
+            cur_w = d0.x;
+            const int i0 = D.nat_solute + 3 * cur_w;
+            T.o[0] = x[3 * i0]; T.o[1] = x[3 * i0 + 1]; T.o[2] = x[3 * i0 + 2];
 #pragma unroll
-        for (int a = 0; a < 3; a++) {
+            for (int a = 0; a < 3; a++) {
 #pragma unroll
-            for (int b = 0; b < 3; b++) {
-                const float dx = uf[b][0] - sf[a][0], dy = uf[b][1] - sf[a][1], dz = uf[b][2] - sf[a][2];
-                float rinv, ev = 0.f, dv;
-                const bool lj = !SPC || (a == 0 && b == 0);   // nonbond_ww_spc: only the first pair carries LJ
-                if (lj) dv = pair_f32<true, false>(dx, dy, dz, D.wwQ[a * 3 + b], D.wwA[a * 3 + b], D.wwB[a * 3 + b], rinv, ev);
-                else dv = pair_f32<false, false>(dx, dy, dz, D.wwQ[a * 3 + b], 0.f, 0.f, rinv, ev);
-                g[a][0] = fmaf(-dx, dv, g[a][0]); g[a][1] = fmaf(-dy, dv, g[a][1]); g[a][2] = fmaf(-dz, dv, g[a][2]);
-                if (own) {
-                    if (lj) energy_f64(ud[b][0] - sd[a][0], ud[b][1] - sd[a][1], ud[b][2] - sd[a][2], D.wwQd[a * 3 + b],
-                                       D.wwAd[a * 3 + b], D.wwBd[a * 3 + b], rinv, eel, evdw);
-                    else eel += coulomb_f64(ud[b][0] - sd[a][0], ud[b][1] - sd[a][1], ud[b][2] - sd[a][2], D.wwQd[a * 3 + b], rinv);
+                for (int k = 0; k < 3; k++) {
+                    T.sd[a][k] = x[3 * (i0 + a) + k] - T.o[k];
+                    T.sf[a][k] = (float)T.sd[a][k];
+                    T.g[a][k] = 0.f;
                 }
             }
         }
+        const bool valid = e0 != kPadEntry;
+        if (d0.y == kChunkB) wp_chunk<PBC, GEOM>(D, T, valid, p0, q0, ct0, (int)(e0 & kIdMask), x, pk_atom);
+        else ww_chunk<PBC, SPC>(D, T, d0.y == kChunkOwn, valid, p0, eel, evdw);
+        d0 = d1; e0 = e1; q0 = q1; ct0 = ct1;
+#pragma unroll
+        for (int k = 0; k < 9; k++) p0[k] = p1[k];
+        d1 = d2; e1 = e2;
     }
-    // ---- solute atoms acting on this water (pw, water side: gradient only)
-    const uint32_t *rowb = row + nown + nmir;
-    for (int k = kstart; k < nb; k += kstep) {
-        const int pb = (int)(rowb[k] & kIdMask);
-        double ux = px[pb] - ox, uy = py[pb] - oy, uz = pz[pb] - oz;
-        if (PBC) {
-            // nonbond_pw_box: shift = boxlength*nint((x(solute switch)-x(water O))*inv_boxl), vec = x(j)-x(i)+shift
-            // for i = solute atom, j = water atom; seen from the water: vec(a->b) = x(b)-x(a)-shift
-            const int sw = D.g_switch[D.grp_of_atom[pk_atom[pb]]];
-            ux -= pshift(x[3 * sw] - ox, D.box[0], D.inv_box[0]);
-            uy -= pshift(x[3 * sw + 1] - oy, D.box[1], D.inv_box[1]);
-            uz -= pshift(x[3 * sw + 2] - oz, D.box[2], D.inv_box[2]);
-        }
-        const float ufx = (float)ux, ufy = (float)uy, ufz = (float)uz;
-        const float qb = pk_q[pb];
-        const int ctb = pk_ct[pb];
-#pragma unroll
-        for (int a = 0; a < 3; a++) {
-            const int code = D.ljcode[ctb * D.nct + D.wct[a]];
-            float A, B, rinv, ev = 0.f;
-            lj_pair<GEOM>(D.ljf, D.wct[a], ctb, code, A, B);
-            const float dx = ufx - sf[a][0], dy = ufy - sf[a][1], dz = ufz - sf[a][2];
-            const float dv = pair_f32<true, false>(dx, dy, dz, D.wq[a] * qb, A, B, rinv, ev);
-            g[a][0] = fmaf(-dx, dv, g[a][0]); g[a][1] = fmaf(-dy, dv, g[a][1]); g[a][2] = fmaf(-dz, dv, g[a][2]);
-        }
-    }
-    // ---- FP64 reduction: lanes (shuffles), then warps (shared memory), one FP64 atomicAdd per component
-    __shared__ double red[kRowWarps][11];
-#pragma unroll
-    for (int a = 0; a < 3; a++)
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            const double s = warp_sum((double)g[a][c]);
-            if (lane == 0) red[wid][a * 3 + c] = s;
-        }
+    flush();
     const double sv = warp_sum(evdw), se = warp_sum(eel);
-    if (lane == 0) { red[wid][9] = sv; red[wid][10] = se; }
-    __syncthreads();
-    if (threadIdx.x < 11) {
-        double s = 0;
-#pragma unroll
-        for (int k = 0; k < kRowWarps; k++) s += red[k][threadIdx.x];
-        if (threadIdx.x < 9) atomicAdd(&grad[3 * i0 + threadIdx.x], s);
-        else if (nown > 0) {
-            double *E = Eslots + (size_t)(blockIdx.x & (kESlots - 1)) * nE;
-            atomicAdd(&E[threadIdx.x == 9 ? QNB_E_WW_VDW : QNB_E_WW_EL], s);
-        }
+    if (lane == 0) {
+        double *E = Eslots + (size_t)(gw & (kESlots - 1)) * nE;
+        atomicAdd(&E[QNB_E_WW_VDW], sv);
+        atomicAdd(&E[QNB_E_WW_EL], se);
     }
 }
 

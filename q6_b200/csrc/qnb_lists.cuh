@@ -277,6 +277,33 @@ k_build_rows(Dev D, Cut C, Grid G, const double *__restrict__ upos, const int *_
     }
 }
 
+// ---- chunked re-layout of the rows of units [u0, u0+n): per unit ceil(nown/32)+ceil(nmir/32)+ceil(nb/32) chunks
+__global__ void k_chunk_count(int u0, int n, const int *__restrict__ counts, int *__restrict__ nch) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int u = u0 + k;
+    nch[k] = (counts[3 * u] + 31) / 32 + (counts[3 * u + 1] + 31) / 32 + (counts[3 * u + 2] + 31) / 32;
+}
+// one warp per unit: copy the three segments into 32-entry chunks padded with kPadEntry
+__global__ void k_chunk_fill(int u0, int n, const int *__restrict__ counts, const int *__restrict__ row_off,
+                             const uint32_t *__restrict__ rows, const int *__restrict__ choff,
+                             int2 *__restrict__ cdesc, uint32_t *__restrict__ crow) {
+    const int lane = threadIdx.x & 31;
+    const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (k >= n) return;
+    const int u = u0 + k;
+    int c = choff[k];
+    int base = row_off[u];
+    for (int seg = 0; seg < 3; seg++) {
+        const int m = counts[3 * u + seg];
+        for (int b = 0; b < m; b += 32, c++) {
+            if (lane == 0) cdesc[c] = make_int2(k, seg);
+            crow[(size_t)c * 32 + lane] = (b + lane < m) ? rows[base + b + lane] : 0xffffffffu;
+        }
+        base += m;
+    }
+}
+
 __global__ void k_row_totals(int nunit, const int *__restrict__ counts, int *__restrict__ tot) {
     int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u < nunit) tot[u] = counts[3 * u] + counts[3 * u + 1] + counts[3 * u + 2];
@@ -416,16 +443,13 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
     double *lt = lrf + (size_t)QNB_LRF_STRIDE * gt;
     const double cx_ = lt[0], cy_ = lt[1], cz_ = lt[2];
     const double pt[3] = {upos[3 * t], upos[3 * t + 1], upos[3 * t + 2]};
-    // phi0 and phi1 in FP64.  phi2 and phi3 enter potential and field only through dr.phi2.dr, phi2.dr and
-    // dr.phi3.dr with |dr| ~ 1 A (atom to group centre) against r >= Rc: corrections of relative size dr/r ~ 0.1 and
-    // (dr/r)^2 ~ 0.01 to the phi1 terms, so they are formed and summed in FP32 (relative error ~1e-6 of
-    // themselves, <= 1e-7 of the LRF energy and field).
-    double m[4];
-    float h[16];
+    // phi0, phi1, phi2 in FP64 (FP32 phi2 was measured to move E%LRF by 1.1e-6 relative).  phi3 enters only the field,
+    // as 1/2 dr.phi3.dr with |dr| ~ 1 A (atom to group centre) against r >= Rc: a (dr/r)^2 ~ 1e-2 correction to
+    // phi1, so it is formed and summed in FP32 (relative error ~1e-6 of itself).
+    double m[10];
+    float h[10];
 #pragma unroll
-    for (int k = 0; k < 4; k++) m[k] = 0.0;
-#pragma unroll
-    for (int k = 0; k < 16; k++) h[k] = 0.f;
+    for (int k = 0; k < 10; k++) { m[k] = 0.0; h[k] = 0.f; }
     const int cu = cell_of[t];
     const int cx = cu % G.n[0], cy = (cu / G.n[0]) % G.n[1], cz = cu / (G.n[0] * G.n[1]);
     const DimRange rz = dim_range(cz, reach.z, G.n[2], G.periodic), ry = dim_range(cy, reach.y, G.n[1], G.periodic);
@@ -468,14 +492,15 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
                 const double f0 = sa.w * ri * ri2;      // field0 = q/r^3
                 m[0] += sa.w * ri;                      // phi0 += field0*r2
                 m[1] -= dx * f0; m[2] -= dy * f0; m[3] -= dz * f0;
-                // phi2 (FP32): field1 = 3 q/r^5; xx xy xz yy yz zz
-                const float fx = (float)dx, fy = (float)dy, fz = (float)dz, qf = (float)sa.w;
-                const float rif2 = rif * rif, f0f = qf * rif * rif2, f1f = 3.0f * f0f * rif2;
-                const float tx = f1f * fx, ty = f1f * fy, tz = f1f * fz;
-                h[10] += tx * fx - f0f; h[11] += tx * fy; h[12] += tx * fz;
-                h[13] += ty * fy - f0f; h[14] += ty * fz; h[15] += tz * fz - f0f;
+                // phi2: field1 = 3 field0/r^2; xx xy xz yy yz zz
+                const double f1 = 3.0 * f0 * ri2;
+                const double tx = f1 * dx, ty = f1 * dy, tz = f1 * dz;
+                m[4] += tx * dx - f0; m[5] += tx * dy; m[6] += tx * dz;
+                m[7] += ty * dy - f0; m[8] += ty * dz; m[9] += tz * dz - f0;
                 // phi3 (FP32): field2 = -field1/r^2 = -3 q/r^7; xxx xxy xxz xyy xyz xzz yyy yyz yzz zzz
-                const float f2 = -f1f * rif2;
+                const float fx = (float)dx, fy = (float)dy, fz = (float)dz;
+                const float rif2 = rif * rif;
+                const float f2 = -3.0f * (float)sa.w * rif * rif2 * rif2 * rif2;
                 const float g5 = 5.0f * f2, gr = f2 * (fx * fx + fy * fy + fz * fz);
                 const float ax = g5 * fx, ay = g5 * fy, az = g5 * fz;
                 const float axx = ax * fx, axy = ax * fy, axz = ax * fz, ayy = ay * fy, ayz = ay * fz, azz = az * fz;
@@ -495,11 +520,10 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
     }
     // red[.][0..3] = phi0, phi1; [4..9] = phi2 unique; [10..19] = phi3 unique
 #pragma unroll
-    for (int k = 0; k < 4; k++) { const double a = warp_sum(m[k]); if (lane == 0) red[wid][k] = a; }
-#pragma unroll
-    for (int k = 0; k < 6; k++) { const double a = warp_sum((double)h[10 + k]); if (lane == 0) red[wid][4 + k] = a; }
-#pragma unroll
-    for (int k = 0; k < 10; k++) { const double a = warp_sum((double)h[k]); if (lane == 0) red[wid][10 + k] = a; }
+    for (int k = 0; k < 10; k++) {
+        const double a = warp_sum(m[k]), b3 = warp_sum((double)h[k]);
+        if (lane == 0) { red[wid][k] = a; red[wid][10 + k] = b3; }
+    }
     __syncthreads();
     __shared__ double mm[20];
     if (threadIdx.x < 20) {
