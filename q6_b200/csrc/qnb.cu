@@ -127,6 +127,7 @@ struct qnb_handle {
         qp_shift_atom;
     DBuf<uint32_t> rows;
     DBuf<double4> item_pos, src;
+    DBuf<float4> item_posf;
     DBuf<int> cell_unsorted, item_nq, src_off, pk_atom, pk_ct;
     DBuf<float> pk_q;
     DBuf<double> pk_qd, px, py, pz;
@@ -299,7 +300,7 @@ static void make_grid(qnb_handle *h, const double *hx) {
     const double rl = std::sqrt(std::max(h->cut.rclrf2, 0.0));
     int r[3];
     for (int d = 0; d < 3; d++) {
-        double m = std::ceil(rl * G.inv_cell[d] * 1.0001) + 1;
+        double m = std::ceil(rl * G.inv_cell[d] * 1.0001);   // |cell index difference| <= ceil(R/edge), also after clamping
         r[d] = (all || m > G.n[d]) ? G.n[d] : (int)m;
     }
     h->lrf_reach = make_int3(r[0], r[1], r[2]);
@@ -322,7 +323,7 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
         h->row_off.ensure(std::max(nu, 1) + 2) ||
         h->flag.ensure(std::max({D.natom, D.nwat, 1}) + 1) || h->pos.ensure(std::max({D.natom, D.nwat, 1}) + 2) ||
         h->qp_list.ensure(std::max(D.nat_solute, 1)) || h->qw_list.ensure(std::max(D.nwat, 1)) ||
-        h->qp_shift_atom.ensure(std::max(D.ncgp_solute, 1)) || h->item_pos.ensure(std::max(nu, 1)) ||
+        h->qp_shift_atom.ensure(std::max(D.ncgp_solute, 1)) || h->item_pos.ensure(std::max(nu, 1)) || h->item_posf.ensure(std::max(nu, 1)) ||
         h->src.ensure(std::max(D.natom, 1)) || h->cell_unsorted.ensure(std::max(nu, 1)) ||
         h->item_nq.ensure(std::max(nu, 1) + 1) || h->src_off.ensure(std::max(nu, 1) + 2) ||
         h->pk_atom.ensure(std::max(D.natom, 1)) || h->pk_ct.ensure(std::max(D.natom, 1)) || h->pk_q.ensure(std::max(D.natom, 1)) ||
@@ -337,7 +338,7 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
         CU(cudaMemsetAsync(h->cell_count.p, 0, sizeof(int) * (G.ncell + 1), h->st));
         LAUNCH(h, k_cell_fill, cdiv(nu, 256), 256, 0, nu, h->cell_of.p, h->cell_start.p, h->cell_count.p, h->cell_unsorted.p);
         LAUNCH(h, k_cell_sort, G.ncell, 64, 0, G.ncell, h->cell_start.p, h->cell_unsorted.p, h->cell_items.p);
-        LAUNCH(h, k_pack_items, cdiv(nu, 256), 256, 0, D, h->upos.p, h->cell_items.p, h->item_pos.p, h->item_nq.p);
+        LAUNCH(h, k_pack_items, cdiv(nu, 256), 256, 0, D, h->upos.p, h->cell_items.p, h->item_pos.p, h->item_posf.p, h->item_nq.p);
         run_exclusive_scan(h, h->item_nq.p, h->src_off.p, nu);
         LAUNCH(h, k_pack_atoms, cdiv(nu, 128), 128, 0, D, h->cell_items.p, h->src_off.p, h->pk_atom.p, h->pk_q.p, h->pk_qd.p, h->pk_ct.p);
         LAUNCH(h, k_build_rows<false>, cdiv(nu * 32, 256), 256, 0, D, h->cut, G, h->upos.p, h->cell_of.p, h->cell_start.p,
@@ -397,7 +398,7 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
         if (nu > 0) {
             if (h->npk > 0) LAUNCH(h, k_pack_sources, cdiv(h->npk, 256), 256, 0, h->npk, h->pk_atom.p, h->x.p, h->crg.p, h->src.p);
             LAUNCH(h, k_lrf_accumulate, nu, 32 * kRowWarps, 0, D, h->cut, G, h->lrf_reach, h->x.p, h->upos.p,
-                   h->cell_of.p, h->cell_start.p, h->item_pos.p, h->src_off.p, h->src.p, h->lrf.p);
+                   h->cell_of.p, h->cell_start.p, h->item_pos.p, h->item_posf.p, h->src_off.p, h->src.p, h->lrf.p);
         }
         if (h->comm) {
             // lrf_gather (nonbondene.f90:616-623): sum the moments, keep cgp_cent (identical on every rank).
@@ -987,6 +988,7 @@ int qnb_finalize(qnb_handle *h) {
     h->qw_list.release(); h->qp_shift_atom.release(); h->rows.release(); h->flush.release();
     h->pk_atom.release(); h->pk_ct.release(); h->pk_q.release(); h->pk_qd.release(); h->px.release(); h->py.release(); h->pz.release();
     h->nch.release(); h->choff.release(); h->wdesc.release(); h->wrow.release();
+    h->item_posf.release();
     h->item_pos.release(); h->src.release(); h->cell_unsorted.release(); h->item_nq.release(); h->src_off.release();
     if (h->hx) cudaFreeHost(h->hx);
     if (h->hout) cudaFreeHost(h->hout);

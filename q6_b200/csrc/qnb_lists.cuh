@@ -92,11 +92,12 @@ __global__ void k_cell_sort(int ncell, const int *__restrict__ cell_start, const
 // cell-ordered copies of what the pair searches read: switch-atom position + unit id, and the number of
 // LRF source atoms (non-Q atoms of the unit's charge group)
 __global__ void k_pack_items(Dev D, const double *__restrict__ upos, const int *__restrict__ cell_items,
-                             double4 *__restrict__ item_pos, int *__restrict__ item_nq) {
+                             double4 *__restrict__ item_pos, float4 *__restrict__ item_posf, int *__restrict__ item_nq) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= D.nunit) return;
     const int u = cell_items[idx];
     item_pos[idx] = make_double4(upos[3 * u], upos[3 * u + 1], upos[3 * u + 2], __longlong_as_double((long long)u));
+    item_posf[idx] = make_float4((float)upos[3 * u], (float)upos[3 * u + 1], (float)upos[3 * u + 2], __int_as_float(u));
     item_nq[idx] = D.u_excl[u] ? 0 : D.g_nq[D.u_grp[u]];
 }
 // Packed atoms: the non-Q atoms of every non-excluded unit, in cell order of the units.  Row entries are indices
@@ -431,10 +432,14 @@ __constant__ int kLrfExpand[40] = {0, 1, 2, 3,
 __global__ void __launch_bounds__(32 * kRowWarps)
 k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x, const double *__restrict__ upos,
                  const int *__restrict__ cell_of, const int *__restrict__ cell_start,
-                 const double4 *__restrict__ item_pos, const int *__restrict__ src_off,
-                 const double4 *__restrict__ src, double *__restrict__ lrf) {
-    // one block (kRowWarps warps) per target unit; the cell rows inside the LRF reach are dealt to the warps
+                 const double4 *__restrict__ item_pos, const float4 *__restrict__ item_posf,
+                 const int *__restrict__ src_off, const double4 *__restrict__ src, double *__restrict__ lrf) {
+    // one block (kRowWarps warps) per target unit; the cell rows inside the LRF reach are dealt to the warps.
+    // Candidates are first screened (FP32 distance with a safety band, exact FP64 test inside the band) and the
+    // accepted ones compacted into a per-warp queue, so that the expensive accumulation always runs on full warps
+    // even when only a few percent of the scanned cells' units lie inside the LRF shell (periodic boxes).
     __shared__ double red[kRowWarps][20];
+    __shared__ int queue[kRowWarps][64];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int t = blockIdx.x;
     if (D.u_excl[t]) return;   // block-uniform
@@ -443,6 +448,13 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
     double *lt = lrf + (size_t)QNB_LRF_STRIDE * gt;
     const double cx_ = lt[0], cy_ = lt[1], cz_ = lt[2];
     const double pt[3] = {upos[3 * t], upos[3 * t + 1], upos[3 * t + 2]};
+    const float ptf[3] = {(float)pt[0], (float)pt[1], (float)pt[2]};
+    const float boxf[3] = {(float)D.box[0], (float)D.box[1], (float)D.box[2]};
+    const float iboxf[3] = {(float)D.inv_box[0], (float)D.inv_box[1], (float)D.inv_box[2]};
+    const float rcmin = (float)fmin(C.rc2[0], fmin(C.rc2[1], C.rc2[2]));
+    const float lo_band = rcmin * (1.0f - 1e-3f) - 0.05f;          // surely listed below this
+    const float hi_band = (float)C.rclrf2 * (1.0f + 1e-3f) + 0.05f;   // surely outside the LRF shell above this
+    const bool any_all = C.lrf_all[0] || C.lrf_all[1] || C.lrf_all[2];
     // phi0, phi1, phi2 in FP64 (FP32 phi2 was measured to move E%LRF by 1.1e-6 relative).  phi3 enters only the field,
     // as 1/2 dr.phi3.dr with |dr| ~ 1 A (atom to group centre) against r >= Rc: a (dr/r)^2 ~ 1e-2 correction to
     // phi1, so it is formed and summed in FP32 (relative error ~1e-6 of itself).
@@ -450,11 +462,60 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
     float h[10];
 #pragma unroll
     for (int k = 0; k < 10; k++) { m[k] = 0.0; h[k] = 0.f; }
+
+    auto accumulate = [&](int idx) {
+        // lrf_update(group1 = source unit of item idx, group2 = target): dr = x(i) - cgp_cent(target) - shift
+        double ox = cx_, oy = cy_, oz = cz_;
+        if (D.use_PBC) {
+            // shift = boxlength*nint((x(cgp(group1)%iswitch) - lrf(group2)%cgp_cent)*inv_boxl)
+            const int s = __float_as_int(item_posf[idx].w);
+            const int isw = D.g_switch[D.u_grp[s]];
+            ox += pshift(x[3 * isw] - cx_, D.box[0], D.inv_box[0]);
+            oy += pshift(x[3 * isw + 1] - cy_, D.box[1], D.inv_box[1]);
+            oz += pshift(x[3 * isw + 2] - cz_, D.box[2], D.inv_box[2]);
+        }
+        const int a0 = src_off[idx], a1 = src_off[idx + 1];
+        for (int k = a0; k < a1; k++) {
+            const double4 sa = src[k];
+            const double dx = sa.x - ox, dy = sa.y - oy, dz = sa.z - oz;
+            const double r2 = dx * dx + dy * dy + dz * dz;
+            const float rif = rsqrtf((float)r2);
+            const double ri = rsqrt_refine(r2, rif), ri2 = ri * ri;
+            const double f0 = sa.w * ri * ri2;      // field0 = q/r^3
+            m[0] += sa.w * ri;                      // phi0 += field0*r2
+            m[1] -= dx * f0; m[2] -= dy * f0; m[3] -= dz * f0;
+            // phi2: field1 = 3 field0/r^2; xx xy xz yy yz zz
+            const double f1 = 3.0 * f0 * ri2;
+            const double tx = f1 * dx, ty = f1 * dy, tz = f1 * dz;
+            m[4] += tx * dx - f0; m[5] += tx * dy; m[6] += tx * dz;
+            m[7] += ty * dy - f0; m[8] += ty * dz; m[9] += tz * dz - f0;
+            // phi3 (FP32): field2 = -field1/r^2 = -3 q/r^7; xxx xxy xxz xyy xyz xzz yyy yyz yzz zzz
+            const float fx = (float)dx, fy = (float)dy, fz = (float)dz;
+            const float rif2 = rif * rif;
+            const float f2 = -3.0f * (float)sa.w * rif * rif2 * rif2 * rif2;
+            const float g5 = 5.0f * f2, gr = f2 * (fx * fx + fy * fy + fz * fz);
+            const float ax = g5 * fx, ay = g5 * fy, az = g5 * fz;
+            const float axx = ax * fx, axy = ax * fy, axz = ax * fz, ayy = ay * fy, ayz = ay * fz, azz = az * fz;
+            const float gx = gr * fx, gy = gr * fy, gz = gr * fz;
+            h[0] += axx * fx - 3.0f * gx;
+            h[1] += axx * fy - gy;
+            h[2] += axx * fz - gz;
+            h[3] += axy * fy - gx;
+            h[4] += axy * fz;
+            h[5] += axz * fz - gx;
+            h[6] += ayy * fy - 3.0f * gy;
+            h[7] += ayy * fz - gz;
+            h[8] += ayz * fz - gy;
+            h[9] += azz * fz - 3.0f * gz;
+        }
+    };
+
     const int cu = cell_of[t];
     const int cx = cu % G.n[0], cy = (cu / G.n[0]) % G.n[1], cz = cu / (G.n[0] * G.n[1]);
     const DimRange rz = dim_range(cz, reach.z, G.n[2], G.periodic), ry = dim_range(cy, reach.y, G.n[1], G.periodic);
     const XSeg xs = x_segments(cx, reach.x, G.n[0], G.periodic);
     const int nrow = rz.count * ry.count * xs.n;
+    int qn = 0;   // entries waiting in this warp's queue (warp-uniform)
     for (int r = wid; r < nrow; r += kRowWarps) {
         const int sgi = r % xs.n, iy = (r / xs.n) % ry.count, iz = r / (xs.n * ry.count);
         int z = rz.start + iz; z = (z % G.n[2] + G.n[2]) % G.n[2];
@@ -462,63 +523,48 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
         const int rowbase = (z * G.n[1] + y) * G.n[0];
         const int lo = cell_start[rowbase + (sgi == 0 ? xs.lo[0] : xs.lo[1])];
         const int hi = cell_start[rowbase + (sgi == 0 ? xs.hi[0] : xs.hi[1])];
-        for (int idx = lo + lane; idx < hi; idx += 32) {
-            const double4 ip = item_pos[idx];
-            const int s = (int)__double_as_longlong(ip.w);
-            const int a0 = src_off[idx], a1 = src_off[idx + 1];   // empty for excluded units
-            if (s == t || a0 == a1) continue;
-            bool owner_is_t;
-            const int cls = pair_class(t, s, ns, owner_is_t);
-            if (!in_shard(D, cls, owner_is_t ? t : s)) continue;
-            const double ps[3] = {ip.x, ip.y, ip.z};
-            const double r2u = owner_is_t ? unit_r2(D, pt, ps) : unit_r2(D, ps, pt);
-            if (r2u <= C.rc2_of(cls)) continue;                      // listed pair, not LRF
-            if (!(r2u <= C.rclrf2 || C.lrf_all_of(cls))) continue;   // beyond the LRF cut-off
-            // lrf_update(group1 = source, group2 = target): dr = x(i) - cgp_cent(target) - shift
-            double ox = cx_, oy = cy_, oz = cz_;
-            if (D.use_PBC) {
-                // shift = boxlength*nint((x(cgp(group1)%iswitch) - lrf(group2)%cgp_cent)*inv_boxl)
-                const int isw = D.g_switch[D.u_grp[s]];
-                ox += pshift(x[3 * isw] - cx_, D.box[0], D.inv_box[0]);
-                oy += pshift(x[3 * isw + 1] - cy_, D.box[1], D.inv_box[1]);
-                oz += pshift(x[3 * isw + 2] - cz_, D.box[2], D.inv_box[2]);
+        for (int base = lo; base < hi; base += 32) {
+            const int idx = base + lane;
+            bool accept = false;
+            if (idx < hi) {
+                const float4 pf = item_posf[idx];
+                const int s = __float_as_int(pf.w);
+                float dxf = pf.x - ptf[0], dyf = pf.y - ptf[1], dzf = pf.z - ptf[2];
+                if (D.use_PBC) {
+                    dxf -= boxf[0] * rintf(dxf * iboxf[0]); dyf -= boxf[1] * rintf(dyf * iboxf[1]); dzf -= boxf[2] * rintf(dzf * iboxf[2]);
+                }
+                const float r2f = dxf * dxf + dyf * dyf + dzf * dzf;
+                const bool maybe = s != t && r2f >= lo_band && (any_all || r2f <= hi_band) && src_off[idx + 1] > src_off[idx];
+                if (maybe) {
+                    bool owner_is_t;
+                    const int cls = pair_class(t, s, ns, owner_is_t);
+                    if (in_shard(D, cls, owner_is_t ? t : s)) {
+                        const double4 ip = item_pos[idx];
+                        const double ps[3] = {ip.x, ip.y, ip.z};
+                        const double r2u = owner_is_t ? unit_r2(D, pt, ps) : unit_r2(D, ps, pt);
+                        // outside the class cut-off (else: a listed pair) and inside the LRF cut-off
+                        accept = !(r2u <= C.rc2_of(cls)) && (r2u <= C.rclrf2 || C.lrf_all_of(cls));
+                    }
+                }
             }
-            for (int k = a0; k < a1; k++) {
-                const double4 sa = src[k];
-                const double dx = sa.x - ox, dy = sa.y - oy, dz = sa.z - oz;
-                const double r2 = dx * dx + dy * dy + dz * dz;
-                const float rif = rsqrtf((float)r2);
-                const double ri = rsqrt_refine(r2, rif), ri2 = ri * ri;
-                const double f0 = sa.w * ri * ri2;      // field0 = q/r^3
-                m[0] += sa.w * ri;                      // phi0 += field0*r2
-                m[1] -= dx * f0; m[2] -= dy * f0; m[3] -= dz * f0;
-                // phi2: field1 = 3 field0/r^2; xx xy xz yy yz zz
-                const double f1 = 3.0 * f0 * ri2;
-                const double tx = f1 * dx, ty = f1 * dy, tz = f1 * dz;
-                m[4] += tx * dx - f0; m[5] += tx * dy; m[6] += tx * dz;
-                m[7] += ty * dy - f0; m[8] += ty * dz; m[9] += tz * dz - f0;
-                // phi3 (FP32): field2 = -field1/r^2 = -3 q/r^7; xxx xxy xxz xyy xyz xzz yyy yyz yzz zzz
-                const float fx = (float)dx, fy = (float)dy, fz = (float)dz;
-                const float rif2 = rif * rif;
-                const float f2 = -3.0f * (float)sa.w * rif * rif2 * rif2 * rif2;
-                const float g5 = 5.0f * f2, gr = f2 * (fx * fx + fy * fy + fz * fz);
-                const float ax = g5 * fx, ay = g5 * fy, az = g5 * fz;
-                const float axx = ax * fx, axy = ax * fy, axz = ax * fz, ayy = ay * fy, ayz = ay * fz, azz = az * fz;
-                const float gx = gr * fx, gy = gr * fy, gz = gr * fz;
-                h[0] += axx * fx - 3.0f * gx;
-                h[1] += axx * fy - gy;
-                h[2] += axx * fz - gz;
-                h[3] += axy * fy - gx;
-                h[4] += axy * fz;
-                h[5] += axz * fz - gx;
-                h[6] += ayy * fy - 3.0f * gy;
-                h[7] += ayy * fz - gz;
-                h[8] += ayz * fz - gy;
-                h[9] += azz * fz - 3.0f * gz;
+            const unsigned mask = __ballot_sync(kFull, accept);
+            if (accept) queue[wid][qn + __popc(mask & ((1u << lane) - 1u))] = idx;
+            qn += __popc(mask);
+            __syncwarp();
+            if (qn >= 32) {
+                accumulate(queue[wid][lane]);
+                const int rest = qn - 32;
+                int moved = 0;
+                if (lane < rest) moved = queue[wid][32 + lane];
+                __syncwarp();
+                if (lane < rest) queue[wid][lane] = moved;
+                qn = rest;
+                __syncwarp();
             }
         }
     }
-    // red[.][0..3] = phi0, phi1; [4..9] = phi2 unique; [10..19] = phi3 unique
+    if (lane < qn) accumulate(queue[wid][lane]);
+    __syncwarp();
 #pragma unroll
     for (int k = 0; k < 10; k++) {
         const double a = warp_sum(m[k]), b3 = warp_sum((double)h[k]);
