@@ -133,9 +133,9 @@ struct qnb_handle {
     DBuf<double> pk_qd, px, py, pz;
     int npk = 0;   // packed atoms: non-Q atoms of non-excluded units in cell order
     DBuf<int> nch, choff;
-    DBuf<int2> wdesc;
-    DBuf<uint32_t> wrow;
-    int nwchunk = 0;   // water-row chunks
+    DBuf<int2> wdesc, sdesc;
+    DBuf<uint32_t> wrow, srow;
+    int nwchunk = 0, nschunk = 0;   // water-row / solute-row chunks
     int nqp = 0, nqw = 0;
     bool qp_done = false, qw_done = false, lists_built = false;
     int64_t total_rows = 0;
@@ -354,18 +354,24 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
         if (h->rows.ensure((size_t)std::max(total, 1))) return 1;
         LAUNCH(h, k_build_rows<true>, cdiv(nu * 32, 256), 256, 0, D, h->cut, G, h->upos.p, h->cell_of.p, h->cell_start.p,
                h->item_pos.p, h->src_off.p, h->counts.p, h->row_off.p, h->rows.p);
-        // chunked copy of the water rows for the streaming force kernel
-        h->nwchunk = 0;
-        if (D.nwat > 0) {
-            if (h->nch.ensure(D.nwat + 1) || h->choff.ensure(D.nwat + 2)) return 1;
-            LAUNCH(h, k_chunk_count, cdiv(D.nwat, 256), 256, 0, D.ncgp_solute, D.nwat, h->counts.p, h->nch.p);
-            run_exclusive_scan(h, h->nch.p, h->choff.p, D.nwat);
-            CU(cudaMemcpyAsync(&h->nwchunk, h->choff.p + D.nwat, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+        // chunked copies of the rows for the streaming force kernels
+        h->nwchunk = h->nschunk = 0;
+        for (int pass = 0; pass < 2; pass++) {
+            const int u0 = pass == 0 ? D.ncgp_solute : 0, n = pass == 0 ? D.nwat : D.ncgp_solute;
+            const int tile_atoms = pass == 0 ? 0 : kITile;
+            if (n <= 0) continue;
+            int &nchunk = pass == 0 ? h->nwchunk : h->nschunk;
+            DBuf<int2> &desc = pass == 0 ? h->wdesc : h->sdesc;
+            DBuf<uint32_t> &crow = pass == 0 ? h->wrow : h->srow;
+            if (h->nch.ensure(n + 1) || h->choff.ensure(n + 2)) return 1;
+            LAUNCH(h, k_chunk_count, cdiv(n, 256), 256, 0, D, u0, n, tile_atoms, h->counts.p, h->nch.p);
+            run_exclusive_scan(h, h->nch.p, h->choff.p, n);
+            CU(cudaMemcpyAsync(&nchunk, h->choff.p + n, sizeof(int), cudaMemcpyDeviceToHost, h->st));
             CU(cudaStreamSynchronize(h->st));
-            if (h->nwchunk > 0) {
-                if (h->wdesc.ensure(h->nwchunk) || h->wrow.ensure((size_t)h->nwchunk * 32)) return 1;
-                LAUNCH(h, k_chunk_fill, cdiv(D.nwat * 32, 256), 256, 0, D.ncgp_solute, D.nwat, h->counts.p, h->row_off.p,
-                       h->rows.p, h->choff.p, h->wdesc.p, h->wrow.p);
+            if (nchunk > 0) {
+                if (desc.ensure(nchunk) || crow.ensure((size_t)nchunk * 32)) return 1;
+                LAUNCH(h, k_chunk_fill, cdiv(n * 32, 256), 256, 0, D, u0, n, tile_atoms, h->counts.p, h->row_off.p, h->rows.p,
+                       h->choff.p, desc.p, crow.p);
             }
         }
     }
@@ -425,7 +431,7 @@ static bool step_kernel_active(const qnb_handle *h, int k, int flags) {
     const bool md = flags & QNB_FLAG_MD;
     switch (k) {
     case K_WATER: return md && D.nwat > 0 && h->nwchunk > 0;
-    case K_SOLUTE: return md && D.ncgp_solute > 0;
+    case K_SOLUTE: return md && D.ncgp_solute > 0 && h->nschunk > 0;
     case K_QPARTNER: return D.nqat > 0 && (h->nqp + h->nqw) > 0;
     case K_QATOM: return D.nqat > 0 && (h->nqp + h->nqw) > 0;
     case K_QSTATIC: return (flags & QNB_FLAG_QQ) && h->T.s.is_master && h->n_qstatic > 0;
@@ -450,8 +456,9 @@ static void launch_step_kernel(qnb_handle *h, int k, cudaStream_t cs) {
         break;
     }
     case K_SOLUTE: {
-        const int grid = D.ncgp_solute;
-#define SCASE(P, G) LAUNCH_ON(h, cs, (k_solute_force<P, G>), grid, 32 * kRowWarps, 0, D, h->x.p, h->px.p, h->py.p, h->pz.p, h->pk_q.p, h->pk_qd.p, h->pk_ct.p, h->pk_atom.p, h->row_off.p, h->counts.p, h->rows.p, grad, E, nE)
+        const int grid = std::max(1, std::min(3 * h->nsm, cdiv(h->nschunk, 4 * 4)));
+        const size_t sm = (size_t)D.nct * 6 * (sizeof(double) + sizeof(float)) + (size_t)D.nct * D.nct;
+#define SCASE(P, G) LAUNCH_ON(h, cs, (k_solute_force<P, G>), grid, 128, sm, D, h->x.p, h->px.p, h->py.p, h->pz.p, h->pk_q.p, h->pk_qd.p, h->pk_ct.p, h->pk_atom.p, h->nschunk, h->sdesc.p, h->srow.p, grad, E, nE)
         if (pbc) { if (geom) SCASE(true, true); else SCASE(true, false); }
         else { if (geom) SCASE(false, true); else SCASE(false, false); }
 #undef SCASE
@@ -987,7 +994,7 @@ int qnb_finalize(qnb_handle *h) {
     h->row_tot.release(); h->row_off.release(); h->flag.release(); h->pos.release(); h->qp_list.release();
     h->qw_list.release(); h->qp_shift_atom.release(); h->rows.release(); h->flush.release();
     h->pk_atom.release(); h->pk_ct.release(); h->pk_q.release(); h->pk_qd.release(); h->px.release(); h->py.release(); h->pz.release();
-    h->nch.release(); h->choff.release(); h->wdesc.release(); h->wrow.release();
+    h->nch.release(); h->choff.release(); h->wdesc.release(); h->wrow.release(); h->sdesc.release(); h->srow.release();
     h->item_posf.release();
     h->item_pos.release(); h->src.release(); h->cell_unsorted.release(); h->item_nq.release(); h->src_off.release();
     if (h->hx) cudaFreeHost(h->hx);

@@ -91,7 +91,7 @@ __device__ __forceinline__ void lj_pair_f64(const double *__restrict__ ljd, int 
 // c+1 are in flight while chunk c is computed -- because at 12k atoms the work is latency-bound (three dependent
 // L2 round trips per chunk against ~500 issue cycles of arithmetic).  Gradients of the current water are kept in
 // registers across its chunks and flushed (FP64 shuffle reduction + 9 atomicAdd) when the water changes.
-constexpr int kChunkOwn = 0, kChunkMir = 1, kChunkB = 2;
+constexpr int kChunkA = 0, kChunkB = 1;   // A: partner units of the own kind (own + mirror entries), B: the other kind
 constexpr uint32_t kPadEntry = 0xffffffffu;
 
 struct WaterTile {          // own molecule of the row being processed
@@ -102,8 +102,8 @@ struct WaterTile {          // own molecule of the row being processed
 };
 
 template <bool PBC, bool SPC>
-__device__ __forceinline__ void ww_chunk(const Dev &D, WaterTile &T, bool own, bool valid, const double (&pj)[9],
-                                         double &eel, double &evdw) {
+__device__ __forceinline__ void ww_chunk(const Dev &D, WaterTile &T, bool own, bool any_own, bool valid,
+                                         const double (&pj)[9], double &eel, double &evdw) {
     if (!valid) return;
     // pj = x,y,z of the partner's three sites (SoA order: x0 x1 x2 y0 y1 y2 z0 z1 z2)
     double shx = 0, shy = 0, shz = 0;
@@ -130,7 +130,7 @@ __device__ __forceinline__ void ww_chunk(const Dev &D, WaterTile &T, bool own, b
             if (lj) dv = pair_f32<true, false>(dx, dy, dz, D.wwQ[a * 3 + b], D.wwA[a * 3 + b], D.wwB[a * 3 + b], rinv, ev);
             else dv = pair_f32<false, false>(dx, dy, dz, D.wwQ[a * 3 + b], 0.f, 0.f, rinv, ev);
             T.g[a][0] = fmaf(-dx, dv, T.g[a][0]); T.g[a][1] = fmaf(-dy, dv, T.g[a][1]); T.g[a][2] = fmaf(-dz, dv, T.g[a][2]);
-            if (own) {
+            if (any_own && own) {   // any_own is warp-uniform: mirror-only chunks skip the FP64 code altogether
                 if (lj) energy_f64(ud[b][0] - T.sd[a][0], ud[b][1] - T.sd[a][1], ud[b][2] - T.sd[a][2], D.wwQd[a * 3 + b],
                                    D.wwAd[a * 3 + b], D.wwBd[a * 3 + b], rinv, eel, evdw);
                 else eel += coulomb_f64(ud[b][0] - T.sd[a][0], ud[b][1] - T.sd[a][1], ud[b][2] - T.sd[a][2], D.wwQd[a * 3 + b], rinv);
@@ -237,7 +237,10 @@ k_water_force(Dev D, const double *__restrict__ x, const double *__restrict__ px
         }
         const bool valid = e0 != kPadEntry;
         if (d0.y == kChunkB) wp_chunk<PBC, GEOM>(D, T, valid, p0, q0, ct0, (int)(e0 & kIdMask), x, pk_atom);
-        else ww_chunk<PBC, SPC>(D, T, d0.y == kChunkOwn, valid, p0, eel, evdw);
+        else {
+            const bool own = valid && (e0 & kOwnerBit);
+            ww_chunk<PBC, SPC>(D, T, own, __any_sync(kFull, own), valid, p0, eel, evdw);
+        }
         d0 = d1; e0 = e1; q0 = q1; ct0 = ct1;
 #pragma unroll
         for (int k = 0; k < 9; k++) p0[k] = p1[k];
@@ -253,8 +256,9 @@ k_water_force(Dev D, const double *__restrict__ x, const double *__restrict__ px
 }
 
 // ------------------------------------------------------------------------------------------------
-// Solute rows: pp + the solute (owner) side of pw.  One warp per charge group, i-atoms in register
-// tiles of four.
+// Solute rows: pp + the solute (owner) side of pw.  Same persistent, software-pipelined structure as the water
+// kernel; a chunk belongs to one (charge group, tile of up to four non-Q atoms) and the tile's gradient stays in
+// registers across its chunks.  The per-type LJ tables live in shared memory.
 constexpr int kITile = 4;
 
 __device__ __forceinline__ int special_code(const Dev &D, int a, int b) {
@@ -268,165 +272,204 @@ __device__ __forceinline__ int special_code(const Dev &D, int a, int b) {
     return -1;
 }
 
+struct SoluteTile {
+    int g, nt;
+    int ai[kITile], cti[kITile];
+    double o[3];
+    double sd[kITile][3], qd[kITile];
+    float sf[kITile][3], qf[kITile];
+    float grad[kITile][3];
+};
+
 template <bool PBC, bool GEOM>
 __global__ void __launch_bounds__(128)
 k_solute_force(Dev D, const double *__restrict__ x, const double *__restrict__ px, const double *__restrict__ py,
                const double *__restrict__ pz, const float *__restrict__ pk_q, const double *__restrict__ pk_qd,
-               const int *__restrict__ pk_ct, const int *__restrict__ pk_atom, const int *__restrict__ row_off,
-               const int *__restrict__ counts, const uint32_t *__restrict__ rows, double *__restrict__ grad,
-               double *__restrict__ Eslots, int nE) {
+               const int *__restrict__ pk_ct, const int *__restrict__ pk_atom, int nchunk, const int2 *__restrict__ cdesc,
+               const uint32_t *__restrict__ crow, double *__restrict__ grad, double *__restrict__ Eslots, int nE) {
+    extern __shared__ unsigned char smem_raw[];
+    // shared LJ tables: ljd [nct*6] doubles, ljf [nct*6] floats, ljcode [nct*nct] bytes
+    double *s_ljd = reinterpret_cast<double *>(smem_raw);
+    float *s_ljf = reinterpret_cast<float *>(s_ljd + D.nct * 6);
+    unsigned char *s_code = reinterpret_cast<unsigned char *>(s_ljf + D.nct * 6);
+    for (int k = threadIdx.x; k < D.nct * 6; k += blockDim.x) { s_ljd[k] = D.ljd[k]; s_ljf[k] = D.ljf[k]; }
+    for (int k = threadIdx.x; k < D.nct * D.nct; k += blockDim.x) s_code[k] = D.ljcode[k];
+    __syncthreads();
+
     const int lane = threadIdx.x & 31;
-    const int gidx = blockIdx.x, wid = threadIdx.x >> 5;
-    const int kstart = wid * 32 + lane, kstep = kRowWarps * 32;
-    __shared__ double red[kRowWarps][3 * kITile];
-    const int nown = counts[3 * gidx], nmir = counts[3 * gidx + 1], nb = counts[3 * gidx + 2];
-    if (nown + nmir + nb == 0) return;   // block-uniform
-    const uint32_t *row = rows + row_off[gidx];
-    const int gf = D.g_first[gidx], gn = D.g_n[gidx];
-    const int sw = D.g_switch[gidx];
-    const double ox = x[3 * sw], oy = x[3 * sw + 1], oz = x[3 * sw + 2];   // row origin = switch atom
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
+    const int per = (nchunk + nwarp - 1) / nwarp;
+    const int c0 = gw * per, c1 = min(nchunk, c0 + per);
+    if (c0 >= c1) return;
+    SoluteTile T;
+    T.g = -1; T.nt = 0;
+    int cur_key = -1;
     double e_pp_el = 0.0, e_pw_el = 0.0, e_pp_vdw = 0.0, e_pw_vdw = 0.0;
 
-    int kscan = 0;   // position in the group's atom list
-    while (kscan < gn) {
-        // next tile of up to four non-Q atoms
-        int ai[kITile], cti[kITile];
-        float sf[kITile][3], qf[kITile];
-        double sd[kITile][3], qd[kITile];
-        int nt = 0;
-#pragma unroll
-        for (int t = 0; t < kITile; t++) { ai[t] = -1; cti[t] = 0; qf[t] = 0.f; qd[t] = 0.0;
-            sf[t][0] = sf[t][1] = sf[t][2] = 0.f; sd[t][0] = sd[t][1] = sd[t][2] = 0.0; }
+    auto flush = [&]() {
+        if (cur_key < 0) return;
 #pragma unroll
         for (int t = 0; t < kITile; t++) {
-            while (kscan < gn && D.is_q[D.g_atoms[gf + kscan]]) kscan++;
-            if (kscan < gn) {
-                const int a = D.g_atoms[gf + kscan++];
-                ai[t] = a; cti[t] = D.ctype[a]; qd[t] = D.crg[a]; qf[t] = (float)qd[t];
-                sd[t][0] = x[3 * a] - ox; sd[t][1] = x[3 * a + 1] - oy; sd[t][2] = x[3 * a + 2] - oz;
-                sf[t][0] = (float)sd[t][0]; sf[t][1] = (float)sd[t][1]; sf[t][2] = (float)sd[t][2];
-                nt = t + 1;
+            double sx = warp_sum((double)T.grad[t][0]), sy = warp_sum((double)T.grad[t][1]), sz = warp_sum((double)T.grad[t][2]);
+            if (t < T.nt && lane < 3) atomicAdd(&grad[3 * T.ai[t] + lane], lane == 0 ? sx : lane == 1 ? sy : sz);
+        }
+    };
+    auto load_tile = [&](int g, int tile) {
+        T.g = g;
+        const int gf = D.g_first[g], gn = D.g_n[g];
+        const int sw = D.g_switch[g];
+        T.o[0] = x[3 * sw]; T.o[1] = x[3 * sw + 1]; T.o[2] = x[3 * sw + 2];   // row origin = switch atom
+        int k = 0, seen = 0;
+        // skip the non-Q atoms of earlier tiles
+        while (k < gn && seen < tile * kITile) { if (!D.is_q[D.g_atoms[gf + k]]) seen++; k++; }
+        T.nt = 0;
+#pragma unroll
+        for (int t = 0; t < kITile; t++) {
+            T.ai[t] = -1; T.cti[t] = 0; T.qf[t] = 0.f; T.qd[t] = 0.0;
+#pragma unroll
+            for (int c = 0; c < 3; c++) { T.sf[t][c] = 0.f; T.sd[t][c] = 0.0; T.grad[t][c] = 0.f; }
+            while (k < gn && D.is_q[D.g_atoms[gf + k]]) k++;
+            if (k < gn) {
+                const int a = D.g_atoms[gf + k++];
+                T.ai[t] = a; T.cti[t] = D.ctype[a]; T.qd[t] = D.crg[a]; T.qf[t] = (float)T.qd[t];
+#pragma unroll
+                for (int c = 0; c < 3; c++) { T.sd[t][c] = x[3 * a + c] - T.o[c]; T.sf[t][c] = (float)T.sd[t][c]; }
+                T.nt = t + 1;
             }
         }
-        if (nt == 0) break;
-        float g[kITile][3];
+    };
+    auto lj32 = [&](int cta, int ctb, int code, float &A, float &B) {
+        const float ax = s_ljf[(cta * 3 + code - 1) * 2], ay = s_ljf[(cta * 3 + code - 1) * 2 + 1];
+        const float bx = s_ljf[(ctb * 3 + code - 1) * 2], by = s_ljf[(ctb * 3 + code - 1) * 2 + 1];
+        if (GEOM) { A = ax * bx; B = ay * by; }
+        else { float t = ax + bx; t = t * t; t = t * t * t; const float e = ay * by; A = t * t * e; B = 2.0f * t * e; }
+    };
+    auto lj64 = [&](int cta, int ctb, int code, double &A, double &B) {
+        const double ax = s_ljd[(cta * 3 + code - 1) * 2], ay = s_ljd[(cta * 3 + code - 1) * 2 + 1];
+        const double bx = s_ljd[(ctb * 3 + code - 1) * 2], by = s_ljd[(ctb * 3 + code - 1) * 2 + 1];
+        if (GEOM) { A = ax * bx; B = ay * by; }
+        else { double t = ax + bx; t = t * t; t = t * t * t; const double e = ay * by; A = t * t * e; B = 2.0 * t * e; }
+    };
+    // pipeline stages
+    auto load_a = [&](int c, int2 &d, uint32_t &e) { d = cdesc[c]; e = crow[(size_t)c * 32 + lane]; };
+    auto load_b = [&](const int2 &d, uint32_t e, double (&pj)[9], float &qb, double &qbd, int &ctb) {
+        if (e == kPadEntry) return;
+        const int p = (int)(e & kIdMask);
+        if ((d.y & 0xff) == kChunkB) {
 #pragma unroll
-        for (int t = 0; t < kITile; t++) g[t][0] = g[t][1] = g[t][2] = 0.f;
-
-        // ---- solute-solute partner atoms
-        for (int k = kstart; k < nown + nmir; k += kstep) {
-            const uint32_t e = row[k];
-            const bool own = k < nown;
-            const int pb = (int)(e & kIdMask);
-            const bool special = (e & kSpecialBit) != 0;
-            double ux = px[pb] - ox, uy = py[pb] - oy, uz = pz[pb] - oz;
-            int b = -1, gb = -1;       // atom id / group of the partner: only the special and periodic paths need them
-            if (special || PBC) { b = pk_atom[pb]; gb = D.grp_of_atom[b]; }
-            if (PBC) {
-                // nonbond_pp_box L4791-4801: shift = boxlength*nint((x(sw_i)-x(sw_j))*inv_boxl)
-                const int swb = D.g_switch[gb];
-                ux += pshift(ox - x[3 * swb], D.box[0], D.inv_box[0]);
-                uy += pshift(oy - x[3 * swb + 1], D.box[1], D.inv_box[1]);
-                uz += pshift(oz - x[3 * swb + 2], D.box[2], D.inv_box[2]);
-            }
-            const float ufx = (float)ux, ufy = (float)uy, ufz = (float)uz;
-            const float qb = pk_q[pb];
-            const double qbd = pk_qd[pb];
-            const int ctb = pk_ct[pb];
-            const bool same = special && gb == gidx;   // own-group partners are always flagged special
+            for (int b = 0; b < 3; b++) { pj[b] = px[p + b]; pj[3 + b] = py[p + b]; pj[6 + b] = pz[p + b]; }
+        } else {
+            pj[0] = px[p]; pj[3] = py[p]; pj[6] = pz[p];
+            qb = pk_q[p]; qbd = pk_qd[p]; ctb = pk_ct[p];
+        }
+    };
+    int2 d0, d1 = make_int2(-1, 0), d2 = make_int2(-1, 0);
+    uint32_t e0, e1 = kPadEntry, e2 = kPadEntry;
+    double p0[9], p1[9], qd0 = 0, qd1 = 0;
+    float q0 = 0.f, q1 = 0.f;
+    int ct0 = 0, ct1 = 0;
 #pragma unroll
-            for (int t = 0; t < kITile; t++) {
-                if (t < nt) {
-                    const int a = ai[t];
-                    int code = D.ljcode[cti[t] * D.nct + ctb];
-                    bool skip = false, i14 = false;
-                    if (special) {
-                        if (a == b) skip = true;
-                        else {
-                            const int sc = special_code(D, a, b);
-                            if (sc == 0) skip = true;
-                            else if (sc == 3) { code = 3; i14 = true; }
+    for (int k = 0; k < 9; k++) { p0[k] = 0.0; p1[k] = 0.0; }
+    load_a(c0, d0, e0);
+    if (c0 + 1 < c1) load_a(c0 + 1, d1, e1);
+    load_b(d0, e0, p0, q0, qd0, ct0);
+    for (int c = c0; c < c1; c++) {
+        if (c + 2 < c1) load_a(c + 2, d2, e2);
+        if (c + 1 < c1) load_b(d1, e1, p1, q1, qd1, ct1);
+        const int key = d0.x * 256 + (d0.y >> 8);   // (group, tile)
+        if (key != cur_key) { flush(); load_tile(d0.x, d0.y >> 8); cur_key = key; }
+        const bool valid = e0 != kPadEntry;
+        if ((d0.y & 0xff) == kChunkA) {
+            // ---- solute-solute partner atom
+            if (valid) {
+                const int pb = (int)(e0 & kIdMask);
+                const bool own = (e0 & kOwnerBit) != 0, special = (e0 & kSpecialBit) != 0;
+                double ux = p0[0] - T.o[0], uy = p0[3] - T.o[1], uz = p0[6] - T.o[2];
+                int b = -1, gb = -1;       // atom id / group of the partner: only the special and periodic paths need them
+                if (special || PBC) { b = pk_atom[pb]; gb = D.grp_of_atom[b]; }
+                if (PBC) {
+                    // nonbond_pp_box L4791-4801: shift = boxlength*nint((x(sw_i)-x(sw_j))*inv_boxl)
+                    const int swb = D.g_switch[gb];
+                    ux += pshift(T.o[0] - x[3 * swb], D.box[0], D.inv_box[0]);
+                    uy += pshift(T.o[1] - x[3 * swb + 1], D.box[1], D.inv_box[1]);
+                    uz += pshift(T.o[2] - x[3 * swb + 2], D.box[2], D.inv_box[2]);
+                }
+                const float ufx = (float)ux, ufy = (float)uy, ufz = (float)uz;
+                const bool same = special && gb == T.g;   // own-group partners are always flagged special
+#pragma unroll
+                for (int t = 0; t < kITile; t++) {
+                    if (t < T.nt) {
+                        const int a = T.ai[t];
+                        int code = s_code[T.cti[t] * D.nct + ct0];
+                        bool skip = false, i14 = false;
+                        if (special) {
+                            if (a == b) skip = true;
+                            else {
+                                const int sc = special_code(D, a, b);
+                                if (sc == 0) skip = true;
+                                else if (sc == 3) { code = 3; i14 = true; }
+                            }
                         }
-                    }
-                    if (!skip) {
-                        float A, B, rinv, ev = 0.f;
-                        lj_pair<GEOM>(D.ljf, cti[t], ctb, code, A, B);
-                        const float qq = i14 ? qf[t] * qb * D.el14f : qf[t] * qb;
-                        const float dx = ufx - sf[t][0], dy = ufy - sf[t][1], dz = ufz - sf[t][2];
-                        const float dv = pair_f32<true, false>(dx, dy, dz, qq, A, B, rinv, ev);
-                        g[t][0] = fmaf(-dx, dv, g[t][0]); g[t][1] = fmaf(-dy, dv, g[t][1]); g[t][2] = fmaf(-dz, dv, g[t][2]);
-                        // energy once per pair: on the owner side; inside one group on the lower atom (i<j, L1874)
-                        if (own && (!same || a < b)) {
-                            const double qqd = i14 ? qd[t] * qbd * D.el14 : qd[t] * qbd;
-                            double Ad, Bd;
-                            lj_pair_f64<GEOM>(D.ljd, cti[t], ctb, code, Ad, Bd);
-                            energy_f64(ux - sd[t][0], uy - sd[t][1], uz - sd[t][2], qqd, Ad, Bd, rinv, e_pp_el, e_pp_vdw);
+                        if (!skip) {
+                            float A, B, rinv, ev = 0.f;
+                            lj32(T.cti[t], ct0, code, A, B);
+                            const float qq = i14 ? T.qf[t] * q0 * D.el14f : T.qf[t] * q0;
+                            const float dx = ufx - T.sf[t][0], dy = ufy - T.sf[t][1], dz = ufz - T.sf[t][2];
+                            const float dv = pair_f32<true, false>(dx, dy, dz, qq, A, B, rinv, ev);
+                            T.grad[t][0] = fmaf(-dx, dv, T.grad[t][0]); T.grad[t][1] = fmaf(-dy, dv, T.grad[t][1]);
+                            T.grad[t][2] = fmaf(-dz, dv, T.grad[t][2]);
+                            // energy once per pair: on the owner side; inside one group on the lower atom (i<j, L1874)
+                            if (own && (!same || a < b)) {
+                                const double qqd = i14 ? T.qd[t] * qd0 * D.el14 : T.qd[t] * qd0;
+                                double Ad, Bd;
+                                lj64(T.cti[t], ct0, code, Ad, Bd);
+                                energy_f64(ux - T.sd[t][0], uy - T.sd[t][1], uz - T.sd[t][2], qqd, Ad, Bd, rinv, e_pp_el, e_pp_vdw);
+                            }
                         }
                     }
                 }
             }
-        }
-        // ---- solute-water: this side owns the pair, all three water atoms with full LJ (nbe)
-        const uint32_t *rowb = row + nown + nmir;
-        for (int k = kstart; k < nb; k += kstep) {
-            const int p0 = (int)(rowb[k] & kIdMask);   // packed index of the water's oxygen
+        } else if (valid) {
+            // ---- solute-water: this side owns the pair, all three water atoms with full LJ (nbe)
             double shx = 0, shy = 0, shz = 0;
             if (PBC) {
-                shx = pshift(ox - px[p0], D.box[0], D.inv_box[0]);
-                shy = pshift(oy - py[p0], D.box[1], D.inv_box[1]);
-                shz = pshift(oz - pz[p0], D.box[2], D.inv_box[2]);
+                shx = pshift(T.o[0] - p0[0], D.box[0], D.inv_box[0]);
+                shy = pshift(T.o[1] - p0[3], D.box[1], D.inv_box[1]);
+                shz = pshift(T.o[2] - p0[6], D.box[2], D.inv_box[2]);
             }
 #pragma unroll
             for (int s = 0; s < 3; s++) {
-                const double ux = (px[p0 + s] - ox) + shx, uy = (py[p0 + s] - oy) + shy, uz = (pz[p0 + s] - oz) + shz;
+                const double ux = (p0[s] - T.o[0]) + shx, uy = (p0[3 + s] - T.o[1]) + shy, uz = (p0[6 + s] - T.o[2]) + shz;
                 const float ufx = (float)ux, ufy = (float)uy, ufz = (float)uz;
                 const int ctb = D.wct[s];
 #pragma unroll
                 for (int t = 0; t < kITile; t++) {
-                    if (t < nt) {
-                        const int code = D.ljcode[cti[t] * D.nct + ctb];
+                    if (t < T.nt) {
+                        const int code = s_code[T.cti[t] * D.nct + ctb];
                         float A, B, rinv, ev = 0.f;
-                        lj_pair<GEOM>(D.ljf, cti[t], ctb, code, A, B);
-                        const float dx = ufx - sf[t][0], dy = ufy - sf[t][1], dz = ufz - sf[t][2];
-                        const float dv = pair_f32<true, false>(dx, dy, dz, qf[t] * D.wq[s], A, B, rinv, ev);
-                        g[t][0] = fmaf(-dx, dv, g[t][0]); g[t][1] = fmaf(-dy, dv, g[t][1]); g[t][2] = fmaf(-dz, dv, g[t][2]);
+                        lj32(T.cti[t], ctb, code, A, B);
+                        const float dx = ufx - T.sf[t][0], dy = ufy - T.sf[t][1], dz = ufz - T.sf[t][2];
+                        const float dv = pair_f32<true, false>(dx, dy, dz, T.qf[t] * D.wq[s], A, B, rinv, ev);
+                        T.grad[t][0] = fmaf(-dx, dv, T.grad[t][0]); T.grad[t][1] = fmaf(-dy, dv, T.grad[t][1]);
+                        T.grad[t][2] = fmaf(-dz, dv, T.grad[t][2]);
                         double Ad, Bd;
-                        lj_pair_f64<GEOM>(D.ljd, cti[t], ctb, code, Ad, Bd);
-                        energy_f64(ux - sd[t][0], uy - sd[t][1], uz - sd[t][2], qd[t] * D.wqd[s], Ad, Bd, rinv, e_pw_el, e_pw_vdw);
+                        lj64(T.cti[t], ctb, code, Ad, Bd);
+                        energy_f64(ux - T.sd[t][0], uy - T.sd[t][1], uz - T.sd[t][2], T.qd[t] * D.wqd[s], Ad, Bd, rinv, e_pw_el, e_pw_vdw);
                     }
                 }
             }
         }
+        d0 = d1; e0 = e1; q0 = q1; qd0 = qd1; ct0 = ct1;
 #pragma unroll
-        for (int t = 0; t < kITile; t++)
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                const double s = warp_sum((double)g[t][c]);
-                if (lane == 0) red[wid][t * 3 + c] = s;
-            }
-        __syncthreads();
-        if (threadIdx.x < 3 * kITile) {
-            const int t = threadIdx.x / 3;
-            double s = 0;
-#pragma unroll
-            for (int k = 0; k < kRowWarps; k++) s += red[k][threadIdx.x];
-            int at = -1;   // ai[] is a register array: select without dynamic indexing
-#pragma unroll
-            for (int tt = 0; tt < kITile; tt++) if (tt == t) at = ai[tt];
-            if (t < nt) atomicAdd(&grad[3 * at + (threadIdx.x - 3 * t)], s);
-        }
-        __syncthreads();
+        for (int k = 0; k < 9; k++) p0[k] = p1[k];
+        d1 = d2; e1 = e2;
     }
+    flush();
     const double s1 = warp_sum(e_pp_el), s2 = warp_sum(e_pp_vdw), s3 = warp_sum(e_pw_el), s4 = warp_sum(e_pw_vdw);
-    if (lane == 0) { red[wid][0] = s1; red[wid][1] = s2; red[wid][2] = s3; red[wid][3] = s4; }
-    __syncthreads();
-    if (threadIdx.x < 4) {
-        double s = 0;
-#pragma unroll
-        for (int k = 0; k < kRowWarps; k++) s += red[k][threadIdx.x];
-        double *E = Eslots + (size_t)(blockIdx.x & (kESlots - 1)) * nE;
-        const int idx[4] = {QNB_E_PP_EL, QNB_E_PP_VDW, QNB_E_PW_EL, QNB_E_PW_VDW};
-        if ((threadIdx.x < 2 && nown > 0) || (threadIdx.x >= 2 && nb > 0)) atomicAdd(&E[idx[threadIdx.x]], s);
+    if (lane == 0) {
+        double *E = Eslots + (size_t)(gw & (kESlots - 1)) * nE;
+        atomicAdd(&E[QNB_E_PP_EL], s1); atomicAdd(&E[QNB_E_PP_VDW], s2);
+        atomicAdd(&E[QNB_E_PW_EL], s3); atomicAdd(&E[QNB_E_PW_VDW], s4);
     }
 }
 

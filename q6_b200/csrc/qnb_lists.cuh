@@ -278,30 +278,39 @@ k_build_rows(Dev D, Cut C, Grid G, const double *__restrict__ upos, const int *_
     }
 }
 
-// ---- chunked re-layout of the rows of units [u0, u0+n): per unit ceil(nown/32)+ceil(nmir/32)+ceil(nb/32) chunks
-__global__ void k_chunk_count(int u0, int n, const int *__restrict__ counts, int *__restrict__ nch) {
+// ---- chunked re-layout of the rows of units [u0, u0+n): per unit and per i-tile ceil((nown+nmir)/32) chunks of
+// kind A and ceil(nb/32) chunks of kind B.  tile_atoms = 0: one tile per unit (waters); else tiles of that many
+// non-Q atoms of the unit's charge group (solute).
+__device__ __forceinline__ int unit_tiles(const Dev &D, int u, int tile_atoms) {
+    return tile_atoms == 0 ? 1 : (D.g_nq[u] + tile_atoms - 1) / tile_atoms;
+}
+__global__ void k_chunk_count(Dev D, int u0, int n, int tile_atoms, const int *__restrict__ counts, int *__restrict__ nch) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const int u = u0 + k;
-    nch[k] = (counts[3 * u] + 31) / 32 + (counts[3 * u + 1] + 31) / 32 + (counts[3 * u + 2] + 31) / 32;
+    nch[k] = unit_tiles(D, u, tile_atoms) * ((counts[3 * u] + counts[3 * u + 1] + 31) / 32 + (counts[3 * u + 2] + 31) / 32);
 }
-// one warp per unit: copy the three segments into 32-entry chunks padded with kPadEntry
-__global__ void k_chunk_fill(int u0, int n, const int *__restrict__ counts, const int *__restrict__ row_off,
-                             const uint32_t *__restrict__ rows, const int *__restrict__ choff,
-                             int2 *__restrict__ cdesc, uint32_t *__restrict__ crow) {
+// one warp per unit: copy the segments into 32-entry chunks padded with 0xffffffff; descriptor = {unit - u0, kind | tile << 8}
+__global__ void k_chunk_fill(Dev D, int u0, int n, int tile_atoms, const int *__restrict__ counts,
+                             const int *__restrict__ row_off, const uint32_t *__restrict__ rows,
+                             const int *__restrict__ choff, int2 *__restrict__ cdesc, uint32_t *__restrict__ crow) {
     const int lane = threadIdx.x & 31;
     const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (k >= n) return;
     const int u = u0 + k;
     int c = choff[k];
-    int base = row_off[u];
-    for (int seg = 0; seg < 3; seg++) {
-        const int m = counts[3 * u + seg];
-        for (int b = 0; b < m; b += 32, c++) {
-            if (lane == 0) cdesc[c] = make_int2(k, seg);
-            crow[(size_t)c * 32 + lane] = (b + lane < m) ? rows[base + b + lane] : 0xffffffffu;
+    const int ntile = unit_tiles(D, u, tile_atoms);
+    const int na = counts[3 * u] + counts[3 * u + 1], nb = counts[3 * u + 2];
+    for (int tile = 0; tile < ntile; tile++) {
+        int base = row_off[u];
+        for (int seg = 0; seg < 2; seg++) {
+            const int m = seg == 0 ? na : nb;
+            for (int b = 0; b < m; b += 32, c++) {
+                if (lane == 0) cdesc[c] = make_int2(k, seg | (tile << 8));
+                crow[(size_t)c * 32 + lane] = (b + lane < m) ? rows[base + b + lane] : 0xffffffffu;
+            }
+            base += m;
         }
-        base += m;
     }
 }
 
