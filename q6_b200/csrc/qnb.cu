@@ -102,7 +102,8 @@ struct qnb_handle {
     cudaStream_t st = nullptr, aux[kAux] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join[kAux] = {};
     cudaGraphExec_t graph[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};   // [with copies][flags]
-    bool use_graph = true;
+    bool use_graph = true, multi_stream = true;
+    int grid_mult = 4;   // persistent force kernels: blocks per SM (measured best of 1..6 on C2 and C5)
     int graph_launches[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
     // static device tables
     DBuf<double> crg, ljd;
@@ -249,6 +250,8 @@ static int init_device(qnb_handle *h) {
     CU(cudaEventCreate(&h->ev0));
     CU(cudaEventCreate(&h->ev1));
     if (const char *e = getenv("QNB_NO_GRAPH")) h->use_graph = !(e[0] == '1');
+    if (const char *e = getenv("QNB_ONE_STREAM")) h->multi_stream = !(e[0] == '1');
+    if (const char *e = getenv("QNB_GRID_MULT")) h->grid_mult = std::max(1, atoi(e));
     return 0;
 }
 
@@ -345,35 +348,39 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
                h->item_pos.p, h->src_off.p, h->counts.p, (const int *)nullptr, (uint32_t *)nullptr);
         LAUNCH(h, k_row_totals, cdiv(nu, 256), 256, 0, nu, h->counts.p, h->row_tot.p);
         run_exclusive_scan(h, h->row_tot.p, h->row_off.p, nu);
+        // chunk tables of the streaming force kernels: counts now, contents after the rows are filled
+        const int nsol = D.ncgp_solute, nwat = D.nwat;
+        if (h->nch.ensure(nu + 2) || h->choff.ensure(nu + 4)) return 1;
+        int *nch_w = h->nch.p, *nch_s = h->nch.p + nwat + 1, *off_w = h->choff.p, *off_s = h->choff.p + nwat + 2;
+        if (nwat > 0) {
+            LAUNCH(h, k_chunk_count, cdiv(nwat, 256), 256, 0, D, nsol, nwat, 0, h->counts.p, nch_w);
+            run_exclusive_scan(h, nch_w, off_w, nwat);
+        }
+        if (nsol > 0) {
+            LAUNCH(h, k_chunk_count, cdiv(nsol, 256), 256, 0, D, 0, nsol, kITile, h->counts.p, nch_s);
+            run_exclusive_scan(h, nch_s, off_s, nsol);
+        }
         int total = 0, npk = 0;
+        h->nwchunk = h->nschunk = 0;
         CU(cudaMemcpyAsync(&total, h->row_off.p + nu, sizeof(int), cudaMemcpyDeviceToHost, h->st));
         CU(cudaMemcpyAsync(&npk, h->src_off.p + nu, sizeof(int), cudaMemcpyDeviceToHost, h->st));
-        CU(cudaStreamSynchronize(h->st));
+        if (nwat > 0) CU(cudaMemcpyAsync(&h->nwchunk, off_w + nwat, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+        if (nsol > 0) CU(cudaMemcpyAsync(&h->nschunk, off_s + nsol, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+        CU(cudaStreamSynchronize(h->st));   // the only host round trip of the build: sizes for the allocations
         h->total_rows = total;
         h->npk = npk;
-        if (h->rows.ensure((size_t)std::max(total, 1))) return 1;
+        if (h->rows.ensure((size_t)std::max(total, 1)) || h->wdesc.ensure(std::max(h->nwchunk, 1)) ||
+            h->wrow.ensure((size_t)std::max(h->nwchunk, 1) * 32) || h->sdesc.ensure(std::max(h->nschunk, 1)) ||
+            h->srow.ensure((size_t)std::max(h->nschunk, 1) * 32))
+            return 1;
         LAUNCH(h, k_build_rows<true>, cdiv(nu * 32, 256), 256, 0, D, h->cut, G, h->upos.p, h->cell_of.p, h->cell_start.p,
                h->item_pos.p, h->src_off.p, h->counts.p, h->row_off.p, h->rows.p);
-        // chunked copies of the rows for the streaming force kernels
-        h->nwchunk = h->nschunk = 0;
-        for (int pass = 0; pass < 2; pass++) {
-            const int u0 = pass == 0 ? D.ncgp_solute : 0, n = pass == 0 ? D.nwat : D.ncgp_solute;
-            const int tile_atoms = pass == 0 ? 0 : kITile;
-            if (n <= 0) continue;
-            int &nchunk = pass == 0 ? h->nwchunk : h->nschunk;
-            DBuf<int2> &desc = pass == 0 ? h->wdesc : h->sdesc;
-            DBuf<uint32_t> &crow = pass == 0 ? h->wrow : h->srow;
-            if (h->nch.ensure(n + 1) || h->choff.ensure(n + 2)) return 1;
-            LAUNCH(h, k_chunk_count, cdiv(n, 256), 256, 0, D, u0, n, tile_atoms, h->counts.p, h->nch.p);
-            run_exclusive_scan(h, h->nch.p, h->choff.p, n);
-            CU(cudaMemcpyAsync(&nchunk, h->choff.p + n, sizeof(int), cudaMemcpyDeviceToHost, h->st));
-            CU(cudaStreamSynchronize(h->st));
-            if (nchunk > 0) {
-                if (desc.ensure(nchunk) || crow.ensure((size_t)nchunk * 32)) return 1;
-                LAUNCH(h, k_chunk_fill, cdiv(n * 32, 256), 256, 0, D, u0, n, tile_atoms, h->counts.p, h->row_off.p, h->rows.p,
-                       h->choff.p, desc.p, crow.p);
-            }
-        }
+        if (h->nwchunk > 0)
+            LAUNCH(h, k_chunk_fill, cdiv(nwat * 32, 256), 256, 0, D, nsol, nwat, 0, h->counts.p, h->row_off.p, h->rows.p, off_w,
+                   h->wdesc.p, h->wrow.p);
+        if (h->nschunk > 0)
+            LAUNCH(h, k_chunk_fill, cdiv(nsol * 32, 256), 256, 0, D, 0, nsol, kITile, h->counts.p, h->row_off.p, h->rows.p, off_s,
+                   h->sdesc.p, h->srow.p);
     }
     // Q-atom partner lists: built once when the cut-off covers everything (nbqplist L3678, nbqwlist L3889,
     // nbqplist_box L3780, nbqwlist_box L3972)
@@ -448,7 +455,7 @@ static void launch_step_kernel(qnb_handle *h, int k, cudaStream_t cs) {
     switch (k) {
     case K_WATER: {
         // persistent: at most 3 blocks of 4 warps per SM, at least ~4 chunks per warp
-        const int grid = std::max(1, std::min(3 * h->nsm, cdiv(h->nwchunk, 4 * 4)));
+        const int grid = std::max(1, std::min(h->grid_mult * h->nsm, cdiv(h->nwchunk, 4 * 4)));
 #define WCASE(P, S, G) LAUNCH_ON(h, cs, (k_water_force<P, S, G>), grid, 128, 0, D, h->x.p, h->px.p, h->py.p, h->pz.p, h->pk_q.p, h->pk_ct.p, h->pk_atom.p, h->nwchunk, h->wdesc.p, h->wrow.p, grad, E, nE)
         if (pbc) { if (spc) WCASE(true, true, true); else if (geom) WCASE(true, false, true); else WCASE(true, false, false); }
         else { if (spc) WCASE(false, true, true); else if (geom) WCASE(false, false, true); else WCASE(false, false, false); }
@@ -456,7 +463,7 @@ static void launch_step_kernel(qnb_handle *h, int k, cudaStream_t cs) {
         break;
     }
     case K_SOLUTE: {
-        const int grid = std::max(1, std::min(3 * h->nsm, cdiv(h->nschunk, 4 * 4)));
+        const int grid = std::max(1, std::min(h->grid_mult * h->nsm, cdiv(h->nschunk, 4 * 4)));
         const size_t sm = (size_t)D.nct * 6 * (sizeof(double) + sizeof(float)) + (size_t)D.nct * D.nct;
 #define SCASE(P, G) LAUNCH_ON(h, cs, (k_solute_force<P, G>), grid, 128, sm, D, h->x.p, h->px.p, h->py.p, h->pz.p, h->pk_q.p, h->pk_qd.p, h->pk_ct.p, h->pk_atom.p, h->nschunk, h->sdesc.p, h->srow.p, grad, E, nE)
         if (pbc) { if (geom) SCASE(true, true); else SCASE(true, false); }
@@ -504,7 +511,7 @@ static int issue_step(qnb_handle *h, int flags) {
     bool used[kAux] = {};
     for (int k = 0; k < K_COUNT; k++) {
         if (!step_kernel_active(h, k, flags)) continue;
-        const int si = kStreamOf[k];
+        const int si = h->multi_stream ? kStreamOf[k] : -1;
         cudaStream_t cs = si < 0 ? h->st : h->aux[si];
         if (si >= 0 && !used[si]) { CU(cudaStreamWaitEvent(cs, h->ev_fork, 0)); used[si] = true; }
         launch_step_kernel(h, k, cs);

@@ -1,0 +1,12 @@
+"""Step-only timing under graph / stream variants (design experiment)."""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from q6_b200 import synth, engine
+q, cuts, lam = synth.config(sys.argv[1] if len(sys.argv) > 1 else "C2")
+g = engine.Qnb(q)
+g.make_pair_lists(q.xtop, **cuts, counts=False)
+g.pot_energy_nonbonds(q.xtop, lam)
+g.bench_nonbond(lam, 50)
+print("graph=%s one_stream=%s" % (os.environ.get("QNB_NO_GRAPH", "0") != "1", os.environ.get("QNB_ONE_STREAM", "0")),
+      "step-only us:", round(g.bench_nonbond(lam, 400) / 400 * 1e3, 2), " build ms:", round(g.bench_build_lists(5) / 5, 3))
