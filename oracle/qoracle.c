@@ -894,6 +894,130 @@ static void nbwwlist_any(qo_state *st, const double *x, double Rcut, double RLRF
     }
 }
 
+/*
+ * Any-atom charge-group cut-offs (iuse_switch_atom == 0).
+ * nbpplis2 (L950), nbpplis2_lrf (L1369), nbpplis2_box (L1091), nbpplis2_box_lrf (L1220):
+ * a group pair is inside when ANY atom pair (Q-atoms included) is within the cut-off.  Sphere+LRF: the LRF
+ * test uses r2 of the LAST atom pair examined (L1453-1468, L1499).  Box: the first pair found inside becomes
+ * the pair's shift reference (L1165-1173); LRF when any examined pair was within RcLRF2 or the squared
+ * argument equals -1 (L1283).
+ */
+static void nbpplis2_any(qo_state *st, const double *x, double Rcut, double RLRF, int lrf) {
+    int ig, jgr, ia, ja, i, j;
+    double rcut2 = Rcut, RcLRF2 = RLRF, r2;
+    st->nbpp.n = 0;
+    st->nbpp_cgp.n = 0;
+    for (ig = S.pp_start; ig <= S.pp_end; ig++) {
+        if (!S.use_PBC && EXCL(CGP_ISWITCH(ig))) continue;
+        for (jgr = 1; jgr <= S.ncgp_solute; jgr++) {
+            int inside = 0, inside_LRF = 0;
+            if (checkerboard_skip(ig, jgr)) continue;
+            if (!S.use_PBC && EXCL(CGP_ISWITCH(jgr))) continue;
+            r2 = 1.0;
+            ia = CGP_FIRST(ig);
+            while (ia <= CGP_LAST(ig) && !inside) {
+                i = CGPATOM(ia);
+                ja = CGP_FIRST(jgr);
+                while (ja <= CGP_LAST(jgr) && !inside) {
+                    j = CGPATOM(ja);
+                    if (!S.use_PBC) r2 = q_dist4(X(x, i), X(x, j));
+                    else {
+                        vec3 shift = v_sub(X(x, i), X(x, j));
+                        r2 = q_dist4(shift, box_shift(st, shift));
+                    }
+                    if (r2 <= rcut2) {
+                        inside = 1;
+                        if (S.use_PBC) {
+                            cgp_pair_t *c = cgp_push(&st->nbpp_cgp);
+                            c->i = i; c->j = j;
+                        }
+                    } else if (S.use_PBC && ((r2 <= RcLRF2) || (RLRF == -1.0))) inside_LRF = 1;
+                    ja++;
+                }
+                ia++;
+            }
+            if (inside) {
+                for (ia = CGP_FIRST(ig); ia <= CGP_LAST(ig); ia++) {
+                    i = CGPATOM(ia);
+                    if (IQATOM(i) != 0) continue;
+                    for (ja = CGP_FIRST(jgr); ja <= CGP_LAST(jgr); ja++) {
+                        precomp_t p;
+                        nb_t *e;
+                        j = CGPATOM(ja);
+                        if (IQATOM(j) != 0) continue;
+                        if (ig == jgr && i >= j) continue;
+                        if (!pp_lookup(st, i, j, &p)) continue;
+                        if (!p.set) continue;
+                        e = nb_push(&st->nbpp);
+                        e->i = i; e->j = j; e->vdWA = p.vdWA; e->vdWB = p.vdWB; e->elec = p.elec;
+                        e->cgp_pair = (int)st->nbpp_cgp.n;
+                    }
+                }
+            } else if (lrf) {
+                if (S.use_PBC ? inside_LRF : (r2 <= RcLRF2)) {
+                    lrf_update(st, x, ig, jgr);
+                    lrf_update(st, x, jgr, ig);
+                }
+            }
+        }
+    }
+}
+
+/* nbpwlis2 (L2137), nbpwlis2_lrf (L2493), nbpwlis2_box (L2247), nbpwlis2_box_lrf (L2359): any solute atom of
+ * the group against the water's first atom */
+static void nbpwlis2_any(qo_state *st, const double *x, double Rcut, double RLRF, int lrf) {
+    int ig, jgr, ia, i, j, ja, jg_cgp;
+    double rcut2 = Rcut, RcLRF2 = RLRF, r2;
+    st->nbpw.n = 0;
+    st->nbpw_cgp.n = 0;
+    for (ig = S.pw_start; ig <= S.pw_end; ig++) {
+        if (!S.use_PBC && EXCL(CGP_ISWITCH(ig))) continue;
+        for (jgr = 1; jgr <= S.nwat; jgr++) {
+            int inside = 0, inside_LRF = 0;
+            ja = S.nat_solute + S.solv_atom * jgr - (S.solv_atom - 1);
+            if (!S.use_PBC && EXCL(ja)) continue;
+            jg_cgp = st->iwhich_cgp[ja - 1];
+            r2 = 1.0;
+            ia = CGP_FIRST(ig);
+            while (ia <= CGP_LAST(ig) && !inside) {
+                i = CGPATOM(ia);
+                if (!S.use_PBC) r2 = q_dist4(X(x, i), X(x, ja));
+                else {
+                    vec3 shift = v_sub(X(x, i), X(x, ja));
+                    r2 = q_dist4(shift, box_shift(st, shift));
+                }
+                if (r2 <= rcut2) {
+                    inside = 1;
+                    if (S.use_PBC) {
+                        cgp_pair_t *c = cgp_push(&st->nbpw_cgp);
+                        c->i = i; c->j = ja;
+                    }
+                } else if (S.use_PBC && ((r2 <= RcLRF2) || (RLRF == -1.0))) inside_LRF = 1;
+                ia++;
+            }
+            if (inside) {
+                for (ia = CGP_FIRST(ig); ia <= CGP_LAST(ig); ia++) {
+                    i = CGPATOM(ia);
+                    if (IQATOM(i) != 0) continue;
+                    for (j = 1; j <= S.solv_atom; j++) {
+                        nb_t *e = nb_push(&st->nbpw);
+                        precomp_t *p = &PW_PRECOMP(i, j);
+                        e->i = i;
+                        e->j = S.nat_solute + (S.solv_atom * jgr) - S.solv_atom + j;
+                        e->vdWA = p->vdWA; e->vdWB = p->vdWB; e->elec = p->elec;
+                        e->cgp_pair = (int)st->nbpw_cgp.n;
+                    }
+                }
+            } else if (lrf) {
+                if (S.use_PBC ? inside_LRF : (r2 <= RcLRF2)) {
+                    lrf_update(st, x, ig, jg_cgp);
+                    lrf_update(st, x, jg_cgp, ig);
+                }
+            }
+        }
+    }
+}
+
 static void nbqp_append(qo_state *st, int i) {
     int iq, is;
     nbq_reserve(&st->nbqp, &st->nbqp_cap, st->nbqp_pair + S.nqat, S.nstates);
@@ -922,6 +1046,35 @@ static void nbqplist(qo_state *st, const double *x, double Rcut) {
         if (EXCL(ia)) continue;
         r2 = q_dist4(X(x, ia), xpcent);
         if (r2 > rcut2) continue;
+        for (ia = CGP_FIRST(ig); ia <= CGP_LAST(ig); ia++) {
+            i = CGPATOM(ia);
+            if (st->qbonded[i - 1]) continue;
+            nbqp_append(st, i);
+        }
+    }
+    st->qp_list_done = 1;
+}
+
+/* nbqplis2, nonbondene.f90:3408-3523: any atom of the group within Rcq of xpcent */
+static void nbqplis2(qo_state *st, const double *x, double Rcut) {
+    int ig, ia, i;
+    double rcut2, r2;
+    vec3 xpcent = {S.xpcent[0], S.xpcent[1], S.xpcent[2]};
+    if (st->qp_list_done && (Rcut > S.rexcl_o * S.rexcl_o)) return;
+    st->nbqp_pair = 0;
+    rcut2 = Rcut;
+    if (S.nqat == 0) return;
+    for (ig = S.qp_start; ig <= S.qp_end; ig++) {
+        int inside = 0;
+        if (EXCL(CGP_ISWITCH(ig))) continue;
+        ia = CGP_FIRST(ig);
+        while (ia <= CGP_LAST(ig) && !inside) {
+            i = CGPATOM(ia);
+            r2 = q_dist4(X(x, i), xpcent);
+            if (r2 <= rcut2) inside = 1;
+            ia++;
+        }
+        if (!inside) continue;
         for (ia = CGP_FIRST(ig); ia <= CGP_LAST(ig); ia++) {
             i = CGPATOM(ia);
             if (st->qbonded[i - 1]) continue;
@@ -1024,41 +1177,28 @@ static void nbqwlist_box(qo_state *st, const double *x, double Rcut, double Rq) 
     st->qw_list_done = 1;
 }
 
-/* make_pair_lists, nonbondene.f90:749-837 (iuse_switch_atom == 1 branches) */
+/* make_pair_lists, nonbondene.f90:749-837 */
 int qo_make_pair_lists(qo_state *st, const double *x, double Rq, double Rcq2, double RcLRF2, double Rcpp2,
                        double Rcpw2, double Rcww2, double RcLRF, int64_t counts_out[8]) {
-    if (S.iuse_switch_atom != 1) {
-        snprintf(qo_err, sizeof qo_err, "any-atom builders (nb??lis2*) are not restated in the oracle");
-        return 1;
-    }
+    const int sw = S.iuse_switch_atom == 1, lrf = S.use_LRF != 0;
     st->RcLRF_global = RcLRF;
+    if (lrf) cgp_centers(st, x);
+    if (sw) {
+        nbpplist_any(st, x, Rcpp2, RcLRF2, lrf);
+        nbpwlist_any(st, x, Rcpw2, RcLRF2, lrf);
+    } else {
+        nbpplis2_any(st, x, Rcpp2, RcLRF2, lrf);
+        nbpwlis2_any(st, x, Rcpw2, RcLRF2, lrf);
+    }
     if (S.use_PBC) {
-        if (!S.use_LRF) {
-            nbpplist_any(st, x, Rcpp2, 0, 0);
-            nbpwlist_any(st, x, Rcpw2, 0, 0);
-            nbqplist_box(st, x, Rcq2, Rq);
-            nbwwlist_any(st, x, Rcww2, 0, 0);
-        } else {
-            cgp_centers(st, x);
-            nbpplist_any(st, x, Rcpp2, RcLRF2, 1);
-            nbpwlist_any(st, x, Rcpw2, RcLRF2, 1);
-            nbqplist_box(st, x, Rcq2, Rq);
-            nbwwlist_any(st, x, Rcww2, RcLRF2, 1);
-        }
+        /* nbqplist_box and nbqplis2_box are the same any-atom scan; they differ only in the %cgp_pair
+           bookkeeping that the oracle defines as in nbqplis2_box (see nbqplist_box above) */
+        nbqplist_box(st, x, Rcq2, Rq);
+        nbwwlist_any(st, x, Rcww2, RcLRF2, lrf);
         nbqwlist_box(st, x, Rcq2, Rq);
     } else {
-        if (!S.use_LRF) {
-            nbpplist_any(st, x, Rcpp2, 0, 0);
-            nbpwlist_any(st, x, Rcpw2, 0, 0);
-            nbqplist(st, x, Rcq2);
-            nbwwlist_any(st, x, Rcww2, 0, 0);
-        } else {
-            cgp_centers(st, x);
-            nbpplist_any(st, x, Rcpp2, RcLRF2, 1);
-            nbpwlist_any(st, x, Rcpw2, RcLRF2, 1);
-            nbqplist(st, x, Rcq2);
-            nbwwlist_any(st, x, Rcww2, RcLRF2, 1);
-        }
+        if (sw) nbqplist(st, x, Rcq2); else nbqplis2(st, x, Rcq2);
+        nbwwlist_any(st, x, Rcww2, RcLRF2, lrf);
         nbqwlist(st, x, Rcq2);
     }
     if (counts_out) {
