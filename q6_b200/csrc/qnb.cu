@@ -176,6 +176,7 @@ static int init_device(qnb_handle *h) {
     D.use_PBC = s.use_PBC != 0; D.use_LRF = s.use_LRF != 0; D.geometric = s.ivdw_rule == QNB_VDW_GEOMETRIC;
     D.spc_water = (s.ivdw_rule == QNB_VDW_GEOMETRIC) && (s.solvent_type == QNB_SOLVENT_SPC);   // potene.f90:347
     D.qswitch0 = s.qswitch - 1;
+    D.any_atom = s.iuse_switch_atom != 1;
     D.el14 = s.el14_scale; D.el14f = (float)s.el14_scale;
     for (int d = 0; d < 3; d++) D.xpcent[d] = s.xpcent[d];
     D.pp_s = s.pp_start; D.pp_e = s.pp_end; D.pw_s = s.pw_start; D.pw_e = s.pw_end; D.qp_s = s.qp_start; D.qp_e = s.qp_end;
@@ -265,7 +266,23 @@ static void drop_graphs(qnb_handle *h) {
 static void make_grid(qnb_handle *h, const double *hx) {
     const qnb_system &s = h->T.s;
     Grid &G = h->grid;
-    double rcmax = std::sqrt(std::max({h->cut.rc2[0], h->cut.rc2[1], h->cut.rc2[2], 1.0})) * 1.0001;
+    // any-atom mode: the deciding atoms may sit up to rmax from either switch atom
+    double rmax2 = 0.0;
+    if (h->D.any_atom) {
+        double r2m = 0.0;
+        for (int g = 0; g < s.ncgp_solute; g++) {
+            const int sw = h->T.g_switch[g];
+            for (int k = 0; k < h->T.g_n[g]; k++) {
+                const int a = h->T.g_atoms[h->T.g_first[g] + k];
+                double d2 = 0;
+                for (int d = 0; d < 3; d++) d2 += (hx[3 * a + d] - hx[3 * sw + d]) * (hx[3 * a + d] - hx[3 * sw + d]);
+                r2m = std::max(r2m, d2);
+            }
+        }
+        rmax2 = 2.0 * std::sqrt(r2m) + 1e-6;
+    }
+    h->cut.rmax2 = rmax2;
+    double rcmax = (std::sqrt(std::max({h->cut.rc2[0], h->cut.rc2[1], h->cut.rc2[2], 1.0})) + rmax2) * 1.0001;
     const int nmax = 40;
     if (s.use_PBC) {
         G.periodic = 1;
@@ -299,8 +316,9 @@ static void make_grid(qnb_handle *h, const double *hx) {
     G.ncell = G.n[0] * G.n[1] * G.n[2];
     h->have_grid = true;
     // LRF reach in cells
-    const bool all = h->cut.lrf_all[0] || h->cut.lrf_all[1] || h->cut.lrf_all[2];
-    const double rl = std::sqrt(std::max(h->cut.rclrf2, 0.0));
+    const bool all = h->cut.lrf_all[0] || h->cut.lrf_all[1] || h->cut.lrf_all[2] ||
+                     (h->D.any_atom && s.use_PBC && h->cut.rclrf2 == -1.0);
+    const double rl = std::sqrt(std::max(h->cut.rclrf2, 0.0)) + rmax2;
     int r[3];
     for (int d = 0; d < 3; d++) {
         double m = std::ceil(rl * G.inv_cell[d] * 1.0001);   // |cell index difference| <= ceil(R/edge), also after clamping
@@ -344,7 +362,7 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
         LAUNCH(h, k_pack_items, cdiv(nu, 256), 256, 0, D, h->upos.p, h->cell_items.p, h->item_pos.p, h->item_posf.p, h->item_nq.p);
         run_exclusive_scan(h, h->item_nq.p, h->src_off.p, nu);
         LAUNCH(h, k_pack_atoms, cdiv(nu, 128), 128, 0, D, h->cell_items.p, h->src_off.p, h->pk_atom.p, h->pk_q.p, h->pk_qd.p, h->pk_ct.p);
-        LAUNCH(h, k_build_rows<false>, cdiv(nu * 32, 256), 256, 0, D, h->cut, G, h->upos.p, h->cell_of.p, h->cell_start.p,
+        LAUNCH(h, k_build_rows<false>, cdiv(nu * 32, 256), 256, 0, D, h->cut, G, h->x.p, h->upos.p, h->cell_of.p, h->cell_start.p,
                h->item_pos.p, h->src_off.p, h->counts.p, (const int *)nullptr, (uint32_t *)nullptr);
         LAUNCH(h, k_row_totals, cdiv(nu, 256), 256, 0, nu, h->counts.p, h->row_tot.p);
         run_exclusive_scan(h, h->row_tot.p, h->row_off.p, nu);
@@ -373,7 +391,7 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
             h->wrow.ensure((size_t)std::max(h->nwchunk, 1) * 32) || h->sdesc.ensure(std::max(h->nschunk, 1)) ||
             h->srow.ensure((size_t)std::max(h->nschunk, 1) * 32))
             return 1;
-        LAUNCH(h, k_build_rows<true>, cdiv(nu * 32, 256), 256, 0, D, h->cut, G, h->upos.p, h->cell_of.p, h->cell_start.p,
+        LAUNCH(h, k_build_rows<true>, cdiv(nu * 32, 256), 256, 0, D, h->cut, G, h->x.p, h->upos.p, h->cell_of.p, h->cell_start.p,
                h->item_pos.p, h->src_off.p, h->counts.p, h->row_off.p, h->rows.p);
         if (h->nwchunk > 0)
             LAUNCH(h, k_chunk_fill, cdiv(nwat * 32, 256), 256, 0, D, nsol, nwat, 0, h->counts.p, h->row_off.p, h->rows.p, off_w,
@@ -410,7 +428,15 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
         LAUNCH(h, k_cgp_centers, cdiv(D.ncgp, 128), 128, 0, D, h->x.p, h->lrf.p);
         if (nu > 0) {
             if (h->npk > 0) LAUNCH(h, k_pack_sources, cdiv(h->npk, 256), 256, 0, h->npk, h->pk_atom.p, h->x.p, h->crg.p, h->src.p);
-            LAUNCH(h, k_lrf_accumulate, nu, 32 * kRowWarps, 0, D, h->cut, G, h->lrf_reach, h->x.p, h->upos.p,
+            // compaction pays when the LRF shell holds a small part of the scanned cells (boxes, short RcLRF)
+            const double rl = std::sqrt(std::max(h->cut.rclrf2, 0.0));
+            const bool all = h->cut.lrf_all[0] || h->cut.lrf_all[1] || h->cut.lrf_all[2];
+            double ext = 0;
+            for (int d = 0; d < 3; d++) ext = std::max(ext, G.n[d] / G.inv_cell[d]);
+            const bool compact = !all && rl < 0.9 * ext;
+            if (compact) LAUNCH(h, k_lrf_accumulate<true>, nu, 32 * kRowWarps, 0, D, h->cut, G, h->lrf_reach,
+                   h->x.p, h->upos.p, h->cell_of.p, h->cell_start.p, h->item_pos.p, h->item_posf.p, h->src_off.p, h->src.p, h->lrf.p);
+            else LAUNCH(h, k_lrf_accumulate<false>, nu, 32 * kRowWarps, 0, D, h->cut, G, h->lrf_reach, h->x.p, h->upos.p,
                    h->cell_of.p, h->cell_start.p, h->item_pos.p, h->item_posf.p, h->src_off.p, h->src.p, h->lrf.p);
         }
         if (h->comm) {
@@ -463,7 +489,7 @@ static void launch_step_kernel(qnb_handle *h, int k, cudaStream_t cs) {
         break;
     }
     case K_SOLUTE: {
-        const int grid = std::max(1, std::min(h->grid_mult * h->nsm, cdiv(h->nschunk, 4 * 4)));
+        const int grid = std::max(1, std::min(std::min(h->grid_mult, 3) * h->nsm, cdiv(h->nschunk, 4 * 4))   /* 168 registers: 3 blocks per SM */);
         const size_t sm = (size_t)D.nct * 6 * (sizeof(double) + sizeof(float)) + (size_t)D.nct * D.nct;
 #define SCASE(P, G) LAUNCH_ON(h, cs, (k_solute_force<P, G>), grid, 128, sm, D, h->x.p, h->px.p, h->py.p, h->pz.p, h->pk_q.p, h->pk_qd.p, h->pk_ct.p, h->pk_atom.p, h->nschunk, h->sdesc.p, h->srow.p, grad, E, nE)
         if (pbc) { if (geom) SCASE(true, true); else SCASE(true, false); }

@@ -142,16 +142,22 @@ __device__ __forceinline__ void ww_chunk(const Dev &D, WaterTile &T, bool own, b
 // solute atom acting on the own water (pw, water side: gradient only)
 template <bool PBC, bool GEOM>
 __device__ __forceinline__ void wp_chunk(const Dev &D, WaterTile &T, bool valid, const double (&pj)[9], float qb, int ctb,
-                                         int pb, const double *__restrict__ x, const int *__restrict__ pk_atom) {
+                                         uint32_t entry, const double *__restrict__ x, const int *__restrict__ pk_atom) {
     if (!valid) return;
+    const int pb = (int)(entry & kIdMask);
     double ux = pj[0] - T.o[0], uy = pj[3] - T.o[1], uz = pj[6] - T.o[2];
     if (PBC) {
-        // nonbond_pw_box: shift = boxlength*nint((x(solute switch)-x(water O))*inv_boxl), vec = x(j)-x(i)+shift
-        // for i = solute atom, j = water atom; seen from the water: vec(a->b) = x(b)-x(a)-shift
-        const int sw = D.g_switch[D.grp_of_atom[pk_atom[pb]]];
-        ux -= pshift(x[3 * sw] - T.o[0], D.box[0], D.inv_box[0]);
-        uy -= pshift(x[3 * sw + 1] - T.o[1], D.box[1], D.inv_box[1]);
-        uz -= pshift(x[3 * sw + 2] - T.o[2], D.box[2], D.inv_box[2]);
+        if (D.any_atom) {
+            // any-atom lists: the image found for the pair's reference atoms at list-build time (entry bits 24-29)
+            ux += D.box[0] * img_comp(entry, 0); uy += D.box[1] * img_comp(entry, 1); uz += D.box[2] * img_comp(entry, 2);
+        } else {
+            // nonbond_pw_box: shift = boxlength*nint((x(solute switch)-x(water O))*inv_boxl), vec = x(j)-x(i)+shift
+            // for i = solute atom, j = water atom; seen from the water: vec(a->b) = x(b)-x(a)-shift
+            const int sw = D.g_switch[D.grp_of_atom[pk_atom[pb]]];
+            ux -= pshift(x[3 * sw] - T.o[0], D.box[0], D.inv_box[0]);
+            uy -= pshift(x[3 * sw + 1] - T.o[1], D.box[1], D.inv_box[1]);
+            uz -= pshift(x[3 * sw + 2] - T.o[2], D.box[2], D.inv_box[2]);
+        }
     }
     const float ufx = (float)ux, ufy = (float)uy, ufz = (float)uz;
 #pragma unroll
@@ -236,7 +242,7 @@ k_water_force(Dev D, const double *__restrict__ x, const double *__restrict__ px
             }
         }
         const bool valid = e0 != kPadEntry;
-        if (d0.y == kChunkB) wp_chunk<PBC, GEOM>(D, T, valid, p0, q0, ct0, (int)(e0 & kIdMask), x, pk_atom);
+        if (d0.y == kChunkB) wp_chunk<PBC, GEOM>(D, T, valid, p0, q0, ct0, e0, x, pk_atom);
         else {
             const bool own = valid && (e0 & kOwnerBit);
             ww_chunk<PBC, SPC>(D, T, own, __any_sync(kFull, own), valid, p0, eel, evdw);
@@ -388,11 +394,15 @@ k_solute_force(Dev D, const double *__restrict__ x, const double *__restrict__ p
                 int b = -1, gb = -1;       // atom id / group of the partner: only the special and periodic paths need them
                 if (special || PBC) { b = pk_atom[pb]; gb = D.grp_of_atom[b]; }
                 if (PBC) {
-                    // nonbond_pp_box L4791-4801: shift = boxlength*nint((x(sw_i)-x(sw_j))*inv_boxl)
-                    const int swb = D.g_switch[gb];
-                    ux += pshift(T.o[0] - x[3 * swb], D.box[0], D.inv_box[0]);
-                    uy += pshift(T.o[1] - x[3 * swb + 1], D.box[1], D.inv_box[1]);
-                    uz += pshift(T.o[2] - x[3 * swb + 2], D.box[2], D.inv_box[2]);
+                    if (D.any_atom) {
+                        ux += D.box[0] * img_comp(e0, 0); uy += D.box[1] * img_comp(e0, 1); uz += D.box[2] * img_comp(e0, 2);
+                    } else {
+                        // nonbond_pp_box L4791-4801: shift = boxlength*nint((x(sw_i)-x(sw_j))*inv_boxl)
+                        const int swb = D.g_switch[gb];
+                        ux += pshift(T.o[0] - x[3 * swb], D.box[0], D.inv_box[0]);
+                        uy += pshift(T.o[1] - x[3 * swb + 1], D.box[1], D.inv_box[1]);
+                        uz += pshift(T.o[2] - x[3 * swb + 2], D.box[2], D.inv_box[2]);
+                    }
                 }
                 const float ufx = (float)ux, ufy = (float)uy, ufz = (float)uz;
                 const bool same = special && gb == T.g;   // own-group partners are always flagged special
@@ -433,9 +443,13 @@ k_solute_force(Dev D, const double *__restrict__ x, const double *__restrict__ p
             // ---- solute-water: this side owns the pair, all three water atoms with full LJ (nbe)
             double shx = 0, shy = 0, shz = 0;
             if (PBC) {
-                shx = pshift(T.o[0] - p0[0], D.box[0], D.inv_box[0]);
-                shy = pshift(T.o[1] - p0[3], D.box[1], D.inv_box[1]);
-                shz = pshift(T.o[2] - p0[6], D.box[2], D.inv_box[2]);
+                if (D.any_atom) {
+                    shx = D.box[0] * img_comp(e0, 0); shy = D.box[1] * img_comp(e0, 1); shz = D.box[2] * img_comp(e0, 2);
+                } else {
+                    shx = pshift(T.o[0] - p0[0], D.box[0], D.inv_box[0]);
+                    shy = pshift(T.o[1] - p0[3], D.box[1], D.inv_box[1]);
+                    shz = pshift(T.o[2] - p0[6], D.box[2], D.inv_box[2]);
+                }
             }
 #pragma unroll
             for (int s = 0; s < 3; s++) {

@@ -24,9 +24,12 @@ constexpr unsigned kFull = 0xffffffffu;
 constexpr int kMaxStatesDev = 8;
 constexpr int kRowWarps = 4;    // warps (of one block) that share a unit's row in the force kernels
 constexpr int kESlots = 32;     // energy accumulators are replicated to keep same-address atomics rare
+// Row entry: bits 0-23 packed atom index, 24-29 periodic image of the pair (any-atom mode), 30 special, 31 owner
 constexpr uint32_t kOwnerBit = 0x80000000u;    // this row's unit is the reference's "i" side of the pair
 constexpr uint32_t kSpecialBit = 0x40000000u;  // solute partner atom with an excluded/1-4/self relation
-constexpr uint32_t kIdMask = 0x3fffffffu;
+constexpr uint32_t kIdMask = 0x00ffffffu;
+constexpr int kImgShift = 24;
+constexpr int kMaxPacked = 1 << 24;
 
 struct QPar4 { double A, B, el, score; };
 
@@ -43,6 +46,7 @@ struct Grid {
 struct Dev {
     int natom, nat_solute, nwat, ncgp, ncgp_solute, nunit, nqat, nstates, nct;
     int use_PBC, use_LRF, geometric, spc_water, qswitch0;
+    int any_atom;   // iuse_switch_atom == 0: any-atom charge-group cut-offs (nb??lis2*)
     double el14;
     float el14f;
     double box[3], inv_box[3];
@@ -87,6 +91,7 @@ struct Cut {
     int lrf_all[3];     // "no LRF cut-off" sentinel per class (box builders)
     double rcq2;
     double Rq;
+    double rmax2;   // any-atom mode: twice the largest switch-atom-to-atom distance of a solute group
     // kernel parameters live in constant memory: select by class without dynamic indexing (which would force a
     // local-memory copy of the struct)
     __host__ __device__ double rc2_of(int cls) const { return cls == 0 ? rc2[0] : cls == 1 ? rc2[1] : rc2[2]; }
@@ -161,6 +166,69 @@ __device__ __forceinline__ double unit_r2(const Dev &D, const double *pu, const 
         dz = __dsub_rn(pshift(sz, D.box[2], D.inv_box[2]), sz);
     }
     return sq3(dx, dy, dz);
+}
+
+// periodic image triple {-1,0,1}^3 <-> 6 bits (0 -> 0, 1 -> +1, 2 -> -1 per component)
+__device__ __forceinline__ uint32_t img_pack(int nx, int ny, int nz) {
+    auto c = [](int n) { return (uint32_t)(n == 0 ? 0 : n > 0 ? 1 : 2); };
+    return c(nx) | (c(ny) << 2) | (c(nz) << 4);
+}
+__device__ __forceinline__ uint32_t img_negate(uint32_t code) {
+    // swap 1 <-> 2 in every 2-bit field
+    const uint32_t nz = (code | (code >> 1)) & 0x15u;   // fields that are non-zero
+    return code ^ (nz * 3u);
+}
+__device__ __forceinline__ double img_comp(uint32_t entry, int d) {
+    const uint32_t c = (entry >> (kImgShift + 2 * d)) & 3u;
+    return c == 0 ? 0.0 : c == 1 ? 1.0 : -1.0;
+}
+
+// Outcome of the reference's cut-off test for the unit pair (i-unit = the reference's outer-loop group).
+struct PairTest { bool listed, lrf; uint32_t img; };
+
+// i-unit io, j-unit jo in OWNER orientation (io is what the reference loops as ig / iw).  pi, pj: switch-atom positions.
+__device__ __forceinline__ PairTest unit_pair_test(const Dev &D, const Cut &C, const double *__restrict__ x, int cls,
+                                                   int io, int jo, const double *pi, const double *pj) {
+    PairTest t;
+    t.img = 0;
+    if (!D.any_atom || cls == 2) {
+        // switching atoms (nbpplist*, nbpwlist*, nbwwlist*): one distance decides both branches
+        const double r2 = unit_r2(D, pi, pj);
+        t.listed = r2 <= C.rc2_of(cls);
+        t.lrf = !t.listed && (r2 <= C.rclrf2 || C.lrf_all_of(cls));
+        return t;
+    }
+    // any atom (nbpplis2*, nbpwlis2*): group io = solute group; jo = solute group (pp) or water (pw, first atom only)
+    const double rc2 = C.rc2_of(cls);
+    const int fi = D.g_first[io], ni = D.g_n[io];
+    int fj, nj;
+    if (cls == 0) { fj = D.g_first[jo]; nj = D.g_n[jo]; } else { fj = 0; nj = 1; }
+    const int jwat = D.nat_solute + 3 * (jo - D.ncgp_solute);
+    bool inside = false, inside_lrf = false;
+    double r2 = 1.0;
+    for (int a = 0; a < ni && !inside; a++) {
+        const int i = D.g_atoms[fi + a];
+        for (int b = 0; b < nj && !inside; b++) {
+            const int j = cls == 0 ? D.g_atoms[fj + b] : jwat;
+            if (!D.use_PBC) {
+                r2 = sq3(__dsub_rn(x[3 * j], x[3 * i]), __dsub_rn(x[3 * j + 1], x[3 * i + 1]), __dsub_rn(x[3 * j + 2], x[3 * i + 2]));
+                if (r2 <= rc2) inside = true;
+            } else {
+                const double sx = __dsub_rn(x[3 * i], x[3 * j]), sy = __dsub_rn(x[3 * i + 1], x[3 * j + 1]),
+                             sz = __dsub_rn(x[3 * i + 2], x[3 * j + 2]);
+                const double nx = round(__dmul_rn(sx, D.inv_box[0])), ny = round(__dmul_rn(sy, D.inv_box[1])),
+                             nz = round(__dmul_rn(sz, D.inv_box[2]));
+                r2 = sq3(__dsub_rn(__dmul_rn(D.box[0], nx), sx), __dsub_rn(__dmul_rn(D.box[1], ny), sy),
+                         __dsub_rn(__dmul_rn(D.box[2], nz), sz));
+                if (r2 <= rc2) { inside = true; t.img = img_pack((int)nx, (int)ny, (int)nz); }
+                else if (r2 <= C.rclrf2 || C.rclrf2 == -1.0) inside_lrf = true;   // squared argument vs -one (L1283, L2437)
+            }
+        }
+    }
+    t.listed = inside;
+    // sphere: r2 of the LAST pair examined decides the LRF branch (L1499, L2601); box: any examined pair inside RcLRF
+    t.lrf = !inside && (D.use_PBC ? inside_lrf : (r2 <= C.rclrf2));
+    return t;
 }
 
 }  // namespace qnb

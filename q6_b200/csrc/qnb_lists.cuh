@@ -175,7 +175,7 @@ __device__ __forceinline__ XSeg x_segments(int c, int m, int n, int periodic) {
 // counts[3*u + {0,1,2}] = |A_own|, |A_mir|, |B|.
 template <bool FILL>
 __global__ void __launch_bounds__(256)
-k_build_rows(Dev D, Cut C, Grid G, const double *__restrict__ upos, const int *__restrict__ cell_of,
+k_build_rows(Dev D, Cut C, Grid G, const double *__restrict__ x, const double *__restrict__ upos, const int *__restrict__ cell_of,
              const int *__restrict__ cell_start, const double4 *__restrict__ item_pos,
              const int *__restrict__ src_off, int *__restrict__ counts, const int *__restrict__ row_off,
              uint32_t *__restrict__ rows) {
@@ -212,13 +212,16 @@ k_build_rows(Dev D, Cut C, Grid G, const double *__restrict__ upos, const int *_
                         if (idx < hi) { ip = item_pos[idx]; v = (int)__double_as_longlong(ip.w); }
                         bool pass = false, owner_is_u = false;
                         int cls = 0;
+                        uint32_t img = 0;   // periodic image of the pair as seen from u (any-atom mode)
                         if (v >= 0 && !D.u_excl[v]) {
                             cls = pair_class(u, v, ns, owner_is_u);
                             if (!(cls == 2 && u == v) && in_shard(D, cls, owner_is_u ? u : v)) {
                                 const double pv[3] = {ip.x, ip.y, ip.z};
-                                // owner orientation (is = owner's switch atom); the value is the same either way
-                                double r2 = owner_is_u ? unit_r2(D, pu, pv) : unit_r2(D, pv, pu);
-                                pass = r2 <= C.rc2_of(cls);
+                                // owner orientation: the reference's outer-loop unit first
+                                const PairTest pt = owner_is_u ? unit_pair_test(D, C, x, cls, u, v, pu, pv)
+                                                               : unit_pair_test(D, C, x, cls, v, u, pv, pu);
+                                pass = pt.listed;
+                                img = (owner_is_u ? pt.img : img_negate(pt.img)) << kImgShift;
                             }
                         }
                         // entries emitted by this lane, by segment
@@ -243,7 +246,7 @@ k_build_rows(Dev D, Cut C, Grid G, const double *__restrict__ upos, const int *_
                             if (v_sol) {
                                 // flatten the group's non-Q atoms (entries = packed atom indices)
                                 const int gf = D.g_first[v], gn = D.g_n[v];
-                                uint32_t flag = (u_sol && owner_is_u) ? kOwnerBit : 0u;
+                                uint32_t flag = ((u_sol && owner_is_u) ? kOwnerBit : 0u) | img;
                                 int p = u_sol ? (owner_is_u ? p_own : p_mir) : p_b;
                                 uint32_t pk = pk0;
                                 for (int k = 0; k < gn; k++) {
@@ -260,7 +263,7 @@ k_build_rows(Dev D, Cut C, Grid G, const double *__restrict__ upos, const int *_
                                 }
                             } else {
                                 // a water partner is named by the packed index of its first atom (O)
-                                if (u_sol) rows[p_b] = pk0 | kOwnerBit;
+                                if (u_sol) rows[p_b] = pk0 | kOwnerBit | img;
                                 else if (owner_is_u) rows[p_own] = pk0 | kOwnerBit;
                                 else rows[p_mir] = pk0;
                             }
@@ -333,10 +336,20 @@ __global__ void k_qp_flags(Dev D, Cut C, const double *__restrict__ x, int *__re
         if (!D.use_PBC) {
             int ia = D.g_switch[g];
             if (!D.excl[ia]) {
-                // r2 = q_dist4(x(ia),xpcent); skip if r2 > rcut2 (L3707-3710)
-                double r2 = sq3(__dsub_rn(D.xpcent[0], x[3 * ia]), __dsub_rn(D.xpcent[1], x[3 * ia + 1]),
-                                __dsub_rn(D.xpcent[2], x[3 * ia + 2]));
-                inside = !(r2 > C.rcq2);
+                if (!D.any_atom) {
+                    // nbqplist: r2 = q_dist4(x(ia),xpcent); skip if r2 > rcut2 (L3707-3710)
+                    double r2 = sq3(__dsub_rn(D.xpcent[0], x[3 * ia]), __dsub_rn(D.xpcent[1], x[3 * ia + 1]),
+                                    __dsub_rn(D.xpcent[2], x[3 * ia + 2]));
+                    inside = !(r2 > C.rcq2);
+                } else {
+                    // nbqplis2: any atom of the group within Rcq of xpcent (L3466-3476)
+                    for (int k = 0; k < gn && !inside; k++) {
+                        const int i = D.g_atoms[gf + k];
+                        double r2 = sq3(__dsub_rn(D.xpcent[0], x[3 * i]), __dsub_rn(D.xpcent[1], x[3 * i + 1]),
+                                        __dsub_rn(D.xpcent[2], x[3 * i + 2]));
+                        inside = r2 <= C.rcq2;
+                    }
+                }
             }
         } else if (C.Rq < 0.0) {
             inside = true;   // no cut-off: every group, no registered reference atom (zero shift)
@@ -438,6 +451,7 @@ __constant__ int kLrfExpand[40] = {0, 1, 2, 3,
 // (outside the class cut-off, inside RcLRF, pair owned by this shard).  20 unique moments are
 // accumulated (phi2 and phi3 are symmetric) and expanded on write.  FP64, no divisions:
 // field0 = q/r^3, field1 = 3 field0/r^2, field2 = -field1/r^2 from 1/r (rsqrt seed + Halley step).
+template <bool COMPACT>
 __global__ void __launch_bounds__(32 * kRowWarps)
 k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x, const double *__restrict__ upos,
                  const int *__restrict__ cell_of, const int *__restrict__ cell_start,
@@ -461,9 +475,11 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
     const float boxf[3] = {(float)D.box[0], (float)D.box[1], (float)D.box[2]};
     const float iboxf[3] = {(float)D.inv_box[0], (float)D.inv_box[1], (float)D.inv_box[2]};
     const float rcmin = (float)fmin(C.rc2[0], fmin(C.rc2[1], C.rc2[2]));
-    const float lo_band = rcmin * (1.0f - 1e-3f) - 0.05f;          // surely listed below this
-    const float hi_band = (float)C.rclrf2 * (1.0f + 1e-3f) + 0.05f;   // surely outside the LRF shell above this
-    const bool any_all = C.lrf_all[0] || C.lrf_all[1] || C.lrf_all[2];
+    // any-atom mode: the deciding atoms sit up to rmax2/2 from either switch atom
+    const float rl = sqrtf(fmaxf((float)C.rclrf2, 0.f)) + (D.any_atom ? (float)C.rmax2 : 0.f);
+    const float lo_band = D.any_atom ? -1.0f : rcmin * (1.0f - 1e-3f) - 0.05f;   // surely listed below this
+    const float hi_band = rl * rl * (1.0f + 1e-3f) + 0.05f;                        // surely outside the LRF shell above this
+    const bool any_all = C.lrf_all[0] || C.lrf_all[1] || C.lrf_all[2] || (D.any_atom && D.use_PBC && C.rclrf2 == -1.0);
     // phi0, phi1, phi2 in FP64 (FP32 phi2 was measured to move E%LRF by 1.1e-6 relative).  phi3 enters only the field,
     // as 1/2 dr.phi3.dr with |dr| ~ 1 A (atom to group centre) against r >= Rc: a (dr/r)^2 ~ 1e-2 correction to
     // phi1, so it is formed and summed in FP32 (relative error ~1e-6 of itself).
@@ -550,11 +566,15 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
                     if (in_shard(D, cls, owner_is_t ? t : s)) {
                         const double4 ip = item_pos[idx];
                         const double ps[3] = {ip.x, ip.y, ip.z};
-                        const double r2u = owner_is_t ? unit_r2(D, pt, ps) : unit_r2(D, ps, pt);
                         // outside the class cut-off (else: a listed pair) and inside the LRF cut-off
-                        accept = !(r2u <= C.rc2_of(cls)) && (r2u <= C.rclrf2 || C.lrf_all_of(cls));
+                        accept = (owner_is_t ? unit_pair_test(D, C, x, cls, t, s, pt, ps) : unit_pair_test(D, C, x, cls, s, t, ps, pt)).lrf;
                     }
                 }
+            }
+            if (!COMPACT) {
+                // nearly every scanned unit is a source (sphere with RcLRF covering it): no queueing needed
+                if (accept) accumulate(idx);
+                continue;
             }
             const unsigned mask = __ballot_sync(kFull, accept);
             if (accept) queue[wid][qn + __popc(mask & ((1u << lane) - 1u))] = idx;

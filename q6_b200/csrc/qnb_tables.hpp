@@ -378,7 +378,7 @@ inline bool HostTables::build(const qnb_system *sys) {
     }
     if (s.nwat > 0 && s.solv_atom != 3) { error = "only 3-site solvent is supported by the CUDA water kernels"; return false; }
     if (s.ntors_gt_solute) { error = "solvents with internal torsions (nonbond_solvent_internal) are not supported"; return false; }
-    if (s.iuse_switch_atom != 1) { error = "any-atom charge-group cut-offs (nb??lis2*) are not supported yet"; return false; }
+    if (n >= (1 << 24)) { error = "more than 2^24 atoms: row entries hold 24-bit packed atom indices"; return false; }
     if (s.use_PBC && s.nqat > 0 && (s.qswitch < 1 || s.qswitch > n)) { error = "PBC with Q-atoms needs a valid qswitch"; return false; }
 
     iac0.resize(n);

@@ -69,7 +69,20 @@ def small_systems():
                 dict(Rq=-1.0, Rcq2=1.0, RcLRF2=1.0, Rcpp2=64.0, Rcpw2=64.0, Rcww2=64.0, RcLRF=-1.0), [1.0]))
     out.append(("box_water", synth.water_box(9, 19), dict(Rq=-1.0, Rcq2=1.0, RcLRF2=12.0 ** 2, Rcpp2=81.0, Rcpw2=81.0, Rcww2=81.0, RcLRF=12.0), [1.0]))
     out.append(("box_water_nolrf", _nolrf(synth.water_box(7, 20)), dict(Rq=-1.0, Rcq2=1.0, RcLRF2=1.0, Rcpp2=49.0, Rcpw2=49.0, Rcww2=49.0, RcLRF=-1.0), [1.0]))
+    # any-atom charge-group cut-offs (iuse_switch_atom = 0: nb??lis2*)
+    out.append(("sph_anyatom", _anyatom(synth.solvated_sphere(16.0, 9.0, 12, 2, 22, fep="evb")), sph_cuts(8.0, rq=10.0, rlrf=14.0), [0.5, 0.5]))
+    out.append(("sph_anyatom_lrf99", _anyatom(synth.solvated_sphere(15.0, 9.0, 8, 1, 23)), sph_cuts(7.5), [1.0]))
+    out.append(("sph_anyatom_nolrf", _nolrf(_anyatom(synth.solvated_sphere(15.0, 9.0, 8, 1, 24))), sph_cuts(8.0), [1.0]))
+    out.append(("box_anyatom", _anyatom(synth.solvated_sphere(0.0, 7.0, 16, 2, 25, fep="evb", pbc_box=box)),
+                dict(Rq=9.0, Rcq2=81.0, RcLRF2=11.0 ** 2, Rcpp2=49.0, Rcpw2=49.0, Rcww2=49.0, RcLRF=11.0), [0.5, 0.5]))
+    out.append(("box_anyatom_nolrfcut", _anyatom(synth.solvated_sphere(0.0, 7.0, 16, 1, 26, pbc_box=box)),
+                dict(Rq=-1.0, Rcq2=1.0, RcLRF2=-1.0, Rcpp2=49.0, Rcpw2=49.0, Rcww2=49.0, RcLRF=-1.0), [1.0]))
     return out
+
+
+def _anyatom(q):
+    q.iuse_switch_atom = 0
+    return q
 
 
 def _nolrf(q):
