@@ -177,6 +177,8 @@ static int init_device(qnb_handle *h) {
     D.spc_water = (s.ivdw_rule == QNB_VDW_GEOMETRIC) && (s.solvent_type == QNB_SOLVENT_SPC);   // potene.f90:347
     D.qswitch0 = s.qswitch - 1;
     D.any_atom = s.iuse_switch_atom != 1;
+    D.sharded = !(s.pp_start <= 1 && s.pp_end >= s.ncgp_solute && s.pw_start <= 1 && s.pw_end >= s.ncgp_solute &&
+                  s.ww_start <= 1 && s.ww_end >= s.nwat);
     D.el14 = s.el14_scale; D.el14f = (float)s.el14_scale;
     for (int d = 0; d < 3; d++) D.xpcent[d] = s.xpcent[d];
     D.pp_s = s.pp_start; D.pp_e = s.pp_end; D.pw_s = s.pw_start; D.pw_e = s.pw_end; D.qp_s = s.qp_start; D.qp_e = s.qp_end;

@@ -47,6 +47,7 @@ struct Dev {
     int natom, nat_solute, nwat, ncgp, ncgp_solute, nunit, nqat, nstates, nct;
     int use_PBC, use_LRF, geometric, spc_water, qswitch0;
     int any_atom;   // iuse_switch_atom == 0: any-atom charge-group cut-offs (nb??lis2*)
+    int sharded;    // the i-ranges do not cover everything: ownership of a pair must be checked
     double el14;
     float el14f;
     double box[3], inv_box[3];
@@ -181,6 +182,22 @@ __device__ __forceinline__ uint32_t img_negate(uint32_t code) {
 __device__ __forceinline__ double img_comp(uint32_t entry, int d) {
     const uint32_t c = (entry >> (kImgShift + 2 * d)) & 3u;
     return c == 0 ? 0.0 : c == 1 ? 1.0 : -1.0;
+}
+
+// FP32 screening of a switch-atom distance against a squared cut-off: -1 surely inside, +1 surely outside, 0 too
+// close to call (the FP64 test decides).  Positions are |x| < ~200 A in FP32: |error(r2)| < 1e-3*r2 + 0.05.
+__device__ __forceinline__ int screen_r2(float r2f, float cut2) {
+    if (r2f < cut2 * (1.0f - 1e-3f) - 0.05f) return -1;
+    if (r2f > cut2 * (1.0f + 1e-3f) + 0.05f) return 1;
+    return 0;
+}
+__device__ __forceinline__ float screen_dist2(const Dev &D, float dx, float dy, float dz) {
+    if (D.use_PBC) {
+        dx -= (float)D.box[0] * rintf(dx * (float)D.inv_box[0]);
+        dy -= (float)D.box[1] * rintf(dy * (float)D.inv_box[1]);
+        dz -= (float)D.box[2] * rintf(dz * (float)D.inv_box[2]);
+    }
+    return dx * dx + dy * dy + dz * dz;
 }
 
 // Outcome of the reference's cut-off test for the unit pair (i-unit = the reference's outer-loop group).

@@ -97,8 +97,10 @@ __global__ void k_pack_items(Dev D, const double *__restrict__ upos, const int *
     if (idx >= D.nunit) return;
     const int u = cell_items[idx];
     item_pos[idx] = make_double4(upos[3 * u], upos[3 * u + 1], upos[3 * u + 2], __longlong_as_double((long long)u));
-    item_posf[idx] = make_float4((float)upos[3 * u], (float)upos[3 * u + 1], (float)upos[3 * u + 2], __int_as_float(u));
-    item_nq[idx] = D.u_excl[u] ? 0 : D.g_nq[D.u_grp[u]];
+    const int nq = D.u_excl[u] ? 0 : D.g_nq[D.u_grp[u]];
+    // screening copy: FP32 position, unit id (-1 - u when the unit has no source atoms: excluded or all Q-atoms)
+    item_posf[idx] = make_float4((float)upos[3 * u], (float)upos[3 * u + 1], (float)upos[3 * u + 2], __int_as_float(nq > 0 ? u : -1 - u));
+    item_nq[idx] = nq;
 }
 // Packed atoms: the non-Q atoms of every non-excluded unit, in cell order of the units.  Row entries are indices
 // into this order, so the lanes of a warp (consecutive row entries = neighbouring units of one cell) read
@@ -193,6 +195,7 @@ k_build_rows(Dev D, Cut C, Grid G, const double *__restrict__ x, const double *_
     }
     if (!D.u_excl[u]) {
         const double pu[3] = {upos[3 * u], upos[3 * u + 1], upos[3 * u + 2]};
+        const float puf[3] = {(float)pu[0], (float)pu[1], (float)pu[2]};
         const int cu = cell_of[u];
         const int cx = cu % G.n[0], cy = (cu / G.n[0]) % G.n[1], cz = cu / (G.n[0] * G.n[1]);
         const DimRange rz = dim_range(cz, 1, G.n[2], G.periodic), ry = dim_range(cy, 1, G.n[1], G.periodic);
@@ -215,13 +218,19 @@ k_build_rows(Dev D, Cut C, Grid G, const double *__restrict__ x, const double *_
                         uint32_t img = 0;   // periodic image of the pair as seen from u (any-atom mode)
                         if (v >= 0 && !D.u_excl[v]) {
                             cls = pair_class(u, v, ns, owner_is_u);
-                            if (!(cls == 2 && u == v) && in_shard(D, cls, owner_is_u ? u : v)) {
-                                const double pv[3] = {ip.x, ip.y, ip.z};
-                                // owner orientation: the reference's outer-loop unit first
-                                const PairTest pt = owner_is_u ? unit_pair_test(D, C, x, cls, u, v, pu, pv)
-                                                               : unit_pair_test(D, C, x, cls, v, u, pv, pu);
-                                pass = pt.listed;
-                                img = (owner_is_u ? pt.img : img_negate(pt.img)) << kImgShift;
+                            if (!(cls == 2 && u == v) && (!D.sharded || in_shard(D, cls, owner_is_u ? u : v))) {
+                                // FP32 screening first; the FP64 test only decides pairs within ~1e-3 of the cut-off
+                                const float r2f = screen_dist2(D, (float)ip.x - puf[0], (float)ip.y - puf[1], (float)ip.z - puf[2]);
+                                const int in = (D.any_atom && cls != 2) ? 0 : screen_r2(r2f, (float)C.rc2_of(cls));
+                                if (in < 0) pass = true;
+                                else if (in == 0) {
+                                    const double pv[3] = {ip.x, ip.y, ip.z};
+                                    // owner orientation: the reference's outer-loop unit first
+                                    const PairTest pt = owner_is_u ? unit_pair_test(D, C, x, cls, u, v, pu, pv)
+                                                                   : unit_pair_test(D, C, x, cls, v, u, pv, pu);
+                                    pass = pt.listed;
+                                    img = (owner_is_u ? pt.img : img_negate(pt.img)) << kImgShift;
+                                }
                             }
                         }
                         // entries emitted by this lane, by segment
@@ -440,6 +449,7 @@ __global__ void k_cgp_centers_only(Dev D, const double *__restrict__ x, double *
     l[0] = cx / n; l[1] = cy / n; l[2] = cz / n;
 }
 
+constexpr int kLrfSegBatch = 256;
 __constant__ int kLrfExpand[40] = {0, 1, 2, 3,
                                    4, 5, 6, 5, 7, 8, 6, 8, 9,
                                    10, 11, 12, 11, 13, 14, 12, 14, 15,    // n = x: (xx*, xy*, xz*)
@@ -472,13 +482,9 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
     const double cx_ = lt[0], cy_ = lt[1], cz_ = lt[2];
     const double pt[3] = {upos[3 * t], upos[3 * t + 1], upos[3 * t + 2]};
     const float ptf[3] = {(float)pt[0], (float)pt[1], (float)pt[2]};
-    const float boxf[3] = {(float)D.box[0], (float)D.box[1], (float)D.box[2]};
-    const float iboxf[3] = {(float)D.inv_box[0], (float)D.inv_box[1], (float)D.inv_box[2]};
-    const float rcmin = (float)fmin(C.rc2[0], fmin(C.rc2[1], C.rc2[2]));
     // any-atom mode: the deciding atoms sit up to rmax2/2 from either switch atom
     const float rl = sqrtf(fmaxf((float)C.rclrf2, 0.f)) + (D.any_atom ? (float)C.rmax2 : 0.f);
-    const float lo_band = D.any_atom ? -1.0f : rcmin * (1.0f - 1e-3f) - 0.05f;   // surely listed below this
-    const float hi_band = rl * rl * (1.0f + 1e-3f) + 0.05f;                        // surely outside the LRF shell above this
+    const float hi_band = rl * rl * (1.0f + 1e-3f) + 0.05f;   // surely outside the LRF shell above this
     const bool any_all = C.lrf_all[0] || C.lrf_all[1] || C.lrf_all[2] || (D.any_atom && D.use_PBC && C.rclrf2 == -1.0);
     // phi0, phi1, phi2 in FP64 (FP32 phi2 was measured to move E%LRF by 1.1e-6 relative).  phi3 enters only the field,
     // as 1/2 dr.phi3.dr with |dr| ~ 1 A (atom to group centre) against r >= Rc: a (dr/r)^2 ~ 1e-2 correction to
@@ -492,14 +498,15 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
         // lrf_update(group1 = source unit of item idx, group2 = target): dr = x(i) - cgp_cent(target) - shift
         double ox = cx_, oy = cy_, oz = cz_;
         if (D.use_PBC) {
-            // shift = boxlength*nint((x(cgp(group1)%iswitch) - lrf(group2)%cgp_cent)*inv_boxl)
-            const int s = __float_as_int(item_posf[idx].w);
-            const int isw = D.g_switch[D.u_grp[s]];
-            ox += pshift(x[3 * isw] - cx_, D.box[0], D.inv_box[0]);
-            oy += pshift(x[3 * isw + 1] - cy_, D.box[1], D.inv_box[1]);
-            oz += pshift(x[3 * isw + 2] - cz_, D.box[2], D.inv_box[2]);
+            // shift = boxlength*nint((x(cgp(group1)%iswitch) - lrf(group2)%cgp_cent)*inv_boxl); the group's switch
+            // atom is the unit's binned position (checked at init: g_switch[u_grp[u]] == u_sw[u])
+            const double4 ip = item_pos[idx];
+            ox += pshift(ip.x - cx_, D.box[0], D.inv_box[0]);
+            oy += pshift(ip.y - cy_, D.box[1], D.inv_box[1]);
+            oz += pshift(ip.z - cz_, D.box[2], D.inv_box[2]);
         }
         const int a0 = src_off[idx], a1 = src_off[idx + 1];
+#pragma unroll 3
         for (int k = a0; k < a1; k++) {
             const double4 sa = src[k];
             const double dx = sa.x - ox, dy = sa.y - oy, dz = sa.z - oz;
@@ -540,58 +547,89 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
     const DimRange rz = dim_range(cz, reach.z, G.n[2], G.periodic), ry = dim_range(cy, reach.y, G.n[1], G.periodic);
     const XSeg xs = x_segments(cx, reach.x, G.n[0], G.periodic);
     const int nrow = rz.count * ry.count * xs.n;
+    // screening thresholds of this target against solute / water sources (FP32, see screen_r2)
+    const bool t_sol = t < ns;
+    const int cls_s = t_sol ? 0 : 1, cls_w = t_sol ? 1 : 2;     // class with a solute / a water source
+    auto lo_of = [](double c2) { return (float)c2 * (1.0f - 1e-3f) - 0.05f; };
+    auto hi_of = [](double c2) { return (float)c2 * (1.0f + 1e-3f) + 0.05f; };
+    const float in_lo_s = lo_of(C.rc2_of(cls_s)), in_hi_s = hi_of(C.rc2_of(cls_s));
+    const float in_lo_w = lo_of(C.rc2_of(cls_w)), in_hi_w = hi_of(C.rc2_of(cls_w));
+    const float out_lo = lo_of(C.rclrf2), out_hi = hi_of(C.rclrf2);
+    const bool all_s = C.lrf_all_of(cls_s), all_w = C.lrf_all_of(cls_w);
+    const float bx = (float)D.box[0], by = (float)D.box[1], bz = (float)D.box[2];
+    const float ibx = (float)D.inv_box[0], iby = (float)D.inv_box[1], ibz = (float)D.inv_box[2];
+    __shared__ int2 seg[kLrfSegBatch];   // item ranges [lo,hi) of the cell rows, computed once per block
     int qn = 0;   // entries waiting in this warp's queue (warp-uniform)
-    for (int r = wid; r < nrow; r += kRowWarps) {
-        const int sgi = r % xs.n, iy = (r / xs.n) % ry.count, iz = r / (xs.n * ry.count);
-        int z = rz.start + iz; z = (z % G.n[2] + G.n[2]) % G.n[2];
-        int y = ry.start + iy; y = (y % G.n[1] + G.n[1]) % G.n[1];
-        const int rowbase = (z * G.n[1] + y) * G.n[0];
-        const int lo = cell_start[rowbase + (sgi == 0 ? xs.lo[0] : xs.lo[1])];
-        const int hi = cell_start[rowbase + (sgi == 0 ? xs.hi[0] : xs.hi[1])];
-        for (int base = lo; base < hi; base += 32) {
-            const int idx = base + lane;
-            bool accept = false;
-            if (idx < hi) {
-                const float4 pf = item_posf[idx];
-                const int s = __float_as_int(pf.w);
-                float dxf = pf.x - ptf[0], dyf = pf.y - ptf[1], dzf = pf.z - ptf[2];
-                if (D.use_PBC) {
-                    dxf -= boxf[0] * rintf(dxf * iboxf[0]); dyf -= boxf[1] * rintf(dyf * iboxf[1]); dzf -= boxf[2] * rintf(dzf * iboxf[2]);
-                }
-                const float r2f = dxf * dxf + dyf * dyf + dzf * dzf;
-                const bool maybe = s != t && r2f >= lo_band && (any_all || r2f <= hi_band) && src_off[idx + 1] > src_off[idx];
-                if (maybe) {
-                    bool owner_is_t;
-                    const int cls = pair_class(t, s, ns, owner_is_t);
-                    if (in_shard(D, cls, owner_is_t ? t : s)) {
-                        const double4 ip = item_pos[idx];
-                        const double ps[3] = {ip.x, ip.y, ip.z};
-                        // outside the class cut-off (else: a listed pair) and inside the LRF cut-off
-                        accept = (owner_is_t ? unit_pair_test(D, C, x, cls, t, s, pt, ps) : unit_pair_test(D, C, x, cls, s, t, ps, pt)).lrf;
+    for (int r0 = 0; r0 < nrow; r0 += kLrfSegBatch) {
+        __syncthreads();
+        for (int r = r0 + threadIdx.x; r < min(nrow, r0 + kLrfSegBatch); r += blockDim.x) {
+            const int sgi = r % xs.n, iy = (r / xs.n) % ry.count, iz = r / (xs.n * ry.count);
+            int z = rz.start + iz; z = (z % G.n[2] + G.n[2]) % G.n[2];
+            int y = ry.start + iy; y = (y % G.n[1] + G.n[1]) % G.n[1];
+            const int rowbase = (z * G.n[1] + y) * G.n[0];
+            seg[r - r0] = make_int2(cell_start[rowbase + (sgi == 0 ? xs.lo[0] : xs.lo[1])],
+                                    cell_start[rowbase + (sgi == 0 ? xs.hi[0] : xs.hi[1])]);
+        }
+        __syncthreads();
+        const int nseg = min(nrow - r0, kLrfSegBatch);
+        for (int r = wid; r < nseg; r += kRowWarps) {
+            const int lo = seg[r].x, hi = seg[r].y;
+            for (int base = lo; base < hi; base += 32) {
+                const int idx = base + lane;
+                bool accept = false;
+                if (idx < hi) {
+                    const float4 pf = item_posf[idx];
+                    const int s = __float_as_int(pf.w);
+                    float dx = pf.x - ptf[0], dy = pf.y - ptf[1], dz = pf.z - ptf[2];
+                    if (D.use_PBC) { dx -= bx * rintf(dx * ibx); dy -= by * rintf(dy * iby); dz -= bz * rintf(dz * ibz); }
+                    const float r2f = dx * dx + dy * dy + dz * dz;
+                    const bool s_sol = s < ns;
+                    // zones: 0 listed or outside the shell, 1 surely inside it, 2 the FP64 test decides
+                    int zone;
+                    if (D.any_atom && (t_sol || s_sol)) zone = (!any_all && r2f > hi_band) ? 0 : 2;
+                    else {
+                        const float il = s_sol ? in_lo_s : in_lo_w, ih = s_sol ? in_hi_s : in_hi_w;
+                        const bool all = s_sol ? all_s : all_w;
+                        zone = (r2f < il || (!all && r2f > out_hi)) ? 0 : (r2f > ih && (all || r2f < out_lo)) ? 1 : 2;
                     }
+                    if (s < 0 || s == t) zone = 0;
+                    if (zone != 0 && (D.sharded || zone == 2)) {
+                        bool owner_is_t;
+                        const int cls = pair_class(t, s, ns, owner_is_t);
+                        if (D.sharded && !in_shard(D, cls, owner_is_t ? t : s)) zone = 0;
+                        else if (zone == 2) {
+                            const double4 ip = item_pos[idx];
+                            const double ps[3] = {ip.x, ip.y, ip.z};
+                            // outside the class cut-off (else: a listed pair) and inside the LRF cut-off
+                            const bool lrf = (owner_is_t ? unit_pair_test(D, C, x, cls, t, s, pt, ps)
+                                                         : unit_pair_test(D, C, x, cls, s, t, ps, pt)).lrf;
+                            zone = lrf ? 1 : 0;
+                        }
+                    }
+                    accept = zone == 1;
                 }
-            }
-            if (!COMPACT) {
-                // nearly every scanned unit is a source (sphere with RcLRF covering it): no queueing needed
-                if (accept) accumulate(idx);
-                continue;
-            }
-            const unsigned mask = __ballot_sync(kFull, accept);
-            if (accept) queue[wid][qn + __popc(mask & ((1u << lane) - 1u))] = idx;
-            qn += __popc(mask);
-            __syncwarp();
-            if (qn >= 32) {
-                accumulate(queue[wid][lane]);
-                const int rest = qn - 32;
-                int moved = 0;
-                if (lane < rest) moved = queue[wid][32 + lane];
-                __syncwarp();
-                if (lane < rest) queue[wid][lane] = moved;
-                qn = rest;
-                __syncwarp();
+                if (!COMPACT) {
+                    // nearly every scanned unit is a source (sphere with RcLRF covering it): no queueing needed
+                    if (accept) accumulate(idx);
+                    continue;
+                }
+                const unsigned mask = __ballot_sync(kFull, accept);
+                if (accept) queue[wid][qn + __popc(mask & ((1u << lane) - 1u))] = idx;
+                qn += __popc(mask);
+                if (qn >= 32) {
+                    __syncwarp();
+                    accumulate(queue[wid][lane]);
+                    const int rest = qn - 32;
+                    int moved = 0;
+                    if (lane < rest) moved = queue[wid][32 + lane];
+                    __syncwarp();
+                    if (lane < rest) queue[wid][lane] = moved;
+                    qn = rest;
+                }
             }
         }
     }
+    __syncwarp();
     if (lane < qn) accumulate(queue[wid][lane]);
     __syncwarp();
 #pragma unroll

@@ -435,6 +435,7 @@ inline bool HostTables::build(const qnb_system *sys) {
             if (u_grp[u] < 0) { error = "water molecule without charge group"; return false; }
         }
         if (seen[u_grp[u]]++) { error = "two units share one charge group"; return false; }
+        if (g_switch[u_grp[u]] != u_sw[u]) { error = "a solvent charge group whose switching atom is not the molecule's first atom is not supported"; return false; }
         u_excl[u] = excl[u_sw[u]];
     }
     // water sites (simprep.f90:3610-3621)
