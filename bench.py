@@ -235,11 +235,15 @@ def main():
             "k_qq_static": nqq * flop_q_pair(1),
             "k_lrf_taylor": q.natom * FLOP_LRF_TAYLOR,
         }
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["bytes_per_launch"]
+        except Exception:
+            traffic = {}
         dom = max(kt, key=kt.get)
         peak_tf = fp32_meas
         ach = alg[dom] / (kt[dom] * 1e-3) / 1e12
         roof = {"bound": "fp32", "kernel": dom, "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                "traffic": None,
+                "traffic": traffic.get(dom),   # dram bytes per launch from the committed ncu --set full capture
                 "peak_source": "FP32 FMA micro-benchmark run in this process (MEASURED_PEAKS.json has no FP32 figure); "
                                f"nominal 148 SM x 128 x 2 x {peaks.get('sm_max_mhz', 1965.0)} MHz = "
                                f"{148 * 128 * 2 * peaks.get('sm_max_mhz', 1965.0) * 1e-6:.1f} TFLOP/s; FP64 pipe measured {fp64_meas:.1f}",

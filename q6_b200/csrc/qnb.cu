@@ -105,6 +105,7 @@ struct qnb_handle {
     bool use_graph = true, multi_stream = true;
     int grid_mult = 4;   // persistent force kernels: blocks per SM (measured best of 1..6 on C2 and C5)
     int graph_launches[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+    bool graph_dirty[2][4] = {{true, true, true, true}, {true, true, true, true}};
     // static device tables
     DBuf<double> crg, ljd;
     DBuf<float> crgf, ljf;
@@ -140,7 +141,7 @@ struct qnb_handle {
     int nqp = 0, nqw = 0;
     bool qp_done = false, qw_done = false, lists_built = false;
     int64_t total_rows = 0;
-    int3 lrf_reach{1, 1, 1};
+    int3 lrf_reach{1, 1, 1}, list_reach{1, 1, 1};
     double box[3] = {0, 0, 0}, inv_box[3] = {0, 0, 0};
     // comm
     ncclCommT comm = nullptr;
@@ -259,10 +260,15 @@ static int init_device(qnb_handle *h) {
 }
 
 // ------------------------------------------------------------------ list build
-static void drop_graphs(qnb_handle *h) {
+// A list build (or a box change) alters launch arguments baked into the captured step.  The executable graphs are
+// kept and refreshed with cudaGraphExecUpdate from a new capture (tens of microseconds) instead of being
+// re-instantiated (hundreds).
+static void drop_graphs(qnb_handle *h, bool destroy = false) {
     for (int c = 0; c < 2; c++)
-        for (int f = 0; f < 4; f++)
-            if (h->graph[c][f]) { cudaGraphExecDestroy(h->graph[c][f]); h->graph[c][f] = nullptr; }
+        for (int f = 0; f < 4; f++) {
+            h->graph_dirty[c][f] = true;
+            if (destroy && h->graph[c][f]) { cudaGraphExecDestroy(h->graph[c][f]); h->graph[c][f] = nullptr; }
+        }
 }
 
 static void make_grid(qnb_handle *h, const double *hx) {
@@ -284,12 +290,17 @@ static void make_grid(qnb_handle *h, const double *hx) {
         rmax2 = 2.0 * std::sqrt(r2m) + 1e-6;
     }
     h->cut.rmax2 = rmax2;
-    double rcmax = (std::sqrt(std::max({h->cut.rc2[0], h->cut.rc2[1], h->cut.rc2[2], 1.0})) + rmax2) * 1.0001;
-    const int nmax = 40;
+    const double rcmax = (std::sqrt(std::max({h->cut.rc2[0], h->cut.rc2[1], h->cut.rc2[2], 1.0})) + rmax2) * 1.0001;
+    // cells of HALF the largest cut-off, searched with reach 2: the scanned volume is (5/2 Rc)^3 instead of (3 Rc)^3
+    // for the lists and hugs the LRF shell twice as tightly (env QNB_CELL_DIV overrides the divisor)
+    int cell_div = 2;
+    if (const char *e = getenv("QNB_CELL_DIV")) cell_div = std::max(1, atoi(e));
+    const double edge = rcmax / cell_div;
+    const int nmax = 48;
     if (s.use_PBC) {
         G.periodic = 1;
         for (int d = 0; d < 3; d++) {
-            int n = (int)std::floor(h->box[d] / rcmax);
+            int n = (int)std::floor(h->box[d] / edge);
             n = std::max(1, std::min(n, nmax));
             G.n[d] = n;
             G.org[d] = 0;
@@ -310,7 +321,7 @@ static void make_grid(qnb_handle *h, const double *hx) {
         }
         for (int d = 0; d < 3; d++) {
             const double ext = G.inv_box[d];
-            double cell = std::max(rcmax, ext / nmax);
+            double cell = std::max(edge, ext / nmax);
             G.n[d] = std::max(1, (int)std::floor(ext / cell) + 1);
             G.inv_cell[d] = 1.0 / cell;
         }
@@ -327,6 +338,11 @@ static void make_grid(qnb_handle *h, const double *hx) {
         r[d] = (all || m > G.n[d]) ? G.n[d] : (int)m;
     }
     h->lrf_reach = make_int3(r[0], r[1], r[2]);
+    for (int d = 0; d < 3; d++) {
+        double m = std::ceil(rcmax * G.inv_cell[d]);
+        r[d] = std::max(1, (int)m);
+    }
+    h->list_reach = make_int3(r[0], r[1], r[2]);
 }
 
 static int run_exclusive_scan(qnb_handle *h, const int *in, int *out, int n) {
@@ -364,7 +380,7 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
         LAUNCH(h, k_pack_items, cdiv(nu, 256), 256, 0, D, h->upos.p, h->cell_items.p, h->item_pos.p, h->item_posf.p, h->item_nq.p);
         run_exclusive_scan(h, h->item_nq.p, h->src_off.p, nu);
         LAUNCH(h, k_pack_atoms, cdiv(nu, 128), 128, 0, D, h->cell_items.p, h->src_off.p, h->pk_atom.p, h->pk_q.p, h->pk_qd.p, h->pk_ct.p);
-        LAUNCH(h, k_build_rows<false>, cdiv(nu * 32, 256), 256, 0, D, h->cut, G, h->x.p, h->upos.p, h->cell_of.p, h->cell_start.p,
+        LAUNCH(h, k_build_rows<false>, cdiv(nu * 32, 256), 256, 0, D, h->cut, G, h->list_reach, h->x.p, h->upos.p, h->cell_of.p, h->cell_start.p,
                h->item_pos.p, h->src_off.p, h->counts.p, (const int *)nullptr, (uint32_t *)nullptr);
         LAUNCH(h, k_row_totals, cdiv(nu, 256), 256, 0, nu, h->counts.p, h->row_tot.p);
         run_exclusive_scan(h, h->row_tot.p, h->row_off.p, nu);
@@ -393,7 +409,7 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
             h->wrow.ensure((size_t)std::max(h->nwchunk, 1) * 32) || h->sdesc.ensure(std::max(h->nschunk, 1)) ||
             h->srow.ensure((size_t)std::max(h->nschunk, 1) * 32))
             return 1;
-        LAUNCH(h, k_build_rows<true>, cdiv(nu * 32, 256), 256, 0, D, h->cut, G, h->x.p, h->upos.p, h->cell_of.p, h->cell_start.p,
+        LAUNCH(h, k_build_rows<true>, cdiv(nu * 32, 256), 256, 0, D, h->cut, G, h->list_reach, h->x.p, h->upos.p, h->cell_of.p, h->cell_start.p,
                h->item_pos.p, h->src_off.p, h->counts.p, h->row_off.p, h->rows.p);
         if (h->nwchunk > 0)
             LAUNCH(h, k_chunk_fill, cdiv(nwat * 32, 256), 256, 0, D, nsol, nwat, 0, h->counts.p, h->row_off.p, h->rows.p, off_w,
@@ -560,7 +576,8 @@ static int step_device(qnb_handle *h, int flags, bool with_copies = false) {
     flags &= 3;
     if (graphable) {
         cudaGraphExec_t &ge = h->graph[with_copies ? 1 : 0][flags];
-        if (!ge) {
+        bool &dirty = h->graph_dirty[with_copies ? 1 : 0][flags];
+        if (!ge || dirty) {
             cudaGraph_t g = nullptr;
             const int64_t l0 = h->launches;
             CU(cudaStreamBeginCapture(h->st, cudaStreamCaptureModeThreadLocal));
@@ -575,9 +592,16 @@ static int step_device(qnb_handle *h, int flags, bool with_copies = false) {
             h->graph_launches[with_copies ? 1 : 0][flags] = (int)(h->launches - l0);
             h->launches = l0;
             if (rc || ce != cudaSuccess || !g) return fail("CUDA graph capture of the step failed: %s", cudaGetErrorString(ce));
-            ce = cudaGraphInstantiate(&ge, g, 0);
+            bool updated = false;
+            if (ge) {
+                cudaGraphExecUpdateResultInfo info;
+                updated = cudaGraphExecUpdate(ge, g, &info) == cudaSuccess;
+                if (!updated) { cudaGetLastError(); cudaGraphExecDestroy(ge); ge = nullptr; }
+            }
+            if (!updated) ce = cudaGraphInstantiate(&ge, g, 0);
             cudaGraphDestroy(g);
             if (ce != cudaSuccess) return fail("cudaGraphInstantiate: %s", cudaGetErrorString(ce));
+            dirty = false;
         }
         CU(cudaGraphLaunch(ge, h->st));
         h->launches += h->graph_launches[with_copies ? 1 : 0][flags];
@@ -1016,7 +1040,7 @@ int qnb_finalize(qnb_handle *h) {
     cudaSetDevice(h->device);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     if (h->st) cudaStreamSynchronize(h->st);
-    drop_graphs(h);
+    drop_graphs(h, true);
     for (int k = 0; k < kAux; k++) { if (h->aux[k]) cudaStreamDestroy(h->aux[k]); if (h->ev_join[k]) cudaEventDestroy(h->ev_join[k]); }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     h->crg.release(); h->ljd.release(); h->crgf.release(); h->ljf.release(); h->ctype.release(); h->grp_of_atom.release();

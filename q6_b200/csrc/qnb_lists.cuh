@@ -177,7 +177,7 @@ __device__ __forceinline__ XSeg x_segments(int c, int m, int n, int periodic) {
 // counts[3*u + {0,1,2}] = |A_own|, |A_mir|, |B|.
 template <bool FILL>
 __global__ void __launch_bounds__(256)
-k_build_rows(Dev D, Cut C, Grid G, const double *__restrict__ x, const double *__restrict__ upos, const int *__restrict__ cell_of,
+k_build_rows(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x, const double *__restrict__ upos, const int *__restrict__ cell_of,
              const int *__restrict__ cell_start, const double4 *__restrict__ item_pos,
              const int *__restrict__ src_off, int *__restrict__ counts, const int *__restrict__ row_off,
              uint32_t *__restrict__ rows) {
@@ -198,8 +198,8 @@ k_build_rows(Dev D, Cut C, Grid G, const double *__restrict__ x, const double *_
         const float puf[3] = {(float)pu[0], (float)pu[1], (float)pu[2]};
         const int cu = cell_of[u];
         const int cx = cu % G.n[0], cy = (cu / G.n[0]) % G.n[1], cz = cu / (G.n[0] * G.n[1]);
-        const DimRange rz = dim_range(cz, 1, G.n[2], G.periodic), ry = dim_range(cy, 1, G.n[1], G.periodic);
-        const XSeg xs = x_segments(cx, 1, G.n[0], G.periodic);
+        const DimRange rz = dim_range(cz, reach.z, G.n[2], G.periodic), ry = dim_range(cy, reach.y, G.n[1], G.periodic);
+        const XSeg xs = x_segments(cx, reach.x, G.n[0], G.periodic);
         const int gs_lo = u_sol ? D.gs_off[u] : 0, gs_hi = u_sol ? D.gs_off[u + 1] : 0;
         for (int iz = 0; iz < rz.count; iz++) {
             int z = rz.start + iz; z = (z % G.n[2] + G.n[2]) % G.n[2];
@@ -546,7 +546,9 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
     const int cx = cu % G.n[0], cy = (cu / G.n[0]) % G.n[1], cz = cu / (G.n[0] * G.n[1]);
     const DimRange rz = dim_range(cz, reach.z, G.n[2], G.periodic), ry = dim_range(cy, reach.y, G.n[1], G.periodic);
     const XSeg xs = x_segments(cx, reach.x, G.n[0], G.periodic);
-    const int nrow = rz.count * ry.count * xs.n;
+    // every cell is in reach (sphere with RcLRF spanning it, "no LRF cut-off" boxes): scan the item array as one row
+    const bool whole = rz.count == G.n[2] && ry.count == G.n[1] && xs.n == 1 && xs.lo[0] == 0 && xs.hi[0] == G.n[0];
+    const int nrow = whole ? 1 : rz.count * ry.count * xs.n;
     // screening thresholds of this target against solute / water sources (FP32, see screen_r2)
     const bool t_sol = t < ns;
     const int cls_s = t_sol ? 0 : 1, cls_w = t_sol ? 1 : 2;     // class with a solute / a water source
@@ -562,7 +564,8 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
     int qn = 0;   // entries waiting in this warp's queue (warp-uniform)
     for (int r0 = 0; r0 < nrow; r0 += kLrfSegBatch) {
         __syncthreads();
-        for (int r = r0 + threadIdx.x; r < min(nrow, r0 + kLrfSegBatch); r += blockDim.x) {
+        if (whole) { if (threadIdx.x == 0) seg[0] = make_int2(0, D.nunit); }
+        else for (int r = r0 + threadIdx.x; r < min(nrow, r0 + kLrfSegBatch); r += blockDim.x) {
             const int sgi = r % xs.n, iy = (r / xs.n) % ry.count, iz = r / (xs.n * ry.count);
             int z = rz.start + iz; z = (z % G.n[2] + G.n[2]) % G.n[2];
             int y = ry.start + iy; y = (y % G.n[1] + G.n[1]) % G.n[1];
@@ -572,9 +575,11 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
         }
         __syncthreads();
         const int nseg = min(nrow - r0, kLrfSegBatch);
-        for (int r = wid; r < nseg; r += kRowWarps) {
-            const int lo = seg[r].x, hi = seg[r].y;
-            for (int base = lo; base < hi; base += 32) {
+        // few long segments: all warps share each segment, striding by kRowWarps*32; else one segment per warp
+        const bool share = nseg < kRowWarps;
+        for (int r = share ? 0 : wid; r < nseg; r += share ? 1 : kRowWarps) {
+            const int lo = seg[r].x + (share ? 32 * wid : 0), hi = seg[r].y;
+            for (int base = lo; base < hi; base += share ? 32 * kRowWarps : 32) {
                 const int idx = base + lane;
                 bool accept = false;
                 if (idx < hi) {

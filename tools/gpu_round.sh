@@ -8,7 +8,9 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O
 (timeout 1200 python -m pytest tests -m gpu -x -q) > $OUT/pytest_$TAG.log 2>&1
 tail -15 $OUT/pytest_$TAG.log
 (timeout 600 python bench.py) > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err
-tail -c 3000 $OUT/bench_$TAG.json; tail -5 $OUT/bench_$TAG.err
+tail -c 1500 $OUT/bench_$TAG.json; tail -5 $OUT/bench_$TAG.err
+(timeout 600 python bench.py --workload C5 --steps 50 --warmup 25 --no-cpu-baseline) > $OUT/bench_${TAG}_c5.json 2> $OUT/bench_${TAG}_c5.err
+(timeout 600 python bench.py --workload C3 --steps 200 --warmup 25 --no-cpu-baseline) > $OUT/bench_${TAG}_c3.json 2> $OUT/bench_${TAG}_c3.err
 (timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches_$TAG.csv \
     python bench.py --steps 30 --warmup 3 --no-cpu-baseline) > $OUT/ncu_launch_$TAG.log 2>&1
 (timeout 900 ncu --set full --clock-control none --import-source on \

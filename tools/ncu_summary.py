@@ -68,7 +68,25 @@ def kernels(rep, out):
                     f.write(f"   {m:86s} {r[i]:>16s} {units[i]}\n")
 
 
+def traffic(rep, out):
+    """dram bytes per launch of every profiled kernel (first captured launch) -> profiles/traffic.json for bench.py"""
+    import json
+    raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    ki, ri, wi = hdr.index('Kernel Name'), hdr.index('dram__bytes_read.sum'), hdr.index('dram__bytes_write.sum')
+    scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    res = {}
+    for r in data:
+        name = r[ki].split('(')[0].replace('void ', '').split('<')[0]
+        if name not in res:
+            res[name] = float(r[ri]) * scale.get(units[ri], 1.0) + float(r[wi]) * scale.get(units[wi], 1.0)
+    json.dump({'source': rep, 'note': 'dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full (cold caches)',
+               'bytes_per_launch': res}, open(out, 'w'), indent=1)
+
+
 if __name__ == '__main__':
     tag = sys.argv[1]
+    traffic(f'gpurun_out/prof_{tag}.ncu-rep', 'profiles/traffic.json')
     launches(f'gpurun_out/launches_{tag}.csv', f'profiles/{tag}_launches.txt')
     kernels(f'gpurun_out/prof_{tag}.ncu-rep', f'profiles/{tag}_kernels.txt')
