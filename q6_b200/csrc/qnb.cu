@@ -103,16 +103,17 @@ struct qnb_handle {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join[kAux] = {};
     cudaGraphExec_t graph[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};   // [with copies][flags]
     bool use_graph = true, multi_stream = true;
-    int grid_mult = 4;   // persistent force kernels: blocks per SM (measured best of 1..6 on C2 and C5)
+    int water_blocks = 0, solute_blocks = 0;   // blocks per SM of the two persistent kernels (0: what the occupancy allows)
     int graph_launches[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
     bool graph_dirty[2][4] = {{true, true, true, true}, {true, true, true, true}};
     // static device tables
     DBuf<double> crg, ljd;
     DBuf<float> crgf, ljf;
     DBuf<int> ctype, grp_of_atom, g_first, g_n, g_switch, g_atoms, g_nq, u_sw, u_grp, sp_off, sp_partner, gs_off,
-        gs_atoms, iqseq;
+        gs_atoms, iqseq, nq_off, nq_atoms;
     DBuf<uint8_t> is_q, excl, qbonded, u_excl, ljcode, sp_code;
     DBuf<QPar4> qp_tab, qw_tab;
+    DBuf<float4> qp_tabf, qw_tabf;
     DBuf<QStatic> qstatic;
     int n_qq = 0, n_qstatic = 0;
     // per-step
@@ -134,9 +135,12 @@ struct qnb_handle {
     DBuf<float> pk_q;
     DBuf<double> pk_qd, px, py, pz;
     int npk = 0;   // packed atoms: non-Q atoms of non-excluded units in cell order
-    DBuf<int> nch, choff;
+    DBuf<int> nch, choff, ucost, cost_off, wstart_w, wstart_s;   // chunk counts / offsets / costs per unit, warp shares
+    int wgrid = 0, sgrid = 0;   // grids of the persistent force kernels (one resident wave)
+    int occ_w = 0, occ_s = 0;
     DBuf<int2> wdesc, sdesc;
     DBuf<uint32_t> wrow, srow;
+    DBuf<uint16_t> sspec;   // solute chunks: per entry, special-pair codes of the tile atoms
     int nwchunk = 0, nschunk = 0;   // water-row / solute-row chunks
     int nqp = 0, nqw = 0;
     bool qp_done = false, qw_done = false, lists_built = false;
@@ -199,7 +203,7 @@ static int init_device(qnb_handle *h) {
         upload(h->grp_of_atom, T.grp_of_atom) || upload(h->g_first, T.g_first) || upload(h->g_n, T.g_n) ||
         upload(h->g_switch, T.g_switch) || upload(h->g_atoms, T.g_atoms) || upload(h->g_nq, g_nq) ||
         upload(h->u_sw, T.u_sw) || upload(h->u_grp, T.u_grp) || upload(h->sp_off, T.sp_off) ||
-        upload(h->sp_partner, T.sp_partner) || upload(h->gs_off, T.gs_off) || upload(h->gs_atoms, T.gs_atoms) ||
+        upload(h->sp_partner, T.sp_partner) || upload(h->gs_off, T.gs_off) || upload(h->gs_atoms, T.gs_atoms) || upload(h->nq_off, T.nq_off) || upload(h->nq_atoms, T.nq_atoms) ||
         upload(h->iqseq, T.iqseq0) || upload(h->is_q, T.is_q) || upload(h->excl, T.excl) ||
         upload(h->qbonded, T.qbonded) || upload(h->u_excl, T.u_excl) || upload(h->ljcode, T.ljcode) ||
         upload(h->sp_code, T.sp_code))
@@ -209,6 +213,10 @@ static int init_device(qnb_handle *h) {
         for (size_t k = 0; k < a.size(); k++) a[k] = QPar4{T.qp_tab[k].A, T.qp_tab[k].B, T.qp_tab[k].el, T.qp_tab[k].score};
         for (size_t k = 0; k < b.size(); k++) b[k] = QPar4{T.qw_tab[k].A, T.qw_tab[k].B, T.qw_tab[k].el, T.qw_tab[k].score};
         if (upload(h->qp_tab, a) || upload(h->qw_tab, b)) return 1;
+        std::vector<float4> af(a.size()), bf(b.size());
+        for (size_t k = 0; k < a.size(); k++) af[k] = make_float4((float)a[k].A, (float)a[k].B, (float)a[k].el, (float)a[k].score);
+        for (size_t k = 0; k < b.size(); k++) bf[k] = make_float4((float)b[k].A, (float)b[k].B, (float)b[k].el, (float)b[k].score);
+        if (upload(h->qp_tabf, af) || upload(h->qw_tabf, bf)) return 1;
         std::vector<QStatic> qs;
         for (const auto &e : T.qq_list) qs.push_back(QStatic{e.i, e.j, e.state, e.soft, QPar4{e.p.A, e.p.B, e.p.el, e.p.score}});
         h->n_qq = (int)qs.size();
@@ -220,7 +228,7 @@ static int init_device(qnb_handle *h) {
     D.grp_of_atom = h->grp_of_atom.p; D.g_first = h->g_first.p; D.g_n = h->g_n.p; D.g_switch = h->g_switch.p;
     D.g_atoms = h->g_atoms.p; D.g_nq = h->g_nq.p; D.u_sw = h->u_sw.p; D.u_grp = h->u_grp.p; D.u_excl = h->u_excl.p;
     D.ljf = h->ljf.p; D.ljd = h->ljd.p; D.ljcode = h->ljcode.p; D.sp_off = h->sp_off.p; D.sp_partner = h->sp_partner.p; D.sp_code = h->sp_code.p;
-    D.gs_off = h->gs_off.p; D.gs_atoms = h->gs_atoms.p; D.iqseq = h->iqseq.p; D.qp_tab = h->qp_tab.p; D.qw_tab = h->qw_tab.p;
+    D.gs_off = h->gs_off.p; D.gs_atoms = h->gs_atoms.p; D.nq_off = h->nq_off.p; D.nq_atoms = h->nq_atoms.p; D.iqseq = h->iqseq.p; D.qp_tab = h->qp_tab.p; D.qw_tab = h->qw_tab.p; D.qp_tabf = h->qp_tabf.p; D.qw_tabf = h->qw_tabf.p;
     for (int a = 0; a < 3; a++) {
         D.wq[a] = s.nwat > 0 ? (float)T.w_crg[a] : 0.f;
         D.wqd[a] = s.nwat > 0 ? T.w_crg[a] : 0.0;
@@ -247,7 +255,15 @@ static int init_device(qnb_handle *h) {
     }
     CU(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
     for (int k = 0; k < kAux; k++) {
-        CU(cudaStreamCreateWithFlags(&h->aux[k], cudaStreamNonBlocking));
+    {
+        // the longest kernel of a step is placed first: stream k carries kernel k (kStreamOf); the solute rows (stream 1)
+        // are the critical path of a solvated protein, the water rows fill the SMs behind them
+        int lo = 0, hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // hi = numerically lowest = most urgent
+        static const int kRank[5] = {2, 0, 1, 1, 3};      // water, solute, q_partner, q_atom, qq_static
+        int pr = std::min(lo, hi + (getenv("QNB_NO_PRIORITY") ? 0 : kRank[k < 5 ? k : 4]));
+        CU(cudaStreamCreateWithPriority(&h->aux[k], cudaStreamNonBlocking, pr));
+    }
         CU(cudaEventCreateWithFlags(&h->ev_join[k], cudaEventDisableTiming));
     }
     CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
@@ -255,7 +271,8 @@ static int init_device(qnb_handle *h) {
     CU(cudaEventCreate(&h->ev1));
     if (const char *e = getenv("QNB_NO_GRAPH")) h->use_graph = !(e[0] == '1');
     if (const char *e = getenv("QNB_ONE_STREAM")) h->multi_stream = !(e[0] == '1');
-    if (const char *e = getenv("QNB_GRID_MULT")) h->grid_mult = std::max(1, atoi(e));
+    if (const char *e = getenv("QNB_WATER_BLOCKS")) h->water_blocks = std::max(0, atoi(e));
+    if (const char *e = getenv("QNB_SOLUTE_BLOCKS")) h->solute_blocks = std::max(0, atoi(e));
     return 0;
 }
 
@@ -365,9 +382,9 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
         h->qp_shift_atom.ensure(std::max(D.ncgp_solute, 1)) || h->item_pos.ensure(std::max(nu, 1)) || h->item_posf.ensure(std::max(nu, 1)) ||
         h->src.ensure(std::max(D.natom, 1)) || h->cell_unsorted.ensure(std::max(nu, 1)) ||
         h->item_nq.ensure(std::max(nu, 1) + 1) || h->src_off.ensure(std::max(nu, 1) + 2) ||
-        h->pk_atom.ensure(std::max(D.natom, 1)) || h->pk_ct.ensure(std::max(D.natom, 1)) || h->pk_q.ensure(std::max(D.natom, 1)) ||
-        h->pk_qd.ensure(std::max(D.natom, 1)) || h->px.ensure(std::max(D.natom, 1)) || h->py.ensure(std::max(D.natom, 1)) ||
-        h->pz.ensure(std::max(D.natom, 1)))
+        h->pk_atom.ensure(D.natom + 4) || h->pk_ct.ensure(D.natom + 4) || h->pk_q.ensure(D.natom + 4) ||
+        h->pk_qd.ensure(D.natom + 4) || h->px.ensure(D.natom + 4) || h->py.ensure(D.natom + 4) ||   // +4: the force kernels always fetch three sites
+        h->pz.ensure(D.natom + 4))
         return 1;
     const bool md_lists = true;
     if (nu > 0 && md_lists) {
@@ -386,15 +403,18 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
         run_exclusive_scan(h, h->row_tot.p, h->row_off.p, nu);
         // chunk tables of the streaming force kernels: counts now, contents after the rows are filled
         const int nsol = D.ncgp_solute, nwat = D.nwat;
-        if (h->nch.ensure(nu + 2) || h->choff.ensure(nu + 4)) return 1;
+        if (h->nch.ensure(nu + 2) || h->choff.ensure(nu + 4) || h->ucost.ensure(nu + 2) || h->cost_off.ensure(nu + 4)) return 1;
         int *nch_w = h->nch.p, *nch_s = h->nch.p + nwat + 1, *off_w = h->choff.p, *off_s = h->choff.p + nwat + 2;
+        int *uc_w = h->ucost.p, *uc_s = h->ucost.p + nwat + 1, *co_w = h->cost_off.p, *co_s = h->cost_off.p + nwat + 2;
         if (nwat > 0) {
-            LAUNCH(h, k_chunk_count, cdiv(nwat, 256), 256, 0, D, nsol, nwat, 0, h->counts.p, nch_w);
+            LAUNCH(h, k_chunk_count, cdiv(nwat, 256), 256, 0, D, nsol, nwat, 0, h->counts.p, nch_w, uc_w);
             run_exclusive_scan(h, nch_w, off_w, nwat);
+            run_exclusive_scan(h, uc_w, co_w, nwat);
         }
         if (nsol > 0) {
-            LAUNCH(h, k_chunk_count, cdiv(nsol, 256), 256, 0, D, 0, nsol, kITile, h->counts.p, nch_s);
+            LAUNCH(h, k_chunk_count, cdiv(nsol, 256), 256, 0, D, 0, nsol, kITile, h->counts.p, nch_s, uc_s);
             run_exclusive_scan(h, nch_s, off_s, nsol);
+            run_exclusive_scan(h, uc_s, co_s, nsol);
         }
         int total = 0, npk = 0;
         h->nwchunk = h->nschunk = 0;
@@ -407,16 +427,24 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
         h->npk = npk;
         if (h->rows.ensure((size_t)std::max(total, 1)) || h->wdesc.ensure(std::max(h->nwchunk, 1)) ||
             h->wrow.ensure((size_t)std::max(h->nwchunk, 1) * 32) || h->sdesc.ensure(std::max(h->nschunk, 1)) ||
-            h->srow.ensure((size_t)std::max(h->nschunk, 1) * 32))
+            h->srow.ensure((size_t)std::max(h->nschunk, 1) * 32) || h->sspec.ensure((size_t)std::max(h->nschunk, 1) * 32))
             return 1;
         LAUNCH(h, k_build_rows<true>, cdiv(nu * 32, 256), 256, 0, D, h->cut, G, h->list_reach, h->x.p, h->upos.p, h->cell_of.p, h->cell_start.p,
                h->item_pos.p, h->src_off.p, h->counts.p, h->row_off.p, h->rows.p);
         if (h->nwchunk > 0)
             LAUNCH(h, k_chunk_fill, cdiv(nwat * 32, 256), 256, 0, D, nsol, nwat, 0, h->counts.p, h->row_off.p, h->rows.p, off_w,
-                   h->wdesc.p, h->wrow.p);
+                   h->wdesc.p, h->wrow.p, h->pk_atom.p, (uint16_t *)nullptr);
         if (h->nschunk > 0)
             LAUNCH(h, k_chunk_fill, cdiv(nsol * 32, 256), 256, 0, D, 0, nsol, kITile, h->counts.p, h->row_off.p, h->rows.p, off_s,
-                   h->sdesc.p, h->srow.p);
+                   h->sdesc.p, h->srow.p, h->pk_atom.p, h->sspec.p);
+        // one resident wave per kernel, every warp an equal share of the estimated work
+        h->wgrid = std::max(1, std::min((h->water_blocks ? h->water_blocks : std::max(h->occ_w, 1)) * h->nsm, cdiv(h->nwchunk, 4 * 4)));
+        h->sgrid = std::max(1, std::min((h->solute_blocks ? h->solute_blocks : std::max(h->occ_s, 1)) * h->nsm, cdiv(h->nschunk, 4 * 4)));
+        if (h->wstart_w.ensure(4 * h->wgrid + 2) || h->wstart_s.ensure(4 * h->sgrid + 2)) return 1;
+        if (h->nwchunk > 0)
+            LAUNCH(h, k_warp_starts, cdiv(4 * h->wgrid + 1, 128), 128, 0, D, nsol, nwat, 0, h->counts.p, off_w, co_w, 4 * h->wgrid, h->wstart_w.p);
+        if (h->nschunk > 0)
+            LAUNCH(h, k_warp_starts, cdiv(4 * h->sgrid + 1, 128), 128, 0, D, 0, nsol, kITile, h->counts.p, off_s, co_s, 4 * h->sgrid, h->wstart_s.p);
     }
     // Q-atom partner lists: built once when the cut-off covers everything (nbqplist L3678, nbqwlist L3889,
     // nbqplist_box L3780, nbqwlist_box L3972)
@@ -491,6 +519,24 @@ static bool step_kernel_active(const qnb_handle *h, int k, int flags) {
     return false;
 }
 
+static size_t solute_smem(const Dev &D) { return (size_t)D.nct * 6 * (sizeof(double) + sizeof(float)) + (size_t)D.nct * D.nct; }
+
+// resident blocks per SM of the two persistent kernels in the variant this system uses (register-limited)
+static void query_occupancy(qnb_handle *h) {
+    const Dev &D = h->D;
+    const bool pbc = D.use_PBC, spc = D.spc_water, geom = D.geometric;
+    const size_t sm = solute_smem(D);
+#define WOCC(P, S, G) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_w, k_water_force<P, S, G>, 128, 0)
+    if (pbc) { if (spc) WOCC(true, true, true); else if (geom) WOCC(true, false, true); else WOCC(true, false, false); }
+    else { if (spc) WOCC(false, true, true); else if (geom) WOCC(false, false, true); else WOCC(false, false, false); }
+#undef WOCC
+#define SOCC(P, G) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_s, k_solute_force<P, G>, 128, sm)
+    if (pbc) { if (geom) SOCC(true, true); else SOCC(true, false); }
+    else { if (geom) SOCC(false, true); else SOCC(false, false); }
+#undef SOCC
+    cudaGetLastError();
+}
+
 static void launch_step_kernel(qnb_handle *h, int k, cudaStream_t cs) {
     const Dev &D = h->D;
     double *grad = h->out.p, *E = h->out.p + 3 * (size_t)D.natom;
@@ -498,18 +544,19 @@ static void launch_step_kernel(qnb_handle *h, int k, cudaStream_t cs) {
     const bool pbc = D.use_PBC, spc = D.spc_water, geom = D.geometric;
     switch (k) {
     case K_WATER: {
-        // persistent: at most 3 blocks of 4 warps per SM, at least ~4 chunks per warp
-        const int grid = std::max(1, std::min(h->grid_mult * h->nsm, cdiv(h->nwchunk, 4 * 4)));
-#define WCASE(P, S, G) LAUNCH_ON(h, cs, (k_water_force<P, S, G>), grid, 128, 0, D, h->x.p, h->px.p, h->py.p, h->pz.p, h->pk_q.p, h->pk_ct.p, h->pk_atom.p, h->nwchunk, h->wdesc.p, h->wrow.p, grad, E, nE)
+#define WCASE(P, S, G)                                                                                                             \
+    LAUNCH_ON(h, cs, (k_water_force<P, S, G>), h->wgrid, 128, 0, D, h->x.p, h->px.p, h->py.p, h->pz.p, h->pk_q.p, h->pk_ct.p,     \
+              h->pk_atom.p, h->wstart_w.p, h->wdesc.p, h->wrow.p, grad, E, nE)
         if (pbc) { if (spc) WCASE(true, true, true); else if (geom) WCASE(true, false, true); else WCASE(true, false, false); }
         else { if (spc) WCASE(false, true, true); else if (geom) WCASE(false, false, true); else WCASE(false, false, false); }
 #undef WCASE
         break;
     }
     case K_SOLUTE: {
-        const int grid = std::max(1, std::min(std::min(h->grid_mult, 3) * h->nsm, cdiv(h->nschunk, 4 * 4))   /* 168 registers: 3 blocks per SM */);
-        const size_t sm = (size_t)D.nct * 6 * (sizeof(double) + sizeof(float)) + (size_t)D.nct * D.nct;
-#define SCASE(P, G) LAUNCH_ON(h, cs, (k_solute_force<P, G>), grid, 128, sm, D, h->x.p, h->px.p, h->py.p, h->pz.p, h->pk_q.p, h->pk_qd.p, h->pk_ct.p, h->pk_atom.p, h->nschunk, h->sdesc.p, h->srow.p, grad, E, nE)
+        const size_t sm = solute_smem(D);
+#define SCASE(P, G)                                                                                                              \
+    LAUNCH_ON(h, cs, (k_solute_force<P, G>), h->sgrid, 128, sm, D, h->x.p, h->px.p, h->py.p, h->pz.p, h->pk_q.p, h->pk_qd.p,    \
+              h->pk_ct.p, h->pk_atom.p, h->wstart_s.p, h->sdesc.p, h->srow.p, h->sspec.p, grad, E, nE)
         if (pbc) { if (geom) SCASE(true, true); else SCASE(true, false); }
         else { if (geom) SCASE(false, true); else SCASE(false, false); }
 #undef SCASE
@@ -517,7 +564,7 @@ static void launch_step_kernel(qnb_handle *h, int k, cudaStream_t cs) {
     }
     case K_QPARTNER: {
         const int n = h->nqp + 3 * h->nqw;
-        const size_t sm = sizeof(double) * (3 * (size_t)D.nqat + D.nstates);
+        const size_t sm = sizeof(float) * (3 * (size_t)D.nqat + D.nstates);
         const dim3 pgrid(cdiv(n, 128), std::max(1, std::min(D.nqat, cdiv(6 * 148, cdiv(n, 128)))));
         if (pbc) LAUNCH_ON(h, cs, k_q_partner<true>, pgrid, 128, sm, D, h->x.p, h->lambda.p, h->nqp, h->qp_list.p, h->qp_shift_atom.p, h->nqw, h->qw_list.p, grad);
         else LAUNCH_ON(h, cs, k_q_partner<false>, pgrid, 128, sm, D, h->x.p, h->lambda.p, h->nqp, h->qp_list.p, h->qp_shift_atom.p, h->nqw, h->qw_list.p, grad);
@@ -553,7 +600,9 @@ static int issue_step(qnb_handle *h, int flags) {
         LAUNCH(h, k_pack_coords, cdiv(h->npk, 256), 256, 0, h->npk, h->pk_atom.p, h->x.p, h->px.p, h->py.p, h->pz.p);
     CU(cudaEventRecord(h->ev_fork, h->st));
     bool used[kAux] = {};
-    for (int k = 0; k < K_COUNT; k++) {
+    static const int kOrder[K_COUNT] = {K_SOLUTE, K_QPARTNER, K_QATOM, K_WATER, K_QSTATIC, K_LRF};
+    for (int o = 0; o < K_COUNT; o++) {
+        const int k = kOrder[o];
         if (!step_kernel_active(h, k, flags)) continue;
         const int si = h->multi_stream ? kStreamOf[k] : -1;
         cudaStream_t cs = si < 0 ? h->st : h->aux[si];
@@ -646,6 +695,18 @@ extern "C" {
 
 const char *qnb_last_error(void) { return g_err.c_str(); }
 
+#ifdef QNB_TRACE
+int qnb_trace_read(unsigned long long *out) {   // [2][8192][6], experiment builds only
+    CU(cudaMemcpyFromSymbol(out, qnb::g_trace, sizeof(unsigned long long) * 2 * 8192 * 6));
+    return 0;
+}
+int qnb_trace_clear(void) {
+    static std::vector<unsigned long long> z(2 * 8192 * 6, 0ull);
+    CU(cudaMemcpyToSymbol(qnb::g_trace, z.data(), sizeof(unsigned long long) * z.size()));
+    return 0;
+}
+#endif
+
 int qnb_device_count(void) {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -664,6 +725,7 @@ int qnb_init(const qnb_system *sys, int device, qnb_handle **out) {
     h->device = device;
     if (!h->T.build(sys)) { fail("qnb_init: %s", h->T.error.c_str()); delete h; return 1; }
     if (init_device(h)) { delete h; return 1; }
+    qnb::query_occupancy(h);
     *out = h;
     return 0;
 }
@@ -1046,14 +1108,14 @@ int qnb_finalize(qnb_handle *h) {
     h->crg.release(); h->ljd.release(); h->crgf.release(); h->ljf.release(); h->ctype.release(); h->grp_of_atom.release();
     h->g_first.release(); h->g_n.release(); h->g_switch.release(); h->g_atoms.release(); h->g_nq.release();
     h->u_sw.release(); h->u_grp.release(); h->sp_off.release(); h->sp_partner.release(); h->gs_off.release();
-    h->gs_atoms.release(); h->iqseq.release(); h->is_q.release(); h->excl.release(); h->qbonded.release();
-    h->u_excl.release(); h->ljcode.release(); h->sp_code.release(); h->qp_tab.release(); h->qw_tab.release();
+    h->gs_atoms.release(); h->nq_off.release(); h->nq_atoms.release(); h->iqseq.release(); h->is_q.release(); h->excl.release(); h->qbonded.release();
+    h->u_excl.release(); h->ljcode.release(); h->sp_code.release(); h->qp_tab.release(); h->qw_tab.release(); h->qp_tabf.release(); h->qw_tabf.release();
     h->qstatic.release(); h->x.release(); h->out.release(); h->lambda.release(); h->lrf.release(); h->upos.release();
     h->cell_of.release(); h->cell_count.release(); h->cell_start.release(); h->cell_items.release(); h->counts.release();
     h->row_tot.release(); h->row_off.release(); h->flag.release(); h->pos.release(); h->qp_list.release();
     h->qw_list.release(); h->qp_shift_atom.release(); h->rows.release(); h->flush.release();
     h->pk_atom.release(); h->pk_ct.release(); h->pk_q.release(); h->pk_qd.release(); h->px.release(); h->py.release(); h->pz.release();
-    h->nch.release(); h->choff.release(); h->wdesc.release(); h->wrow.release(); h->sdesc.release(); h->srow.release();
+    h->nch.release(); h->choff.release(); h->ucost.release(); h->cost_off.release(); h->wstart_w.release(); h->wstart_s.release(); h->wdesc.release(); h->wrow.release(); h->sdesc.release(); h->srow.release(); h->sspec.release();
     h->item_posf.release();
     h->item_pos.release(); h->src.release(); h->cell_unsorted.release(); h->item_nq.release(); h->src_off.release();
     if (h->hx) cudaFreeHost(h->hx);

@@ -13,6 +13,15 @@
 
 namespace qnb {
 
+#ifdef QNB_TRACE
+// design experiment (tools/exp_trace.py): per-warp timestamps of the two persistent kernels
+__device__ unsigned long long g_trace[2][8192][6];
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define QTRACE(k, gw, i, v) do { if ((threadIdx.x & 31) == 0 && (gw) < 8192) g_trace[k][gw][i] = (v); } while (0)
+#else
+#define QTRACE(k, gw, i, v) do { } while (0)
+#endif
+
 // FP32 LJ parameters of a pair from per-type tables (precompute_set_values_*: simprep.f90:3326-3342)
 template <bool GEOM>
 __device__ __forceinline__ void lj_pair(const float *__restrict__ ljf, int cta, int ctb, int code, float &A, float &B) {
@@ -36,7 +45,7 @@ template <bool LJ, bool ENERGY>
 __device__ __forceinline__ float pair_f32(float dx, float dy, float dz, float qq, float A, float B, float &rinv_out,
                                           float &evdw) {
     const float r2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-    const float rinv = rsqrtf(r2);
+    const float rinv = rsqrt_fast(r2);
     const float rinv2 = rinv * rinv;
     rinv_out = rinv;
     const float vel = qq * rinv;
@@ -64,6 +73,15 @@ __device__ __forceinline__ void energy_f64(double dx, double dy, double dz, doub
     eel = fma(qq, y, eel);
     const double y2 = y * y, r6 = y2 * y2 * y2;
     evdw += fma(A * r6, r6, -B * r6);
+}
+// same, returning the two terms (callers add them under a select)
+__device__ __forceinline__ void energy_terms_f64(double dx, double dy, double dz, double qq, double A, double B,
+                                                 float rinv_seed, double &tel, double &tvdw) {
+    const double r2 = fma(dx, dx, fma(dy, dy, dz * dz));
+    const double y = rsqrt_refine(r2, rinv_seed);
+    tel = qq * y;
+    const double y2 = y * y, r6 = y2 * y2 * y2;
+    tvdw = fma(A * r6, r6, -B * r6);
 }
 template <bool GEOM>
 __device__ __forceinline__ void lj_pair_f64(const double *__restrict__ ljd, int cta, int ctb, int code, double &A, double &B) {
@@ -104,7 +122,8 @@ struct WaterTile {          // own molecule of the row being processed
 template <bool PBC, bool SPC>
 __device__ __forceinline__ void ww_chunk(const Dev &D, WaterTile &T, bool own, bool any_own, bool valid,
                                          const double (&pj)[9], double &eel, double &evdw) {
-    if (!valid) return;
+    // Straight-line code for all 32 lanes: a padding lane computes on packed atom 0 and its dv is replaced by zero
+    // (an early return of those lanes keeps the nine pairs from being scheduled together).
     // pj = x,y,z of the partner's three sites (SoA order: x0 x1 x2 y0 y1 y2 z0 z1 z2)
     double shx = 0, shy = 0, shz = 0;
     if (PBC) {
@@ -120,22 +139,39 @@ __device__ __forceinline__ void ww_chunk(const Dev &D, WaterTile &T, bool own, b
         ud[b][0] = (pj[b] - T.o[0]) + shx; ud[b][1] = (pj[3 + b] - T.o[1]) + shy; ud[b][2] = (pj[6 + b] - T.o[2]) + shz;
         uf[b][0] = (float)ud[b][0]; uf[b][1] = (float)ud[b][1]; uf[b][2] = (float)ud[b][2];
     }
+    float seed[3][3];   // FP32 1/r of the nine site pairs: seeds of the FP64 energies
 #pragma unroll
     for (int a = 0; a < 3; a++) {
 #pragma unroll
         for (int b = 0; b < 3; b++) {
             const float dx = uf[b][0] - T.sf[a][0], dy = uf[b][1] - T.sf[a][1], dz = uf[b][2] - T.sf[a][2];
-            float rinv, ev = 0.f, dv;
+            float ev = 0.f, dv;
             const bool lj = !SPC || (a == 0 && b == 0);   // nonbond_ww_spc: only the first pair carries LJ
-            if (lj) dv = pair_f32<true, false>(dx, dy, dz, D.wwQ[a * 3 + b], D.wwA[a * 3 + b], D.wwB[a * 3 + b], rinv, ev);
-            else dv = pair_f32<false, false>(dx, dy, dz, D.wwQ[a * 3 + b], 0.f, 0.f, rinv, ev);
+            if (lj) dv = pair_f32<true, false>(dx, dy, dz, D.wwQ[a * 3 + b], D.wwA[a * 3 + b], D.wwB[a * 3 + b], seed[a][b], ev);
+            else dv = pair_f32<false, false>(dx, dy, dz, D.wwQ[a * 3 + b], 0.f, 0.f, seed[a][b], ev);
+            dv = valid ? dv : 0.f;   // a select, not a product: the padding lane may hold r = 0
             T.g[a][0] = fmaf(-dx, dv, T.g[a][0]); T.g[a][1] = fmaf(-dy, dv, T.g[a][1]); T.g[a][2] = fmaf(-dz, dv, T.g[a][2]);
-            if (any_own && own) {   // any_own is warp-uniform: mirror-only chunks skip the FP64 code altogether
+        }
+    }
+    // Energies once per pair, on the owner side, FP64.  ONE warp-uniform branch around all nine pairs (mirror-only chunks
+    // skip it): nine independent dependency chains that the scheduler interleaves -- a branch per pair serialises them.
+#ifdef QNB_EXP_OWNLANES
+    if (own) {
+#else
+    if (any_own) {
+#endif
+        double ea[3] = {0.0, 0.0, 0.0}, ev = 0.0;
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+#pragma unroll
+            for (int b = 0; b < 3; b++) {
+                const bool lj = !SPC || (a == 0 && b == 0);
                 if (lj) energy_f64(ud[b][0] - T.sd[a][0], ud[b][1] - T.sd[a][1], ud[b][2] - T.sd[a][2], D.wwQd[a * 3 + b],
-                                   D.wwAd[a * 3 + b], D.wwBd[a * 3 + b], rinv, eel, evdw);
-                else eel += coulomb_f64(ud[b][0] - T.sd[a][0], ud[b][1] - T.sd[a][1], ud[b][2] - T.sd[a][2], D.wwQd[a * 3 + b], rinv);
+                                   D.wwAd[a * 3 + b], D.wwBd[a * 3 + b], seed[a][b], ea[a], ev);
+                else ea[a] += coulomb_f64(ud[b][0] - T.sd[a][0], ud[b][1] - T.sd[a][1], ud[b][2] - T.sd[a][2], D.wwQd[a * 3 + b], seed[a][b]);
             }
         }
+        if (own) { eel += (ea[0] + ea[1]) + ea[2]; evdw += ev; }
     }
 }
 
@@ -171,64 +207,51 @@ __device__ __forceinline__ void wp_chunk(const Dev &D, WaterTile &T, bool valid,
     }
 }
 
+#ifndef QNB_WATER_MINB
+#define QNB_WATER_MINB 3   // measured on C2 and C5: 3 blocks (<=168 registers) beat 4 (spills) and 2
+#endif
 template <bool PBC, bool SPC, bool GEOM>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, QNB_WATER_MINB)
 k_water_force(Dev D, const double *__restrict__ x, const double *__restrict__ px, const double *__restrict__ py,
               const double *__restrict__ pz, const float *__restrict__ pk_q, const int *__restrict__ pk_ct,
-              const int *__restrict__ pk_atom, int nchunk, const int2 *__restrict__ cdesc,
+              const int *__restrict__ pk_atom, const int *__restrict__ wstart, const int2 *__restrict__ cdesc,
               const uint32_t *__restrict__ crow, double *__restrict__ grad, double *__restrict__ Eslots, int nE) {
     const int lane = threadIdx.x & 31;
-    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
-    const int per = (nchunk + nwarp - 1) / nwarp;
-    const int c0 = gw * per, c1 = min(nchunk, c0 + per);
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int c0 = wstart[gw], c1 = wstart[gw + 1];   // this warp's share of the chunks (k_warp_starts)
+    QTRACE(0, gw, 0, gtime()); QTRACE(0, gw, 1, (unsigned long long)clock64()); QTRACE(0, gw, 4, (unsigned long long)(c1 > c0 ? c1 - c0 : 0)); QTRACE(0, gw, 5, 0ull);
     if (c0 >= c1) return;
     WaterTile T;
     int cur_w = -1;
     double evdw = 0.0, eel = 0.0;
+    const int slot = split_slot<9, 16>(lane);   // which gradient component this lane owns after the split reduction
 
     auto flush = [&]() {
         if (cur_w < 0) return;
         const int i0 = D.nat_solute + 3 * cur_w;
-        double s[9];
+        float s[9];
 #pragma unroll
-        for (int k = 0; k < 9; k++) s[k] = warp_sum((double)T.g[k / 3][k % 3]);
-        double mine = 0;
-#pragma unroll
-        for (int k = 0; k < 9; k++) if (lane == k) mine = s[k];
-        if (lane < 9) atomicAdd(&grad[3 * i0 + lane], mine);
+        for (int k = 0; k < 9; k++) s[k] = T.g[k / 3][k % 3];
+        const float mine = split_reduce<9, 16>(s, lane);
+        if (slot >= 0) atomicAdd(&grad[3 * i0 + slot], (double)mine);
     };
-    // stage A: descriptor + entry; stage B: partner coordinates
+    // stage A: descriptor + entry; stage B: partner coordinates.  Both are branch-free (padding entries fetch packed
+    // atom 0, solute partners fetch three sites like waters do: the arrays are padded) so that the loads land directly
+    // in the registers the NEXT iteration computes from: a conditional load costs a register move that waits for it.
     auto load_a = [&](int c, int2 &d, uint32_t &e) {
         d = cdesc[c];
         e = crow[(size_t)c * 32 + lane];
     };
-    auto load_b = [&](const int2 &d, uint32_t e, double (&pj)[9], float &qb, int &ctb) {
-        if (e == kPadEntry) return;
-        const int p = (int)(e & kIdMask);
-        if (d.y == kChunkB) {
-            pj[0] = px[p]; pj[3] = py[p]; pj[6] = pz[p];
-            qb = pk_q[p]; ctb = pk_ct[p];
-        } else {
+    auto load_b = [&](uint32_t e, double (&pj)[9], float &qb, int &ctb) {
+        const int p = (e == kPadEntry) ? 0 : (int)(e & kIdMask);
 #pragma unroll
-            for (int b = 0; b < 3; b++) { pj[b] = px[p + b]; pj[3 + b] = py[p + b]; pj[6 + b] = pz[p + b]; }
-        }
+        for (int b = 0; b < 3; b++) { pj[b] = px[p + b]; pj[3 + b] = py[p + b]; pj[6 + b] = pz[p + b]; }
+        qb = pk_q[p]; ctb = pk_ct[p];
     };
-    int2 d0, d1 = make_int2(-1, 0), d2 = make_int2(-1, 0);
-    uint32_t e0, e1 = kPadEntry, e2 = kPadEntry;
-    double p0[9], p1[9];
-    float q0 = 0.f, q1 = 0.f;
-    int ct0 = 0, ct1 = 0;
-#pragma unroll
-    for (int k = 0; k < 9; k++) { p0[k] = 0.0; p1[k] = 0.0; }
-    load_a(c0, d0, e0);
-    if (c0 + 1 < c1) load_a(c0 + 1, d1, e1);
-    load_b(d0, e0, p0, q0, ct0);
-    for (int c = c0; c < c1; c++) {
-        if (c + 2 < c1) load_a(c + 2, d2, e2);
-        if (c + 1 < c1) load_b(d1, e1, p1, q1, ct1);
-        if (d0.x != cur_w) {
+    auto compute = [&](const int2 &d, uint32_t e, const double (&pj)[9], float qb, int ctb) {
+        if (d.x != cur_w) {
             flush();
-            cur_w = d0.x;
+            cur_w = d.x;
             const int i0 = D.nat_solute + 3 * cur_w;
             T.o[0] = x[3 * i0]; T.o[1] = x[3 * i0 + 1]; T.o[2] = x[3 * i0 + 2];
 #pragma unroll
@@ -241,18 +264,36 @@ k_water_force(Dev D, const double *__restrict__ x, const double *__restrict__ px
                 }
             }
         }
-        const bool valid = e0 != kPadEntry;
-        if (d0.y == kChunkB) wp_chunk<PBC, GEOM>(D, T, valid, p0, q0, ct0, e0, x, pk_atom);
+        const bool valid = e != kPadEntry;
+        if (d.y == kChunkB) wp_chunk<PBC, GEOM>(D, T, valid, pj, qb, ctb, e, x, pk_atom);
         else {
-            const bool own = valid && (e0 & kOwnerBit);
-            ww_chunk<PBC, SPC>(D, T, own, __any_sync(kFull, own), valid, p0, eel, evdw);
+            const bool own = valid && (e & kOwnerBit);
+            ww_chunk<PBC, SPC>(D, T, own, __any_sync(kFull, own), valid, pj, eel, evdw);
         }
-        d0 = d1; e0 = e1; q0 = q1; ct0 = ct1;
-#pragma unroll
-        for (int k = 0; k < 9; k++) p0[k] = p1[k];
-        d1 = d2; e1 = e2;
+    };
+    // chunk c computes from (d0,e0,P); chunk c+1 is (d1,e1) with its coordinates landing in R; (d2,e2) is chunk c+2.
+    // The body is written out twice so that P and R swap roles without register moves.
+    int2 d0, d1, d2;
+    uint32_t e0, e1, e2;
+    double P[9], R[9];
+    float qP, qR;
+    int ctP, ctR;
+    const int clast = c1 - 1;
+    load_a(c0, d0, e0);
+    load_a(min(c0 + 1, clast), d1, e1);
+    load_b(e0, P, qP, ctP);
+    for (int c = c0; c < c1; c += 2) {
+        load_a(min(c + 2, clast), d2, e2);
+        load_b(e1, R, qR, ctR);
+        compute(d0, e0, P, qP, ctP);
+        if (c + 1 >= c1) break;
+        load_a(min(c + 3, clast), d0, e0);
+        load_b(e2, P, qP, ctP);
+        compute(d1, e1, R, qR, ctR);
+        d1 = d0; e1 = e0; d0 = d2; e0 = e2;   // chunk c+2 -> slot 0 (coordinates already in P), chunk c+3 -> slot 1
     }
     flush();
+    QTRACE(0, gw, 2, (unsigned long long)clock64()); QTRACE(0, gw, 3, gtime());
     const double sv = warp_sum(evdw), se = warp_sum(eel);
     if (lane == 0) {
         double *E = Eslots + (size_t)(gw & (kESlots - 1)) * nE;
@@ -267,17 +308,6 @@ k_water_force(Dev D, const double *__restrict__ x, const double *__restrict__ px
 // registers across its chunks.  The per-type LJ tables live in shared memory.
 constexpr int kITile = 4;
 
-__device__ __forceinline__ int special_code(const Dev &D, int a, int b) {
-    // -1: ordinary pair; kPairExcluded(0): skip; 3: 1-4 pair
-    int lo = D.sp_off[a], hi = D.sp_off[a + 1];
-    while (lo < hi) {
-        const int m = (lo + hi) >> 1;
-        if (D.sp_partner[m] < b) lo = m + 1; else hi = m;
-    }
-    if (lo < D.sp_off[a + 1] && D.sp_partner[lo] == b) return (int)D.sp_code[lo];
-    return -1;
-}
-
 struct SoluteTile {
     int g, nt;
     int ai[kITile], cti[kITile];
@@ -287,12 +317,16 @@ struct SoluteTile {
     float grad[kITile][3];
 };
 
+#ifndef QNB_SOLUTE_MINB
+#define QNB_SOLUTE_MINB 2
+#endif
 template <bool PBC, bool GEOM>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, QNB_SOLUTE_MINB)
 k_solute_force(Dev D, const double *__restrict__ x, const double *__restrict__ px, const double *__restrict__ py,
                const double *__restrict__ pz, const float *__restrict__ pk_q, const double *__restrict__ pk_qd,
-               const int *__restrict__ pk_ct, const int *__restrict__ pk_atom, int nchunk, const int2 *__restrict__ cdesc,
-               const uint32_t *__restrict__ crow, double *__restrict__ grad, double *__restrict__ Eslots, int nE) {
+               const int *__restrict__ pk_ct, const int *__restrict__ pk_atom, const int *__restrict__ wstart,
+               const int2 *__restrict__ cdesc, const uint32_t *__restrict__ crow, const uint16_t *__restrict__ cspec, double *__restrict__ grad,
+               double *__restrict__ Eslots, int nE) {
     extern __shared__ unsigned char smem_raw[];
     // shared LJ tables: ljd [nct*6] doubles, ljf [nct*6] floats, ljcode [nct*nct] bytes
     double *s_ljd = reinterpret_cast<double *>(smem_raw);
@@ -300,47 +334,53 @@ k_solute_force(Dev D, const double *__restrict__ x, const double *__restrict__ p
     unsigned char *s_code = reinterpret_cast<unsigned char *>(s_ljf + D.nct * 6);
     for (int k = threadIdx.x; k < D.nct * 6; k += blockDim.x) { s_ljd[k] = D.ljd[k]; s_ljf[k] = D.ljf[k]; }
     for (int k = threadIdx.x; k < D.nct * D.nct; k += blockDim.x) s_code[k] = D.ljcode[k];
+#ifdef QNB_TRACE
+    const unsigned long long tr0 = gtime();
+#endif
     __syncthreads();
 
     const int lane = threadIdx.x & 31;
-    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
-    const int per = (nchunk + nwarp - 1) / nwarp;
-    const int c0 = gw * per, c1 = min(nchunk, c0 + per);
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int c0 = wstart[gw], c1 = wstart[gw + 1];
+#ifdef QNB_TRACE
+    QTRACE(1, gw, 5, tr0);
+#endif
+    QTRACE(1, gw, 0, gtime()); QTRACE(1, gw, 1, (unsigned long long)clock64()); QTRACE(1, gw, 4, (unsigned long long)(c1 > c0 ? c1 - c0 : 0));
     if (c0 >= c1) return;
     SoluteTile T;
     T.g = -1; T.nt = 0;
     int cur_key = -1;
     double e_pp_el = 0.0, e_pw_el = 0.0, e_pp_vdw = 0.0, e_pw_vdw = 0.0;
 
+    const int slot = split_slot<3 * kITile, 16>(lane);   // gradient component (3*tile atom + axis) this lane flushes
     auto flush = [&]() {
         if (cur_key < 0) return;
+        float s[3 * kITile];
 #pragma unroll
-        for (int t = 0; t < kITile; t++) {
-            double sx = warp_sum((double)T.grad[t][0]), sy = warp_sum((double)T.grad[t][1]), sz = warp_sum((double)T.grad[t][2]);
-            if (t < T.nt && lane < 3) atomicAdd(&grad[3 * T.ai[t] + lane], lane == 0 ? sx : lane == 1 ? sy : sz);
-        }
+        for (int k = 0; k < 3 * kITile; k++) s[k] = T.grad[k / 3][k % 3];
+        const float mine = split_reduce<3 * kITile, 16>(s, lane);
+        const int t = slot / 3;
+        int a = T.ai[0];
+#pragma unroll
+        for (int k = 1; k < kITile; k++) a = (t == k) ? T.ai[k] : a;
+        if (slot >= 0 && t < T.nt) atomicAdd(&grad[3 * a + (slot - 3 * t)], (double)mine);
     };
     auto load_tile = [&](int g, int tile) {
         T.g = g;
-        const int gf = D.g_first[g], gn = D.g_n[g];
         const int sw = D.g_switch[g];
         T.o[0] = x[3 * sw]; T.o[1] = x[3 * sw + 1]; T.o[2] = x[3 * sw + 2];   // row origin = switch atom
-        int k = 0, seen = 0;
-        // skip the non-Q atoms of earlier tiles
-        while (k < gn && seen < tile * kITile) { if (!D.is_q[D.g_atoms[gf + k]]) seen++; k++; }
-        T.nt = 0;
+        const int k0 = D.nq_off[g] + tile * kITile;
+        T.nt = min(kITile, D.nq_off[g + 1] - k0);
 #pragma unroll
         for (int t = 0; t < kITile; t++) {
             T.ai[t] = -1; T.cti[t] = 0; T.qf[t] = 0.f; T.qd[t] = 0.0;
 #pragma unroll
             for (int c = 0; c < 3; c++) { T.sf[t][c] = 0.f; T.sd[t][c] = 0.0; T.grad[t][c] = 0.f; }
-            while (k < gn && D.is_q[D.g_atoms[gf + k]]) k++;
-            if (k < gn) {
-                const int a = D.g_atoms[gf + k++];
+            if (t < T.nt) {
+                const int a = D.nq_atoms[k0 + t];
                 T.ai[t] = a; T.cti[t] = D.ctype[a]; T.qd[t] = D.crg[a]; T.qf[t] = (float)T.qd[t];
 #pragma unroll
                 for (int c = 0; c < 3; c++) { T.sd[t][c] = x[3 * a + c] - T.o[c]; T.sf[t][c] = (float)T.sd[t][c]; }
-                T.nt = t + 1;
             }
         }
     };
@@ -356,129 +396,142 @@ k_solute_force(Dev D, const double *__restrict__ x, const double *__restrict__ p
         if (GEOM) { A = ax * bx; B = ay * by; }
         else { double t = ax + bx; t = t * t; t = t * t * t; const double e = ay * by; A = t * t * e; B = 2.0 * t * e; }
     };
-    // pipeline stages
-    auto load_a = [&](int c, int2 &d, uint32_t &e) { d = cdesc[c]; e = crow[(size_t)c * 32 + lane]; };
-    auto load_b = [&](const int2 &d, uint32_t e, double (&pj)[9], float &qb, double &qbd, int &ctb) {
-        if (e == kPadEntry) return;
-        const int p = (int)(e & kIdMask);
-        if ((d.y & 0xff) == kChunkB) {
-#pragma unroll
-            for (int b = 0; b < 3; b++) { pj[b] = px[p + b]; pj[3 + b] = py[p + b]; pj[6 + b] = pz[p + b]; }
-        } else {
-            pj[0] = px[p]; pj[3] = py[p]; pj[6] = pz[p];
-            qb = pk_q[p]; qbd = pk_qd[p]; ctb = pk_ct[p];
-        }
+    // pipeline stages (branch-free loads, see k_water_force)
+    auto load_a = [&](int c, int2 &d, uint32_t &e) {
+        d = cdesc[c];
+        e = crow[(size_t)c * 32 + lane];
+        d.y |= (int)cspec[(size_t)c * 32 + lane] << 16;   // per-lane special-pair codes ride in the descriptor's upper half
     };
-    int2 d0, d1 = make_int2(-1, 0), d2 = make_int2(-1, 0);
-    uint32_t e0, e1 = kPadEntry, e2 = kPadEntry;
-    double p0[9], p1[9], qd0 = 0, qd1 = 0;
-    float q0 = 0.f, q1 = 0.f;
-    int ct0 = 0, ct1 = 0;
+    auto load_b = [&](uint32_t e, double (&pj)[9], float &qb, double &qbd, int &ctb) {
+        const int p = (e == kPadEntry) ? 0 : (int)(e & kIdMask);
 #pragma unroll
-    for (int k = 0; k < 9; k++) { p0[k] = 0.0; p1[k] = 0.0; }
-    load_a(c0, d0, e0);
-    if (c0 + 1 < c1) load_a(c0 + 1, d1, e1);
-    load_b(d0, e0, p0, q0, qd0, ct0);
-    for (int c = c0; c < c1; c++) {
-        if (c + 2 < c1) load_a(c + 2, d2, e2);
-        if (c + 1 < c1) load_b(d1, e1, p1, q1, qd1, ct1);
-        const int key = d0.x * 256 + (d0.y >> 8);   // (group, tile)
-        if (key != cur_key) { flush(); load_tile(d0.x, d0.y >> 8); cur_key = key; }
-        const bool valid = e0 != kPadEntry;
-        if ((d0.y & 0xff) == kChunkA) {
+        for (int b = 0; b < 3; b++) { pj[b] = px[p + b]; pj[3 + b] = py[p + b]; pj[6 + b] = pz[p + b]; }
+        qb = pk_q[p]; qbd = pk_qd[p]; ctb = pk_ct[p];
+    };
+    // One chunk.  Straight-line over the tile atoms: atoms beyond T.nt, padding lanes and excluded pairs are computed
+    // and then dropped by a select, so that the tile's pairs (and afterwards their FP64 energies) form independent
+    // dependency chains the scheduler can interleave.
+    auto compute = [&](const int2 &d, uint32_t e, const double (&pj)[9], float qb, double qbd, int ctb) {
+        const int tile = (d.y >> 8) & 0xff;
+        const int key = d.x * 256 + tile;   // (group, tile)
+        if (key != cur_key) { flush(); load_tile(d.x, tile); cur_key = key; }
+        const bool valid = e != kPadEntry;
+        if ((d.y & 0xff) == kChunkA) {
             // ---- solute-solute partner atom
-            if (valid) {
-                const int pb = (int)(e0 & kIdMask);
-                const bool own = (e0 & kOwnerBit) != 0, special = (e0 & kSpecialBit) != 0;
-                double ux = p0[0] - T.o[0], uy = p0[3] - T.o[1], uz = p0[6] - T.o[2];
-                int b = -1, gb = -1;       // atom id / group of the partner: only the special and periodic paths need them
-                if (special || PBC) { b = pk_atom[pb]; gb = D.grp_of_atom[b]; }
-                if (PBC) {
-                    if (D.any_atom) {
-                        ux += D.box[0] * img_comp(e0, 0); uy += D.box[1] * img_comp(e0, 1); uz += D.box[2] * img_comp(e0, 2);
-                    } else {
-                        // nonbond_pp_box L4791-4801: shift = boxlength*nint((x(sw_i)-x(sw_j))*inv_boxl)
-                        const int swb = D.g_switch[gb];
-                        ux += pshift(T.o[0] - x[3 * swb], D.box[0], D.inv_box[0]);
-                        uy += pshift(T.o[1] - x[3 * swb + 1], D.box[1], D.inv_box[1]);
-                        uz += pshift(T.o[2] - x[3 * swb + 2], D.box[2], D.inv_box[2]);
-                    }
-                }
-                const float ufx = (float)ux, ufy = (float)uy, ufz = (float)uz;
-                const bool same = special && gb == T.g;   // own-group partners are always flagged special
-#pragma unroll
-                for (int t = 0; t < kITile; t++) {
-                    if (t < T.nt) {
-                        const int a = T.ai[t];
-                        int code = s_code[T.cti[t] * D.nct + ct0];
-                        bool skip = false, i14 = false;
-                        if (special) {
-                            if (a == b) skip = true;
-                            else {
-                                const int sc = special_code(D, a, b);
-                                if (sc == 0) skip = true;
-                                else if (sc == 3) { code = 3; i14 = true; }
-                            }
-                        }
-                        if (!skip) {
-                            float A, B, rinv, ev = 0.f;
-                            lj32(T.cti[t], ct0, code, A, B);
-                            const float qq = i14 ? T.qf[t] * q0 * D.el14f : T.qf[t] * q0;
-                            const float dx = ufx - T.sf[t][0], dy = ufy - T.sf[t][1], dz = ufz - T.sf[t][2];
-                            const float dv = pair_f32<true, false>(dx, dy, dz, qq, A, B, rinv, ev);
-                            T.grad[t][0] = fmaf(-dx, dv, T.grad[t][0]); T.grad[t][1] = fmaf(-dy, dv, T.grad[t][1]);
-                            T.grad[t][2] = fmaf(-dz, dv, T.grad[t][2]);
-                            // energy once per pair: on the owner side; inside one group on the lower atom (i<j, L1874)
-                            if (own && (!same || a < b)) {
-                                const double qqd = i14 ? T.qd[t] * qd0 * D.el14 : T.qd[t] * qd0;
-                                double Ad, Bd;
-                                lj64(T.cti[t], ct0, code, Ad, Bd);
-                                energy_f64(ux - T.sd[t][0], uy - T.sd[t][1], uz - T.sd[t][2], qqd, Ad, Bd, rinv, e_pp_el, e_pp_vdw);
-                            }
-                        }
-                    }
+            const int pb = (int)(e & kIdMask);
+            const bool own = valid && (e & kOwnerBit) != 0;
+            double ux = pj[0] - T.o[0], uy = pj[3] - T.o[1], uz = pj[6] - T.o[2];
+            if (PBC) {
+                if (D.any_atom) {
+                    ux += D.box[0] * img_comp(e, 0); uy += D.box[1] * img_comp(e, 1); uz += D.box[2] * img_comp(e, 2);
+                } else if (valid) {
+                    // nonbond_pp_box L4791-4801: shift = boxlength*nint((x(sw_i)-x(sw_j))*inv_boxl)
+                    const int swb = D.g_switch[D.grp_of_atom[pk_atom[pb]]];
+                    ux += pshift(T.o[0] - x[3 * swb], D.box[0], D.inv_box[0]);
+                    uy += pshift(T.o[1] - x[3 * swb + 1], D.box[1], D.inv_box[1]);
+                    uz += pshift(T.o[2] - x[3 * swb + 2], D.box[2], D.inv_box[2]);
                 }
             }
-        } else if (valid) {
+            const float ufx = (float)ux, ufy = (float)uy, ufz = (float)uz;
+            // special pairs (exclusions, 1-4 neighbours, own group) were resolved per tile atom when the chunks were
+            // laid out (k_chunk_fill): 3 bits per tile atom = skip | 1-4 | energy on the other side
+            const unsigned spec = (unsigned)d.y >> 16;
+            int code[kITile];
+            bool keep[kITile], lower[kITile], i14[kITile];   // evaluated at all; energy side inside one group (i<j, L1874)
+#pragma unroll
+            for (int t = 0; t < kITile; t++) {
+                const unsigned sb = (spec >> (3 * t)) & 7u;
+                i14[t] = (sb & 2u) != 0;
+                code[t] = i14[t] ? 3 : s_code[T.cti[t] * D.nct + ctb];
+                keep[t] = valid && t < T.nt && !(sb & 1u);
+                lower[t] = !(sb & 4u);
+            }
+            float seed[kITile];
+#pragma unroll
+            for (int t = 0; t < kITile; t++) {
+                float A, B, ev = 0.f;
+                lj32(T.cti[t], ctb, code[t], A, B);
+                const float qq = i14[t] ? T.qf[t] * qb * D.el14f : T.qf[t] * qb;
+                const float dx = ufx - T.sf[t][0], dy = ufy - T.sf[t][1], dz = ufz - T.sf[t][2];
+                float dv = pair_f32<true, false>(dx, dy, dz, qq, A, B, seed[t], ev);
+                dv = keep[t] ? dv : 0.f;
+                T.grad[t][0] = fmaf(-dx, dv, T.grad[t][0]); T.grad[t][1] = fmaf(-dy, dv, T.grad[t][1]);
+                T.grad[t][2] = fmaf(-dz, dv, T.grad[t][2]);
+            }
+            // energy once per pair: on the owner side
+            if (__any_sync(kFull, own)) {
+#pragma unroll
+                for (int t = 0; t < kITile; t++) {
+                    const double qqd = i14[t] ? T.qd[t] * qbd * D.el14 : T.qd[t] * qbd;
+                    double Ad, Bd, tel, tvdw;
+                    lj64(T.cti[t], ctb, code[t], Ad, Bd);
+                    energy_terms_f64(ux - T.sd[t][0], uy - T.sd[t][1], uz - T.sd[t][2], qqd, Ad, Bd, seed[t], tel, tvdw);
+                    const bool add = own && keep[t] && lower[t];
+                    e_pp_el += add ? tel : 0.0; e_pp_vdw += add ? tvdw : 0.0;
+                }
+            }
+        } else {
             // ---- solute-water: this side owns the pair, all three water atoms with full LJ (nbe)
             double shx = 0, shy = 0, shz = 0;
             if (PBC) {
                 if (D.any_atom) {
-                    shx = D.box[0] * img_comp(e0, 0); shy = D.box[1] * img_comp(e0, 1); shz = D.box[2] * img_comp(e0, 2);
+                    shx = D.box[0] * img_comp(e, 0); shy = D.box[1] * img_comp(e, 1); shz = D.box[2] * img_comp(e, 2);
                 } else {
-                    shx = pshift(T.o[0] - p0[0], D.box[0], D.inv_box[0]);
-                    shy = pshift(T.o[1] - p0[3], D.box[1], D.inv_box[1]);
-                    shz = pshift(T.o[2] - p0[6], D.box[2], D.inv_box[2]);
+                    shx = pshift(T.o[0] - pj[0], D.box[0], D.inv_box[0]);
+                    shy = pshift(T.o[1] - pj[3], D.box[1], D.inv_box[1]);
+                    shz = pshift(T.o[2] - pj[6], D.box[2], D.inv_box[2]);
                 }
             }
 #pragma unroll
-            for (int s = 0; s < 3; s++) {
-                const double ux = (p0[s] - T.o[0]) + shx, uy = (p0[3 + s] - T.o[1]) + shy, uz = (p0[6 + s] - T.o[2]) + shz;
+            for (int sw = 0; sw < 3; sw++) {
+                const double ux = (pj[sw] - T.o[0]) + shx, uy = (pj[3 + sw] - T.o[1]) + shy, uz = (pj[6 + sw] - T.o[2]) + shz;
                 const float ufx = (float)ux, ufy = (float)uy, ufz = (float)uz;
-                const int ctb = D.wct[s];
+                const int ctw = D.wct[sw];
+                float seed[kITile];
+                int code[kITile];
 #pragma unroll
                 for (int t = 0; t < kITile; t++) {
-                    if (t < T.nt) {
-                        const int code = s_code[T.cti[t] * D.nct + ctb];
-                        float A, B, rinv, ev = 0.f;
-                        lj32(T.cti[t], ctb, code, A, B);
-                        const float dx = ufx - T.sf[t][0], dy = ufy - T.sf[t][1], dz = ufz - T.sf[t][2];
-                        const float dv = pair_f32<true, false>(dx, dy, dz, T.qf[t] * D.wq[s], A, B, rinv, ev);
-                        T.grad[t][0] = fmaf(-dx, dv, T.grad[t][0]); T.grad[t][1] = fmaf(-dy, dv, T.grad[t][1]);
-                        T.grad[t][2] = fmaf(-dz, dv, T.grad[t][2]);
-                        double Ad, Bd;
-                        lj64(T.cti[t], ctb, code, Ad, Bd);
-                        energy_f64(ux - T.sd[t][0], uy - T.sd[t][1], uz - T.sd[t][2], T.qd[t] * D.wqd[s], Ad, Bd, rinv, e_pw_el, e_pw_vdw);
-                    }
+                    code[t] = s_code[T.cti[t] * D.nct + ctw];
+                    float A, B, ev = 0.f;
+                    lj32(T.cti[t], ctw, code[t], A, B);
+                    const float dx = ufx - T.sf[t][0], dy = ufy - T.sf[t][1], dz = ufz - T.sf[t][2];
+                    float dv = pair_f32<true, false>(dx, dy, dz, T.qf[t] * D.wq[sw], A, B, seed[t], ev);
+                    dv = (valid && t < T.nt) ? dv : 0.f;
+                    T.grad[t][0] = fmaf(-dx, dv, T.grad[t][0]); T.grad[t][1] = fmaf(-dy, dv, T.grad[t][1]);
+                    T.grad[t][2] = fmaf(-dz, dv, T.grad[t][2]);
+                }
+#pragma unroll
+                for (int t = 0; t < kITile; t++) {
+                    double Ad, Bd, tel, tvdw;
+                    lj64(T.cti[t], ctw, code[t], Ad, Bd);
+                    energy_terms_f64(ux - T.sd[t][0], uy - T.sd[t][1], uz - T.sd[t][2], T.qd[t] * D.wqd[sw], Ad, Bd, seed[t], tel, tvdw);
+                    const bool add = valid && t < T.nt;
+                    e_pw_el += add ? tel : 0.0; e_pw_vdw += add ? tvdw : 0.0;
                 }
             }
         }
-        d0 = d1; e0 = e1; q0 = q1; qd0 = qd1; ct0 = ct1;
-#pragma unroll
-        for (int k = 0; k < 9; k++) p0[k] = p1[k];
-        d1 = d2; e1 = e2;
+    };
+    int2 d0, d1, d2;
+    uint32_t e0, e1, e2;
+    double P[9], R[9], qdP, qdR;
+    float qP, qR;
+    int ctP, ctR;
+    const int clast = c1 - 1;
+    load_a(c0, d0, e0);
+    load_a(min(c0 + 1, clast), d1, e1);
+    load_b(e0, P, qP, qdP, ctP);
+    for (int c = c0; c < c1; c += 2) {
+        load_a(min(c + 2, clast), d2, e2);
+        load_b(e1, R, qR, qdR, ctR);
+        compute(d0, e0, P, qP, qdP, ctP);
+        if (c + 1 >= c1) break;
+        load_a(min(c + 3, clast), d0, e0);
+        load_b(e2, P, qP, qdP, ctP);
+        compute(d1, e1, R, qR, qdR, ctR);
+        d1 = d0; e1 = e0; d0 = d2; e0 = e2;
     }
     flush();
+    QTRACE(1, gw, 2, (unsigned long long)clock64()); QTRACE(1, gw, 3, gtime());
     const double s1 = warp_sum(e_pp_el), s2 = warp_sum(e_pp_vdw), s3 = warp_sum(e_pw_el), s4 = warp_sum(e_pw_vdw);
     if (lane == 0) {
         double *E = Eslots + (size_t)(gw & (kESlots - 1)) * nE;
@@ -540,47 +593,61 @@ __device__ __forceinline__ void q_shift(const Dev &D, const double *__restrict__
 }
 
 // Gradient on the PARTNER atoms (nonbond_qp/_box, nonbond_qw(_spc)/_box seen from atom j): one thread per
-// partner site, all Q-atoms looped from shared memory.
+// partner site, all Q-atoms looped from shared memory.  No energies leave this kernel, so it follows the rule of
+// the other gradient paths: FP64 only to form coordinates relative to a local origin (the Q switch atom; periodic
+// shift folded in), FP32 pair arithmetic with FP32 parameter tables.
 template <bool PBC>
 __global__ void __launch_bounds__(128)
 k_q_partner(Dev D, const double *__restrict__ x, const double *__restrict__ lambda, int nqp,
             const int *__restrict__ qp_list, const int *__restrict__ qp_shift_atom, int nqw,
             const int *__restrict__ qw_list, double *__restrict__ grad) {
-    extern __shared__ double sh[];
-    double *xq = sh;                 // [nqat][3]
-    double *lam = sh + 3 * D.nqat;   // [nstates]
+    extern __shared__ float shq[];
+    float *xq = shq;                 // [nqat][3] relative to the origin
+    float *lam = shq + 3 * D.nqat;   // [nstates]
+    const int org = D.iqseq[0];
+    const double ox = x[3 * org], oy = x[3 * org + 1], oz = x[3 * org + 2];
     for (int k = threadIdx.x; k < D.nqat; k += blockDim.x) {
         const int a = D.iqseq[k];
-        xq[3 * k] = x[3 * a]; xq[3 * k + 1] = x[3 * a + 1]; xq[3 * k + 2] = x[3 * a + 2];
+        xq[3 * k] = (float)(x[3 * a] - ox); xq[3 * k + 1] = (float)(x[3 * a + 1] - oy); xq[3 * k + 2] = (float)(x[3 * a + 2] - oz);
     }
-    for (int k = threadIdx.x; k < D.nstates; k += blockDim.x) lam[k] = lambda[k];
+    for (int k = threadIdx.x; k < D.nstates; k += blockDim.x) lam[k] = (float)lambda[k];
     __syncthreads();
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= nqp + 3 * nqw) return;
     const int nst = D.nstates;
     const QSite s = q_site(D, p, nqp, qp_list, qw_list);
-    const double jx = x[3 * s.atom], jy = x[3 * s.atom + 1], jz = x[3 * s.atom + 2];
     double shf[3];
     q_shift<PBC>(D, x, s, qp_shift_atom, shf);
+    // vec = shift - (x(i) - x(j)) = (x(j) + shift - origin) - (x(i) - origin)
+    const float jx = (float)((x[3 * s.atom] - ox) + shf[0]), jy = (float)((x[3 * s.atom + 1] - oy) + shf[1]),
+                jz = (float)((x[3 * s.atom + 2] - oz) + shf[2]);
     const bool coul_only = s.water && D.spc_water && s.site > 0;   // nbe_qspc
-    double gx = 0, gy = 0, gz = 0;
+    float gx = 0.f, gy = 0.f, gz = 0.f;
     // the Q-atoms are dealt to gridDim.y blocks so that the few thousand partner sites still fill the machine
     const int qchunk = (D.nqat + gridDim.y - 1) / gridDim.y;
     const int q0 = blockIdx.y * qchunk, q1 = min(D.nqat, q0 + qchunk);
 #pragma unroll 2
     for (int q = q0; q < q1; q++) {
-        const double vx = shf[0] - (xq[3 * q] - jx), vy = shf[1] - (xq[3 * q + 1] - jy), vz = shf[2] - (xq[3 * q + 2] - jz);
-        const double r2 = vx * vx + vy * vy + vz * vz, rinv = rinv_f64(r2);
-        double dv = 0;
+        const float vx = jx - xq[3 * q], vy = jy - xq[3 * q + 1], vz = jz - xq[3 * q + 2];
+        const float r2 = fmaf(vx, vx, fmaf(vy, vy, vz * vz)), rinv = rsqrt_fast(r2), r2inv = rinv * rinv;
+        const float r6_hc = r2 * r2 * r2;
+        float dv = 0.f;
         for (int st = 0; st < nst; st++) {
-            const QPar4 pr = s.water ? D.qw_tab[(size_t)(q * nst + st) * 3 + s.site]
-                                     : D.qp_tab[(size_t)(q * nst + st) * D.nat_solute + s.atom];
-            if (coul_only) dv += -(rinv * rinv) * (pr.el * rinv) * lam[st];
-            else dv += qx_eval(r2, rinv, pr, lam[st]).dv;
+            const float4 pr = s.water ? D.qw_tabf[(size_t)(q * nst + st) * 3 + s.site]
+                                      : D.qp_tabf[(size_t)(q * nst + st) * D.nat_solute + s.atom];   // A B el score
+            const float vel = pr.z * rinv;
+            float t = -vel;
+            if (!coul_only) {
+                // nbe_qx (nonbonded.f90:200-222): softcore 1/(r^6 + alpha)
+                const float r6s = __fdividef(1.0f, r6_hc + pr.w);
+                const float va = pr.x * r6s * r6s, vb = pr.y * r6s;
+                t -= (12.0f * va - 6.0f * vb) * r6s * r6_hc;
+            }
+            dv = fmaf(r2inv * t, lam[st], dv);
         }
-        gx += vx * dv; gy += vy * dv; gz += vz * dv;   // d(j) += vec*dv
+        gx = fmaf(vx, dv, gx); gy = fmaf(vy, dv, gy); gz = fmaf(vz, dv, gz);   // d(j) += vec*dv
     }
-    atomicAdd(&grad[3 * s.atom], gx); atomicAdd(&grad[3 * s.atom + 1], gy); atomicAdd(&grad[3 * s.atom + 2], gz);
+    atomicAdd(&grad[3 * s.atom], (double)gx); atomicAdd(&grad[3 * s.atom + 1], (double)gy); atomicAdd(&grad[3 * s.atom + 2], (double)gz);
 }
 
 // Gradient on the Q-atoms and the per-state energies EQ(:)%qp, EQ(:)%qw.  Block (q, slice): the partner sites

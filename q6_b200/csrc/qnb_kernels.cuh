@@ -73,6 +73,7 @@ struct Dev {
     const int *sp_off, *sp_partner;
     const uint8_t *sp_code;
     const int *gs_off, *gs_atoms;
+    const int *nq_off, *nq_atoms;   // non-Q atoms per solute group
     // water sites
     float wq[3];                // site charges
     double wqd[3];
@@ -84,6 +85,7 @@ struct Dev {
     const int *iqseq;           // [nqat]
     const QPar4 *qp_tab;        // [(iq*nstates+s)][nat_solute]
     const QPar4 *qw_tab;        // [(iq*nstates+s)][3]
+    const float4 *qp_tabf, *qw_tabf;   // same as (A, B, el, score) in FP32: partner-side gradients
 };
 
 struct Cut {
@@ -104,6 +106,46 @@ __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
     return v;
+}
+// Sum N per-lane values over the warp with N + O(log N) shuffles instead of 5 N: at every butterfly level the two
+// partner lanes split the remaining values, each keeps one half and hands the other over.  After the levels with
+// masks 16..2 a lane holds ONE value; split_slot() tells which (or -1).  FP32: the inputs are FP32 partial sums.
+template <int N, int MASK>
+__device__ __forceinline__ float split_reduce(const float (&v)[N], int lane) {
+    if constexpr (N == 1) {
+        float s = v[0];
+#pragma unroll
+        for (int o = MASK; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
+        return s;
+    } else {
+        static_assert(MASK >= 2, "split_reduce: at most 16 values");
+        constexpr int H = (N + 1) / 2;
+        const bool up = (lane & MASK) != 0;
+        float w[H];
+#pragma unroll
+        for (int i = 0; i < H; i++) {
+            const float hi = (H + i < N) ? v[H + i] : 0.f;
+            const float send = up ? v[i] : hi, keep = up ? hi : v[i];
+            w[i] = keep + __shfl_xor_sync(kFull, send, MASK);
+        }
+        return split_reduce<H, MASK / 2>(w, lane);
+    }
+}
+// index of the value split_reduce<N,16> leaves in this lane, -1 for lanes that hold a duplicate or a padding slot
+template <int N, int MASK>
+__device__ __forceinline__ int split_slot(int lane, int base = 0, int count = N) {
+    if constexpr (N == 1) return (count >= 1 && (lane & (2 * MASK - 1)) == 0) ? base : -1;
+    else {
+        constexpr int H = (N + 1) / 2;
+        const bool up = (lane & MASK) != 0;
+        return split_slot<H, MASK / 2>(lane, up ? base + H : base, up ? count - H : min(count, H));
+    }
+}
+// MUFU.RSQ alone (rsqrtf() wraps it in denormal scaling: three more instructions per pair)
+__device__ __forceinline__ float rsqrt_fast(float v) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
 }
 __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
 #pragma unroll
@@ -130,7 +172,19 @@ __device__ __forceinline__ double rsqrt_refine(double r2, float seed) {
     return fma(y, t, y);
 }
 
-__device__ __forceinline__ double rinv_f64(double r2) { return rsqrt_refine(r2, rsqrtf((float)r2)); }
+__device__ __forceinline__ double rinv_f64(double r2) { return rsqrt_refine(r2, rsqrt_fast((float)r2)); }
+
+__device__ __forceinline__ int special_code(const Dev &D, int a, int b) {
+    // -1: ordinary pair; kPairExcluded(0): skip; 3: 1-4 pair
+    int lo = D.sp_off[a], hi = D.sp_off[a + 1];
+    while (lo < hi) {
+        const int m = (lo + hi) >> 1;
+        if (D.sp_partner[m] < b) lo = m + 1; else hi = m;
+    }
+    if (lo < D.sp_off[a + 1] && D.sp_partner[lo] == b) return (int)D.sp_code[lo];
+    return -1;
+}
+
 
 // class of a unit pair and the reference's owner side.  Units: [0,ns) solute groups, then waters.
 // returns class 0 pp, 1 pw, 2 ww; owner_is_u: the reference lists the pair while looping i = u.

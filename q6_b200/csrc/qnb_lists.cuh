@@ -296,16 +296,62 @@ k_build_rows(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x, con
 __device__ __forceinline__ int unit_tiles(const Dev &D, int u, int tile_atoms) {
     return tile_atoms == 0 ? 1 : (D.g_nq[u] + tile_atoms - 1) / tile_atoms;
 }
-__global__ void k_chunk_count(Dev D, int u0, int n, int tile_atoms, const int *__restrict__ counts, int *__restrict__ nch) {
+// Relative cost of a chunk for the static work split of the persistent force kernels (instruction-count estimates,
+// checked against per-warp timelines: tools/exp_trace.py): own = carries FP64 energies, mir = forces only,
+// b = the other unit kind.  [0] water rows, [1] solute rows.
+struct ChunkCost { int own, mir, b; };
+__device__ __forceinline__ ChunkCost chunk_cost(int tile_atoms) {
+    return tile_atoms == 0 ? ChunkCost{50, 30, 14} : ChunkCost{38, 24, 96};
+}
+// chunk counts of one unit's tile: own-carrying A chunks, mirror-only A chunks, B chunks (own entries come first)
+__device__ __forceinline__ void unit_chunks(const int *__restrict__ counts, int u, int &n_own, int &n_mir, int &n_b) {
+    const int own = counts[3 * u], na = own + counts[3 * u + 1];
+    n_own = (own + 31) / 32;
+    n_mir = (na + 31) / 32 - n_own;
+    n_b = (counts[3 * u + 2] + 31) / 32;
+}
+__global__ void k_chunk_count(Dev D, int u0, int n, int tile_atoms, const int *__restrict__ counts, int *__restrict__ nch,
+                              int *__restrict__ ucost) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const int u = u0 + k;
-    nch[k] = unit_tiles(D, u, tile_atoms) * ((counts[3 * u] + counts[3 * u + 1] + 31) / 32 + (counts[3 * u + 2] + 31) / 32);
+    int n_own, n_mir, n_b;
+    unit_chunks(counts, u, n_own, n_mir, n_b);
+    const ChunkCost w = chunk_cost(tile_atoms);
+    const int tiles = unit_tiles(D, u, tile_atoms);
+    nch[k] = tiles * (n_own + n_mir + n_b);
+    ucost[k] = tiles * (n_own * w.own + n_mir * w.mir + n_b * w.b);
+}
+// first chunk of every warp of a persistent force kernel: equal shares of the summed chunk costs.
+// wstart[w] = smallest chunk c whose cost prefix reaches w*total/nwarp; wstart[nwarp] = number of chunks.
+__global__ void k_warp_starts(Dev D, int u0, int n, int tile_atoms, const int *__restrict__ counts,
+                              const int *__restrict__ choff, const int *__restrict__ cost_off, int nwarp,
+                              int *__restrict__ wstart) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w > nwarp) return;
+    if (w == nwarp) { wstart[w] = choff[n]; return; }
+    const long long total = cost_off[n];
+    const int target = (int)((total * w) / nwarp);
+    int lo = 0, hi = n;   // last unit k with cost_off[k] <= target
+    while (hi - lo > 1) { const int m = (lo + hi) >> 1; if (cost_off[m] <= target) lo = m; else hi = m; }
+    const int k = lo, u = u0 + k;
+    int n_own, n_mir, n_b;
+    unit_chunks(counts, u, n_own, n_mir, n_b);
+    const ChunkCost cw = chunk_cost(tile_atoms);
+    const int tiles = unit_tiles(D, u, tile_atoms);
+    int c = choff[k], acc = cost_off[k];
+    for (int tile = 0; tile < tiles && acc < target; tile++)
+        for (int seg = 0; seg < 3 && acc < target; seg++) {
+            const int m = seg == 0 ? n_own : seg == 1 ? n_mir : n_b, cst = seg == 0 ? cw.own : seg == 1 ? cw.mir : cw.b;
+            for (int j = 0; j < m && acc < target; j++) { acc += cst; c++; }
+        }
+    wstart[w] = min(c, choff[n]);
 }
 // one warp per unit: copy the segments into 32-entry chunks padded with 0xffffffff; descriptor = {unit - u0, kind | tile << 8}
 __global__ void k_chunk_fill(Dev D, int u0, int n, int tile_atoms, const int *__restrict__ counts,
                              const int *__restrict__ row_off, const uint32_t *__restrict__ rows,
-                             const int *__restrict__ choff, int2 *__restrict__ cdesc, uint32_t *__restrict__ crow) {
+                             const int *__restrict__ choff, int2 *__restrict__ cdesc, uint32_t *__restrict__ crow,
+                             const int *__restrict__ pk_atom, uint16_t *__restrict__ cspec) {
     const int lane = threadIdx.x & 31;
     const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (k >= n) return;
@@ -319,7 +365,31 @@ __global__ void k_chunk_fill(Dev D, int u0, int n, int tile_atoms, const int *__
             const int m = seg == 0 ? na : nb;
             for (int b = 0; b < m; b += 32, c++) {
                 if (lane == 0) cdesc[c] = make_int2(k, seg | (tile << 8));
-                crow[(size_t)c * 32 + lane] = (b + lane < m) ? rows[base + b + lane] : 0xffffffffu;
+                const uint32_t e = (b + lane < m) ? rows[base + b + lane] : 0xffffffffu;
+                crow[(size_t)c * 32 + lane] = e;
+                if (cspec) {
+                    // solute tiles: resolve the special pairs (exclusion lists, 1-4 neighbours, own group) of this
+                    // partner against every tile atom now, 3 bits each: 1 skip, 2 1-4 pair, 4 energy on the other side
+                    unsigned sp = 0;
+                    if (seg == 0 && e != 0xffffffffu && (e & kSpecialBit)) {
+                        const int bb = pk_atom[e & kIdMask];
+                        const bool same = D.grp_of_atom[bb] == u;
+                        const int k0 = D.nq_off[u] + tile * tile_atoms, nt = min(tile_atoms, D.nq_off[u + 1] - k0);
+                        for (int t = 0; t < nt; t++) {
+                            const int a = D.nq_atoms[k0 + t];
+                            unsigned bits = 0;
+                            if (a == bb) bits = 1;
+                            else {
+                                const int sc = special_code(D, a, bb);
+                                if (sc == 0) bits = 1;
+                                else if (sc == 3) bits = 2;
+                            }
+                            if (same && !(a < bb)) bits |= 4;
+                            sp |= bits << (3 * t);
+                        }
+                    }
+                    cspec[(size_t)c * 32 + lane] = (uint16_t)sp;
+                }
             }
             base += m;
         }
@@ -511,7 +581,7 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
             const double4 sa = src[k];
             const double dx = sa.x - ox, dy = sa.y - oy, dz = sa.z - oz;
             const double r2 = dx * dx + dy * dy + dz * dz;
-            const float rif = rsqrtf((float)r2);
+            const float rif = rsqrt_fast((float)r2);
             const double ri = rsqrt_refine(r2, rif), ri2 = ri * ri;
             const double f0 = sa.w * ri * ri2;      // field0 = q/r^3
             m[0] += sa.w * ri;                      // phi0 += field0*r2

@@ -58,6 +58,7 @@ struct HostTables {
     std::vector<uint8_t> sp_code;
     // per group: sorted atoms that are special to at least one atom of the group (incl. its own atoms)
     std::vector<int> gs_off, gs_atoms;
+    std::vector<int> nq_off, nq_atoms;   // non-Q atoms of every solute group, group order (tiles of the solute kernel)
     // --- water site parameters
     std::vector<double> w_crg;            // [solv_atom]
     std::vector<int> w_ctype;             // [solv_atom]
@@ -214,6 +215,13 @@ inline void HostTables::build_specials(const qnb_system *sys) {
         u.erase(std::unique(u.begin(), u.end()), u.end());
         gs_atoms.insert(gs_atoms.end(), u.begin(), u.end());
         gs_off[g + 1] = (int)gs_atoms.size();
+    }
+    nq_off.assign(s.ncgp_solute + 1, 0);
+    nq_atoms.clear();
+    for (int g = 0; g < s.ncgp_solute; g++) {
+        for (int k = 0; k < g_n[g]; k++)
+            if (!is_q[g_atoms[g_first[g] + k]]) nq_atoms.push_back(g_atoms[g_first[g] + k]);
+        nq_off[g + 1] = (int)nq_atoms.size();
     }
 }
 

@@ -3,7 +3,7 @@ import sys, os, shutil
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from q6_b200 import synth, engine
-q, cuts, lam = synth.config("C2")
+q, cuts, lam = synth.config(os.environ.get("WL", "C2"))
 for v in sys.argv[1:]:
     lib = engine.load_library() if v == "MAIN" else engine.load_library(os.path.abspath(f"tools/exp/libqnb_{v}.so"))
     g = engine.Qnb(q, lib=lib)
