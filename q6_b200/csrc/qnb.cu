@@ -480,10 +480,17 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
             double ext = 0;
             for (int d = 0; d < 3; d++) ext = std::max(ext, G.n[d] / G.inv_cell[d]);
             const bool compact = !all && rl < 0.9 * ext;
-            if (compact) LAUNCH(h, k_lrf_accumulate<true>, nu, 32 * kRowWarps, 0, D, h->cut, G, h->lrf_reach,
-                   h->x.p, h->upos.p, h->cell_of.p, h->cell_start.p, h->item_pos.p, h->item_posf.p, h->src_off.p, h->src.p, h->lrf.p);
-            else LAUNCH(h, k_lrf_accumulate<false>, nu, 32 * kRowWarps, 0, D, h->cut, G, h->lrf_reach, h->x.p, h->upos.p,
-                   h->cell_of.p, h->cell_start.p, h->item_pos.p, h->item_posf.p, h->src_off.p, h->src.p, h->lrf.p);
+            // periodic image by cell row when 2(m+1) <= n in every dimension (then |delta| < box/2 for every scanned cell)
+            bool rowshift = G.periodic && !all;
+            const int rr[3] = {h->lrf_reach.x, h->lrf_reach.y, h->lrf_reach.z};
+            for (int d = 0; d < 3; d++) rowshift = rowshift && 2 * (rr[d] + 1) <= G.n[d];
+            const bool general = D.any_atom || D.sharded;
+#define LRFCASE(CP, RS, GN) LAUNCH(h, (k_lrf_accumulate<CP, RS, GN>), nu, 32 * kRowWarps, 0, D, h->cut, G, h->lrf_reach, h->x.p, h->upos.p, \
+                                   h->cell_of.p, h->cell_start.p, h->item_pos.p, h->item_posf.p, h->src_off.p, h->src.p, h->lrf.p)
+            if (rowshift) { if (general) LRFCASE(true, true, true); else LRFCASE(true, true, false); }
+            else if (compact) { if (general) LRFCASE(true, false, true); else LRFCASE(true, false, false); }
+            else { if (general) LRFCASE(false, false, true); else LRFCASE(false, false, false); }
+#undef LRFCASE
         }
         if (h->comm) {
             // lrf_gather (nonbondene.f90:616-623): sum the moments, keep cgp_cent (identical on every rank).

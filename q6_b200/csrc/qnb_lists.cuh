@@ -99,7 +99,10 @@ __global__ void k_pack_items(Dev D, const double *__restrict__ upos, const int *
     item_pos[idx] = make_double4(upos[3 * u], upos[3 * u + 1], upos[3 * u + 2], __longlong_as_double((long long)u));
     const int nq = D.u_excl[u] ? 0 : D.g_nq[D.u_grp[u]];
     // screening copy: FP32 position, unit id (-1 - u when the unit has no source atoms: excluded or all Q-atoms)
-    item_posf[idx] = make_float4((float)upos[3 * u], (float)upos[3 * u + 1], (float)upos[3 * u + 2], __int_as_float(nq > 0 ? u : -1 - u));
+    double w[3] = {upos[3 * u], upos[3 * u + 1], upos[3 * u + 2]};
+    if (D.use_PBC)
+        for (int d = 0; d < 3; d++) w[d] -= D.box[d] * floor(w[d] * D.inv_box[d]);   // as binned (cell_coord); screening is min-image
+    item_posf[idx] = make_float4((float)w[0], (float)w[1], (float)w[2], __int_as_float(nq > 0 ? u : -1 - u));
     item_nq[idx] = nq;
 }
 // Packed atoms: the non-Q atoms of every non-excluded unit, in cell order of the units.  Row entries are indices
@@ -531,7 +534,12 @@ __constant__ int kLrfExpand[40] = {0, 1, 2, 3,
 // (outside the class cut-off, inside RcLRF, pair owned by this shard).  20 unique moments are
 // accumulated (phi2 and phi3 are symmetric) and expanded on write.  FP64, no divisions:
 // field0 = q/r^3, field1 = 3 field0/r^2, field2 = -field1/r^2 from 1/r (rsqrt seed + Halley step).
-template <bool COMPACT>
+// Scan modes.  ROWSHIFT (periodic box, reach small enough that the image of a scanned cell row is known from its cell
+// offset, 2(m+1) <= n in every dimension): the periodic image is applied once per cell row to the TARGET, rows that
+// cannot reach the LRF shell are skipped and the x-range of the others is trimmed to the shell's chord, so the
+// per-candidate screening is nine FP32 instructions.  GENERAL adds what any-atom cut-offs and sharded builds need.
+struct LrfSeg { int lo, hi; float tx, ty, tz; };
+template <bool COMPACT, bool ROWSHIFT, bool GENERAL>
 __global__ void __launch_bounds__(32 * kRowWarps)
 k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x, const double *__restrict__ upos,
                  const int *__restrict__ cell_of, const int *__restrict__ cell_start,
@@ -551,7 +559,6 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
     double *lt = lrf + (size_t)QNB_LRF_STRIDE * gt;
     const double cx_ = lt[0], cy_ = lt[1], cz_ = lt[2];
     const double pt[3] = {upos[3 * t], upos[3 * t + 1], upos[3 * t + 2]};
-    const float ptf[3] = {(float)pt[0], (float)pt[1], (float)pt[2]};
     // any-atom mode: the deciding atoms sit up to rmax2/2 from either switch atom
     const float rl = sqrtf(fmaxf((float)C.rclrf2, 0.f)) + (D.any_atom ? (float)C.rmax2 : 0.f);
     const float hi_band = rl * rl * (1.0f + 1e-3f) + 0.05f;   // surely outside the LRF shell above this
@@ -617,8 +624,8 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
     const DimRange rz = dim_range(cz, reach.z, G.n[2], G.periodic), ry = dim_range(cy, reach.y, G.n[1], G.periodic);
     const XSeg xs = x_segments(cx, reach.x, G.n[0], G.periodic);
     // every cell is in reach (sphere with RcLRF spanning it, "no LRF cut-off" boxes): scan the item array as one row
-    const bool whole = rz.count == G.n[2] && ry.count == G.n[1] && xs.n == 1 && xs.lo[0] == 0 && xs.hi[0] == G.n[0];
-    const int nrow = whole ? 1 : rz.count * ry.count * xs.n;
+    const bool whole = !ROWSHIFT && rz.count == G.n[2] && ry.count == G.n[1] && xs.n == 1 && xs.lo[0] == 0 && xs.hi[0] == G.n[0];
+    const int nrow = whole ? 1 : rz.count * ry.count * (ROWSHIFT ? 2 : xs.n);
     // screening thresholds of this target against solute / water sources (FP32, see screen_r2)
     const bool t_sol = t < ns;
     const int cls_s = t_sol ? 0 : 1, cls_w = t_sol ? 1 : 2;     // class with a solute / a water source
@@ -630,48 +637,95 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
     const bool all_s = C.lrf_all_of(cls_s), all_w = C.lrf_all_of(cls_w);
     const float bx = (float)D.box[0], by = (float)D.box[1], bz = (float)D.box[2];
     const float ibx = (float)D.inv_box[0], iby = (float)D.inv_box[1], ibz = (float)D.inv_box[2];
-    __shared__ int2 seg[kLrfSegBatch];   // item ranges [lo,hi) of the cell rows, computed once per block
+    // target position as the candidates are stored: wrapped into the box when periodic (k_pack_items)
+    double ptw[3] = {pt[0], pt[1], pt[2]};
+    if (G.periodic)
+        for (int d = 0; d < 3; d++) ptw[d] -= D.box[d] * floor(ptw[d] * D.inv_box[d]);
+    const float ptf[3] = {(float)ptw[0], (float)ptw[1], (float)ptw[2]};
+    __shared__ LrfSeg seg[kLrfSegBatch];   // item ranges [lo,hi) of the cell rows (+ target image), computed once per block
+    __shared__ int seg_n, seg_next;        // non-empty segments of the batch; next one to hand out
     int qn = 0;   // entries waiting in this warp's queue (warp-uniform)
     for (int r0 = 0; r0 < nrow; r0 += kLrfSegBatch) {
         __syncthreads();
-        if (whole) { if (threadIdx.x == 0) seg[0] = make_int2(0, D.nunit); }
+        if (threadIdx.x == 0) { seg_n = 0; seg_next = 0; }
+        __syncthreads();
+        if (whole) { if (threadIdx.x == 0) { seg[0] = LrfSeg{0, D.nunit, ptf[0], ptf[1], ptf[2]}; seg_n = 1; } }
         else for (int r = r0 + threadIdx.x; r < min(nrow, r0 + kLrfSegBatch); r += blockDim.x) {
-            const int sgi = r % xs.n, iy = (r / xs.n) % ry.count, iz = r / (xs.n * ry.count);
-            int z = rz.start + iz; z = (z % G.n[2] + G.n[2]) % G.n[2];
-            int y = ry.start + iy; y = (y % G.n[1] + G.n[1]) % G.n[1];
+            const int nxs = ROWSHIFT ? 2 : xs.n;
+            const int sgi = r % nxs, iy = (r / nxs) % ry.count, iz = r / (nxs * ry.count);
+            const int zu = rz.start + iz, yu = ry.start + iy;           // unwrapped cell indices of the row
+            const int z = (zu % G.n[2] + G.n[2]) % G.n[2], y = (yu % G.n[1] + G.n[1]) % G.n[1];
             const int rowbase = (z * G.n[1] + y) * G.n[0];
-            seg[r - r0] = make_int2(cell_start[rowbase + (sgi == 0 ? xs.lo[0] : xs.lo[1])],
-                                    cell_start[rowbase + (sgi == 0 ? xs.hi[0] : xs.hi[1])]);
+            LrfSeg sg{0, 0, ptf[0], ptf[1], ptf[2]};
+            if (!ROWSHIFT) {
+                sg.lo = cell_start[rowbase + (sgi == 0 ? xs.lo[0] : xs.lo[1])];
+                sg.hi = cell_start[rowbase + (sgi == 0 ? xs.hi[0] : xs.hi[1])];
+            } else {
+                // distance from the target to the row's y/z slab (cell size = box/n exactly, see cell_coord)
+                const float cyl = by / (float)G.n[1], czl = bz / (float)G.n[2], cxl = bx / (float)G.n[0];
+                const float ylo = (float)yu * cyl, zlo = (float)zu * czl;
+                const float dy = fmaxf(0.f, fmaxf(ylo - ptf[1], ptf[1] - (ylo + cyl)));
+                const float dz = fmaxf(0.f, fmaxf(zlo - ptf[2], ptf[2] - (zlo + czl)));
+                const float rr = rl * (1.0f + 1e-3f) + 0.05f;             // same safety as hi_band
+                const float h2 = rr * rr - dy * dy - dz * dz;
+                if (h2 > 0.f) {
+                    const float xh = sqrtf(h2) + 1e-3f * cxl;
+                    int xa = max(cx - reach.x, (int)floorf((ptf[0] - xh) / cxl));
+                    int xb = min(cx + reach.x, (int)floorf((ptf[0] + xh) / cxl));
+                    // unwrapped range [xa,xb] -> part in the image of xa (sgi 0) and the rest (sgi 1)
+                    const int ia = (xa >= 0 ? xa / G.n[0] : -((-xa + G.n[0] - 1) / G.n[0]));   // floor(xa/n)
+                    const int split = (ia + 1) * G.n[0];                                          // first cell of the next image
+                    int a0 = sgi == 0 ? xa : max(xa, split), b0 = sgi == 0 ? min(xb, split - 1) : xb;
+                    if (a0 <= b0) {
+                        const int img = sgi == 0 ? ia : ia + 1;
+                        sg.lo = cell_start[rowbase + (a0 - img * G.n[0])];
+                        sg.hi = cell_start[rowbase + (b0 - img * G.n[0]) + 1];
+                        const int iyg = (yu >= 0 ? yu / G.n[1] : -((-yu + G.n[1] - 1) / G.n[1]));
+                        const int izg = (zu >= 0 ? zu / G.n[2] : -((-zu + G.n[2] - 1) / G.n[2]));
+                        // candidate image = stored position + img*box: subtract it from the target instead
+                        sg.tx = ptf[0] - (float)img * bx; sg.ty = ptf[1] - (float)iyg * by; sg.tz = ptf[2] - (float)izg * bz;
+                    }
+                }
+            }
+            if (sg.hi > sg.lo) seg[atomicAdd(&seg_n, 1)] = sg;   // only rows that hold candidates
         }
         __syncthreads();
-        const int nseg = min(nrow - r0, kLrfSegBatch);
-        // few long segments: all warps share each segment, striding by kRowWarps*32; else one segment per warp
+        const int nseg = seg_n;
+        // few long segments: all warps share each segment, striding by kRowWarps*32; else the warps draw segments from
+        // a shared counter (rows differ in length after trimming: a fixed deal leaves warps idle at the barrier)
         const bool share = nseg < kRowWarps;
-        for (int r = share ? 0 : wid; r < nseg; r += share ? 1 : kRowWarps) {
-            const int lo = seg[r].x + (share ? 32 * wid : 0), hi = seg[r].y;
+        for (int r = 0;;) {
+            if (share) { if (r >= nseg) break; }
+            else {
+                if (lane == 0) r = atomicAdd(&seg_next, 1);
+                r = __shfl_sync(kFull, r, 0);
+                if (r >= nseg) break;
+            }
+            const LrfSeg sg = seg[r];
+            const int lo = sg.lo + (share ? 32 * wid : 0), hi = sg.hi;
             for (int base = lo; base < hi; base += share ? 32 * kRowWarps : 32) {
                 const int idx = base + lane;
                 bool accept = false;
                 if (idx < hi) {
                     const float4 pf = item_posf[idx];
                     const int s = __float_as_int(pf.w);
-                    float dx = pf.x - ptf[0], dy = pf.y - ptf[1], dz = pf.z - ptf[2];
-                    if (D.use_PBC) { dx -= bx * rintf(dx * ibx); dy -= by * rintf(dy * iby); dz -= bz * rintf(dz * ibz); }
+                    float dx = pf.x - sg.tx, dy = pf.y - sg.ty, dz = pf.z - sg.tz;
+                    if (!ROWSHIFT && D.use_PBC) { dx -= bx * rintf(dx * ibx); dy -= by * rintf(dy * iby); dz -= bz * rintf(dz * ibz); }
                     const float r2f = dx * dx + dy * dy + dz * dz;
                     const bool s_sol = s < ns;
                     // zones: 0 listed or outside the shell, 1 surely inside it, 2 the FP64 test decides
                     int zone;
-                    if (D.any_atom && (t_sol || s_sol)) zone = (!any_all && r2f > hi_band) ? 0 : 2;
+                    if (GENERAL && D.any_atom && (t_sol || s_sol)) zone = (!any_all && r2f > hi_band) ? 0 : 2;
                     else {
                         const float il = s_sol ? in_lo_s : in_lo_w, ih = s_sol ? in_hi_s : in_hi_w;
                         const bool all = s_sol ? all_s : all_w;
                         zone = (r2f < il || (!all && r2f > out_hi)) ? 0 : (r2f > ih && (all || r2f < out_lo)) ? 1 : 2;
                     }
                     if (s < 0 || s == t) zone = 0;
-                    if (zone != 0 && (D.sharded || zone == 2)) {
+                    if (zone != 0 && ((GENERAL && D.sharded) || zone == 2)) {
                         bool owner_is_t;
                         const int cls = pair_class(t, s, ns, owner_is_t);
-                        if (D.sharded && !in_shard(D, cls, owner_is_t ? t : s)) zone = 0;
+                        if (GENERAL && D.sharded && !in_shard(D, cls, owner_is_t ? t : s)) zone = 0;
                         else if (zone == 2) {
                             const double4 ip = item_pos[idx];
                             const double ps[3] = {ip.x, ip.y, ip.z};
@@ -702,6 +756,7 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
                     qn = rest;
                 }
             }
+            if (share) r++;
         }
     }
     __syncwarp();

@@ -69,6 +69,10 @@ def small_systems():
                 dict(Rq=-1.0, Rcq2=1.0, RcLRF2=1.0, Rcpp2=64.0, Rcpw2=64.0, Rcww2=64.0, RcLRF=-1.0), [1.0]))
     out.append(("box_water", synth.water_box(9, 19), dict(Rq=-1.0, Rcq2=1.0, RcLRF2=12.0 ** 2, Rcpp2=81.0, Rcpw2=81.0, Rcww2=81.0, RcLRF=12.0), [1.0]))
     out.append(("box_water_nolrf", _nolrf(synth.water_box(7, 20)), dict(Rq=-1.0, Rcq2=1.0, RcLRF2=1.0, Rcpp2=49.0, Rcpw2=49.0, Rcww2=49.0, RcLRF=-1.0), [1.0]))
+    # boxes large against the LRF cut-off: the LRF scan takes the periodic image per cell row (and skips far rows)
+    out.append(("box_water_rowimage", synth.water_box(10, 27), dict(Rq=-1.0, Rcq2=1.0, RcLRF2=8.0 ** 2, Rcpp2=36.0, Rcpw2=36.0, Rcww2=36.0, RcLRF=8.0), [1.0]))
+    out.append(("box_solute_rowimage", synth.solvated_sphere(0.0, 6.0, 10, 2, 28, fep="evb", pbc_box=10 * synth.A_LATTICE),
+                dict(Rq=8.0, Rcq2=64.0, RcLRF2=8.5 ** 2, Rcpp2=36.0, Rcpw2=30.25, Rcww2=36.0, RcLRF=8.5), [0.4, 0.6]))
     # any-atom charge-group cut-offs (iuse_switch_atom = 0: nb??lis2*)
     out.append(("sph_anyatom", _anyatom(synth.solvated_sphere(16.0, 9.0, 12, 2, 22, fep="evb")), sph_cuts(8.0, rq=10.0, rlrf=14.0), [0.5, 0.5]))
     out.append(("sph_anyatom_lrf99", _anyatom(synth.solvated_sphere(15.0, 9.0, 8, 1, 23)), sph_cuts(7.5), [1.0]))
