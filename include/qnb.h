@@ -168,6 +168,16 @@ int qnb_init(const qnb_system *sys, int device, qnb_handle **out);
 int qnb_update_box(qnb_handle *h, const double boxlength[3], const double inv_boxl[3]);
 
 /*
+ * MC_volume (md.f90:1976-2284) keeps the pair lists, their counts and the LRF moments of the current box while it
+ * tries a scaled one (old_nbww = nbww ... old_lrf(:) = lrf(:), md.f90:2022-2058) and puts them back when the move is
+ * rejected (md.f90:2214-2256).  qnb_save_lists remembers the state of the last qnb_build_lists (coordinates the
+ * lists were built from, cut-offs, box, LRF moments); qnb_restore_lists re-creates the device lists from it
+ * (the lists are a pure function of that state) and restores the saved box and LRF moments bit for bit.
+ */
+int qnb_save_lists(qnb_handle *h);
+int qnb_restore_lists(qnb_handle *h);
+
+/*
  * make_pair_lists (nonbondene.f90:749): rebuild nbpp/nbpw/nbww/nbqp/nbqw for the
  * handle's shard from coordinates x[3*natom] and accumulate the LRF moments.
  * Arguments are the reference's, in its order; RcLRF (unsquared) is the global

@@ -44,6 +44,17 @@ interface
         real(c_double), intent(in) :: boxlength(3), inv_boxl(3)
         integer(c_int) :: rc
     end function
+    ! MC_volume (md.f90:1976): "old_nbww = nbww ... old_lrf = lrf" / the restore of a rejected move
+    function qnb_save_lists(handle) bind(c, name='qnb_save_lists') result(rc)
+        import :: c_int, c_ptr
+        type(c_ptr), value :: handle
+        integer(c_int) :: rc
+    end function
+    function qnb_restore_lists(handle) bind(c, name='qnb_restore_lists') result(rc)
+        import :: c_int, c_ptr
+        type(c_ptr), value :: handle
+        integer(c_int) :: rc
+    end function
     function qnb_build_lists(handle, x, Rq, Rcq2, RcLRF2, Rcpp2, Rcpw2, Rcww2, RcLRF, counts) &
             bind(c, name='qnb_build_lists') result(rc)
         import :: c_int, c_ptr, c_double

@@ -140,7 +140,13 @@ struct qnb_handle {
     int occ_w = 0, occ_s = 0;
     DBuf<int2> wdesc, sdesc;
     DBuf<uint32_t> wrow, srow;
-    DBuf<uint16_t> sspec;   // solute chunks: per entry, special-pair codes of the tile atoms
+    DBuf<uint16_t> sspec;
+    // MC_volume: state of the last list build and its saved copy
+    DBuf<double> x_saved, lrf_saved;
+    std::vector<double> hx_build, hx_saved;
+    double box_saved[3] = {0, 0, 0}, inv_saved[3] = {0, 0, 0};
+    Cut cut_build{}, cut_saved{};
+    bool have_saved = false, restoring = false;   // solute chunks: per entry, special-pair codes of the tile atoms
     int nwchunk = 0, nschunk = 0;   // water-row / solute-row chunks
     int nqp = 0, nqw = 0;
     bool qp_done = false, qw_done = false, lists_built = false;
@@ -371,6 +377,10 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
     const Dev &D = h->D;
     drop_graphs(h);   // row pointers, counts and list sizes are baked into the captured launches
     const int nu = D.nunit;
+    if (!h->restoring) {   // what qnb_save_lists would have to remember
+        h->hx_build.assign(hx_for_grid, hx_for_grid + 3 * (size_t)D.natom);
+        h->cut_build = h->cut;
+    }
     make_grid(h, hx_for_grid);
     const Grid G = h->grid;
     if (h->upos.ensure(3 * (size_t)std::max(nu, 1)) || h->cell_of.ensure(std::max(nu, 1)) ||
@@ -470,7 +480,7 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
         }
     }
     // LRF: cgp_centers + lrf_update over every pair that falls in the LRF branch
-    if (D.use_LRF && D.ncgp > 0) {
+    if (D.use_LRF && D.ncgp > 0 && !h->restoring) {   // a restore copies the saved moments back instead
         LAUNCH(h, k_cgp_centers, cdiv(D.ncgp, 128), 128, 0, D, h->x.p, h->lrf.p);
         if (nu > 0) {
             if (h->npk > 0) LAUNCH(h, k_pack_sources, cdiv(h->npk, 256), 256, 0, h->npk, h->pk_atom.p, h->x.p, h->crg.p, h->src.p);
@@ -742,6 +752,43 @@ int qnb_update_box(qnb_handle *h, const double boxlength[3], const double inv_bo
     for (int d = 0; d < 3; d++) { h->box[d] = boxlength[d]; h->inv_box[d] = inv_boxl[d]; }
     refresh_dev(h);
     drop_graphs(h);
+    return 0;
+}
+
+int qnb_save_lists(qnb_handle *h) {
+    if (!h) return fail("null handle");
+    if (!h->lists_built) return fail("qnb_save_lists: pair lists have not been built");
+    CU(cudaSetDevice(h->device));
+    const size_t nl = (size_t)QNB_LRF_STRIDE * std::max(h->T.s.ncgp, 1);
+    if (h->lrf_saved.ensure(nl)) return 1;
+    CU(cudaMemcpyAsync(h->lrf_saved.p, h->lrf.p, nl * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    h->hx_saved = h->hx_build;
+    h->cut_saved = h->cut_build;
+    for (int d = 0; d < 3; d++) { h->box_saved[d] = h->box[d]; h->inv_saved[d] = h->inv_box[d]; }
+    h->have_saved = true;
+    return 0;
+}
+
+int qnb_restore_lists(qnb_handle *h) {
+    if (!h) return fail("null handle");
+    if (!h->have_saved) return fail("qnb_restore_lists: nothing saved (call qnb_save_lists)");
+    CU(cudaSetDevice(h->device));
+    for (int d = 0; d < 3; d++) { h->box[d] = h->box_saved[d]; h->inv_box[d] = h->inv_saved[d]; }
+    refresh_dev(h);
+    h->cut = h->cut_saved;
+    const size_t n3 = 3 * (size_t)h->T.s.natom;
+    memcpy(h->hx, h->hx_saved.data(), n3 * sizeof(double));
+    CU(cudaMemcpyAsync(h->x.p, h->hx, n3 * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    h->restoring = true;
+    const int rc = build_device(h, h->hx_saved.data());
+    h->restoring = false;
+    if (rc) return 1;
+    h->hx_build = h->hx_saved;
+    h->cut_build = h->cut_saved;
+    const size_t nl = (size_t)QNB_LRF_STRIDE * std::max(h->T.s.ncgp, 1);
+    CU(cudaMemcpyAsync(h->lrf.p, h->lrf_saved.p, nl * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+    CU(cudaStreamSynchronize(h->st));
     return 0;
 }
 
@@ -1122,7 +1169,7 @@ int qnb_finalize(qnb_handle *h) {
     h->row_tot.release(); h->row_off.release(); h->flag.release(); h->pos.release(); h->qp_list.release();
     h->qw_list.release(); h->qp_shift_atom.release(); h->rows.release(); h->flush.release();
     h->pk_atom.release(); h->pk_ct.release(); h->pk_q.release(); h->pk_qd.release(); h->px.release(); h->py.release(); h->pz.release();
-    h->nch.release(); h->choff.release(); h->ucost.release(); h->cost_off.release(); h->wstart_w.release(); h->wstart_s.release(); h->wdesc.release(); h->wrow.release(); h->sdesc.release(); h->srow.release(); h->sspec.release();
+    h->nch.release(); h->choff.release(); h->ucost.release(); h->cost_off.release(); h->wstart_w.release(); h->wstart_s.release(); h->wdesc.release(); h->wrow.release(); h->sdesc.release(); h->srow.release(); h->sspec.release(); h->x_saved.release(); h->lrf_saved.release();
     h->item_posf.release();
     h->item_pos.release(); h->src.release(); h->cell_unsorted.release(); h->item_nq.release(); h->src_off.release();
     if (h->hx) cudaFreeHost(h->hx);

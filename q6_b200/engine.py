@@ -66,6 +66,9 @@ def load_library(path: str = LIB_PATH):
     lib.qnb_init.argtypes = [C.POINTER(qnb_system), C.c_int, C.POINTER(H)]
     lib.qnb_update_box.restype = C.c_int
     lib.qnb_update_box.argtypes = [H, _PD, _PD]
+    for fn in (lib.qnb_save_lists, lib.qnb_restore_lists):
+        fn.restype = C.c_int
+        fn.argtypes = [H]
     lib.qnb_build_lists.restype = C.c_int
     lib.qnb_build_lists.argtypes = [H, _PD] + [C.c_double] * 7 + [_PL]
     lib.qnb_nonbond.restype = C.c_int
@@ -146,6 +149,14 @@ class Qnb:
         b = np.ascontiguousarray(boxlength, dtype=np.float64)
         ib = np.ascontiguousarray(1.0 / b if inv_boxl is None else inv_boxl, dtype=np.float64)
         self._check(self.lib.qnb_update_box(self.h, _dp(b), _dp(ib)))
+
+    def save_lists(self):
+        """MC_volume keeping the lists of the current box: old_nbww = nbww ... old_lrf = lrf (md.f90:2022-2058)."""
+        self._check(self.lib.qnb_save_lists(self.h))
+
+    def restore_lists(self):
+        """MC_volume, rejected move: lists, LRF moments and box as saved (md.f90:2214-2256)."""
+        self._check(self.lib.qnb_restore_lists(self.h))
 
     def make_pair_lists(self, x, Rq, Rcq2, RcLRF2, Rcpp2, Rcpw2, Rcww2, RcLRF=None, counts=True):
         """make_pair_lists(Rq,Rcq2,RcLRF2,Rcpp2,Rcpw2,Rcww2), nonbondene.f90:749.

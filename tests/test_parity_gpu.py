@@ -168,3 +168,49 @@ def test_properties_water_box_full_size():
         g2.close()
     finally:
         g.close()
+
+
+@pytest.mark.parametrize("case", [c for c in small_systems() if c[0] in ("box_water", "box_solute_q", "box_solute_rowimage")],
+                         ids=lambda c: c[0])
+def test_mc_volume_save_restore(case):
+    """MC_volume (md.f90:1976-2284): lists + LRF of the old box are kept while a scaled box is tried, and come back
+    unchanged when the move is rejected."""
+    from oracle.pyoracle import Oracle
+    from q6_b200.engine import Qnb
+    name, q, cuts, lam = case
+    lam = np.array(lam)
+    g, o = Qnb(q), Oracle(q)
+    try:
+        x0 = q.xtop
+        rng = np.random.default_rng(3)
+        x1 = x0 + rng.normal(0, 0.02, x0.shape)          # some steps after the list build
+        g.make_pair_lists(x0, **cuts)
+        o.make_pair_lists(x0, **cuts)
+        lists0 = [sorted_pairs(g.export_list(w, 1)[0]) for w in range(5)]
+        lrf0 = g.export_lrf()
+        d0, E0, EQ0 = g.pot_energy_nonbonds(x1, lam)
+        g.save_lists()
+        # trial move: box and coordinates scaled by 1 %, new lists, new energy (md.f90:2087-2177)
+        box0 = np.array(q.boxlength, dtype=float)
+        s = 1.01
+        g.update_box(box0 * s)
+        g.make_pair_lists(x1 * s, **cuts)
+        dt, Et, EQt = g.pot_energy_nonbonds(x1 * s, lam)
+        assert abs(Et[4] - E0[4]) > 0 or abs(Et[0] - E0[0]) > 0      # it really was another state
+        # rejected: everything back
+        g.restore_lists()
+        for w in range(5):
+            assert np.array_equal(sorted_pairs(g.export_list(w, 1)[0]), lists0[w]), f"{LIST_NAMES[w]} list differs after restore"
+        assert np.array_equal(g.export_lrf(), lrf0), "LRF moments are not restored bit for bit"
+        d2, E2, EQ2 = g.pot_energy_nonbonds(x1, lam)
+        # same lists as sets; the order inside a row (hence FP32 summation order) may differ between two builds
+        assert rel_rms(d2, d0) < 2e-6
+        assert np.allclose(E2, E0, rtol=1e-10, atol=1e-9) and np.allclose(EQ2, EQ0, rtol=1e-10, atol=1e-9)
+        # and it is still the reference's answer for the old box
+        do, Eo, EQo = o.pot_energy_nonbonds(x1, lam)
+        assert rel_rms(d2, do) <= FORCE_REL_RMS
+        for k, nm in enumerate(("pp.el", "pp.vdw", "pw.el", "pw.vdw", "ww.el", "ww.vdw", "LRF")):
+            assert_energy(nm, E2[k], Eo[k])
+    finally:
+        g.close()
+        o.close()
