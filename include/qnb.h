@@ -178,6 +178,19 @@ int qnb_save_lists(qnb_handle *h);
 int qnb_restore_lists(qnb_handle *h);
 
 /*
+ * qcp_run (qcp.f90:319-372, 478-525): for every bead i the coordinates of the path-integral atoms are set to
+ * x(iqseq(qcp_atom(j))) = x_save(..) + qcp_coord(j,i) and pot_energy(qcp_E,qcp_EQ,.false.) is called; only the
+ * per-state Q energies are used.  This entry evaluates the nonbonded part of all beads in one call (one upload of
+ * x_save, the beads' displacements applied on the device, one download of the energies).
+ *   atoms[natq]           1-based atom numbers of the displaced atoms (iqseq(qcp_atom(j)))
+ *   coord[nbeads][natq][3] displacements (qcp_coord(j,i), bead-major)
+ *   EQ_out[nbeads][6*nstates] as qnb_nonbond's EQ_out, per bead
+ * Uses the current pair lists (QCP never rebuilds them, qcp.f90).  Forces are not produced.
+ */
+int qnb_qcp_beads(qnb_handle *h, const double *x_save, int natq, const int32_t *atoms, int nbeads, const double *coord,
+                  const double *lambda, double *EQ_out);
+
+/*
  * make_pair_lists (nonbondene.f90:749): rebuild nbpp/nbpw/nbww/nbqp/nbqw for the
  * handle's shard from coordinates x[3*natom] and accumulate the LRF moments.
  * Arguments are the reference's, in its order; RcLRF (unsquared) is the global

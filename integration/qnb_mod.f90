@@ -55,6 +55,18 @@ interface
         type(c_ptr), value :: handle
         integer(c_int) :: rc
     end function
+    ! qcp_run (qcp.f90:319-372, 478-525): all beads of one sampling step in one call
+    function qnb_qcp_beads(handle, x_save, natq, atoms, nbeads, coord, lambda, EQ_out) bind(c, name='qnb_qcp_beads') result(rc)
+        import :: c_int, c_ptr, c_double, c_int32_t
+        type(c_ptr), value :: handle
+        real(c_double), intent(in) :: x_save(*)           ! x_save(natom) as 3*natom doubles
+        integer(c_int), value :: natq, nbeads
+        integer(c_int32_t), intent(in) :: atoms(*)        ! iqseq(qcp_atom(1:qcp_atnum))
+        real(c_double), intent(in) :: coord(*)            ! qcp_coord(j,i) copied bead-major: (3, natq, nbeads)
+        real(c_double), intent(in) :: lambda(*)
+        real(c_double), intent(out) :: EQ_out(*)          ! (6, nstates, nbeads): qq, qp, qw x (el, vdw)
+        integer(c_int) :: rc
+    end function
     function qnb_build_lists(handle, x, Rq, Rcq2, RcLRF2, Rcpp2, Rcpw2, Rcww2, RcLRF, counts) &
             bind(c, name='qnb_build_lists') result(rc)
         import :: c_int, c_ptr, c_double

@@ -522,13 +522,15 @@ enum StepKernel { K_WATER = 0, K_SOLUTE, K_QPARTNER, K_QATOM, K_QSTATIC, K_LRF, 
 static const char *kStepKernelNames[K_COUNT] = {"k_water_force", "k_solute_force", "k_q_partner", "k_q_atom",
                                                 "k_qq_static", "k_lrf_taylor"};
 
+constexpr int kFlagEnergiesOnly = 4;   // internal (QCP beads): no kernel whose only product is a gradient
+
 static bool step_kernel_active(const qnb_handle *h, int k, int flags) {
     const Dev &D = h->D;
     const bool md = flags & QNB_FLAG_MD;
     switch (k) {
     case K_WATER: return md && D.nwat > 0 && h->nwchunk > 0;
     case K_SOLUTE: return md && D.ncgp_solute > 0 && h->nschunk > 0;
-    case K_QPARTNER: return D.nqat > 0 && (h->nqp + h->nqw) > 0;
+    case K_QPARTNER: return !(flags & kFlagEnergiesOnly) && D.nqat > 0 && (h->nqp + h->nqw) > 0;
     case K_QATOM: return D.nqat > 0 && (h->nqp + h->nqw) > 0;
     case K_QSTATIC: return (flags & QNB_FLAG_QQ) && h->T.s.is_master && h->n_qstatic > 0;
     case K_LRF: return md && D.use_LRF;
@@ -789,6 +791,45 @@ int qnb_restore_lists(qnb_handle *h) {
     const size_t nl = (size_t)QNB_LRF_STRIDE * std::max(h->T.s.ncgp, 1);
     CU(cudaMemcpyAsync(h->lrf.p, h->lrf_saved.p, nl * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
     CU(cudaStreamSynchronize(h->st));
+    return 0;
+}
+
+int qnb_qcp_beads(qnb_handle *h, const double *x_save, int natq, const int32_t *atoms, int nbeads, const double *coord,
+                  const double *lambda, double *EQ_out) {
+    if (!h || !x_save || !atoms || !coord || !lambda || !EQ_out) return fail("qnb_qcp_beads: null argument");
+    if (!h->lists_built) return fail("qnb_qcp_beads: pair lists have not been built (call qnb_build_lists)");
+    if (natq <= 0 || nbeads <= 0) return fail("qnb_qcp_beads: natq and nbeads must be positive");
+    CU(cudaSetDevice(h->device));
+    const qnb_system &s = h->T.s;
+    const size_t n3 = 3 * (size_t)s.natom;
+    const int nEQ = QNB_EQ_STRIDE * s.nstates;
+    std::vector<int> a0(natq);
+    std::vector<double> base(3 * (size_t)natq);
+    for (int j = 0; j < natq; j++) {
+        if (atoms[j] < 1 || atoms[j] > s.natom) return fail("qnb_qcp_beads: atom %d out of range", (int)atoms[j]);
+        a0[j] = atoms[j] - 1;
+        for (int c = 0; c < 3; c++) base[3 * j + c] = x_save[3 * (size_t)a0[j] + c];
+    }
+    DBuf<int> d_atoms;
+    DBuf<double> d_base, d_disp, d_eq;
+    if (upload(d_atoms, a0) || upload(d_base, base) || d_disp.ensure(3 * (size_t)natq * nbeads) || d_eq.ensure((size_t)h->nE * nbeads)) return 1;
+    memcpy(h->hx, x_save, n3 * sizeof(double));
+    for (int k = 0; k < s.nstates; k++) h->hlam[k] = lambda[k];
+    CU(cudaMemcpyAsync(h->x.p, h->hx, n3 * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    CU(cudaMemcpyAsync(h->lambda.p, h->hlam, kMaxStates * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    CU(cudaMemcpyAsync(d_disp.p, coord, sizeof(double) * 3 * (size_t)natq * nbeads, cudaMemcpyHostToDevice, h->st));
+    for (int b = 0; b < nbeads; b++) {
+        LAUNCH(h, k_set_bead, cdiv(3 * natq, 128), 128, 0, natq, d_atoms.p, d_base.p, d_disp.p + 3 * (size_t)natq * b, h->x.p);
+        if (issue_step(h, QNB_FLAG_QQ | kFlagEnergiesOnly)) return 1;
+        LAUNCH(h, k_collect_energies, cdiv(h->nE, 128), 128, 0, h->nE, kESlots, h->out.p + n3, d_eq.p + (size_t)h->nE * b);
+    }
+    std::vector<double> eq((size_t)h->nE * nbeads);
+    CU(cudaMemcpyAsync(eq.data(), d_eq.p, sizeof(double) * eq.size(), cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    CU(cudaGetLastError());
+    for (int b = 0; b < nbeads; b++)
+        for (int k = 0; k < nEQ; k++) EQ_out[(size_t)b * nEQ + k] = eq[(size_t)b * h->nE + QNB_E_COUNT + k];
+    d_atoms.release(); d_base.release(); d_disp.release(); d_eq.release();
     return 0;
 }
 

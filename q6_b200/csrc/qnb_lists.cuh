@@ -141,6 +141,22 @@ __global__ void k_pack_coords(int npk, const int *__restrict__ pk_atom, const do
     px[p] = x[3 * i]; py[p] = x[3 * i + 1]; pz[p] = x[3 * i + 2];
 }
 
+// qcp_run: x(atom j) = x_save(atom j) + qcp_coord(j, bead)  (qcp.f90:325-328)
+__global__ void k_set_bead(int natq, const int *__restrict__ atoms0, const double *__restrict__ base,
+                           const double *__restrict__ disp, double *__restrict__ x) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= 3 * natq) return;
+    x[3 * atoms0[k / 3] + k % 3] = base[k] + disp[k];
+}
+// fixed-order sum of the replicated energy slots: dst[k] = sum_s E[s][k]
+__global__ void k_collect_energies(int nE, int nslot, const double *__restrict__ E, double *__restrict__ dst) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nE) return;
+    double e = 0;
+    for (int s = 0; s < nslot; s++) e += E[(size_t)s * nE + k];
+    dst[k] = e;
+}
+
 // range of cells along one dimension around c with reach m
 struct DimRange { int start, count; };
 __device__ __forceinline__ DimRange dim_range(int c, int m, int n, int periodic) {

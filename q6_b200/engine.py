@@ -69,6 +69,8 @@ def load_library(path: str = LIB_PATH):
     for fn in (lib.qnb_save_lists, lib.qnb_restore_lists):
         fn.restype = C.c_int
         fn.argtypes = [H]
+    lib.qnb_qcp_beads.restype = C.c_int
+    lib.qnb_qcp_beads.argtypes = [H, _PD, C.c_int, _PI, C.c_int, _PD, _PD, _PD]
     lib.qnb_build_lists.restype = C.c_int
     lib.qnb_build_lists.argtypes = [H, _PD] + [C.c_double] * 7 + [_PL]
     lib.qnb_nonbond.restype = C.c_int
@@ -186,6 +188,19 @@ class Qnb:
         flags = (QNB_FLAG_MD if md else 0) | (QNB_FLAG_QQ if qq else 0)
         self._check(self.lib.qnb_nonbond(self.h, _dp(x), _dp(lam), flags, _dp(d.reshape(-1)), _dp(E), _dp(EQ)))
         return d.reshape(-1, 3), E, EQ.reshape(self.sys.nstates, EQ_STRIDE)
+
+    def qcp_beads(self, x_save, atoms, coord, lambdas):
+        """qcp_run's bead loop (qcp.f90:319-372): for every bead, x(atoms) = x_save(atoms) + coord[bead] and
+        pot_energy(..., .false.); returns EQ[nbeads][nstates][6] (nonbonded Q terms).  atoms are 1-based."""
+        x = np.ascontiguousarray(x_save, dtype=np.float64).reshape(-1)
+        at = np.ascontiguousarray(atoms, dtype=np.int32).reshape(-1)
+        cd = np.ascontiguousarray(coord, dtype=np.float64)
+        assert cd.ndim == 3 and cd.shape[1] == at.size and cd.shape[2] == 3
+        lam = np.ascontiguousarray(lambdas, dtype=np.float64).reshape(-1)
+        assert lam.size == self.sys.nstates
+        out = np.zeros((cd.shape[0], self.sys.nstates, EQ_STRIDE))
+        self._check(self.lib.qnb_qcp_beads(self.h, _dp(x), at.size, at.ctypes.data_as(_PI), cd.shape[0], _dp(cd), _dp(lam), _dp(out)))
+        return out
 
     def list_count(self, which: int, state: int = 1) -> int:
         n = C.c_int64()

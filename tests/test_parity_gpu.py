@@ -214,3 +214,40 @@ def test_mc_volume_save_restore(case):
     finally:
         g.close()
         o.close()
+
+
+@pytest.mark.parametrize("case", [c for c in small_systems() if c[0] in ("sph_evb2", "box_solute_q", "sph_anyatom")],
+                         ids=lambda c: c[0])
+def test_qcp_beads(case):
+    """qcp_run (qcp.f90:319-372): per-bead pot_energy(E,EQ,.false.) with the path-integral atoms displaced; the batched
+    entry must give, bead by bead, what the reference's loop gives."""
+    from oracle.pyoracle import Oracle
+    from q6_b200.engine import Qnb
+    name, q, cuts, lam = case
+    lam = np.array(lam)
+    g, o = Qnb(q), Oracle(q)
+    try:
+        x0 = q.xtop
+        g.make_pair_lists(x0, **cuts)
+        o.make_pair_lists(x0, **cuts)
+        rng = np.random.default_rng(9)
+        qat = np.asarray(q.iqseq[:q.nqat])
+        atoms = qat[rng.choice(q.nqat, size=min(3, q.nqat), replace=False)]     # the qcp_atom selection
+        nbeads = 8
+        coord = rng.normal(0, 0.08, (nbeads, atoms.size, 3))
+        coord -= coord.mean(axis=0, keepdims=True)                              # qcp_center
+        EQ = g.qcp_beads(x0, atoms, coord, lam)
+        for b in range(nbeads):
+            xb = x0.copy()
+            xb[atoms - 1] += coord[b]
+            _, _, EQo = o.pot_energy_nonbonds(xb, lam, md=False)
+            for s in range(q.nstates):
+                for k, nm in enumerate(("qq.el", "qq.vdw", "qp.el", "qp.vdw", "qw.el", "qw.vdw")):
+                    assert_energy(f"bead {b} state {s + 1} {nm}", EQ[b, s, k], EQo[s, k])
+        # the beads really differ from each other
+        assert np.abs(EQ - EQ[0]).max() > 0
+        # and the handle is unharmed: a normal step afterwards still matches
+        _check_step(g, o, q, x0, lam)
+    finally:
+        g.close()
+        o.close()
