@@ -396,6 +396,41 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
         h->pk_qd.ensure(D.natom + 4) || h->px.ensure(D.natom + 4) || h->py.ensure(D.natom + 4) ||   // +4: the force kernels always fetch three sites
         h->pz.ensure(D.natom + 4))
         return 1;
+    // LRF: cgp_centers + lrf_update over every pair that falls in the LRF branch.  It needs the cell tables and the
+    // packed atoms but not the rows, and it is the longest kernel of a build: it runs on a side stream next to the
+    // row/chunk kernels (which are short, latency-bound and interrupted by the host round trip for the sizes).
+    constexpr int kLrfStream = 4;
+    bool lrf_forked = false;
+    auto launch_lrf = [&]() {
+        if (!(D.use_LRF && D.ncgp > 0) || h->restoring) return;
+        cudaStream_t ls = h->multi_stream ? h->aux[kLrfStream] : h->st;
+        if (h->multi_stream) {
+            cudaEventRecord(h->ev_fork, h->st);
+            cudaStreamWaitEvent(ls, h->ev_fork, 0);
+        }
+        LAUNCH_ON(h, ls, k_cgp_centers, cdiv(D.ncgp, 128), 128, 0, D, h->x.p, h->lrf.p);
+        if (nu > 0) {
+            LAUNCH_ON(h, ls, k_pack_sources, cdiv(D.natom, 256), 256, 0, h->src_off.p + nu, h->pk_atom.p, h->x.p, h->crg.p, h->src.p);
+            // compaction pays when the LRF shell holds a small part of the scanned cells (boxes, short RcLRF)
+            const double rl = std::sqrt(std::max(h->cut.rclrf2, 0.0));
+            const bool all = h->cut.lrf_all[0] || h->cut.lrf_all[1] || h->cut.lrf_all[2];
+            double ext = 0;
+            for (int d = 0; d < 3; d++) ext = std::max(ext, G.n[d] / G.inv_cell[d]);
+            const bool compact = !all && rl < 0.9 * ext;
+            // periodic image by cell row when 2(m+1) <= n in every dimension (then |delta| < box/2 for every scanned cell)
+            bool rowshift = G.periodic && !all;
+            const int rr[3] = {h->lrf_reach.x, h->lrf_reach.y, h->lrf_reach.z};
+            for (int d = 0; d < 3; d++) rowshift = rowshift && 2 * (rr[d] + 1) <= G.n[d];
+            const bool general = D.any_atom || D.sharded;
+#define LRFCASE(CP, RS, GN) LAUNCH_ON(h, ls, (k_lrf_accumulate<CP, RS, GN>), nu, 32 * kRowWarps, 0, D, h->cut, G, h->lrf_reach, h->x.p, h->upos.p, \
+                                      h->cell_of.p, h->cell_start.p, h->item_pos.p, h->item_posf.p, h->src_off.p, h->src.p, h->lrf.p)
+            if (rowshift) { if (general) LRFCASE(true, true, true); else LRFCASE(true, true, false); }
+            else if (compact) { if (general) LRFCASE(true, false, true); else LRFCASE(true, false, false); }
+            else { if (general) LRFCASE(false, false, true); else LRFCASE(false, false, false); }
+#undef LRFCASE
+        }
+        if (h->multi_stream) { cudaEventRecord(h->ev_join[kLrfStream], ls); lrf_forked = true; }
+    };
     const bool md_lists = true;
     if (nu > 0 && md_lists) {
         CU(cudaMemsetAsync(h->cell_count.p, 0, sizeof(int) * (G.ncell + 1), h->st));
@@ -407,6 +442,7 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
         LAUNCH(h, k_pack_items, cdiv(nu, 256), 256, 0, D, h->upos.p, h->cell_items.p, h->item_pos.p, h->item_posf.p, h->item_nq.p);
         run_exclusive_scan(h, h->item_nq.p, h->src_off.p, nu);
         LAUNCH(h, k_pack_atoms, cdiv(nu, 128), 128, 0, D, h->cell_items.p, h->src_off.p, h->pk_atom.p, h->pk_q.p, h->pk_qd.p, h->pk_ct.p);
+        launch_lrf();
         LAUNCH(h, k_build_rows<false>, cdiv(nu * 32, 256), 256, 0, D, h->cut, G, h->list_reach, h->x.p, h->upos.p, h->cell_of.p, h->cell_start.p,
                h->item_pos.p, h->src_off.p, h->counts.p, (const int *)nullptr, (uint32_t *)nullptr);
         LAUNCH(h, k_row_totals, cdiv(nu, 256), 256, 0, nu, h->counts.p, h->row_tot.p);
@@ -479,29 +515,9 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
             h->qw_done = true;
         }
     }
-    // LRF: cgp_centers + lrf_update over every pair that falls in the LRF branch
-    if (D.use_LRF && D.ncgp > 0 && !h->restoring) {   // a restore copies the saved moments back instead
-        LAUNCH(h, k_cgp_centers, cdiv(D.ncgp, 128), 128, 0, D, h->x.p, h->lrf.p);
-        if (nu > 0) {
-            if (h->npk > 0) LAUNCH(h, k_pack_sources, cdiv(h->npk, 256), 256, 0, h->npk, h->pk_atom.p, h->x.p, h->crg.p, h->src.p);
-            // compaction pays when the LRF shell holds a small part of the scanned cells (boxes, short RcLRF)
-            const double rl = std::sqrt(std::max(h->cut.rclrf2, 0.0));
-            const bool all = h->cut.lrf_all[0] || h->cut.lrf_all[1] || h->cut.lrf_all[2];
-            double ext = 0;
-            for (int d = 0; d < 3; d++) ext = std::max(ext, G.n[d] / G.inv_cell[d]);
-            const bool compact = !all && rl < 0.9 * ext;
-            // periodic image by cell row when 2(m+1) <= n in every dimension (then |delta| < box/2 for every scanned cell)
-            bool rowshift = G.periodic && !all;
-            const int rr[3] = {h->lrf_reach.x, h->lrf_reach.y, h->lrf_reach.z};
-            for (int d = 0; d < 3; d++) rowshift = rowshift && 2 * (rr[d] + 1) <= G.n[d];
-            const bool general = D.any_atom || D.sharded;
-#define LRFCASE(CP, RS, GN) LAUNCH(h, (k_lrf_accumulate<CP, RS, GN>), nu, 32 * kRowWarps, 0, D, h->cut, G, h->lrf_reach, h->x.p, h->upos.p, \
-                                   h->cell_of.p, h->cell_start.p, h->item_pos.p, h->item_posf.p, h->src_off.p, h->src.p, h->lrf.p)
-            if (rowshift) { if (general) LRFCASE(true, true, true); else LRFCASE(true, true, false); }
-            else if (compact) { if (general) LRFCASE(true, false, true); else LRFCASE(true, false, false); }
-            else { if (general) LRFCASE(false, false, true); else LRFCASE(false, false, false); }
-#undef LRFCASE
-        }
+    // LRF: the moments were started on the side stream after the cell tables (see above); join, then the exchange
+    if (D.use_LRF && D.ncgp > 0 && !h->restoring) {
+        if (lrf_forked) CU(cudaStreamWaitEvent(h->st, h->ev_join[kLrfStream], 0));
         if (h->comm) {
             // lrf_gather (nonbondene.f90:616-623): sum the moments, keep cgp_cent (identical on every rank).
             // cgp_cent is divided by nranks after the sum so one all-reduce serves both.

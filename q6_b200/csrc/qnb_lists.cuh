@@ -125,10 +125,10 @@ __global__ void k_pack_atoms(Dev D, const int *__restrict__ cell_items, const in
     }
 }
 // per list build: LRF source records (x,y,z,q) in packed order
-__global__ void k_pack_sources(int npk, const int *__restrict__ pk_atom, const double *__restrict__ x,
+__global__ void k_pack_sources(const int *__restrict__ npk, const int *__restrict__ pk_atom, const double *__restrict__ x,
                                const double *__restrict__ crg, double4 *__restrict__ src) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= npk) return;
+    if (p >= *npk) return;   // number of packed atoms, still on the device when this is launched
     const int i = pk_atom[p];
     src[p] = make_double4(x[3 * i], x[3 * i + 1], x[3 * i + 2], crg[i]);
 }
