@@ -101,6 +101,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C2", choices=["C2", "C3", "C4s", "C5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--windows-per-gpu", type=int, default=4,
+                    help="also time this many independent windows sharing each GPU (0/1: skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -204,6 +206,37 @@ def main():
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     host_breakdown = g.last_timing()
     h2d, d2h = g.last_copy_bytes()
+    # ---- k independent windows per GPU (FEP production: the windows do not talk to each other; one host thread and
+    # one handle each, same C-ABI calls with host buffers).  Reported next to the single-window e2e, not instead of it.
+    kwin = args.windows_per_gpu
+    win_s = None
+    if kwin > 1:
+        import threading
+        extra = [Qnb(q, device=dev) for _ in range(kwin - 1)]
+        handles = [g] + extra
+
+        def window(hd, nst):
+            xw = q.xtop.copy()
+            dw = np.zeros((q.natom, 3))
+            for k in range(nst):
+                if k % NBCYCLE == 0:
+                    hd.make_pair_lists(xw, **cuts, counts=False)
+                dw[:] = 0
+                hd.pot_energy_nonbonds(xw, lam, d=dw)
+
+        for hd in handles:
+            window(hd, NBCYCLE + 3)
+        th = [threading.Thread(target=window, args=(hd, steps)) for hd in handles]
+        barrier()
+        t0 = time.perf_counter()
+        for a in th:
+            a.start()
+        for a in th:
+            a.join()
+        barrier()
+        win_s = max_over_ranks(time.perf_counter() - t0)
+        for hd in extra:
+            hd.close()
     h2d_step = h2d + (3 * q.natom * 8) / NBCYCLE   # + the list build's coordinate upload, amortised
     if proc is not None:
         proc.terminate()
@@ -271,6 +304,13 @@ def main():
                         "h2d_bytes_per_step": int(h2d_step), "d2h_bytes_per_step": int(d2h),
                         "host_breakdown_last_call_us": {k: round(v * 1e6, 1) for k, v in host_breakdown.items()}},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}
+        if win_s is not None:
+            agg = world * kwin * steps / win_s      # MD steps per second over all windows of all GPUs
+            line["concurrent_windows"] = {"windows_per_gpu": kwin, "steps_per_s": agg, "value": npairs * agg, "unit": "pairs/s",
+                                          "ms_per_step_per_window": win_s / steps * 1e3,
+                                          "fep_windows_per_hour": 3600.0 * agg / STEPS_PER_WINDOW,
+                                          "note": "same end-to-end path as e2e (host buffers, list build every "
+                                                  f"{NBCYCLE} steps), {kwin} handles and host threads per GPU"}
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
             t_cpu, nsteps, _ = cpu_reference(q, cuts, lam, threads, target_seconds=12.0)
