@@ -43,6 +43,10 @@ extern "C" {
 /* flags of qnb_nonbond */
 #define QNB_FLAG_MD 1 /* pot_energy(...,in_md=.true.): pp/pw/ww/LRF as well as Q terms (potene.f90:333-376) */
 #define QNB_FLAG_QQ 2 /* also evaluate the static nbqq/nbqqp lists (master only, potene.f90:176-177) */
+/* Extension (off by default; the reference accumulates E on every call): the caller does not need the pp/pw/ww
+ * energies of this step -- md.f90 reads E only when mod(istep, iout_cycle / iene_cycle / itemp_cycle) == 0 -- so the
+ * row kernels skip their FP64 energy code.  E_out[pp,pw,ww] return 0; gradient, LRF and every Q term are unchanged. */
+#define QNB_FLAG_NO_ENERGY 4
 
 /* which list for qnb_list_count / qnb_export_list */
 #define QNB_LIST_PP 0  /* nbpp  (globals.f90:415) */

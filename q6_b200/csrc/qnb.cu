@@ -101,11 +101,11 @@ struct qnb_handle {
     Dev D{};
     cudaStream_t st = nullptr, aux[kAux] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join[kAux] = {};
-    cudaGraphExec_t graph[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};   // [with copies][flags]
+    cudaGraphExec_t graph[2][8] = {};   // [with copies][flags]
     bool use_graph = true, multi_stream = true;
     int water_blocks = 0, solute_blocks = 0;   // blocks per SM of the two persistent kernels (0: what the occupancy allows)
-    int graph_launches[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
-    bool graph_dirty[2][4] = {{true, true, true, true}, {true, true, true, true}};
+    int graph_launches[2][8] = {};
+    bool graph_dirty[2][8] = {{true, true, true, true, true, true, true, true}, {true, true, true, true, true, true, true, true}};
     // static device tables
     DBuf<double> crg, ljd;
     DBuf<float> crgf, ljf;
@@ -288,7 +288,7 @@ static int init_device(qnb_handle *h) {
 // re-instantiated (hundreds).
 static void drop_graphs(qnb_handle *h, bool destroy = false) {
     for (int c = 0; c < 2; c++)
-        for (int f = 0; f < 4; f++) {
+        for (int f = 0; f < 8; f++) {
             h->graph_dirty[c][f] = true;
             if (destroy && h->graph[c][f]) { cudaGraphExecDestroy(h->graph[c][f]); h->graph[c][f] = nullptr; }
         }
@@ -538,7 +538,7 @@ enum StepKernel { K_WATER = 0, K_SOLUTE, K_QPARTNER, K_QATOM, K_QSTATIC, K_LRF, 
 static const char *kStepKernelNames[K_COUNT] = {"k_water_force", "k_solute_force", "k_q_partner", "k_q_atom",
                                                 "k_qq_static", "k_lrf_taylor"};
 
-constexpr int kFlagEnergiesOnly = 4;   // internal (QCP beads): no kernel whose only product is a gradient
+constexpr int kFlagEnergiesOnly = 8;   // internal (QCP beads): no kernel whose only product is a gradient
 
 static bool step_kernel_active(const qnb_handle *h, int k, int flags) {
     const Dev &D = h->D;
@@ -572,7 +572,8 @@ static void query_occupancy(qnb_handle *h) {
     cudaGetLastError();
 }
 
-static void launch_step_kernel(qnb_handle *h, int k, cudaStream_t cs) {
+static void launch_step_kernel(qnb_handle *h, int k, cudaStream_t cs, int flags) {
+    const int want_e = (flags & QNB_FLAG_NO_ENERGY) ? 0 : 1;
     const Dev &D = h->D;
     double *grad = h->out.p, *E = h->out.p + 3 * (size_t)D.natom;
     const int nE = h->nE;
@@ -581,7 +582,7 @@ static void launch_step_kernel(qnb_handle *h, int k, cudaStream_t cs) {
     case K_WATER: {
 #define WCASE(P, S, G)                                                                                                             \
     LAUNCH_ON(h, cs, (k_water_force<P, S, G>), h->wgrid, 128, 0, D, h->x.p, h->px.p, h->py.p, h->pz.p, h->pk_q.p, h->pk_ct.p,     \
-              h->pk_atom.p, h->wstart_w.p, h->wdesc.p, h->wrow.p, grad, E, nE)
+              h->pk_atom.p, h->wstart_w.p, h->wdesc.p, h->wrow.p, grad, E, nE, want_e)
         if (pbc) { if (spc) WCASE(true, true, true); else if (geom) WCASE(true, false, true); else WCASE(true, false, false); }
         else { if (spc) WCASE(false, true, true); else if (geom) WCASE(false, false, true); else WCASE(false, false, false); }
 #undef WCASE
@@ -591,7 +592,7 @@ static void launch_step_kernel(qnb_handle *h, int k, cudaStream_t cs) {
         const size_t sm = solute_smem(D);
 #define SCASE(P, G)                                                                                                              \
     LAUNCH_ON(h, cs, (k_solute_force<P, G>), h->sgrid, 128, sm, D, h->x.p, h->px.p, h->py.p, h->pz.p, h->pk_q.p, h->pk_qd.p,    \
-              h->pk_ct.p, h->pk_atom.p, h->wstart_s.p, h->sdesc.p, h->srow.p, h->sspec.p, grad, E, nE)
+              h->pk_ct.p, h->pk_atom.p, h->wstart_s.p, h->sdesc.p, h->srow.p, h->sspec.p, grad, E, nE, want_e)
         if (pbc) { if (geom) SCASE(true, true); else SCASE(true, false); }
         else { if (geom) SCASE(false, true); else SCASE(false, false); }
 #undef SCASE
@@ -642,7 +643,7 @@ static int issue_step(qnb_handle *h, int flags) {
         const int si = h->multi_stream ? kStreamOf[k] : -1;
         cudaStream_t cs = si < 0 ? h->st : h->aux[si];
         if (si >= 0 && !used[si]) { CU(cudaStreamWaitEvent(cs, h->ev_fork, 0)); used[si] = true; }
-        launch_step_kernel(h, k, cs);
+        launch_step_kernel(h, k, cs, flags);
     }
     for (int k = 0; k < kAux; k++)
         if (used[k]) {
@@ -657,7 +658,7 @@ static int issue_step(qnb_handle *h, int flags) {
 static int step_device(qnb_handle *h, int flags, bool with_copies = false) {
     const size_t n3 = 3 * (size_t)h->T.s.natom;
     const bool graphable = h->use_graph && !h->comm;
-    flags &= 3;
+    flags &= 7;
     if (graphable) {
         cudaGraphExec_t &ge = h->graph[with_copies ? 1 : 0][flags];
         bool &dirty = h->graph_dirty[with_copies ? 1 : 0][flags];
@@ -1183,7 +1184,7 @@ int qnb_bench_kernels(qnb_handle *h, const double *lambda, int flags, int reps, 
             cudaMemsetAsync(h->out.p, 0, h->nout * sizeof(double), h->st);
             if (do_flush && flush_l2(h)) return -1;
             cudaEventRecord(h->ev0, h->st);
-            launch_step_kernel(h, k, h->st);
+            launch_step_kernel(h, k, h->st, flags);
             cudaEventRecord(h->ev1, h->st);
             cudaEventSynchronize(h->ev1);
             float ms = 0;

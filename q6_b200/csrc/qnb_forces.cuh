@@ -215,7 +215,8 @@ __global__ void __launch_bounds__(128, QNB_WATER_MINB)
 k_water_force(Dev D, const double *__restrict__ x, const double *__restrict__ px, const double *__restrict__ py,
               const double *__restrict__ pz, const float *__restrict__ pk_q, const int *__restrict__ pk_ct,
               const int *__restrict__ pk_atom, const int *__restrict__ wstart, const int2 *__restrict__ cdesc,
-              const uint32_t *__restrict__ crow, double *__restrict__ grad, double *__restrict__ Eslots, int nE) {
+              const uint32_t *__restrict__ crow, double *__restrict__ grad, double *__restrict__ Eslots, int nE,
+              int want_energy) {
     const int lane = threadIdx.x & 31;
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int c0 = wstart[gw], c1 = wstart[gw + 1];   // this warp's share of the chunks (k_warp_starts)
@@ -268,7 +269,7 @@ k_water_force(Dev D, const double *__restrict__ x, const double *__restrict__ px
         if (d.y == kChunkB) wp_chunk<PBC, GEOM>(D, T, valid, pj, qb, ctb, e, x, pk_atom);
         else {
             const bool own = valid && (e & kOwnerBit);
-            ww_chunk<PBC, SPC>(D, T, own, __any_sync(kFull, own), valid, pj, eel, evdw);
+            ww_chunk<PBC, SPC>(D, T, own, want_energy && __any_sync(kFull, own), valid, pj, eel, evdw);
         }
     };
     // chunk c computes from (d0,e0,P); chunk c+1 is (d1,e1) with its coordinates landing in R; (d2,e2) is chunk c+2.
@@ -326,7 +327,7 @@ k_solute_force(Dev D, const double *__restrict__ x, const double *__restrict__ p
                const double *__restrict__ pz, const float *__restrict__ pk_q, const double *__restrict__ pk_qd,
                const int *__restrict__ pk_ct, const int *__restrict__ pk_atom, const int *__restrict__ wstart,
                const int2 *__restrict__ cdesc, const uint32_t *__restrict__ crow, const uint16_t *__restrict__ cspec, double *__restrict__ grad,
-               double *__restrict__ Eslots, int nE) {
+               double *__restrict__ Eslots, int nE, int want_energy) {
     extern __shared__ unsigned char smem_raw[];
     // shared LJ tables: ljd [nct*6] doubles, ljf [nct*6] floats, ljcode [nct*nct] bytes
     double *s_ljd = reinterpret_cast<double *>(smem_raw);
@@ -459,7 +460,7 @@ k_solute_force(Dev D, const double *__restrict__ x, const double *__restrict__ p
                 T.grad[t][2] = fmaf(-dz, dv, T.grad[t][2]);
             }
             // energy once per pair: on the owner side
-            if (__any_sync(kFull, own)) {
+            if (want_energy && __any_sync(kFull, own)) {
 #pragma unroll
                 for (int t = 0; t < kITile; t++) {
                     const double qqd = i14[t] ? T.qd[t] * qbd * D.el14 : T.qd[t] * qbd;
@@ -500,6 +501,7 @@ k_solute_force(Dev D, const double *__restrict__ x, const double *__restrict__ p
                     T.grad[t][0] = fmaf(-dx, dv, T.grad[t][0]); T.grad[t][1] = fmaf(-dy, dv, T.grad[t][1]);
                     T.grad[t][2] = fmaf(-dz, dv, T.grad[t][2]);
                 }
+                if (want_energy)
 #pragma unroll
                 for (int t = 0; t < kITile; t++) {
                     double Ad, Bd, tel, tvdw;

@@ -20,6 +20,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libqnb.so")
 
 QNB_FLAG_MD = 1
 QNB_FLAG_QQ = 2
+QNB_FLAG_NO_ENERGY = 4
 LIST_PP, LIST_PW, LIST_WW, LIST_QP, LIST_QW, LIST_QQ, LIST_QQP = range(7)
 LRF_STRIDE = 43
 E_COUNT = 7
@@ -174,8 +175,9 @@ class Qnb:
                                              out.ctypes.data_as(_PL) if counts else None))
         return out
 
-    def pot_energy_nonbonds(self, x, lambdas, md=True, qq=True, d=None):
-        """pot_energy_nonbonds(E,EQ,md) (+ nonbond_qq/nonbond_qqp when qq): returns (d, E[7], EQ[nstates][6])."""
+    def pot_energy_nonbonds(self, x, lambdas, md=True, qq=True, d=None, energies=True):
+        """pot_energy_nonbonds(E,EQ,md) (+ nonbond_qq/nonbond_qqp when qq): returns (d, E[7], EQ[nstates][6]).
+        energies=False (extension, QNB_FLAG_NO_ENERGY): the pp/pw/ww energies of this step are not needed."""
         x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
         lam = np.ascontiguousarray(lambdas, dtype=np.float64).reshape(-1)
         assert lam.size == self.sys.nstates
@@ -185,7 +187,7 @@ class Qnb:
             assert d.dtype == np.float64 and d.flags.c_contiguous
         E = np.zeros(E_COUNT)
         EQ = np.zeros(EQ_STRIDE * self.sys.nstates)
-        flags = (QNB_FLAG_MD if md else 0) | (QNB_FLAG_QQ if qq else 0)
+        flags = (QNB_FLAG_MD if md else 0) | (QNB_FLAG_QQ if qq else 0) | (0 if energies else QNB_FLAG_NO_ENERGY)
         self._check(self.lib.qnb_nonbond(self.h, _dp(x), _dp(lam), flags, _dp(d.reshape(-1)), _dp(E), _dp(EQ)))
         return d.reshape(-1, 3), E, EQ.reshape(self.sys.nstates, EQ_STRIDE)
 
@@ -230,10 +232,10 @@ class Qnb:
         self._check(self.lib.qnb_comm_init(self.h, rank, nranks, C.c_char_p(uid)))
 
     # -- measurement
-    def bench_nonbond(self, lambdas, steps: int, md=True, qq=True, flush_l2=False) -> float:
+    def bench_nonbond(self, lambdas, steps: int, md=True, qq=True, flush_l2=False, energies=True) -> float:
         lam = np.ascontiguousarray(lambdas, dtype=np.float64)
         ms = C.c_float()
-        flags = (QNB_FLAG_MD if md else 0) | (QNB_FLAG_QQ if qq else 0)
+        flags = (QNB_FLAG_MD if md else 0) | (QNB_FLAG_QQ if qq else 0) | (0 if energies else QNB_FLAG_NO_ENERGY)
         self._check(self.lib.qnb_bench_nonbond(self.h, _dp(lam), flags, steps, int(flush_l2), C.byref(ms)))
         return ms.value
 

@@ -63,6 +63,13 @@ def _run_case(q, cuts, lam, check_lists=True):
         _check_step(g, o, q, x2, lam)
         # Q-only evaluation (pot_energy(...,.false.) as called by QCP)
         _check_step(g, o, q, x2, lam, md=False)
+        # QNB_FLAG_NO_ENERGY: same gradient, LRF and Q terms; the pp/pw/ww energies are simply not produced
+        d1, E1, EQ1 = g.pot_energy_nonbonds(x2, lam)
+        d1 = d1.copy()
+        d0, E0, EQ0 = g.pot_energy_nonbonds(x2, lam, energies=False)
+        assert rel_rms(d0, d1) < 1e-9
+        assert np.all(E0[:6] == 0.0), E0
+        assert np.isclose(E0[6], E1[6], rtol=1e-12, atol=1e-12) and np.allclose(EQ0, EQ1, rtol=1e-12, atol=1e-12)
         return r
     finally:
         g.close()

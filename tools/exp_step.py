@@ -9,4 +9,5 @@ g.make_pair_lists(q.xtop, **cuts, counts=False)
 g.pot_energy_nonbonds(q.xtop, lam)
 g.bench_nonbond(lam, 50)
 print("graph=%s one_stream=%s" % (os.environ.get("QNB_NO_GRAPH", "0") != "1", os.environ.get("QNB_ONE_STREAM", "0")),
-      "step-only us:", round(g.bench_nonbond(lam, 400) / 400 * 1e3, 2), " build ms:", round(g.bench_build_lists(5) / 5, 3))
+      "step-only us:", round(g.bench_nonbond(lam, 400) / 400 * 1e3, 2), " build ms:", round(g.bench_build_lists(5) / 5, 3),
+      " step without pp/pw/ww energies us:", round(g.bench_nonbond(lam, 400, energies=False) / 400 * 1e3, 2))

@@ -12,9 +12,9 @@ tail -c 1500 $OUT/bench_$TAG.json; tail -5 $OUT/bench_$TAG.err
 (timeout 600 python bench.py --workload C5 --steps 50 --warmup 25 --no-cpu-baseline) > $OUT/bench_${TAG}_c5.json 2> $OUT/bench_${TAG}_c5.err
 (timeout 600 python bench.py --workload C3 --steps 200 --warmup 25 --no-cpu-baseline) > $OUT/bench_${TAG}_c3.json 2> $OUT/bench_${TAG}_c3.err
 (timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches_$TAG.csv \
-    python bench.py --steps 30 --warmup 3 --no-cpu-baseline) > $OUT/ncu_launch_$TAG.log 2>&1
+    python bench.py --steps 30 --warmup 3 --no-cpu-baseline --windows-per-gpu 0) > $OUT/ncu_launch_$TAG.log 2>&1
 (timeout 900 ncu --set full --clock-control none --import-source on \
     -k 'regex:k_water_force|k_solute_force|k_lrf_accumulate|k_build_rows|k_q_atom|k_q_partner' -s 12 -c 12 -f -o $OUT/prof_$TAG \
-    python bench.py --steps 30 --warmup 3 --no-cpu-baseline) > $OUT/ncu_full_$TAG.log 2>&1
+    python bench.py --steps 30 --warmup 3 --no-cpu-baseline --windows-per-gpu 0) > $OUT/ncu_full_$TAG.log 2>&1
 tail -3 $OUT/ncu_full_$TAG.log
 ls -la $OUT
