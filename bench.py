@@ -47,18 +47,20 @@ def clocks_sampler(path):
          "clocks_event_reasons.sw_power_cap")
     try:
         f = open(path, "w")
-        return subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+        return subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
                                 stdout=f, stderr=subprocess.DEVNULL), f
     except Exception:
         return None, None
 
 
-def clocks_summary(path, device):
+def clocks_summary(path, devices):
+    """Median SM clock under load and throttle reasons over the GPUs of this job (one sampler, on rank 0: every
+    nvidia-smi query takes driver locks, so one process per rank would perturb the step it is watching)."""
     sm, mx, reasons = [], 0.0, set()
     try:
         for line in open(path):
             p = [t.strip() for t in line.split(",")]
-            if len(p) < 9 or p[0] != str(device):
+            if len(p) < 9 or not p[0].isdigit() or int(p[0]) not in devices:
                 continue
             try:
                 sm.append(float(p[1]))
@@ -180,7 +182,7 @@ def main():
     # ---- device-resident throughput
     g.bench_md(lam, warmup, NBCYCLE)
     clk_path = os.path.join(ROOT, f".bench_clocks_{rank}.csv")
-    proc, fh = clocks_sampler(clk_path)
+    proc, fh = clocks_sampler(clk_path) if rank == 0 else (None, None)
     l0 = g.launch_count()
     barrier()
     ms = g.bench_md(lam, steps, NBCYCLE)
@@ -241,7 +243,7 @@ def main():
     if proc is not None:
         proc.terminate()
         fh.close()
-    clocks = clocks_summary(clk_path, dev)
+    clocks = clocks_summary(clk_path, set(range(world)) if world > 1 else {dev}) if rank == 0 else None
     try:
         os.remove(clk_path)
     except OSError:

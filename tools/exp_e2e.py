@@ -4,7 +4,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from q6_b200 import synth, engine
 q, cuts, lam = synth.config(sys.argv[1] if len(sys.argv) > 1 else "C2")
-g = engine.Qnb(q)
+g = engine.Qnb(q, device=int(os.environ.get('DEV', '0')))
 x = q.xtop.copy(); d = np.zeros((q.natom, 3))
 for k in range(30):
     if k % 25 == 0: g.make_pair_lists(x, **cuts, counts=False)
