@@ -75,7 +75,8 @@ def load_library(path: str = LIB_PATH):
     lib.qnb_build_lists.restype = C.c_int
     lib.qnb_build_lists.argtypes = [H, _PD] + [C.c_double] * 7 + [_PL]
     lib.qnb_nonbond.restype = C.c_int
-    lib.qnb_nonbond.argtypes = [H, _PD, _PD, C.c_int, _PD, _PD, _PD]
+    # per-step call: raw addresses (array.ctypes costs microseconds per argument)
+    lib.qnb_nonbond.argtypes = [H, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.qnb_list_count.restype = C.c_int
     lib.qnb_list_count.argtypes = [H, C.c_int, C.c_int, _PL]
     lib.qnb_export_list.restype = C.c_int
@@ -111,6 +112,16 @@ def load_library(path: str = LIB_PATH):
 
 def _dp(a: np.ndarray):
     return a.ctypes.data_as(_PD)
+
+
+def _addr(a: np.ndarray) -> int:
+    return a.__array_interface__["data"][0]
+
+
+def _f64(a) -> np.ndarray:
+    if isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous:
+        return a
+    return np.ascontiguousarray(a, dtype=np.float64)
 
 
 class Qnb:
@@ -178,18 +189,19 @@ class Qnb:
     def pot_energy_nonbonds(self, x, lambdas, md=True, qq=True, d=None, energies=True):
         """pot_energy_nonbonds(E,EQ,md) (+ nonbond_qq/nonbond_qqp when qq): returns (d, E[7], EQ[nstates][6]).
         energies=False (extension, QNB_FLAG_NO_ENERGY): the pp/pw/ww energies of this step are not needed."""
-        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
-        lam = np.ascontiguousarray(lambdas, dtype=np.float64).reshape(-1)
-        assert lam.size == self.sys.nstates
+        x = _f64(x)
+        lam = _f64(lambdas)
+        assert x.size == 3 * self.sys.natom and lam.size == self.sys.nstates
         if d is None:
-            d = np.zeros(3 * self.sys.natom)
+            d = np.zeros((self.sys.natom, 3))
         else:
-            assert d.dtype == np.float64 and d.flags.c_contiguous
-        E = np.zeros(E_COUNT)
-        EQ = np.zeros(EQ_STRIDE * self.sys.nstates)
+            assert d.dtype == np.float64 and d.flags.c_contiguous and d.size == 3 * self.sys.natom
+        E = np.empty(E_COUNT)
+        EQ = np.empty((self.sys.nstates, EQ_STRIDE))
         flags = (QNB_FLAG_MD if md else 0) | (QNB_FLAG_QQ if qq else 0) | (0 if energies else QNB_FLAG_NO_ENERGY)
-        self._check(self.lib.qnb_nonbond(self.h, _dp(x), _dp(lam), flags, _dp(d.reshape(-1)), _dp(E), _dp(EQ)))
-        return d.reshape(-1, 3), E, EQ.reshape(self.sys.nstates, EQ_STRIDE)
+        if self.lib.qnb_nonbond(self.h, _addr(x), _addr(lam), flags, _addr(d), _addr(E), _addr(EQ)):
+            self._check(1)
+        return d.reshape(-1, 3), E, EQ
 
     def qcp_beads(self, x_save, atoms, coord, lambdas):
         """qcp_run's bead loop (qcp.f90:319-372): for every bead, x(atoms) = x_save(atoms) + coord[bead] and
