@@ -100,7 +100,7 @@ struct qnb_handle {
     HostTables T;
     Dev D{};
     cudaStream_t st = nullptr, aux[kAux] = {};
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join[kAux] = {};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_pack = nullptr, ev_join[kAux] = {};
     cudaGraphExec_t graph[2][8] = {};   // [with copies][flags]
     bool use_graph = true, multi_stream = true;
     int water_blocks = 0, solute_blocks = 0;   // blocks per SM of the two persistent kernels (0: what the occupancy allows)
@@ -117,8 +117,9 @@ struct qnb_handle {
     DBuf<QStatic> qstatic;
     int n_qq = 0, n_qstatic = 0;
     // per-step
-    DBuf<double> x, out /* grad[3n] | E[7] | EQ[6*nstates] */, lambda, lrf;
-    double *hx = nullptr, *hout = nullptr, *hlam = nullptr;   // pinned staging
+    DBuf<double> x /* x[3n] | lambda[kMaxStates] */, out /* grad[3n] | E[7] | EQ[6*nstates] */, lrf;
+    double *hx = nullptr, *hout = nullptr, *hlam = nullptr;   // pinned staging; hlam = tail of hx: [x | lambda] goes up in one copy
+    double *lam_dev = nullptr;                                // device lambda = tail of the x buffer
     size_t nout = 0;
     int nE = 0;   // energies per slot: E[7] | EQ[6*nstates]; the output buffer holds kESlots partial copies
     // per-build
@@ -247,13 +248,15 @@ static int init_device(qnb_handle *h) {
     const size_t n3 = 3 * (size_t)s.natom;
     h->nE = QNB_E_COUNT + QNB_EQ_STRIDE * s.nstates;
     h->nout = n3 + (size_t)kESlots * h->nE;
-    if (h->x.ensure(n3) || h->out.ensure(h->nout) || h->lambda.ensure(kMaxStates) ||
+    if (h->x.ensure(n3 + kMaxStates) || h->out.ensure(h->nout) ||
         h->lrf.ensure((size_t)QNB_LRF_STRIDE * std::max(s.ncgp, 1)))
         return 1;
     CU(cudaMemset(h->lrf.p, 0, sizeof(double) * QNB_LRF_STRIDE * std::max(s.ncgp, 1)));
-    CU(cudaMallocHost(&h->hx, n3 * sizeof(double)));
+    CU(cudaMallocHost(&h->hx, (n3 + kMaxStates) * sizeof(double)));
+    h->hlam = h->hx + n3;
+    for (int k = 0; k < kMaxStates; k++) h->hlam[k] = 0.0;
+    h->lam_dev = h->x.p + n3;
     CU(cudaMallocHost(&h->hout, h->nout * sizeof(double)));
-    CU(cudaMallocHost(&h->hlam, kMaxStates * sizeof(double)));
     {
         cudaDeviceProp prop;
         CU(cudaGetDeviceProperties(&prop, h->device));
@@ -273,6 +276,7 @@ static int init_device(qnb_handle *h) {
         CU(cudaEventCreateWithFlags(&h->ev_join[k], cudaEventDisableTiming));
     }
     CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_pack, cudaEventDisableTiming));
     CU(cudaEventCreate(&h->ev0));
     CU(cudaEventCreate(&h->ev1));
     if (const char *e = getenv("QNB_NO_GRAPH")) h->use_graph = !(e[0] == '1');
@@ -602,15 +606,15 @@ static void launch_step_kernel(qnb_handle *h, int k, cudaStream_t cs, int flags)
         const int n = h->nqp + 3 * h->nqw;
         const size_t sm = sizeof(float) * (3 * (size_t)D.nqat + D.nstates);
         const dim3 pgrid(cdiv(n, 128), std::max(1, std::min(D.nqat, cdiv(6 * 148, cdiv(n, 128)))));
-        if (pbc) LAUNCH_ON(h, cs, k_q_partner<true>, pgrid, 128, sm, D, h->x.p, h->lambda.p, h->nqp, h->qp_list.p, h->qp_shift_atom.p, h->nqw, h->qw_list.p, grad);
-        else LAUNCH_ON(h, cs, k_q_partner<false>, pgrid, 128, sm, D, h->x.p, h->lambda.p, h->nqp, h->qp_list.p, h->qp_shift_atom.p, h->nqw, h->qw_list.p, grad);
+        if (pbc) LAUNCH_ON(h, cs, k_q_partner<true>, pgrid, 128, sm, D, h->x.p, h->lam_dev, h->nqp, h->qp_list.p, h->qp_shift_atom.p, h->nqw, h->qw_list.p, grad);
+        else LAUNCH_ON(h, cs, k_q_partner<false>, pgrid, 128, sm, D, h->x.p, h->lam_dev, h->nqp, h->qp_list.p, h->qp_shift_atom.p, h->nqw, h->qw_list.p, grad);
         break;
     }
     case K_QATOM: {
         const int nsite = h->nqp + 3 * h->nqw;
         const int slices = std::max(1, std::min(cdiv(nsite, 128), cdiv(4 * 148, std::max(D.nqat, 1))));
         const dim3 qgrid(D.nqat, slices);
-#define QCASE(P, N) LAUNCH_ON(h, cs, (k_q_atom<P, N>), qgrid, 128, 0, D, h->x.p, h->lambda.p, h->nqp, h->qp_list.p, h->qp_shift_atom.p, h->nqw, h->qw_list.p, grad, E, nE)
+#define QCASE(P, N) LAUNCH_ON(h, cs, (k_q_atom<P, N>), qgrid, 128, 0, D, h->x.p, h->lam_dev, h->nqp, h->qp_list.p, h->qp_shift_atom.p, h->nqw, h->qw_list.p, grad, E, nE)
         const int ns = D.nstates;
         if (pbc) { if (ns <= 1) QCASE(true, 1); else if (ns <= 2) QCASE(true, 2); else if (ns <= 4) QCASE(true, 4); else QCASE(true, 8); }
         else { if (ns <= 1) QCASE(false, 1); else if (ns <= 2) QCASE(false, 2); else if (ns <= 4) QCASE(false, 4); else QCASE(false, 8); }
@@ -618,7 +622,7 @@ static void launch_step_kernel(qnb_handle *h, int k, cudaStream_t cs, int flags)
         break;
     }
     case K_QSTATIC:
-        LAUNCH_ON(h, cs, k_qq_static, cdiv(h->n_qstatic, 128), 128, 0, h->n_qstatic, h->n_qq, h->qstatic.p, h->x.p, h->lambda.p, grad, E, nE);
+        LAUNCH_ON(h, cs, k_qq_static, cdiv(h->n_qstatic, 128), 128, 0, h->n_qstatic, h->n_qq, h->qstatic.p, h->x.p, h->lam_dev, grad, E, nE);
         break;
     case K_LRF:
         LAUNCH_ON(h, cs, k_lrf_taylor, cdiv(D.natom, 128), 128, 0, D, h->x.p, h->lrf.p, grad, E, nE);
@@ -630,8 +634,8 @@ static void launch_step_kernel(qnb_handle *h, int k, cudaStream_t cs, int flags)
 // four streams between a fork and a join event: at 12k atoms no single kernel fills 148 SMs.
 static const int kStreamOf[K_COUNT] = {0, 1, 2, 3, 4, -1};   // aux stream index, -1 = main stream
 
-static int issue_step(qnb_handle *h, int flags) {
-    CU(cudaMemsetAsync(h->out.p, 0, h->nout * sizeof(double), h->st));
+static int issue_step(qnb_handle *h, int flags, bool out_cleared = false) {
+    if (!out_cleared) CU(cudaMemsetAsync(h->out.p, 0, h->nout * sizeof(double), h->st));
     if ((flags & QNB_FLAG_MD) && h->npk > 0)
         LAUNCH(h, k_pack_coords, cdiv(h->npk, 256), 256, 0, h->npk, h->pk_atom.p, h->x.p, h->px.p, h->py.p, h->pz.p);
     CU(cudaEventRecord(h->ev_fork, h->st));
@@ -667,11 +671,20 @@ static int step_device(qnb_handle *h, int flags, bool with_copies = false) {
             const int64_t l0 = h->launches;
             CU(cudaStreamBeginCapture(h->st, cudaStreamCaptureModeThreadLocal));
             int rc = 0;
+            bool cleared = false;
             if (with_copies) {
-                rc |= cudaMemcpyAsync(h->x.p, h->hx, n3 * sizeof(double), cudaMemcpyHostToDevice, h->st) != cudaSuccess;
-                rc |= cudaMemcpyAsync(h->lambda.p, h->hlam, kMaxStates * sizeof(double), cudaMemcpyHostToDevice, h->st) != cudaSuccess;
+                if (h->multi_stream) {
+                    // clearing the output does not depend on the upload: a parallel branch of the graph
+                    rc |= cudaEventRecord(h->ev_pack, h->st) != cudaSuccess;
+                    rc |= cudaStreamWaitEvent(h->aux[4], h->ev_pack, 0) != cudaSuccess;
+                    rc |= cudaMemsetAsync(h->out.p, 0, h->nout * sizeof(double), h->aux[4]) != cudaSuccess;
+                    rc |= cudaEventRecord(h->ev_join[4], h->aux[4]) != cudaSuccess;
+                    cleared = true;
+                }
+                rc |= cudaMemcpyAsync(h->x.p, h->hx, (n3 + kMaxStates) * sizeof(double), cudaMemcpyHostToDevice, h->st) != cudaSuccess;
+                if (cleared) rc |= cudaStreamWaitEvent(h->st, h->ev_join[4], 0) != cudaSuccess;
             }
-            rc |= issue_step(h, flags);
+            rc |= issue_step(h, flags, cleared);
             if (with_copies) rc |= cudaMemcpyAsync(h->hout, h->out.p, h->nout * sizeof(double), cudaMemcpyDeviceToHost, h->st) != cudaSuccess;
             cudaError_t ce = cudaStreamEndCapture(h->st, &g);
             h->graph_launches[with_copies ? 1 : 0][flags] = (int)(h->launches - l0);
@@ -693,8 +706,7 @@ static int step_device(qnb_handle *h, int flags, bool with_copies = false) {
         return 0;
     }
     if (with_copies) {
-        CU(cudaMemcpyAsync(h->x.p, h->hx, n3 * sizeof(double), cudaMemcpyHostToDevice, h->st));
-        CU(cudaMemcpyAsync(h->lambda.p, h->hlam, kMaxStates * sizeof(double), cudaMemcpyHostToDevice, h->st));
+        CU(cudaMemcpyAsync(h->x.p, h->hx, (n3 + kMaxStates) * sizeof(double), cudaMemcpyHostToDevice, h->st));
     }
     if (issue_step(h, flags)) return 1;
     if (h->comm) {
@@ -833,7 +845,7 @@ int qnb_qcp_beads(qnb_handle *h, const double *x_save, int natq, const int32_t *
     memcpy(h->hx, x_save, n3 * sizeof(double));
     for (int k = 0; k < s.nstates; k++) h->hlam[k] = lambda[k];
     CU(cudaMemcpyAsync(h->x.p, h->hx, n3 * sizeof(double), cudaMemcpyHostToDevice, h->st));
-    CU(cudaMemcpyAsync(h->lambda.p, h->hlam, kMaxStates * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    CU(cudaMemcpyAsync(h->lam_dev, h->hlam, kMaxStates * sizeof(double), cudaMemcpyHostToDevice, h->st));
     CU(cudaMemcpyAsync(d_disp.p, coord, sizeof(double) * 3 * (size_t)natq * nbeads, cudaMemcpyHostToDevice, h->st));
     for (int b = 0; b < nbeads; b++) {
         LAUNCH(h, k_set_bead, cdiv(3 * natq, 128), 128, 0, natq, d_atoms.p, d_base.p, d_disp.p + 3 * (size_t)natq * b, h->x.p);
@@ -1091,7 +1103,7 @@ int qnb_bench_md(qnb_handle *h, const double *lambda, int flags, int steps, int 
     if (!h->lists_built) return fail("pair lists have not been built");
     CU(cudaSetDevice(h->device));
     for (int k = 0; k < h->T.s.nstates; k++) h->hlam[k] = lambda[k];
-    CU(cudaMemcpyAsync(h->lambda.p, h->hlam, h->T.s.nstates * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    CU(cudaMemcpyAsync(h->lam_dev, h->hlam, h->T.s.nstates * sizeof(double), cudaMemcpyHostToDevice, h->st));
     CU(cudaStreamSynchronize(h->st));
     CU(cudaEventRecord(h->ev0, h->st));
     for (int k = 0; k < steps; k++) {
@@ -1120,7 +1132,7 @@ int qnb_bench_nonbond(qnb_handle *h, const double *lambda, int flags, int steps,
     if (!h->lists_built) return fail("pair lists have not been built");
     CU(cudaSetDevice(h->device));
     for (int k = 0; k < h->T.s.nstates; k++) h->hlam[k] = lambda[k];
-    CU(cudaMemcpyAsync(h->lambda.p, h->hlam, h->T.s.nstates * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    CU(cudaMemcpyAsync(h->lam_dev, h->hlam, h->T.s.nstates * sizeof(double), cudaMemcpyHostToDevice, h->st));
     float total = 0.f;
     if (do_flush) {
         for (int k = 0; k < steps; k++) {
@@ -1172,7 +1184,7 @@ int qnb_bench_kernels(qnb_handle *h, const double *lambda, int flags, int reps, 
     if (!h->lists_built) { fail("pair lists have not been built"); return -1; }
     if (cudaSetDevice(h->device) != cudaSuccess) { fail("cudaSetDevice"); return -1; }
     for (int k = 0; k < h->T.s.nstates; k++) h->hlam[k] = lambda[k];
-    cudaMemcpyAsync(h->lambda.p, h->hlam, h->T.s.nstates * sizeof(double), cudaMemcpyHostToDevice, h->st);
+    cudaMemcpyAsync(h->lam_dev, h->hlam, h->T.s.nstates * sizeof(double), cudaMemcpyHostToDevice, h->st);
     std::string names;
     int n = 0;
     if (h->npk > 0) LAUNCH(h, k_pack_coords, cdiv(h->npk, 256), 256, 0, h->npk, h->pk_atom.p, h->x.p, h->px.p, h->py.p, h->pz.p);
@@ -1217,12 +1229,13 @@ int qnb_finalize(qnb_handle *h) {
     drop_graphs(h, true);
     for (int k = 0; k < kAux; k++) { if (h->aux[k]) cudaStreamDestroy(h->aux[k]); if (h->ev_join[k]) cudaEventDestroy(h->ev_join[k]); }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_pack) cudaEventDestroy(h->ev_pack);
     h->crg.release(); h->ljd.release(); h->crgf.release(); h->ljf.release(); h->ctype.release(); h->grp_of_atom.release();
     h->g_first.release(); h->g_n.release(); h->g_switch.release(); h->g_atoms.release(); h->g_nq.release();
     h->u_sw.release(); h->u_grp.release(); h->sp_off.release(); h->sp_partner.release(); h->gs_off.release();
     h->gs_atoms.release(); h->nq_off.release(); h->nq_atoms.release(); h->iqseq.release(); h->is_q.release(); h->excl.release(); h->qbonded.release();
     h->u_excl.release(); h->ljcode.release(); h->sp_code.release(); h->qp_tab.release(); h->qw_tab.release(); h->qp_tabf.release(); h->qw_tabf.release();
-    h->qstatic.release(); h->x.release(); h->out.release(); h->lambda.release(); h->lrf.release(); h->upos.release();
+    h->qstatic.release(); h->x.release(); h->out.release(); h->lrf.release(); h->upos.release();
     h->cell_of.release(); h->cell_count.release(); h->cell_start.release(); h->cell_items.release(); h->counts.release();
     h->row_tot.release(); h->row_off.release(); h->flag.release(); h->pos.release(); h->qp_list.release();
     h->qw_list.release(); h->qp_shift_atom.release(); h->rows.release(); h->flush.release();
@@ -1232,7 +1245,6 @@ int qnb_finalize(qnb_handle *h) {
     h->item_pos.release(); h->src.release(); h->cell_unsorted.release(); h->item_nq.release(); h->src_off.release();
     if (h->hx) cudaFreeHost(h->hx);
     if (h->hout) cudaFreeHost(h->hout);
-    if (h->hlam) cudaFreeHost(h->hlam);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->st) cudaStreamDestroy(h->st);
