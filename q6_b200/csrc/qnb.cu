@@ -744,12 +744,12 @@ extern "C" {
 const char *qnb_last_error(void) { return g_err.c_str(); }
 
 #ifdef QNB_TRACE
-int qnb_trace_read(unsigned long long *out) {   // [2][8192][6], experiment builds only
-    CU(cudaMemcpyFromSymbol(out, qnb::g_trace, sizeof(unsigned long long) * 2 * 8192 * 6));
+int qnb_trace_read(unsigned long long *out) {   // [2][8192][10], experiment builds only
+    CU(cudaMemcpyFromSymbol(out, qnb::g_trace, sizeof(unsigned long long) * 2 * 8192 * 10));
     return 0;
 }
 int qnb_trace_clear(void) {
-    static std::vector<unsigned long long> z(2 * 8192 * 6, 0ull);
+    static std::vector<unsigned long long> z(2 * 8192 * 10, 0ull);
     CU(cudaMemcpyToSymbol(qnb::g_trace, z.data(), sizeof(unsigned long long) * z.size()));
     return 0;
 }

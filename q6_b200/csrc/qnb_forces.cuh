@@ -15,7 +15,7 @@ namespace qnb {
 
 #ifdef QNB_TRACE
 // design experiment (tools/exp_trace.py): per-warp timestamps of the two persistent kernels
-__device__ unsigned long long g_trace[2][8192][6];
+__device__ unsigned long long g_trace[2][8192][10];   // t0 c0 c1 t1 nchunk aux | tile loads, own / mirror / other-kind chunks
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #define QTRACE(k, gw, i, v) do { if ((threadIdx.x & 31) == 0 && (gw) < 8192) g_trace[k][gw][i] = (v); } while (0)
 #else
@@ -249,8 +249,14 @@ k_water_force(Dev D, const double *__restrict__ x, const double *__restrict__ px
         for (int b = 0; b < 3; b++) { pj[b] = px[p + b]; pj[3 + b] = py[p + b]; pj[6 + b] = pz[p + b]; }
         qb = pk_q[p]; ctb = pk_ct[p];
     };
+#ifdef QNB_TRACE
+    unsigned long long tc_tile = 0, tc_own = 0, tc_mir = 0, tc_b = 0;
+#endif
     auto compute = [&](const int2 &d, uint32_t e, const double (&pj)[9], float qb, int ctb) {
         if (d.x != cur_w) {
+#ifdef QNB_TRACE
+            tc_tile++;
+#endif
             flush();
             cur_w = d.x;
             const int i0 = D.nat_solute + 3 * cur_w;
@@ -266,9 +272,15 @@ k_water_force(Dev D, const double *__restrict__ x, const double *__restrict__ px
             }
         }
         const bool valid = e != kPadEntry;
+#ifdef QNB_TRACE
+        if (d.y == kChunkB) tc_b++;
+#endif
         if (d.y == kChunkB) wp_chunk<PBC, GEOM>(D, T, valid, pj, qb, ctb, e, x, pk_atom);
         else {
             const bool own = valid && (e & kOwnerBit);
+#ifdef QNB_TRACE
+            if (__any_sync(kFull, own)) tc_own++; else tc_mir++;
+#endif
             ww_chunk<PBC, SPC>(D, T, own, want_energy && __any_sync(kFull, own), valid, pj, eel, evdw);
         }
     };
@@ -295,6 +307,9 @@ k_water_force(Dev D, const double *__restrict__ x, const double *__restrict__ px
     }
     flush();
     QTRACE(0, gw, 2, (unsigned long long)clock64()); QTRACE(0, gw, 3, gtime());
+#ifdef QNB_TRACE
+    QTRACE(0, gw, 6, tc_tile); QTRACE(0, gw, 7, tc_own); QTRACE(0, gw, 8, tc_mir); QTRACE(0, gw, 9, tc_b);
+#endif
     const double sv = warp_sum(evdw), se = warp_sum(eel);
     if (lane == 0) {
         double *E = Eslots + (size_t)(gw & (kESlots - 1)) * nE;
@@ -409,12 +424,20 @@ k_solute_force(Dev D, const double *__restrict__ x, const double *__restrict__ p
         for (int b = 0; b < 3; b++) { pj[b] = px[p + b]; pj[3 + b] = py[p + b]; pj[6 + b] = pz[p + b]; }
         qb = pk_q[p]; qbd = pk_qd[p]; ctb = pk_ct[p];
     };
+#ifdef QNB_TRACE
+    unsigned long long tc_tile = 0, tc_own = 0, tc_mir = 0, tc_b = 0;
+#endif
     // One chunk.  Straight-line over the tile atoms: atoms beyond T.nt, padding lanes and excluded pairs are computed
     // and then dropped by a select, so that the tile's pairs (and afterwards their FP64 energies) form independent
     // dependency chains the scheduler can interleave.
     auto compute = [&](const int2 &d, uint32_t e, const double (&pj)[9], float qb, double qbd, int ctb) {
         const int tile = (d.y >> 8) & 0xff;
         const int key = d.x * 256 + tile;   // (group, tile)
+#ifdef QNB_TRACE
+        if (key != cur_key) tc_tile++;
+        if ((d.y & 0xff) != kChunkA) tc_b++;
+        else if (__any_sync(kFull, e != kPadEntry && (e & kOwnerBit) != 0)) tc_own++; else tc_mir++;
+#endif
         if (key != cur_key) { flush(); load_tile(d.x, tile); cur_key = key; }
         const bool valid = e != kPadEntry;
         if ((d.y & 0xff) == kChunkA) {
@@ -534,6 +557,9 @@ k_solute_force(Dev D, const double *__restrict__ x, const double *__restrict__ p
     }
     flush();
     QTRACE(1, gw, 2, (unsigned long long)clock64()); QTRACE(1, gw, 3, gtime());
+#ifdef QNB_TRACE
+    QTRACE(1, gw, 6, tc_tile); QTRACE(1, gw, 7, tc_own); QTRACE(1, gw, 8, tc_mir); QTRACE(1, gw, 9, tc_b);
+#endif
     const double s1 = warp_sum(e_pp_el), s2 = warp_sum(e_pp_vdw), s3 = warp_sum(e_pw_el), s4 = warp_sum(e_pw_vdw);
     if (lane == 0) {
         double *E = Eslots + (size_t)(gw & (kESlots - 1)) * nE;

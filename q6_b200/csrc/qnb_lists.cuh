@@ -315,12 +315,13 @@ k_build_rows(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x, con
 __device__ __forceinline__ int unit_tiles(const Dev &D, int u, int tile_atoms) {
     return tile_atoms == 0 ? 1 : (D.g_nq[u] + tile_atoms - 1) / tile_atoms;
 }
-// Relative cost of a chunk for the static work split of the persistent force kernels (instruction-count estimates,
-// checked against per-warp timelines: tools/exp_trace.py): own = carries FP64 energies, mir = forces only,
-// b = the other unit kind.  [0] water rows, [1] solute rows.
-struct ChunkCost { int own, mir, b; };
+// Cost of a chunk and of a tile change (load of the own atoms + flush of their gradient) for the static work split of
+// the persistent force kernels, in units of 10 cycles: least-squares fit of the per-warp busy time against the per-warp
+// counts on C2 and C5 (tools/exp_trace.py, -DQNB_TRACE).  own = carries FP64 energies, mir = forces only, b = the
+// other unit kind.
+struct ChunkCost { int own, mir, b, tile; };
 __device__ __forceinline__ ChunkCost chunk_cost(int tile_atoms) {
-    return tile_atoms == 0 ? ChunkCost{50, 30, 14} : ChunkCost{38, 24, 96};
+    return tile_atoms == 0 ? ChunkCost{110, 75, 68, 80} : ChunkCost{165, 145, 510, 160};
 }
 // chunk counts of one unit's tile: own-carrying A chunks, mirror-only A chunks, B chunks (own entries come first)
 __device__ __forceinline__ void unit_chunks(const int *__restrict__ counts, int u, int &n_own, int &n_mir, int &n_b) {
@@ -339,7 +340,7 @@ __global__ void k_chunk_count(Dev D, int u0, int n, int tile_atoms, const int *_
     const ChunkCost w = chunk_cost(tile_atoms);
     const int tiles = unit_tiles(D, u, tile_atoms);
     nch[k] = tiles * (n_own + n_mir + n_b);
-    ucost[k] = tiles * (n_own * w.own + n_mir * w.mir + n_b * w.b);
+    ucost[k] = (n_own + n_mir + n_b) > 0 ? tiles * (n_own * w.own + n_mir * w.mir + n_b * w.b + w.tile) : 0;
 }
 // first chunk of every warp of a persistent force kernel: equal shares of the summed chunk costs.
 // wstart[w] = smallest chunk c whose cost prefix reaches w*total/nwarp; wstart[nwarp] = number of chunks.
@@ -359,11 +360,14 @@ __global__ void k_warp_starts(Dev D, int u0, int n, int tile_atoms, const int *_
     const ChunkCost cw = chunk_cost(tile_atoms);
     const int tiles = unit_tiles(D, u, tile_atoms);
     int c = choff[k], acc = cost_off[k];
-    for (int tile = 0; tile < tiles && acc < target; tile++)
+    for (int tile = 0; tile < tiles && acc < target && n_own + n_mir + n_b > 0; tile++) {
+        acc += cw.tile;
         for (int seg = 0; seg < 3 && acc < target; seg++) {
             const int m = seg == 0 ? n_own : seg == 1 ? n_mir : n_b, cst = seg == 0 ? cw.own : seg == 1 ? cw.mir : cw.b;
             for (int j = 0; j < m && acc < target; j++) { acc += cst; c++; }
         }
+        // the walk stopped inside this tile, or the tile is complete and c stands at the next one
+    }
     wstart[w] = min(c, choff[n]);
 }
 // one warp per unit: copy the segments into 32-entry chunks padded with 0xffffffff; descriptor = {unit - u0, kind | tile << 8}

@@ -12,7 +12,7 @@ g.make_pair_lists(q.xtop, **cuts, counts=False)
 for _ in range(5): g.pot_energy_nonbonds(q.xtop, lam)
 lib.qnb_trace_clear()
 g.pot_energy_nonbonds(q.xtop, lam)
-buf = np.zeros((2, 8192, 6), dtype=np.uint64)
+buf = np.zeros((2, 8192, 10), dtype=np.uint64)
 lib.qnb_trace_read(buf.ctypes.data_as(ctypes.c_void_p))
 t_all0 = min(int(buf[k, :, 0][buf[k, :, 0] > 0].min()) for k in range(2) if (buf[k, :, 0] > 0).any())
 for k, name in enumerate(["water", "solute"]):
@@ -32,3 +32,9 @@ for k, name in enumerate(["water", "solute"]):
     print("   warp busy cyc  : min %d p50 %d p90 %d max %d   chunks/warp min %d max %d" % (dur_cyc.min(), np.median(dur_cyc), np.percentile(dur_cyc, 90), dur_cyc.max(), nchunk.min(), nchunk.max()))
     per = dur_cyc / np.maximum(nchunk, 1)
     print("   cycles per chunk: p10 %d p50 %d p90 %d max %d" % (np.percentile(per, 10), np.median(per), np.percentile(per, 90), per.max()))
+    # least-squares cost of a tile load and of the three chunk kinds (cycles), for chunk_cost() in qnb_lists.cuh
+    A = b[done][:, 6:10].astype(float)
+    A = np.hstack([A, np.ones((A.shape[0], 1))])
+    coef, res, rk, sv = np.linalg.lstsq(A, dur_cyc.astype(float), rcond=None)
+    pred = A @ coef
+    print("   fit cycles: tile %.0f own %.0f mirror %.0f other %.0f const %.0f   rms residual %.0f (busy mean %.0f)" % (*coef, np.sqrt(np.mean((pred - dur_cyc) ** 2)), dur_cyc.mean()))
