@@ -182,6 +182,34 @@ int qnb_save_lists(qnb_handle *h);
 int qnb_restore_lists(qnb_handle *h);
 
 /*
+ * Spherical-boundary solvent restraints, the per-step host neighbours of the nonbonded call inside pot_energy
+ * (potene.f90:161-167): restrain_solvent (nonbondene.f90:6466-6543) and watpol
+ * (nonbondene.f90:6547-6746) for three-site solvents.  The parameters are what the host prepared from the input
+ * and in wat_shells (simprep.f90:4707-4891); wshell(:)%theta_corr stays host state (it changes every itdis steps,
+ * nonbondene.f90:6640-6652) and is pushed with qnb_set_theta_corr.  With QNB_FLAG_SOLVENT_RESTRAINTS (and
+ * QNB_FLAG_MD, sphere only) qnb_nonbond adds both terms to d inside the same device step -- no extra copies.
+ */
+#define QNB_MAX_SHELLS 8
+typedef struct qnb_solvent_restraints {
+    double xwcent[3];     /* solvent sphere centre */
+    double rwat;          /* solvent sphere radius */
+    double fk_wsphere;    /* radial force constant */
+    double shift;         /* q_sqrt(Boltz*Tfree/fk_wsphere), zero when fk_wsphere == 0 (nonbondene.f90:6479-6483) */
+    double Dwmz, awmz;    /* surface well */
+    double fkwpol;        /* polarisation force constant */
+    int32_t wpol_restr;   /* polarisation restraint switched on (potene.f90:167) */
+    int32_t nwpolr_shell; /* 0..QNB_MAX_SHELLS */
+    double rout[QNB_MAX_SHELLS], dr[QNB_MAX_SHELLS], cstb[QNB_MAX_SHELLS]; /* SHELL_TYPE, globals.f90:165 */
+} qnb_solvent_restraints;
+#define QNB_FLAG_SOLVENT_RESTRAINTS 16
+int qnb_set_solvent_restraints(qnb_handle *h, const qnb_solvent_restraints *p);
+int qnb_set_theta_corr(qnb_handle *h, const double *theta_corr /* [nwpolr_shell] */);
+/* Results of the last qnb_nonbond that carried QNB_FLAG_SOLVENT_RESTRAINTS: E[0] = E%restraint%solvent_radial,
+ * E[1] = E%restraint%water_pol; per shell the sum of theta over its molecules (avtdum, nonbondene.f90:6668) and
+ * n_insh, from which the host keeps wshell%avtheta / avn_insh (L6738-6741). */
+int qnb_last_restraints(qnb_handle *h, double E[2], double *shell_theta_sum, int32_t *shell_n);
+
+/*
  * qcp_run (qcp.f90:319-372, 478-525): for every bead i the coordinates of the path-integral atoms are set to
  * x(iqseq(qcp_atom(j))) = x_save(..) + qcp_coord(j,i) and pot_energy(qcp_E,qcp_EQ,.false.) is called; only the
  * per-state Q energies are used.  This entry evaluates the nonbonded part of all beads in one call (one upload of

@@ -55,6 +55,29 @@ interface
         type(c_ptr), value :: handle
         integer(c_int) :: rc
     end function
+    ! restrain_solvent / watpol (nonbondene.f90:6466-6746) inside the device step: type(qnb_solvent_restraints) mirrors
+    ! include/qnb.h field for field (xwcent(3), rwat, fk_wsphere, shift, Dwmz, awmz, fkwpol, wpol_restr, nwpolr_shell,
+    ! rout(8), dr(8), cstb(8)); the wrapper of watpol keeps wshell%avtheta / avn_insh / theta_corr on the host
+    function qnb_set_solvent_restraints(handle, p) bind(c, name='qnb_set_solvent_restraints') result(rc)
+        import :: c_int, c_ptr
+        type(c_ptr), value :: handle
+        type(c_ptr), value :: p                           ! c_loc of a type(qnb_solvent_restraints)
+        integer(c_int) :: rc
+    end function
+    function qnb_set_theta_corr(handle, theta_corr) bind(c, name='qnb_set_theta_corr') result(rc)
+        import :: c_int, c_ptr, c_double
+        type(c_ptr), value :: handle
+        real(c_double), intent(in) :: theta_corr(*)       ! wshell(1:nwpolr_shell)%theta_corr
+        integer(c_int) :: rc
+    end function
+    function qnb_last_restraints(handle, E, shell_theta_sum, shell_n) bind(c, name='qnb_last_restraints') result(rc)
+        import :: c_int, c_ptr, c_double, c_int32_t
+        type(c_ptr), value :: handle
+        real(c_double), intent(out) :: E(2)               ! solvent_radial, water_pol
+        real(c_double), intent(out) :: shell_theta_sum(*) ! avtdum per shell
+        integer(c_int32_t), intent(out) :: shell_n(*)     ! wshell(:)%n_insh
+        integer(c_int) :: rc
+    end function
     ! qcp_run (qcp.f90:319-372, 478-525): all beads of one sampling step in one call
     function qnb_qcp_beads(handle, x_save, natq, atoms, nbeads, coord, lambda, EQ_out) bind(c, name='qnb_qcp_beads') result(rc)
         import :: c_int, c_ptr, c_double, c_int32_t

@@ -55,6 +55,8 @@ def load():
     lib.qo_make_qconn.restype = None
     lib.qo_make_qconn.argtypes = [C.c_int, C.c_int, C.c_int, _PI, _PI, C.c_int, _PI, C.c_int, _PI, _PI, C.c_int,
                                   _PI, _PI, _PI]
+    lib.qo_solvent_restraints.restype = C.c_int
+    lib.qo_solvent_restraints.argtypes = [C.POINTER(qnb_system), C.c_void_p, _PD, _PD, C.c_int, _PD, _PD, _PD, _PI]
     lib.qo_time_decomposed.restype = C.c_double
     lib.qo_time_decomposed.argtypes = [C.POINTER(qnb_system), _PD, _PD, C.c_int, _PD, _PD, C.c_int, C.c_int,
                                        C.c_int, _PD, _PD, _PD, _PD]
@@ -128,6 +130,24 @@ class Oracle:
         out = np.zeros((self.sys.ncgp, 43))
         self.lib.qo_export_lrf(self.h, _dp(out))
         return out
+
+
+def solvent_restraints(qsys: QSystem, params, theta_corr, x, md=True):
+    """restrain_solvent + watpol (nonbondene.f90:6466-6746): returns (d, E[2], shell_theta_sum, shell_n)."""
+    lib = load()
+    st, keep = qsys.as_struct()
+    x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+    tc = np.ascontiguousarray(theta_corr, dtype=np.float64)
+    d = np.zeros(3 * qsys.natom)
+    E = np.zeros(2)
+    n = max(int(params.nwpolr_shell), 1)
+    ts, ns = np.zeros(n), np.zeros(n, np.int32)
+    rc = lib.qo_solvent_restraints(C.byref(st), C.addressof(params), _dp(tc), _dp(x), int(md), _dp(d), _dp(E), _dp(ts),
+                                   ns.ctypes.data_as(_PI))
+    if rc:
+        raise RuntimeError("qo_solvent_restraints failed")
+    k = int(params.nwpolr_shell)
+    return d.reshape(-1, 3), E, ts[:k], ns[:k]
 
 
 def make_qconn(nstates, nat_solute, nqat, iqseq, iqatom, bnd_solute, qbnd_ij, qbnd_cod, exspec_ij, exspec_flag):

@@ -1761,3 +1761,127 @@ double qo_time_decomposed(const qnb_system *sys, const double *x, const double *
     free(w); free(th);
     return wall;
 }
+
+
+/* ------------------------------------------------------------------------------------------------
+ * restrain_solvent (nonbondene.f90:6466-6543, solv_atom == 3 branch) and watpol (L6547-6746, SPC/TIP3P branch).
+ * Literal restatement, same loop orders.
+ */
+int qo_solvent_restraints(const qnb_system *sys, const qnb_solvent_restraints *p, const double *theta_corr,
+                          const double *x, int md, double *d, double E[2], double *shell_theta_sum, int32_t *shell_n) {
+    const int nwat = sys->nwat, ns = sys->nat_solute, nsh = p->nwpolr_shell;
+    const double pi = 3.14159265358979323846;
+    /* ---- restrain_solvent L6486-6509: iw over the water charge groups, i = switch atom = O */
+    for (int iw = 0; iw < nwat; iw++) {
+        const int i = ns + 3 * iw;                       /* 0-based O */
+        if (sys->excl[i]) continue;
+        /* q_dist5(xwcent, x(i)): vec = x(i) - xwcent? -- math.f90: q_dist5(a,b)%vec = b - a */
+        const double vx = x[3 * i] - p->xwcent[0], vy = x[3 * i + 1] - p->xwcent[1], vz = x[3 * i + 2] - p->xwcent[2];
+        const double r2 = vx * vx + vy * vy + vz * vz;
+        const double b = sqrt(r2);
+        const double db = b - (p->rwat - p->shift);
+        double erst, dv;
+        if (db > 0.0) {
+            erst = 0.5 * p->fk_wsphere * db * db - p->Dwmz;
+            dv = p->fk_wsphere * db / b;
+        } else if (b > 0.0) {
+            const double fexp = exp(p->awmz * db);
+            erst = p->Dwmz * (fexp * fexp - 2.0 * fexp);
+            dv = -2.0 * p->Dwmz * p->awmz * (fexp - fexp * fexp) / b;
+        } else { dv = 0.0; erst = 0.0; }
+        d[3 * i] += vx * dv; d[3 * i + 1] += vy * dv; d[3 * i + 2] += vz * dv;
+        E[0] += erst;
+    }
+    for (int is = 0; is < nsh; is++) { shell_theta_sum[is] = 0.0; shell_n[is] = 0; }
+    if (!p->wpol_restr || nsh <= 0) return 0;
+    /* ---- watpol */
+    double *theta = (double *)calloc((size_t)(nwat > 0 ? nwat : 1), sizeof(double));
+    double *tdum = (double *)calloc((size_t)(nwat > 0 ? nwat : 1), sizeof(double));
+    int *list_sh = (int *)malloc(sizeof(int) * (size_t)(nwat > 0 ? nwat : 1) * (size_t)nsh);
+    int *nsort = (int *)malloc(sizeof(int) * (size_t)(nwat > 0 ? nwat : 1) * (size_t)nsh);
+    int *n_insh = (int *)calloc((size_t)nsh, sizeof(int));
+    if (!theta || !tdum || !list_sh || !nsort || !n_insh) return 1;
+    /* the sort happens "if (md)"; with md false the previous step's nsort would be reused -- potene only calls watpol
+     * with in_md true (potene.f90:161-167), so that branch is not restated */
+    (void)md;
+    for (int iw = 0; iw < nwat; iw++) {                  /* L6565-6625 */
+        theta[iw] = 0.0;
+        const int i = ns + 3 * iw;
+        if (sys->excl[i]) continue;
+        double rmu[3], rcu[3];
+        for (int c = 0; c < 3; c++) rmu[c] = (x[3 * (i + 1) + c] + x[3 * (i + 2) + c]) - x[3 * i + c] * 2.0;
+        const double rm = sqrt(rmu[0] * rmu[0] + rmu[1] * rmu[1] + rmu[2] * rmu[2]);
+        for (int c = 0; c < 3; c++) rmu[c] /= rm;
+        for (int c = 0; c < 3; c++) rcu[c] = x[3 * i + c] - p->xwcent[c];
+        const double rc = sqrt(rcu[0] * rcu[0] + rcu[1] * rcu[1] + rcu[2] * rcu[2]);
+        for (int c = 0; c < 3; c++) rcu[c] /= rc;
+        double scp = rmu[0] * rcu[0] + rmu[1] * rcu[1] + rmu[2] * rcu[2];
+        if (scp > 1.0) scp = 1.0;
+        if (scp < -1.0) scp = -1.0;
+        theta[iw] = acos(scp);
+        tdum[iw] = theta[iw];
+        if (rc > p->rout[nsh - 1] - p->dr[nsh - 1]) {
+            int is;
+            for (is = nsh; is >= 2; is--)                /* do is = nwpolr_shell, 2, -1; exit if rc <= rout(is) */
+                if (rc <= p->rout[is - 1]) break;
+            /* after a completed Fortran loop is == 1 */
+            list_sh[(size_t)(is - 1) * nwat + n_insh[is - 1]] = iw;
+            n_insh[is - 1]++;
+        }
+    }
+    for (int is = 0; is < nsh; is++) {                   /* L6627-6643: selection sort by theta, first minimum wins */
+        int jmin = 0;
+        for (int il = 0; il < n_insh[is]; il++) {
+            double tmin = 2.0 * pi;
+            for (int jl = 0; jl < n_insh[is]; jl++) {
+                const int jw = list_sh[(size_t)is * nwat + jl];
+                if (tdum[jw] < tmin) { jmin = jw; tmin = theta[jw]; }
+            }
+            nsort[(size_t)is * nwat + il] = jmin;
+            tdum[jmin] = 99999.0;
+        }
+    }
+    for (int is = 0; is < nsh; is++) {                   /* L6663-6742 */
+        if (n_insh[is] == 0) continue;
+        double avtdum = 0.0;
+        for (int il = 1; il <= n_insh[is]; il++) {
+            const int iw = nsort[(size_t)is * nwat + il - 1];
+            const double arg = 1.0 + (1.0 - 2.0 * (double)il) / (double)n_insh[is];
+            double theta0 = acos(arg);
+            theta0 = theta0 - 3.0 * sin(theta0) * p->cstb[is] / 2.0;
+            if (theta0 < 0.0) theta0 = 0.0;
+            if (theta0 > pi) theta0 = pi;
+            avtdum += theta[iw];
+            const double dth = theta[iw] - theta0 + theta_corr[is];
+            E[1] += 0.5 * p->fkwpol * dth * dth;
+            const double dv = p->fkwpol * dth;
+            const int i = ns + 3 * iw;
+            double rmu[3], rcu[3];
+            for (int c = 0; c < 3; c++) rmu[c] = (x[3 * (i + 1) + c] + x[3 * (i + 2) + c]) - x[3 * i + c] * 2.0;
+            const double rm = sqrt(rmu[0] * rmu[0] + rmu[1] * rmu[1] + rmu[2] * rmu[2]);
+            for (int c = 0; c < 3; c++) rmu[c] /= rm;
+            for (int c = 0; c < 3; c++) rcu[c] = x[3 * i + c] - p->xwcent[c];
+            const double rc = sqrt(rcu[0] * rcu[0] + rcu[1] * rcu[1] + rcu[2] * rcu[2]);
+            for (int c = 0; c < 3; c++) rcu[c] /= rc;
+            double scp = rmu[0] * rcu[0] + rmu[1] * rcu[1] + rmu[2] * rcu[2];
+            if (scp > 1.0) scp = 1.0;
+            if (scp < -1.0) scp = -1.0;
+            double f0 = sin(acos(scp));
+            if (fabs(f0) < 1.0e-10) f0 = 1.0e-10;   /* QREAL_EPS, sizes.f90:50 (double precision build) */
+            f0 = -1.0 / f0;
+            f0 = dv * f0;
+            for (int c = 0; c < 3; c++) {
+                const double f1 = ((rcu[c] - rmu[c] * scp) * (-2.0)) / rm;
+                const double f3 = (rcu[c] - rmu[c] * scp) / rm;
+                const double f2 = (rmu[c] - rcu[c] * scp) / rc;
+                d[3 * i + c] += (f1 + f2) * f0;
+                d[3 * (i + 1) + c] += f3 * f0;
+                d[3 * (i + 2) + c] += f3 * f0;
+            }
+        }
+        shell_theta_sum[is] = avtdum;
+        shell_n[is] = n_insh[is];
+    }
+    free(theta); free(tdum); free(list_sh); free(nsort); free(n_insh);
+    return 0;
+}

@@ -48,6 +48,11 @@ int qo_list_count(qo_state *s, int which, int state, int64_t *n);
 int qo_export_list(qo_state *s, int which, int state, int32_t *ij, double *params, int64_t capacity);
 int qo_export_lrf(qo_state *s, double *lrf);
 
+/* restrain_solvent (nonbondene.f90:6466-6543) + watpol (L6547-6746) for solv_atom == 3; d +=, E[2] +=;
+ * shell_theta_sum / shell_n as qnb_last_restraints.  md as watpol's argument. */
+int qo_solvent_restraints(const qnb_system *sys, const qnb_solvent_restraints *p, const double *theta_corr,
+                          const double *x, int md, double *d, double E[2], double *shell_theta_sum, int32_t *shell_n);
+
 /* make_qconn / find_bonded (nonbondene.f90:3087-3187), for validating the host-side port.
  * bnd: [3*nbonds_solute] i,j,cod; qbnd_ij: [2*nqbond]; qbnd_cod: [nqbond*nstates] (bond,state);
  * exspec_ij: [2*nexspec]; exspec_flag: [nexspec*nstates]; out: qconn[nstates*nat_solute*nqat] */

@@ -101,11 +101,11 @@ struct qnb_handle {
     Dev D{};
     cudaStream_t st = nullptr, aux[kAux] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_pack = nullptr, ev_join[kAux] = {};
-    cudaGraphExec_t graph[2][8] = {};   // [with copies][flags]
+    cudaGraphExec_t graph[2][16] = {};   // [with copies][graph_index(flags)]
     bool use_graph = true, multi_stream = true;
     int water_blocks = 0, solute_blocks = 0;   // blocks per SM of the two persistent kernels (0: what the occupancy allows)
-    int graph_launches[2][8] = {};
-    bool graph_dirty[2][8] = {{true, true, true, true, true, true, true, true}, {true, true, true, true, true, true, true, true}};
+    int graph_launches[2][16] = {};
+    bool graph_dirty[2][16] = {};   // set by drop_graphs at init
     // static device tables
     DBuf<double> crg, ljd;
     DBuf<float> crgf, ljf;
@@ -142,6 +142,13 @@ struct qnb_handle {
     DBuf<int2> wdesc, sdesc;
     DBuf<uint32_t> wrow, srow;
     DBuf<uint16_t> sspec;
+    // solvent restraints (restrain_solvent / watpol)
+    qnb_solvent_restraints rst{};
+    bool rst_set = false;
+    double theta_corr[QNB_MAX_SHELLS] = {};
+    DBuf<double> wp_theta;
+    DBuf<int> wp_shell_n, wp_shell_list;
+    double last_rst[kRstOut] = {};
     // MC_volume: state of the last list build and its saved copy
     DBuf<double> x_saved, lrf_saved;
     std::vector<double> hx_build, hx_saved;
@@ -247,7 +254,7 @@ static int init_device(qnb_handle *h) {
     }
     const size_t n3 = 3 * (size_t)s.natom;
     h->nE = QNB_E_COUNT + QNB_EQ_STRIDE * s.nstates;
-    h->nout = n3 + (size_t)kESlots * h->nE;
+    h->nout = n3 + (size_t)kESlots * h->nE + kRstOut;   // [gradient | energy slots | restraint results]
     if (h->x.ensure(n3 + kMaxStates) || h->out.ensure(h->nout) ||
         h->lrf.ensure((size_t)QNB_LRF_STRIDE * std::max(s.ncgp, 1)))
         return 1;
@@ -292,7 +299,7 @@ static int init_device(qnb_handle *h) {
 // re-instantiated (hundreds).
 static void drop_graphs(qnb_handle *h, bool destroy = false) {
     for (int c = 0; c < 2; c++)
-        for (int f = 0; f < 8; f++) {
+        for (int f = 0; f < 16; f++) {
             h->graph_dirty[c][f] = true;
             if (destroy && h->graph[c][f]) { cudaGraphExecDestroy(h->graph[c][f]); h->graph[c][f] = nullptr; }
         }
@@ -538,9 +545,9 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
 }
 
 // ------------------------------------------------------------------ one nonbonded evaluation on device
-enum StepKernel { K_WATER = 0, K_SOLUTE, K_QPARTNER, K_QATOM, K_QSTATIC, K_LRF, K_COUNT };
+enum StepKernel { K_WATER = 0, K_SOLUTE, K_QPARTNER, K_QATOM, K_QSTATIC, K_LRF, K_RST, K_COUNT };
 static const char *kStepKernelNames[K_COUNT] = {"k_water_force", "k_solute_force", "k_q_partner", "k_q_atom",
-                                                "k_qq_static", "k_lrf_taylor"};
+                                                "k_qq_static", "k_lrf_taylor", "k_solvent_restraints"};
 
 constexpr int kFlagEnergiesOnly = 8;   // internal (QCP beads): no kernel whose only product is a gradient
 
@@ -554,6 +561,8 @@ static bool step_kernel_active(const qnb_handle *h, int k, int flags) {
     case K_QATOM: return D.nqat > 0 && (h->nqp + h->nqw) > 0;
     case K_QSTATIC: return (flags & QNB_FLAG_QQ) && h->T.s.is_master && h->n_qstatic > 0;
     case K_LRF: return md && D.use_LRF;
+    // restrain_solvent / watpol: only in_md and only for the sphere (potene.f90:161-167)
+    case K_RST: return md && (flags & QNB_FLAG_SOLVENT_RESTRAINTS) && h->rst_set && !D.use_PBC && D.nwat > 0;
     }
     return false;
 }
@@ -627,12 +636,29 @@ static void launch_step_kernel(qnb_handle *h, int k, cudaStream_t cs, int flags)
     case K_LRF:
         LAUNCH_ON(h, cs, k_lrf_taylor, cdiv(D.natom, 128), 128, 0, D, h->x.p, h->lrf.p, grad, E, nE);
         break;
+    case K_RST: {
+        const qnb_solvent_restraints &r = h->rst;
+        RstPar P{};
+        for (int c = 0; c < 3; c++) P.xw[c] = r.xwcent[c];
+        P.rsurf = r.rwat - r.shift; P.fk = r.fk_wsphere; P.Dwmz = r.Dwmz; P.awmz = r.awmz; P.fkwpol = r.fkwpol;
+        P.nsh = r.wpol_restr ? r.nwpolr_shell : 0;
+        P.wpol = P.nsh > 0;
+        for (int k = 0; k < P.nsh; k++) { P.rout[k] = r.rout[k]; P.cstb[k] = r.cstb[k]; P.tcorr[k] = h->theta_corr[k]; }
+        if (P.nsh > 0) P.rin_last = r.rout[P.nsh - 1] - r.dr[P.nsh - 1];
+        double *rst = h->out.p + 3 * (size_t)D.natom + (size_t)kESlots * nE;
+        if (P.wpol) cudaMemsetAsync(h->wp_shell_n.p, 0, sizeof(int) * QNB_MAX_SHELLS, cs);
+        LAUNCH_ON(h, cs, k_rst_theta, cdiv(D.nwat, 128), 128, 0, D, P, h->x.p, grad, rst, h->wp_theta.p, h->wp_shell_n.p, h->wp_shell_list.p);
+        if (P.wpol)
+            LAUNCH_ON(h, cs, k_rst_watpol, dim3(cdiv(D.nwat, 128), P.nsh), 128, 0, D, P, h->x.p, grad, rst, h->wp_theta.p,
+                      h->wp_shell_n.p, h->wp_shell_list.p);
+        break;
+    }
     }
 }
 
 // The kernels of one evaluation are independent (they only meet in atomicAdd on grad/E), so they are issued on
 // four streams between a fork and a join event: at 12k atoms no single kernel fills 148 SMs.
-static const int kStreamOf[K_COUNT] = {0, 1, 2, 3, 4, -1};   // aux stream index, -1 = main stream
+static const int kStreamOf[K_COUNT] = {0, 1, 2, 3, 4, -1, 4};   // aux stream index, -1 = main stream
 
 static int issue_step(qnb_handle *h, int flags, bool out_cleared = false) {
     if (!out_cleared) CU(cudaMemsetAsync(h->out.p, 0, h->nout * sizeof(double), h->st));
@@ -640,7 +666,7 @@ static int issue_step(qnb_handle *h, int flags, bool out_cleared = false) {
         LAUNCH(h, k_pack_coords, cdiv(h->npk, 256), 256, 0, h->npk, h->pk_atom.p, h->x.p, h->px.p, h->py.p, h->pz.p);
     CU(cudaEventRecord(h->ev_fork, h->st));
     bool used[kAux] = {};
-    static const int kOrder[K_COUNT] = {K_SOLUTE, K_QPARTNER, K_QATOM, K_WATER, K_QSTATIC, K_LRF};
+    static const int kOrder[K_COUNT] = {K_SOLUTE, K_QPARTNER, K_QATOM, K_WATER, K_QSTATIC, K_RST, K_LRF};
     for (int o = 0; o < K_COUNT; o++) {
         const int k = kOrder[o];
         if (!step_kernel_active(h, k, flags)) continue;
@@ -662,10 +688,11 @@ static int issue_step(qnb_handle *h, int flags, bool out_cleared = false) {
 static int step_device(qnb_handle *h, int flags, bool with_copies = false) {
     const size_t n3 = 3 * (size_t)h->T.s.natom;
     const bool graphable = h->use_graph && !h->comm;
-    flags &= 7;
+    flags &= (QNB_FLAG_MD | QNB_FLAG_QQ | QNB_FLAG_NO_ENERGY | QNB_FLAG_SOLVENT_RESTRAINTS);
+    const int gi = (flags & 7) | ((flags & QNB_FLAG_SOLVENT_RESTRAINTS) ? 8 : 0);
     if (graphable) {
-        cudaGraphExec_t &ge = h->graph[with_copies ? 1 : 0][flags];
-        bool &dirty = h->graph_dirty[with_copies ? 1 : 0][flags];
+        cudaGraphExec_t &ge = h->graph[with_copies ? 1 : 0][gi];
+        bool &dirty = h->graph_dirty[with_copies ? 1 : 0][gi];
         if (!ge || dirty) {
             cudaGraph_t g = nullptr;
             const int64_t l0 = h->launches;
@@ -687,7 +714,7 @@ static int step_device(qnb_handle *h, int flags, bool with_copies = false) {
             rc |= issue_step(h, flags, cleared);
             if (with_copies) rc |= cudaMemcpyAsync(h->hout, h->out.p, h->nout * sizeof(double), cudaMemcpyDeviceToHost, h->st) != cudaSuccess;
             cudaError_t ce = cudaStreamEndCapture(h->st, &g);
-            h->graph_launches[with_copies ? 1 : 0][flags] = (int)(h->launches - l0);
+            h->graph_launches[with_copies ? 1 : 0][gi] = (int)(h->launches - l0);
             h->launches = l0;
             if (rc || ce != cudaSuccess || !g) return fail("CUDA graph capture of the step failed: %s", cudaGetErrorString(ce));
             bool updated = false;
@@ -702,7 +729,7 @@ static int step_device(qnb_handle *h, int flags, bool with_copies = false) {
             dirty = false;
         }
         CU(cudaGraphLaunch(ge, h->st));
-        h->launches += h->graph_launches[with_copies ? 1 : 0][flags];
+        h->launches += h->graph_launches[with_copies ? 1 : 0][gi];
         return 0;
     }
     if (with_copies) {
@@ -783,6 +810,38 @@ int qnb_update_box(qnb_handle *h, const double boxlength[3], const double inv_bo
     for (int d = 0; d < 3; d++) { h->box[d] = boxlength[d]; h->inv_box[d] = inv_boxl[d]; }
     refresh_dev(h);
     drop_graphs(h);
+    return 0;
+}
+
+int qnb_set_solvent_restraints(qnb_handle *h, const qnb_solvent_restraints *p) {
+    if (!h || !p) return fail("null argument");
+    if (p->nwpolr_shell < 0 || p->nwpolr_shell > QNB_MAX_SHELLS) return fail("qnb_set_solvent_restraints: %d shells (max %d)", (int)p->nwpolr_shell, QNB_MAX_SHELLS);
+    if (h->T.s.use_PBC) return fail("qnb_set_solvent_restraints: restrain_solvent/watpol belong to the spherical boundary (potene.f90:161)");
+    CU(cudaSetDevice(h->device));
+    const int nw = std::max(h->T.s.nwat, 1);
+    if (h->wp_theta.ensure(nw) || h->wp_shell_n.ensure(QNB_MAX_SHELLS) || h->wp_shell_list.ensure((size_t)nw * QNB_MAX_SHELLS)) return 1;
+    h->rst = *p;
+    h->rst_set = true;
+    drop_graphs(h);   // the parameters are baked into the captured launches
+    return 0;
+}
+
+int qnb_set_theta_corr(qnb_handle *h, const double *theta_corr) {
+    if (!h || !theta_corr) return fail("null argument");
+    if (!h->rst_set) return fail("qnb_set_theta_corr: call qnb_set_solvent_restraints first");
+    for (int k = 0; k < h->rst.nwpolr_shell; k++) h->theta_corr[k] = theta_corr[k];
+    drop_graphs(h);
+    return 0;
+}
+
+int qnb_last_restraints(qnb_handle *h, double E[2], double *shell_theta_sum, int32_t *shell_n) {
+    if (!h || !E || !shell_theta_sum || !shell_n) return fail("null argument");
+    if (!h->rst_set) return fail("qnb_last_restraints: no solvent restraints set");
+    E[0] = h->last_rst[0]; E[1] = h->last_rst[1];
+    for (int k = 0; k < h->rst.nwpolr_shell; k++) {
+        shell_theta_sum[k] = h->last_rst[2 + k];
+        shell_n[k] = (int32_t)h->last_rst[2 + QNB_MAX_SHELLS + k];
+    }
     return 0;
 }
 
@@ -912,6 +971,7 @@ int qnb_nonbond(qnb_handle *h, const double *x, const double *lambda, int flags,
         for (int sl = 0; sl < kESlots; sl++) e += h->hout[n3 + (size_t)sl * h->nE + k];
         if (k < QNB_E_COUNT) E_out[k] = e; else EQ_out[k - QNB_E_COUNT] = e;
     }
+    for (int k = 0; k < kRstOut; k++) h->last_rst[k] = h->hout[n3 + (size_t)kESlots * h->nE + k];
     const auto t4 = clk::now();
     auto sec = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double>(b - a).count(); };
     h->t_stage_in = sec(t0, t1); h->t_issue = sec(t1, t2); h->t_wait = sec(t2, t3); h->t_add_out = sec(t3, t4);
@@ -1240,7 +1300,7 @@ int qnb_finalize(qnb_handle *h) {
     h->row_tot.release(); h->row_off.release(); h->flag.release(); h->pos.release(); h->qp_list.release();
     h->qw_list.release(); h->qp_shift_atom.release(); h->rows.release(); h->flush.release();
     h->pk_atom.release(); h->pk_ct.release(); h->pk_q.release(); h->pk_qd.release(); h->px.release(); h->py.release(); h->pz.release();
-    h->nch.release(); h->choff.release(); h->ucost.release(); h->cost_off.release(); h->wstart_w.release(); h->wstart_s.release(); h->wdesc.release(); h->wrow.release(); h->sdesc.release(); h->srow.release(); h->sspec.release(); h->x_saved.release(); h->lrf_saved.release();
+    h->nch.release(); h->choff.release(); h->ucost.release(); h->cost_off.release(); h->wstart_w.release(); h->wstart_s.release(); h->wdesc.release(); h->wrow.release(); h->sdesc.release(); h->srow.release(); h->sspec.release(); h->x_saved.release(); h->lrf_saved.release(); h->wp_theta.release(); h->wp_shell_n.release(); h->wp_shell_list.release();
     h->item_posf.release();
     h->item_pos.release(); h->src.release(); h->cell_unsorted.release(); h->item_nq.release(); h->src_off.release();
     if (h->hx) cudaFreeHost(h->hx);

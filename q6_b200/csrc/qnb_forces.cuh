@@ -807,4 +807,116 @@ __global__ void k_lrf_taylor(Dev D, const double *__restrict__ x, const double *
     if ((threadIdx.x & 31) == 0 && e != 0.0) atomicAdd(&E[QNB_E_LRF], e);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Spherical-boundary solvent restraints, FP64 throughout.
+// rst = [E solvent_radial, E water_pol, theta sums per shell (QNB_MAX_SHELLS), n_insh per shell (QNB_MAX_SHELLS)]
+struct RstPar {
+    double xw[3], rsurf /* rwat - shift */, fk, Dwmz, awmz, fkwpol;
+    int wpol, nsh;
+    double rout[QNB_MAX_SHELLS], cstb[QNB_MAX_SHELLS], tcorr[QNB_MAX_SHELLS];
+    double rin_last;   // rout(nsh) - dr(nsh): inner edge of the innermost shell
+};
+constexpr int kRstOut = 2 + 2 * QNB_MAX_SHELLS;
+
+// water-molecule geometry of watpol (L6583-6620): unit dipole direction rmu, its length rm, unit radial vector rcu, rc
+struct WpGeom { double rmu[3], rcu[3], rm, rc, scp; };
+__device__ __forceinline__ WpGeom wp_geom(const double *__restrict__ x, int i, const RstPar &P) {
+    WpGeom g;
+#pragma unroll
+    for (int c = 0; c < 3; c++) g.rmu[c] = (x[3 * (i + 1) + c] + x[3 * (i + 2) + c]) - x[3 * i + c] * 2.0;
+    g.rm = sqrt(g.rmu[0] * g.rmu[0] + g.rmu[1] * g.rmu[1] + g.rmu[2] * g.rmu[2]);
+#pragma unroll
+    for (int c = 0; c < 3; c++) { g.rmu[c] /= g.rm; g.rcu[c] = x[3 * i + c] - P.xw[c]; }
+    g.rc = sqrt(g.rcu[0] * g.rcu[0] + g.rcu[1] * g.rcu[1] + g.rcu[2] * g.rcu[2]);
+#pragma unroll
+    for (int c = 0; c < 3; c++) g.rcu[c] /= g.rc;
+    g.scp = fmin(1.0, fmax(-1.0, g.rmu[0] * g.rcu[0] + g.rmu[1] * g.rcu[1] + g.rmu[2] * g.rcu[2]));
+    return g;
+}
+
+// restrain_solvent (nonbondene.f90:6486-6509) and the first loop of watpol (L6565-6625): theta and shell membership
+__global__ void k_rst_theta(Dev D, RstPar P, const double *__restrict__ x, double *__restrict__ grad,
+                            double *__restrict__ rst, double *__restrict__ theta, int *__restrict__ shell_n,
+                            int *__restrict__ shell_list) {
+    const int iw = blockIdx.x * blockDim.x + threadIdx.x;
+    double erst = 0.0;
+    if (iw < D.nwat) {
+        const int i = D.nat_solute + 3 * iw;
+        if (!D.excl[i]) {
+            const double vx = x[3 * i] - P.xw[0], vy = x[3 * i + 1] - P.xw[1], vz = x[3 * i + 2] - P.xw[2];
+            const double b = sqrt(vx * vx + vy * vy + vz * vz);
+            const double db = b - P.rsurf;
+            double dv = 0.0;
+            if (db > 0.0) {
+                erst = 0.5 * P.fk * db * db - P.Dwmz;
+                dv = P.fk * db / b;
+            } else if (b > 0.0) {
+                const double fexp = exp(P.awmz * db);
+                erst = P.Dwmz * (fexp * fexp - 2.0 * fexp);
+                dv = -2.0 * P.Dwmz * P.awmz * (fexp - fexp * fexp) / b;
+            }
+            atomicAdd(&grad[3 * i], vx * dv); atomicAdd(&grad[3 * i + 1], vy * dv); atomicAdd(&grad[3 * i + 2], vz * dv);
+            if (P.wpol) {
+                const WpGeom g = wp_geom(x, i, P);
+                theta[iw] = acos(g.scp);
+                if (g.rc > P.rin_last) {
+                    int is = P.nsh;                       // do is = nwpolr_shell, 2, -1; if (rc <= rout(is)) exit
+                    while (is >= 2 && !(g.rc <= P.rout[is - 1])) is--;
+                    const int pos = atomicAdd(&shell_n[is - 1], 1);
+                    shell_list[(size_t)(is - 1) * D.nwat + pos] = iw;
+                }
+            }
+        } else if (P.wpol) theta[iw] = 0.0;
+    }
+    erst = warp_sum(erst);
+    if ((threadIdx.x & 31) == 0 && erst != 0.0) atomicAdd(&rst[0], erst);
+}
+
+// second part of watpol (L6627-6742): rank of the molecule inside its shell by (theta, molecule number) -- the order the
+// reference's selection sort produces --, target angle of that rank, energy and gradient.  blockIdx.y = shell.
+__global__ void k_rst_watpol(Dev D, RstPar P, const double *__restrict__ x, double *__restrict__ grad,
+                             double *__restrict__ rst, const double *__restrict__ theta,
+                             const int *__restrict__ shell_n, const int *__restrict__ shell_list) {
+    const int is = blockIdx.y, n = shell_n[is];
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int *lst = shell_list + (size_t)is * D.nwat;
+    double e = 0.0, tsum = 0.0;
+    if (j < n) {
+        const int iw = lst[j];
+        const double th = theta[iw];
+        int il = 1;
+        for (int k = 0; k < n; k++) {
+            const int jw = lst[k];
+            const double t = theta[jw];
+            il += (t < th) || (t == th && jw < iw);
+        }
+        const double pi = 3.14159265358979323846;
+        const double arg = 1.0 + (1.0 - 2.0 * (double)il) / (double)n;
+        double theta0 = acos(arg);
+        theta0 = theta0 - 3.0 * sin(theta0) * P.cstb[is] / 2.0;
+        theta0 = fmin(pi, fmax(0.0, theta0));
+        const double dth = th - theta0 + P.tcorr[is];
+        e = 0.5 * P.fkwpol * dth * dth;
+        tsum = th;
+        const double dv = P.fkwpol * dth;
+        const int i = D.nat_solute + 3 * iw;
+        const WpGeom g = wp_geom(x, i, P);
+        double f0 = sin(acos(g.scp));
+        if (fabs(f0) < 1.0e-10) f0 = 1.0e-10;   // QREAL_EPS (sizes.f90:50)
+        f0 = dv * (-1.0 / f0);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const double f1 = ((g.rcu[c] - g.rmu[c] * g.scp) * (-2.0)) / g.rm;
+            const double f3 = (g.rcu[c] - g.rmu[c] * g.scp) / g.rm;
+            const double f2 = (g.rmu[c] - g.rcu[c] * g.scp) / g.rc;
+            atomicAdd(&grad[3 * i + c], (f1 + f2) * f0);
+            atomicAdd(&grad[3 * (i + 1) + c], f3 * f0);
+            atomicAdd(&grad[3 * (i + 2) + c], f3 * f0);
+        }
+    }
+    e = warp_sum(e); tsum = warp_sum(tsum);
+    if ((threadIdx.x & 31) == 0 && (e != 0.0 || tsum != 0.0)) { atomicAdd(&rst[1], e); atomicAdd(&rst[2 + is], tsum); }
+    if (j == 0) rst[2 + QNB_MAX_SHELLS + is] = (double)n;
+}
+
 }  // namespace qnb

@@ -21,6 +21,50 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libqnb.so")
 QNB_FLAG_MD = 1
 QNB_FLAG_QQ = 2
 QNB_FLAG_NO_ENERGY = 4
+QNB_FLAG_SOLVENT_RESTRAINTS = 16
+MAX_SHELLS = 8
+
+
+class SolventRestraints(C.Structure):
+    """qnb_solvent_restraints (include/qnb.h): restrain_solvent / watpol parameters as the host prepares them."""
+    _fields_ = [("xwcent", C.c_double * 3), ("rwat", C.c_double), ("fk_wsphere", C.c_double), ("shift", C.c_double),
+                ("Dwmz", C.c_double), ("awmz", C.c_double), ("fkwpol", C.c_double), ("wpol_restr", C.c_int32),
+                ("nwpolr_shell", C.c_int32), ("rout", C.c_double * MAX_SHELLS), ("dr", C.c_double * MAX_SHELLS),
+                ("cstb", C.c_double * MAX_SHELLS)]
+
+
+def wat_shells(xwcent, rwat, fk_wsphere=60.0, Dwmz=None, awmz=None, Tfree=300.0, wpol_restr=True, fkwpol=20.0,
+               wpolr_layer=3.0, drout=0.5, crgQtot=0.0, rho_wat=0.0335, mu_w=None, dielectric=80.0):
+    """The host-side preparation of the solvent restraint parameters: defaults of md.f90 (fk_wsphere 60, fkwpol 20,
+    Dwmz = 0.26 exp(-0.19 (rwat-15)) + 0.74, awmz = 0.2/(1+exp(0.4 (rwat-25))) + 0.3 (simprep.f90:4659-4671),
+    wpolr_layer 3, drout 0.5) and wat_shells (simprep.f90:4745-4886:
+    shells of width drout, 2 drout, ... from the surface inwards; cstb = crgQtot (1-1/eps) / (rho mu_w 4 pi rshell^2))."""
+    import math
+    p = SolventRestraints()
+    for c in range(3):
+        p.xwcent[c] = float(xwcent[c])
+    p.rwat, p.fk_wsphere, p.fkwpol = float(rwat), float(fk_wsphere), float(fkwpol)
+    p.awmz = float(awmz) if awmz is not None else 0.2 / (1.0 + math.exp(0.4 * (rwat - 25.0))) + 0.3
+    p.Dwmz = float(Dwmz) if Dwmz is not None else 0.26 * math.exp(-0.19 * (rwat - 15.0)) + 0.74
+    boltz = 0.001986
+    p.shift = math.sqrt(boltz * Tfree / fk_wsphere) if fk_wsphere != 0.0 else 0.0
+    p.wpol_restr = 1 if wpol_restr else 0
+    drs = wpolr_layer / drout
+    nsh = int(-0.5 + math.sqrt(2.0 * drs + 0.25))
+    assert nsh <= MAX_SHELLS
+    p.nwpolr_shell = nsh if wpol_restr else 0
+    if mu_w is None:
+        mu_w = 0.834 * 0.9572 * math.cos(math.radians(104.52) / 2.0)   # -chg_solv(1) * bnd0 * cos(ang0/2), TIP3P
+    rout = rwat
+    eps = 1.0 - 1.0 / dielectric
+    for i in range(nsh):
+        dr = drout * (i + 1)
+        ri = rout - dr
+        rshell = (0.5 * (rout ** 3 + ri ** 3)) ** (1.0 / 3.0)
+        p.rout[i], p.dr[i] = rout, dr
+        p.cstb[i] = crgQtot * eps / (rho_wat * mu_w * 4.0 * math.pi * rshell ** 2)
+        rout -= dr
+    return p
 LIST_PP, LIST_PW, LIST_WW, LIST_QP, LIST_QW, LIST_QQ, LIST_QQP = range(7)
 LRF_STRIDE = 43
 E_COUNT = 7
@@ -70,6 +114,12 @@ def load_library(path: str = LIB_PATH):
     for fn in (lib.qnb_save_lists, lib.qnb_restore_lists):
         fn.restype = C.c_int
         fn.argtypes = [H]
+    lib.qnb_set_solvent_restraints.restype = C.c_int
+    lib.qnb_set_solvent_restraints.argtypes = [H, C.POINTER(SolventRestraints)]
+    lib.qnb_set_theta_corr.restype = C.c_int
+    lib.qnb_set_theta_corr.argtypes = [H, _PD]
+    lib.qnb_last_restraints.restype = C.c_int
+    lib.qnb_last_restraints.argtypes = [H, _PD, _PD, _PI]
     lib.qnb_qcp_beads.restype = C.c_int
     lib.qnb_qcp_beads.argtypes = [H, _PD, C.c_int, _PI, C.c_int, _PD, _PD, _PD]
     lib.qnb_build_lists.restype = C.c_int
@@ -186,7 +236,29 @@ class Qnb:
                                              out.ctypes.data_as(_PL) if counts else None))
         return out
 
-    def pot_energy_nonbonds(self, x, lambdas, md=True, qq=True, d=None, energies=True):
+    def set_solvent_restraints(self, params: SolventRestraints, theta_corr=None):
+        """Hand restrain_solvent / watpol to the device step (pot_energy, potene.f90:161-167)."""
+        self._check(self.lib.qnb_set_solvent_restraints(self.h, C.byref(params)))
+        self._nshell = int(params.nwpolr_shell)
+        if theta_corr is not None:
+            self.set_theta_corr(theta_corr)
+
+    def set_theta_corr(self, theta_corr):
+        tc = np.ascontiguousarray(theta_corr, dtype=np.float64)
+        assert tc.size >= getattr(self, "_nshell", 0)
+        self._check(self.lib.qnb_set_theta_corr(self.h, _dp(tc)))
+
+    def last_restraints(self):
+        """(E[solvent_radial, water_pol], per-shell sum of theta, per-shell n_insh) of the last step with restraints."""
+        n = max(getattr(self, "_nshell", 0), 1)
+        E = np.zeros(2)
+        ts = np.zeros(n)
+        ns = np.zeros(n, np.int32)
+        self._check(self.lib.qnb_last_restraints(self.h, _dp(E), _dp(ts), ns.ctypes.data_as(_PI)))
+        k = getattr(self, "_nshell", 0)
+        return E, ts[:k], ns[:k]
+
+    def pot_energy_nonbonds(self, x, lambdas, md=True, qq=True, d=None, energies=True, restraints=False):
         """pot_energy_nonbonds(E,EQ,md) (+ nonbond_qq/nonbond_qqp when qq): returns (d, E[7], EQ[nstates][6]).
         energies=False (extension, QNB_FLAG_NO_ENERGY): the pp/pw/ww energies of this step are not needed."""
         x = _f64(x)
@@ -198,7 +270,8 @@ class Qnb:
             assert d.dtype == np.float64 and d.flags.c_contiguous and d.size == 3 * self.sys.natom
         E = np.empty(E_COUNT)
         EQ = np.empty((self.sys.nstates, EQ_STRIDE))
-        flags = (QNB_FLAG_MD if md else 0) | (QNB_FLAG_QQ if qq else 0) | (0 if energies else QNB_FLAG_NO_ENERGY)
+        flags = ((QNB_FLAG_MD if md else 0) | (QNB_FLAG_QQ if qq else 0) | (0 if energies else QNB_FLAG_NO_ENERGY)
+                 | (QNB_FLAG_SOLVENT_RESTRAINTS if restraints else 0))
         if self.lib.qnb_nonbond(self.h, _addr(x), _addr(lam), flags, _addr(d), _addr(E), _addr(EQ)):
             self._check(1)
         return d.reshape(-1, 3), E, EQ

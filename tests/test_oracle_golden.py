@@ -147,3 +147,29 @@ def test_fixture_files_reparse_identically():
     g, _, _, _ = golden_system("c1_sph")
     for k in ("crg", "iac", "cgp", "cgpatom", "listex", "list14", "qconn", "qcrg", "xtop"):
         assert np.array_equal(np.asarray(getattr(q, k)), np.asarray(getattr(g, k))), k
+
+
+def test_solvent_restraint_oracle_is_a_gradient():
+    """restrain_solvent + watpol restatement (nonbondene.f90:6466-6746): d must be the gradient of the two energies
+    (central differences; the shell ranking is fixed for the tiny displacement) and the shell lists must be the
+    molecules of each radial band."""
+    import numpy as np
+    from oracle import pyoracle
+    from q6_b200 import synth, engine
+    q = synth.solvated_sphere(radius=15.0, core_radius=8.0, nq=8, nstates=1, seed=31)
+    par = engine.wat_shells(q.xpcent, 14.6, crgQtot=1.0)
+    tc = np.array([0.01, -0.02, 0.03])
+    x = q.xtop
+    d, E, ts, ns = pyoracle.solvent_restraints(q, par, tc, x)
+    rng = np.random.default_rng(1)
+    dx = rng.normal(0, 1, x.shape)
+    h = 1e-6
+    Ep = pyoracle.solvent_restraints(q, par, tc, x + h * dx)[1].sum()
+    Em = pyoracle.solvent_restraints(q, par, tc, x - h * dx)[1].sum()
+    assert abs((Ep - Em) / (2 * h) - (d * dx).sum()) <= 1e-6 * abs((d * dx).sum())
+    # shell populations = oxygens in the radial bands (excluded waters never counted)
+    O = x[q.nat_solute::3]
+    rc = np.linalg.norm(O - np.asarray(q.xpcent), axis=1)
+    rin = par.rout[par.nwpolr_shell - 1] - par.dr[par.nwpolr_shell - 1]
+    assert ns.sum() == int((rc > rin).sum())
+    assert ns[2] == int(((rc > rin) & (rc <= par.rout[2])).sum())

@@ -293,3 +293,49 @@ def test_unwrapped_periodic_coordinates(case):
     finally:
         g.close()
         o.close()
+
+
+@pytest.mark.parametrize("case", [c for c in small_systems() if c[0] in ("sph_fep2", "sph_excl_shell", "sph_noq")],
+                         ids=lambda c: c[0])
+def test_solvent_restraints(case):
+    """restrain_solvent + watpol (nonbondene.f90:6466-6746) inside the device step: gradient and energies of the step
+    with QNB_FLAG_SOLVENT_RESTRAINTS = nonbonded oracle + restraint oracle; shell populations exact."""
+    from oracle import pyoracle
+    from oracle.pyoracle import Oracle
+    from q6_b200.engine import Qnb, wat_shells
+    name, q, cuts, lam = case
+    lam = np.array(lam)
+    rwat = float(np.linalg.norm(q.xtop[q.nat_solute:] - np.asarray(q.xpcent), axis=1).max()) - 0.3
+    par = wat_shells(q.xpcent, rwat, crgQtot=-1.0)
+    tc = np.array([0.02, -0.01, 0.005][:par.nwpolr_shell])
+    g, o = Qnb(q), Oracle(q)
+    try:
+        rng = np.random.default_rng(4)
+        x = q.xtop + rng.normal(0, 0.03, q.xtop.shape)
+        g.make_pair_lists(x, **cuts)
+        o.make_pair_lists(x, **cuts)
+        g.set_solvent_restraints(par, tc)
+        dg, Eg, EQg = g.pot_energy_nonbonds(x, lam, restraints=True)
+        Er, ts, ns = g.last_restraints()
+        do, Eo, EQo = o.pot_energy_nonbonds(x, lam)
+        dr, Ero, tso, nso = pyoracle.solvent_restraints(q, par, tc, x)
+        assert ns.sum() > 0 and np.array_equal(ns, nso), (ns, nso)
+        assert rel_rms(dg, do + dr) <= FORCE_REL_RMS
+        # the restraint part on its own (FP64 on both sides)
+        d0, _, _ = g.pot_energy_nonbonds(x, lam)
+        assert rel_rms(dg - d0, dr) <= 1e-6
+        assert_energy("solvent_radial", Er[0], Ero[0])
+        assert_energy("water_pol", Er[1], Ero[1])
+        assert np.allclose(ts, tso, rtol=1e-12)
+        for k, nm in enumerate(("pp.el", "pp.vdw", "pw.el", "pw.vdw", "ww.el", "ww.vdw", "LRF")):
+            assert_energy(nm, Eg[k], Eo[k])
+        # new theta_corr (every itdis steps on the host) reaches the captured step
+        tc2 = tc + 0.1
+        g.set_theta_corr(tc2)
+        dg2, _, _ = g.pot_energy_nonbonds(x, lam, restraints=True)
+        dr2, Ero2, _, _ = pyoracle.solvent_restraints(q, par, tc2, x)
+        assert rel_rms(dg2 - d0, dr2) <= 1e-6
+        assert_energy("water_pol (new theta_corr)", g.last_restraints()[0][1], Ero2[1])
+    finally:
+        g.close()
+        o.close()
