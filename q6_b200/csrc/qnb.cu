@@ -146,7 +146,7 @@ struct qnb_handle {
     qnb_solvent_restraints rst{};
     bool rst_set = false;
     double theta_corr[QNB_MAX_SHELLS] = {};
-    DBuf<double> wp_theta;
+    DBuf<double> wp_theta, wp_shell_theta;
     DBuf<int> wp_shell_n, wp_shell_list;
     double last_rst[kRstOut] = {};
     // MC_volume: state of the last list build and its saved copy
@@ -276,7 +276,7 @@ static int init_device(qnb_handle *h) {
         // are the critical path of a solvated protein, the water rows fill the SMs behind them
         int lo = 0, hi = 0;
         CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // hi = numerically lowest = most urgent
-        static const int kRank[5] = {2, 0, 1, 1, 3};      // water, solute, q_partner, q_atom, qq_static
+        static const int kRank[5] = {2, 0, 1, 1, 0};      // water, solute, q_partner, q_atom, the tiny kernels (static lists, restraints)
         int pr = std::min(lo, hi + (getenv("QNB_NO_PRIORITY") ? 0 : kRank[k < 5 ? k : 4]));
         CU(cudaStreamCreateWithPriority(&h->aux[k], cudaStreamNonBlocking, pr));
     }
@@ -562,7 +562,8 @@ static bool step_kernel_active(const qnb_handle *h, int k, int flags) {
     case K_QSTATIC: return (flags & QNB_FLAG_QQ) && h->T.s.is_master && h->n_qstatic > 0;
     case K_LRF: return md && D.use_LRF;
     // restrain_solvent / watpol: only in_md and only for the sphere (potene.f90:161-167)
-    case K_RST: return md && (flags & QNB_FLAG_SOLVENT_RESTRAINTS) && h->rst_set && !D.use_PBC && D.nwat > 0;
+    // (one rank only when the step is sharded: every rank would add the same term to the summed gradient)
+    case K_RST: return md && (flags & QNB_FLAG_SOLVENT_RESTRAINTS) && h->rst_set && !D.use_PBC && D.nwat > 0 && h->T.s.is_master;
     }
     return false;
 }
@@ -646,11 +647,11 @@ static void launch_step_kernel(qnb_handle *h, int k, cudaStream_t cs, int flags)
         for (int k = 0; k < P.nsh; k++) { P.rout[k] = r.rout[k]; P.cstb[k] = r.cstb[k]; P.tcorr[k] = h->theta_corr[k]; }
         if (P.nsh > 0) P.rin_last = r.rout[P.nsh - 1] - r.dr[P.nsh - 1];
         double *rst = h->out.p + 3 * (size_t)D.natom + (size_t)kESlots * nE;
-        if (P.wpol) cudaMemsetAsync(h->wp_shell_n.p, 0, sizeof(int) * QNB_MAX_SHELLS, cs);
-        LAUNCH_ON(h, cs, k_rst_theta, cdiv(D.nwat, 128), 128, 0, D, P, h->x.p, grad, rst, h->wp_theta.p, h->wp_shell_n.p, h->wp_shell_list.p);
+        int *shell_cnt = reinterpret_cast<int *>(rst + 2 + 2 * QNB_MAX_SHELLS);   // zeroed with the output buffer
+        LAUNCH_ON(h, cs, k_rst_theta, cdiv(D.nwat, 128), 128, 0, D, P, h->x.p, grad, rst, h->wp_theta.p, shell_cnt, h->wp_shell_list.p, h->wp_shell_theta.p);
         if (P.wpol)
-            LAUNCH_ON(h, cs, k_rst_watpol, dim3(cdiv(D.nwat, 128), P.nsh), 128, 0, D, P, h->x.p, grad, rst, h->wp_theta.p,
-                      h->wp_shell_n.p, h->wp_shell_list.p);
+            LAUNCH_ON(h, cs, k_rst_watpol, dim3(std::min(cdiv(D.nwat, 4), 192), P.nsh), 128, 0, D, P, h->x.p, grad, rst, h->wp_theta.p,
+                      shell_cnt, h->wp_shell_list.p, h->wp_shell_theta.p);
         break;
     }
     }
@@ -666,7 +667,7 @@ static int issue_step(qnb_handle *h, int flags, bool out_cleared = false) {
         LAUNCH(h, k_pack_coords, cdiv(h->npk, 256), 256, 0, h->npk, h->pk_atom.p, h->x.p, h->px.p, h->py.p, h->pz.p);
     CU(cudaEventRecord(h->ev_fork, h->st));
     bool used[kAux] = {};
-    static const int kOrder[K_COUNT] = {K_SOLUTE, K_QPARTNER, K_QATOM, K_WATER, K_QSTATIC, K_RST, K_LRF};
+    static const int kOrder[K_COUNT] = {K_RST, K_QSTATIC, K_SOLUTE, K_QPARTNER, K_QATOM, K_WATER, K_LRF};
     for (int o = 0; o < K_COUNT; o++) {
         const int k = kOrder[o];
         if (!step_kernel_active(h, k, flags)) continue;
@@ -819,7 +820,8 @@ int qnb_set_solvent_restraints(qnb_handle *h, const qnb_solvent_restraints *p) {
     if (h->T.s.use_PBC) return fail("qnb_set_solvent_restraints: restrain_solvent/watpol belong to the spherical boundary (potene.f90:161)");
     CU(cudaSetDevice(h->device));
     const int nw = std::max(h->T.s.nwat, 1);
-    if (h->wp_theta.ensure(nw) || h->wp_shell_n.ensure(QNB_MAX_SHELLS) || h->wp_shell_list.ensure((size_t)nw * QNB_MAX_SHELLS)) return 1;
+    if (h->wp_theta.ensure(nw) || h->wp_shell_n.ensure(QNB_MAX_SHELLS) || h->wp_shell_list.ensure((size_t)nw * QNB_MAX_SHELLS) ||
+        h->wp_shell_theta.ensure((size_t)nw * QNB_MAX_SHELLS)) return 1;
     h->rst = *p;
     h->rst_set = true;
     drop_graphs(h);   // the parameters are baked into the captured launches
@@ -1300,7 +1302,7 @@ int qnb_finalize(qnb_handle *h) {
     h->row_tot.release(); h->row_off.release(); h->flag.release(); h->pos.release(); h->qp_list.release();
     h->qw_list.release(); h->qp_shift_atom.release(); h->rows.release(); h->flush.release();
     h->pk_atom.release(); h->pk_ct.release(); h->pk_q.release(); h->pk_qd.release(); h->px.release(); h->py.release(); h->pz.release();
-    h->nch.release(); h->choff.release(); h->ucost.release(); h->cost_off.release(); h->wstart_w.release(); h->wstart_s.release(); h->wdesc.release(); h->wrow.release(); h->sdesc.release(); h->srow.release(); h->sspec.release(); h->x_saved.release(); h->lrf_saved.release(); h->wp_theta.release(); h->wp_shell_n.release(); h->wp_shell_list.release();
+    h->nch.release(); h->choff.release(); h->ucost.release(); h->cost_off.release(); h->wstart_w.release(); h->wstart_s.release(); h->wdesc.release(); h->wrow.release(); h->sdesc.release(); h->srow.release(); h->sspec.release(); h->x_saved.release(); h->lrf_saved.release(); h->wp_theta.release(); h->wp_shell_n.release(); h->wp_shell_list.release(); h->wp_shell_theta.release();
     h->item_posf.release();
     h->item_pos.release(); h->src.release(); h->cell_unsorted.release(); h->item_nq.release(); h->src_off.release();
     if (h->hx) cudaFreeHost(h->hx);

@@ -809,14 +809,15 @@ __global__ void k_lrf_taylor(Dev D, const double *__restrict__ x, const double *
 
 // ------------------------------------------------------------------------------------------------
 // Spherical-boundary solvent restraints, FP64 throughout.
-// rst = [E solvent_radial, E water_pol, theta sums per shell (QNB_MAX_SHELLS), n_insh per shell (QNB_MAX_SHELLS)]
+// rst = [E solvent_radial, E water_pol, theta sums per shell (QNB_MAX_SHELLS), n_insh per shell (QNB_MAX_SHELLS),
+//        QNB_MAX_SHELLS int32 append counters of the shell lists]: part of the step's output buffer, cleared with it
 struct RstPar {
     double xw[3], rsurf /* rwat - shift */, fk, Dwmz, awmz, fkwpol;
     int wpol, nsh;
     double rout[QNB_MAX_SHELLS], cstb[QNB_MAX_SHELLS], tcorr[QNB_MAX_SHELLS];
     double rin_last;   // rout(nsh) - dr(nsh): inner edge of the innermost shell
 };
-constexpr int kRstOut = 2 + 2 * QNB_MAX_SHELLS;
+constexpr int kRstOut = 2 + 2 * QNB_MAX_SHELLS + QNB_MAX_SHELLS / 2;   // + the shell counters (int32), cleared with the buffer
 
 // water-molecule geometry of watpol (L6583-6620): unit dipole direction rmu, its length rm, unit radial vector rcu, rc
 struct WpGeom { double rmu[3], rcu[3], rm, rc, scp; };
@@ -837,7 +838,7 @@ __device__ __forceinline__ WpGeom wp_geom(const double *__restrict__ x, int i, c
 // restrain_solvent (nonbondene.f90:6486-6509) and the first loop of watpol (L6565-6625): theta and shell membership
 __global__ void k_rst_theta(Dev D, RstPar P, const double *__restrict__ x, double *__restrict__ grad,
                             double *__restrict__ rst, double *__restrict__ theta, int *__restrict__ shell_n,
-                            int *__restrict__ shell_list) {
+                            int *__restrict__ shell_list, double *__restrict__ shell_theta) {
     const int iw = blockIdx.x * blockDim.x + threadIdx.x;
     double erst = 0.0;
     if (iw < D.nwat) {
@@ -864,6 +865,7 @@ __global__ void k_rst_theta(Dev D, RstPar P, const double *__restrict__ x, doubl
                     while (is >= 2 && !(g.rc <= P.rout[is - 1])) is--;
                     const int pos = atomicAdd(&shell_n[is - 1], 1);
                     shell_list[(size_t)(is - 1) * D.nwat + pos] = iw;
+                    shell_theta[(size_t)(is - 1) * D.nwat + pos] = theta[iw];   // compact copy for the ranking
                 }
             }
         } else if (P.wpol) theta[iw] = 0.0;
@@ -876,28 +878,36 @@ __global__ void k_rst_theta(Dev D, RstPar P, const double *__restrict__ x, doubl
 // reference's selection sort produces --, target angle of that rank, energy and gradient.  blockIdx.y = shell.
 __global__ void k_rst_watpol(Dev D, RstPar P, const double *__restrict__ x, double *__restrict__ grad,
                              double *__restrict__ rst, const double *__restrict__ theta,
-                             const int *__restrict__ shell_n, const int *__restrict__ shell_list) {
+                             const int *__restrict__ shell_n, const int *__restrict__ shell_list,
+                             const double *__restrict__ shell_theta) {
+    // one WARP per shell member (grid-stride over the members): its lanes share the n comparisons of the ranking (a
+    // thread per member walks them serially: 600 dependent iterations on a handful of warps took 43 us)
     const int is = blockIdx.y, n = shell_n[is];
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5, nwarp = gridDim.x * wpb;
     const int *lst = shell_list + (size_t)is * D.nwat;
+    const double *sth = shell_theta + (size_t)is * D.nwat;
     double e = 0.0, tsum = 0.0;
-    if (j < n) {
+    for (int j = blockIdx.x * wpb + (threadIdx.x >> 5); j < n; j += nwarp) {
         const int iw = lst[j];
-        const double th = theta[iw];
-        int il = 1;
-        for (int k = 0; k < n; k++) {
-            const int jw = lst[k];
-            const double t = theta[jw];
-            il += (t < th) || (t == th && jw < iw);
+        const double th = sth[j];
+        int cnt = 0;
+        for (int k = lane; k < n; k += 32) {
+            const double t = sth[k];
+            cnt += (int)(t < th) | ((int)(t == th) & (int)(lst[k] < iw));
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(kFull, cnt, o);
+        if (lane != 0) continue;
+        const int il = cnt + 1;
         const double pi = 3.14159265358979323846;
         const double arg = 1.0 + (1.0 - 2.0 * (double)il) / (double)n;
         double theta0 = acos(arg);
         theta0 = theta0 - 3.0 * sin(theta0) * P.cstb[is] / 2.0;
         theta0 = fmin(pi, fmax(0.0, theta0));
         const double dth = th - theta0 + P.tcorr[is];
-        e = 0.5 * P.fkwpol * dth * dth;
-        tsum = th;
+        e += 0.5 * P.fkwpol * dth * dth;
+        tsum += th;
         const double dv = P.fkwpol * dth;
         const int i = D.nat_solute + 3 * iw;
         const WpGeom g = wp_geom(x, i, P);
@@ -914,9 +924,16 @@ __global__ void k_rst_watpol(Dev D, RstPar P, const double *__restrict__ x, doub
             atomicAdd(&grad[3 * (i + 2) + c], f3 * f0);
         }
     }
-    e = warp_sum(e); tsum = warp_sum(tsum);
-    if ((threadIdx.x & 31) == 0 && (e != 0.0 || tsum != 0.0)) { atomicAdd(&rst[1], e); atomicAdd(&rst[2 + is], tsum); }
-    if (j == 0) rst[2 + QNB_MAX_SHELLS + is] = (double)n;
+    // block sum of the warps' terms, then one pair of atomics per block
+    __shared__ double red[2][32];
+    if (lane == 0) { red[0][threadIdx.x >> 5] = e; red[1][threadIdx.x >> 5] = tsum; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double es = 0.0, ts = 0.0;
+        for (int k = 0; k < wpb; k++) { es += red[0][k]; ts += red[1][k]; }
+        if (es != 0.0 || ts != 0.0) { atomicAdd(&rst[1], es); atomicAdd(&rst[2 + is], ts); }
+        if (blockIdx.x == 0) rst[2 + QNB_MAX_SHELLS + is] = (double)n;
+    }
 }
 
 }  // namespace qnb

@@ -317,10 +317,11 @@ class Qnb:
         self._check(self.lib.qnb_comm_init(self.h, rank, nranks, C.c_char_p(uid)))
 
     # -- measurement
-    def bench_nonbond(self, lambdas, steps: int, md=True, qq=True, flush_l2=False, energies=True) -> float:
+    def bench_nonbond(self, lambdas, steps: int, md=True, qq=True, flush_l2=False, energies=True, restraints=False) -> float:
         lam = np.ascontiguousarray(lambdas, dtype=np.float64)
         ms = C.c_float()
-        flags = (QNB_FLAG_MD if md else 0) | (QNB_FLAG_QQ if qq else 0) | (0 if energies else QNB_FLAG_NO_ENERGY)
+        flags = ((QNB_FLAG_MD if md else 0) | (QNB_FLAG_QQ if qq else 0) | (0 if energies else QNB_FLAG_NO_ENERGY)
+                 | (QNB_FLAG_SOLVENT_RESTRAINTS if restraints else 0))
         self._check(self.lib.qnb_bench_nonbond(self.h, _dp(lam), flags, steps, int(flush_l2), C.byref(ms)))
         return ms.value
 
@@ -336,11 +337,11 @@ class Qnb:
         self._check(self.lib.qnb_bench_build_lists(self.h, reps, C.byref(ms)))
         return ms.value
 
-    def bench_kernels(self, lambdas, reps: int, md=True, qq=True, flush_l2=False) -> dict:
+    def bench_kernels(self, lambdas, reps: int, md=True, qq=True, flush_l2=False, restraints=False) -> dict:
         lam = np.ascontiguousarray(lambdas, dtype=np.float64)
         names = C.create_string_buffer(4096)
         ms = (C.c_float * 64)()
-        flags = (QNB_FLAG_MD if md else 0) | (QNB_FLAG_QQ if qq else 0)
+        flags = (QNB_FLAG_MD if md else 0) | (QNB_FLAG_QQ if qq else 0) | (QNB_FLAG_SOLVENT_RESTRAINTS if restraints else 0)
         n = self.lib.qnb_bench_kernels(self.h, _dp(lam), flags, reps, int(flush_l2), names, 4096, ms, 64)
         if n < 0:
             raise QnbError(self.lib.qnb_last_error().decode())

@@ -16,6 +16,7 @@ if not q.use_PBC and q.nwat > 0:
     g.set_solvent_restraints(engine.wat_shells(q.xpcent, rw, crgQtot=-1.0), np.zeros(8))
     x = q.xtop.copy(); d = np.zeros((q.natom, 3))
     import time
+    print('   device step us with restraints:', round(g.bench_nonbond(lam, 400, restraints=True) / 400 * 1e3, 2), {k: round(v * 1e3, 1) for k, v in g.bench_kernels(lam, 20, restraints=True).items()})
     for r in (False, True):
         for _ in range(50): g.pot_energy_nonbonds(x, lam, d=d, restraints=r)
         t = time.perf_counter()
