@@ -313,6 +313,15 @@ def main():
                                           "fep_windows_per_hour": 3600.0 * agg / STEPS_PER_WINDOW,
                                           "note": "same end-to-end path as e2e (host buffers, list build every "
                                                   f"{NBCYCLE} steps), {kwin} handles and host threads per GPU"}
+        # ---- optional paths, reported next to the headline (never part of it)
+        ext = {"device_step_ms": g.bench_nonbond(lam, 200) / 200,
+               "device_step_ms_no_pp_pw_ww_energies": g.bench_nonbond(lam, 200, energies=False) / 200}
+        if not q.use_PBC and q.nwat > 0:
+            from q6_b200.engine import wat_shells
+            rw = float(np.linalg.norm(q.xtop[q.nat_solute:] - np.asarray(q.xpcent), axis=1).max())
+            g.set_solvent_restraints(wat_shells(q.xpcent, rw, crgQtot=-1.0), np.zeros(8))
+            ext["device_step_ms_with_solvent_restraints"] = g.bench_nonbond(lam, 200, restraints=True) / 200
+        line["extensions"] = ext
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
             t_cpu, nsteps, _ = cpu_reference(q, cuts, lam, threads, target_seconds=12.0)
