@@ -147,6 +147,7 @@ struct qnb_handle {
     bool rst_set = false;
     double theta_corr[QNB_MAX_SHELLS] = {};
     DBuf<double> wp_theta, wp_shell_theta;
+    DBuf<double> lrf_mom;   // [nunit][20] unexpanded LRF moments (all-pairs kernel)
     DBuf<int> wp_shell_n, wp_shell_list;
     double last_rst[kRstOut] = {};
     // MC_volume: state of the last list build and its saved copy
@@ -433,6 +434,19 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
             const int rr[3] = {h->lrf_reach.x, h->lrf_reach.y, h->lrf_reach.z};
             for (int d = 0; d < 3; d++) rowshift = rowshift && 2 * (rr[d] + 1) <= G.n[d];
             const bool general = D.any_atom || D.sharded;
+            // sphere, switching-atom lists, unsharded, every cell within the LRF reach: all-pairs tiling
+            int gmax = 0;
+            for (int gn : h->T.g_n) gmax = std::max(gmax, gn);
+            bool allpairs = !G.periodic && !general && gmax <= kLrfTileAtoms && !getenv("QNB_LRF_GENERAL");
+            for (int d = 0; d < 3; d++) allpairs = allpairs && rr[d] >= G.n[d];
+            if (allpairs && !h->lrf_mom.ensure((size_t)20 * nu)) {
+                cudaMemsetAsync(h->lrf_mom.p, 0, sizeof(double) * 20 * (size_t)nu, ls);
+                const int tb = cdiv(nu, 128);
+                const int slices = std::max(1, std::min(cdiv(nu, kLrfTileItems), cdiv(4 * h->nsm, tb)));
+                LAUNCH_ON(h, ls, k_lrf_allpairs, dim3(tb, slices), 128, 0, D, h->cut, h->x.p, h->upos.p, h->item_pos.p, h->item_posf.p,
+                          h->src_off.p, h->src.p, h->lrf.p, h->lrf_mom.p);
+                LAUNCH_ON(h, ls, k_lrf_expand, cdiv(nu * 40, 256), 256, 0, D, h->lrf_mom.p, h->lrf.p);
+            } else
 #define LRFCASE(CP, RS, GN) LAUNCH_ON(h, ls, (k_lrf_accumulate<CP, RS, GN>), nu, 32 * kRowWarps, 0, D, h->cut, G, h->lrf_reach, h->x.p, h->upos.p, \
                                       h->cell_of.p, h->cell_start.p, h->item_pos.p, h->item_posf.p, h->src_off.p, h->src.p, h->lrf.p)
             if (rowshift) { if (general) LRFCASE(true, true, true); else LRFCASE(true, true, false); }
@@ -1302,7 +1316,7 @@ int qnb_finalize(qnb_handle *h) {
     h->row_tot.release(); h->row_off.release(); h->flag.release(); h->pos.release(); h->qp_list.release();
     h->qw_list.release(); h->qp_shift_atom.release(); h->rows.release(); h->flush.release();
     h->pk_atom.release(); h->pk_ct.release(); h->pk_q.release(); h->pk_qd.release(); h->px.release(); h->py.release(); h->pz.release();
-    h->nch.release(); h->choff.release(); h->ucost.release(); h->cost_off.release(); h->wstart_w.release(); h->wstart_s.release(); h->wdesc.release(); h->wrow.release(); h->sdesc.release(); h->srow.release(); h->sspec.release(); h->x_saved.release(); h->lrf_saved.release(); h->wp_theta.release(); h->wp_shell_n.release(); h->wp_shell_list.release(); h->wp_shell_theta.release();
+    h->nch.release(); h->choff.release(); h->ucost.release(); h->cost_off.release(); h->wstart_w.release(); h->wstart_s.release(); h->wdesc.release(); h->wrow.release(); h->sdesc.release(); h->srow.release(); h->sspec.release(); h->x_saved.release(); h->lrf_saved.release(); h->wp_theta.release(); h->wp_shell_n.release(); h->wp_shell_list.release(); h->wp_shell_theta.release(); h->lrf_mom.release();
     h->item_posf.release();
     h->item_pos.release(); h->src.release(); h->cell_unsorted.release(); h->item_nq.release(); h->src_off.release();
     if (h->hx) cudaFreeHost(h->hx);

@@ -802,4 +802,138 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
     }
 }
 
+// ---------------------------------------------------------------- LRF, sphere with the LRF cut-off spanning it
+// Every unit is a source of (nearly) every target: the classic all-pairs tiling.  One THREAD per target keeps its 20
+// moments in registers; a block streams a slice of the cell-ordered source items through shared memory (positions,
+// atom ranges, atoms), so every lane reads the same source atom (a broadcast, no gathers, no dependent global loads)
+// and the moments of the slice are added to an unexpanded [nunit][20] buffer that k_lrf_expand turns into LRF_TYPE.
+// Switching-atom lists, unsharded, non-periodic only (the general kernel above serves everything else).
+constexpr int kLrfTileItems = 64, kLrfTileAtoms = 320;
+__global__ void __launch_bounds__(128)
+k_lrf_allpairs(Dev D, Cut C, const double *__restrict__ x, const double *__restrict__ upos, const double4 *__restrict__ item_pos,
+               const float4 *__restrict__ item_posf, const int *__restrict__ src_off, const double4 *__restrict__ src,
+               const double *__restrict__ lrf, double *__restrict__ mom /* [nunit][20] */) {
+    __shared__ float4 s_pos[kLrfTileItems];
+    __shared__ int s_a0[kLrfTileItems + 1];
+    __shared__ double4 s_atom[kLrfTileAtoms];
+    __shared__ float4 s_atomf[kLrfTileAtoms];   // FP32 copy for the phi3 path and the rsqrt seed: conversions cost XU slots
+    __shared__ int s_tile_end;
+    const int ns = D.ncgp_solute;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = t < D.nunit && !D.u_excl[t];
+    const int tt = live ? t : 0;
+    const int gt = D.u_grp[tt];
+    const double cx_ = lrf[(size_t)QNB_LRF_STRIDE * gt], cy_ = lrf[(size_t)QNB_LRF_STRIDE * gt + 1], cz_ = lrf[(size_t)QNB_LRF_STRIDE * gt + 2];
+    const double pt[3] = {upos[3 * tt], upos[3 * tt + 1], upos[3 * tt + 2]};
+    const float ptf[3] = {(float)pt[0], (float)pt[1], (float)pt[2]};
+    const float cxf = (float)cx_, cyf = (float)cy_, czf = (float)cz_;
+    const bool t_sol = tt < ns;
+    const int cls_s = t_sol ? 0 : 1, cls_w = t_sol ? 1 : 2;
+    auto lo_of = [](double c2) { return (float)c2 * (1.0f - 1e-3f) - 0.05f; };
+    auto hi_of = [](double c2) { return (float)c2 * (1.0f + 1e-3f) + 0.05f; };
+    const float in_lo_s = lo_of(C.rc2_of(cls_s)), in_hi_s = hi_of(C.rc2_of(cls_s));
+    const float in_lo_w = lo_of(C.rc2_of(cls_w)), in_hi_w = hi_of(C.rc2_of(cls_w));
+    const float out_lo = lo_of(C.rclrf2), out_hi = hi_of(C.rclrf2);
+    double m[10];
+    float h[10];
+#pragma unroll
+    for (int k = 0; k < 10; k++) { m[k] = 0.0; h[k] = 0.f; }
+    // this block's slice of the items
+    const int per = (D.nunit + gridDim.y - 1) / gridDim.y;
+    const int lo = blockIdx.y * per, hi = min(D.nunit, lo + per);
+    for (int base = lo; base < hi;) {
+        __syncthreads();
+        // tile = up to kLrfTileItems items whose atoms fit
+        if (threadIdx.x == 0) {
+            int e = min(hi, base + kLrfTileItems);
+            const int a_first = src_off[base];
+            while (e > base + 1 && src_off[e] - a_first > kLrfTileAtoms) e--;
+            s_tile_end = e;
+        }
+        __syncthreads();
+        const int tend = s_tile_end, nit = tend - base;
+        const int a_first = src_off[base], nat = src_off[tend] - a_first;
+        for (int k = threadIdx.x; k < nit; k += blockDim.x) s_pos[k] = item_posf[base + k];
+        for (int k = threadIdx.x; k <= nit; k += blockDim.x) s_a0[k] = src_off[base + k] - a_first;
+        for (int k = threadIdx.x; k < min(nat, kLrfTileAtoms); k += blockDim.x) {
+            const double4 a = src[a_first + k];
+            s_atom[k] = a;
+            s_atomf[k] = make_float4((float)a.x, (float)a.y, (float)a.z, (float)a.w);
+        }
+        __syncthreads();
+        if (live && nat <= kLrfTileAtoms) {
+            for (int it = 0; it < nit; it++) {
+                const float4 pf = s_pos[it];
+                const int s = __float_as_int(pf.w);
+                if (s < 0 || s == t) continue;
+                const float dx = pf.x - ptf[0], dy = pf.y - ptf[1], dz = pf.z - ptf[2];
+                const float r2f = dx * dx + dy * dy + dz * dz;
+                const bool s_sol = s < ns;
+                const float il = s_sol ? in_lo_s : in_lo_w, ih = s_sol ? in_hi_s : in_hi_w;
+                // zones: 0 listed or outside the shell, 1 surely inside it, 2 the FP64 test decides
+                int zone = (r2f < il || r2f > out_hi) ? 0 : (r2f > ih && r2f < out_lo) ? 1 : 2;
+                if (zone == 2) {
+                    bool owner_is_t;
+                    const int cls = pair_class(t, s, ns, owner_is_t);
+                    const double4 ip = item_pos[base + it];
+                    const double ps[3] = {ip.x, ip.y, ip.z};
+                    const bool lrf_pair = (owner_is_t ? unit_pair_test(D, C, x, cls, t, s, pt, ps)
+                                                      : unit_pair_test(D, C, x, cls, s, t, ps, pt)).lrf;
+                    zone = lrf_pair ? 1 : 0;
+                }
+                if (zone != 1) continue;
+                for (int k = s_a0[it]; k < s_a0[it + 1]; k++) {
+                    // lrf_update (nonbondene.f90:656-719), see k_lrf_accumulate
+                    const double4 sa = s_atom[k];
+                    const double ddx = sa.x - cx_, ddy = sa.y - cy_, ddz = sa.z - cz_;
+                    const double r2 = ddx * ddx + ddy * ddy + ddz * ddz;
+                    // FP32 displacement from FP32 copies (|x| ~ 30 A: 2e-6 A, the phi3 path is FP32 anyway; as the
+                    // rsqrt seed its 1e-6 error is cubed away by the Halley step)
+                    const float4 af = s_atomf[k];
+                    const float fx = af.x - cxf, fy = af.y - cyf, fz = af.z - czf;
+                    const float rif = rsqrt_fast(fmaf(fx, fx, fmaf(fy, fy, fz * fz)));
+                    const double ri = rsqrt_refine(r2, rif), ri2 = ri * ri;
+                    const double f0 = sa.w * ri * ri2;
+                    m[0] += sa.w * ri;
+                    m[1] -= ddx * f0; m[2] -= ddy * f0; m[3] -= ddz * f0;
+                    const double f1 = 3.0 * f0 * ri2;
+                    const double tx = f1 * ddx, ty = f1 * ddy, tz = f1 * ddz;
+                    m[4] += tx * ddx - f0; m[5] += tx * ddy; m[6] += tx * ddz;
+                    m[7] += ty * ddy - f0; m[8] += ty * ddz; m[9] += tz * ddz - f0;
+                    const float rif2 = rif * rif;
+                    const float f2 = -3.0f * af.w * rif * rif2 * rif2 * rif2;
+                    const float g5 = 5.0f * f2, gr = f2 * (fx * fx + fy * fy + fz * fz);
+                    const float ax = g5 * fx, ay = g5 * fy, az = g5 * fz;
+                    const float axx = ax * fx, axy = ax * fy, axz = ax * fz, ayy = ay * fy, ayz = ay * fz, azz = az * fz;
+                    const float gx = gr * fx, gy = gr * fy, gz = gr * fz;
+                    h[0] += axx * fx - 3.0f * gx;
+                    h[1] += axx * fy - gy;
+                    h[2] += axx * fz - gz;
+                    h[3] += axy * fy - gx;
+                    h[4] += axy * fz;
+                    h[5] += axz * fz - gx;
+                    h[6] += ayy * fy - 3.0f * gy;
+                    h[7] += ayy * fz - gz;
+                    h[8] += ayz * fz - gy;
+                    h[9] += azz * fz - 3.0f * gz;
+                }
+            }
+        }
+        base = tend;
+    }
+    if (live) {
+        double *mt = mom + (size_t)20 * t;
+#pragma unroll
+        for (int k = 0; k < 10; k++) { atomicAdd(&mt[k], m[k]); atomicAdd(&mt[10 + k], (double)h[k]); }
+    }
+}
+// unique moments -> LRF_TYPE (phi0, phi1(3), phi2(3x3), phi3(9x3)) of the unit's charge group
+__global__ void k_lrf_expand(Dev D, const double *__restrict__ mom, double *__restrict__ lrf) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= D.nunit * 40) return;
+    const int t = i / 40, k = i - 40 * t;
+    if (D.u_excl[t]) return;
+    lrf[(size_t)QNB_LRF_STRIDE * D.u_grp[t] + 3 + k] = mom[(size_t)20 * t + kLrfExpand[k]];
+}
+
 }  // namespace qnb
