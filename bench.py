@@ -103,6 +103,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C2", choices=["C2", "C3", "C4s", "C5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sharded", action="store_true",
+                    help="N>1: ONE system, i-ranges of the pair lists sharded over the GPUs, NCCL all-reduce of forces and "
+                         "energies (strong scaling). Default for --workload C5; otherwise one independent window per GPU")
     ap.add_argument("--windows-per-gpu", type=int, default=4,
                     help="also time this many independent windows sharing each GPU (0/1: skip)")
     args = ap.parse_args()
@@ -160,10 +163,27 @@ def main():
         # independent lambda windows: rank r runs window r of 51 (gen_inps.pl: 1.00 -> 0.00 step 0.02)
         l1 = 1.0 - 0.02 * (rank % 51)
         lam = np.array([l1, 1.0 - l1])
-    g = Qnb(q, device=dev)
+    sharded = world > 1 and (args.sharded or args.workload == "C5")
+    if sharded:
+        # distribute_nonbonds (nonbondene.f90:80-505): contiguous i-ranges per rank, everything else replicated
+        from q6_b200.system import shard_system
+        g = Qnb(shard_system(q, rank, world), device=dev)
+        uid = [g.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        g.comm_init(rank, world, uid[0])
+        config["replicas"] = f"one system, pair lists sharded over {world} GPUs, NCCL all-reduce of [d|E|EQ] per step"
+        args.windows_per_gpu = 0
+    else:
+        g = Qnb(q, device=dev)
     x = q.xtop.copy()
     counts = g.make_pair_lists(x, **cuts)
     nqq = sum(g.list_count(5, s + 1) + g.list_count(6, s + 1) for s in range(q.nstates))
+    counts_local, nqq_local = np.array(counts).copy(), nqq     # what THIS rank's kernels process (roofline)
+    if sharded:
+        t = torch.tensor([float(c) for c in counts[:5]] + [float(nqq)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        counts = np.array([int(v) for v in t[:5].tolist()] + [0] * (len(counts) - 5))
+        nqq = int(t[5].item())
     npairs = pairs_per_step(counts, q.nstates, nqq)
 
     def barrier():
@@ -251,10 +271,12 @@ def main():
 
     # ---- per-kernel times (L2 flushed before each launch) and the roofline of the dominant kernel
     line = None
+    list_ms_all = g.bench_build_lists(3) / 3 if sharded else None   # the sharded build all-reduces the LRF moments
     if rank == 0:
         kt = g.bench_kernels(lam, 20, flush_l2=True)
         kt_warm = g.bench_kernels(lam, 20, flush_l2=False)
-        list_ms = g.bench_build_lists(3) / 3
+        list_ms = list_ms_all if sharded else g.bench_build_lists(3) / 3
+        counts, nqq = counts_local, nqq_local
         peaks = measured_peaks()
         fp32_meas = bench_peak(0, dev)
         fp64_meas = bench_peak(1, dev)
@@ -293,16 +315,18 @@ def main():
         lb["achieved_gbs"] = lb["algorithmic_bytes"] / (lb["ms"] * 1e-3) / 1e9
         if lb["hbm_peak_gbs"]:
             lb["frac"] = lb["achieved_gbs"] / lb["hbm_peak_gbs"]
-        value = npairs * world / t_step
+        nsys = 1 if sharded else world          # systems advanced per step over the whole job
+        value = npairs * nsys / t_step
         e2e_step = e2e_s / steps
         line = {"metric": "nonbonded pair interactions/s", "value": value, "unit": "pairs/s", "n_gpus": world,
                 "steps": steps, "warmup": warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32 pair math, f64 accumulation and energies",
+                "scaling": "strong" if sharded else "weak", "vs_baseline": None,
+                "dtype": "f32 pair math, f64 accumulation and energies",
                 "data": "synthetic", "config": config, "pairs_per_step": npairs,
                 "ns_per_day": 86400.0 / e2e_step * DT_FS * 1e-6,
                 "ns_per_day_device_resident": 86400.0 / t_step * DT_FS * 1e-6,
-                "fep_windows_per_hour": world * 3600.0 / (STEPS_PER_WINDOW * e2e_step),
-                "e2e": {"value": npairs * world / e2e_step, "unit": "pairs/s", "ms_per_step": e2e_step * 1e3,
+                "fep_windows_per_hour": nsys * 3600.0 / (STEPS_PER_WINDOW * e2e_step),
+                "e2e": {"value": npairs * nsys / e2e_step, "unit": "pairs/s", "ms_per_step": e2e_step * 1e3,
                         "h2d_bytes_per_step": int(h2d_step), "d2h_bytes_per_step": int(d2h),
                         "host_breakdown_last_call_us": {k: round(v * 1e6, 1) for k, v in host_breakdown.items()}},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}
@@ -314,9 +338,9 @@ def main():
                                           "note": "same end-to-end path as e2e (host buffers, list build every "
                                                   f"{NBCYCLE} steps), {kwin} handles and host threads per GPU"}
         # ---- optional paths, reported next to the headline (never part of it)
-        ext = {"device_step_ms": g.bench_nonbond(lam, 200) / 200,
-               "device_step_ms_no_pp_pw_ww_energies": g.bench_nonbond(lam, 200, energies=False) / 200}
-        if not q.use_PBC and q.nwat > 0:
+        ext = {} if sharded else {"device_step_ms": g.bench_nonbond(lam, 200) / 200,
+                                  "device_step_ms_no_pp_pw_ww_energies": g.bench_nonbond(lam, 200, energies=False) / 200}
+        if not sharded and not q.use_PBC and q.nwat > 0:
             from q6_b200.engine import wat_shells
             rw = float(np.linalg.norm(q.xtop[q.nat_solute:] - np.asarray(q.xpcent), axis=1).max())
             g.set_solvent_restraints(wat_shells(q.xpcent, rw, crgQtot=-1.0), np.zeros(8))
