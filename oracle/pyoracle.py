@@ -150,6 +150,77 @@ def solvent_restraints(qsys: QSystem, params, theta_corr, x, md=True):
     return d.reshape(-1, 3), E, ts[:k], ns[:k]
 
 
+CONST_TOL = 0.0001          # globals.f90:519
+CONST_MAX_ITER = 1000       # globals.f90:520
+
+
+def shake_constraints(bnd, bondlib, mass, nat_solute, shake_solvent=True, shake_solute=False, shake_hydrogens=True,
+                      shake_heavy=False):
+    """init_constraints (simprep.f90:2167-2345) restated for the bond part: the constrained bonds in topology order as
+    rows (i, j, dist2) with 1-based atom numbers.  heavy = mass >= 4 (topo.f90:896-903); bonds with code 0 are
+    skipped; defaults are those of md.f90:338-357 (solvent bonds to hydrogens: O-H, O-H and the H-H "bond" of TIP3P)."""
+    heavy = np.asarray(mass) >= 4.0
+    out = []
+    for ia, ja, cod in np.asarray(bnd).reshape(-1, 3):
+        if cod == 0:
+            continue
+        has_h = (not heavy[ia - 1]) or (not heavy[ja - 1])
+        on = (shake_solute and ia <= nat_solute) or (shake_solvent and ia > nat_solute)
+        if on and ((has_h and shake_hydrogens) or (not has_h and shake_heavy)):
+            out.append((int(ia), int(ja), float(bondlib[cod - 1][1]) ** 2))
+    return out
+
+
+def shake(constraints, istart_mol, winv, xx, x):
+    """SHAKE as ``shake(xx, x)`` of bondene.f90:1069-1150: x is corrected along the bond vectors of the reference
+    coordinates xx until every constraint of a molecule is within CONST_TOL (relative, on the squared length).  Literal
+    restatement incl. the order of operations: a constraint found in range is flagged ready and still receives that
+    pass's correction.  Returns (x_new, iterations per molecule)."""
+    x = np.array(x, dtype=np.float64)
+    xx = np.asarray(xx, dtype=np.float64)
+    bounds = list(istart_mol) + [len(x) + 1]
+    by_mol = {}
+    for c in constraints:
+        m = int(np.searchsorted(bounds, c[0], side="right")) - 1
+        by_mol.setdefault(m, []).append(c)
+    nits_all = []
+    for m in sorted(by_mol):
+        cons = by_mol[m]
+        ready = [False] * len(cons)
+        nits = 0
+        while True:
+            for ic, (i, j, dist2) in enumerate(cons):
+                if ready[ic]:
+                    continue
+                i0, j0 = i - 1, j - 1
+                xij = x[i0] - x[j0]                          # q_dist5(x(j), x(i))%vec, math.f90:270
+                diff = dist2 - (xij[0] * xij[0] + xij[1] * xij[1] + xij[2] * xij[2])
+                if abs(diff) < CONST_TOL * dist2:
+                    ready[ic] = True
+                xxij = xx[i0] - xx[j0]
+                scp = xij[0] * xxij[0] + xij[1] * xxij[1] + xij[2] * xxij[2]
+                corr = diff / (2.0 * scp * (winv[i0] + winv[j0]))
+                x[i0] = x[i0] + xxij * corr * winv[i0]
+                x[j0] = x[j0] + (-xxij) * corr * winv[j0]
+            nits += 1
+            if all(ready):
+                break
+            if nits >= CONST_MAX_ITER:
+                raise RuntimeError("shake failure")          # die('shake failure'), bondene.f90:1143
+        nits_all.append(nits)
+    return x, nits_all
+
+
+def initial_constraint_x(topo, x=None):
+    """The coordinate part of initial_constraint (bondene.f90:1035-1036; called from qdyn.f90:133 when iseed > 0):
+    xx = x; shake(xx, x).  The velocity part does not touch x.  These are the coordinates the reference's step-0
+    energies (the first row of tests/basic_tests/*_benchmark.en) are evaluated at."""
+    x = topo.xtop if x is None else x
+    mass = topo.iaclib[np.asarray(topo.iac) - 1, 0]
+    cons = shake_constraints(topo.bnd, topo.bondlib, mass, topo.nat_solute)
+    return shake(cons, topo.istart_mol, 1.0 / mass, x, x)
+
+
 def make_qconn(nstates, nat_solute, nqat, iqseq, iqatom, bnd_solute, qbnd_ij, qbnd_cod, exspec_ij, exspec_flag):
     """Literal find_bonded recursion (nonbondene.f90:3131); returns [iq][atom][state]."""
     lib = load()

@@ -89,6 +89,7 @@ class Topology:
     nbonds: int = 0
     nbonds_solute: int = 0
     bnd: np.ndarray = field(default_factory=lambda: np.zeros((0, 3), np.int32))  # i, j, cod
+    bondlib: np.ndarray = field(default_factory=lambda: np.zeros((0, 2)))  # fk, bnd0 per bond code (topo.f90:691-700)
     nangles: int = 0
     nangles_solute: int = 0
     ntors: int = 0
@@ -196,8 +197,11 @@ def _read(rec: _Records, t: Topology) -> None:
     if t.nbonds > 0:
         t.bnd = np.array(rec.values(3 * t.nbonds, int), dtype=np.int32).reshape(t.nbonds, 3)
     nbndcod = rec.leading(rec.line(), int, 1)[0]
-    for _ in range(nbndcod):
-        rec.skip()
+    t.bondlib = np.zeros((nbndcod, 2))
+    for i in range(nbndcod):
+        v = rec.leading(rec.line(), _to_float, 3)     # code number, fk, bnd0 [, SYBYL type]
+        if len(v) >= 3:
+            t.bondlib[i] = v[1:3]
     # 6. angles (L712-743)
     v = rec.leading(rec.line(), int, 2)
     t.nangles = v[0]

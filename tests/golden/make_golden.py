@@ -13,6 +13,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
+from oracle import pyoracle  # noqa: E402
 from oracle.pyoracle import Oracle  # noqa: E402
 from q6_b200.fep import load_fep  # noqa: E402
 from q6_b200.system import build_system  # noqa: E402
@@ -32,6 +33,12 @@ FIXTURES = {
     "c4_evb": (f"{REF}/exclude_tests/inputs/2cjpFH_ionres_oplsa.top", f"{REF}/exclude_tests/inputs/lig.fep",
                dict(Rq=99.0, Rcq2=99.0 ** 2, RcLRF2=99.0 ** 2, Rcpp2=100.0, Rcpw2=100.0, Rcww2=100.0, RcLRF=99.0), [0.5, 0.5]),
 }
+
+
+# Row 1 of tests/basic_tests/{SPH,PBC}_*_benchmark.en (lower == upper bound; identical in all six files of a kind):
+# QEL QVdW (= "Q-surr." el, vdw: qp + qw) and EL VdW (= solute + solvent + solute-solvent el, vdw; LRF not included),
+# eval_test.sh:99-101, 191-196.  Printed with two decimals.
+STEP0 = {"c1_sph": (3.12, 139.43, -7.30, -413.17), "c1_pbc": (-31.30, 228.64, 380.33, -1990.55)}
 
 
 def list_checksum(ij: np.ndarray) -> np.ndarray:
@@ -57,6 +64,18 @@ def main():
         for which, nm in enumerate(("pp", "pw", "ww", "qp", "qw", "qq", "qqp")):
             ij, p = o.export_list(which, 1)
             res[f"sum_{nm}"] = list_checksum(ij)
+        if name in STEP0:
+            # the coordinates of the reference's step 0: topology coordinates after the initial solvent SHAKE
+            # (qdyn.f90:133 -> initial_constraint, bondene.f90:1025-1048), and the oracle's results there
+            xs, nits = pyoracle.initial_constraint_x(t)
+            res["x_step0"] = xs
+            res["shake_iterations"] = np.array(nits, np.int32)
+            res["counts_step0"] = o.make_pair_lists(xs, **cuts)
+            d0, E0, EQ0 = o.pot_energy_nonbonds(xs, lam)
+            res.update(d_step0=d0, E_step0=E0, EQ_step0=EQ0)
+            print(name, "step 0 (post-SHAKE): QEL %.4f QVdW %.4f EL %.4f VdW %.4f" % (
+                EQ0[0, 2] + EQ0[0, 4], EQ0[0, 3] + EQ0[0, 5], E0[0] + E0[2] + E0[4], E0[1] + E0[3] + E0[5]),
+                "reference:", STEP0[name])
         np.savez_compressed(os.path.join(OUT, f"{name}_oracle.npz"), **res)
         print(name, "natom", q.natom, "counts", counts[:5], "E", np.round(E, 3), "EQ", np.round(EQ, 3))
 

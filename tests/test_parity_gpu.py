@@ -117,6 +117,30 @@ def test_golden_scalars_c1():
         g.close()
 
 
+@pytest.mark.parametrize("name", ["c1_sph", "c1_pbc"])
+def test_reference_step0_goldens(name):
+    """The CUDA path against the reference's OWN numbers: row 1 of tests/basic_tests/{SPH,PBC}_*_benchmark.en and
+    eval_test.sh:99-101 (QEL, QVdW, EL, VdW at step 0, printed with two decimals), evaluated at the post-SHAKE
+    coordinates of the fixture (qdyn.f90:133), plus the oracle's full result there."""
+    from q6_b200.engine import Qnb
+    from test_oracle_golden import STEP0_GOLDEN, step0_terms
+    q, cuts, lam, z = golden_system(name)
+    g = Qnb(q)
+    try:
+        c = g.make_pair_lists(z["x_step0"], **cuts)
+        assert np.array_equal(c[:5], z["counts_step0"][:5])
+        d, E, EQ = g.pot_energy_nonbonds(z["x_step0"], lam)
+        got = step0_terms(E, EQ)
+        for v, want in zip(got, STEP0_GOLDEN[name]):
+            assert abs(v - want) <= 0.005 + 1e-9, (got, STEP0_GOLDEN[name])
+        assert rel_rms(d, z["d_step0"]) <= FORCE_REL_RMS
+        for k in range(7):
+            assert_energy(f"E[{k}]", E[k], z["E_step0"][k])
+        assert_energy("EQ", EQ, z["EQ_step0"])
+    finally:
+        g.close()
+
+
 @pytest.mark.parametrize("name", ["C2", "C3", "C4s"])
 def test_baseline_configs(name):
     """The BASELINE.json configurations at full size (synthetic systems of the named shapes)."""
