@@ -1,0 +1,244 @@
+"""The compiled (C++) host side above the C ABI -- q6_b200/host -- against the Python mirror and the oracle.
+
+The reference host is Fortran; with no Fortran compiler in the image its role is played by qdyn_host.cpp (topo_read,
+qatom_load_fep, prep_sim, make_qconn, initial SHAKE, Nonbonded::make_pair_lists / pot_energy_nonbonds, write_out).
+CPU tests: the tables it prepares from the reference's shipped topology / FEP files equal the Python readers' tables
+field by field, the oracle fed with them reproduces the reference's step-0 goldens, and its write_out prints the very
+line eval_test.sh:99-101 greps for.  GPU test: the Nonbonded class through libqnb against the committed goldens.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import common
+from common import golden_system
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "q6_b200", "host", "libqdynhost.so")
+REF = "/root/reference/tests"
+have_ref = pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted")
+
+FILES = {
+    "c1_sph": (f"{REF}/basic_tests/prep_SPH/lig_w.top", f"{REF}/basic_tests/prep_SPH/lig_w.fep"),
+    "c1_pbc": (f"{REF}/basic_tests/prep_PBC/lig_w.top", f"{REF}/basic_tests/prep_PBC/lig_w.fep"),
+    "c4_evb": (f"{REF}/exclude_tests/inputs/2cjpFH_ionres_oplsa.top", f"{REF}/exclude_tests/inputs/lig.fep"),
+}
+
+
+def host_lib():
+    from q6_b200 import engine
+    from q6_b200.system import qnb_system
+    engine.load_library()          # libqdynhost.so links against libqnb.so
+    lib = C.CDLL(LIB)
+    H = C.c_void_p
+    PD, PL = C.POINTER(C.c_double), C.POINTER(C.c_int64)
+    lib.qhost_last_error.restype = C.c_char_p
+    lib.qhost_open.restype = C.c_int
+    lib.qhost_open.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(H)]
+    lib.qhost_from_system.restype = C.c_int
+    lib.qhost_from_system.argtypes = [C.POINTER(qnb_system), PD, C.POINTER(H)]
+    lib.qhost_system.restype = C.POINTER(qnb_system)
+    lib.qhost_system.argtypes = [H]
+    lib.qhost_xtop.restype = PD
+    lib.qhost_xtop.argtypes = [H]
+    lib.qhost_boxlength.restype = PD
+    lib.qhost_boxlength.argtypes = [H]
+    lib.qhost_shard.argtypes = [H, C.c_int, C.c_int]
+    lib.qhost_constraint_count.restype = C.c_int64
+    lib.qhost_constraint_count.argtypes = [H]
+    lib.qhost_initial_constraint.argtypes = [H, PD, C.POINTER(C.c_int)]
+    lib.qhost_attach_gpu.argtypes = [H, C.c_int]
+    lib.qhost_make_pair_lists.argtypes = [H, PD] + [C.c_double] * 7 + [PL]
+    lib.qhost_pot_energy_nonbonds.argtypes = [H, PD, PD, C.c_int, PD, PD, PD]
+    lib.qhost_write_out.restype = C.c_char_p
+    lib.qhost_write_out.argtypes = [H, PD, PD, PD, C.c_int]
+    lib.qhost_close.argtypes = [H]
+    return lib
+
+
+def _open(lib, name, use_lrf=1):
+    top, fep = FILES[name]
+    h = C.c_void_p()
+    rc = lib.qhost_open(top.encode(), fep.encode(), use_lrf, -1, C.byref(h))
+    assert rc == 0, lib.qhost_last_error().decode()
+    return h
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _struct_arrays(st):
+    """Every array of a qnb_system as numpy copies, sized from its scalars."""
+    nat, nsol, nq, ns = st.natom, st.nat_solute, st.nqat, st.nstates
+    ncgpatom = max([st.cgp[3 * g + 2] for g in range(st.ncgp)] + [0])     # cgp(ncgp)%last
+    sizes = dict(cgp=3 * st.ncgp, cgpatom=ncgpatom, excl=nat, iqatom=nat, iqseq=nq, iac=nat, crg=nat, iaclib=7 * st.natyps,
+                 ljcod=st.num_atyp ** 2, listex=st.max_nbr_range * nsol, list14=st.max_nbr_range * nsol,
+                 listexlong=2 * st.nexlong, list14long=2 * st.n14long, qcrg=nq * ns, qiac=nq * ns, qavdw=3 * st.nqlib,
+                 qbvdw=3 * st.nqlib, sc_lookup=nq * (st.natyps + nq) * ns, iqexpnb=st.nqexpnb, jqexpnb=st.nqexpnb,
+                 el_scale_iq=st.nel_scale, el_scale_jq=st.nel_scale, el_scale=st.nel_scale * ns, qconn=ns * nsol * nq)
+    return {k: np.array(getattr(st, k)[:n]) for k, n in sizes.items()}
+
+
+def _scalars():
+    from q6_b200.system import qnb_system
+    return [n for n, t in qnb_system._fields_ if t in (C.c_int32, C.c_double)]
+
+
+@have_ref
+@pytest.mark.parametrize("name", list(FILES))
+def test_cpp_host_tables_equal_python_mirror(name):
+    """topo_read + qatom_load_fep + prep_sim in C++ == q6_b200.topo/fep/system on the reference's shipped inputs:
+    every scalar and every array of qnb_system, bit for bit."""
+    from q6_b200.fep import load_fep
+    from q6_b200.system import build_system
+    from q6_b200.topo import topo_read
+    lib = host_lib()
+    h = _open(lib, name)
+    try:
+        cs = lib.qhost_system(h).contents
+        t = topo_read(FILES[name][0])
+        py, keep = build_system(t, load_fep(FILES[name][1], t), use_LRF=True).as_struct()
+        for n in _scalars():
+            assert getattr(cs, n) == getattr(py, n), n
+        assert list(cs.xpcent) == list(py.xpcent)
+        a, b = _struct_arrays(cs), _struct_arrays(py)
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k
+        x = np.ctypeslib.as_array(lib.qhost_xtop(h), shape=(cs.natom, 3))
+        assert np.array_equal(x, t.xtop)
+        if t.use_PBC:
+            assert np.array_equal(np.ctypeslib.as_array(lib.qhost_boxlength(h), shape=(3,)), t.boxlength)
+    finally:
+        lib.qhost_close(h)
+
+
+@have_ref
+@pytest.mark.parametrize("name", ["c1_sph", "c1_pbc"])
+def test_cpp_host_reproduces_reference_step0(name):
+    """The compiled host end to end on the CPU side: shipped files -> tables -> initial SHAKE (bit-identical to the
+    fixture's post-SHAKE coordinates) -> the oracle on those tables gives the reference's step-0 energies, and
+    write_out prints the line eval_test.sh compares."""
+    from oracle import pyoracle
+    from test_oracle_golden import STEP0_GOLDEN, step0_terms
+    lib = host_lib()
+    h = _open(lib, name)
+    try:
+        cs = lib.qhost_system(h)
+        st = cs.contents
+        assert lib.qhost_constraint_count(h) == 3 * st.nwat
+        q, cuts, lam, z = golden_system(name)
+        x = np.ctypeslib.as_array(lib.qhost_xtop(h), shape=(st.natom, 3)).copy()
+        nit = C.c_int()
+        assert lib.qhost_initial_constraint(h, _dp(x), C.byref(nit)) == 0, lib.qhost_last_error().decode()
+        assert np.array_equal(x, z["x_step0"])
+        # the oracle driven by the C++ host's struct
+        ol = pyoracle.load()
+        oh = ol.qo_create(cs)
+        assert oh, ol.qo_last_error().decode()
+        if st.use_PBC:
+            b = np.ctypeslib.as_array(lib.qhost_boxlength(h), shape=(3,)).copy()
+            ib = 1.0 / b
+            ol.qo_update_box(oh, _dp(b), _dp(ib))
+        counts = np.zeros(8, np.int64)
+        c7 = [cuts[k] for k in common.CUT_KEYS]
+        assert ol.qo_make_pair_lists(oh, _dp(x.reshape(-1)), *c7, counts.ctypes.data_as(C.POINTER(C.c_int64))) == 0
+        d, E, EQ = np.zeros(3 * st.natom), np.zeros(7), np.zeros(6 * st.nstates)
+        lam = np.ascontiguousarray(lam, dtype=np.float64)
+        ol.qo_nonbond(oh, _dp(x.reshape(-1)), _dp(lam), 3, _dp(d), _dp(E), _dp(EQ))
+        ol.qo_destroy(oh)
+        assert np.array_equal(counts, z["counts_step0"])
+        assert np.allclose(E, z["E_step0"], rtol=1e-12, atol=1e-9)
+        got = step0_terms(E, EQ.reshape(-1, 6))
+        for v, want in zip(got, STEP0_GOLDEN[name]):
+            assert abs(v - want) <= 0.005 + 1e-9
+        text = lib.qhost_write_out(h, _dp(E), _dp(EQ), _dp(lam), 0).decode()
+        want = {"c1_sph": "Q-surr. 1 1.0000      3.12    139.43", "c1_pbc": "Q-surr. 1 1.0000    -31.30    228.64"}[name]
+        assert want in text.split("\n"), text          # INIT_QSURR_BM, eval_test.sh:99-101
+        assert "at step      0" in text
+    finally:
+        lib.qhost_close(h)
+
+
+def test_cpp_host_from_struct_and_sharding():
+    """system_from_struct deep-copies tables prepared elsewhere; shard() is distribute_nonbonds with equal shares."""
+    from q6_b200.system import distribute_nonbonds
+    lib = host_lib()
+    q, cuts, lam, z = golden_system("c4_evb")
+    st, keep = q.as_struct()
+    h = C.c_void_p()
+    assert lib.qhost_from_system(C.byref(st), None, C.byref(h)) == 0, lib.qhost_last_error().decode()
+    try:
+        cs = lib.qhost_system(h).contents
+        a, b = _struct_arrays(cs), _struct_arrays(st)
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k
+        assert lib.qhost_shard(h, 1, 4) == 0
+        cs = lib.qhost_system(h).contents
+        assert (cs.pp_start, cs.pp_end) == distribute_nonbonds(np.ones(q.ncgp_solute), 4)[1]
+        assert (cs.ww_start, cs.ww_end) == distribute_nonbonds(np.ones(q.nwat), 4)[1]
+        assert cs.is_master == 0
+    finally:
+        lib.qhost_close(h)
+
+
+def test_cpp_host_dies_without_gpu_and_on_bad_files(tmp_path):
+    """Error behaviour: topo_read's message for an unreadable topology; Nonbonded refuses to exist without a GPU."""
+    from q6_b200 import engine
+    lib = host_lib()
+    bad = tmp_path / "bad.top"
+    bad.write_text("not a topology\n1 2 x\n")
+    h = C.c_void_p()
+    assert lib.qhost_open(str(bad).encode(), b"", 1, -1, C.byref(h)) != 0
+    assert "Could not read topology file" in lib.qhost_last_error().decode()
+    assert lib.qhost_open(b"/nonexistent.top", b"", 1, -1, C.byref(h)) != 0
+    if engine.load_library().qnb_device_count() > 0:
+        return
+    q, cuts, lam, z = golden_system("c1_sph")
+    st, keep = q.as_struct()
+    assert lib.qhost_from_system(C.byref(st), None, C.byref(h)) == 0
+    try:
+        assert lib.qhost_attach_gpu(h, 0) != 0
+        assert "qnb_init" in lib.qhost_last_error().decode()
+    finally:
+        lib.qhost_close(h)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["c1_sph", "c1_pbc", "c4_evb"])
+def test_cpp_nonbonded_class_on_gpu(name):
+    """qdyn::Nonbonded (make_pair_lists / pot_energy_nonbonds with the reference's argument lists) through libqnb on
+    the reference's shipped systems: list sizes, energies and gradient against the committed oracle results, and for
+    the two basic_tests systems the reference's own step-0 numbers."""
+    from test_oracle_golden import STEP0_GOLDEN, step0_terms
+    lib = host_lib()
+    q, cuts, lam, z = golden_system(name)
+    st, keep = q.as_struct()
+    h = C.c_void_p()
+    box = np.ascontiguousarray(q.boxlength, dtype=np.float64)
+    assert lib.qhost_from_system(C.byref(st), _dp(box), C.byref(h)) == 0, lib.qhost_last_error().decode()
+    try:
+        assert lib.qhost_attach_gpu(h, 0) == 0, lib.qhost_last_error().decode()
+        cases = [("", q.xtop)] + ([("_step0", z["x_step0"])] if name in STEP0_GOLDEN else [])
+        lam = np.ascontiguousarray(lam, dtype=np.float64)
+        for tag, x in cases:
+            x = np.ascontiguousarray(x, dtype=np.float64)
+            counts = np.zeros(8, np.int64)
+            c7 = [cuts[k] for k in common.CUT_KEYS]
+            rc = lib.qhost_make_pair_lists(h, _dp(x), *c7, counts.ctypes.data_as(C.POINTER(C.c_int64)))
+            assert rc == 0, lib.qhost_last_error().decode()
+            assert np.array_equal(counts[:5], z["counts" + tag][:5])
+            d, E, EQ = np.zeros((q.natom, 3)), np.zeros(7), np.zeros(6 * q.nstates)
+            rc = lib.qhost_pot_energy_nonbonds(h, _dp(x), _dp(lam), 1, _dp(d), _dp(E), _dp(EQ))
+            assert rc == 0, lib.qhost_last_error().decode()
+            assert common.rel_rms(d, z["d" + tag]) <= common.FORCE_REL_RMS
+            for k in range(7):
+                common.assert_energy(f"E[{k}]", E[k], z["E" + tag][k])
+            common.assert_energy("EQ", EQ.reshape(-1, 6), z["EQ" + tag])
+            if tag:
+                for v, want in zip(step0_terms(E, EQ.reshape(-1, 6)), STEP0_GOLDEN[name]):
+                    assert abs(v - want) <= 0.005 + 1e-9
+    finally:
+        lib.qhost_close(h)
