@@ -95,6 +95,28 @@ def cpu_reference(q, cuts, lam, threads, target_seconds=12.0):
     return t_step, steps, r
 
 
+def compiled_host_e2e(q, cuts, lam, steps, device):
+    """The same end-to-end loop (host buffers, list build every NBCYCLE steps) driven by the compiled host
+    q6_b200/host/qdyn_nb from written topology / FEP files: what a Fortran/C++ host pays, without Python in the loop."""
+    import re
+    import tempfile
+    from q6_b200 import synth
+    exe = os.path.join(ROOT, "q6_b200", "host", "qdyn_nb")
+    with tempfile.TemporaryDirectory() as tmp:
+        top, fep = os.path.join(tmp, "s.top"), os.path.join(tmp, "s.fep")
+        synth.write_files(q, top, fep)
+        cmd = [exe, top, fep if q.nqat else "-", "--no-shake", "--q_atom", repr(float(cuts["Rq"])),
+               "--lrf", repr(float(cuts["RcLRF"])), "--solute_solute", repr(float(np.sqrt(cuts["Rcpp2"]))),
+               "--solute_solvent", repr(float(np.sqrt(cuts["Rcpw2"]))), "--solvent_solvent", repr(float(np.sqrt(cuts["Rcww2"]))),
+               "--lambda", ",".join(repr(float(v)) for v in lam), "--steps", str(int(steps)), "--non_bond", str(NBCYCLE),
+               "--device", str(int(device))]
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    m = re.search(r"([0-9.]+) ms per step", out.stdout)
+    if out.returncode != 0 or not m:
+        raise RuntimeError((out.stdout + out.stderr)[-300:])
+    return float(m.group(1))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -337,6 +359,15 @@ def main():
                                           "fep_windows_per_hour": 3600.0 * agg / STEPS_PER_WINDOW,
                                           "note": "same end-to-end path as e2e (host buffers, list build every "
                                                   f"{NBCYCLE} steps), {kwin} handles and host threads per GPU"}
+        if world == 1 and args.workload != "C5":      # qdyn_nb squares Rq for Rcq2; C5 passes them independently
+            try:
+                ms_c = compiled_host_e2e(q, cuts, lam, max(steps, 10 * NBCYCLE), dev)
+                line["e2e_compiled_host"] = {"ms_per_step": ms_c, "value": npairs / (ms_c * 1e-3), "unit": "pairs/s",
+                                             "note": "q6_b200/host/qdyn_nb (C++ host over the C ABI, input files written by "
+                                                     "synth.write_files, host buffers, list build every "
+                                                     f"{NBCYCLE} steps); separate process, timed by its own host clock"}
+            except Exception as e:  # reported, never fatal: the headline e2e above does not depend on it
+                line["e2e_compiled_host"] = {"error": str(e)[-200:]}
         # ---- optional paths, reported next to the headline (never part of it)
         ext = {} if sharded else {"device_step_ms": g.bench_nonbond(lam, 200) / 200,
                                   "device_step_ms_no_pp_pw_ww_energies": g.bench_nonbond(lam, 200, energies=False) / 200}

@@ -1211,7 +1211,7 @@ void Nonbonded::update_box(const double boxlength[3]) {
 }
 
 void Nonbonded::make_pair_lists(double Rq, double Rcq2, double RcLRF2, double Rcpp2, double Rcpw2, double Rcww2) {
-    if (qnb_build_lists(h_, x.data(), Rq, Rcq2, RcLRF2, Rcpp2, Rcpw2, Rcww2, RcLRF, nb_pairs) != 0)
+    if (qnb_build_lists(h_, x.data(), Rq, Rcq2, RcLRF2, Rcpp2, Rcpw2, Rcww2, RcLRF, dump ? nb_pairs : nullptr) != 0)
         throw Die(std::string("make_pair_lists: ") + qnb_last_error());
 }
 

@@ -163,6 +163,9 @@ class Nonbonded {
     std::vector<double> x, d;   // [3*natom]
     double RcLRF = -1.0;        // the unsquared global the box builders test (nonbondene.f90:3066)
     int64_t nb_pairs[8] = {0};  // nbpp_pair, nbpw_pair, nbww_pair, nbqp_pair, nbqw_pair, nb??_cgp_pair
+    // the reference prints the list sizes at a list update only when built with -DDUMP (md.f90:1692-1696); counting
+    // the device lists costs host round trips, so nb_pairs is refreshed only while this is set
+    bool dump = false;
 
     // nonbondene.f90:749, the reference's argument list
     void make_pair_lists(double Rq, double Rcq2, double RcLRF2, double Rcpp2, double Rcpw2, double Rcww2);

@@ -83,6 +83,7 @@ int qhost_make_pair_lists(qhost *h, const double *x, double Rq, double Rcq2, dou
         if (!h->nb) throw Die("qhost_make_pair_lists: no GPU attached");
         std::memcpy(h->nb->x.data(), x, sizeof(double) * h->nb->x.size());
         h->nb->RcLRF = RcLRF;
+        h->nb->dump = counts != nullptr;
         h->nb->make_pair_lists(Rq, Rcq2, RcLRF2, Rcpp2, Rcpw2, Rcww2);
         if (counts) std::memcpy(counts, h->nb->nb_pairs, sizeof(int64_t) * 8);
     });

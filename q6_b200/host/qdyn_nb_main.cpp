@@ -95,7 +95,9 @@ int main(int argc, char **argv) {
         }
         nb.RcLRF = use_lrf ? RcLRF : -1.0;
         const double RcLRF2 = use_lrf ? RcLRF * RcLRF : -1.0;
+        nb.dump = true;  // list sizes for the log of the first update only
         nb.make_pair_lists(Rcq, Rcq * Rcq, RcLRF2, Rcpp * Rcpp, Rcpw * Rcpw, Rcww * Rcww);
+        nb.dump = false;
         std::printf("%-13s%13s%13s%13s%13s\n", "solute-solute", "solute-water", "water-water", "Q-solute", "Q-water");
         std::printf("%13lld%13lld%13lld%13lld%13lld\n", (long long)nb.nb_pairs[0], (long long)nb.nb_pairs[1],
                     (long long)nb.nb_pairs[2], (long long)nb.nb_pairs[3], (long long)nb.nb_pairs[4]);
@@ -106,6 +108,12 @@ int main(int argc, char **argv) {
         nb.pot_energy_nonbonds(E, EQ, true);
         std::fputs(write_out_nonbonded(sys, E, EQ, 0).c_str(), stdout);
         if (steps > 0) {
+            for (int istep = 0; istep < nbcycle + 3; istep++) {  // warm-up: first rebuild, graph instantiation
+                if (istep % nbcycle == 0)
+                    nb.make_pair_lists(Rcq, Rcq * Rcq, RcLRF2, Rcpp * Rcpp, Rcpw * Rcpw, Rcww * Rcww);
+                std::fill(nb.d.begin(), nb.d.end(), 0.0);
+                nb.pot_energy_nonbonds(E, EQ, true);
+            }
             auto t0 = std::chrono::steady_clock::now();
             for (int istep = 0; istep < steps; istep++) {
                 if (istep % nbcycle == 0)

@@ -78,6 +78,10 @@ def _base(natyp_used=9) -> QSystem:
 def _finish(q: QSystem, x, iac, crg, groups, nat_solute, nwat, bonds, listex_pairs, list14_pairs, q_atoms,
             nstates, qcrg=None, fep_types=None, softcore_alpha=None, soft_pairs=(), qbnd=None):
     """Assemble the Fortran-layout tables. groups: list of (switch, [atoms]) 1-based."""
+    # what a topology / FEP file of this system holds (write_files)
+    q.raw = dict(crg=[float(c) for c in crg], bonds=[tuple(int(v) for v in b) for b in bonds],
+                 qcrg=None if qcrg is None else np.asarray(qcrg, np.float64).copy(),
+                 fep_types=fep_types, softcore_alpha=softcore_alpha, soft_pairs=list(soft_pairs), qbnd=qbnd)
     q.natom, q.nat_solute, q.nwat, q.solv_atom = len(iac), nat_solute, nwat, 3
     q.iac = np.asarray(iac, np.int32)
     q.num_atyp = int(q.iac.max())
@@ -324,7 +328,7 @@ def solvated_sphere(radius: float = 30.0, core_radius: float = 19.5, nq: int = 4
             # a bond that exists only in state 1 and one only in state 2 (changes qconn per state)
             qb = (np.array([[2, 9], [3, 12]], np.int32), np.array([[1, 0], [0, 1]], np.int32))
             kw = dict(qcrg=np.stack([base, ch2], 1), fep_types=(lib_a, lib_b, qiac), softcore_alpha=alpha,
-                      soft_pairs=[(5, 20), (6, 30)], qbnd=qb)
+                      soft_pairs=[p for p in ((5, 20), (6, 30)) if p[1] <= nq], qbnd=qb)
     qs = _finish(q, x, iac, crg, groups, nat_solute, nwat, bonds, ex, l14, q_atoms, nstates, **kw)
     if excl_shell > 0 and not pbc_box:
         rr = np.linalg.norm(qs.xtop - center, axis=1)
@@ -335,6 +339,135 @@ def solvated_sphere(radius: float = 30.0, core_radius: float = 19.5, nq: int = 4
                 for a in qs.cgpatom[qs.cgp[g, 1] - 1:qs.cgp[g, 2]]:
                     qs.excl[a - 1] = 1
     return qs
+
+
+def _wrap(items, per_line, fmt=str):
+    items = [fmt(v) for v in items]
+    return [" ".join(items[i:i + per_line]) for i in range(0, len(items), per_line)]
+
+
+def write_files(q: QSystem, top_path: str, fep_path: str | None = None) -> None:
+    """Writes a synthetic system as Qdyn6 input files -- a version-5 Q topology (the record order topo_read expects,
+    topo.f90:522-1114) and, when it has Q-atoms, an FEP file (qatom.f90 sections) -- so that the unchanged readers
+    (q6_b200/topo.py + fep.py, q6_b200/host/qdyn_host.cpp) and the compiled driver can be run where the reference's
+    shipped inputs do not exist.  Numbers are written with repr(): reading the files back reproduces every table of q
+    bit for bit (tests/test_host_cpp.py)."""
+    raw = q.raw
+    nat, nsol, nw = q.natom, q.nat_solute, q.nwat
+    f = repr
+    L = ["Q topology file", "TITLE      synthetic system (q6_b200.synth)", "VERSION     5.03", "END        of header",
+         f"{nat} {nsol} = Total no. of atoms, no. of solute atoms. Coordinates: (2*3 per line)"]
+    L += _wrap(np.asarray(q.xtop).reshape(-1).tolist(), 6, f)
+    L.append(f"{nat} = No. of integer atom codes. Array:")
+    L += _wrap(np.asarray(q.iac).tolist(), 20)
+    # bonds: solute bonds (code 1), then O-H, O-H, H-H of every water (codes 2, 2, 3) -- the SHAKE constraints
+    bonds = list(raw["bonds"])
+    nb_sol = len(bonds)
+    for k in range(nw):
+        o = nsol + 3 * k + 1
+        bonds += [(o, o + 1, 2), (o, o + 2, 2), (o + 1, o + 2, 3)]
+    L.append(f"{len(bonds)} {nb_sol} = No. of bonds, no. of solute bonds. i - j - icode: (5 per line)")
+    L += _wrap([v for b in bonds for v in b], 15)
+    L.append("3 = No. of bond codes. Parameters: fk, r0")
+    h_h = 2.0 * R_OH * float(np.sin(ANG_HOH / 2))
+    L += [f"1 {f(300.0)} {f(1.53)}", f"2 {f(1106.0)} {f(R_OH)}", f"3 {f(0.0)} {f(h_h)}"]
+    L += ["0 0 = No. of angles, no. of solute angles", "0 = No. of angle codes",
+          "0 0 = No. of torsions, solute torsions", "0 = No. of torsion codes",
+          "0 0 = No. of impropers, solute impropers", "0 = No. of improper codes",
+          f"{nat} = No. of atomic charges"]
+    L += _wrap(raw["crg"][:nat], 6, f)
+    L.append(f"{q.ncgp} {q.ncgp_solute} {q.iuse_switch_atom} = No. of charge groups, no. of solute cgps, switch-atom flag")
+    cgp = np.asarray(q.cgp).reshape(-1, 3)
+    for g in range(q.ncgp):
+        isw, first, last = (int(v) for v in cgp[g])
+        L.append(f"{last - first + 1} {isw}")
+        L += _wrap(np.asarray(q.cgpatom)[first - 1:last].tolist(), 20)
+    lib = np.asarray(q.iaclib).reshape(-1, 7)
+    L += [f"{q.natyps} = No. of atom types", f"{q.ivdw_rule} = vdW combination rule",
+          f"{f(float(q.el14_scale))} {f(COULOMB)} = Electrostatic 1-4 scaling factor and Coulomb constant", "Masses:"]
+    L += _wrap(lib[:, 0].tolist(), 6, f)
+    for j, nm in enumerate(("1", "2", "3")):
+        L.append(f"Av/Aii({nm}) terms:")
+        L += _wrap(lib[:, 1 + j].tolist(), 6, f)
+        L.append(f"Bv/Bii({nm}) terms:")
+        L += _wrap(lib[:, 4 + j].tolist(), 6, f)
+    L.append("0 = No. of type-2 vdW interactions")
+
+    def bit_rows(tab):
+        flat = "".join("1" if v else "0" for v in np.asarray(tab).reshape(-1))
+        return [flat[i:i + 80] for i in range(0, len(flat), 80)]
+
+    l14long = np.asarray(q.list14long).reshape(-1, 2)
+    exlong = np.asarray(q.listexlong).reshape(-1, 2)
+    L.append(f"{int(np.asarray(q.list14).sum())} = No. of 1-4 neighbours. List (range={MAX_NBR_RANGE})")
+    if nsol > 0:
+        L += bit_rows(q.list14)
+    L.append(f"{len(l14long)} = No. of long-range 1-4 nbrs (>{MAX_NBR_RANGE})")
+    L += [f"{int(a)} {int(b)}" for a, b in l14long]
+    L.append(f"{int(np.asarray(q.listex).sum())} = No. of exclusions. List (range={MAX_NBR_RANGE})")
+    if nsol > 0:
+        L += bit_rows(q.listex)
+    L.append(f"{len(exlong)} = No. of long-range exclusions (>{MAX_NBR_RANGE})")
+    L += [f"{int(a)} {int(b)}" for a, b in exlong]
+    # one residue / molecule for the solute, one per water
+    starts = ([1] if nsol > 0 else []) + [nsol + 3 * k + 1 for k in range(nw)]
+    names = (["SYN "] if nsol > 0 else []) + ["HOH "] * nw
+    L.append(f"{len(starts)} {1 if nsol > 0 else 0} = No. of residues, No of solute residues. start atoms:")
+    L += _wrap(starts, 13)
+    L.append("Sequence:")
+    L += ["".join(n.ljust(5) for n in names[i:i + 16]) for i in range(0, len(names), 16)]
+    L.append(f"{len(starts)} = No. of separate molecules. start atoms:")
+    L += _wrap(starts, 13)
+    L.append("Atom type names:")
+    tac = [f"T{i + 1}" for i in range(q.natyps)]
+    L += ["".join(n.ljust(9) for n in tac[i:i + 8]) for i in range(0, len(tac), 8)]
+    L.append("SYBYL atom types:")
+    L += ["".join("Du   " for _ in tac[i:i + 13]) for i in range(0, len(tac), 13)]
+    L.append(f"{q.solvent_type} = solvent type (0=SPC,1=3-atom,2=general)")
+    if q.use_PBC:
+        L.append("PBC = boundary condition")
+        L.append(" ".join(f(float(v)) for v in q.boxlength) + " = Boxlength")
+        L.append("0.0 0.0 0.0 = Centre of the box")
+    else:
+        L.append(f"{f(float(q.rexcl_o))} {f(float(q.rexcl_o))} {f(float(q.rexcl_o))} = Exclusion, eff. solvent & solvent radius")
+        L.append(" ".join(f(float(v)) for v in q.xpcent) + " = Solute centre")
+        L.append(" ".join(f(float(v)) for v in q.xpcent) + " = Solvent centre")
+        ex = np.asarray(q.excl).astype(bool)
+        L.append(f"{int(ex.sum())} {int(ex[nsol:].sum()) // 3} = No. of excluded atoms (incl. water), no. of excluded waters")
+        flat = "".join("T" if v else "F" for v in ex)
+        L += [flat[i:i + 80] for i in range(0, len(flat), 80)]
+    with open(top_path, "w") as fh:
+        fh.write("\n".join(L) + "\n")
+    if not q.nqat or fep_path is None:
+        return
+    ns, nq = q.nstates, q.nqat
+    F = ["! synthetic FEP file (q6_b200.synth)", "[FEP]", f"states {ns}"]
+    if q.use_PBC:
+        F += ["[PBC]", f"switching_atom {q.qswitch}"]
+    F.append("[atoms]")
+    F += [f"{k + 1} {int(a)}" for k, a in enumerate(q.iqseq)]
+    if raw["qcrg"] is not None:
+        F.append("[change_charges]")
+        F += [f"{k + 1} " + " ".join(f(float(v)) for v in raw["qcrg"][k]) for k in range(nq)]
+    if raw["fep_types"] is not None:
+        lib_a, lib_b, qiac = raw["fep_types"]
+        F.append("[atom_types]")
+        for i in range(len(lib_a)):
+            ab = " ".join(f"{f(float(lib_a[i][k]))} {f(float(lib_b[i][k]))}" for k in range(3))
+            F.append(f"Q{i + 1} {ab} {f(12.0)}")
+        F.append("[change_atoms]")
+        F += [f"{k + 1} " + " ".join(f"Q{int(t)}" for t in np.asarray(qiac)[k]) for k in range(nq)]
+    if raw["soft_pairs"]:
+        F.append("[soft_pairs]")
+        F += [f"{int(a)} {int(b)}" for a, b in raw["soft_pairs"]]
+    if raw["qbnd"] is not None:
+        F.append("[change_bonds]")
+        F += [f"{int(i)} {int(j)} " + " ".join(str(int(c)) for c in cod) for (i, j), cod in zip(*raw["qbnd"])]
+    if raw["softcore_alpha"] is not None:
+        F.append("[softcore]")
+        F += [f"{k + 1} " + " ".join(f(float(v)) for v in np.asarray(raw["softcore_alpha"])[k]) for k in range(nq)]
+    with open(fep_path, "w") as fh:
+        fh.write("\n".join(F) + "\n")
 
 
 def config(name: str) -> tuple:

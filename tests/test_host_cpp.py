@@ -242,3 +242,118 @@ def test_cpp_nonbonded_class_on_gpu(name):
                     assert abs(v - want) <= 0.005 + 1e-9
     finally:
         lib.qhost_close(h)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Synthetic systems written as Qdyn6 input files (q6_b200.synth.write_files): these run where /root/reference does not
+# exist (the GPU box), so both readers and the compiled driver are covered there too.
+
+def _small(names=None):
+    return [c for c in common.small_systems() if names is None or c[0] in names]
+
+
+@pytest.mark.parametrize("case", _small(), ids=lambda c: c[0])
+def test_written_input_files_round_trip_through_both_readers(case, tmp_path):
+    """write_files -> (Python topo_read/load_fep/build_system, C++ topo_read/qatom_load_fep/prep_sim) reproduces every
+    table of the synthetic system bit for bit: sphere and box, 0-2 states, softcore, soft pairs, per-state Q-bonds,
+    long-range exclusion / 1-4 lists, excluded shells, any-atom cut-offs, no solute, no water."""
+    from q6_b200 import synth
+    from q6_b200.fep import load_fep
+    from q6_b200.system import QSystem, build_system
+    from q6_b200.topo import topo_read
+    name, q, cuts, lam = case
+    top, fep = str(tmp_path / "s.top"), str(tmp_path / "s.fep")
+    synth.write_files(q, top, fep)
+    t = topo_read(top)
+    r = build_system(t, load_fep(fep, t) if q.nqat else None, use_LRF=bool(q.use_LRF))
+    for k in QSystem._SCALARS:
+        assert getattr(q, k) == getattr(r, k), k
+    for k in QSystem._ARRAYS:
+        a, b = getattr(q, k), getattr(r, k)
+        a = np.zeros(0) if a is None else np.asarray(a).reshape(-1)
+        b = np.zeros(0) if b is None else np.asarray(b).reshape(-1)
+        assert a.size == b.size and np.array_equal(a, b), k
+    lib = host_lib()
+    h = C.c_void_p()
+    rc = lib.qhost_open(top.encode(), fep.encode() if q.nqat else b"", int(q.use_LRF), -1, C.byref(h))
+    assert rc == 0, lib.qhost_last_error().decode()
+    try:
+        cs = lib.qhost_system(h).contents
+        py, keep = q.as_struct()
+        for n in _scalars():
+            assert getattr(cs, n) == getattr(py, n), n
+        assert list(cs.xpcent) == list(py.xpcent)
+        a, b = _struct_arrays(cs), _struct_arrays(py)
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k
+        assert np.array_equal(np.ctypeslib.as_array(lib.qhost_xtop(h), shape=(q.natom, 3)), q.xtop)
+        # initial SHAKE of the jittered rigid waters: the C++ host and the Python restatement agree bit for bit
+        if q.nwat:
+            from oracle import pyoracle
+            assert lib.qhost_constraint_count(h) == 3 * q.nwat
+            x = q.xtop.copy()
+            assert lib.qhost_initial_constraint(h, _dp(x), None) == 0, lib.qhost_last_error().decode()
+            xs, nits = pyoracle.initial_constraint_x(t)
+            assert np.array_equal(x, xs)
+            assert np.abs(x - q.xtop).max() > 1e-4          # the jitter really broke the constraints
+    finally:
+        lib.qhost_close(h)
+
+
+def _driver_rows(text):
+    """The numbers of the energy summary rows qdyn_nb prints (write_out formats)."""
+    rows = {}
+    for ln in text.splitlines():
+        for key in ("solute-solvent", "solute", "solvent", "LRF"):
+            if ln.startswith(key.ljust(16)):
+                rows[key] = [float(v) for v in ln[16:].split()]
+                break
+        for key in ("Q-Q", "Q-prot", "Q-wat", "Q-surr."):
+            if ln.startswith(key.ljust(7)) and len(ln) > 16 and ln[7:9].strip().isdigit():
+                rows.setdefault(key, {})[int(ln[7:9])] = [float(ln[16:26]), float(ln[26:36])]
+    return rows
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", _small(("sph_evb2", "box_solute_q")), ids=lambda c: c[0])
+def test_compiled_driver_end_to_end_on_gpu(case, tmp_path):
+    """q6_b200/host/qdyn_nb on written input files: read -> prepare -> initial SHAKE -> make_pair_lists -> pot_energy ->
+    write_out, everything above the C ABI in C++; the printed step-0 summary against the oracle at the same
+    (post-SHAKE) coordinates, to the two printed decimals."""
+    import subprocess
+    from oracle import pyoracle
+    from oracle.pyoracle import Oracle
+    from q6_b200 import synth
+    from q6_b200.topo import topo_read
+    name, q, cuts, lam = case
+    top, fep = str(tmp_path / "s.top"), str(tmp_path / "s.fep")
+    synth.write_files(q, top, fep)
+    rc2 = float(np.sqrt(cuts["Rcpp2"]))
+    cmd = [os.path.join(ROOT, "q6_b200", "host", "qdyn_nb"), top, fep, "--q_atom", repr(cuts["Rq"]), "--lrf",
+           repr(cuts["RcLRF"]), "--solute_solute", repr(rc2), "--solute_solvent", repr(float(np.sqrt(cuts["Rcpw2"]))),
+           "--solvent_solvent", repr(float(np.sqrt(cuts["Rcww2"]))), "--lambda", ",".join(repr(float(v)) for v in lam),
+           "--steps", "30"]
+    if not q.use_LRF:
+        cmd.append("--no-lrf")
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    rows = _driver_rows(out.stdout)
+    xs, _ = pyoracle.initial_constraint_x(topo_read(top))
+    o = Oracle(q)
+    c = o.make_pair_lists(xs, **cuts)
+    d, E, EQ = o.pot_energy_nonbonds(xs, lam)
+    o.close()
+    counts = [int(v) for v in out.stdout.splitlines()[[i for i, l in enumerate(out.stdout.splitlines())
+                                                       if l.startswith("solute-solute")][0] + 1].split()]
+    assert counts == [int(v) for v in c[:5]]
+    tol = lambda v: 0.0051 + 1e-6 * abs(v)
+    assert abs(rows["solute"][0] - E[0]) <= tol(E[0]) and abs(rows["solute"][1] - E[1]) <= tol(E[1])
+    assert abs(rows["solvent"][0] - E[4]) <= tol(E[4]) and abs(rows["solvent"][1] - E[5]) <= tol(E[5])
+    assert abs(rows["solute-solvent"][0] - E[2]) <= tol(E[2]) and abs(rows["solute-solvent"][1] - E[3]) <= tol(E[3])
+    if q.use_LRF:
+        assert abs(rows["LRF"][0] - E[6]) <= tol(E[6])
+    for s in range(q.nstates):
+        for key, k0 in (("Q-Q", 0), ("Q-prot", 2), ("Q-wat", 4)):
+            got = rows[key][s + 1]
+            assert abs(got[0] - EQ[s, k0]) <= tol(EQ[s, k0]) and abs(got[1] - EQ[s, k0 + 1]) <= tol(EQ[s, k0 + 1]), key
+    assert "ms per step" in out.stdout
