@@ -359,7 +359,7 @@ def main():
                                           "fep_windows_per_hour": 3600.0 * agg / STEPS_PER_WINDOW,
                                           "note": "same end-to-end path as e2e (host buffers, list build every "
                                                   f"{NBCYCLE} steps), {kwin} handles and host threads per GPU"}
-        if world == 1 and args.workload != "C5":      # qdyn_nb squares Rq for Rcq2; C5 passes them independently
+        if world == 1:
             try:
                 ms_c = compiled_host_e2e(q, cuts, lam, max(steps, 10 * NBCYCLE), dev)
                 line["e2e_compiled_host"] = {"ms_per_step": ms_c, "value": npairs / (ms_c * 1e-3), "unit": "pairs/s",

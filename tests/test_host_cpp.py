@@ -27,10 +27,19 @@ FILES = {
 }
 
 
+def _ensure_built():
+    """libqdynhost.so / qdyn_nb are built by __graft_entry__.build(); build them here if a fresh checkout runs the tests."""
+    import subprocess
+    host = os.path.join(ROOT, "q6_b200", "host")
+    if not (os.path.exists(LIB) and os.path.exists(os.path.join(host, "qdyn_nb"))):
+        subprocess.check_call(["make", "-s", "-C", host])
+
+
 def host_lib():
     from q6_b200 import engine
     from q6_b200.system import qnb_system
     engine.load_library()          # libqdynhost.so links against libqnb.so
+    _ensure_built()
     lib = C.CDLL(LIB)
     H = C.c_void_p
     PD, PL = C.POINTER(C.c_double), C.POINTER(C.c_int64)
