@@ -210,6 +210,27 @@ int qnb_set_theta_corr(qnb_handle *h, const double *theta_corr /* [nwpolr_shell]
 int qnb_last_restraints(qnb_handle *h, double E[2], double *shell_theta_sum, int32_t *shell_n);
 
 /*
+ * SHAKE of solvent-sized molecules: shake(xx, x) of bondene.f90:1069-1150 over the constraints
+ * init_constraints (simprep.f90:2167-2345) builds -- with the default input the three constraints of every water.
+ * After the nonbonded path is offloaded this is the largest per-step loop left on the host (md.f90: leap-frog update,
+ * then `niter = constraint(const_method, xx, x)`).
+ *   nmol, mol_first[nmol+1]  constrained molecules: constraints mol_first[m] .. mol_first[m+1]-1 (0-based, CSR) belong
+ *                            to molecule m, in the order the reference sweeps them; at most 32 per molecule (solute
+ *                            SHAKE -- one molecule with thousands of constraints -- stays on the host); molecules
+ *                            must not share atoms
+ *   ij[2*n], dist2[n]        const_mol%bond%bond(:)%i, %j (1-based atoms) and %dist2
+ *   winv[natom]              inverse masses (simprep.f90:3675)
+ * qnb_shake corrects x[3*natom] in place.  xx = reference coordinates; NULL = the coordinates already resident on the
+ * device from this step's qnb_nonbond (the leap-frog case: xx is the x the forces were evaluated at), which saves one
+ * upload.  iterations (may be NULL) receives the sweeps summed over molecules (the reference returns that sum / nmol).
+ * A molecule that does not converge in CONST_MAX_ITER sweeps fails the call with "shake failure" (bondene.f90:1143).
+ * Same order of operations as the reference in explicitly rounded FP64: results are bit-identical to a CPU SHAKE.
+ */
+int qnb_set_constraints(qnb_handle *h, int nmol, const int32_t *mol_first, const int32_t *ij, const double *dist2,
+                        const double *winv);
+int qnb_shake(qnb_handle *h, const double *xx, double *x, int64_t *iterations);
+
+/*
  * qcp_run (qcp.f90:319-372, 478-525): for every bead i the coordinates of the path-integral atoms are set to
  * x(iqseq(qcp_atom(j))) = x_save(..) + qcp_coord(j,i) and pot_energy(qcp_E,qcp_EQ,.false.) is called; only the
  * per-state Q energies are used.  This entry evaluates the nonbonded part of all beads in one call (one upload of

@@ -90,6 +90,25 @@ interface
         real(c_double), intent(out) :: EQ_out(*)          ! (6, nstates, nbeads): qq, qp, qw x (el, vdw)
         integer(c_int) :: rc
     end function
+    ! solvent SHAKE (bondene.f90:1069): constraints of the solvent molecules once, then shake(xx, x) per step
+    function qnb_set_constraints(handle, nmol, mol_first, ij, dist2, winv) bind(c, name='qnb_set_constraints') result(rc)
+        import :: c_int, c_ptr, c_double, c_int32_t
+        type(c_ptr), value :: handle
+        integer(c_int), value :: nmol
+        integer(c_int32_t), intent(in) :: mol_first(*)    ! (nmol+1) first constraint of every constrained molecule, 0-based
+        integer(c_int32_t), intent(in) :: ij(*)           ! const_mol(m)%bond%bond(ic)%i, %j interleaved, 1-based atoms
+        real(c_double), intent(in) :: dist2(*)
+        real(c_double), intent(in) :: winv(*)             ! winv(natom)
+        integer(c_int) :: rc
+    end function
+    function qnb_shake(handle, xx, x, iterations) bind(c, name='qnb_shake') result(rc)
+        import :: c_int, c_ptr, c_double, c_int64_t
+        type(c_ptr), value :: handle
+        type(c_ptr), value :: xx                          ! c_loc(xx) or c_null_ptr: the coordinates of this step's qnb_nonbond
+        real(c_double), intent(inout) :: x(*)
+        integer(c_int64_t), intent(out) :: iterations     ! sweeps summed over molecules (shake = iterations/nmol)
+        integer(c_int) :: rc
+    end function
     function qnb_build_lists(handle, x, Rq, Rcq2, RcLRF2, Rcpp2, Rcpw2, Rcww2, RcLRF, counts) &
             bind(c, name='qnb_build_lists') result(rc)
         import :: c_int, c_ptr, c_double

@@ -15,6 +15,7 @@
 #include "../../include/qnb.h"
 #include "qnb_kernels.cuh"
 #include "qnb_forces.cuh"
+#include "qnb_shake.cuh"
 #include "qnb_lists.cuh"
 #include "qnb_tables.hpp"
 
@@ -162,6 +163,13 @@ struct qnb_handle {
     int64_t total_rows = 0;
     int3 lrf_reach{1, 1, 1}, list_reach{1, 1, 1};
     double box[3] = {0, 0, 0}, inv_box[3] = {0, 0, 0};
+    // SHAKE of solvent-sized molecules (qnb_set_constraints / qnb_shake)
+    DBuf<int> shk_first;
+    DBuf<int2> shk_ij;
+    DBuf<double> shk_d2, shk_winv, shk_x, shk_xx;
+    DBuf<unsigned long long> shk_iter;   // [0] summed sweeps, [1] (as int) failure flag
+    int shk_nmol = 0;
+    bool shk_set = false;
     // comm
     ncclCommT comm = nullptr;
     int rank = 0, nranks = 1;
@@ -861,6 +869,73 @@ int qnb_last_restraints(qnb_handle *h, double E[2], double *shell_theta_sum, int
     return 0;
 }
 
+int qnb_set_constraints(qnb_handle *h, int nmol, const int32_t *mol_first, const int32_t *ij, const double *dist2,
+                        const double *winv) {
+    if (!h || !mol_first || !ij || !dist2 || !winv) return fail("qnb_set_constraints: null argument");
+    if (nmol < 0) return fail("qnb_set_constraints: nmol < 0");
+    CU(cudaSetDevice(h->device));
+    const int natom = h->T.s.natom;
+    if (mol_first[0] != 0) return fail("qnb_set_constraints: mol_first[0] must be 0");
+    const int nc = nmol > 0 ? mol_first[nmol] : 0;
+    std::vector<int> first(mol_first, mol_first + nmol + 1);
+    std::vector<int2> cij((size_t)std::max(nc, 0));
+    std::vector<int> owner((size_t)natom, -1);   // molecules must not share atoms: one thread relaxes one molecule
+    for (int m = 0; m < nmol; m++) {
+        const int n = first[m + 1] - first[m];
+        if (n < 0) return fail("qnb_set_constraints: mol_first must not decrease");
+        if (n > kMaxMolConstraints)
+            return fail("qnb_set_constraints: molecule %d has %d constraints; the device SHAKE handles solvent-sized molecules "
+                        "(<= %d constraints), shake_solute stays on the host", m + 1, n, kMaxMolConstraints);
+        for (int c = first[m]; c < first[m + 1]; c++) {
+            const int i = ij[2 * c], j = ij[2 * c + 1];
+            if (i < 1 || i > natom || j < 1 || j > natom || i == j) return fail("qnb_set_constraints: constraint %d: atoms %d %d out of range", c + 1, i, j);
+            if (!(dist2[c] > 0.0)) return fail("qnb_set_constraints: constraint %d: dist2 must be positive", c + 1);
+            for (int a : {i - 1, j - 1}) {
+                if (owner[a] >= 0 && owner[a] != m) return fail("qnb_set_constraints: atom %d is constrained in two molecules", a + 1);
+                owner[a] = m;
+            }
+            cij[c] = make_int2(i - 1, j - 1);
+        }
+    }
+    std::vector<double> d2(dist2, dist2 + std::max(nc, 0)), w(winv, winv + natom);
+    if (upload(h->shk_first, first) || upload(h->shk_ij, cij) || upload(h->shk_d2, d2) || upload(h->shk_winv, w)) return 1;
+    const size_t n3 = 3 * (size_t)natom;
+    if (h->shk_x.ensure(n3) || h->shk_xx.ensure(n3) || h->shk_iter.ensure(2)) return 1;
+    h->shk_nmol = nmol;
+    h->shk_set = true;
+    return 0;
+}
+
+int qnb_shake(qnb_handle *h, const double *xx, double *x, int64_t *iterations) {
+    if (!h || !x) return fail("qnb_shake: null argument");
+    if (!h->shk_set) return fail("qnb_shake: no constraints (call qnb_set_constraints)");
+    CU(cudaSetDevice(h->device));
+    const size_t n3 = 3 * (size_t)h->T.s.natom;
+    // xx == NULL: the reference coordinates are the ones already resident from this step's qnb_nonbond / qnb_build_lists
+    const double *dxx = h->x.p;
+    if (xx) {
+        memcpy(h->hout, xx, n3 * sizeof(double));   // pinned staging (free between two nonbonded calls)
+        CU(cudaMemcpyAsync(h->shk_xx.p, h->hout, n3 * sizeof(double), cudaMemcpyHostToDevice, h->st));
+        dxx = h->shk_xx.p;
+    }
+    memcpy(h->hx, x, n3 * sizeof(double));
+    CU(cudaMemcpyAsync(h->shk_x.p, h->hx, n3 * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    CU(cudaMemsetAsync(h->shk_iter.p, 0, 2 * sizeof(unsigned long long), h->st));
+    if (h->shk_nmol > 0)
+        LAUNCH(h, k_shake, cdiv(h->shk_nmol, 128), 128, 0, h->shk_nmol, h->shk_first.p, h->shk_ij.p, h->shk_d2.p, h->shk_winv.p,
+               dxx, h->shk_x.p, h->shk_iter.p, (int *)(h->shk_iter.p + 1));
+    // hout is reused for the way back: the copies are ordered on h->st
+    unsigned long long res[2] = {0, 0};
+    CU(cudaMemcpyAsync(h->hout, h->shk_x.p, n3 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    CU(cudaMemcpyAsync(res, h->shk_iter.p, sizeof res, cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    CU(cudaGetLastError());
+    if ((int)(res[1] & 0xffffffffu)) return fail("shake failure");   // bondene.f90:1143
+    memcpy(x, h->hout, n3 * sizeof(double));
+    if (iterations) *iterations = (int64_t)res[0];
+    return 0;
+}
+
 int qnb_save_lists(qnb_handle *h) {
     if (!h) return fail("null handle");
     if (!h->lists_built) return fail("qnb_save_lists: pair lists have not been built");
@@ -1317,6 +1392,8 @@ int qnb_finalize(qnb_handle *h) {
     h->qw_list.release(); h->qp_shift_atom.release(); h->rows.release(); h->flush.release();
     h->pk_atom.release(); h->pk_ct.release(); h->pk_q.release(); h->pk_qd.release(); h->px.release(); h->py.release(); h->pz.release();
     h->nch.release(); h->choff.release(); h->ucost.release(); h->cost_off.release(); h->wstart_w.release(); h->wstart_s.release(); h->wdesc.release(); h->wrow.release(); h->sdesc.release(); h->srow.release(); h->sspec.release(); h->x_saved.release(); h->lrf_saved.release(); h->wp_theta.release(); h->wp_shell_n.release(); h->wp_shell_list.release(); h->wp_shell_theta.release(); h->lrf_mom.release();
+    h->shk_first.release(); h->shk_ij.release(); h->shk_d2.release(); h->shk_winv.release(); h->shk_x.release();
+    h->shk_xx.release(); h->shk_iter.release();
     h->item_posf.release();
     h->item_pos.release(); h->src.release(); h->cell_unsorted.release(); h->item_nq.release(); h->src_off.release();
     if (h->hx) cudaFreeHost(h->hx);

@@ -120,6 +120,10 @@ def load_library(path: str = LIB_PATH):
     lib.qnb_set_theta_corr.argtypes = [H, _PD]
     lib.qnb_last_restraints.restype = C.c_int
     lib.qnb_last_restraints.argtypes = [H, _PD, _PD, _PI]
+    lib.qnb_set_constraints.restype = C.c_int
+    lib.qnb_set_constraints.argtypes = [H, C.c_int, _PI, _PI, _PD, _PD]
+    lib.qnb_shake.restype = C.c_int
+    lib.qnb_shake.argtypes = [H, _PD, _PD, _PL]
     lib.qnb_qcp_beads.restype = C.c_int
     lib.qnb_qcp_beads.argtypes = [H, _PD, C.c_int, _PI, C.c_int, _PD, _PD, _PD]
     lib.qnb_build_lists.restype = C.c_int
@@ -306,6 +310,37 @@ class Qnb:
         out = np.zeros((self.sys.ncgp, LRF_STRIDE))
         self._check(self.lib.qnb_export_lrf(self.h, _dp(out)))
         return out
+
+    # -- SHAKE of solvent-sized molecules (N2)
+    def set_constraints(self, constraints, istart_mol, winv):
+        """init_constraints' result (simprep.f90:2167-2345): rows (i, j, dist2) with 1-based atoms in topology order, grouped
+        into molecules by istart_mol (1-based first atom of every molecule) like const_mol(:)."""
+        cons = list(constraints)
+        starts = np.asarray(istart_mol, np.int64)
+        mol = np.searchsorted(starts, np.array([c[0] for c in cons], np.int64), side="right") - 1 if cons else np.zeros(0, np.int64)
+        if len(mol) and (np.diff(mol) < 0).any():
+            raise QnbError("constraints must be listed molecule by molecule")
+        first = [0]
+        for k in range(1, len(cons) + 1):
+            if k == len(cons) or mol[k] != mol[k - 1]:
+                first.append(k)
+        first = np.ascontiguousarray(first, np.int32)
+        ij = np.ascontiguousarray([[c[0], c[1]] for c in cons], np.int32).reshape(-1, 2)
+        d2 = np.ascontiguousarray([c[2] for c in cons], np.float64)
+        w = np.ascontiguousarray(winv, np.float64)
+        if ij.size == 0:
+            ij, d2 = np.zeros((1, 2), np.int32), np.zeros(1)
+        self._check(self.lib.qnb_set_constraints(self.h, len(first) - 1, first.ctypes.data_as(_PI), ij.ctypes.data_as(_PI),
+                                                 _dp(d2), _dp(w)))
+
+    def shake(self, x, xx=None):
+        """shake(xx, x), bondene.f90:1069: returns (constrained copy of x, sweeps summed over molecules).  xx=None: the
+        coordinates resident on the device from the last pot_energy_nonbonds / make_pair_lists are the reference."""
+        x = np.array(x, dtype=np.float64).reshape(-1)
+        n = C.c_int64()
+        xxp = None if xx is None else _dp(np.ascontiguousarray(xx, dtype=np.float64).reshape(-1))
+        self._check(self.lib.qnb_shake(self.h, xxp, _dp(x), C.byref(n)))
+        return x.reshape(-1, 3), n.value
 
     # -- multi-GPU
     def unique_id(self) -> bytes:
