@@ -14,7 +14,7 @@ tail -c 1500 $OUT/bench_$TAG.json; tail -5 $OUT/bench_$TAG.err
 (timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches_$TAG.csv \
     python bench.py --steps 30 --warmup 3 --no-cpu-baseline --windows-per-gpu 0) > $OUT/ncu_launch_$TAG.log 2>&1
 (timeout 900 ncu --set full --clock-control none --import-source on \
-    -k 'regex:k_water_force|k_solute_force|k_lrf_accumulate|k_build_rows|k_q_atom|k_q_partner' -s 12 -c 12 -f -o $OUT/prof_$TAG \
+    -k 'regex:k_water_force|k_solute_force|k_lrf_accumulate|k_lrf_allpairs|k_build_rows|k_q_atom|k_q_partner' -s 14 -c 14 -f -o $OUT/prof_$TAG \
     python bench.py --steps 30 --warmup 3 --no-cpu-baseline --windows-per-gpu 0) > $OUT/ncu_full_$TAG.log 2>&1
 tail -3 $OUT/ncu_full_$TAG.log
 ls -la $OUT
