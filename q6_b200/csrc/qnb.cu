@@ -207,6 +207,9 @@ static int init_device(qnb_handle *h) {
     D.any_atom = s.iuse_switch_atom != 1;
     D.sharded = !(s.pp_start <= 1 && s.pp_end >= s.ncgp_solute && s.pw_start <= 1 && s.pw_end >= s.ncgp_solute &&
                   s.ww_start <= 1 && s.ww_end >= s.nwat);
+    // QNB_SHARD_ROWS=1: row partition (row_in_shard; shards the candidate scan as well).  Written after the round-1 GPU
+    // budget was spent, so the verified pair partition stays the default until the multi-GPU tests have run with it.
+    D.shard_rows = getenv("QNB_SHARD_ROWS") ? 1 : 0;
     D.el14 = s.el14_scale; D.el14f = (float)s.el14_scale;
     for (int d = 0; d < 3; d++) D.xpcent[d] = s.xpcent[d];
     D.pp_s = s.pp_start; D.pp_e = s.pp_end; D.pw_s = s.pw_start; D.pw_e = s.pw_end; D.qp_s = s.qp_start; D.qp_e = s.qp_end;

@@ -48,6 +48,7 @@ struct Dev {
     int use_PBC, use_LRF, geometric, spc_water, qswitch0;
     int any_atom;   // iuse_switch_atom == 0: any-atom charge-group cut-offs (nb??lis2*)
     int sharded;    // the i-ranges do not cover everything: ownership of a pair must be checked
+    int shard_rows; // sharded builds partition ROWS (and LRF targets), not pairs: see row_in_shard
     double el14;
     float el14f;
     double box[3], inv_box[3];
@@ -204,6 +205,23 @@ __device__ __forceinline__ bool in_shard(const Dev &D, int cls, int owner_unit) 
     if (cls == 2) { int w = owner_unit - D.ncgp_solute + 1; return w >= D.ww_s && w <= D.ww_e; }
     int g = owner_unit + 1;
     return cls == 0 ? (g >= D.pp_s && g <= D.pp_e) : (g >= D.pw_s && g <= D.pw_e);
+}
+// Row partition of a sharded build.  The reference gives rank r the pairs whose outer-loop unit i lies in r's range and
+// lets r add both sides of the pair; gather_nonbond then sums d over the ranks.  Since the sum is all that survives,
+// any partition of the (unit, partner) work gives the same d, E and LRF moments.  Here a rank builds the COMPLETE row
+// (own, mirror and other-kind entries) of every unit of its ranges and nothing else: the candidate scan of the list
+// build is sharded too (with the pair partition every rank screened all unit pairs), the gradient of an atom is
+// complete on exactly one rank, every pair's energy is counted once (on the rank that holds its owner entry), and the
+// owner entries a rank holds are still exactly the reference's list for calculation_assignment's i-range.
+//   solute row u: pp partners if u in the pp range, water partners (pw, owner side) if u in the pw range
+//   water row u:  water partners (ww) and solute partners (water side of pw) if u in the ww range
+__device__ __forceinline__ bool row_in_shard(const Dev &D, int cls, int u) {
+    if (u >= D.ncgp_solute) { const int w = u - D.ncgp_solute + 1; return w >= D.ww_s && w <= D.ww_e; }
+    const int g = u + 1;
+    return cls == 0 ? (g >= D.pp_s && g <= D.pp_e) : (g >= D.pw_s && g <= D.pw_e);
+}
+__device__ __forceinline__ bool row_in_any_shard(const Dev &D, int u) {
+    return row_in_shard(D, 0, u) || row_in_shard(D, 1, u);
 }
 // squared switch-atom distance exactly as the builders compute it
 __device__ __forceinline__ double unit_r2(const Dev &D, const double *pu, const double *pv) {

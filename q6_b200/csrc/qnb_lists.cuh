@@ -212,7 +212,7 @@ k_build_rows(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x, con
         base_mir = base_own + counts[3 * u];
         base_b = base_mir + counts[3 * u + 1];
     }
-    if (!D.u_excl[u]) {
+    if (!D.u_excl[u] && !(D.sharded && D.shard_rows && !row_in_any_shard(D, u))) {
         const double pu[3] = {upos[3 * u], upos[3 * u + 1], upos[3 * u + 2]};
         const float puf[3] = {(float)pu[0], (float)pu[1], (float)pu[2]};
         const int cu = cell_of[u];
@@ -237,7 +237,7 @@ k_build_rows(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x, con
                         uint32_t img = 0;   // periodic image of the pair as seen from u (any-atom mode)
                         if (v >= 0 && !D.u_excl[v]) {
                             cls = pair_class(u, v, ns, owner_is_u);
-                            if (!(cls == 2 && u == v) && (!D.sharded || in_shard(D, cls, owner_is_u ? u : v))) {
+                            if (!(cls == 2 && u == v) && (!D.sharded || (D.shard_rows ? row_in_shard(D, cls, u) : in_shard(D, cls, owner_is_u ? u : v)))) {
                                 // FP32 screening first; the FP64 test only decides pairs within ~1e-3 of the cut-off
                                 const float r2f = screen_dist2(D, (float)ip.x - puf[0], (float)ip.y - puf[1], (float)ip.z - puf[2]);
                                 const int in = (D.any_atom && cls != 2) ? 0 : screen_r2(r2f, (float)C.rc2_of(cls));
@@ -574,6 +574,7 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int t = blockIdx.x;
     if (D.u_excl[t]) return;   // block-uniform
+    if (GENERAL && D.sharded && D.shard_rows && !row_in_any_shard(D, t)) return;   // another rank's target: stays zero, summed later
     const int ns = D.ncgp_solute;
     const int gt = D.u_grp[t];
     double *lt = lrf + (size_t)QNB_LRF_STRIDE * gt;
@@ -745,7 +746,7 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
                     if (zone != 0 && ((GENERAL && D.sharded) || zone == 2)) {
                         bool owner_is_t;
                         const int cls = pair_class(t, s, ns, owner_is_t);
-                        if (GENERAL && D.sharded && !in_shard(D, cls, owner_is_t ? t : s)) zone = 0;
+                        if (GENERAL && D.sharded && !(D.shard_rows ? row_in_shard(D, cls, t) : in_shard(D, cls, owner_is_t ? t : s))) zone = 0;
                         else if (zone == 2) {
                             const double4 ip = item_pos[idx];
                             const double ps[3] = {ip.x, ip.y, ip.z};
