@@ -713,7 +713,10 @@ static int issue_step(qnb_handle *h, int flags, bool out_cleared = false) {
 // Captured once per list build into a CUDA graph (one launch per MD step instead of ~10 API calls).
 static int step_device(qnb_handle *h, int flags, bool with_copies = false) {
     const size_t n3 = 3 * (size_t)h->T.s.natom;
-    const bool graphable = h->use_graph && !h->comm;
+    // sharded step: the all-reduce is issued eagerly after the kernels unless QNB_SHARD_GRAPH=1 asks for it to be captured
+    // with them (NCCL >= 2.9 supports capture once the communicator has been used; not yet run on hardware)
+    static const bool shard_graph = getenv("QNB_SHARD_GRAPH") != nullptr;
+    const bool graphable = h->use_graph && (!h->comm || shard_graph);
     flags &= (QNB_FLAG_MD | QNB_FLAG_QQ | QNB_FLAG_NO_ENERGY | QNB_FLAG_SOLVENT_RESTRAINTS);
     const int gi = (flags & 7) | ((flags & QNB_FLAG_SOLVENT_RESTRAINTS) ? 8 : 0);
     if (graphable) {
@@ -738,6 +741,7 @@ static int step_device(qnb_handle *h, int flags, bool with_copies = false) {
                 if (cleared) rc |= cudaStreamWaitEvent(h->st, h->ev_join[4], 0) != cudaSuccess;
             }
             rc |= issue_step(h, flags, cleared);
+            if (h->comm) rc |= g_nccl.AllReduce(h->out.p, h->out.p, h->nout, kNcclDouble, kNcclSum, h->comm, h->st) != 0;
             if (with_copies) rc |= cudaMemcpyAsync(h->hout, h->out.p, h->nout * sizeof(double), cudaMemcpyDeviceToHost, h->st) != cudaSuccess;
             cudaError_t ce = cudaStreamEndCapture(h->st, &g);
             h->graph_launches[with_copies ? 1 : 0][gi] = (int)(h->launches - l0);
