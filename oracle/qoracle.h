@@ -9,12 +9,16 @@
  * never links or calls it.
  *
  * Pinning: the reference cannot be compiled in the build container (no Fortran
- * compiler), so the oracle is pinned on the reference's own shipped fixtures:
- *   tests/basic_tests/prep_SPH/lig_w.top at topology coordinates must give
- *   56 402 water pairs inside 10 A and E%ww%vdw = -413.17 (row 1 of
- *   SPH_leap-frog_berendsen_benchmark.en), see tests/test_oracle_golden.py.
- * Everything not reachable from those scalars (forces, LRF moments, per-state
- * Q energies) is "parity unpinned" beyond self-consistency checks
+ * compiler), so the oracle is pinned on the reference's own golden values
+ * (tests/test_oracle_golden.py): row 1 of tests/basic_tests/{SPH,PBC}_*_benchmark.en
+ * and eval_test.sh:99-101 -- the step-0 energies QEL, QVdW (qp+qw) and EL, VdW
+ * (pp+pw+ww) of the shipped sphere and periodic runs -- are reproduced to the
+ * printed digit (3.12 139.43 -7.30 -413.17 / -31.30 228.64 380.33 -1990.55) at the
+ * coordinates the reference evaluates them at, i.e. after its initial solvent
+ * SHAKE (restated in oracle/pyoracle.py: shake), plus 56 402 water pairs inside
+ * 10 A.  That pins the ww and qw list builders and energy sums (sphere and box).
+ * Forces, the pp/pw/qp/qq terms, LRF moments and multi-state energies are held by
+ * no reference test: "parity unpinned" there, beyond self-consistency checks
  * (finite differences, LRF convergence); DESIGN.md says so too.
  */
 #ifndef QORACLE_H
