@@ -104,6 +104,13 @@ std::vector<int32_t> make_qconn(int nstates, int nat_solute, int nqat, const std
 
 // The static tables of one node in the Fortran host's layouts (what qnb_system points into).
 struct System {
+    System() = default;
+    // s holds raw pointers into the vectors below: moving keeps them valid (the heap buffers travel), copying would not
+    System(const System &) = delete;
+    System &operator=(const System &) = delete;
+    System(System &&) = default;
+    System &operator=(System &&) = default;
+
     qnb_system s{};                    // scalars filled in; pointers set by view()
     double boxlength[3] = {0, 0, 0};
     std::vector<double> xtop, mass;    // topology coordinates, per-atom masses (for SHAKE)
