@@ -165,7 +165,7 @@ struct qnb_handle {
     double box[3] = {0, 0, 0}, inv_box[3] = {0, 0, 0};
     // SHAKE of solvent-sized molecules (qnb_set_constraints / qnb_shake)
     DBuf<int> shk_first;
-    DBuf<int2> shk_ij;
+    DBuf<ShakePair> shk_ij;
     DBuf<double> shk_d2, shk_winv, shk_x, shk_xx;
     DBuf<unsigned long long> shk_iter;   // [0] summed sweeps, [1] (as int) failure flag
     int shk_nmol = 0;
@@ -885,7 +885,7 @@ int qnb_set_constraints(qnb_handle *h, int nmol, const int32_t *mol_first, const
     if (mol_first[0] != 0) return fail("qnb_set_constraints: mol_first[0] must be 0");
     const int nc = nmol > 0 ? mol_first[nmol] : 0;
     std::vector<int> first(mol_first, mol_first + nmol + 1);
-    std::vector<int2> cij((size_t)std::max(nc, 0));
+    std::vector<ShakePair> cij((size_t)std::max(nc, 0));
     std::vector<int> owner((size_t)natom, -1);   // molecules must not share atoms: one thread relaxes one molecule
     for (int m = 0; m < nmol; m++) {
         const int n = first[m + 1] - first[m];
@@ -901,7 +901,7 @@ int qnb_set_constraints(qnb_handle *h, int nmol, const int32_t *mol_first, const
                 if (owner[a] >= 0 && owner[a] != m) return fail("qnb_set_constraints: atom %d is constrained in two molecules", a + 1);
                 owner[a] = m;
             }
-            cij[c] = make_int2(i - 1, j - 1);
+            cij[c] = ShakePair{i - 1, j - 1};
         }
     }
     std::vector<double> d2(dist2, dist2 + std::max(nc, 0)), w(winv, winv + natom);
