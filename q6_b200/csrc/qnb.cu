@@ -916,6 +916,7 @@ int qnb_set_constraints(qnb_handle *h, int nmol, const int32_t *mol_first, const
 int qnb_shake(qnb_handle *h, const double *xx, double *x, int64_t *iterations) {
     if (!h || !x) return fail("qnb_shake: null argument");
     if (!h->shk_set) return fail("qnb_shake: no constraints (call qnb_set_constraints)");
+    if (!xx && !h->lists_built) return fail("qnb_shake: xx == NULL needs coordinates resident from qnb_build_lists / qnb_nonbond");
     CU(cudaSetDevice(h->device));
     const size_t n3 = 3 * (size_t)h->T.s.natom;
     // xx == NULL: the reference coordinates are the ones already resident from this step's qnb_nonbond / qnb_build_lists
