@@ -30,6 +30,20 @@ _TYPES = np.array([
     [32.060, 2000.00, 0.0, 1414.2, 35.00, 0.0, 24.75],  # 8 S
     [1.008, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0],              # 9 polar H
 ])
+# the same atom types for the arithmetic rule (ivdw_rule 2): R* (half Rmin) in the A columns, epsilon in the B columns,
+# as AMBER / CHARMM style libraries hold them (topo.f90:847-891; epsilon is square-rooted by topology(), simprep.f90:4567)
+_TYPES_ARITH = np.array([
+    # mass    R*1     R*2   R*3(1-4) eps1    eps2  eps3(1-4)
+    [15.999, 1.7683, 0.0, 1.7683, 0.1520, 0.0, 0.0760],   # 1 water O
+    [1.008, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0],                # 2 water H (no LJ)
+    [12.011, 1.9080, 0.0, 1.9080, 0.1094, 0.0, 0.0547],   # 3 C sp3
+    [1.008, 1.4870, 0.0, 1.4870, 0.0157, 0.0, 0.0079],    # 4 H
+    [15.999, 1.6612, 0.0, 1.6612, 0.2100, 0.0, 0.1050],   # 5 O
+    [14.007, 1.8240, 0.0, 1.8240, 0.1700, 0.0, 0.0850],   # 6 N
+    [12.011, 1.9080, 0.0, 1.9080, 0.0860, 0.0, 0.0430],   # 7 C aromatic
+    [32.060, 2.0000, 0.0, 2.0000, 0.2500, 0.0, 0.1250],   # 8 S
+    [1.008, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0],                # 9 polar H
+])
 R_OH, ANG_HOH = 0.9572, np.deg2rad(104.52)
 Q_O, Q_H = -0.834, 0.417
 
@@ -64,24 +78,30 @@ def _lattice(a, half):
     return np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
 
 
-def _base(natyp_used=9) -> QSystem:
+def _base(natyp_used=9, ivdw_rule=1, solvent_type=0) -> QSystem:
     q = QSystem()
     q.natyps = len(_TYPES)
-    q.iaclib = _TYPES.copy()
-    q.ivdw_rule = 1
-    q.solvent_type = 0
+    q.ivdw_rule = ivdw_rule
+    q.types_file = (_TYPES if ivdw_rule == 1 else _TYPES_ARITH).copy()   # as a topology file holds them
+    q.iaclib = q.types_file.copy()
+    if ivdw_rule == 2:
+        q.iaclib[:, 4:7] = np.sqrt(np.abs(q.iaclib[:, 4:7]))             # topology(), simprep.f90:4567-4571
+    q.solvent_type = solvent_type
     q.el14_scale = 0.5
     q.iuse_switch_atom = 1
     return q
 
 
 def _finish(q: QSystem, x, iac, crg, groups, nat_solute, nwat, bonds, listex_pairs, list14_pairs, q_atoms,
-            nstates, qcrg=None, fep_types=None, softcore_alpha=None, soft_pairs=(), qbnd=None):
+            nstates, qcrg=None, fep_types=None, softcore_alpha=None, soft_pairs=(), qbnd=None, el_scale=(),
+            qq_use_library_charges=False):
     """Assemble the Fortran-layout tables. groups: list of (switch, [atoms]) 1-based."""
     # what a topology / FEP file of this system holds (write_files)
     q.raw = dict(crg=[float(c) for c in crg], bonds=[tuple(int(v) for v in b) for b in bonds],
                  qcrg=None if qcrg is None else np.asarray(qcrg, np.float64).copy(),
-                 fep_types=fep_types, softcore_alpha=softcore_alpha, soft_pairs=list(soft_pairs), qbnd=qbnd)
+                 fep_types=fep_types, softcore_alpha=softcore_alpha, soft_pairs=list(soft_pairs), qbnd=qbnd,
+                 el_scale=list(el_scale), types_file=q.types_file)
+    q.qq_use_library_charges = int(qq_use_library_charges)
     q.natom, q.nat_solute, q.nwat, q.solv_atom = len(iac), nat_solute, nwat, 3
     q.iac = np.asarray(iac, np.int32)
     q.num_atyp = int(q.iac.max())
@@ -137,7 +157,10 @@ def _finish(q: QSystem, x, iac, crg, groups, nat_solute, nwat, bonds, listex_pai
         else:
             lib_a, lib_b, qiac = fep_types
             q.qvdw_flag, q.nqlib = 1, len(lib_a)
-            q.qavdw, q.qbvdw, q.qiac = np.asarray(lib_a, float), np.asarray(lib_b, float), np.asarray(qiac, np.int32)
+            q.qavdw, q.qbvdw, q.qiac = np.array(lib_a, float), np.array(lib_b, float), np.asarray(qiac, np.int32)
+            if q.ivdw_rule == 2:                 # get_fep, simprep.f90:1041-1046: epsilon of codes 1 and 3, not the soft pair's ai
+                q.qbvdw[:, 0] = np.sqrt(q.qbvdw[:, 0])
+                q.qbvdw[:, 2] = np.sqrt(q.qbvdw[:, 2])
         q.sc_lookup = np.zeros((nq, q.natyps + nq, nstates))
         if softcore_alpha is not None:
             al = np.asarray(softcore_alpha, float)      # [nq][nstates], plain alphas (qatom.f90:1932,1974)
@@ -147,9 +170,9 @@ def _finish(q: QSystem, x, iac, crg, groups, nat_solute, nwat, bonds, listex_pai
             q.sc_lookup[:, q.natyps:, :][both0] = 0.0
         q.iqexpnb = np.asarray([p[0] for p in soft_pairs], np.int32)
         q.jqexpnb = np.asarray([p[1] for p in soft_pairs], np.int32)
-        q.el_scale_iq = np.zeros(0, np.int32)
-        q.el_scale_jq = np.zeros(0, np.int32)
-        q.el_scale = np.zeros((0, nstates))
+        q.el_scale_iq = np.asarray([e[0] for e in el_scale], np.int32)
+        q.el_scale_jq = np.asarray([e[1] for e in el_scale], np.int32)
+        q.el_scale = np.asarray([e[2] for e in el_scale], np.float64).reshape(len(el_scale), nstates)
         bnd = np.asarray(bonds, np.int32).reshape(-1, 3)
         qb_ij = np.zeros((0, 2), np.int32) if qbnd is None else np.asarray(qbnd[0], np.int32)
         qb_cod = np.zeros((0, nstates), np.int32) if qbnd is None else np.asarray(qbnd[1], np.int32)
@@ -205,11 +228,15 @@ def _q_chain(rng, nq, center):
 
 def solvated_sphere(radius: float = 30.0, core_radius: float = 19.5, nq: int = 46, nstates: int = 1,
                     seed: int = 20261017, jitter: float = 0.05, fep: str = "none", pbc_box: float = 0.0,
-                    excl_shell: float = 0.0) -> QSystem:
+                    excl_shell: float = 0.0, ivdw_rule: int = 1, solvent_type: int = 0, el_scale: bool = False,
+                    qq_use_library_charges: bool = False) -> QSystem:
     """C2 (radius 30, 1 state) / C3 (radius 25, core 0, fep='annihilate', 2 states) / EVB-like ('evb').
 
     pbc_box > 0 builds the same content in a periodic cube instead of a sphere (tests of the box paths).
     excl_shell > 0 flags atoms further than radius-excl_shell from the centre as excluded.
+    ivdw_rule 2 = arithmetic combination rule (R*, epsilon libraries); solvent_type 1 = a three-site solvent whose
+    hydrogens carry LJ parameters (with either, potene.f90:347 takes the general ww/qw routines instead of the SPC ones);
+    el_scale adds two [el_scale] pairs, qq_use_library_charges the [FEP] switch of that name.
     """
     rng = np.random.Generator(np.random.PCG64(seed))
     center = np.zeros(3)
@@ -281,17 +308,18 @@ def solvated_sphere(radius: float = 30.0, core_radius: float = 19.5, nq: int = 4
         keep &= ~np.all(np.abs(lat) < q_extent + 1.0, axis=1)
     w = _waters(rng, lat[keep])
     nwat = len(w)
+    hw = 2 if solvent_type == 0 else 4      # general three-site solvent: hydrogens of a type with LJ parameters
     for k in range(nwat):
         i0 = nat + 1
         x.extend([w[k, 0], w[k, 1], w[k, 2]])
-        iac.extend([1, 2, 2])
+        iac.extend([1, hw, hw])
         crg.extend([Q_O, Q_H, Q_H])
         groups.append((i0, [i0, i0 + 1, i0 + 2]))
         nat += 3
     x = np.array(x)
     x = x + np.random.Generator(np.random.PCG64(seed + 1)).normal(0, jitter, x.shape)
 
-    q = _base()
+    q = _base(ivdw_rule=ivdw_rule, solvent_type=solvent_type)
     q.use_LRF = 1
     if pbc_box > 0:
         q.use_PBC = 1
@@ -306,8 +334,8 @@ def solvated_sphere(radius: float = 30.0, core_radius: float = 19.5, nq: int = 4
     if nq and fep in ("annihilate", "evb"):
         assert nstates == 2
         # Q-atom type library: one row per topology type (normal, soft-pair Ci/ai, 1-4) + a dummy
-        lib_a = np.vstack([_TYPES[:, 1:4], np.zeros((1, 3))])
-        lib_b = np.vstack([_TYPES[:, 4:7], np.zeros((1, 3))])
+        lib_a = np.vstack([q.types_file[:, 1:4], np.zeros((1, 3))])
+        lib_b = np.vstack([q.types_file[:, 4:7], np.zeros((1, 3))])
         lib_a[:, 1] = 90.0   # Ci of the exponential repulsion (soft pairs)
         lib_b[:, 1] = 1.8    # ai
         dummy = len(_TYPES) + 1
@@ -329,7 +357,10 @@ def solvated_sphere(radius: float = 30.0, core_radius: float = 19.5, nq: int = 4
             qb = (np.array([[2, 9], [3, 12]], np.int32), np.array([[1, 0], [0, 1]], np.int32))
             kw = dict(qcrg=np.stack([base, ch2], 1), fep_types=(lib_a, lib_b, qiac), softcore_alpha=alpha,
                       soft_pairs=[p for p in ((5, 20), (6, 30)) if p[1] <= nq], qbnd=qb)
-    qs = _finish(q, x, iac, crg, groups, nat_solute, nwat, bonds, ex, l14, q_atoms, nstates, **kw)
+    if nq >= 6 and el_scale:
+        kw["el_scale"] = [(1, 3, [0.5, 0.8][:nstates]), (6, 2, [0.25, 1.0][:nstates])]
+    qs = _finish(q, x, iac, crg, groups, nat_solute, nwat, bonds, ex, l14, q_atoms, nstates,
+                 qq_use_library_charges=qq_use_library_charges, **kw)
     if excl_shell > 0 and not pbc_box:
         rr = np.linalg.norm(qs.xtop - center, axis=1)
         # whole charge groups are excluded through their switch atom; flag all atoms of such groups
@@ -382,7 +413,7 @@ def write_files(q: QSystem, top_path: str, fep_path: str | None = None) -> None:
         isw, first, last = (int(v) for v in cgp[g])
         L.append(f"{last - first + 1} {isw}")
         L += _wrap(np.asarray(q.cgpatom)[first - 1:last].tolist(), 20)
-    lib = np.asarray(q.iaclib).reshape(-1, 7)
+    lib = np.asarray(raw["types_file"]).reshape(-1, 7)      # epsilon not yet square-rooted for the arithmetic rule
     L += [f"{q.natyps} = No. of atom types", f"{q.ivdw_rule} = vdW combination rule",
           f"{f(float(q.el14_scale))} {f(COULOMB)} = Electrostatic 1-4 scaling factor and Coulomb constant", "Masses:"]
     L += _wrap(lib[:, 0].tolist(), 6, f)
@@ -442,6 +473,8 @@ def write_files(q: QSystem, top_path: str, fep_path: str | None = None) -> None:
         return
     ns, nq = q.nstates, q.nqat
     F = ["! synthetic FEP file (q6_b200.synth)", "[FEP]", f"states {ns}"]
+    if q.qq_use_library_charges:
+        F.append("qq_use_library_charges on")
     if q.use_PBC:
         F += ["[PBC]", f"switching_atom {q.qswitch}"]
     F.append("[atoms]")
@@ -460,6 +493,9 @@ def write_files(q: QSystem, top_path: str, fep_path: str | None = None) -> None:
     if raw["soft_pairs"]:
         F.append("[soft_pairs]")
         F += [f"{int(a)} {int(b)}" for a, b in raw["soft_pairs"]]
+    if raw["el_scale"]:
+        F.append("[el_scale]")
+        F += [f"{int(a)} {int(b)} " + " ".join(f(float(v)) for v in sc) for a, b, sc in raw["el_scale"]]
     if raw["qbnd"] is not None:
         F.append("[change_bonds]")
         F += [f"{int(i)} {int(j)} " + " ".join(str(int(c)) for c in cod) for (i, j), cod in zip(*raw["qbnd"])]

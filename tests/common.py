@@ -84,6 +84,24 @@ def small_systems():
     return out
 
 
+def variant_systems():
+    """Parameter-rule and solvent variants that none of the reference's shipped inputs exercises (they are all Q-OPLSAA:
+    geometric rule, SPC-type TIP3P): arithmetic combination rule, a three-site solvent with LJ on the hydrogens (either
+    one sends pot_energy_nonbonds to the general ww/qw routines, potene.f90:347), [el_scale] pairs and
+    qq_use_library_charges."""
+    box = 8 * synth.A_LATTICE
+    out = []
+    out.append(("sph_arith_evb", synth.solvated_sphere(16.0, 9.0, 20, 2, 31, fep="evb", ivdw_rule=2), sph_cuts(8.0), [0.4, 0.6]))
+    out.append(("sph_general_solvent", synth.solvated_sphere(15.0, 8.0, 12, 1, 32, solvent_type=1), sph_cuts(8.0), [1.0]))
+    out.append(("box_arith_general", synth.solvated_sphere(0.0, 7.0, 16, 2, 33, fep="evb", pbc_box=box, ivdw_rule=2, solvent_type=1),
+                dict(Rq=9.0, Rcq2=81.0, RcLRF2=11.5 ** 2, Rcpp2=64.0, Rcpw2=64.0, Rcww2=64.0, RcLRF=11.5), [0.5, 0.5]))
+    out.append(("sph_elscale_libcrg", synth.solvated_sphere(16.0, 9.0, 20, 2, 34, fep="evb", el_scale=True,
+                                                            qq_use_library_charges=True), sph_cuts(8.0), [0.3, 0.7]))
+    out.append(("sph_arith_fep", synth.solvated_sphere(15.0, 8.0, 14, 2, 35, fep="annihilate", ivdw_rule=2, el_scale=True),
+                sph_cuts(8.0), [0.6, 0.4]))
+    return out
+
+
 def _anyatom(q):
     q.iuse_switch_atom = 0
     return q

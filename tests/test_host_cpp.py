@@ -258,7 +258,7 @@ def test_cpp_nonbonded_class_on_gpu(name):
 # exist (the GPU box), so both readers and the compiled driver are covered there too.
 
 def _small(names=None):
-    return [c for c in common.small_systems() if names is None or c[0] in names]
+    return [c for c in common.small_systems() + common.variant_systems() if names is None or c[0] in names]
 
 
 @pytest.mark.parametrize("case", _small(), ids=lambda c: c[0])

@@ -60,7 +60,7 @@ def _build(lib, q, **override):
 def _cases():
     out = [(n,) + tuple(golden_system(n)[:3]) for n in ("c1_sph", "c1_pbc", "c4_evb")]
     names = ("sph_fep2", "sph_evb2", "sph_small_rcq", "sph_nowater", "box_solute_q", "box_solute_rowimage", "sph_anyatom")
-    return out + [c for c in common.small_systems() if c[0] in names]
+    return out + [c for c in common.small_systems() if c[0] in names] + common.variant_systems()
 
 
 def _same(a, b):

@@ -136,6 +136,36 @@ def test_finite_difference_gradient():
     assert worst < 1e-6
 
 
+@pytest.mark.parametrize("case", common.variant_systems(), ids=lambda c: c[0])
+def test_finite_difference_gradient_variants(case):
+    """The same check on the arithmetic-rule / general-solvent / el_scale / library-charge variants (no reference input
+    exercises them, so the oracle's only anchor there is its own consistency)."""
+    import copy
+    from oracle.pyoracle import Oracle
+    name, q, cuts, lam = case
+    q = copy.copy(q)
+    q.use_LRF = 0
+    lam = np.array(lam)
+    o = Oracle(q)
+    x = q.xtop
+    o.make_pair_lists(x, **cuts)
+    d, E, EQ = o.pot_energy_nonbonds(x, lam)
+
+    def etot(xx):
+        _, E1, EQ1 = o.pot_energy_nonbonds(xx, lam)
+        return E1.sum() + (EQ1 * lam[:, None]).sum()
+    worst = 0.0
+    for a in (0, 3, q.nqat - 1, q.nqat + 2, q.nat_solute + 1, q.natom - 1):
+        for c in range(3):
+            h = 1e-5
+            xp, xm = x.copy(), x.copy()
+            xp[a, c] += h
+            xm[a, c] -= h
+            fd = (etot(xp) - etot(xm)) / (2 * h)
+            worst = max(worst, abs(fd - d[a, c]) / max(1.0, abs(d[a, c])))
+    assert worst < 2e-6
+
+
 def test_lrf_converges_to_explicit_coulomb():
     """LRF self-consistency: for a well separated pair of neutral groups the third-order expansion at the
     group centre reproduces the explicit Coulomb interaction energy of the far atoms."""
