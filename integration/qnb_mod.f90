@@ -127,6 +127,23 @@ interface
         real(c_double), intent(out) :: E_out(7), EQ_out(*) ! 6*nstates
         integer(c_int) :: rc
     end function
+    ! list sizes / explicit lists as the reference holds them (-DDUMP logging, debugging, nbmonitor-style analysis)
+    function qnb_list_count(handle, which, state, n) bind(c, name='qnb_list_count') result(rc)
+        import :: c_int, c_ptr, c_int64_t
+        type(c_ptr), value :: handle
+        integer(c_int), value :: which, state             ! QNB_LIST_PP..QNB_LIST_QQP (0..6); state 1-based for the Q lists
+        integer(c_int64_t), intent(out) :: n
+        integer(c_int) :: rc
+    end function
+    function qnb_export_list(handle, which, state, ij, params, capacity) bind(c, name='qnb_export_list') result(rc)
+        import :: c_int, c_ptr, c_int32_t, c_int64_t
+        type(c_ptr), value :: handle
+        integer(c_int), value :: which, state
+        integer(c_int32_t), intent(out) :: ij(*)          ! (2, n): i, j as in NB_TYPE / NBQP_TYPE / NBQ_TYPE, 1-based
+        type(c_ptr), value :: params                      ! c_loc of real(c_double) (4, n): vdWA, vdWB, elec, score; or c_null_ptr
+        integer(c_int64_t), value :: capacity
+        integer(c_int) :: rc
+    end function
     function qnb_export_lrf(handle, lrf) bind(c, name='qnb_export_lrf') result(rc)
         import :: c_int, c_ptr, c_double
         type(c_ptr), value :: handle

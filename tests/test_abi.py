@@ -64,3 +64,37 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".cpp")):
                 src = open(os.path.join(dp, f), errors="replace").read()
                 assert "qoracle" not in src and "pyoracle" not in src and "oracle/" not in src, f
+
+
+def test_fortran_interface_module_matches_header():
+    """integration/qnb_mod.f90 cannot be compiled here (no Fortran compiler), so at least its text is held against the
+    header: type(qnb_system) lists the C struct's fields in the same order with matching kinds, and every C prototype of
+    include/qnb.h that the Fortran host calls has a bind(c) interface of that name."""
+    from q6_b200.system import qnb_system
+    import ctypes as C
+    f90 = open(os.path.join(ROOT, "integration", "qnb_mod.f90")).read()
+    body = f90[f90.index("type, bind(c) :: qnb_system"):f90.index("end type qnb_system")]
+    fields = []
+    for line in body.splitlines()[1:]:
+        line = line.split("!")[0].strip()
+        if "::" not in line:
+            continue
+        kind, names = line.split("::")
+        kind = kind.strip().replace(" ", "")
+        for nm in names.split(","):
+            nm = re.sub(r"\(.*\)", "", nm).strip()
+            if nm:
+                fields.append((nm, kind))
+    want = []
+    for nm, t in qnb_system._fields_:
+        kind = {C.c_int32: "integer(c_int32_t)", C.c_double: "real(c_double)"}.get(t)
+        if kind is None:
+            kind = "real(c_double)" if getattr(t, "_type_", None) is C.c_double and hasattr(t, "_length_") else "type(c_ptr)"
+        want.append((nm, kind))
+    assert fields == want
+    # measurement hooks and debug exports are not part of the Fortran host's surface
+    host_calls = [n for n in _declared() if not n.startswith(("qnb_bench_", "qnb_last_timing", "qnb_last_copy_bytes",
+                                                              "qnb_launch_count", "qnb_device_count"))]
+    assert len(host_calls) >= 18
+    for n in host_calls:
+        assert re.search(rf"bind\(c,\s*name='{n}'\)", f90), f"no Fortran interface for {n}"
