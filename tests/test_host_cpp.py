@@ -366,3 +366,34 @@ def test_compiled_driver_end_to_end_on_gpu(case, tmp_path):
             got = rows[key][s + 1]
             assert abs(got[0] - EQ[s, k0]) <= tol(EQ[s, k0]) and abs(got[1] - EQ[s, k0 + 1]) <= tol(EQ[s, k0 + 1]), key
     assert "ms per step" in out.stdout
+
+
+@pytest.mark.parametrize("name", ["sph_evb2", "sph_arith_evb"])
+def test_softcore_max_potential_tables_agree_between_readers(name, tmp_path):
+    """[FEP] softcore_use_max_potential on (qatom.f90:1932-1990): sc_lookup is derived from alpha and the LJ parameters,
+    with different formulas for the geometric and the arithmetic rule.  No shipped input uses it; the C++ and the Python
+    reader must at least agree with each other bit for bit, and differ from the plain-alpha tables."""
+    from q6_b200 import synth
+    from q6_b200.fep import load_fep
+    from q6_b200.system import build_system
+    from q6_b200.topo import topo_read
+    q = [c for c in _small((name,))][0][1]
+    top, fep = str(tmp_path / "s.top"), str(tmp_path / "s.fep")
+    synth.write_files(q, top, fep)
+    text = open(fep).read().replace("[FEP]\n", "[FEP]\nsoftcore_use_max_potential on\n", 1)
+    open(fep, "w").write(text)
+    t = topo_read(top)
+    py, keep = build_system(t, load_fep(fep, t), use_LRF=True).as_struct()
+    lib = host_lib()
+    h = C.c_void_p()
+    assert lib.qhost_open(top.encode(), fep.encode(), 1, -1, C.byref(h)) == 0, lib.qhost_last_error().decode()
+    try:
+        cs = lib.qhost_system(h).contents
+        a, b = _struct_arrays(cs), _struct_arrays(py)
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k
+        plain, _ = q.as_struct()
+        assert not np.array_equal(a["sc_lookup"], _struct_arrays(plain)["sc_lookup"])
+        assert np.isfinite(a["sc_lookup"]).all() and (a["sc_lookup"] >= 0).all()
+    finally:
+        lib.qhost_close(h)
