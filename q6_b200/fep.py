@@ -277,6 +277,10 @@ def _softcore(sec: dict, f: Fep, topo: Topology) -> None:
             for j in range(nt):  # q - surroundings
                 if f.softcore_use_max_potential:
                     aj, bj = topo.iaclib[j, 1], topo.iaclib[j, 4]
+                    if not geom:
+                        # qdyn.f90:114-116: topology() has already square-rooted the library epsilons
+                        # (simprep.f90:4567-4571) when get_fep -> qatom_load_fep runs; the Q-atom epsilons have not
+                        bj = np.sqrt(abs(bj))
                     if am[i, s] > 1e-6:
                         if geom:
                             f.sc_lookup[i, j, s] = (-bq * bj + np.sqrt(bq * bq * bj * bj + 4.0 * am[i, s] * aq * aj)) / (

@@ -522,7 +522,10 @@ void softcore(const Sections &sec, Fep &f, const Topology &topo) {
             const double aq = f.qavdw[(size_t)ti * NLJTYP], bq = f.qbvdw[(size_t)ti * NLJTYP];
             for (int j = 0; j < nt; j++) {  // q - surroundings
                 if (f.softcore_use_max_potential) {
-                    const double aj = topo.iaclib[7 * j + 1], bj = topo.iaclib[7 * j + 4];
+                    // qdyn.f90:114-116: topology() has already square-rooted the library epsilons (simprep.f90:4567-4571)
+                    // when get_fep -> qatom_load_fep runs; the Q-atom epsilons (bq) have not been
+                    const double aj = topo.iaclib[7 * j + 1];
+                    const double bj = geom ? topo.iaclib[7 * j + 4] : std::sqrt(std::fabs(topo.iaclib[7 * j + 4]));
                     if (am(i, s) > 1e-6) {
                         if (geom)
                             sc(i, j, s) = (-bq * bj + std::sqrt(bq * bq * bj * bj + 4.0 * am(i, s) * aq * aj)) /
