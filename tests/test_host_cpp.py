@@ -397,3 +397,52 @@ def test_softcore_max_potential_tables_agree_between_readers(name, tmp_path):
         assert np.isfinite(a["sc_lookup"]).all() and (a["sc_lookup"] >= 0).all()
     finally:
         lib.qhost_close(h)
+
+
+@pytest.mark.parametrize("key", ["offset", "offset_residue", "offset_name"])
+def test_fep_offsets_reproduce_the_same_tables(key, tmp_path):
+    """[FEP] offset / offset_residue / offset_name (qatom.f90:383-432): topology numbers in [atoms], [change_bonds],
+    [excluded_pairs] and [PBC] switching_atom are relative to the offset.  A file rewritten with an offset must give the
+    very tables of the original one, in both readers."""
+    from q6_b200 import synth
+    from q6_b200.fep import load_fep
+    from q6_b200.system import build_system
+    from q6_b200.topo import topo_read
+    q = [c for c in _small(("box_solute_q",))][0][1]          # periodic (switching atom), EVB (per-state Q-bonds)
+    top, fep0, fep1 = str(tmp_path / "s.top"), str(tmp_path / "s0.fep"), str(tmp_path / "s1.fep")
+    synth.write_files(q, top, fep0)
+    t = topo_read(top)
+    # the synthetic solute is one residue starting at atom 1: offset_residue 1 / offset_name SYN give offset 0
+    off = 3 if key == "offset" else 0
+    head = {"offset": f"offset {off}", "offset_residue": "offset_residue 1", "offset_name": "offset_name SYN"}[key]
+    out, sec = [], None
+    for ln in open(fep0).read().splitlines():
+        if ln.startswith("["):
+            sec = ln.strip("[]").lower()
+            out.append(ln)
+            if sec == "fep":
+                out.append(head)
+            continue
+        tok = ln.split()
+        if sec == "atoms":
+            tok[1] = str(int(tok[1]) - off)
+        elif sec == "change_bonds":
+            tok[0], tok[1] = str(int(tok[0]) - off), str(int(tok[1]) - off)
+        elif sec == "pbc" and tok[0] == "switching_atom":
+            tok[1] = str(int(tok[1]) - off)
+        out.append(" ".join(tok))
+    open(fep1, "w").write("\n".join(out) + "\n")
+    want, keep0 = q.as_struct()
+    py, keep1 = build_system(t, load_fep(fep1, t), use_LRF=bool(q.use_LRF)).as_struct()
+    lib = host_lib()
+    h = C.c_void_p()
+    assert lib.qhost_open(top.encode(), fep1.encode(), int(q.use_LRF), -1, C.byref(h)) == 0, lib.qhost_last_error().decode()
+    try:
+        cs = lib.qhost_system(h).contents
+        for st in (py, cs):
+            assert st.qswitch == want.qswitch
+            a, b = _struct_arrays(st), _struct_arrays(want)
+            for k in a:
+                assert np.array_equal(a[k], b[k]), k
+    finally:
+        lib.qhost_close(h)
