@@ -1,7 +1,7 @@
 """The algorithm of the device SHAKE on the CPU: q6_b200/csrc/qnb_shake.cuh's shake_molecule() is __host__ __device__, so
 the source the kernel k_shake runs per thread is compiled here with g++ (tests/cpu_shims/shake_shim.cpp) and compared,
 bit for bit, with the restatement of shake(xx, x) (bondene.f90:1069-1150) that the reference's step-0 goldens pin.
-What this cannot cover is the thread mapping of the kernel and the copies in qnb_shake (tests/test_zz_shake_gpu.py)."""
+What this cannot cover is the thread mapping of the kernel and the copies in qnb_shake (tests/test_zx_shake_gpu.py)."""
 import ctypes as C
 import os
 import subprocess
