@@ -376,6 +376,22 @@ def main():
             rw = float(np.linalg.norm(q.xtop[q.nat_solute:] - np.asarray(q.xpcent), axis=1).max())
             g.set_solvent_restraints(wat_shells(q.xpcent, rw, crgQtot=-1.0), np.zeros(8))
             ext["device_step_ms_with_solvent_restraints"] = g.bench_nonbond(lam, 200, restraints=True) / 200
+        if not sharded and q.nwat > 0:
+            # N2: solvent SHAKE on the device (qnb_shake; xx = the coordinates resident from the step).  Reported, never
+            # fatal: the kernel has not run on hardware before this bench.
+            try:
+                cons, starts, winv = synth.water_constraints(q)
+                g.set_constraints(cons, starts, winv)
+                g.pot_energy_nonbonds(x, lam)
+                moved = x + np.random.default_rng(3).normal(0, 0.01, x.shape)
+                _, sweeps = g.shake(moved)
+                t0 = time.perf_counter()
+                for _ in range(50):
+                    g.shake(moved)
+                ext["solvent_shake"] = {"ms_per_call_host_buffers": (time.perf_counter() - t0) / 50 * 1e3,
+                                        "molecules": int(q.nwat), "sweeps_per_molecule": sweeps / max(int(q.nwat), 1)}
+            except Exception as e:
+                ext["solvent_shake"] = {"error": str(e)[-200:]}
         line["extensions"] = ext
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1

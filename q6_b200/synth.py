@@ -372,6 +372,20 @@ def solvated_sphere(radius: float = 30.0, core_radius: float = 19.5, nq: int = 4
     return qs
 
 
+def water_constraints(q: QSystem):
+    """What init_constraints (simprep.f90:2167-2345) builds for a synthetic system with the default input (solvent bonds
+    to hydrogens): rows (i, j, dist2) with the bond lengths write_files puts into the topology, the first atom of every
+    molecule, and the inverse masses."""
+    hh = (2.0 * R_OH * float(np.sin(ANG_HOH / 2))) ** 2
+    cons = []
+    for k in range(q.nwat):
+        o = q.nat_solute + 3 * k + 1
+        cons += [(o, o + 1, R_OH ** 2), (o, o + 2, R_OH ** 2), (o + 1, o + 2, hh)]
+    starts = ([1] if q.nat_solute else []) + [q.nat_solute + 3 * k + 1 for k in range(q.nwat)]
+    mass = np.asarray(q.iaclib).reshape(-1, 7)[np.asarray(q.iac) - 1, 0]
+    return cons, starts, 1.0 / mass
+
+
 def _wrap(items, per_line, fmt=str):
     items = [fmt(v) for v in items]
     return [" ".join(items[i:i + per_line]) for i in range(0, len(items), per_line)]

@@ -21,17 +21,8 @@ pytestmark = [pytest.mark.gpu,
 
 
 def _water_constraints(q):
-    """init_constraints for the default input: O-H, O-H, H-H of every three-site water (written by synth.write_files
-    with the same numbers)."""
     from q6_b200 import synth
-    hh = (2.0 * synth.R_OH * float(np.sin(synth.ANG_HOH / 2))) ** 2
-    cons = []
-    for k in range(q.nwat):
-        o = q.nat_solute + 3 * k + 1
-        cons += [(o, o + 1, synth.R_OH ** 2), (o, o + 2, synth.R_OH ** 2), (o + 1, o + 2, hh)]
-    starts = ([1] if q.nat_solute else []) + [q.nat_solute + 3 * k + 1 for k in range(q.nwat)]
-    mass = np.asarray(q.iaclib).reshape(-1, 7)[np.asarray(q.iac) - 1, 0]
-    return cons, starts, 1.0 / mass
+    return synth.water_constraints(q)
 
 
 @pytest.mark.parametrize("case", [c for c in common.small_systems() if c[0] in ("sph_fep2", "box_water", "sph_noq")],
