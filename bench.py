@@ -376,7 +376,7 @@ def main():
             rw = float(np.linalg.norm(q.xtop[q.nat_solute:] - np.asarray(q.xpcent), axis=1).max())
             g.set_solvent_restraints(wat_shells(q.xpcent, rw, crgQtot=-1.0), np.zeros(8))
             ext["device_step_ms_with_solvent_restraints"] = g.bench_nonbond(lam, 200, restraints=True) / 200
-        if not sharded and q.nwat > 0:
+        if world == 1 and q.nwat > 0:
             # N2: solvent SHAKE on the device (qnb_shake; xx = the coordinates resident from the step).  Reported, never
             # fatal: the kernel has not run on hardware before this bench.
             try:
