@@ -1132,25 +1132,27 @@ constexpr double CONST_TOL = 0.0001;  // globals.f90:519
 constexpr int CONST_MAX_ITER = 1000;  // globals.f90:520
 }  // namespace
 
-int shake(const System &sys, const double *xx, double *x) {
-    // bondene.f90:1069-1150, literal order of operations: a constraint found within tolerance is flagged ready and
-    // still receives that pass's correction; ready constraints are not looked at again in this call.
+std::vector<int32_t> constraint_molecules(const System &sys) {
+    std::vector<int32_t> first{0};
     const size_t nc = sys.const_dist2.size();
-    if (nc == 0) return 0;
-    const int natom = sys.s.natom;
-    // molecule of every constraint (the topology lists bonds molecule by molecule)
     auto mol_of = [&](int atom) {
         auto it = std::upper_bound(sys.istart_mol.begin(), sys.istart_mol.end(), atom);
         return (int)(it - sys.istart_mol.begin()) - 1;
     };
+    for (size_t c = 1; c <= nc; c++)
+        if (c == nc || mol_of(sys.const_ij[2 * c]) != mol_of(sys.const_ij[2 * (c - 1)])) first.push_back((int32_t)c);
+    return first;
+}
+
+int shake(const System &sys, const double *xx, double *x) {
+    // bondene.f90:1069-1150, literal order of operations: a constraint found within tolerance is flagged ready and
+    // still receives that pass's correction; ready constraints are not looked at again in this call.
+    const int natom = sys.s.natom;
+    const std::vector<int32_t> first = constraint_molecules(sys);
     long total = 0;
-    int nmol_const = 0;
-    size_t c0 = 0;
     std::vector<char> ready;
-    while (c0 < nc) {
-        int mol = mol_of(sys.const_ij[2 * c0]);
-        size_t c1 = c0;
-        while (c1 < nc && mol_of(sys.const_ij[2 * c1]) == mol) c1++;
+    for (size_t m = 0; m + 1 < first.size(); m++) {
+        const size_t c0 = first[m], c1 = first[m + 1];
         ready.assign(c1 - c0, 0);
         int nits = 0;
         for (;;) {
@@ -1179,8 +1181,6 @@ int shake(const System &sys, const double *xx, double *x) {
             if (nits >= CONST_MAX_ITER) throw Die("shake failure");  // bondene.f90:1143
         }
         total += nits;
-        nmol_const++;
-        c0 = c1;
     }
     const int nmol = (int)sys.istart_mol.size();
     return nmol > 0 ? (int)(total / nmol) : 0;
@@ -1213,6 +1213,50 @@ void Nonbonded::update_box(const double boxlength[3]) {
     if (qnb_update_box(h_, sys_.boxlength, inv) != 0) throw Die(std::string("qnb_update_box: ") + qnb_last_error());
 }
 
+void Nonbonded::save_lists() {
+    if (qnb_save_lists(h_) != 0) throw Die(std::string("MC_volume (save lists): ") + qnb_last_error());
+}
+
+void Nonbonded::restore_lists() {
+    if (qnb_restore_lists(h_) != 0) throw Die(std::string("MC_volume (restore lists): ") + qnb_last_error());
+}
+
+void Nonbonded::set_solvent_restraints(const qnb_solvent_restraints &p) {
+    if (qnb_set_solvent_restraints(h_, &p) != 0) throw Die(std::string("restrain_solvent: ") + qnb_last_error());
+}
+
+void Nonbonded::set_theta_corr(const double *theta_corr) {
+    if (qnb_set_theta_corr(h_, theta_corr) != 0) throw Die(std::string("watpol: ") + qnb_last_error());
+}
+
+void Nonbonded::last_restraints(double E[2], double *shell_theta_sum, int32_t *shell_n) {
+    if (qnb_last_restraints(h_, E, shell_theta_sum, shell_n) != 0) throw Die(std::string("watpol: ") + qnb_last_error());
+}
+
+void Nonbonded::set_constraints() {
+    const std::vector<int32_t> first = constraint_molecules(sys_);
+    const size_t nc = sys_.const_dist2.size();
+    std::vector<double> winv(sys_.mass.size());
+    for (size_t i = 0; i < winv.size(); i++) winv[i] = 1.0 / sys_.mass[i];   // simprep.f90:3675
+    static const int32_t no_ij[2] = {0, 0};
+    static const double no_d2[1] = {0.0};
+    if (qnb_set_constraints(h_, (int)first.size() - 1, first.data(), nc ? sys_.const_ij.data() : no_ij,
+                            nc ? sys_.const_dist2.data() : no_d2, winv.data()) != 0)
+        throw Die(std::string("init_constraints: ") + qnb_last_error());
+}
+
+int64_t Nonbonded::shake(const double *xx, double *x) {
+    int64_t it = 0;
+    if (qnb_shake(h_, xx, x, &it) != 0) throw Die(qnb_last_error());   // 'shake failure', bondene.f90:1143
+    return it;
+}
+
+void Nonbonded::qcp_beads(const double *x_save, int natq, const int32_t *atoms, int nbeads, const double *coord,
+                          const double *lambda, double *EQ_out) {
+    if (qnb_qcp_beads(h_, x_save, natq, atoms, nbeads, coord, lambda, EQ_out) != 0)
+        throw Die(std::string("qcp_run: ") + qnb_last_error());
+}
+
 void Nonbonded::make_pair_lists(double Rq, double Rcq2, double RcLRF2, double Rcpp2, double Rcpw2, double Rcww2) {
     if (qnb_build_lists(h_, x.data(), Rq, Rcq2, RcLRF2, Rcpp2, Rcpw2, Rcww2, RcLRF, dump ? nb_pairs : nullptr) != 0)
         throw Die(std::string("make_pair_lists: ") + qnb_last_error());
@@ -1224,7 +1268,7 @@ void Nonbonded::pot_energy_nonbonds(ENERGIES &E_loc, std::vector<OQ_ENERGIES> &E
     std::vector<double> lambda(ns), EQ(QNB_EQ_STRIDE * (size_t)ns, 0.0);
     for (int s = 0; s < ns; s++) lambda[s] = EQ_loc[s].lambda;
     double E[QNB_E_COUNT] = {0};
-    const int flags = (md ? QNB_FLAG_MD : 0) | QNB_FLAG_QQ;
+    const int flags = (md ? QNB_FLAG_MD : 0) | QNB_FLAG_QQ | ((md && restraints_on) ? QNB_FLAG_SOLVENT_RESTRAINTS : 0);
     if (qnb_nonbond(h_, x.data(), lambda.data(), flags, d.data(), E, EQ.data()) != 0)
         throw Die(std::string("pot_energy_nonbonds: ") + qnb_last_error());
     E_loc.pp = {E[QNB_E_PP_EL], E[QNB_E_PP_VDW]};

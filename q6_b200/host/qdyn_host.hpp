@@ -140,6 +140,9 @@ System system_from_struct(const qnb_system &src, const double boxlength[3]);
 // contiguous 1-based inclusive i-ranges balanced by per-i counts (nonbondene.f90:171-296, equal shares)
 std::vector<std::pair<int, int>> distribute_nonbonds(const std::vector<double> &per_i_counts, int nranks);
 
+// const_mol(:) of init_constraints: first constraint (0-based) of every constrained molecule, plus the end (CSR); the
+// topology lists bonds molecule by molecule
+std::vector<int32_t> constraint_molecules(const System &sys);
 // shake(xx, x) of bondene.f90:1069-1150 over the system's constraints; returns the summed iterations / nmol
 int shake(const System &sys, const double *xx, double *x);
 // initial_constraint (bondene.f90:1025-1048), coordinate part: xx = x; shake(xx, x)
@@ -181,6 +184,23 @@ class Nonbonded {
     void pot_energy_nonbonds(ENERGIES &E_loc, std::vector<OQ_ENERGIES> &EQ_loc, bool md);
     // md.f90 MC_volume / put_back_in_box
     void update_box(const double boxlength[3]);
+    // MC_volume keeping / putting back the lists of the current box (md.f90:2022-2058, 2214-2256)
+    void save_lists();
+    void restore_lists();
+    // restrain_solvent + watpol inside the device step (potene.f90:161-167): parameters once, theta_corr when it changes;
+    // while restraints_on is set pot_energy_nonbonds(md=.true.) adds both terms to d and last_restraints() returns
+    // E%restraint%solvent_radial, E%restraint%water_pol and the per-shell sums the host keeps its averages from
+    void set_solvent_restraints(const qnb_solvent_restraints &p);
+    void set_theta_corr(const double *theta_corr);
+    void last_restraints(double E[2], double *shell_theta_sum, int32_t *shell_n);
+    bool restraints_on = false;
+    // shake(xx, x) for the solvent (bondene.f90:1069): constraints from System (init_constraints), then per step;
+    // xx == nullptr: the coordinates of this step's pot_energy_nonbonds.  Returns the sweeps summed over molecules.
+    void set_constraints();
+    int64_t shake(const double *xx, double *x);
+    // qcp_run's bead loop (qcp.f90:319-372): EQ_out[nbeads][6*nstates]
+    void qcp_beads(const double *x_save, int natq, const int32_t *atoms, int nbeads, const double *coord,
+                   const double *lambda, double *EQ_out);
     qnb_handle *handle() { return h_; }
 
   private:

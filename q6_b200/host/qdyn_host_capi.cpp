@@ -63,6 +63,12 @@ int qhost_shard(qhost *h, int rank, int nranks) {
     return guarded([&] { h->sys.shard(rank, nranks); });
 }
 int64_t qhost_constraint_count(qhost *h) { return (int64_t)h->sys.const_dist2.size(); }
+// constraint_molecules(): writes up to cap entries of the CSR array, returns its length (molecules + 1)
+int64_t qhost_constraint_molecules(qhost *h, int32_t *first, int64_t cap) {
+    const std::vector<int32_t> f = constraint_molecules(h->sys);
+    for (int64_t k = 0; k < (int64_t)f.size() && k < cap; k++) first[k] = f[k];
+    return (int64_t)f.size();
+}
 
 // initial_constraint (bondene.f90:1025), coordinate part, in place on x[3*natom]; iterations per molecule in *niter
 int qhost_initial_constraint(qhost *h, double *x, int *niter) {

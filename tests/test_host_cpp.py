@@ -57,6 +57,8 @@ def host_lib():
     lib.qhost_shard.argtypes = [H, C.c_int, C.c_int]
     lib.qhost_constraint_count.restype = C.c_int64
     lib.qhost_constraint_count.argtypes = [H]
+    lib.qhost_constraint_molecules.restype = C.c_int64
+    lib.qhost_constraint_molecules.argtypes = [H, C.POINTER(C.c_int32), C.c_int64]
     lib.qhost_initial_constraint.argtypes = [H, PD, C.POINTER(C.c_int)]
     lib.qhost_attach_gpu.argtypes = [H, C.c_int]
     lib.qhost_make_pair_lists.argtypes = [H, PD] + [C.c_double] * 7 + [PL]
@@ -300,6 +302,9 @@ def test_written_input_files_round_trip_through_both_readers(case, tmp_path):
         if q.nwat:
             from oracle import pyoracle
             assert lib.qhost_constraint_count(h) == 3 * q.nwat
+            first = np.zeros(q.nwat + 1, np.int32)            # const_mol(:): three constraints per water, molecule by molecule
+            assert lib.qhost_constraint_molecules(h, first.ctypes.data_as(C.POINTER(C.c_int32)), len(first)) == q.nwat + 1
+            assert np.array_equal(first, 3 * np.arange(q.nwat + 1))
             x = q.xtop.copy()
             assert lib.qhost_initial_constraint(h, _dp(x), None) == 0, lib.qhost_last_error().decode()
             xs, nits = pyoracle.initial_constraint_x(t)
