@@ -80,5 +80,27 @@ def main():
         print(name, "natom", q.natom, "counts", counts[:5], "E", np.round(E, 3), "EQ", np.round(EQ, 3))
 
 
+def full_size_fingerprints():
+    """Oracle results at BASELINE.json's full sizes for the configurations the oracle cannot be run on inside a GPU test
+    in seconds (C5: 98 304 atoms, the O(ncgp^2) reference list build takes ~25 s): list sizes, an order-independent
+    checksum of the water-water list, energies, the gradient of a fixed random sample of atoms plus its global norm, and
+    the LRF moments of a sample of charge groups.  No reference files needed (synthetic system)."""
+    from q6_b200 import synth
+    q, cuts, lam = synth.config("C5")
+    o = Oracle(q)
+    counts = o.make_pair_lists(q.xtop, **cuts)
+    d, E, EQ = o.pot_energy_nonbonds(q.xtop, lam)
+    rng = np.random.default_rng(20261018)
+    atoms = np.sort(rng.choice(q.natom, 4096, replace=False))
+    groups = np.sort(rng.choice(q.ncgp, 512, replace=False))
+    ij, _ = o.export_list(2, 1, params=False)
+    np.savez_compressed(os.path.join(OUT, "c5_box_fingerprint.npz"), counts=counts, E=E, EQ=EQ, atoms=atoms, d_sample=d[atoms],
+                        d_norm2=float((d ** 2).sum()), d_abs_sum=float(np.abs(d).sum()), groups=groups,
+                        lrf_sample=o.export_lrf()[groups], sum_ww=list_checksum(ij),
+                        cuts=np.array([cuts[k] for k in ("Rq", "Rcq2", "RcLRF2", "Rcpp2", "Rcpw2", "Rcww2", "RcLRF")]))
+    print("C5 fingerprint: counts", counts[:5], "E", np.round(E, 3))
+
+
 if __name__ == "__main__":
     main()
+    full_size_fingerprints()
