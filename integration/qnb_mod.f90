@@ -3,6 +3,9 @@
 ! NOT COMPILED IN THIS REPOSITORY'S IMAGE (no Fortran compiler is installed there); it is the
 ! binding a Q6 maintainer adds to src/ and lists in the makefile before nonbondene.f90.
 ! Every interface below mirrors one prototype of include/qnb.h.
+! Coordinate and gradient arrays are TYPE(qr_vec) (three reals, sizes.f90:109-111) in Q6; they are passed as
+! assumed-type, assumed-size dummies (type(*), dimension(*): Fortran 2018 / TS 29113, gfortran >= 4.9), which hands the
+! C side the address of the first element without a type mismatch against real(c_double).
 module QNB
 use, intrinsic :: iso_c_binding
 implicit none
@@ -82,7 +85,7 @@ interface
     function qnb_qcp_beads(handle, x_save, natq, atoms, nbeads, coord, lambda, EQ_out) bind(c, name='qnb_qcp_beads') result(rc)
         import :: c_int, c_ptr, c_double, c_int32_t
         type(c_ptr), value :: handle
-        real(c_double), intent(in) :: x_save(*)           ! x_save(natom) as 3*natom doubles
+        type(*), dimension(*), intent(in) :: x_save       ! TYPE(qr_vec) x_save(natom) == 3*natom doubles
         integer(c_int), value :: natq, nbeads
         integer(c_int32_t), intent(in) :: atoms(*)        ! iqseq(qcp_atom(1:qcp_atnum))
         real(c_double), intent(in) :: coord(*)            ! qcp_coord(j,i) copied bead-major: (3, natq, nbeads)
@@ -105,7 +108,7 @@ interface
         import :: c_int, c_ptr, c_double, c_int64_t
         type(c_ptr), value :: handle
         type(c_ptr), value :: xx                          ! c_loc(xx) or c_null_ptr: the coordinates of this step's qnb_nonbond
-        real(c_double), intent(inout) :: x(*)
+        type(*), dimension(*), intent(inout) :: x         ! TYPE(qr_vec) x(natom)
         integer(c_int64_t), intent(out) :: iterations     ! sweeps summed over molecules (shake = iterations/nmol)
         integer(c_int) :: rc
     end function
@@ -113,7 +116,7 @@ interface
             bind(c, name='qnb_build_lists') result(rc)
         import :: c_int, c_ptr, c_double
         type(c_ptr), value :: handle
-        real(c_double), intent(in) :: x(*)                ! TYPE(qr_vec) x(natom) == 3*natom doubles
+        type(*), dimension(*), intent(in) :: x            ! TYPE(qr_vec) x(natom) == 3*natom doubles
         real(c_double), value :: Rq, Rcq2, RcLRF2, Rcpp2, Rcpw2, Rcww2, RcLRF
         type(c_ptr), value :: counts                      ! c_null_ptr or int64(8)
         integer(c_int) :: rc
@@ -121,9 +124,10 @@ interface
     function qnb_nonbond(handle, x, lambda, flags, d, E_out, EQ_out) bind(c, name='qnb_nonbond') result(rc)
         import :: c_int, c_ptr, c_double
         type(c_ptr), value :: handle
-        real(c_double), intent(in) :: x(*), lambda(*)
+        type(*), dimension(*), intent(in) :: x            ! TYPE(qr_vec) x(natom)
+        real(c_double), intent(in) :: lambda(*)
         integer(c_int), value :: flags
-        real(c_double), intent(inout) :: d(*)             ! added to
+        type(*), dimension(*), intent(inout) :: d         ! TYPE(qr_vec) d(natom): added to
         real(c_double), intent(out) :: E_out(7), EQ_out(*) ! 6*nstates
         integer(c_int) :: rc
     end function
