@@ -15,6 +15,7 @@
 #include "../../include/qnb.h"
 #include "qnb_kernels.cuh"
 #include "qnb_forces.cuh"
+#include "qnb_rows.cuh"
 #include "qnb_shake.cuh"
 #include "qnb_lists.cuh"
 #include "qnb_tables.hpp"
@@ -94,7 +95,7 @@ static int upload(DBuf<T> &b, const std::vector<T> &v) {
 
 using namespace qnb;
 
-constexpr int kAux = 5;   // auxiliary streams: the kernels of one evaluation run concurrently
+constexpr int kAux = 6;   // auxiliary streams: the kernels of one evaluation run concurrently
 
 struct qnb_handle {
     int device = 0, nsm = 148;
@@ -158,6 +159,18 @@ struct qnb_handle {
     Cut cut_build{}, cut_saved{};
     bool have_saved = false, restoring = false;   // solute chunks: per entry, special-pair codes of the tile atoms
     int nwchunk = 0, nschunk = 0;   // water-row / solute-row chunks
+    // round-2 row kernels (qnb_rows.cuh): per-step packed records, pair tables, flat energy lists
+    DBuf<int> upk, pk_sw, e_cnt, e_off;
+    DBuf<int4> rec_i;
+    DBuf<float4> rec_f, wT, pw12;
+    DBuf<float2> ljp, pw0;
+    DBuf<int2> ww_pairs, pp_pairs, pw_pairs;
+    int n_ww_e = 0, n_pp_e = 0, n_pw_e = 0;
+    int occ_wr = 0, occ_sr = 0;
+    bool legacy_rows = false, pw_hlj = false;
+    RowPar rowpar{};
+    EnergyPar epar{};
+    FixFrame fix{};
     int nqp = 0, nqw = 0;
     bool qp_done = false, qw_done = false, lists_built = false;
     int64_t total_rows = 0;
@@ -191,8 +204,29 @@ namespace qnb {
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// fixed-point frame of the row kernels: the box when periodic, else a power-of-two period that covers the binned extent
+// four times over (only differences between listed partners are ever formed)
+static void refresh_frame(qnb_handle *h) {
+    const Grid &G = h->grid;
+    FixFrame &F = h->fix;
+    for (int d = 0; d < 3; d++) {
+        double period;
+        if (h->D.use_PBC) { F.org[d] = 0.0; period = h->box[d] > 0 ? h->box[d] : 1.0; }
+        else {
+            const double ext = G.inv_box[d];   // extent of the padded bounding box (make_grid)
+            period = 128.0;
+            while (period < 4.0 * (ext + 16.0)) period *= 2.0;
+            F.org[d] = G.org[d] - 8.0;
+        }
+        F.inv_period[d] = 1.0 / period;
+        F.scale[d] = (float)(period / 4294967296.0);
+        h->rowpar.scale[d] = F.scale[d];
+        h->epar.box[d] = h->box[d]; h->epar.inv_box[d] = h->inv_box[d];
+    }
+}
 static void refresh_dev(qnb_handle *h) {
     for (int d = 0; d < 3; d++) { h->D.box[d] = h->box[d]; h->D.inv_box[d] = h->inv_box[d]; }
+    if (h->have_grid) refresh_frame(h);
 }
 
 static int init_device(qnb_handle *h) {
@@ -264,6 +298,54 @@ static int init_device(qnb_handle *h) {
             D.wwA[a * 3 + b] = (float)p.A; D.wwB[a * 3 + b] = (float)p.B; D.wwQ[a * 3 + b] = (float)p.el; D.wwQd[a * 3 + b] = p.el; D.wwAd[a * 3 + b] = p.A; D.wwBd[a * 3 + b] = p.B;
         }
     }
+    // ---- round-2 row kernels (qnb_rows.cuh): type-pair tables with the combination rule resolved, {12 A, 6 B} in FP32
+    {
+        const int nct = T.nct;
+        std::vector<float2> ljp((size_t)2 * nct * nct), pw0((size_t)std::max(nct, 1));
+        std::vector<float4> pw12((size_t)std::max(nct, 1));
+        for (int a = 0; a < nct; a++)
+            for (int b = 0; b < nct; b++)
+                for (int plane = 0; plane < 2; plane++) {
+                    const int code = plane ? 3 : T.ljcode[(size_t)a * nct + b];
+                    double A, B;
+                    T.combine(T.lj_a[a * 3 + code - 1], T.lj_b[a * 3 + code - 1], T.lj_a[b * 3 + code - 1], T.lj_b[b * 3 + code - 1], A, B);
+                    ljp[((size_t)plane * nct + a) * nct + b] = make_float2((float)(12.0 * A), (float)(6.0 * B));
+                }
+        h->pw_hlj = false;
+        RowPar &R = h->rowpar;
+        EnergyPar &E = h->epar;
+        if (s.nwat > 0) {
+            double A[3], B[3];
+            for (int a = 0; a < nct; a++) {
+                for (int site = 0; site < 3; site++) {
+                    const int code = T.ljcode[(size_t)a * nct + T.w_ctype[site]];
+                    T.combine(T.lj_a[a * 3 + code - 1], T.lj_b[a * 3 + code - 1], T.lj_a[T.w_ctype[site] * 3 + code - 1],
+                              T.lj_b[T.w_ctype[site] * 3 + code - 1], A[site], B[site]);
+                }
+                pw0[a] = make_float2((float)(12.0 * A[0]), (float)(6.0 * B[0]));
+                pw12[a] = make_float4((float)(12.0 * A[1]), (float)(12.0 * A[2]), (float)(6.0 * B[1]), (float)(6.0 * B[2]));
+                if (A[1] != 0.0 || A[2] != 0.0 || B[1] != 0.0 || B[2] != 0.0) h->pw_hlj = true;
+            }
+            // packed groups of k_water_rows: (a,b) = {(1,0),(2,0)} {(1,1),(2,2)} {(1,2),(2,1)} {(0,1),(0,2)}
+            static const int ga[4][2] = {{1, 2}, {1, 2}, {1, 2}, {0, 0}}, gb[4][2] = {{0, 0}, {1, 2}, {2, 1}, {1, 2}};
+            for (int g = 0; g < 4; g++) {
+                const QPar &p0 = T.ww_par[ga[g][0] * 3 + gb[g][0]], &p1 = T.ww_par[ga[g][1] * 3 + gb[g][1]];
+                R.wQ[g] = make_float2((float)p0.el, (float)p1.el);
+                R.wA12[g] = make_float2((float)(12.0 * p0.A), (float)(12.0 * p1.A));
+                R.wB6[g] = make_float2((float)(6.0 * p0.B), (float)(6.0 * p1.B));
+            }
+            R.q00 = (float)T.ww_par[0].el; R.A00 = (float)(12.0 * T.ww_par[0].A); R.B00 = (float)(6.0 * T.ww_par[0].B);
+            R.wq0 = (float)T.w_crg[0]; R.wq12 = make_float2((float)T.w_crg[1], (float)T.w_crg[2]);
+            for (int k = 0; k < 9; k++) { E.wwQ[k] = T.ww_par[k].el; E.wwA[k] = T.ww_par[k].A; E.wwB[k] = T.ww_par[k].B; }
+            for (int k = 0; k < 3; k++) { E.wq[k] = T.w_crg[k]; E.wct[k] = T.w_ctype[k]; }
+        }
+        R.el14 = (float)s.el14_scale; R.nct = nct;
+        E.el14 = s.el14_scale; E.nct = nct; E.geometric = D.geometric; E.any_atom = D.any_atom; E.spc = D.spc_water;
+        if (upload(h->ljp, ljp) || upload(h->pw0, pw0) || upload(h->pw12, pw12)) return 1;
+        // any-atom periodic lists carry the image of the pair's reference atoms, which need not be the minimum image
+        // of the switching atoms the fixed-point rows work with: the round-1 general kernels keep that case
+        h->legacy_rows = (D.any_atom && D.use_PBC) || getenv("QNB_LEGACY_ROWS");
+    }
     const size_t n3 = 3 * (size_t)s.natom;
     h->nE = QNB_E_COUNT + QNB_EQ_STRIDE * s.nstates;
     h->nout = n3 + (size_t)kESlots * h->nE + kRstOut;   // [gradient | energy slots | restraint results]
@@ -288,8 +370,8 @@ static int init_device(qnb_handle *h) {
         // are the critical path of a solvated protein, the water rows fill the SMs behind them
         int lo = 0, hi = 0;
         CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // hi = numerically lowest = most urgent
-        static const int kRank[5] = {2, 0, 1, 1, 0};      // water, solute, q_partner, q_atom, the tiny kernels (static lists, restraints)
-        int pr = std::min(lo, hi + (getenv("QNB_NO_PRIORITY") ? 0 : kRank[k < 5 ? k : 4]));
+        static const int kRank[kAux] = {1, 0, 1, 0, 0, 1};   // water, solute, q_partner, q_atom, the tiny kernels (static lists, restraints), energies
+        int pr = std::min(lo, hi + (getenv("QNB_NO_PRIORITY") ? 0 : kRank[k]));
         CU(cudaStreamCreateWithPriority(&h->aux[k], cudaStreamNonBlocking, pr));
     }
         CU(cudaEventCreateWithFlags(&h->ev_join[k], cudaEventDisableTiming));
@@ -406,6 +488,7 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
     }
     make_grid(h, hx_for_grid);
     const Grid G = h->grid;
+    refresh_frame(h);
     if (h->upos.ensure(3 * (size_t)std::max(nu, 1)) || h->cell_of.ensure(std::max(nu, 1)) ||
         h->cell_count.ensure(G.ncell + 1) || h->cell_start.ensure(G.ncell + 2) || h->cell_items.ensure(std::max(nu, 1)) ||
         h->counts.ensure(3 * (size_t)std::max(nu, 1)) || h->row_tot.ensure(std::max(nu, 1) + 1) ||
@@ -417,7 +500,9 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
         h->item_nq.ensure(std::max(nu, 1) + 1) || h->src_off.ensure(std::max(nu, 1) + 2) ||
         h->pk_atom.ensure(D.natom + 4) || h->pk_ct.ensure(D.natom + 4) || h->pk_q.ensure(D.natom + 4) ||
         h->pk_qd.ensure(D.natom + 4) || h->px.ensure(D.natom + 4) || h->py.ensure(D.natom + 4) ||   // +4: the force kernels always fetch three sites
-        h->pz.ensure(D.natom + 4))
+        h->pz.ensure(D.natom + 4) || h->upk.ensure(std::max(nu, 1)) || h->pk_sw.ensure(D.natom + 4) ||
+        h->rec_i.ensure(D.natom + 4) || h->rec_f.ensure(D.natom + 4) || h->wT.ensure(D.natom + 4) ||
+        h->e_cnt.ensure(std::max(nu, 1) + D.ncgp_solute + 4) || h->e_off.ensure(std::max(nu, 1) + D.ncgp_solute + 8))
         return 1;
     // LRF: cgp_centers + lrf_update over every pair that falls in the LRF branch.  It needs the cell tables and the
     // packed atoms but not the rows, and it is the longest kernel of a build: it runs on a side stream next to the
@@ -477,42 +562,54 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
         LAUNCH(h, k_cell_sort, G.ncell, 64, 0, G.ncell, h->cell_start.p, h->cell_unsorted.p, h->cell_items.p);
         LAUNCH(h, k_pack_items, cdiv(nu, 256), 256, 0, D, h->upos.p, h->cell_items.p, h->item_pos.p, h->item_posf.p, h->item_nq.p);
         run_exclusive_scan(h, h->item_nq.p, h->src_off.p, nu);
-        LAUNCH(h, k_pack_atoms, cdiv(nu, 128), 128, 0, D, h->cell_items.p, h->src_off.p, h->pk_atom.p, h->pk_q.p, h->pk_qd.p, h->pk_ct.p);
+        LAUNCH(h, k_pack_atoms, cdiv(nu, 128), 128, 0, D, h->cell_items.p, h->src_off.p, h->pk_atom.p, h->pk_q.p, h->pk_qd.p, h->pk_ct.p, h->pk_sw.p, h->upk.p);
         launch_lrf();
         LAUNCH(h, k_build_rows<false>, cdiv(nu * 32, 256), 256, 0, D, h->cut, G, h->list_reach, h->x.p, h->upos.p, h->cell_of.p, h->cell_start.p,
                h->item_pos.p, h->src_off.p, h->counts.p, (const int *)nullptr, (uint32_t *)nullptr);
         LAUNCH(h, k_row_totals, cdiv(nu, 256), 256, 0, nu, h->counts.p, h->row_tot.p);
-        run_exclusive_scan(h, h->row_tot.p, h->row_off.p, nu);
-        // chunk tables of the streaming force kernels: counts now, contents after the rows are filled
+        // chunk tables of the streaming force kernels and flat pair lists of the energy kernel: counts now, contents after
+        // the rows are filled; all eight prefix sums in one launch
         const int nsol = D.ncgp_solute, nwat = D.nwat;
         if (h->nch.ensure(nu + 2) || h->choff.ensure(nu + 4) || h->ucost.ensure(nu + 2) || h->cost_off.ensure(nu + 4)) return 1;
         int *nch_w = h->nch.p, *nch_s = h->nch.p + nwat + 1, *off_w = h->choff.p, *off_s = h->choff.p + nwat + 2;
         int *uc_w = h->ucost.p, *uc_s = h->ucost.p + nwat + 1, *co_w = h->cost_off.p, *co_s = h->cost_off.p + nwat + 2;
-        if (nwat > 0) {
-            LAUNCH(h, k_chunk_count, cdiv(nwat, 256), 256, 0, D, nsol, nwat, 0, h->counts.p, nch_w, uc_w);
-            run_exclusive_scan(h, nch_w, off_w, nwat);
-            run_exclusive_scan(h, uc_w, co_w, nwat);
-        }
-        if (nsol > 0) {
-            LAUNCH(h, k_chunk_count, cdiv(nsol, 256), 256, 0, D, 0, nsol, kITile, h->counts.p, nch_s, uc_s);
-            run_exclusive_scan(h, nch_s, off_s, nsol);
-            run_exclusive_scan(h, uc_s, co_s, nsol);
+        int *en_ww = h->e_cnt.p, *en_pp = h->e_cnt.p + nwat, *en_pw = h->e_cnt.p + nwat + nsol;
+        int *eo_ww = h->e_off.p, *eo_pp = h->e_off.p + nwat + 1, *eo_pw = h->e_off.p + nwat + nsol + 2;
+        const bool new_rows = !h->legacy_rows;
+        if (nwat > 0) LAUNCH(h, k_chunk_count, cdiv(nwat, 256), 256, 0, D, nsol, nwat, 0, new_rows, h->counts.p, nch_w, uc_w);
+        if (nsol > 0) LAUNCH(h, k_chunk_count, cdiv(nsol, 256), 256, 0, D, 0, nsol, kITile, new_rows, h->counts.p, nch_s, uc_s);
+        LAUNCH(h, k_energy_counts, cdiv(nu, 256), 256, 0, D, h->counts.p, en_ww, en_pp, en_pw);
+        {
+            ScanJobs J{};
+            int nj = 0;
+            auto job = [&](const int *in, int *out, int n) { J.in[nj] = in; J.out[nj] = out; J.n[nj] = n; nj++; };
+            job(h->row_tot.p, h->row_off.p, nu);
+            job(nch_w, off_w, nwat); job(uc_w, co_w, nwat); job(nch_s, off_s, nsol); job(uc_s, co_s, nsol);
+            job(en_ww, eo_ww, nwat); job(en_pp, eo_pp, nsol); job(en_pw, eo_pw, nsol);
+            LAUNCH(h, k_multi_scan, nj, 1024, 0, J);
         }
         int total = 0, npk = 0;
         h->nwchunk = h->nschunk = 0;
         CU(cudaMemcpyAsync(&total, h->row_off.p + nu, sizeof(int), cudaMemcpyDeviceToHost, h->st));
         CU(cudaMemcpyAsync(&npk, h->src_off.p + nu, sizeof(int), cudaMemcpyDeviceToHost, h->st));
-        if (nwat > 0) CU(cudaMemcpyAsync(&h->nwchunk, off_w + nwat, sizeof(int), cudaMemcpyDeviceToHost, h->st));
-        if (nsol > 0) CU(cudaMemcpyAsync(&h->nschunk, off_s + nsol, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+        CU(cudaMemcpyAsync(&h->nwchunk, off_w + nwat, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+        CU(cudaMemcpyAsync(&h->nschunk, off_s + nsol, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+        CU(cudaMemcpyAsync(&h->n_ww_e, eo_ww + nwat, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+        CU(cudaMemcpyAsync(&h->n_pp_e, eo_pp + nsol, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+        CU(cudaMemcpyAsync(&h->n_pw_e, eo_pw + nsol, sizeof(int), cudaMemcpyDeviceToHost, h->st));
         CU(cudaStreamSynchronize(h->st));   // the only host round trip of the build: sizes for the allocations
         h->total_rows = total;
         h->npk = npk;
         if (h->rows.ensure((size_t)std::max(total, 1)) || h->wdesc.ensure(std::max(h->nwchunk, 1)) ||
             h->wrow.ensure((size_t)std::max(h->nwchunk, 1) * 32) || h->sdesc.ensure(std::max(h->nschunk, 1)) ||
-            h->srow.ensure((size_t)std::max(h->nschunk, 1) * 32) || h->sspec.ensure((size_t)std::max(h->nschunk, 1) * 32))
+            h->srow.ensure((size_t)std::max(h->nschunk, 1) * 32) || h->sspec.ensure((size_t)std::max(h->nschunk, 1) * 32) ||
+            h->ww_pairs.ensure(std::max(h->n_ww_e, 1)) || h->pp_pairs.ensure(std::max(h->n_pp_e, 1)) || h->pw_pairs.ensure(std::max(h->n_pw_e, 1)))
             return 1;
         LAUNCH(h, k_build_rows<true>, cdiv(nu * 32, 256), 256, 0, D, h->cut, G, h->list_reach, h->x.p, h->upos.p, h->cell_of.p, h->cell_start.p,
                h->item_pos.p, h->src_off.p, h->counts.p, h->row_off.p, h->rows.p);
+        if (h->n_ww_e + h->n_pp_e + h->n_pw_e > 0)
+            LAUNCH(h, k_energy_fill, cdiv(nu * 32, 256), 256, 0, D, h->counts.p, h->row_off.p, h->rows.p, h->upk.p, h->pk_atom.p, eo_ww, eo_pp,
+                   eo_pw, h->ww_pairs.p, h->pp_pairs.p, h->pw_pairs.p);
         if (h->nwchunk > 0)
             LAUNCH(h, k_chunk_fill, cdiv(nwat * 32, 256), 256, 0, D, nsol, nwat, 0, h->counts.p, h->row_off.p, h->rows.p, off_w,
                    h->wdesc.p, h->wrow.p, h->pk_atom.p, (uint16_t *)nullptr);
@@ -520,13 +617,15 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
             LAUNCH(h, k_chunk_fill, cdiv(nsol * 32, 256), 256, 0, D, 0, nsol, kITile, h->counts.p, h->row_off.p, h->rows.p, off_s,
                    h->sdesc.p, h->srow.p, h->pk_atom.p, h->sspec.p);
         // one resident wave per kernel, every warp an equal share of the estimated work
-        h->wgrid = std::max(1, std::min((h->water_blocks ? h->water_blocks : std::max(h->occ_w, 1)) * h->nsm, cdiv(h->nwchunk, 4 * 4)));
-        h->sgrid = std::max(1, std::min((h->solute_blocks ? h->solute_blocks : std::max(h->occ_s, 1)) * h->nsm, cdiv(h->nschunk, 4 * 4)));
+        const int occw = new_rows ? h->occ_wr : h->occ_w, occs = new_rows ? h->occ_sr : h->occ_s;
+        const int min_chunks = new_rows ? 2 : 4;   // chunks per warp below which more blocks only add launch overhead
+        h->wgrid = std::max(1, std::min((h->water_blocks ? h->water_blocks : std::max(occw, 1)) * h->nsm, cdiv(h->nwchunk, 4 * min_chunks)));
+        h->sgrid = std::max(1, std::min((h->solute_blocks ? h->solute_blocks : std::max(occs, 1)) * h->nsm, cdiv(h->nschunk, 4 * min_chunks)));
         if (h->wstart_w.ensure(4 * h->wgrid + 2) || h->wstart_s.ensure(4 * h->sgrid + 2)) return 1;
         if (h->nwchunk > 0)
-            LAUNCH(h, k_warp_starts, cdiv(4 * h->wgrid + 1, 128), 128, 0, D, nsol, nwat, 0, h->counts.p, off_w, co_w, 4 * h->wgrid, h->wstart_w.p);
+            LAUNCH(h, k_warp_starts, cdiv(4 * h->wgrid + 1, 128), 128, 0, D, nsol, nwat, 0, new_rows, h->counts.p, off_w, co_w, 4 * h->wgrid, h->wstart_w.p);
         if (h->nschunk > 0)
-            LAUNCH(h, k_warp_starts, cdiv(4 * h->sgrid + 1, 128), 128, 0, D, 0, nsol, kITile, h->counts.p, off_s, co_s, 4 * h->sgrid, h->wstart_s.p);
+            LAUNCH(h, k_warp_starts, cdiv(4 * h->sgrid + 1, 128), 128, 0, D, 0, nsol, kITile, new_rows, h->counts.p, off_s, co_s, 4 * h->sgrid, h->wstart_s.p);
     }
     // Q-atom partner lists: built once when the cut-off covers everything (nbqplist L3678, nbqwlist L3889,
     // nbqplist_box L3780, nbqwlist_box L3972)
@@ -570,9 +669,9 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
 }
 
 // ------------------------------------------------------------------ one nonbonded evaluation on device
-enum StepKernel { K_WATER = 0, K_SOLUTE, K_QPARTNER, K_QATOM, K_QSTATIC, K_LRF, K_RST, K_COUNT };
-static const char *kStepKernelNames[K_COUNT] = {"k_water_force", "k_solute_force", "k_q_partner", "k_q_atom",
-                                                "k_qq_static", "k_lrf_taylor", "k_solvent_restraints"};
+enum StepKernel { K_WATER = 0, K_SOLUTE, K_QPARTNER, K_QATOM, K_QSTATIC, K_LRF, K_RST, K_ENERGY, K_COUNT };
+static const char *kStepKernelNames[K_COUNT] = {"k_water_rows", "k_solute_rows", "k_q_partner", "k_q_atom",
+                                                "k_qq_static", "k_lrf_taylor", "k_solvent_restraints", "k_pair_energy"};
 
 constexpr int kFlagEnergiesOnly = 8;   // internal (QCP beads): no kernel whose only product is a gradient
 
@@ -589,6 +688,8 @@ static bool step_kernel_active(const qnb_handle *h, int k, int flags) {
     // restrain_solvent / watpol: only in_md and only for the sphere (potene.f90:161-167)
     // (one rank only when the step is sharded: every rank would add the same term to the summed gradient)
     case K_RST: return md && (flags & QNB_FLAG_SOLVENT_RESTRAINTS) && h->rst_set && !D.use_PBC && D.nwat > 0 && h->T.s.is_master;
+    // E%pp, E%pw, E%ww: every listed pair once, FP64 (the row kernels produce gradients only)
+    case K_ENERGY: return md && !(flags & QNB_FLAG_NO_ENERGY) && (h->n_ww_e + h->n_pp_e + h->n_pw_e) > 0;
     }
     return false;
 }
@@ -608,17 +709,30 @@ static void query_occupancy(qnb_handle *h) {
     if (pbc) { if (geom) SOCC(true, true); else SOCC(true, false); }
     else { if (geom) SOCC(false, true); else SOCC(false, false); }
 #undef SOCC
+    if (spc) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_wr, k_water_rows<true>, 128, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_wr, k_water_rows<false>, 128, 0);
+    if (h->pw_hlj) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_sr, k_solute_rows<true>, 128, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_sr, k_solute_rows<false>, 128, 0);
     cudaGetLastError();
 }
 
 static void launch_step_kernel(qnb_handle *h, int k, cudaStream_t cs, int flags) {
-    const int want_e = (flags & QNB_FLAG_NO_ENERGY) ? 0 : 1;
     const Dev &D = h->D;
     double *grad = h->out.p, *E = h->out.p + 3 * (size_t)D.natom;
     const int nE = h->nE;
     const bool pbc = D.use_PBC, spc = D.spc_water, geom = D.geometric;
+    // the round-1 general kernels serve any-atom periodic lists (QNB_LEGACY_ROWS=1 forces them), gradient only:
+    // the energies always come from k_pair_energy
+    const int want_e = 0;
     switch (k) {
     case K_WATER: {
+        if (!h->legacy_rows) {
+            if (spc) LAUNCH_ON(h, cs, k_water_rows<true>, h->wgrid, 128, 0, h->rowpar, D.ncgp_solute, h->upk.p, h->rec_i.p, h->rec_f.p, h->wT.p,
+                               h->pw0.p, h->pw12.p, h->wstart_w.p, h->wdesc.p, h->wrow.p, D.nat_solute, grad);
+            else LAUNCH_ON(h, cs, k_water_rows<false>, h->wgrid, 128, 0, h->rowpar, D.ncgp_solute, h->upk.p, h->rec_i.p, h->rec_f.p, h->wT.p,
+                           h->pw0.p, h->pw12.p, h->wstart_w.p, h->wdesc.p, h->wrow.p, D.nat_solute, grad);
+            break;
+        }
 #define WCASE(P, S, G)                                                                                                             \
     LAUNCH_ON(h, cs, (k_water_force<P, S, G>), h->wgrid, 128, 0, D, h->x.p, h->px.p, h->py.p, h->pz.p, h->pk_q.p, h->pk_ct.p,     \
               h->pk_atom.p, h->wstart_w.p, h->wdesc.p, h->wrow.p, grad, E, nE, want_e)
@@ -628,6 +742,13 @@ static void launch_step_kernel(qnb_handle *h, int k, cudaStream_t cs, int flags)
         break;
     }
     case K_SOLUTE: {
+        if (!h->legacy_rows) {
+            if (h->pw_hlj) LAUNCH_ON(h, cs, k_solute_rows<true>, h->sgrid, 128, 0, h->rowpar, h->upk.p, h->nq_off.p, h->rec_i.p, h->rec_f.p, h->wT.p,
+                                     h->ljp.p, h->pw0.p, h->pw12.p, h->wstart_s.p, h->sdesc.p, h->srow.p, h->sspec.p, h->pk_atom.p, grad);
+            else LAUNCH_ON(h, cs, k_solute_rows<false>, h->sgrid, 128, 0, h->rowpar, h->upk.p, h->nq_off.p, h->rec_i.p, h->rec_f.p, h->wT.p,
+                           h->ljp.p, h->pw0.p, h->pw12.p, h->wstart_s.p, h->sdesc.p, h->srow.p, h->sspec.p, h->pk_atom.p, grad);
+            break;
+        }
         const size_t sm = solute_smem(D);
 #define SCASE(P, G)                                                                                                              \
     LAUNCH_ON(h, cs, (k_solute_force<P, G>), h->sgrid, 128, sm, D, h->x.p, h->px.p, h->py.p, h->pz.p, h->pk_q.p, h->pk_qd.p,    \
@@ -662,6 +783,15 @@ static void launch_step_kernel(qnb_handle *h, int k, cudaStream_t cs, int flags)
     case K_LRF:
         LAUNCH_ON(h, cs, k_lrf_taylor, cdiv(D.natom, 128), 128, 0, D, h->x.p, h->lrf.p, grad, E, nE);
         break;
+    case K_ENERGY: {
+        const int n = h->n_ww_e + h->n_pp_e + h->n_pw_e;
+        const int grid = std::max(1, std::min(cdiv(n, 128), 8 * h->nsm));
+        if (pbc) LAUNCH_ON(h, cs, k_pair_energy<true>, grid, 128, 0, h->epar, h->n_ww_e, h->ww_pairs.p, h->n_pp_e, h->pp_pairs.p, h->n_pw_e,
+                           h->pw_pairs.p, h->px.p, h->py.p, h->pz.p, h->pk_qd.p, h->pk_ct.p, h->pk_sw.p, h->x.p, h->ljd.p, h->ljcode.p, E, nE);
+        else LAUNCH_ON(h, cs, k_pair_energy<false>, grid, 128, 0, h->epar, h->n_ww_e, h->ww_pairs.p, h->n_pp_e, h->pp_pairs.p, h->n_pw_e,
+                       h->pw_pairs.p, h->px.p, h->py.p, h->pz.p, h->pk_qd.p, h->pk_ct.p, h->pk_sw.p, h->x.p, h->ljd.p, h->ljcode.p, E, nE);
+        break;
+    }
     case K_RST: {
         const qnb_solvent_restraints &r = h->rst;
         RstPar P{};
@@ -684,15 +814,16 @@ static void launch_step_kernel(qnb_handle *h, int k, cudaStream_t cs, int flags)
 
 // The kernels of one evaluation are independent (they only meet in atomicAdd on grad/E), so they are issued on
 // four streams between a fork and a join event: at 12k atoms no single kernel fills 148 SMs.
-static const int kStreamOf[K_COUNT] = {0, 1, 2, 3, 4, -1, 4};   // aux stream index, -1 = main stream
+static const int kStreamOf[K_COUNT] = {0, 1, 2, 3, 4, -1, 4, 5};   // aux stream index, -1 = main stream
 
 static int issue_step(qnb_handle *h, int flags, bool out_cleared = false) {
     if (!out_cleared) CU(cudaMemsetAsync(h->out.p, 0, h->nout * sizeof(double), h->st));
     if ((flags & QNB_FLAG_MD) && h->npk > 0)
-        LAUNCH(h, k_pack_coords, cdiv(h->npk, 256), 256, 0, h->npk, h->pk_atom.p, h->x.p, h->px.p, h->py.p, h->pz.p);
+        LAUNCH(h, k_pack_step, cdiv(h->npk, 256), 256, 0, h->npk, h->fix, h->D.nat_solute, h->pk_atom.p, h->pk_sw.p, h->pk_q.p, h->pk_ct.p,
+               h->x.p, h->px.p, h->py.p, h->pz.p, h->rec_i.p, h->rec_f.p, h->wT.p);
     CU(cudaEventRecord(h->ev_fork, h->st));
     bool used[kAux] = {};
-    static const int kOrder[K_COUNT] = {K_RST, K_QSTATIC, K_SOLUTE, K_QPARTNER, K_QATOM, K_WATER, K_LRF};
+    static const int kOrder[K_COUNT] = {K_RST, K_QSTATIC, K_SOLUTE, K_QATOM, K_QPARTNER, K_WATER, K_ENERGY, K_LRF};
     for (int o = 0; o < K_COUNT; o++) {
         const int k = kOrder[o];
         if (!step_kernel_active(h, k, flags)) continue;
@@ -1346,7 +1477,9 @@ int qnb_bench_kernels(qnb_handle *h, const double *lambda, int flags, int reps, 
     cudaMemcpyAsync(h->lam_dev, h->hlam, h->T.s.nstates * sizeof(double), cudaMemcpyHostToDevice, h->st);
     std::string names;
     int n = 0;
-    if (h->npk > 0) LAUNCH(h, k_pack_coords, cdiv(h->npk, 256), 256, 0, h->npk, h->pk_atom.p, h->x.p, h->px.p, h->py.p, h->pz.p);
+    if (h->npk > 0)
+        LAUNCH(h, k_pack_step, cdiv(h->npk, 256), 256, 0, h->npk, h->fix, h->D.nat_solute, h->pk_atom.p, h->pk_sw.p, h->pk_q.p, h->pk_ct.p,
+               h->x.p, h->px.p, h->py.p, h->pz.p, h->rec_i.p, h->rec_f.p, h->wT.p);
     for (int k = 0; k < K_COUNT; k++) {
         if (!step_kernel_active(h, k, flags)) continue;
         if (n >= ms_cap) break;
@@ -1403,6 +1536,8 @@ int qnb_finalize(qnb_handle *h) {
     h->shk_first.release(); h->shk_ij.release(); h->shk_d2.release(); h->shk_winv.release(); h->shk_x.release();
     h->shk_xx.release(); h->shk_iter.release();
     h->item_posf.release();
+    h->upk.release(); h->pk_sw.release(); h->e_cnt.release(); h->e_off.release(); h->rec_i.release(); h->rec_f.release(); h->wT.release();
+    h->pw12.release(); h->ljp.release(); h->pw0.release(); h->ww_pairs.release(); h->pp_pairs.release(); h->pw_pairs.release();
     h->item_pos.release(); h->src.release(); h->cell_unsorted.release(); h->item_nq.release(); h->src_off.release();
     if (h->hx) cudaFreeHost(h->hx);
     if (h->hout) cudaFreeHost(h->hout);

@@ -108,19 +108,22 @@ __global__ void k_pack_items(Dev D, const double *__restrict__ upos, const int *
 // Packed atoms: the non-Q atoms of every non-excluded unit, in cell order of the units.  Row entries are indices
 // into this order, so the lanes of a warp (consecutive row entries = neighbouring units of one cell) read
 // neighbouring records instead of gathering all over the coordinate array.
+// upk[u] = first packed atom of unit u (-1: not packed), pk_sw[p] = switch atom of the packed atom's unit.
 __global__ void k_pack_atoms(Dev D, const int *__restrict__ cell_items, const int *__restrict__ src_off,
                              int *__restrict__ pk_atom, float *__restrict__ pk_q, double *__restrict__ pk_qd,
-                             int *__restrict__ pk_ct) {
+                             int *__restrict__ pk_ct, int *__restrict__ pk_sw, int *__restrict__ upk) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= D.nunit) return;
     const int u = cell_items[idx];
-    if (D.u_excl[u]) return;
+    if (D.u_excl[u]) { upk[u] = -1; return; }
     const int g = D.u_grp[u], gf = D.g_first[g], gn = D.g_n[g];
     int p = src_off[idx];
+    upk[u] = p;
+    const int sw = D.u_sw[u];
     for (int k = 0; k < gn; k++) {
         const int i = D.g_atoms[gf + k];
         if (D.is_q[i]) continue;
-        pk_atom[p] = i; pk_q[p] = D.crgf[i]; pk_qd[p] = D.crg[i]; pk_ct[p] = D.ctype[i];
+        pk_atom[p] = i; pk_q[p] = D.crgf[i]; pk_qd[p] = D.crg[i]; pk_ct[p] = D.ctype[i]; pk_sw[p] = sw;
         p++;
     }
 }
@@ -320,7 +323,10 @@ __device__ __forceinline__ int unit_tiles(const Dev &D, int u, int tile_atoms) {
 // counts on C2 and C5 (tools/exp_trace.py, -DQNB_TRACE).  own = carries FP64 energies, mir = forces only, b = the
 // other unit kind.
 struct ChunkCost { int own, mir, b, tile; };
-__device__ __forceinline__ ChunkCost chunk_cost(int tile_atoms) {
+// new_rows: the round-2 gradient-only kernels (qnb_rows.cuh), where own and mirror chunks cost the same (issue slots per
+// chunk counted in the SASS: water A 105, B 70; solute A 130, B 290; tile change ~60 / ~90)
+__device__ __forceinline__ ChunkCost chunk_cost(int tile_atoms, bool new_rows) {
+    if (new_rows) return tile_atoms == 0 ? ChunkCost{105, 105, 70, 60} : ChunkCost{130, 130, 290, 90};
     return tile_atoms == 0 ? ChunkCost{110, 75, 68, 80} : ChunkCost{165, 145, 510, 160};
 }
 // chunk counts of one unit's tile: own-carrying A chunks, mirror-only A chunks, B chunks (own entries come first)
@@ -330,21 +336,21 @@ __device__ __forceinline__ void unit_chunks(const int *__restrict__ counts, int 
     n_mir = (na + 31) / 32 - n_own;
     n_b = (counts[3 * u + 2] + 31) / 32;
 }
-__global__ void k_chunk_count(Dev D, int u0, int n, int tile_atoms, const int *__restrict__ counts, int *__restrict__ nch,
+__global__ void k_chunk_count(Dev D, int u0, int n, int tile_atoms, bool new_rows, const int *__restrict__ counts, int *__restrict__ nch,
                               int *__restrict__ ucost) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const int u = u0 + k;
     int n_own, n_mir, n_b;
     unit_chunks(counts, u, n_own, n_mir, n_b);
-    const ChunkCost w = chunk_cost(tile_atoms);
+    const ChunkCost w = chunk_cost(tile_atoms, new_rows);
     const int tiles = unit_tiles(D, u, tile_atoms);
     nch[k] = tiles * (n_own + n_mir + n_b);
     ucost[k] = (n_own + n_mir + n_b) > 0 ? tiles * (n_own * w.own + n_mir * w.mir + n_b * w.b + w.tile) : 0;
 }
 // first chunk of every warp of a persistent force kernel: equal shares of the summed chunk costs.
 // wstart[w] = smallest chunk c whose cost prefix reaches w*total/nwarp; wstart[nwarp] = number of chunks.
-__global__ void k_warp_starts(Dev D, int u0, int n, int tile_atoms, const int *__restrict__ counts,
+__global__ void k_warp_starts(Dev D, int u0, int n, int tile_atoms, bool new_rows, const int *__restrict__ counts,
                               const int *__restrict__ choff, const int *__restrict__ cost_off, int nwarp,
                               int *__restrict__ wstart) {
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
@@ -357,7 +363,7 @@ __global__ void k_warp_starts(Dev D, int u0, int n, int tile_atoms, const int *_
     const int k = lo, u = u0 + k;
     int n_own, n_mir, n_b;
     unit_chunks(counts, u, n_own, n_mir, n_b);
-    const ChunkCost cw = chunk_cost(tile_atoms);
+    const ChunkCost cw = chunk_cost(tile_atoms, new_rows);
     const int tiles = unit_tiles(D, u, tile_atoms);
     int c = choff[k], acc = cost_off[k];
     for (int tile = 0; tile < tiles && acc < target && n_own + n_mir + n_b > 0; tile++) {

@@ -1,0 +1,578 @@
+// qnb_rows.cuh -- round-2 row kernels: FP32 gradient kernels over the chunked unit rows and one FP64 energy kernel
+// over flat per-pair lists.
+//
+// Replaces the bodies of nonbond_pp/_box, nonbond_pw/_box, nonbond_ww/_box, nonbond_ww_spc/_box (nbe, nbe_b, nbe_spc,
+// nbe_spcb: nonbondene.f90:4694-5012, 5509-5657, 5886-6077; nonbonded.f90:45-109, 247-291).
+//
+// Why two kinds of kernel.  The north_star asks for FP32 pair math with FP64 accumulation.  Gradients tolerate FP32
+// (bar: 1e-5 relative RMS); the energy sums do not: E%ww%el of a water sphere is ~ -7 kcal/mol out of 5e5 terms of
+// magnitude 30-80, so a 1e-6 bar on the net value needs ~1e-10 per term.  Round 1 carried FP64 energy chains inside
+// the FP32 kernels: 163-248 registers, 12-16 warps per SM, 63 FP64->FP32 conversions per chunk on the 16-lane XU pipe.
+// Here the two jobs are separate kernels that run concurrently and use different pipes:
+//   k_water_rows / k_solute_rows  gradient only, pure FP32, packed FFMA2/FMUL2/FADD2 (sm_100) for two site pairs per
+//                                 instruction, coordinates as 32-bit fixed point so that i-j differences are exact
+//                                 and periodic images come from integer wrap-around;
+//   k_pair_energy                 energies only, pure FP64, one thread per listed pair (owner side), MUFU.RSQ64H seed +
+//                                 one Newton step folded into two running sums per charge class.
+// Each pair's gradient is still evaluated from both sides (full rows, gather only).  Measured alternative
+// (tools/microbench2.cu, profiles/r02a_microbench2.txt): returning the partner's nine gradient components through
+// warp-coalesced RED.F64 costs 10-16 SM clocks per RED instruction, 90-140 per 32-pair chunk, against ~31 SM clocks to
+// recompute the chunk from the other side.
+#pragma once
+#include "qnb_kernels.cuh"
+
+namespace qnb {
+
+// ---- fixed-point frame: P = frac((x - org) / period) * 2^32 per component.  Differences of two P wrap modulo the
+// period, i.e. they ARE the minimum image when period = box length (boxlength*nint(dx/boxlength) of the reference for
+// every pair whose components stay clear of half a box length: all listed pairs).  Non-periodic systems use a
+// power-of-two period that covers the system several times.
+struct FixFrame {
+    double org[3], inv_period[3];
+    float scale[3];   // period / 2^32
+};
+__device__ __forceinline__ int fix_coord(double x, double org, double invp) {
+    double u = (x - org) * invp;
+    u -= floor(u);
+    return (int)__double2uint_rd(u * 4294967296.0);   // saturating conversion: u == 1.0 after rounding stays in range
+}
+
+typedef float2 f2;
+__device__ __forceinline__ f2 mk2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ f2 rsq2(f2 a) { return mk2(rsqrt_fast(a.x), rsqrt_fast(a.y)); }
+
+// per packed atom, rewritten every step by k_pack_step
+//   rec_i = {P of the atom's unit switch atom (x,y,z), compact type}
+//   rec_f = {offset from that switch atom (x,y,z), charge}
+//   wT    = waters only, three float4 starting at the oxygen's packed index: hydrogen offsets from the oxygen, laid
+//           out as the packed operands of the water kernel:
+//           {t1x,t2x,t1y,t2y} {t1z,t2z,t2x,t1x} {t2y,t1y,t2z,t1z}
+// and px/py/pz: FP64 coordinates in packed order (energy kernel)
+__global__ void __launch_bounds__(256)
+k_pack_step(int npk, FixFrame F, int nat_solute, const int *__restrict__ pk_atom, const int *__restrict__ pk_sw,
+            const float *__restrict__ pk_q, const int *__restrict__ pk_ct, const double *__restrict__ x,
+            double *__restrict__ px, double *__restrict__ py, double *__restrict__ pz, int4 *__restrict__ rec_i,
+            float4 *__restrict__ rec_f, float4 *__restrict__ wT) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npk) return;
+    const int i = pk_atom[p], sw = pk_sw[p];
+    const double xi = x[3 * i], yi = x[3 * i + 1], zi = x[3 * i + 2];
+    double xs = xi, ys = yi, zs = zi;
+    if (sw != i) { xs = x[3 * sw]; ys = x[3 * sw + 1]; zs = x[3 * sw + 2]; }
+    px[p] = xi; py[p] = yi; pz[p] = zi;
+    rec_i[p] = make_int4(fix_coord(xs, F.org[0], F.inv_period[0]), fix_coord(ys, F.org[1], F.inv_period[1]),
+                         fix_coord(zs, F.org[2], F.inv_period[2]), pk_ct[p]);
+    rec_f[p] = make_float4((float)(xi - xs), (float)(yi - ys), (float)(zi - zs), pk_q[p]);
+    if (i >= nat_solute && sw == i) {
+        const float t1x = (float)(x[3 * i + 3] - xi), t1y = (float)(x[3 * i + 4] - yi), t1z = (float)(x[3 * i + 5] - zi);
+        const float t2x = (float)(x[3 * i + 6] - xi), t2y = (float)(x[3 * i + 7] - yi), t2z = (float)(x[3 * i + 8] - zi);
+        wT[p] = make_float4(t1x, t2x, t1y, t2y);
+        wT[p + 1] = make_float4(t1z, t2z, t2x, t1x);
+        wT[p + 2] = make_float4(t2y, t1y, t2z, t1z);
+    }
+}
+
+// FP32 parameters of the row kernels (kernel argument, constant bank)
+struct RowPar {
+    float scale[3];
+    // water-water, packed by the groups of the kernel: g=0 (a in {1,2}, b=0), 1 (1,1)(2,2), 2 (1,2)(2,1), 3 (0,1)(0,2)
+    f2 wQ[4], wA12[4], wB6[4];
+    float q00, A00, B00;          // (0,0): charge product, 12 A, 6 B
+    float wq0;                    // charges of the three water sites (pw)
+    f2 wq12;
+    float el14;
+    int nct;
+};
+
+// LJ + Coulomb scale factor of one site pair: returns c with grad_i += d * c  (c = -dv of nbe, nonbonded.f90:45-75)
+__device__ __forceinline__ float pair_c(float r2, float qq, float A12, float B6) {
+    const float ri = rsqrt_fast(r2), ri2 = ri * ri, r6 = ri2 * ri2 * ri2;
+    const float w = fmaf(A12 * r6, r6, fmaf(-B6, r6, qq * ri));
+    return w * ri2;
+}
+__device__ __forceinline__ f2 pair_c2(f2 r2, f2 qq, f2 A12, f2 B6) {
+    const f2 ri = rsq2(r2), ri2 = mul2(ri, ri), r6 = mul2(mul2(ri2, ri2), ri2);
+    const f2 w = fma2(mul2(A12, r6), r6, fma2(mk2(-B6.x, -B6.y), r6, mul2(qq, ri)));
+    return mul2(w, ri2);
+}
+__device__ __forceinline__ f2 coul_c2(f2 r2, f2 qq) {
+    const f2 ri = rsq2(r2), ri2 = mul2(ri, ri);
+    return mul2(mul2(qq, ri), ri2);
+}
+__device__ __forceinline__ f2 len2(f2 dx, f2 dy, f2 dz) { return fma2(dx, dx, fma2(dy, dy, mul2(dz, dz))); }
+
+// ------------------------------------------------------------------------------------------------
+// Water rows, gradient only: ww (3x3 site tile, both sides of every pair) + the water side of pw.
+// One warp streams a contiguous range of 32-entry chunks (k_warp_starts); lanes = partners of the row's water.
+#ifndef QNB_WROWS_MINB
+#define QNB_WROWS_MINB 5
+#endif
+template <bool SPC>
+__global__ void __launch_bounds__(128, QNB_WROWS_MINB)
+k_water_rows(RowPar P, int nsol, const int *__restrict__ upk, const int4 *__restrict__ rec_i, const float4 *__restrict__ rec_f,
+             const float4 *__restrict__ wT, const float2 *__restrict__ pw0, const float4 *__restrict__ pw12,
+             const int *__restrict__ wstart, const int2 *__restrict__ cdesc, const uint32_t *__restrict__ crow,
+             int i0_water /* nat_solute */, double *__restrict__ grad) {
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int c0 = wstart[gw], c1 = wstart[gw + 1];
+    if (c0 >= c1) return;
+    int cur_w = -1;
+    int Pix = 0, Piy = 0, Piz = 0;
+    f2 nSx = mk2(0, 0), nSy = nSx, nSz = nSx;                 // minus the own hydrogens' offsets {s1, s2}
+    f2 G12x = nSx, G12y = nSx, G12z = nSx, G0x = nSx, G0y = nSx, G0z = nSx;   // gradient of sites 1,2 / of site 0 (two halves)
+    float g0x = 0.f, g0y = 0.f, g0z = 0.f;
+    const int slot = split_slot<9, 16>(lane);
+
+    auto flush = [&]() {
+        if (cur_w < 0) return;
+        float s[9] = {g0x + (G0x.x + G0x.y), g0y + (G0y.x + G0y.y), g0z + (G0z.x + G0z.y),
+                      G12x.x, G12y.x, G12z.x, G12x.y, G12y.y, G12z.y};
+        const float mine = split_reduce<9, 16>(s, lane);
+        if (slot >= 0) atomicAdd(&grad[3 * (size_t)(i0_water + 3 * cur_w) + slot], (double)mine);
+    };
+    int2 dn = cdesc[c0];
+    uint32_t en = crow[(size_t)c0 * 32 + lane];
+    for (int c = c0; c < c1; c++) {
+        const int2 d = dn;
+        const uint32_t e = en;
+        if (c + 1 < c1) { dn = cdesc[c + 1]; en = crow[(size_t)(c + 1) * 32 + lane]; }
+        if (d.x != cur_w) {
+            flush();
+            cur_w = d.x;
+            const int pi = upk[nsol + cur_w];
+            const int4 ri = rec_i[pi];
+            const float4 a = wT[pi], b = wT[pi + 1];
+            Pix = ri.x; Piy = ri.y; Piz = ri.z;
+            nSx = mk2(-a.x, -a.y); nSy = mk2(-a.z, -a.w); nSz = mk2(-b.x, -b.y);
+            G12x = G12y = G12z = G0x = G0y = G0z = mk2(0.f, 0.f);
+            g0x = g0y = g0z = 0.f;
+        }
+        const bool valid = e != kPadEntry;
+        const int p = valid ? (int)(e & kIdMask) : 0;
+        const int4 rj = rec_i[p];
+        // vector from the own oxygen to the partner's switch atom; a padding lane is sent to 1e18 A, where every
+        // r^-3 and r^-6 below flushes to zero
+        float Rx = (float)(rj.x - Pix) * P.scale[0];
+        const float Ry = (float)(rj.y - Piy) * P.scale[1], Rz = (float)(rj.z - Piz) * P.scale[2];
+        Rx = valid ? Rx : 1.0e18f;
+        const f2 RRx = mk2(Rx, Rx), RRy = mk2(Ry, Ry), RRz = mk2(Rz, Rz);
+        if (d.y == kChunkA) {
+            const float4 ta = wT[p], tb = wT[p + 1], tc = wT[p + 2];
+            const f2 U12x = add2(RRx, mk2(ta.x, ta.y)), U12y = add2(RRy, mk2(ta.z, ta.w)), U12z = add2(RRz, mk2(tb.x, tb.y));
+            const f2 U21x = add2(RRx, mk2(tb.z, tb.w)), U21y = add2(RRy, mk2(tc.x, tc.y)), U21z = add2(RRz, mk2(tc.z, tc.w));
+            f2 dx, dy, dz, cc;
+            // (1,0) (2,0)
+            dx = add2(RRx, nSx); dy = add2(RRy, nSy); dz = add2(RRz, nSz);
+            cc = SPC ? coul_c2(len2(dx, dy, dz), P.wQ[0]) : pair_c2(len2(dx, dy, dz), P.wQ[0], P.wA12[0], P.wB6[0]);
+            G12x = fma2(dx, cc, G12x); G12y = fma2(dy, cc, G12y); G12z = fma2(dz, cc, G12z);
+            // (1,1) (2,2)
+            dx = add2(U12x, nSx); dy = add2(U12y, nSy); dz = add2(U12z, nSz);
+            cc = SPC ? coul_c2(len2(dx, dy, dz), P.wQ[1]) : pair_c2(len2(dx, dy, dz), P.wQ[1], P.wA12[1], P.wB6[1]);
+            G12x = fma2(dx, cc, G12x); G12y = fma2(dy, cc, G12y); G12z = fma2(dz, cc, G12z);
+            // (1,2) (2,1)
+            dx = add2(U21x, nSx); dy = add2(U21y, nSy); dz = add2(U21z, nSz);
+            cc = SPC ? coul_c2(len2(dx, dy, dz), P.wQ[2]) : pair_c2(len2(dx, dy, dz), P.wQ[2], P.wA12[2], P.wB6[2]);
+            G12x = fma2(dx, cc, G12x); G12y = fma2(dy, cc, G12y); G12z = fma2(dz, cc, G12z);
+            // (0,1) (0,2)
+            cc = SPC ? coul_c2(len2(U12x, U12y, U12z), P.wQ[3]) : pair_c2(len2(U12x, U12y, U12z), P.wQ[3], P.wA12[3], P.wB6[3]);
+            G0x = fma2(U12x, cc, G0x); G0y = fma2(U12y, cc, G0y); G0z = fma2(U12z, cc, G0z);
+            // (0,0): the pair that carries LJ in nonbond_ww_spc
+            const float c00 = pair_c(fmaf(Rx, Rx, fmaf(Ry, Ry, Rz * Rz)), P.q00, P.A00, P.B00);
+            g0x = fmaf(Rx, c00, g0x); g0y = fmaf(Ry, c00, g0y); g0z = fmaf(Rz, c00, g0z);
+        } else {
+            // solute atom acting on the own water (pw seen from the water: gradient only)
+            const float4 oj = rec_f[p];
+            const float ex = Rx + oj.x, ey = Ry + oj.y, ez = Rz + oj.z;
+            const float2 l0 = pw0[rj.w];
+            const float4 l12 = pw12[rj.w];
+            const f2 dx = add2(mk2(ex, ex), nSx), dy = add2(mk2(ey, ey), nSy), dz = add2(mk2(ez, ez), nSz);
+            const f2 cc = pair_c2(len2(dx, dy, dz), mul2(P.wq12, mk2(oj.w, oj.w)), mk2(l12.x, l12.y), mk2(l12.z, l12.w));
+            G12x = fma2(dx, cc, G12x); G12y = fma2(dy, cc, G12y); G12z = fma2(dz, cc, G12z);
+            const float c0 = pair_c(fmaf(ex, ex, fmaf(ey, ey, ez * ez)), P.wq0 * oj.w, l0.x, l0.y);
+            g0x = fmaf(ex, c0, g0x); g0y = fmaf(ey, c0, g0y); g0z = fmaf(ez, c0, g0z);
+        }
+    }
+    flush();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Solute rows, gradient only: pp (both sides) + the solute side of pw.  A chunk belongs to one (charge group, tile of
+// up to four non-Q atoms); the tile's atoms are the packed halves: {t0,t1} and {t2,t3}.
+// ljp: [2][nct][nct] {12 A, 6 B} of a type pair, plane 0 by the pair's own LJ code (ljcod), plane 1 for 1-4 pairs
+// (code 3); both combination rules are resolved on the host.
+#ifndef QNB_SROWS_MINB
+#define QNB_SROWS_MINB 4
+#endif
+template <bool HLJ /* solvent hydrogens carry LJ against some solute type */>
+__global__ void __launch_bounds__(128, QNB_SROWS_MINB)
+k_solute_rows(RowPar P, const int *__restrict__ upk, const int *__restrict__ nq_off, const int4 *__restrict__ rec_i,
+              const float4 *__restrict__ rec_f, const float4 *__restrict__ wT, const float2 *__restrict__ ljp,
+              const float2 *__restrict__ pw0, const float4 *__restrict__ pw12, const int *__restrict__ wstart,
+              const int2 *__restrict__ cdesc, const uint32_t *__restrict__ crow, const uint16_t *__restrict__ cspec,
+              const int *__restrict__ pk_atom, double *__restrict__ grad) {
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int c0 = wstart[gw], c1 = wstart[gw + 1];
+    if (c0 >= c1) return;
+    int cur_key = -1, nt = 0, pi0 = 0;
+    int Pix = 0, Piy = 0, Piz = 0;
+    f2 nOx[2], nOy[2], nOz[2], Q[2];      // minus the tile atoms' offsets from the switch atom; charges
+    int ct[4] = {0, 0, 0, 0};
+    f2 Gx[2] = {mk2(0.f, 0.f), mk2(0.f, 0.f)}, Gy[2] = {mk2(0.f, 0.f), mk2(0.f, 0.f)}, Gz[2] = {mk2(0.f, 0.f), mk2(0.f, 0.f)};
+    const int slot = split_slot<12, 16>(lane);
+    auto flush = [&]() {
+        if (cur_key < 0) return;
+        float s[12] = {Gx[0].x, Gy[0].x, Gz[0].x, Gx[0].y, Gy[0].y, Gz[0].y, Gx[1].x, Gy[1].x, Gz[1].x, Gx[1].y, Gy[1].y, Gz[1].y};
+        const float mine = split_reduce<12, 16>(s, lane);
+        const int t = slot / 3;
+        if (slot >= 0 && t < nt) atomicAdd(&grad[3 * (size_t)pk_atom[pi0 + t] + (slot - 3 * t)], (double)mine);
+    };
+    int2 dn = cdesc[c0];
+    uint32_t en = crow[(size_t)c0 * 32 + lane];
+    uint32_t sn = cspec[(size_t)c0 * 32 + lane];
+    for (int c = c0; c < c1; c++) {
+        const int2 d = dn;
+        const uint32_t e = en, spec = sn;
+        if (c + 1 < c1) { dn = cdesc[c + 1]; en = crow[(size_t)(c + 1) * 32 + lane]; sn = cspec[(size_t)(c + 1) * 32 + lane]; }
+        const int tile = (d.y >> 8) & 0xff;
+        const int key = d.x * 256 + tile;
+        if (key != cur_key) {
+            flush();
+            cur_key = key;
+            const int k0 = nq_off[d.x] + tile * 4;
+            nt = min(4, nq_off[d.x + 1] - k0);
+            pi0 = upk[d.x] + tile * 4;
+            const int4 r0 = rec_i[pi0];
+            Pix = r0.x; Piy = r0.y; Piz = r0.z;
+            float ox[4], oy[4], oz[4], q[4];
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                // atoms beyond the tile repeat the last one with zero charge and a type whose row is never kept
+                const int pt = pi0 + min(t, nt - 1);
+                const float4 o = rec_f[pt];
+                ox[t] = -o.x; oy[t] = -o.y; oz[t] = -o.z; q[t] = t < nt ? o.w : 0.f;
+                ct[t] = rec_i[pt].w;
+            }
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                nOx[h] = mk2(ox[2 * h], ox[2 * h + 1]); nOy[h] = mk2(oy[2 * h], oy[2 * h + 1]); nOz[h] = mk2(oz[2 * h], oz[2 * h + 1]);
+                Q[h] = mk2(q[2 * h], q[2 * h + 1]);
+                Gx[h] = Gy[h] = Gz[h] = mk2(0.f, 0.f);
+            }
+        }
+        const bool valid = e != kPadEntry;
+        const int p = valid ? (int)(e & kIdMask) : 0;
+        const int4 rj = rec_i[p];
+        float Rx = (float)(rj.x - Pix) * P.scale[0];
+        const float Ry = (float)(rj.y - Piy) * P.scale[1], Rz = (float)(rj.z - Piz) * P.scale[2];
+        Rx = valid ? Rx : 1.0e18f;
+        if ((d.y & 0xff) == kChunkA) {
+            // ---- solute partner atom: 3 bits per tile atom from k_chunk_fill: 1 skip, 2 1-4 pair, (4 energy side)
+            const float4 oj = rec_f[p];
+            const float ex = Rx + oj.x, ey = Ry + oj.y, ez = Rz + oj.z;
+            const f2 EEx = mk2(ex, ex), EEy = mk2(ey, ey), EEz = mk2(ez, ez);
+            const int plane = P.nct * P.nct;
+            float A12[4], B6[4], qs[4];
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                const unsigned sb = (spec >> (3 * t)) & 7u;
+                const bool i14 = (sb & 2u) != 0, skip = (sb & 1u) != 0 || t >= nt;
+                const float2 l = ljp[(i14 ? plane : 0) + ct[t] * P.nct + rj.w];
+                A12[t] = skip ? 0.f : l.x; B6[t] = skip ? 0.f : l.y;
+                qs[t] = skip ? 0.f : (i14 ? oj.w * P.el14 : oj.w);
+            }
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const f2 dx = add2(EEx, nOx[h]), dy = add2(EEy, nOy[h]), dz = add2(EEz, nOz[h]);
+                // r = 0 only for an atom against itself (skip): keep its 1/r finite
+                f2 r2 = len2(dx, dy, dz);
+                r2 = mk2(fmaxf(r2.x, 1e-12f), fmaxf(r2.y, 1e-12f));
+                const f2 cc = pair_c2(r2, mul2(Q[h], mk2(qs[2 * h], qs[2 * h + 1])), mk2(A12[2 * h], A12[2 * h + 1]), mk2(B6[2 * h], B6[2 * h + 1]));
+                Gx[h] = fma2(dx, cc, Gx[h]); Gy[h] = fma2(dy, cc, Gy[h]); Gz[h] = fma2(dz, cc, Gz[h]);
+            }
+        } else {
+            // ---- partner water: the three sites against every tile atom (nonbond_pw, solute side)
+            const float4 ta = wT[p], tb = wT[p + 1];
+            const float ux[3] = {Rx, Rx + ta.x, Rx + ta.y}, uy[3] = {Ry, Ry + ta.z, Ry + ta.w}, uz[3] = {Rz, Rz + tb.x, Rz + tb.y};
+            float2 l0[4];
+            float4 l12[4];
+#pragma unroll
+            for (int t = 0; t < 4; t++) { l0[t] = pw0[ct[t]]; if (HLJ) l12[t] = pw12[ct[t]]; }
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+#pragma unroll
+                for (int b = 0; b < 3; b++) {
+                    const f2 dx = add2(mk2(ux[b], ux[b]), nOx[h]), dy = add2(mk2(uy[b], uy[b]), nOy[h]), dz = add2(mk2(uz[b], uz[b]), nOz[h]);
+                    const float qb = b == 0 ? P.wq0 : (b == 1 ? P.wq12.x : P.wq12.y);
+                    const f2 qq = mul2(Q[h], mk2(qb, qb));
+                    f2 cc;
+                    if (b == 0) cc = pair_c2(len2(dx, dy, dz), qq, mk2(l0[2 * h].x, l0[2 * h + 1].x), mk2(l0[2 * h].y, l0[2 * h + 1].y));
+                    else if (HLJ) {
+                        const f2 A = b == 1 ? mk2(l12[2 * h].x, l12[2 * h + 1].x) : mk2(l12[2 * h].y, l12[2 * h + 1].y);
+                        const f2 B = b == 1 ? mk2(l12[2 * h].z, l12[2 * h + 1].z) : mk2(l12[2 * h].w, l12[2 * h + 1].w);
+                        cc = pair_c2(len2(dx, dy, dz), qq, A, B);
+                    } else cc = coul_c2(len2(dx, dy, dz), qq);
+                    Gx[h] = fma2(dx, cc, Gx[h]); Gy[h] = fma2(dy, cc, Gy[h]); Gz[h] = fma2(dz, cc, Gz[h]);
+                }
+            }
+        }
+    }
+    flush();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Energies: one thread per listed pair (the reference's own list: each pair once), FP64.
+//   ww_pairs {pi, pj}: packed indices of the two oxygens                      (E%ww, nonbond_ww(_spc)(_box))
+//   pp_pairs {pi, pj | img << 24 | 1-4 << 30 | skip << 31}: packed atoms      (E%pp, nonbond_pp(_box))
+//   pw_pairs {pi, pj | img << 24}: packed solute atom, packed water oxygen    (E%pw, nonbond_pw(_box))
+// 1/r: MUFU.RSQ64H seed y0 (relative error e ~ 2^-21) and one Newton step, y = y0 (3/2 - r2 y0^2 / 2), error 3/2 e^2.
+struct EnergyPar {
+    double wwQ[9], wwA[9], wwB[9];   // water-water site pairs (a*3+b)
+    double wq[3];
+    double el14;
+    int wct[3];
+    int nct, geometric, any_atom, spc;
+    double box[3], inv_box[3];
+};
+__device__ __forceinline__ double rsq64_seed(double r2) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(r2));
+    return y;
+}
+__device__ __forceinline__ double rsq64(double r2) {
+    const double y0 = rsq64_seed(r2);
+    const double p = r2 * y0;
+    return y0 * fma(-0.5 * p, y0, 1.5);
+}
+__device__ __forceinline__ void lj_f64(const EnergyPar &P, const double *__restrict__ ljd, int cta, int ctb, int code, double &A, double &B) {
+    const double ax = ljd[(cta * 3 + code - 1) * 2], ay = ljd[(cta * 3 + code - 1) * 2 + 1];
+    const double bx = ljd[(ctb * 3 + code - 1) * 2], by = ljd[(ctb * 3 + code - 1) * 2 + 1];
+    if (P.geometric) { A = ax * bx; B = ay * by; }
+    else { double t = ax + bx; t = t * t; t = t * t * t; const double e = ay * by; A = t * t * e; B = 2.0 * t * e; }
+}
+
+template <bool PBC>
+__global__ void __launch_bounds__(128)
+k_pair_energy(EnergyPar P, int n_ww, const int2 *__restrict__ ww_pairs, int n_pp, const int2 *__restrict__ pp_pairs,
+              int n_pw, const int2 *__restrict__ pw_pairs, const double *__restrict__ px, const double *__restrict__ py,
+              const double *__restrict__ pz, const double *__restrict__ pk_qd, const int *__restrict__ pk_ct,
+              const int *__restrict__ pk_sw, const double *__restrict__ x, const double *__restrict__ ljd,
+              const uint8_t *__restrict__ ljcode, double *__restrict__ Eslots, int nE) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    double e_ww_el = 0.0, e_ww_vdw = 0.0, e_pp_el = 0.0, e_pp_vdw = 0.0, e_pw_el = 0.0, e_pw_vdw = 0.0;
+    // ---- water-water
+    {
+        // SPC-type water with equal hydrogens: sum 1/r per charge class (OO, OH, HH) and weigh at the end
+        const bool classes = P.spc && P.wwQ[1] == P.wwQ[2] && P.wwQ[1] == P.wwQ[3] && P.wwQ[1] == P.wwQ[6] && P.wwQ[4] == P.wwQ[5] &&
+                             P.wwQ[4] == P.wwQ[7] && P.wwQ[4] == P.wwQ[8];
+        double s1[3] = {0, 0, 0}, s2[3] = {0, 0, 0};
+        for (int t = tid; t < n_ww; t += nthr) {
+            const int2 pr = ww_pairs[t];
+            double xi[3][3], xj[3][3];
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                xi[a][0] = px[pr.x + a]; xi[a][1] = py[pr.x + a]; xi[a][2] = pz[pr.x + a];
+                xj[a][0] = px[pr.y + a]; xj[a][1] = py[pr.y + a]; xj[a][2] = pz[pr.y + a];
+            }
+            if (PBC) {
+                // one shift per molecule pair from the O-O vector (nonbond_ww_spc_box L6016-6017, nonbond_ww_box)
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    const double sh = pshift(xi[0][k] - xj[0][k], P.box[k], P.inv_box[k]);
+                    xj[0][k] += sh; xj[1][k] += sh; xj[2][k] += sh;
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+#pragma unroll
+                for (int b = 0; b < 3; b++) {
+                    const double dx = xj[b][0] - xi[a][0], dy = xj[b][1] - xi[a][1], dz = xj[b][2] - xi[a][2];
+                    const double r2 = fma(dx, dx, fma(dy, dy, dz * dz));
+                    const bool lj = !P.spc || (a == 0 && b == 0);
+                    if (classes && !lj) {
+                        const int cl = (a == 0 || b == 0) ? 1 : 2;
+                        const double y0 = rsq64_seed(r2);
+                        s1[cl] += y0;
+                        s2[cl] = fma(y0 * y0, r2 * y0, s2[cl]);
+                    } else {
+                        const double y = rsq64(r2);
+                        e_ww_el = fma(P.wwQ[a * 3 + b], y, e_ww_el);
+                        if (lj) {
+                            const double y2 = y * y, r6 = y2 * y2 * y2;
+                            e_ww_vdw += fma(P.wwA[a * 3 + b] * r6, r6, -P.wwB[a * 3 + b] * r6);
+                        }
+                    }
+                }
+            }
+        }
+        e_ww_el += P.wwQ[1] * (1.5 * s1[1] - 0.5 * s2[1]) + P.wwQ[4] * (1.5 * s1[2] - 0.5 * s2[2]);
+    }
+    // ---- solute-solute
+    for (int t = tid; t < n_pp; t += nthr) {
+        const int2 pr = pp_pairs[t];
+        if (pr.y < 0) continue;   // excluded pair, or the other orientation of a pair inside one group
+        const int pj = pr.y & (int)kIdMask;
+        const bool i14 = (pr.y >> 30) & 1;
+        double dx = px[pj] - px[pr.x], dy = py[pj] - py[pr.x], dz = pz[pj] - pz[pr.x];
+        if (PBC) {
+            if (P.any_atom) {
+                dx += P.box[0] * img_comp((uint32_t)pr.y, 0); dy += P.box[1] * img_comp((uint32_t)pr.y, 1); dz += P.box[2] * img_comp((uint32_t)pr.y, 2);
+            } else {
+                // nonbond_pp_box L4791-4801: shift = boxlength*nint((x(sw_i)-x(sw_j))*inv_boxl)
+                const int si = pk_sw[pr.x], sj = pk_sw[pj];
+                dx += pshift(x[3 * si] - x[3 * sj], P.box[0], P.inv_box[0]);
+                dy += pshift(x[3 * si + 1] - x[3 * sj + 1], P.box[1], P.inv_box[1]);
+                dz += pshift(x[3 * si + 2] - x[3 * sj + 2], P.box[2], P.inv_box[2]);
+            }
+        }
+        const int cti = pk_ct[pr.x], ctj = pk_ct[pj];
+        double A, B;
+        lj_f64(P, ljd, cti, ctj, i14 ? 3 : (int)ljcode[cti * P.nct + ctj], A, B);
+        const double qq = i14 ? pk_qd[pr.x] * pk_qd[pj] * P.el14 : pk_qd[pr.x] * pk_qd[pj];
+        const double y = rsq64(fma(dx, dx, fma(dy, dy, dz * dz)));
+        const double y2 = y * y, r6 = y2 * y2 * y2;
+        e_pp_el = fma(qq, y, e_pp_el);
+        e_pp_vdw += fma(A * r6, r6, -B * r6);
+    }
+    // ---- solute-water
+    for (int t = tid; t < n_pw; t += nthr) {
+        const int2 pr = pw_pairs[t];
+        const int pj = pr.y & (int)kIdMask;
+        double sh[3] = {0, 0, 0};
+        const double xi = px[pr.x], yi = py[pr.x], zi = pz[pr.x];
+        if (PBC) {
+            if (P.any_atom) {
+                sh[0] = P.box[0] * img_comp((uint32_t)pr.y, 0); sh[1] = P.box[1] * img_comp((uint32_t)pr.y, 1); sh[2] = P.box[2] * img_comp((uint32_t)pr.y, 2);
+            } else {
+                // nonbond_pw_box: shift = boxlength*nint((x(solute switch)-x(water O))*inv_boxl)
+                const int si = pk_sw[pr.x];
+                sh[0] = pshift(x[3 * si] - px[pj], P.box[0], P.inv_box[0]);
+                sh[1] = pshift(x[3 * si + 1] - py[pj], P.box[1], P.inv_box[1]);
+                sh[2] = pshift(x[3 * si + 2] - pz[pj], P.box[2], P.inv_box[2]);
+            }
+        }
+        const int cti = pk_ct[pr.x];
+        const double qi = pk_qd[pr.x];
+#pragma unroll
+        for (int b = 0; b < 3; b++) {
+            const double dx = (px[pj + b] - xi) + sh[0], dy = (py[pj + b] - yi) + sh[1], dz = (pz[pj + b] - zi) + sh[2];
+            double A, B;
+            lj_f64(P, ljd, cti, P.wct[b], (int)ljcode[cti * P.nct + P.wct[b]], A, B);
+            const double y = rsq64(fma(dx, dx, fma(dy, dy, dz * dz)));
+            const double y2 = y * y, r6 = y2 * y2 * y2;
+            e_pw_el = fma(qi * P.wq[b], y, e_pw_el);
+            e_pw_vdw += fma(A * r6, r6, -B * r6);
+        }
+    }
+    // ---- block sums, one set of atomics per block
+    __shared__ double red[4][6];
+    double v[6] = {e_pp_el, e_pp_vdw, e_pw_el, e_pw_vdw, e_ww_el, e_ww_vdw};
+#pragma unroll
+    for (int k = 0; k < 6; k++) v[k] = warp_sum(v[k]);
+    if ((threadIdx.x & 31) == 0)
+        for (int k = 0; k < 6; k++) red[threadIdx.x >> 5][k] = v[k];
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        const double s = (red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x]);
+        if (s != 0.0) atomicAdd(&Eslots[(size_t)(blockIdx.x & (kESlots - 1)) * nE + threadIdx.x], s);
+    }
+}
+
+// ---- flat pair lists of the energy kernel, written at list-build time (one warp per unit)
+//   ww: own entries of water rows; pp: own entries of solute rows x the group's non-Q atoms; pw: B entries of solute rows
+//   x the group's non-Q atoms.  off_*[k]: first entry of unit k (scan of the counts k_energy_counts writes).
+__global__ void k_energy_counts(Dev D, const int *__restrict__ counts, int *__restrict__ n_ww, int *__restrict__ n_pp,
+                                int *__restrict__ n_pw) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= D.nunit) return;
+    if (u < D.ncgp_solute) {
+        const int nq = D.nq_off[u + 1] - D.nq_off[u];
+        n_pp[u] = nq * counts[3 * u];
+        n_pw[u] = nq * counts[3 * u + 2];
+    } else n_ww[u - D.ncgp_solute] = counts[3 * u];
+}
+__global__ void __launch_bounds__(256)
+k_energy_fill(Dev D, const int *__restrict__ counts, const int *__restrict__ row_off, const uint32_t *__restrict__ rows,
+              const int *__restrict__ upk, const int *__restrict__ pk_atom, const int *__restrict__ off_ww,
+              const int *__restrict__ off_pp, const int *__restrict__ off_pw, int2 *__restrict__ ww_pairs,
+              int2 *__restrict__ pp_pairs, int2 *__restrict__ pw_pairs) {
+    const int lane = threadIdx.x & 31;
+    const int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (u >= D.nunit) return;
+    const int own = counts[3 * u], nb = counts[3 * u + 2];
+    const uint32_t *r = rows + row_off[u];
+    const int pi0 = upk[u];
+    if (u >= D.ncgp_solute) {
+        int2 *dst = ww_pairs + off_ww[u - D.ncgp_solute];
+        for (int k = lane; k < own; k += 32) dst[k] = make_int2(pi0, (int)(r[k] & kIdMask));
+        return;
+    }
+    const int nq = D.nq_off[u + 1] - D.nq_off[u];
+    if (nq == 0) return;
+    int2 *dpp = pp_pairs + off_pp[u];
+    for (int k = lane; k < own; k += 32) {
+        const uint32_t e = r[k];
+        const int pb = (int)(e & kIdMask);
+        const int bb = pk_atom[pb];
+        const bool special = (e & kSpecialBit) != 0, same = special && D.grp_of_atom[bb] == u;
+        for (int t = 0; t < nq; t++) {
+            const int a = D.nq_atoms[D.nq_off[u] + t];
+            uint32_t w = (uint32_t)pb | (e & (0x3fu << kImgShift));
+            if (special) {
+                if (a == bb) w |= 0x80000000u;
+                else {
+                    const int sc = special_code(D, a, bb);
+                    if (sc == 0) w |= 0x80000000u;
+                    else if (sc == 3) w |= 0x40000000u;
+                }
+                if (same && !(a < bb)) w |= 0x80000000u;   // count once inside a group (i < j, L1874)
+            }
+            dpp[(size_t)k * nq + t] = make_int2(pi0 + t, (int)w);
+        }
+    }
+    int2 *dpw = pw_pairs + off_pw[u];
+    const uint32_t *rb = r + own + counts[3 * u + 1];
+    for (int k = lane; k < nb; k += 32) {
+        const uint32_t e = rb[k];
+        for (int t = 0; t < nq; t++) dpw[(size_t)k * nq + t] = make_int2(pi0 + t, (int)(e & (kIdMask | (0x3fu << kImgShift))));
+    }
+}
+
+// several exclusive scans in one launch: block b scans in[b][0..n[b]) into out[b][0..n[b]] (out[n] = total)
+struct ScanJobs { const int *in[8]; int *out[8]; int n[8]; };
+__global__ void __launch_bounds__(1024) k_multi_scan(ScanJobs J) {
+    __shared__ int warp_off[32];
+    __shared__ int block_total;
+    __shared__ int carry;
+    const int *in = J.in[blockIdx.x];
+    int *out = J.out[blockIdx.x];
+    const int n = J.n[blockIdx.x];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int i = base + tid;
+        const int v = i < n ? in[i] : 0;
+        const int inc = warp_incl_scan(v, lane);
+        if (lane == 31) warp_off[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            const int t = lane < nw ? warp_off[lane] : 0;
+            const int ti = warp_incl_scan(t, lane);
+            warp_off[lane] = ti - t;
+            if (lane == 31) block_total = ti;
+        }
+        __syncthreads();
+        if (i < n) out[i] = carry + warp_off[wid] + inc - v;
+        __syncthreads();
+        if (tid == 0) carry += block_total;
+        __syncthreads();
+    }
+    if (tid == 0) out[n] = carry;
+}
+
+}  // namespace qnb

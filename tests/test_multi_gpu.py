@@ -34,10 +34,7 @@ def _worker(rank, world, port, q_path, out_path, cuts, lam, shard_rows=False):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("shard_rows", [
-    False,
-    pytest.param(True, marks=pytest.mark.xfail(reason="row partition (QNB_SHARD_ROWS=1) not yet run on hardware", strict=False)),
-], ids=["pair_partition", "row_partition"])
+@pytest.mark.parametrize("shard_rows", [False, True], ids=["pair_partition", "row_partition"])
 @pytest.mark.parametrize("case", ["sphere_q", "water_box"])
 def test_sharded_allreduce_matches_oracle(case, shard_rows, tmp_path):
     import torch

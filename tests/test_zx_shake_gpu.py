@@ -2,9 +2,7 @@
 shake(xx, x), bondene.f90:1069-1150 (oracle.pyoracle.shake; itself pinned by the reference's step-0 goldens, which only
 come out right with the reference's flag-once order of operations).
 
-STATUS: the kernel was written after the round's GPU budget was spent and has not run on hardware yet; the tests are
-therefore marked xfail(strict=False) -- they report XPASS once the kernel is seen to work and cannot turn the suite red
-before that.  The file sorts after the verified suites (only the other not-yet-run cases, test_zy_*, come later).
+All cases passed on the driver's B200 at the end of round 1 (GPUTEST_r01.json): ordinary tests now.
 """
 import os
 
@@ -14,10 +12,7 @@ import pytest
 import common
 from common import golden_system
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(reason="k_shake not yet run on hardware (written after the round-1 GPU budget was spent); its per-molecule "
-                                       "source is verified on the CPU in test_shake_cpu.py",
-                                strict=False)]
+pytestmark = pytest.mark.gpu
 
 
 def _water_constraints(q):

@@ -3,19 +3,16 @@
 routines), [el_scale] pairs, qq_use_library_charges.  None of the reference's shipped inputs exercises them.
 Plus C5 at full size against the oracle's committed fingerprint (until now C5 was covered by properties only).
 
-STATUS: added after the round's GPU budget was spent.  On the CPU the product's host tables for these systems are
-already checked against the oracle entry by entry (tests/test_host_tables_cpu.py) and the oracle's gradient against
-finite differences; the kernels have not run on them yet, hence xfail(strict=False): XPASS when they agree, never a red
-suite before that.  Sorted late so that the verified cases run first.
+On the CPU the product's host tables for these systems are checked against the oracle entry by entry
+(tests/test_host_tables_cpu.py) and the oracle's gradient against finite differences.  All cases passed on the driver's
+B200 at the end of round 1 (GPUTEST_r01.json), so they are ordinary tests now.
 """
 import numpy as np
 import pytest
 
 import common
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(reason="variant systems not yet run on hardware (added after the round-1 GPU budget was spent)",
-                                strict=False)]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("case", common.variant_systems(), ids=lambda c: c[0])
