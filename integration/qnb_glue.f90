@@ -25,7 +25,7 @@ integer(c_int32_t), allocatable, target, save, private :: g_ljcod(:,:), g_listex
 integer(c_int32_t), allocatable, target, save, private :: g_qiac(:,:), g_iqexpnb(:), g_jqexpnb(:), g_els_i(:), g_els_j(:), g_qconn(:,:,:)
 real(c_double), allocatable, target, save, private     :: g_crg(:), g_iaclib(:,:), g_qcrg(:,:), g_qavdw(:,:), g_qbvdw(:,:)
 real(c_double), allocatable, target, save, private     :: g_sc(:,:,:), g_els(:,:)
-integer, save :: qnb_gpus_per_node = 8           ! device = mod(nodeid, qnb_gpus_per_node)
+! device = mod(nodeid, qnb_device_count()): ranks are dealt round-robin to the GPUs this node really has
 
 contains
 
@@ -46,8 +46,22 @@ end function qnb_message
 ! --- once, after precompute_interactions (qdyn.f90:153)
 subroutine qnb_setup
   type(qnb_system) :: s
-  integer :: i, k
+  integer :: i, k, ngpu
   real(c_double) :: bl(3), ibl(3)
+
+  ! The interfaces pass x, d and every real table as c_double: a Q6 built with -DQSINGLE / -DQUADRUPLE cannot use them.
+  if (kind(1.0_prec) /= c_double) call die('USE_QNB needs the double-precision build of Q6 (-DQDOUBLE)')
+  ! Not wired up in this glue (each would be silently wrong otherwise, ADVICE r1):
+  !  * Qdyn6p with several ranks: make_pair_lists returns before lrf_gather (nonbondene.f90:831) and gather_nonbond /
+  !    the master sum (potene.f90:114-119, 195-222) would add the GPU's already complete d, E, EQ once per rank.  The
+  !    multi-GPU route is qnb_comm_init on every rank (NCCL all-reduce inside qnb_build_lists / qnb_nonbond) WITH those
+  !    two MPI steps removed; see INTEGRATION.md.
+  !  * MC_volume (constant_pressure, md.f90:1976-2284) needs qnb_save_lists before the trial move, qnb_update_box after
+  !    every change of boxlength and qnb_restore_lists on rejection; the patch does not add those hunks.
+  if (numnodes > 1) call die('USE_QNB: run one rank per GPU only after wiring qnb_comm_init (INTEGRATION.md); this glue is serial')
+  if (use_PBC .and. constant_pressure) call die('USE_QNB: constant_pressure (MC_volume) is not hooked up in this glue')
+  ngpu = qnb_device_count()
+  if (ngpu < 1) call die('USE_QNB: no CUDA device: '//qnb_message())
 
   allocate(g_cgp(3,ncgp), g_cgpatom(size(cgpatom)), g_excl(natom), g_iqatom(natom), g_iac(natom), g_crg(natom))
   do i = 1, ncgp
@@ -122,7 +136,7 @@ subroutine qnb_setup
   s%natom_start = calculation_assignment%natom%start; s%natom_end = calculation_assignment%natom%end
   s%is_master = merge(1, 0, nodeid == 0)
 
-  if (qnb_init(s, mod(nodeid, qnb_gpus_per_node), qnb_handle) /= 0) call die('qnb_init: '//qnb_message())
+  if (qnb_init(s, mod(nodeid, ngpu), qnb_handle) /= 0) call die('qnb_init: '//qnb_message())
   if (use_PBC) then
      bl = (/ boxlength%x, boxlength%y, boxlength%z /); ibl = (/ inv_boxl%x, inv_boxl%y, inv_boxl%z /)
      if (qnb_update_box(qnb_handle, bl, ibl) /= 0) call die('qnb_update_box: '//qnb_message())

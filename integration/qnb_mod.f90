@@ -34,6 +34,10 @@ interface
         import :: c_ptr
         type(c_ptr) :: msg
     end function
+    function qnb_device_count() bind(c, name='qnb_device_count') result(n)
+        import :: c_int
+        integer(c_int) :: n                               ! usable CUDA devices on this node (0: every call fails)
+    end function
     function qnb_init(sys, device, handle) bind(c, name='qnb_init') result(rc)
         import :: c_int, c_ptr, qnb_system
         type(qnb_system), intent(in) :: sys

@@ -173,6 +173,9 @@ struct qnb_handle {
     FixFrame fix{};
     int nqp = 0, nqw = 0;
     bool qp_done = false, qw_done = false, lists_built = false;
+    bool x_from_nonbond = false;   // the device coordinates are the ones of the last qnb_nonbond (qnb_shake with xx == NULL)
+    DBuf<int> bead_atoms;          // qnb_qcp_beads work buffers, kept between calls
+    DBuf<double> bead_base, bead_disp, bead_eq;
     int64_t total_rows = 0;
     int3 lrf_reach{1, 1, 1}, list_reach{1, 1, 1};
     double box[3] = {0, 0, 0}, inv_box[3] = {0, 0, 0};
@@ -1047,7 +1050,9 @@ int qnb_set_constraints(qnb_handle *h, int nmol, const int32_t *mol_first, const
 int qnb_shake(qnb_handle *h, const double *xx, double *x, int64_t *iterations) {
     if (!h || !x) return fail("qnb_shake: null argument");
     if (!h->shk_set) return fail("qnb_shake: no constraints (call qnb_set_constraints)");
-    if (!xx && !h->lists_built) return fail("qnb_shake: xx == NULL needs coordinates resident from qnb_build_lists / qnb_nonbond");
+    if (!xx && !h->x_from_nonbond)
+        return fail("qnb_shake: xx == NULL needs the coordinates of this step's qnb_nonbond resident on the device "
+                    "(qnb_build_lists, qnb_restore_lists and qnb_qcp_beads replace them)");
     CU(cudaSetDevice(h->device));
     const size_t n3 = 3 * (size_t)h->T.s.natom;
     // xx == NULL: the reference coordinates are the ones already resident from this step's qnb_nonbond / qnb_build_lists
@@ -1101,6 +1106,7 @@ int qnb_restore_lists(qnb_handle *h) {
     memcpy(h->hx, h->hx_saved.data(), n3 * sizeof(double));
     CU(cudaMemcpyAsync(h->x.p, h->hx, n3 * sizeof(double), cudaMemcpyHostToDevice, h->st));
     h->restoring = true;
+    h->x_from_nonbond = false;
     const int rc = build_device(h, h->hx_saved.data());
     h->restoring = false;
     if (rc) return 1;
@@ -1128,8 +1134,9 @@ int qnb_qcp_beads(qnb_handle *h, const double *x_save, int natq, const int32_t *
         a0[j] = atoms[j] - 1;
         for (int c = 0; c < 3; c++) base[3 * j + c] = x_save[3 * (size_t)a0[j] + c];
     }
-    DBuf<int> d_atoms;
-    DBuf<double> d_base, d_disp, d_eq;
+    h->x_from_nonbond = false;   // the last bead's displaced coordinates stay on the device
+    DBuf<int> &d_atoms = h->bead_atoms;
+    DBuf<double> &d_base = h->bead_base, &d_disp = h->bead_disp, &d_eq = h->bead_eq;
     if (upload(d_atoms, a0) || upload(d_base, base) || d_disp.ensure(3 * (size_t)natq * nbeads) || d_eq.ensure((size_t)h->nE * nbeads)) return 1;
     memcpy(h->hx, x_save, n3 * sizeof(double));
     for (int k = 0; k < s.nstates; k++) h->hlam[k] = lambda[k];
@@ -1147,7 +1154,6 @@ int qnb_qcp_beads(qnb_handle *h, const double *x_save, int natq, const int32_t *
     CU(cudaGetLastError());
     for (int b = 0; b < nbeads; b++)
         for (int k = 0; k < nEQ; k++) EQ_out[(size_t)b * nEQ + k] = eq[(size_t)b * h->nE + QNB_E_COUNT + k];
-    d_atoms.release(); d_base.release(); d_disp.release(); d_eq.release();
     return 0;
 }
 
@@ -1167,6 +1173,7 @@ int qnb_build_lists(qnb_handle *h, const double *x, double Rq, double Rcq2, doub
     const size_t n3 = 3 * (size_t)s.natom;
     memcpy(h->hx, x, n3 * sizeof(double));
     CU(cudaMemcpyAsync(h->x.p, h->hx, n3 * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    h->x_from_nonbond = false;
     if (build_device(h, x)) return 1;
     if (counts_out) {
         for (int k = 0; k < 8; k++) counts_out[k] = 0;
@@ -1202,6 +1209,7 @@ int qnb_nonbond(qnb_handle *h, const double *x, const double *lambda, int flags,
         if (k < QNB_E_COUNT) E_out[k] = e; else EQ_out[k - QNB_E_COUNT] = e;
     }
     for (int k = 0; k < kRstOut; k++) h->last_rst[k] = h->hout[n3 + (size_t)kESlots * h->nE + k];
+    h->x_from_nonbond = true;
     const auto t4 = clk::now();
     auto sec = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double>(b - a).count(); };
     h->t_stage_in = sec(t0, t1); h->t_issue = sec(t1, t2); h->t_wait = sec(t2, t3); h->t_add_out = sec(t3, t4);
@@ -1535,6 +1543,7 @@ int qnb_finalize(qnb_handle *h) {
     h->nch.release(); h->choff.release(); h->ucost.release(); h->cost_off.release(); h->wstart_w.release(); h->wstart_s.release(); h->wdesc.release(); h->wrow.release(); h->sdesc.release(); h->srow.release(); h->sspec.release(); h->x_saved.release(); h->lrf_saved.release(); h->wp_theta.release(); h->wp_shell_n.release(); h->wp_shell_list.release(); h->wp_shell_theta.release(); h->lrf_mom.release();
     h->shk_first.release(); h->shk_ij.release(); h->shk_d2.release(); h->shk_winv.release(); h->shk_x.release();
     h->shk_xx.release(); h->shk_iter.release();
+    h->bead_atoms.release(); h->bead_base.release(); h->bead_disp.release(); h->bead_eq.release();
     h->item_posf.release();
     h->upk.release(); h->pk_sw.release(); h->e_cnt.release(); h->e_off.release(); h->rec_i.release(); h->rec_f.release(); h->wT.release();
     h->pw12.release(); h->ljp.release(); h->pw0.release(); h->ww_pairs.release(); h->pp_pairs.release(); h->pw_pairs.release();

@@ -94,7 +94,7 @@ def test_fortran_interface_module_matches_header():
     assert fields == want
     # measurement hooks and debug exports are not part of the Fortran host's surface
     host_calls = [n for n in _declared() if not n.startswith(("qnb_bench_", "qnb_last_timing", "qnb_last_copy_bytes",
-                                                              "qnb_launch_count", "qnb_device_count"))]
+                                                              "qnb_launch_count"))]
     assert len(host_calls) >= 18
     for n in host_calls:
         assert re.search(rf"bind\(c,\s*name='{n}'\)", f90), f"no Fortran interface for {n}"
