@@ -162,9 +162,10 @@ struct qnb_handle {
     // round-2 row kernels (qnb_rows.cuh): per-step packed records, pair tables, flat energy lists
     DBuf<int> upk, pk_sw, e_cnt, e_off;
     DBuf<int4> rec_i;
-    DBuf<float4> rec_f, wT, pw12;
+    DBuf<float4> rec_f, wT, wown, pw12;
     DBuf<float2> ljp, pw0;
     DBuf<int2> ww_pairs, pp_pairs, pw_pairs;
+    DBuf<double2> wd;
     int n_ww_e = 0, n_pp_e = 0, n_pw_e = 0;
     int occ_wr = 0, occ_sr = 0;
     bool legacy_rows = false, pw_hlj = false;
@@ -504,7 +505,7 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
         h->pk_atom.ensure(D.natom + 4) || h->pk_ct.ensure(D.natom + 4) || h->pk_q.ensure(D.natom + 4) ||
         h->pk_qd.ensure(D.natom + 4) || h->px.ensure(D.natom + 4) || h->py.ensure(D.natom + 4) ||   // +4: the force kernels always fetch three sites
         h->pz.ensure(D.natom + 4) || h->upk.ensure(std::max(nu, 1)) || h->pk_sw.ensure(D.natom + 4) ||
-        h->rec_i.ensure(D.natom + 4) || h->rec_f.ensure(D.natom + 4) || h->wT.ensure(D.natom + 4) ||
+        h->rec_i.ensure(D.natom + 4) || h->rec_f.ensure(D.natom + 4) || h->wT.ensure(D.natom + 4) || h->wown.ensure(3 * (size_t)std::max(D.nwat, 1)) || h->wd.ensure(5 * (size_t)std::max(D.nwat, 1)) ||
         h->e_cnt.ensure(std::max(nu, 1) + D.ncgp_solute + 4) || h->e_off.ensure(std::max(nu, 1) + D.ncgp_solute + 8))
         return 1;
     // LRF: cgp_centers + lrf_update over every pair that falls in the LRF branch.  It needs the cell tables and the
@@ -615,10 +616,10 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
                    eo_pw, h->ww_pairs.p, h->pp_pairs.p, h->pw_pairs.p);
         if (h->nwchunk > 0)
             LAUNCH(h, k_chunk_fill, cdiv(nwat * 32, 256), 256, 0, D, nsol, nwat, 0, h->counts.p, h->row_off.p, h->rows.p, off_w,
-                   h->wdesc.p, h->wrow.p, h->pk_atom.p, (uint16_t *)nullptr);
+                   h->wdesc.p, h->wrow.p, h->pk_atom.p, (uint16_t *)nullptr, new_rows);
         if (h->nschunk > 0)
             LAUNCH(h, k_chunk_fill, cdiv(nsol * 32, 256), 256, 0, D, 0, nsol, kITile, h->counts.p, h->row_off.p, h->rows.p, off_s,
-                   h->sdesc.p, h->srow.p, h->pk_atom.p, h->sspec.p);
+                   h->sdesc.p, h->srow.p, h->pk_atom.p, h->sspec.p, false);
         // one resident wave per kernel, every warp an equal share of the estimated work
         const int occw = new_rows ? h->occ_wr : h->occ_w, occs = new_rows ? h->occ_sr : h->occ_s;
         const int min_chunks = new_rows ? 2 : 4;   // chunks per warp below which more blocks only add launch overhead
@@ -730,9 +731,9 @@ static void launch_step_kernel(qnb_handle *h, int k, cudaStream_t cs, int flags)
     switch (k) {
     case K_WATER: {
         if (!h->legacy_rows) {
-            if (spc) LAUNCH_ON(h, cs, k_water_rows<true>, h->wgrid, 128, 0, h->rowpar, D.ncgp_solute, h->upk.p, h->rec_i.p, h->rec_f.p, h->wT.p,
+            if (spc) LAUNCH_ON(h, cs, k_water_rows<true>, h->wgrid, 128, 0, h->rowpar, h->rec_i.p, h->rec_f.p, h->wT.p, h->wown.p,
                                h->pw0.p, h->pw12.p, h->wstart_w.p, h->wdesc.p, h->wrow.p, D.nat_solute, grad);
-            else LAUNCH_ON(h, cs, k_water_rows<false>, h->wgrid, 128, 0, h->rowpar, D.ncgp_solute, h->upk.p, h->rec_i.p, h->rec_f.p, h->wT.p,
+            else LAUNCH_ON(h, cs, k_water_rows<false>, h->wgrid, 128, 0, h->rowpar, h->rec_i.p, h->rec_f.p, h->wT.p, h->wown.p,
                            h->pw0.p, h->pw12.p, h->wstart_w.p, h->wdesc.p, h->wrow.p, D.nat_solute, grad);
             break;
         }
@@ -790,9 +791,9 @@ static void launch_step_kernel(qnb_handle *h, int k, cudaStream_t cs, int flags)
         const int n = h->n_ww_e + h->n_pp_e + h->n_pw_e;
         const int grid = std::max(1, std::min(cdiv(n, 128), 8 * h->nsm));
         if (pbc) LAUNCH_ON(h, cs, k_pair_energy<true>, grid, 128, 0, h->epar, h->n_ww_e, h->ww_pairs.p, h->n_pp_e, h->pp_pairs.p, h->n_pw_e,
-                           h->pw_pairs.p, h->px.p, h->py.p, h->pz.p, h->pk_qd.p, h->pk_ct.p, h->pk_sw.p, h->x.p, h->ljd.p, h->ljcode.p, E, nE);
+                           h->pw_pairs.p, h->px.p, h->py.p, h->pz.p, h->pk_qd.p, h->pk_ct.p, h->pk_sw.p, h->x.p, h->wd.p, h->ljd.p, h->ljcode.p, E, nE);
         else LAUNCH_ON(h, cs, k_pair_energy<false>, grid, 128, 0, h->epar, h->n_ww_e, h->ww_pairs.p, h->n_pp_e, h->pp_pairs.p, h->n_pw_e,
-                       h->pw_pairs.p, h->px.p, h->py.p, h->pz.p, h->pk_qd.p, h->pk_ct.p, h->pk_sw.p, h->x.p, h->ljd.p, h->ljcode.p, E, nE);
+                       h->pw_pairs.p, h->px.p, h->py.p, h->pz.p, h->pk_qd.p, h->pk_ct.p, h->pk_sw.p, h->x.p, h->wd.p, h->ljd.p, h->ljcode.p, E, nE);
         break;
     }
     case K_RST: {
@@ -823,7 +824,7 @@ static int issue_step(qnb_handle *h, int flags, bool out_cleared = false) {
     if (!out_cleared) CU(cudaMemsetAsync(h->out.p, 0, h->nout * sizeof(double), h->st));
     if ((flags & QNB_FLAG_MD) && h->npk > 0)
         LAUNCH(h, k_pack_step, cdiv(h->npk, 256), 256, 0, h->npk, h->fix, h->D.nat_solute, h->pk_atom.p, h->pk_sw.p, h->pk_q.p, h->pk_ct.p,
-               h->x.p, h->px.p, h->py.p, h->pz.p, h->rec_i.p, h->rec_f.p, h->wT.p);
+               h->x.p, h->px.p, h->py.p, h->pz.p, h->rec_i.p, h->rec_f.p, h->wT.p, h->wown.p, h->wd.p);
     CU(cudaEventRecord(h->ev_fork, h->st));
     bool used[kAux] = {};
     static const int kOrder[K_COUNT] = {K_RST, K_QSTATIC, K_SOLUTE, K_QATOM, K_QPARTNER, K_WATER, K_ENERGY, K_LRF};
@@ -1487,7 +1488,7 @@ int qnb_bench_kernels(qnb_handle *h, const double *lambda, int flags, int reps, 
     int n = 0;
     if (h->npk > 0)
         LAUNCH(h, k_pack_step, cdiv(h->npk, 256), 256, 0, h->npk, h->fix, h->D.nat_solute, h->pk_atom.p, h->pk_sw.p, h->pk_q.p, h->pk_ct.p,
-               h->x.p, h->px.p, h->py.p, h->pz.p, h->rec_i.p, h->rec_f.p, h->wT.p);
+               h->x.p, h->px.p, h->py.p, h->pz.p, h->rec_i.p, h->rec_f.p, h->wT.p, h->wown.p, h->wd.p);
     for (int k = 0; k < K_COUNT; k++) {
         if (!step_kernel_active(h, k, flags)) continue;
         if (n >= ms_cap) break;
@@ -1545,7 +1546,7 @@ int qnb_finalize(qnb_handle *h) {
     h->shk_xx.release(); h->shk_iter.release();
     h->bead_atoms.release(); h->bead_base.release(); h->bead_disp.release(); h->bead_eq.release();
     h->item_posf.release();
-    h->upk.release(); h->pk_sw.release(); h->e_cnt.release(); h->e_off.release(); h->rec_i.release(); h->rec_f.release(); h->wT.release();
+    h->upk.release(); h->pk_sw.release(); h->e_cnt.release(); h->e_off.release(); h->rec_i.release(); h->rec_f.release(); h->wT.release(); h->wown.release(); h->wd.release();
     h->pw12.release(); h->ljp.release(); h->pw0.release(); h->ww_pairs.release(); h->pp_pairs.release(); h->pw_pairs.release();
     h->item_pos.release(); h->src.release(); h->cell_unsorted.release(); h->item_nq.release(); h->src_off.release();
     if (h->hx) cudaFreeHost(h->hx);

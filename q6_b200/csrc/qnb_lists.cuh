@@ -380,7 +380,7 @@ __global__ void k_warp_starts(Dev D, int u0, int n, int tile_atoms, bool new_row
 __global__ void k_chunk_fill(Dev D, int u0, int n, int tile_atoms, const int *__restrict__ counts,
                              const int *__restrict__ row_off, const uint32_t *__restrict__ rows,
                              const int *__restrict__ choff, int2 *__restrict__ cdesc, uint32_t *__restrict__ crow,
-                             const int *__restrict__ pk_atom, uint16_t *__restrict__ cspec) {
+                             const int *__restrict__ pk_atom, uint16_t *__restrict__ cspec, bool mark_kind) {
     const int lane = threadIdx.x & 31;
     const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (k >= n) return;
@@ -394,7 +394,10 @@ __global__ void k_chunk_fill(Dev D, int u0, int n, int tile_atoms, const int *__
             const int m = seg == 0 ? na : nb;
             for (int b = 0; b < m; b += 32, c++) {
                 if (lane == 0) cdesc[c] = make_int2(k, seg | (tile << 8));
-                const uint32_t e = (b + lane < m) ? rows[base + b + lane] : 0xffffffffu;
+                uint32_t e = (b + lane < m) ? rows[base + b + lane] : 0xffffffffu;
+                // water rows of the pipelined kernel (k_water_rows): bit 30 of EVERY lane names the chunk's kind, so the
+                // gathers of a chunk can be issued from its entries alone; a padding lane is one whose id field is all ones
+                if (mark_kind) e = seg == 0 ? (e & ~kSpecialBit) : (e | kSpecialBit);
                 crow[(size_t)c * 32 + lane] = e;
                 if (cspec) {
                     // solute tiles: resolve the special pairs (exclusion lists, 1-4 neighbours, own group) of this

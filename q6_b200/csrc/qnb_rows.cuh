@@ -47,15 +47,16 @@ __device__ __forceinline__ f2 rsq2(f2 a) { return mk2(rsqrt_fast(a.x), rsqrt_fas
 // per packed atom, rewritten every step by k_pack_step
 //   rec_i = {P of the atom's unit switch atom (x,y,z), compact type}
 //   rec_f = {offset from that switch atom (x,y,z), charge}
-//   wT    = waters only, three float4 starting at the oxygen's packed index: hydrogen offsets from the oxygen, laid
-//           out as the packed operands of the water kernel:
-//           {t1x,t2x,t1y,t2y} {t1z,t2z,t2x,t1x} {t2y,t1y,t2z,t1z}
+//   wT    = waters only, three float4 starting at the oxygen's packed index: the oxygen's fixed-point position and the
+//           hydrogen offsets t1, t2 from it, laid out as the packed (f2) operands of the row kernels:
+//           {Px, Py, t1x, t2x} {Pz, 0, t1y, t2y} {t1z, t2z, 0, 0}        (Px, Py, Pz: int bits)
+//   own   = the same three float4 per water, indexed by water number (the own molecule of a water row)
 // and px/py/pz: FP64 coordinates in packed order (energy kernel)
 __global__ void __launch_bounds__(256)
 k_pack_step(int npk, FixFrame F, int nat_solute, const int *__restrict__ pk_atom, const int *__restrict__ pk_sw,
             const float *__restrict__ pk_q, const int *__restrict__ pk_ct, const double *__restrict__ x,
             double *__restrict__ px, double *__restrict__ py, double *__restrict__ pz, int4 *__restrict__ rec_i,
-            float4 *__restrict__ rec_f, float4 *__restrict__ wT) {
+            float4 *__restrict__ rec_f, float4 *__restrict__ wT, float4 *__restrict__ own, double2 *__restrict__ wd) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npk) return;
     const int i = pk_atom[p], sw = pk_sw[p];
@@ -63,15 +64,23 @@ k_pack_step(int npk, FixFrame F, int nat_solute, const int *__restrict__ pk_atom
     double xs = xi, ys = yi, zs = zi;
     if (sw != i) { xs = x[3 * sw]; ys = x[3 * sw + 1]; zs = x[3 * sw + 2]; }
     px[p] = xi; py[p] = yi; pz[p] = zi;
-    rec_i[p] = make_int4(fix_coord(xs, F.org[0], F.inv_period[0]), fix_coord(ys, F.org[1], F.inv_period[1]),
-                         fix_coord(zs, F.org[2], F.inv_period[2]), pk_ct[p]);
+    const int Px = fix_coord(xs, F.org[0], F.inv_period[0]), Py = fix_coord(ys, F.org[1], F.inv_period[1]),
+              Pz = fix_coord(zs, F.org[2], F.inv_period[2]);
+    rec_i[p] = make_int4(Px, Py, Pz, pk_ct[p]);
     rec_f[p] = make_float4((float)(xi - xs), (float)(yi - ys), (float)(zi - zs), pk_q[p]);
     if (i >= nat_solute && sw == i) {
         const float t1x = (float)(x[3 * i + 3] - xi), t1y = (float)(x[3 * i + 4] - yi), t1z = (float)(x[3 * i + 5] - zi);
         const float t2x = (float)(x[3 * i + 6] - xi), t2y = (float)(x[3 * i + 7] - yi), t2z = (float)(x[3 * i + 8] - zi);
-        wT[p] = make_float4(t1x, t2x, t1y, t2y);
-        wT[p + 1] = make_float4(t1z, t2z, t2x, t1x);
-        wT[p + 2] = make_float4(t2y, t1y, t2z, t1z);
+        const float4 a = make_float4(__int_as_float(Px), __int_as_float(Py), t1x, t2x);
+        const float4 b = make_float4(__int_as_float(Pz), 0.f, t1y, t2y);
+        const float4 c = make_float4(t1z, t2z, 0.f, 0.f);
+        wT[p] = a; wT[p + 1] = b; wT[p + 2] = c;
+        const int w = (i - nat_solute) / 3;
+        own[3 * w] = a; own[3 * w + 1] = b; own[3 * w + 2] = c;
+        // FP64 sites of the molecule, contiguous (energy kernel): {Ox,Oy} {Oz,H1x} {H1y,H1z} {H2x,H2y} {H2z,-}
+        double2 *o = wd + 5 * (size_t)w;
+        o[0] = make_double2(xi, yi); o[1] = make_double2(zi, x[3 * i + 3]); o[2] = make_double2(x[3 * i + 4], x[3 * i + 5]);
+        o[3] = make_double2(x[3 * i + 6], x[3 * i + 7]); o[4] = make_double2(x[3 * i + 8], 0.0);
     }
 }
 
@@ -107,94 +116,152 @@ __device__ __forceinline__ f2 len2(f2 dx, f2 dy, f2 dz) { return fma2(dx, dx, fm
 // ------------------------------------------------------------------------------------------------
 // Water rows, gradient only: ww (3x3 site tile, both sides of every pair) + the water side of pw.
 // One warp streams a contiguous range of 32-entry chunks (k_warp_starts); lanes = partners of the row's water.
+//
+// The partners' records are gathers (cell-ordered, so neighbouring lanes hit neighbouring records, but still one L1/L2
+// round trip per chunk): r02c measured 60 % of the stall samples on their first consumers at 20 warps per SM.  They
+// are therefore staged through shared memory with cp.async (LDGSTS), three chunks deep: every lane copies the records
+// of ITS partner of chunk c+2 into its own 48-byte slot while chunk c is computed, so no registers are held by loads
+// in flight and no lane ever reads another lane's slot (no barrier).  The own molecule's record of the next row
+// travels the same way (lanes 0-2, a ring of four slots).  Entries and chunk descriptors are plain coalesced loads, three ahead.
+constexpr uint32_t kKindBit = kSpecialBit;   // water-row chunk entries: set in every lane of a B chunk (k_chunk_fill)
+constexpr int kWStages = 3;
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 #ifndef QNB_WROWS_MINB
 #define QNB_WROWS_MINB 5
 #endif
 template <bool SPC>
 __global__ void __launch_bounds__(128, QNB_WROWS_MINB)
-k_water_rows(RowPar P, int nsol, const int *__restrict__ upk, const int4 *__restrict__ rec_i, const float4 *__restrict__ rec_f,
-             const float4 *__restrict__ wT, const float2 *__restrict__ pw0, const float4 *__restrict__ pw12,
+k_water_rows(RowPar P, const int4 *__restrict__ rec_i, const float4 *__restrict__ rec_f, const float4 *__restrict__ wT,
+             const float4 *__restrict__ own, const float2 *__restrict__ pw0, const float4 *__restrict__ pw12,
              const int *__restrict__ wstart, const int2 *__restrict__ cdesc, const uint32_t *__restrict__ crow,
              int i0_water /* nat_solute */, double *__restrict__ grad) {
-    const int lane = threadIdx.x & 31;
+    __shared__ float4 S[4][kWStages][3][32];   // [warp][stage][record part][lane]
+    __shared__ float4 Own[4][4][4];            // [warp][slot][record part]; the issue side runs at most three row changes ahead
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int c0 = wstart[gw], c1 = wstart[gw + 1];
     if (c0 >= c1) return;
     int cur_w = -1;
     int Pix = 0, Piy = 0, Piz = 0;
     f2 nSx = mk2(0, 0), nSy = nSx, nSz = nSx;                 // minus the own hydrogens' offsets {s1, s2}
-    f2 G12x = nSx, G12y = nSx, G12z = nSx, G0x = nSx, G0y = nSx, G0z = nSx;   // gradient of sites 1,2 / of site 0 (two halves)
+    f2 nWx = nSx, nWy = nSx, nWz = nSx;                       // the same, swapped: {s2, s1}
+    // gradient of the own sites {1,2}, {2,1} (from the swapped operands) and of site 0 (two halves + the O-O term)
+    f2 G12x = nSx, G12y = nSx, G12z = nSx, G21x = nSx, G21y = nSx, G21z = nSx, G0x = nSx, G0y = nSx, G0z = nSx;
     float g0x = 0.f, g0y = 0.f, g0z = 0.f;
     const int slot = split_slot<9, 16>(lane);
+    const f2 wQ2 = mk2(P.wQ[2].y, P.wQ[2].x), wA2 = mk2(P.wA12[2].y, P.wA12[2].x), wB2 = mk2(P.wB6[2].y, P.wB6[2].x);
 
     auto flush = [&]() {
         if (cur_w < 0) return;
         float s[9] = {g0x + (G0x.x + G0x.y), g0y + (G0y.x + G0y.y), g0z + (G0z.x + G0z.y),
-                      G12x.x, G12y.x, G12z.x, G12x.y, G12y.y, G12z.y};
+                      G12x.x + G21x.y, G12y.x + G21y.y, G12z.x + G21z.y, G12x.y + G21x.x, G12y.y + G21y.x, G12z.y + G21z.x};
         const float mine = split_reduce<9, 16>(s, lane);
         if (slot >= 0) atomicAdd(&grad[3 * (size_t)(i0_water + 3 * cur_w) + slot], (double)mine);
     };
-    int2 dn = cdesc[c0];
-    uint32_t en = crow[(size_t)c0 * 32 + lane];
+    const int *__restrict__ cunit = reinterpret_cast<const int *>(cdesc);
+    auto ld_e = [&](int c) -> uint32_t { return c < c1 ? crow[(size_t)c * 32 + lane] : 0xffffffffu; };
+    auto ld_u = [&](int c) -> int { return c < c1 ? cunit[2 * (size_t)c] : -1; };
+    int ipar = 0, cpar = 0;   // own-record slots: next to be filled / next to be read
+    // gathers of chunk cc (entry e, unit u; up = unit of the chunk before it) into stage st; always closes a group
+    auto issue = [&](int cc, uint32_t e, int u, int up, int st) {
+        if (cc < c1) {
+            const bool valid = (e & kIdMask) != kIdMask;
+            const int p = valid ? (int)(e & kIdMask) : 0;
+            float4 *dst = &S[wib][st][0][lane];
+            if (__ballot_sync(kFull, (e & kKindBit) != 0) == 0) {
+                const float4 *src = wT + p;
+                cp_async16(dst, src); cp_async16(dst + 32, src + 1); cp_async16(dst + 64, src + 2);
+            } else {
+                cp_async16(dst, rec_i + p); cp_async16(dst + 32, rec_f + p);
+            }
+            if (u != up) {
+                if (lane < 3) cp_async16(&Own[wib][ipar][lane], own + 3 * (size_t)u + lane);
+                ipar = (ipar + 1) & 3;
+            }
+        }
+        cp_async_commit();
+    };
+    uint32_t e0 = ld_e(c0), e1 = ld_e(c0 + 1), e2 = ld_e(c0 + 2), e3;
+    int u0 = ld_u(c0), u1 = ld_u(c0 + 1), u2 = ld_u(c0 + 2), u3;
+    issue(c0, e0, u0, -1, 0);
+    issue(c0 + 1, e1, u1, u0, 1);
+    int st_c = 0, st_i = 2;
     for (int c = c0; c < c1; c++) {
-        const int2 d = dn;
-        const uint32_t e = en;
-        if (c + 1 < c1) { dn = cdesc[c + 1]; en = crow[(size_t)(c + 1) * 32 + lane]; }
-        if (d.x != cur_w) {
+        e3 = ld_e(c + 3); u3 = ld_u(c + 3);
+        issue(c + 2, e2, u2, u1, st_i);
+        cp_async_wait<2>();
+        if (u0 != cur_w) {
             flush();
-            cur_w = d.x;
-            const int pi = upk[nsol + cur_w];
-            const int4 ri = rec_i[pi];
-            const float4 a = wT[pi], b = wT[pi + 1];
-            Pix = ri.x; Piy = ri.y; Piz = ri.z;
-            nSx = mk2(-a.x, -a.y); nSy = mk2(-a.z, -a.w); nSz = mk2(-b.x, -b.y);
-            G12x = G12y = G12z = G0x = G0y = G0z = mk2(0.f, 0.f);
+            cur_w = u0;
+            __syncwarp();   // lanes 0-2 have passed their wait: the own record is complete
+            const float4 a = Own[wib][cpar][0], b = Own[wib][cpar][1], cc = Own[wib][cpar][2];
+            __syncwarp();
+            cpar = (cpar + 1) & 3;
+            Pix = __float_as_int(a.x); Piy = __float_as_int(a.y); Piz = __float_as_int(b.x);
+            nSx = mk2(-a.z, -a.w); nSy = mk2(-b.z, -b.w); nSz = mk2(-cc.x, -cc.y);
+            nWx = mk2(-a.w, -a.z); nWy = mk2(-b.w, -b.z); nWz = mk2(-cc.y, -cc.x);
+            G12x = G12y = G12z = G21x = G21y = G21z = G0x = G0y = G0z = mk2(0.f, 0.f);
             g0x = g0y = g0z = 0.f;
         }
-        const bool valid = e != kPadEntry;
-        const int p = valid ? (int)(e & kIdMask) : 0;
-        const int4 rj = rec_i[p];
-        // vector from the own oxygen to the partner's switch atom; a padding lane is sent to 1e18 A, where every
-        // r^-3 and r^-6 below flushes to zero
-        float Rx = (float)(rj.x - Pix) * P.scale[0];
-        const float Ry = (float)(rj.y - Piy) * P.scale[1], Rz = (float)(rj.z - Piz) * P.scale[2];
-        Rx = valid ? Rx : 1.0e18f;
-        const f2 RRx = mk2(Rx, Rx), RRy = mk2(Ry, Ry), RRz = mk2(Rz, Rz);
-        if (d.y == kChunkA) {
-            const float4 ta = wT[p], tb = wT[p + 1], tc = wT[p + 2];
-            const f2 U12x = add2(RRx, mk2(ta.x, ta.y)), U12y = add2(RRy, mk2(ta.z, ta.w)), U12z = add2(RRz, mk2(tb.x, tb.y));
-            const f2 U21x = add2(RRx, mk2(tb.z, tb.w)), U21y = add2(RRy, mk2(tc.x, tc.y)), U21z = add2(RRz, mk2(tc.z, tc.w));
+        const uint32_t e = e0;
+        const bool valid = (e & kIdMask) != kIdMask;
+        const float4 r0 = S[wib][st_c][0][lane], r1 = S[wib][st_c][1][lane];
+        if (__ballot_sync(kFull, (e & kKindBit) != 0) == 0) {
+            const float4 r2 = S[wib][st_c][2][lane];
+            // vector from the own oxygen to the partner's; a padding lane is sent to 1e18 A, where every r^-3 and
+            // r^-6 below flushes to zero
+            float Rx = (float)(__float_as_int(r0.x) - Pix) * P.scale[0];
+            const float Ry = (float)(__float_as_int(r0.y) - Piy) * P.scale[1], Rz = (float)(__float_as_int(r1.x) - Piz) * P.scale[2];
+            Rx = valid ? Rx : 1.0e18f;
+            const f2 RRx = mk2(Rx, Rx), RRy = mk2(Ry, Ry), RRz = mk2(Rz, Rz);
+            // partner hydrogens {1, 2} seen from the own oxygen
+            const f2 Ux = add2(RRx, mk2(r0.z, r0.w)), Uy = add2(RRy, mk2(r1.z, r1.w)), Uz = add2(RRz, mk2(r2.x, r2.y));
             f2 dx, dy, dz, cc;
-            // (1,0) (2,0)
+            // own {1,2} - partner 0
             dx = add2(RRx, nSx); dy = add2(RRy, nSy); dz = add2(RRz, nSz);
             cc = SPC ? coul_c2(len2(dx, dy, dz), P.wQ[0]) : pair_c2(len2(dx, dy, dz), P.wQ[0], P.wA12[0], P.wB6[0]);
             G12x = fma2(dx, cc, G12x); G12y = fma2(dy, cc, G12y); G12z = fma2(dz, cc, G12z);
-            // (1,1) (2,2)
-            dx = add2(U12x, nSx); dy = add2(U12y, nSy); dz = add2(U12z, nSz);
+            // own {1,2} - partner {1,2}
+            dx = add2(Ux, nSx); dy = add2(Uy, nSy); dz = add2(Uz, nSz);
             cc = SPC ? coul_c2(len2(dx, dy, dz), P.wQ[1]) : pair_c2(len2(dx, dy, dz), P.wQ[1], P.wA12[1], P.wB6[1]);
             G12x = fma2(dx, cc, G12x); G12y = fma2(dy, cc, G12y); G12z = fma2(dz, cc, G12z);
-            // (1,2) (2,1)
-            dx = add2(U21x, nSx); dy = add2(U21y, nSy); dz = add2(U21z, nSz);
-            cc = SPC ? coul_c2(len2(dx, dy, dz), P.wQ[2]) : pair_c2(len2(dx, dy, dz), P.wQ[2], P.wA12[2], P.wB6[2]);
-            G12x = fma2(dx, cc, G12x); G12y = fma2(dy, cc, G12y); G12z = fma2(dz, cc, G12z);
-            // (0,1) (0,2)
-            cc = SPC ? coul_c2(len2(U12x, U12y, U12z), P.wQ[3]) : pair_c2(len2(U12x, U12y, U12z), P.wQ[3], P.wA12[3], P.wB6[3]);
-            G0x = fma2(U12x, cc, G0x); G0y = fma2(U12y, cc, G0y); G0z = fma2(U12z, cc, G0z);
+            // own {2,1} - partner {1,2}: the own offsets are swapped (once per row), not the partner's (once per chunk)
+            dx = add2(Ux, nWx); dy = add2(Uy, nWy); dz = add2(Uz, nWz);
+            cc = SPC ? coul_c2(len2(dx, dy, dz), wQ2) : pair_c2(len2(dx, dy, dz), wQ2, wA2, wB2);
+            G21x = fma2(dx, cc, G21x); G21y = fma2(dy, cc, G21y); G21z = fma2(dz, cc, G21z);
+            // own 0 - partner {1,2}
+            cc = SPC ? coul_c2(len2(Ux, Uy, Uz), P.wQ[3]) : pair_c2(len2(Ux, Uy, Uz), P.wQ[3], P.wA12[3], P.wB6[3]);
+            G0x = fma2(Ux, cc, G0x); G0y = fma2(Uy, cc, G0y); G0z = fma2(Uz, cc, G0z);
             // (0,0): the pair that carries LJ in nonbond_ww_spc
             const float c00 = pair_c(fmaf(Rx, Rx, fmaf(Ry, Ry, Rz * Rz)), P.q00, P.A00, P.B00);
             g0x = fmaf(Rx, c00, g0x); g0y = fmaf(Ry, c00, g0y); g0z = fmaf(Rz, c00, g0z);
         } else {
             // solute atom acting on the own water (pw seen from the water: gradient only)
-            const float4 oj = rec_f[p];
+            const int4 rj = make_int4(__float_as_int(r0.x), __float_as_int(r0.y), __float_as_int(r0.z), __float_as_int(r0.w));
+            const float4 oj = r1;
+            float Rx = (float)(rj.x - Pix) * P.scale[0];
+            const float Ry = (float)(rj.y - Piy) * P.scale[1], Rz = (float)(rj.z - Piz) * P.scale[2];
+            Rx = valid ? Rx : 1.0e18f;
             const float ex = Rx + oj.x, ey = Ry + oj.y, ez = Rz + oj.z;
             const float2 l0 = pw0[rj.w];
             const float4 l12 = pw12[rj.w];
             const f2 dx = add2(mk2(ex, ex), nSx), dy = add2(mk2(ey, ey), nSy), dz = add2(mk2(ez, ez), nSz);
             const f2 cc = pair_c2(len2(dx, dy, dz), mul2(P.wq12, mk2(oj.w, oj.w)), mk2(l12.x, l12.y), mk2(l12.z, l12.w));
             G12x = fma2(dx, cc, G12x); G12y = fma2(dy, cc, G12y); G12z = fma2(dz, cc, G12z);
-            const float c0 = pair_c(fmaf(ex, ex, fmaf(ey, ey, ez * ez)), P.wq0 * oj.w, l0.x, l0.y);
-            g0x = fmaf(ex, c0, g0x); g0y = fmaf(ey, c0, g0y); g0z = fmaf(ez, c0, g0z);
+            const float c0q = pair_c(fmaf(ex, ex, fmaf(ey, ey, ez * ez)), P.wq0 * oj.w, l0.x, l0.y);
+            g0x = fmaf(ex, c0q, g0x); g0y = fmaf(ey, c0q, g0y); g0z = fmaf(ez, c0q, g0z);
         }
+        e0 = e1; e1 = e2; e2 = e3;
+        u0 = u1; u1 = u2; u2 = u3;
+        st_c = st_c == kWStages - 1 ? 0 : st_c + 1;
+        st_i = st_i == kWStages - 1 ? 0 : st_i + 1;
     }
     flush();
 }
@@ -296,8 +363,8 @@ k_solute_rows(RowPar P, const int *__restrict__ upk, const int *__restrict__ nq_
             }
         } else {
             // ---- partner water: the three sites against every tile atom (nonbond_pw, solute side)
-            const float4 ta = wT[p], tb = wT[p + 1];
-            const float ux[3] = {Rx, Rx + ta.x, Rx + ta.y}, uy[3] = {Ry, Ry + ta.z, Ry + ta.w}, uz[3] = {Rz, Rz + tb.x, Rz + tb.y};
+            const float4 ta = wT[p], tb = wT[p + 1], tc = wT[p + 2];
+            const float ux[3] = {Rx, Rx + ta.z, Rx + ta.w}, uy[3] = {Ry, Ry + tb.z, Ry + tb.w}, uz[3] = {Rz, Rz + tc.x, Rz + tc.y};
             float2 l0[4];
             float4 l12[4];
 #pragma unroll
@@ -326,7 +393,7 @@ k_solute_rows(RowPar P, const int *__restrict__ upk, const int *__restrict__ nq_
 
 // ------------------------------------------------------------------------------------------------
 // Energies: one thread per listed pair (the reference's own list: each pair once), FP64.
-//   ww_pairs {pi, pj}: packed indices of the two oxygens                      (E%ww, nonbond_ww(_spc)(_box))
+//   ww_pairs {wi, wj}: water numbers (0-based) of the two molecules            (E%ww, nonbond_ww(_spc)(_box))
 //   pp_pairs {pi, pj | img << 24 | 1-4 << 30 | skip << 31}: packed atoms      (E%pp, nonbond_pp(_box))
 //   pw_pairs {pi, pj | img << 24}: packed solute atom, packed water oxygen    (E%pw, nonbond_pw(_box))
 // 1/r: MUFU.RSQ64H seed y0 (relative error e ~ 2^-21) and one Newton step, y = y0 (3/2 - r2 y0^2 / 2), error 3/2 e^2.
@@ -360,8 +427,8 @@ __global__ void __launch_bounds__(128)
 k_pair_energy(EnergyPar P, int n_ww, const int2 *__restrict__ ww_pairs, int n_pp, const int2 *__restrict__ pp_pairs,
               int n_pw, const int2 *__restrict__ pw_pairs, const double *__restrict__ px, const double *__restrict__ py,
               const double *__restrict__ pz, const double *__restrict__ pk_qd, const int *__restrict__ pk_ct,
-              const int *__restrict__ pk_sw, const double *__restrict__ x, const double *__restrict__ ljd,
-              const uint8_t *__restrict__ ljcode, double *__restrict__ Eslots, int nE) {
+              const int *__restrict__ pk_sw, const double *__restrict__ x, const double2 *__restrict__ wd,
+              const double *__restrict__ ljd, const uint8_t *__restrict__ ljcode, double *__restrict__ Eslots, int nE) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
     double e_ww_el = 0.0, e_ww_vdw = 0.0, e_pp_el = 0.0, e_pp_vdw = 0.0, e_pw_el = 0.0, e_pw_vdw = 0.0;
     // ---- water-water
@@ -373,16 +440,21 @@ k_pair_energy(EnergyPar P, int n_ww, const int2 *__restrict__ ww_pairs, int n_pp
         for (int t = tid; t < n_ww; t += nthr) {
             const int2 pr = ww_pairs[t];
             double xi[3][3], xj[3][3];
-#pragma unroll
-            for (int a = 0; a < 3; a++) {
-                xi[a][0] = px[pr.x + a]; xi[a][1] = py[pr.x + a]; xi[a][2] = pz[pr.x + a];
-                xj[a][0] = px[pr.y + a]; xj[a][1] = py[pr.y + a]; xj[a][2] = pz[pr.y + a];
+            {
+                const double2 *wi = wd + 5 * (size_t)pr.x, *wj = wd + 5 * (size_t)pr.y;
+                const double2 a0 = wi[0], a1 = wi[1], a2 = wi[2], a3 = wi[3], a4 = wi[4];
+                const double2 b0 = wj[0], b1 = wj[1], b2 = wj[2], b3 = wj[3], b4 = wj[4];
+                xi[0][0] = a0.x; xi[0][1] = a0.y; xi[0][2] = a1.x; xi[1][0] = a1.y; xi[1][1] = a2.x; xi[1][2] = a2.y;
+                xi[2][0] = a3.x; xi[2][1] = a3.y; xi[2][2] = a4.x;
+                xj[0][0] = b0.x; xj[0][1] = b0.y; xj[0][2] = b1.x; xj[1][0] = b1.y; xj[1][1] = b2.x; xj[1][2] = b2.y;
+                xj[2][0] = b3.x; xj[2][1] = b3.y; xj[2][2] = b4.x;
             }
             if (PBC) {
-                // one shift per molecule pair from the O-O vector (nonbond_ww_spc_box L6016-6017, nonbond_ww_box)
+                // one shift per molecule pair from the O-O vector (nonbond_ww_spc_box L6016-6017, nonbond_ww_box); rint
+                // instead of nint: they differ only for a pair exactly half a box apart, which no list holds
 #pragma unroll
                 for (int k = 0; k < 3; k++) {
-                    const double sh = pshift(xi[0][k] - xj[0][k], P.box[k], P.inv_box[k]);
+                    const double sh = P.box[k] * rint((xi[0][k] - xj[0][k]) * P.inv_box[k]);
                     xj[0][k] += sh; xj[1][k] += sh; xj[2][k] += sh;
                 }
             }
@@ -508,7 +580,8 @@ k_energy_fill(Dev D, const int *__restrict__ counts, const int *__restrict__ row
     const int pi0 = upk[u];
     if (u >= D.ncgp_solute) {
         int2 *dst = ww_pairs + off_ww[u - D.ncgp_solute];
-        for (int k = lane; k < own; k += 32) dst[k] = make_int2(pi0, (int)(r[k] & kIdMask));
+        for (int k = lane; k < own; k += 32)
+            dst[k] = make_int2(u - D.ncgp_solute, (pk_atom[r[k] & kIdMask] - D.nat_solute) / 3);
         return;
     }
     const int nq = D.nq_off[u + 1] - D.nq_off[u];
