@@ -263,6 +263,17 @@ int qnb_build_lists(qnb_handle *h, const double *x, double Rq, double Rcq2, doub
 int qnb_nonbond(qnb_handle *h, const double *x, const double *lambda, int flags, double *d,
                 double *E_out, double *EQ_out);
 
+/*
+ * Several independent systems of one process -- FEP lambda windows (tests/exclude_tests/run_excl_test.sh:92-125 runs 51
+ * of them as separate Qdyn6 jobs), EVB frames, replicas -- advanced together on one GPU: the same calls as
+ * make_pair_lists / pot_energy_nonbonds for every system k = 0..n-1 (its own handle, coordinates, lambda, gradient and
+ * energy arrays), issued so that the device works on all of them at once.  Results are those of n single calls.
+ */
+int qnb_build_lists_batch(int n, qnb_handle *const *h, const double *const *x, double Rq, double Rcq2, double RcLRF2,
+                          double Rcpp2, double Rcpw2, double Rcww2, double RcLRF, int64_t *counts_out /* [n][8] or NULL */);
+int qnb_nonbond_batch(int n, qnb_handle *const *h, const double *const *x, const double *const *lambda, int flags,
+                      double *const *d, double *const *E_out, double *const *EQ_out);
+
 /* Number of entries of a list as the reference would hold it (per state for Q lists). */
 int qnb_list_count(qnb_handle *h, int which, int state /*1-based, Q lists*/, int64_t *n);
 /*
@@ -286,6 +297,9 @@ int qnb_comm_init(qnb_handle *h, int rank, int nranks, const void *id128);
  * ms_out = CUDA-event time of the whole loop on the handle's stream. */
 int qnb_bench_nonbond(qnb_handle *h, const double *lambda, int flags, int steps, int flush_l2, float *ms_out);
 int qnb_bench_build_lists(qnb_handle *h, int reps, float *ms_out);
+/* Parts of the builds timed by the last qnb_bench_build_lists, ms per build (CUDA events on the streams the kernels
+ * run on): LRF accumulation (lrf_update, on its side stream), row scan count pass, row scan fill pass. */
+int qnb_bench_last_build_timing(qnb_handle *h, float out[3]);
 /* md_run's loop on device-resident coordinates: a list rebuild every nbcycle steps (md.f90:1661) plus one
  * nonbonded evaluation per step; ms_out = CUDA-event time of the loop. */
 int qnb_bench_md(qnb_handle *h, const double *lambda, int flags, int steps, int nbcycle, float *ms_out);
@@ -296,6 +310,8 @@ int qnb_bench_peak(int device, int which, float *tflops_out);
  * names_out: '\n'-separated list; returns number of kernels. */
 int qnb_bench_kernels(qnb_handle *h, const double *lambda, int flags, int reps, int flush_l2,
                       char *names_out, int names_cap, float *ms_out, int ms_cap);
+/* ms per all-reduce of [d | E | EQ] alone (sharded handles; the collective that replaces gather_nonbond). */
+int qnb_bench_allreduce(qnb_handle *h, int reps, float *ms_out);
 /* Kernel launches issued by this handle since creation. */
 int64_t qnb_launch_count(qnb_handle *h);
 /* Host-side seconds of the last qnb_nonbond: staging x into pinned memory, issuing the step (graph launch),

@@ -135,6 +135,24 @@ interface
         real(c_double), intent(out) :: E_out(7), EQ_out(*) ! 6*nstates
         integer(c_int) :: rc
     end function
+    ! several independent systems of one process (lambda windows of a FEP farm, EVB frames) advanced together on one
+    ! GPU: arrays of n handles / c_loc addresses, one entry per system; results are those of n single calls
+    function qnb_build_lists_batch(n, handles, x, Rq, Rcq2, RcLRF2, Rcpp2, Rcpw2, Rcww2, RcLRF, counts) &
+            bind(c, name='qnb_build_lists_batch') result(rc)
+        import :: c_int, c_ptr, c_double
+        integer(c_int), value :: n
+        type(c_ptr), intent(in) :: handles(*), x(*)       ! x(k) = c_loc of system k's coordinates
+        real(c_double), value :: Rq, Rcq2, RcLRF2, Rcpp2, Rcpw2, Rcww2, RcLRF
+        type(c_ptr), value :: counts                      ! c_null_ptr or int64(8, n)
+        integer(c_int) :: rc
+    end function
+    function qnb_nonbond_batch(n, handles, x, lambda, flags, d, E_out, EQ_out) bind(c, name='qnb_nonbond_batch') result(rc)
+        import :: c_int, c_ptr
+        integer(c_int), value :: n
+        type(c_ptr), intent(in) :: handles(*), x(*), lambda(*), d(*), E_out(*), EQ_out(*)   ! c_loc addresses per system
+        integer(c_int), value :: flags
+        integer(c_int) :: rc
+    end function
     ! list sizes / explicit lists as the reference holds them (-DDUMP logging, debugging, nbmonitor-style analysis)
     function qnb_list_count(handle, which, state, n) bind(c, name='qnb_list_count') result(rc)
         import :: c_int, c_ptr, c_int64_t

@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/qnb.h"
@@ -103,6 +104,9 @@ struct qnb_handle {
     Dev D{};
     cudaStream_t st = nullptr, aux[kAux] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_pack = nullptr, ev_join[kAux] = {};
+    cudaEvent_t ev_bt[6] = {};   // qnb_bench_build_lists: LRF kernels (0,1), row count pass (2,3), row fill pass (4,5)
+    bool time_build = false;
+    float build_ms[3] = {0, 0, 0};   // of the last timed build: LRF accumulation, row count pass, row fill pass
     cudaGraphExec_t graph[2][16] = {};   // [with copies][graph_index(flags)]
     bool use_graph = true, multi_stream = true;
     int water_blocks = 0, solute_blocks = 0;   // blocks per SM of the two persistent kernels (0: what the occupancy allows)
@@ -133,7 +137,7 @@ struct qnb_handle {
         qp_shift_atom;
     DBuf<uint32_t> rows;
     DBuf<double4> item_pos, src;
-    DBuf<float4> item_posf;
+    DBuf<float4> item_posf, item_scr;
     DBuf<int> cell_unsorted, item_nq, src_off, pk_atom, pk_ct;
     DBuf<float> pk_q;
     DBuf<double> pk_qd, px, py, pz;
@@ -167,7 +171,7 @@ struct qnb_handle {
     DBuf<int2> ww_pairs, pp_pairs, pw_pairs;
     DBuf<double2> wd;
     int n_ww_e = 0, n_pp_e = 0, n_pw_e = 0;
-    int occ_wr = 0, occ_sr = 0;
+    int occ_wr = 0, occ_sr = 0, wrows_minb = 5;
     bool legacy_rows = false, pw_hlj = false;
     RowPar rowpar{};
     EnergyPar epar{};
@@ -245,9 +249,10 @@ static int init_device(qnb_handle *h) {
     D.any_atom = s.iuse_switch_atom != 1;
     D.sharded = !(s.pp_start <= 1 && s.pp_end >= s.ncgp_solute && s.pw_start <= 1 && s.pw_end >= s.ncgp_solute &&
                   s.ww_start <= 1 && s.ww_end >= s.nwat);
-    // QNB_SHARD_ROWS=1: row partition (row_in_shard; shards the candidate scan as well).  Written after the round-1 GPU
-    // budget was spent, so the verified pair partition stays the default until the multi-GPU tests have run with it.
-    D.shard_rows = getenv("QNB_SHARD_ROWS") ? 1 : 0;
+    // Sharded builds partition ROWS (row_in_shard; shards the candidate scan as well as the pairs: r02d, 2 x B200, list
+    // build 3.54 -> 2.39 ms, step 0.220 -> 0.174 ms against the pair partition).  QNB_SHARD_PAIRS=1 selects the reference's
+    // pair partition (every rank holds exactly the pairs of its calculation_assignment ranges).
+    D.shard_rows = getenv("QNB_SHARD_PAIRS") ? 0 : 1;
     D.el14 = s.el14_scale; D.el14f = (float)s.el14_scale;
     for (int d = 0; d < 3; d++) D.xpcent[d] = s.xpcent[d];
     D.pp_s = s.pp_start; D.pp_e = s.pp_end; D.pw_s = s.pw_start; D.pw_e = s.pw_end; D.qp_s = s.qp_start; D.qp_e = s.qp_end;
@@ -305,6 +310,7 @@ static int init_device(qnb_handle *h) {
     // ---- round-2 row kernels (qnb_rows.cuh): type-pair tables with the combination rule resolved, {12 A, 6 B} in FP32
     {
         const int nct = T.nct;
+        if (nct > 255) return fail("qnb_init: %d atom types in use; the packed records hold the compact type in 8 bits", nct);
         std::vector<float2> ljp((size_t)2 * nct * nct), pw0((size_t)std::max(nct, 1));
         std::vector<float4> pw12((size_t)std::max(nct, 1));
         for (int a = 0; a < nct; a++)
@@ -384,6 +390,7 @@ static int init_device(qnb_handle *h) {
     CU(cudaEventCreateWithFlags(&h->ev_pack, cudaEventDisableTiming));
     CU(cudaEventCreate(&h->ev0));
     CU(cudaEventCreate(&h->ev1));
+    for (int k = 0; k < 6; k++) CU(cudaEventCreate(&h->ev_bt[k]));
     if (const char *e = getenv("QNB_NO_GRAPH")) h->use_graph = !(e[0] == '1');
     if (const char *e = getenv("QNB_ONE_STREAM")) h->multi_stream = !(e[0] == '1');
     if (const char *e = getenv("QNB_WATER_BLOCKS")) h->water_blocks = std::max(0, atoi(e));
@@ -499,13 +506,13 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
         h->row_off.ensure(std::max(nu, 1) + 2) ||
         h->flag.ensure(std::max({D.natom, D.nwat, 1}) + 1) || h->pos.ensure(std::max({D.natom, D.nwat, 1}) + 2) ||
         h->qp_list.ensure(std::max(D.nat_solute, 1)) || h->qw_list.ensure(std::max(D.nwat, 1)) ||
-        h->qp_shift_atom.ensure(std::max(D.ncgp_solute, 1)) || h->item_pos.ensure(std::max(nu, 1)) || h->item_posf.ensure(std::max(nu, 1)) ||
+        h->qp_shift_atom.ensure(std::max(D.ncgp_solute, 1)) || h->item_pos.ensure(std::max(nu, 1)) || h->item_posf.ensure(std::max(nu, 1)) || h->item_scr.ensure(std::max(nu, 1)) ||
         h->src.ensure(std::max(D.natom, 1)) || h->cell_unsorted.ensure(std::max(nu, 1)) ||
         h->item_nq.ensure(std::max(nu, 1) + 1) || h->src_off.ensure(std::max(nu, 1) + 2) ||
         h->pk_atom.ensure(D.natom + 4) || h->pk_ct.ensure(D.natom + 4) || h->pk_q.ensure(D.natom + 4) ||
         h->pk_qd.ensure(D.natom + 4) || h->px.ensure(D.natom + 4) || h->py.ensure(D.natom + 4) ||   // +4: the force kernels always fetch three sites
         h->pz.ensure(D.natom + 4) || h->upk.ensure(std::max(nu, 1)) || h->pk_sw.ensure(D.natom + 4) ||
-        h->rec_i.ensure(D.natom + 4) || h->rec_f.ensure(D.natom + 4) || h->wT.ensure(D.natom + 4) || h->wown.ensure(3 * (size_t)std::max(D.nwat, 1)) || h->wd.ensure(5 * (size_t)std::max(D.nwat, 1)) ||
+        h->rec_i.ensure(D.natom + 4) || h->rec_f.ensure(D.natom + 4) || h->wT.ensure(D.natom + 4) || h->wown.ensure(3 * (size_t)std::max(D.nwat, 1)) || h->wd.ensure(2 * (size_t)(D.natom + 4)) ||
         h->e_cnt.ensure(std::max(nu, 1) + D.ncgp_solute + 4) || h->e_off.ensure(std::max(nu, 1) + D.ncgp_solute + 8))
         return 1;
     // LRF: cgp_centers + lrf_update over every pair that falls in the LRF branch.  It needs the cell tables and the
@@ -520,6 +527,7 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
             cudaEventRecord(h->ev_fork, h->st);
             cudaStreamWaitEvent(ls, h->ev_fork, 0);
         }
+        if (h->time_build) cudaEventRecord(h->ev_bt[0], ls);
         LAUNCH_ON(h, ls, k_cgp_centers, cdiv(D.ncgp, 128), 128, 0, D, h->x.p, h->lrf.p);
         if (nu > 0) {
             LAUNCH_ON(h, ls, k_pack_sources, cdiv(D.natom, 256), 256, 0, h->src_off.p + nu, h->pk_atom.p, h->x.p, h->crg.p, h->src.p);
@@ -554,6 +562,7 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
             else { if (general) LRFCASE(false, false, true); else LRFCASE(false, false, false); }
 #undef LRFCASE
         }
+        if (h->time_build) cudaEventRecord(h->ev_bt[1], ls);
         if (h->multi_stream) { cudaEventRecord(h->ev_join[kLrfStream], ls); lrf_forked = true; }
     };
     const bool md_lists = true;
@@ -564,12 +573,20 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
         CU(cudaMemsetAsync(h->cell_count.p, 0, sizeof(int) * (G.ncell + 1), h->st));
         LAUNCH(h, k_cell_fill, cdiv(nu, 256), 256, 0, nu, h->cell_of.p, h->cell_start.p, h->cell_count.p, h->cell_unsorted.p);
         LAUNCH(h, k_cell_sort, G.ncell, 64, 0, G.ncell, h->cell_start.p, h->cell_unsorted.p, h->cell_items.p);
-        LAUNCH(h, k_pack_items, cdiv(nu, 256), 256, 0, D, h->upos.p, h->cell_items.p, h->item_pos.p, h->item_posf.p, h->item_nq.p);
+        LAUNCH(h, k_pack_items, cdiv(nu, 256), 256, 0, D, h->upos.p, h->cell_items.p, h->item_pos.p, h->item_posf.p, h->item_scr.p, h->item_nq.p);
         run_exclusive_scan(h, h->item_nq.p, h->src_off.p, nu);
         LAUNCH(h, k_pack_atoms, cdiv(nu, 128), 128, 0, D, h->cell_items.p, h->src_off.p, h->pk_atom.p, h->pk_q.p, h->pk_qd.p, h->pk_ct.p, h->pk_sw.p, h->upk.p);
         launch_lrf();
-        LAUNCH(h, k_build_rows<false>, cdiv(nu * 32, 256), 256, 0, D, h->cut, G, h->list_reach, h->x.p, h->upos.p, h->cell_of.p, h->cell_start.p,
-               h->item_pos.p, h->src_off.p, h->counts.p, (const int *)nullptr, (uint32_t *)nullptr);
+        // QNB_OLD_ROWS=1: the round-1 builder (one cell-row segment per step), kept for comparison
+        static const bool old_rows = getenv("QNB_OLD_ROWS") != nullptr;
+        if (h->time_build) cudaEventRecord(h->ev_bt[2], h->st);
+        if (old_rows)
+            LAUNCH(h, k_build_rows<false>, cdiv(nu * 32, 256), 256, 0, D, h->cut, G, h->list_reach, h->x.p, h->upos.p, h->cell_of.p, h->cell_start.p,
+                   h->item_pos.p, h->src_off.p, h->counts.p, (const int *)nullptr, (uint32_t *)nullptr);
+        else
+            LAUNCH(h, k_rows_scan<false>, cdiv(nu, kRowScanWarps), 32 * kRowScanWarps, 0, D, h->cut, G, h->list_reach, h->x.p, h->upos.p, h->cell_of.p,
+                   h->cell_start.p, h->item_pos.p, h->item_scr.p, h->src_off.p, h->counts.p, (const int *)nullptr, (uint32_t *)nullptr);
+        if (h->time_build) cudaEventRecord(h->ev_bt[3], h->st);
         LAUNCH(h, k_row_totals, cdiv(nu, 256), 256, 0, nu, h->counts.p, h->row_tot.p);
         // chunk tables of the streaming force kernels and flat pair lists of the energy kernel: counts now, contents after
         // the rows are filled; all eight prefix sums in one launch
@@ -609,8 +626,14 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
             h->srow.ensure((size_t)std::max(h->nschunk, 1) * 32) || h->sspec.ensure((size_t)std::max(h->nschunk, 1) * 32) ||
             h->ww_pairs.ensure(std::max(h->n_ww_e, 1)) || h->pp_pairs.ensure(std::max(h->n_pp_e, 1)) || h->pw_pairs.ensure(std::max(h->n_pw_e, 1)))
             return 1;
-        LAUNCH(h, k_build_rows<true>, cdiv(nu * 32, 256), 256, 0, D, h->cut, G, h->list_reach, h->x.p, h->upos.p, h->cell_of.p, h->cell_start.p,
-               h->item_pos.p, h->src_off.p, h->counts.p, h->row_off.p, h->rows.p);
+        if (h->time_build) cudaEventRecord(h->ev_bt[4], h->st);
+        if (old_rows)
+            LAUNCH(h, k_build_rows<true>, cdiv(nu * 32, 256), 256, 0, D, h->cut, G, h->list_reach, h->x.p, h->upos.p, h->cell_of.p, h->cell_start.p,
+                   h->item_pos.p, h->src_off.p, h->counts.p, h->row_off.p, h->rows.p);
+        else
+            LAUNCH(h, k_rows_scan<true>, cdiv(nu, kRowScanWarps), 32 * kRowScanWarps, 0, D, h->cut, G, h->list_reach, h->x.p, h->upos.p, h->cell_of.p,
+                   h->cell_start.p, h->item_pos.p, h->item_scr.p, h->src_off.p, h->counts.p, h->row_off.p, h->rows.p);
+        if (h->time_build) cudaEventRecord(h->ev_bt[5], h->st);
         if (h->n_ww_e + h->n_pp_e + h->n_pw_e > 0)
             LAUNCH(h, k_energy_fill, cdiv(nu * 32, 256), 256, 0, D, h->counts.p, h->row_off.p, h->rows.p, h->upk.p, h->pk_atom.p, eo_ww, eo_pp,
                    eo_pw, h->ww_pairs.p, h->pp_pairs.p, h->pw_pairs.p);
@@ -713,8 +736,17 @@ static void query_occupancy(qnb_handle *h) {
     if (pbc) { if (geom) SOCC(true, true); else SOCC(true, false); }
     else { if (geom) SOCC(false, true); else SOCC(false, false); }
 #undef SOCC
-    if (spc) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_wr, k_water_rows<true>, 128, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_wr, k_water_rows<false>, 128, 0);
+    if (const char *e = getenv("QNB_WROWS_MINB")) h->wrows_minb = std::min(6, std::max(4, atoi(e)));
+    if (h->wrows_minb == 4) {
+        if (spc) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_wr, k_water_rows<true, 4>, 128, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_wr, k_water_rows<false, 4>, 128, 0);
+    } else if (h->wrows_minb == 5) {
+        if (spc) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_wr, k_water_rows<true, 5>, 128, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_wr, k_water_rows<false, 5>, 128, 0);
+    } else {
+        if (spc) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_wr, k_water_rows<true, 6>, 128, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_wr, k_water_rows<false, 6>, 128, 0);
+    }
     if (h->pw_hlj) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_sr, k_solute_rows<true>, 128, 0);
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_sr, k_solute_rows<false>, 128, 0);
     cudaGetLastError();
@@ -731,10 +763,12 @@ static void launch_step_kernel(qnb_handle *h, int k, cudaStream_t cs, int flags)
     switch (k) {
     case K_WATER: {
         if (!h->legacy_rows) {
-            if (spc) LAUNCH_ON(h, cs, k_water_rows<true>, h->wgrid, 128, 0, h->rowpar, h->rec_i.p, h->rec_f.p, h->wT.p, h->wown.p,
-                               h->pw0.p, h->pw12.p, h->wstart_w.p, h->wdesc.p, h->wrow.p, D.nat_solute, grad);
-            else LAUNCH_ON(h, cs, k_water_rows<false>, h->wgrid, 128, 0, h->rowpar, h->rec_i.p, h->rec_f.p, h->wT.p, h->wown.p,
-                           h->pw0.p, h->pw12.p, h->wstart_w.p, h->wdesc.p, h->wrow.p, D.nat_solute, grad);
+#define WROWS(S, M) LAUNCH_ON(h, cs, (k_water_rows<S, M>), h->wgrid, 128, 0, h->rowpar, h->rec_i.p, h->rec_f.p, h->wT.p, h->wown.p, \
+                              h->pw0.p, h->pw12.p, h->wstart_w.p, h->wdesc.p, h->wrow.p, D.nat_solute, grad)
+            if (h->wrows_minb == 4) { if (spc) WROWS(true, 4); else WROWS(false, 4); }
+            else if (h->wrows_minb == 5) { if (spc) WROWS(true, 5); else WROWS(false, 5); }
+            else { if (spc) WROWS(true, 6); else WROWS(false, 6); }
+#undef WROWS
             break;
         }
 #define WCASE(P, S, G)                                                                                                             \
@@ -1184,9 +1218,31 @@ int qnb_build_lists(qnb_handle *h, const double *x, double Rq, double Rcq2, doub
     return 0;
 }
 
-int qnb_nonbond(qnb_handle *h, const double *x, const double *lambda, int flags, double *d, double *E_out, double *EQ_out) {
-    if (!h || !x || !lambda || !d || !E_out || !EQ_out) return fail("qnb_nonbond: null argument");
-    if (!h->lists_built) return fail("qnb_nonbond: pair lists have not been built (call qnb_build_lists)");
+// make_pair_lists of several independent systems: every build has host round trips for its sizes, so each runs on its
+// own host thread (the handles own their streams; graph capture is thread-local) and the builds overlap on the device.
+int qnb_build_lists_batch(int n, qnb_handle *const *hs, const double *const *x, double Rq, double Rcq2, double RcLRF2, double Rcpp2,
+                          double Rcpw2, double Rcww2, double RcLRF, int64_t *counts_out /* [n][8] or NULL */) {
+    if (n < 0 || (n > 0 && (!hs || !x))) return fail("qnb_build_lists_batch: null argument");
+    for (int k = 0; k < n; k++) {
+        if (!hs[k] || !x[k]) return fail("qnb_build_lists_batch: null argument for system %d", k);
+        for (int j = 0; j < k; j++) if (hs[j] == hs[k]) return fail("qnb_build_lists_batch: handle %d given twice", k);
+    }
+    std::vector<int> rc(n, 0);
+    std::vector<std::string> err(n);
+    auto work = [&](int k) {
+        rc[k] = qnb_build_lists(hs[k], x[k], Rq, Rcq2, RcLRF2, Rcpp2, Rcpw2, Rcww2, RcLRF, counts_out ? counts_out + 8 * (size_t)k : nullptr);
+        if (rc[k]) err[k] = g_err;
+    };
+    std::vector<std::thread> th;
+    for (int k = 1; k < n; k++) th.emplace_back(work, k);
+    if (n > 0) work(0);
+    for (auto &t : th) t.join();
+    for (int k = 0; k < n; k++) if (rc[k]) return fail("qnb_build_lists_batch: system %d: %s", k, err[k].c_str());
+    return 0;
+}
+
+// qnb_nonbond in two halves, so that several handles can be in flight at once (qnb_nonbond_batch)
+static int nonbond_begin(qnb_handle *h, const double *x, const double *lambda, int flags) {
     CU(cudaSetDevice(h->device));
     const qnb_system &s = h->T.s;
     const size_t n3 = 3 * (size_t)s.natom;
@@ -1196,14 +1252,20 @@ int qnb_nonbond(qnb_handle *h, const double *x, const double *lambda, int flags,
     for (int k = 0; k < s.nstates; k++) h->hlam[k] = lambda[k];
     h->last_flags = flags;
     const auto t1 = clk::now();
-    if (step_device(h, flags, true)) return 1;
-    const auto t2 = clk::now();
+    const int rc = step_device(h, flags, true);
+    h->t_stage_in = std::chrono::duration<double>(t1 - t0).count();
+    h->t_issue = std::chrono::duration<double>(clk::now() - t1).count();
+    return rc;
+}
+static int nonbond_end(qnb_handle *h, double *d, double *E_out, double *EQ_out) {
+    const qnb_system &s = h->T.s;
+    const size_t n3 = 3 * (size_t)s.natom;
     CU(cudaStreamSynchronize(h->st));
     CU(cudaGetLastError());
-    const auto t3 = clk::now();
     h->last_h2d = (int64_t)((n3 + s.nstates) * sizeof(double));
     h->last_d2h = (int64_t)(h->nout * sizeof(double));
-    for (size_t k = 0; k < n3; k++) d[k] += h->hout[k];
+    const double *__restrict__ g = h->hout;
+    for (size_t k = 0; k < n3; k++) d[k] += g[k];
     for (int k = 0; k < h->nE; k++) {
         double e = 0;   // fixed-order sum of the partial accumulators
         for (int sl = 0; sl < kESlots; sl++) e += h->hout[n3 + (size_t)sl * h->nE + k];
@@ -1211,10 +1273,45 @@ int qnb_nonbond(qnb_handle *h, const double *x, const double *lambda, int flags,
     }
     for (int k = 0; k < kRstOut; k++) h->last_rst[k] = h->hout[n3 + (size_t)kESlots * h->nE + k];
     h->x_from_nonbond = true;
+    return 0;
+}
+
+int qnb_nonbond(qnb_handle *h, const double *x, const double *lambda, int flags, double *d, double *E_out, double *EQ_out) {
+    if (!h || !x || !lambda || !d || !E_out || !EQ_out) return fail("qnb_nonbond: null argument");
+    if (!h->lists_built) return fail("qnb_nonbond: pair lists have not been built (call qnb_build_lists)");
+    using clk = std::chrono::steady_clock;
+    const auto t0 = clk::now();
+    if (nonbond_begin(h, x, lambda, flags)) return 1;
+    const auto t2 = clk::now();
+    CU(cudaStreamSynchronize(h->st));
+    const auto t3 = clk::now();
+    if (nonbond_end(h, d, E_out, EQ_out)) return 1;
     const auto t4 = clk::now();
     auto sec = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double>(b - a).count(); };
-    h->t_stage_in = sec(t0, t1); h->t_issue = sec(t1, t2); h->t_wait = sec(t2, t3); h->t_add_out = sec(t3, t4);
+    (void)t0;
+    h->t_wait = sec(t2, t3); h->t_add_out = sec(t3, t4);
     return 0;
+}
+
+// Independent systems of one process (FEP lambda windows, EVB frames, replicas) advanced together: the step of every
+// handle is in flight on its own streams before the first result is awaited, so the kernels of the windows fill the SMs
+// side by side and the staging of window k+1 overlaps the device work of window k.  Same results as n qnb_nonbond calls.
+int qnb_nonbond_batch(int n, qnb_handle *const *hs, const double *const *x, const double *const *lambda, int flags,
+                      double *const *d, double *const *E_out, double *const *EQ_out) {
+    if (n < 0 || (n > 0 && (!hs || !x || !lambda || !d || !E_out || !EQ_out))) return fail("qnb_nonbond_batch: null argument");
+    for (int k = 0; k < n; k++) {
+        if (!hs[k] || !x[k] || !lambda[k] || !d[k] || !E_out[k] || !EQ_out[k]) return fail("qnb_nonbond_batch: null argument for system %d", k);
+        if (!hs[k]->lists_built) return fail("qnb_nonbond_batch: pair lists of system %d have not been built", k);
+        for (int j = 0; j < k; j++) if (hs[j] == hs[k]) return fail("qnb_nonbond_batch: handle %d given twice", k);
+    }
+    int started = 0, rc = 0;
+    for (; started < n; started++)
+        if (nonbond_begin(hs[started], x[started], lambda[started], flags)) { rc = 1; break; }
+    const std::string err = rc ? g_err : std::string();
+    for (int k = 0; k < started; k++)
+        if (nonbond_end(hs[k], d[k], E_out[k], EQ_out[k]) && !rc) rc = 1;
+    if (!err.empty()) g_err = err;
+    return rc;
 }
 
 int qnb_last_timing(qnb_handle *h, double out[4]) {
@@ -1463,17 +1560,31 @@ int qnb_bench_build_lists(qnb_handle *h, int reps, float *ms_out) {
     if (!h->lists_built) return fail("pair lists have not been built");
     CU(cudaSetDevice(h->device));
     float total = 0.f;
+    h->time_build = true;
+    for (int k = 0; k < 3; k++) h->build_ms[k] = 0.f;
     for (int k = 0; k < reps; k++) {
         h->qp_done = h->qw_done = false;
         CU(cudaEventRecord(h->ev0, h->st));
-        if (build_device(h, h->hx)) return 1;
+        if (build_device(h, h->hx)) { h->time_build = false; return 1; }
         CU(cudaEventRecord(h->ev1, h->st));
         CU(cudaEventSynchronize(h->ev1));
         float ms;
         CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
         total += ms;
+        for (int j = 0; j < 3; j++) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, h->ev_bt[2 * j], h->ev_bt[2 * j + 1]) == cudaSuccess) h->build_ms[j] += t / reps;
+            else cudaGetLastError();   // this part did not run in the build (no LRF, no units)
+        }
     }
+    h->time_build = false;
     *ms_out = total;
+    return 0;
+}
+
+int qnb_bench_last_build_timing(qnb_handle *h, float out[3]) {
+    if (!h || !out) return fail("null argument");
+    for (int k = 0; k < 3; k++) out[k] = h->build_ms[k];
     return 0;
 }
 
@@ -1513,6 +1624,23 @@ int qnb_bench_kernels(qnb_handle *h, const double *lambda, int flags, int reps, 
     return n;
 }
 
+// the all-reduce of [d | E | EQ] alone (gather_nonbond + master sum), on the handle's stream
+int qnb_bench_allreduce(qnb_handle *h, int reps, float *ms_out) {
+    if (!h || !ms_out) return fail("null argument");
+    if (!h->comm) return fail("qnb_bench_allreduce: no communicator (qnb_comm_init)");
+    CU(cudaSetDevice(h->device));
+    for (int k = 0; k < reps + 2; k++) {
+        if (k == 2) CU(cudaEventRecord(h->ev0, h->st));
+        int rc = g_nccl.AllReduce(h->out.p, h->out.p, h->nout, kNcclDouble, kNcclSum, h->comm, h->st);
+        if (rc) return fail("ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
+    }
+    CU(cudaEventRecord(h->ev1, h->st));
+    CU(cudaEventSynchronize(h->ev1));
+    CU(cudaEventElapsedTime(ms_out, h->ev0, h->ev1));
+    *ms_out /= (float)std::max(reps, 1);
+    return 0;
+}
+
 int64_t qnb_launch_count(qnb_handle *h) { return h ? h->launches : 0; }
 
 int qnb_last_copy_bytes(qnb_handle *h, int64_t *h2d, int64_t *d2h) {
@@ -1531,6 +1659,7 @@ int qnb_finalize(qnb_handle *h) {
     for (int k = 0; k < kAux; k++) { if (h->aux[k]) cudaStreamDestroy(h->aux[k]); if (h->ev_join[k]) cudaEventDestroy(h->ev_join[k]); }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_pack) cudaEventDestroy(h->ev_pack);
+    for (int k = 0; k < 6; k++) if (h->ev_bt[k]) cudaEventDestroy(h->ev_bt[k]);
     h->crg.release(); h->ljd.release(); h->crgf.release(); h->ljf.release(); h->ctype.release(); h->grp_of_atom.release();
     h->g_first.release(); h->g_n.release(); h->g_switch.release(); h->g_atoms.release(); h->g_nq.release();
     h->u_sw.release(); h->u_grp.release(); h->sp_off.release(); h->sp_partner.release(); h->gs_off.release();
@@ -1545,7 +1674,7 @@ int qnb_finalize(qnb_handle *h) {
     h->shk_first.release(); h->shk_ij.release(); h->shk_d2.release(); h->shk_winv.release(); h->shk_x.release();
     h->shk_xx.release(); h->shk_iter.release();
     h->bead_atoms.release(); h->bead_base.release(); h->bead_disp.release(); h->bead_eq.release();
-    h->item_posf.release();
+    h->item_posf.release(); h->item_scr.release();
     h->upk.release(); h->pk_sw.release(); h->e_cnt.release(); h->e_off.release(); h->rec_i.release(); h->rec_f.release(); h->wT.release(); h->wown.release(); h->wd.release();
     h->pw12.release(); h->ljp.release(); h->pw0.release(); h->ww_pairs.release(); h->pp_pairs.release(); h->pw_pairs.release();
     h->item_pos.release(); h->src.release(); h->cell_unsorted.release(); h->item_nq.release(); h->src_off.release();

@@ -92,7 +92,8 @@ __global__ void k_cell_sort(int ncell, const int *__restrict__ cell_start, const
 // cell-ordered copies of what the pair searches read: switch-atom position + unit id, and the number of
 // LRF source atoms (non-Q atoms of the unit's charge group)
 __global__ void k_pack_items(Dev D, const double *__restrict__ upos, const int *__restrict__ cell_items,
-                             double4 *__restrict__ item_pos, float4 *__restrict__ item_posf, int *__restrict__ item_nq) {
+                             double4 *__restrict__ item_pos, float4 *__restrict__ item_posf, float4 *__restrict__ item_scr,
+                             int *__restrict__ item_nq) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= D.nunit) return;
     const int u = cell_items[idx];
@@ -103,6 +104,10 @@ __global__ void k_pack_items(Dev D, const double *__restrict__ upos, const int *
     if (D.use_PBC)
         for (int d = 0; d < 3; d++) w[d] -= D.box[d] * floor(w[d] * D.inv_box[d]);   // as binned (cell_coord); screening is min-image
     item_posf[idx] = make_float4((float)w[0], (float)w[1], (float)w[2], __int_as_float(nq > 0 ? u : -1 - u));
+    // screening record of the row builder: unit id | entries the unit adds to a partner's row << 24 | excluded << 31
+    const int cnt = u < D.ncgp_solute ? D.g_nq[u] : 1;
+    item_scr[idx] = make_float4((float)w[0], (float)w[1], (float)w[2],
+                                __int_as_float((int)((unsigned)u | ((unsigned)cnt << 24) | (D.u_excl[u] ? 0x80000000u : 0u))));
     item_nq[idx] = nq;
 }
 // Packed atoms: the non-Q atoms of every non-excluded unit, in cell order of the units.  Row entries are indices
@@ -304,6 +309,185 @@ k_build_rows(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x, con
                         n_b += __shfl_sync(kFull, s_b, 31);
                     }
                 }
+            }
+        }
+    }
+    if (!FILL && lane == 0) {
+        counts[3 * u] = n_own; counts[3 * u + 1] = n_mir; counts[3 * u + 2] = n_b;
+    }
+}
+
+// ---------------------------------------------------------------- neighbour rows, flattened scan (round 2)
+// Same rows as k_build_rows, built for issue efficiency (r02e: 302 M instructions per pass on the 98 k-atom box, 280 per
+// 32-candidate step, a third of the lanes idle because every step took ONE cell-row segment of ~21 candidates, two
+// dependent cell_start loads and integer divisions per step, FP64 positions converted lane by lane):
+//  * the (<= 2 x rows) item ranges of the scanned cells are tabulated once per unit in shared memory, all cell_start
+//    loads in parallel, and the candidates of all ranges are walked as ONE sequence in full steps of 32;
+//  * a 16-byte FP32 screening record per candidate (position, unit, entry count, excluded flag) decides all but the
+//    borderline candidates (|r2 - Rc2| < 1e-3 Rc2 + 0.05), which take the reference's FP64 expression as before;
+//  * positions in the segments come from ballots when no solute group is among the accepted candidates.
+constexpr int kRowSegCap = 128;    // item ranges tabulated per batch (5 x 5 rows x 2 x-segments = 50 with reach 2)
+constexpr int kRowScanWarps = 8;
+template <bool FILL>
+__global__ void __launch_bounds__(32 * kRowScanWarps)
+k_rows_scan(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x, const double *__restrict__ upos, const int *__restrict__ cell_of,
+            const int *__restrict__ cell_start, const double4 *__restrict__ item_pos, const float4 *__restrict__ item_scr,
+            const int *__restrict__ src_off, int *__restrict__ counts, const int *__restrict__ row_off,
+            uint32_t *__restrict__ rows) {
+    __shared__ int s_lo[kRowScanWarps][kRowSegCap], s_cum[kRowScanWarps][kRowSegCap + 1];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (u >= D.nunit) return;
+    const int ns = D.ncgp_solute;
+    const bool u_sol = u < ns;
+    int n_own = 0, n_mir = 0, n_b = 0;      // warp-uniform cursors
+    int base_own = 0, base_mir = 0, base_b = 0;
+    if (FILL) {
+        base_own = row_off[u];
+        base_mir = base_own + counts[3 * u];
+        base_b = base_mir + counts[3 * u + 1];
+    }
+    if (!D.u_excl[u] && !(D.sharded && D.shard_rows && !row_in_any_shard(D, u))) {
+        const double pu[3] = {upos[3 * u], upos[3 * u + 1], upos[3 * u + 2]};
+        float puf[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            double w = pu[d];
+            if (D.use_PBC) w -= D.box[d] * floor(w * D.inv_box[d]);   // as the records are stored (k_pack_items)
+            puf[d] = (float)w;
+        }
+        const float bx = (float)D.box[0], by = (float)D.box[1], bz = (float)D.box[2];
+        const float ibx = (float)D.inv_box[0], iby = (float)D.inv_box[1], ibz = (float)D.inv_box[2];
+        // screening thresholds by the partner's kind (see screen_r2)
+        const float rc_s = (float)C.rc2_of(u_sol ? 0 : 1), rc_w = (float)C.rc2_of(u_sol ? 1 : 2);
+        const float lo_s = rc_s * (1.0f - 1e-3f) - 0.05f, hi_s = rc_s * (1.0f + 1e-3f) + 0.05f;
+        const float lo_w = rc_w * (1.0f - 1e-3f) - 0.05f, hi_w = rc_w * (1.0f + 1e-3f) + 0.05f;
+        const int cu = cell_of[u];
+        const int cx = cu % G.n[0], cy = (cu / G.n[0]) % G.n[1], cz = cu / (G.n[0] * G.n[1]);
+        const DimRange rz = dim_range(cz, reach.z, G.n[2], G.periodic), ry = dim_range(cy, reach.y, G.n[1], G.periodic);
+        const XSeg xs = x_segments(cx, reach.x, G.n[0], G.periodic);
+        const int xlo0 = xs.lo[0], xhi0 = xs.hi[0], xlo1 = xs.lo[1], xhi1 = xs.hi[1];
+        const int gs_lo = u_sol ? D.gs_off[u] : 0, gs_hi = u_sol ? D.gs_off[u + 1] : 0;
+        const int nseg = rz.count * ry.count * xs.n;
+        const int a_u = u_sol ? u + 1 : u - ns + 1;   // 1-based number inside its kind (checkerboard rule)
+        for (int t0 = 0; t0 < nseg; t0 += kRowSegCap) {
+            const int nb = min(kRowSegCap, nseg - t0);
+            // ---- item ranges of this batch of cell-row segments, then their running offsets
+            __syncwarp();
+            int carry = 0;
+            for (int tb = 0; tb < nb; tb += 32) {
+                const int t = t0 + tb + lane;
+                int lo = 0, len = 0;
+                if (tb + lane < nb) {
+                    const int sgi = xs.n == 2 ? (t & 1) : 0, r = xs.n == 2 ? (t >> 1) : t;
+                    const int iz = r / ry.count, iy = r - iz * ry.count;
+                    int z = rz.start + iz, y = ry.start + iy;
+                    z += z < 0 ? G.n[2] : 0; z -= z >= G.n[2] ? G.n[2] : 0;
+                    y += y < 0 ? G.n[1] : 0; y -= y >= G.n[1] ? G.n[1] : 0;
+                    const int rowbase = (z * G.n[1] + y) * G.n[0];
+                    lo = cell_start[rowbase + (sgi ? xlo1 : xlo0)];
+                    len = cell_start[rowbase + (sgi ? xhi1 : xhi0)] - lo;
+                    s_lo[wib][tb + lane] = lo;
+                }
+                const int inc = warp_incl_scan(len, lane);
+                if (tb + lane < nb) s_cum[wib][tb + lane] = carry + inc - len;
+                carry += __shfl_sync(kFull, inc, 31);
+            }
+            if (lane == 0) s_cum[wib][nb] = carry;
+            __syncwarp();
+            const int total = carry;
+            int s0 = 0;
+            for (int v0 = 0; v0 < total; v0 += 32) {
+                const int vi = v0 + lane;
+                const bool act = vi < total;
+                int sg = s0;
+                if (act) while (vi >= s_cum[wib][sg + 1]) sg++;
+                s0 = __shfl_sync(kFull, sg, 31);
+                const int idx = act ? s_lo[wib][sg] + (vi - s_cum[wib][sg]) : 0;
+                bool pass = false, owner_is_u = false;
+                int v = -1, cnt = 0;
+                uint32_t img = 0;   // periodic image of the pair as seen from u (any-atom mode)
+                if (act) {
+                    const float4 pf = item_scr[idx];
+                    const uint32_t sb = (uint32_t)__float_as_int(pf.w);
+                    v = (int)(sb & kIdMask);
+                    cnt = (int)((sb >> 24) & 0x7fu);
+                    const bool v_sol = v < ns;
+                    bool consider = !(sb & 0x80000000u) && !(!u_sol && u == v);
+                    // class and owner side (pair_class): pw is owned by the solute group, else the checkerboard rule
+                    int cls;
+                    if (u_sol != v_sol) { cls = 1; owner_is_u = u_sol; }
+                    else {
+                        cls = u_sol ? 0 : 2;
+                        const int a_v = v_sol ? v + 1 : v - ns + 1;
+                        const bool even = ((a_u + a_v) & 1) == 0;
+                        owner_is_u = a_u == a_v ? true : (a_u > a_v ? !even : even);
+                    }
+                    if (consider && D.sharded) consider = D.shard_rows ? row_in_shard(D, cls, u) : in_shard(D, cls, owner_is_u ? u : v);
+                    if (consider) {
+                        float dx = pf.x - puf[0], dy = pf.y - puf[1], dz = pf.z - puf[2];
+                        if (D.use_PBC) { dx -= bx * rintf(dx * ibx); dy -= by * rintf(dy * iby); dz -= bz * rintf(dz * ibz); }
+                        const float r2f = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                        const float lo = v_sol ? lo_s : lo_w, hi = v_sol ? hi_s : hi_w;
+                        if (!(D.any_atom && cls != 2) && r2f < lo) pass = true;
+                        else if ((D.any_atom && cls != 2) || !(r2f > hi)) {
+                            const double4 ip = item_pos[idx];
+                            const double pv[3] = {ip.x, ip.y, ip.z};
+                            // owner orientation: the reference's outer-loop unit first
+                            const PairTest pt = owner_is_u ? unit_pair_test(D, C, x, cls, u, v, pu, pv)
+                                                           : unit_pair_test(D, C, x, cls, v, u, pv, pu);
+                            pass = pt.listed;
+                            img = (owner_is_u ? pt.img : img_negate(pt.img)) << kImgShift;
+                        }
+                    }
+                }
+                const bool v_sol = v >= 0 && v < ns;
+                // segment of the entries this lane emits: 0 own, 1 mirror, 2 other kind
+                const int seg = (u_sol != v_sol) ? 2 : (owner_is_u ? 0 : 1);
+                const int c_emit = pass ? cnt : 0;
+                int p_own, p_mir, p_b;   // exclusive positions inside this step
+                int t_own, t_mir, t_b;   // totals of this step
+                if (!__any_sync(kFull, pass && v_sol)) {
+                    // one entry per accepted candidate: ballots
+                    const unsigned lt = (1u << lane) - 1u;
+                    const unsigned m0 = __ballot_sync(kFull, pass && seg == 0), m1 = __ballot_sync(kFull, pass && seg == 1),
+                                   m2 = __ballot_sync(kFull, pass && seg == 2);
+                    p_own = __popc(m0 & lt); p_mir = __popc(m1 & lt); p_b = __popc(m2 & lt);
+                    t_own = __popc(m0); t_mir = __popc(m1); t_b = __popc(m2);
+                } else {
+                    const int c0 = seg == 0 ? c_emit : 0, c1 = seg == 1 ? c_emit : 0, c2 = seg == 2 ? c_emit : 0;
+                    const int s_own = warp_incl_scan(c0, lane), s_mir = warp_incl_scan(c1, lane), s_b = warp_incl_scan(c2, lane);
+                    p_own = s_own - c0; p_mir = s_mir - c1; p_b = s_b - c2;
+                    t_own = __shfl_sync(kFull, s_own, 31); t_mir = __shfl_sync(kFull, s_mir, 31); t_b = __shfl_sync(kFull, s_b, 31);
+                }
+                if (FILL && pass) {
+                    const uint32_t pk0 = (uint32_t)src_off[idx];   // first packed atom of unit v
+                    if (v_sol) {
+                        // flatten the group's non-Q atoms (entries = packed atom indices)
+                        const int gf = D.g_first[v], gn = D.g_n[v];
+                        const uint32_t flag = ((u_sol && owner_is_u) ? kOwnerBit : 0u) | img;
+                        int p = u_sol ? (owner_is_u ? base_own + n_own + p_own : base_mir + n_mir + p_mir) : base_b + n_b + p_b;
+                        uint32_t pk = pk0;
+                        for (int k = 0; k < gn; k++) {
+                            const int b = D.g_atoms[gf + k];
+                            if (D.is_q[b]) continue;
+                            uint32_t e = (pk++) | flag;
+                            if (u_sol) {
+                                // special if b relates to any atom of group u (excluded / 1-4 / same group)
+                                int l = gs_lo, h = gs_hi;
+                                while (l < h) { const int m = (l + h) >> 1; if (D.gs_atoms[m] < b) l = m + 1; else h = m; }
+                                if (l < gs_hi && D.gs_atoms[l] == b) e |= kSpecialBit;
+                            }
+                            rows[p++] = e;
+                        }
+                    } else {
+                        // a water partner is named by the packed index of its first atom (O)
+                        if (u_sol) rows[base_b + n_b + p_b] = pk0 | kOwnerBit | img;
+                        else if (owner_is_u) rows[base_own + n_own + p_own] = pk0 | kOwnerBit;
+                        else rows[base_mir + n_mir + p_mir] = pk0;
+                    }
+                }
+                n_own += t_own; n_mir += t_mir; n_b += t_b;
             }
         }
     }

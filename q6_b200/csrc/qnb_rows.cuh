@@ -37,6 +37,7 @@ __device__ __forceinline__ int fix_coord(double x, double org, double invp) {
     return (int)__double2uint_rd(u * 4294967296.0);   // saturating conversion: u == 1.0 after rounding stays in range
 }
 
+constexpr int kRecValid = 0x100;   // rec_i.w = compact type | kRecValid: a zero-filled record is a padding lane of a chunk
 typedef float2 f2;
 __device__ __forceinline__ f2 mk2(float a, float b) { return make_float2(a, b); }
 __device__ __forceinline__ f2 add2(f2 a, f2 b) { return __fadd2_rn(a, b); }
@@ -45,12 +46,13 @@ __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c
 __device__ __forceinline__ f2 rsq2(f2 a) { return mk2(rsqrt_fast(a.x), rsqrt_fast(a.y)); }
 
 // per packed atom, rewritten every step by k_pack_step
-//   rec_i = {P of the atom's unit switch atom (x,y,z), compact type}
+//   rec_i = {P of the atom's unit switch atom (x,y,z), compact type | 0x100}
 //   rec_f = {offset from that switch atom (x,y,z), charge}
 //   wT    = waters only, three float4 starting at the oxygen's packed index: the oxygen's fixed-point position and the
 //           hydrogen offsets t1, t2 from it, laid out as the packed (f2) operands of the row kernels:
-//           {Px, Py, t1x, t2x} {Pz, 0, t1y, t2y} {t1z, t2z, 0, 0}        (Px, Py, Pz: int bits)
-//   own   = the same three float4 per water, indexed by water number (the own molecule of a water row)
+//           {Px, Py, t1x, t2x} {Pz, 1, t1y, t2y} {t1z, t2z, 0, 0}        (Px, Py, Pz: int bits)
+//   own   = the same three float4 per water, indexed by water number (the own molecule of a water row), the water
+//           number in the third one's .z
 // and px/py/pz: FP64 coordinates in packed order (energy kernel)
 __global__ void __launch_bounds__(256)
 k_pack_step(int npk, FixFrame F, int nat_solute, const int *__restrict__ pk_atom, const int *__restrict__ pk_sw,
@@ -66,19 +68,20 @@ k_pack_step(int npk, FixFrame F, int nat_solute, const int *__restrict__ pk_atom
     px[p] = xi; py[p] = yi; pz[p] = zi;
     const int Px = fix_coord(xs, F.org[0], F.inv_period[0]), Py = fix_coord(ys, F.org[1], F.inv_period[1]),
               Pz = fix_coord(zs, F.org[2], F.inv_period[2]);
-    rec_i[p] = make_int4(Px, Py, Pz, pk_ct[p]);
+    rec_i[p] = make_int4(Px, Py, Pz, pk_ct[p] | kRecValid);
     rec_f[p] = make_float4((float)(xi - xs), (float)(yi - ys), (float)(zi - zs), pk_q[p]);
     if (i >= nat_solute && sw == i) {
         const float t1x = (float)(x[3 * i + 3] - xi), t1y = (float)(x[3 * i + 4] - yi), t1z = (float)(x[3 * i + 5] - zi);
         const float t2x = (float)(x[3 * i + 6] - xi), t2y = (float)(x[3 * i + 7] - yi), t2z = (float)(x[3 * i + 8] - zi);
         const float4 a = make_float4(__int_as_float(Px), __int_as_float(Py), t1x, t2x);
-        const float4 b = make_float4(__int_as_float(Pz), 0.f, t1y, t2y);
+        const float4 b = make_float4(__int_as_float(Pz), 1.f, t1y, t2y);   // .y: marks a real record (padding lanes read zeros)
         const float4 c = make_float4(t1z, t2z, 0.f, 0.f);
         wT[p] = a; wT[p + 1] = b; wT[p + 2] = c;
         const int w = (i - nat_solute) / 3;
-        own[3 * w] = a; own[3 * w + 1] = b; own[3 * w + 2] = c;
-        // FP64 sites of the molecule, contiguous (energy kernel): {Ox,Oy} {Oz,H1x} {H1y,H1z} {H2x,H2y} {H2z,-}
-        double2 *o = wd + 5 * (size_t)w;
+        own[3 * w] = a; own[3 * w + 1] = b; own[3 * w + 2] = make_float4(t1z, t2z, __int_as_float(w), 0.f);
+        // FP64 sites of the molecule, contiguous and in packed (cell) order (energy kernel): two double2 slots per
+        // packed atom, the water's five {Ox,Oy} {Oz,H1x} {H1y,H1z} {H2x,H2y} {H2z,-} start at its oxygen's
+        double2 *o = wd + 2 * (size_t)p;
         o[0] = make_double2(xi, yi); o[1] = make_double2(zi, x[3 * i + 3]); o[2] = make_double2(x[3 * i + 4], x[3 * i + 5]);
         o[3] = make_double2(x[3 * i + 6], x[3 * i + 7]); o[4] = make_double2(x[3 * i + 8], 0.0);
     }
@@ -125,19 +128,27 @@ __device__ __forceinline__ f2 len2(f2 dx, f2 dy, f2 dz) { return fma2(dx, dx, fm
 // travels the same way (lanes 0-2, a ring of four slots).  Entries and chunk descriptors are plain coalesced loads, three ahead.
 constexpr uint32_t kKindBit = kSpecialBit;   // water-row chunk entries: set in every lane of a B chunk (k_chunk_fill)
 constexpr int kWStages = 3;
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+// 16-byte asynchronous copy global -> shared; nbytes = 0 fills the destination with zeros (padding lanes)
+__device__ __forceinline__ void cp_async16(unsigned dst, const void *gsrc, unsigned nbytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gsrc), "r"(nbytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// the chunk entries stream from DRAM (21 MB per step on the 98 k-atom box): their lines are pulled into L2 kWPrefetch
+// chunks ahead, so that the register prefetch one step ahead only has to cover an L2 hit
+constexpr int kWPrefetch = 10;
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ float4 lds128(unsigned addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
 
-#ifndef QNB_WROWS_MINB
-#define QNB_WROWS_MINB 5
-#endif
-template <bool SPC>
-__global__ void __launch_bounds__(128, QNB_WROWS_MINB)
+// MINB: resident blocks per SM the register allocation aims at (5: 95 registers, 6: 79; QNB_WROWS_MINB selects at run time)
+template <bool SPC, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 k_water_rows(RowPar P, const int4 *__restrict__ rec_i, const float4 *__restrict__ rec_f, const float4 *__restrict__ wT,
              const float4 *__restrict__ own, const float2 *__restrict__ pw0, const float4 *__restrict__ pw12,
              const int *__restrict__ wstart, const int2 *__restrict__ cdesc, const uint32_t *__restrict__ crow,
@@ -148,6 +159,8 @@ k_water_rows(RowPar P, const int4 *__restrict__ rec_i, const float4 *__restrict_
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int c0 = wstart[gw], c1 = wstart[gw + 1];
     if (c0 >= c1) return;
+    const unsigned sS = smem_addr(&S[wib][0][0][lane]), sOwn = smem_addr(&Own[wib][0][0]);
+    constexpr unsigned kPart = 32 * 16, kStage = 3 * kPart;
     int cur_w = -1;
     int Pix = 0, Piy = 0, Piz = 0;
     f2 nSx = mk2(0, 0), nSy = nSx, nSz = nSx;                 // minus the own hydrogens' offsets {s1, s2}
@@ -166,60 +179,56 @@ k_water_rows(RowPar P, const int4 *__restrict__ rec_i, const float4 *__restrict_
         if (slot >= 0) atomicAdd(&grad[3 * (size_t)(i0_water + 3 * cur_w) + slot], (double)mine);
     };
     const int *__restrict__ cunit = reinterpret_cast<const int *>(cdesc);
-    auto ld_e = [&](int c) -> uint32_t { return c < c1 ? crow[(size_t)c * 32 + lane] : 0xffffffffu; };
-    auto ld_u = [&](int c) -> int { return c < c1 ? cunit[2 * (size_t)c] : -1; };
-    int ipar = 0, cpar = 0;   // own-record slots: next to be filled / next to be read
-    // gathers of chunk cc (entry e, unit u; up = unit of the chunk before it) into stage st; always closes a group
-    auto issue = [&](int cc, uint32_t e, int u, int up, int st) {
+    // Pipeline state.  e2/u2: entry and unit of the chunk whose gathers are issued next (c+2), e3/u3: those of c+3, in
+    // flight; up: unit of chunk c+1.  kinds/rows: one bit per chunk in flight (bit k = chunk c+k): B chunk / first chunk
+    // of a row, so that the compute side needs neither the entries nor the descriptors again.
+    uint32_t e2, e3 = 0xffffffffu;
+    int u2, u3 = -1, up;
+    unsigned kinds = 0, rows = 0, islot = 0, cslot = 0;
+    int ie = (c0 + 3) * 32 + lane;   // entry index of chunk c+3
+    auto issue = [&](int cc, uint32_t e, int u, int uprev, unsigned dst, unsigned bit) {
         if (cc < c1) {
             const bool valid = (e & kIdMask) != kIdMask;
             const int p = valid ? (int)(e & kIdMask) : 0;
-            float4 *dst = &S[wib][st][0][lane];
-            if (__ballot_sync(kFull, (e & kKindBit) != 0) == 0) {
+            const unsigned nb = valid ? 16u : 0u;
+            if (!__any_sync(kFull, (e & kKindBit) != 0)) {
                 const float4 *src = wT + p;
-                cp_async16(dst, src); cp_async16(dst + 32, src + 1); cp_async16(dst + 64, src + 2);
+                cp_async16(dst, src, nb); cp_async16(dst + kPart, src + 1, nb); cp_async16(dst + 2 * kPart, src + 2, nb);
             } else {
-                cp_async16(dst, rec_i + p); cp_async16(dst + 32, rec_f + p);
+                cp_async16(dst, rec_i + p, nb); cp_async16(dst + kPart, rec_f + p, nb);
+                kinds |= bit;
             }
-            if (u != up) {
-                if (lane < 3) cp_async16(&Own[wib][ipar][lane], own + 3 * (size_t)u + lane);
-                ipar = (ipar + 1) & 3;
+            if (u != uprev) {
+                if (lane < 3) cp_async16(sOwn + islot * 64 + lane * 16, own + 3 * (size_t)u + lane, 16u);
+                islot = (islot + 1) & 3;
+                rows |= bit;
             }
         }
         cp_async_commit();
     };
-    uint32_t e0 = ld_e(c0), e1 = ld_e(c0 + 1), e2 = ld_e(c0 + 2), e3;
-    int u0 = ld_u(c0), u1 = ld_u(c0 + 1), u2 = ld_u(c0 + 2), u3;
-    issue(c0, e0, u0, -1, 0);
-    issue(c0 + 1, e1, u1, u0, 1);
-    int st_c = 0, st_i = 2;
-    for (int c = c0; c < c1; c++) {
-        e3 = ld_e(c + 3); u3 = ld_u(c + 3);
-        issue(c + 2, e2, u2, u1, st_i);
+    auto compute = [&](unsigned src) {
         cp_async_wait<2>();
-        if (u0 != cur_w) {
+        if (rows & 1u) {
             flush();
-            cur_w = u0;
             __syncwarp();   // lanes 0-2 have passed their wait: the own record is complete
-            const float4 a = Own[wib][cpar][0], b = Own[wib][cpar][1], cc = Own[wib][cpar][2];
-            __syncwarp();
-            cpar = (cpar + 1) & 3;
+            const unsigned so = sOwn + cslot * 64;
+            const float4 a = lds128(so), b = lds128(so + 16), cc = lds128(so + 32);
+            cslot = (cslot + 1) & 3;
+            cur_w = __float_as_int(cc.z);
             Pix = __float_as_int(a.x); Piy = __float_as_int(a.y); Piz = __float_as_int(b.x);
             nSx = mk2(-a.z, -a.w); nSy = mk2(-b.z, -b.w); nSz = mk2(-cc.x, -cc.y);
             nWx = mk2(-a.w, -a.z); nWy = mk2(-b.w, -b.z); nWz = mk2(-cc.y, -cc.x);
             G12x = G12y = G12z = G21x = G21y = G21z = G0x = G0y = G0z = mk2(0.f, 0.f);
             g0x = g0y = g0z = 0.f;
         }
-        const uint32_t e = e0;
-        const bool valid = (e & kIdMask) != kIdMask;
-        const float4 r0 = S[wib][st_c][0][lane], r1 = S[wib][st_c][1][lane];
-        if (__ballot_sync(kFull, (e & kKindBit) != 0) == 0) {
-            const float4 r2 = S[wib][st_c][2][lane];
-            // vector from the own oxygen to the partner's; a padding lane is sent to 1e18 A, where every r^-3 and
-            // r^-6 below flushes to zero
+        const float4 r0 = lds128(src), r1 = lds128(src + kPart);
+        if (!(kinds & 1u)) {
+            const float4 r2 = lds128(src + 2 * kPart);
+            // vector from the own oxygen to the partner's; a padding lane (zero-filled record) is sent to 1e18 A, where
+            // every r^-3 and r^-6 below flushes to zero
             float Rx = (float)(__float_as_int(r0.x) - Pix) * P.scale[0];
             const float Ry = (float)(__float_as_int(r0.y) - Piy) * P.scale[1], Rz = (float)(__float_as_int(r1.x) - Piz) * P.scale[2];
-            Rx = valid ? Rx : 1.0e18f;
+            Rx = r1.y != 0.f ? Rx : 1.0e18f;
             const f2 RRx = mk2(Rx, Rx), RRy = mk2(Ry, Ry), RRz = mk2(Rz, Rz);
             // partner hydrogens {1, 2} seen from the own oxygen
             const f2 Ux = add2(RRx, mk2(r0.z, r0.w)), Uy = add2(RRy, mk2(r1.z, r1.w)), Uz = add2(RRz, mk2(r2.x, r2.y));
@@ -244,25 +253,50 @@ k_water_rows(RowPar P, const int4 *__restrict__ rec_i, const float4 *__restrict_
             g0x = fmaf(Rx, c00, g0x); g0y = fmaf(Ry, c00, g0y); g0z = fmaf(Rz, c00, g0z);
         } else {
             // solute atom acting on the own water (pw seen from the water: gradient only)
-            const int4 rj = make_int4(__float_as_int(r0.x), __float_as_int(r0.y), __float_as_int(r0.z), __float_as_int(r0.w));
+            const int ctw = __float_as_int(r0.w);
             const float4 oj = r1;
-            float Rx = (float)(rj.x - Pix) * P.scale[0];
-            const float Ry = (float)(rj.y - Piy) * P.scale[1], Rz = (float)(rj.z - Piz) * P.scale[2];
-            Rx = valid ? Rx : 1.0e18f;
+            float Rx = (float)(__float_as_int(r0.x) - Pix) * P.scale[0];
+            const float Ry = (float)(__float_as_int(r0.y) - Piy) * P.scale[1], Rz = (float)(__float_as_int(r0.z) - Piz) * P.scale[2];
+            Rx = (ctw & kRecValid) ? Rx : 1.0e18f;
             const float ex = Rx + oj.x, ey = Ry + oj.y, ez = Rz + oj.z;
-            const float2 l0 = pw0[rj.w];
-            const float4 l12 = pw12[rj.w];
+            const float2 l0 = pw0[ctw & 0xff];
+            const float4 l12 = pw12[ctw & 0xff];
             const f2 dx = add2(mk2(ex, ex), nSx), dy = add2(mk2(ey, ey), nSy), dz = add2(mk2(ez, ez), nSz);
             const f2 cc = pair_c2(len2(dx, dy, dz), mul2(P.wq12, mk2(oj.w, oj.w)), mk2(l12.x, l12.y), mk2(l12.z, l12.w));
             G12x = fma2(dx, cc, G12x); G12y = fma2(dy, cc, G12y); G12z = fma2(dz, cc, G12z);
             const float c0q = pair_c(fmaf(ex, ex, fmaf(ey, ey, ez * ez)), P.wq0 * oj.w, l0.x, l0.y);
             g0x = fmaf(ex, c0q, g0x); g0y = fmaf(ey, c0q, g0y); g0z = fmaf(ez, c0q, g0z);
         }
-        e0 = e1; e1 = e2; e2 = e3;
-        u0 = u1; u1 = u2; u2 = u3;
-        st_c = st_c == kWStages - 1 ? 0 : st_c + 1;
-        st_i = st_i == kWStages - 1 ? 0 : st_i + 1;
+    };
+    {
+        const uint32_t e0 = crow[(size_t)c0 * 32 + lane];
+        const uint32_t e1 = c0 + 1 < c1 ? crow[(size_t)(c0 + 1) * 32 + lane] : 0xffffffffu;
+        e2 = c0 + 2 < c1 ? crow[(size_t)(c0 + 2) * 32 + lane] : 0xffffffffu;
+        const int u0 = cunit[2 * (size_t)c0], u1 = c0 + 1 < c1 ? cunit[2 * (size_t)(c0 + 1)] : -1;
+        u2 = c0 + 2 < c1 ? cunit[2 * (size_t)(c0 + 2)] : -1;
+        issue(c0, e0, u0, -1, sS, 1u);
+        issue(c0 + 1, e1, u1, u0, sS + kStage, 2u);
+        up = u1;
     }
+    int c = c0;
+    // one step: prefetch entry/unit of chunk c+3, issue the gathers of chunk c+2 (stage SI), compute chunk c (stage SC)
+#define QNB_WSTEP(SC, SI)                                                              \
+    {                                                                                  \
+        if (c + 3 < c1) { e3 = crow[ie]; u3 = cunit[2 * (size_t)(c + 3)]; }             \
+        if (lane == 0 && c + kWPrefetch < c1) prefetch_l2(crow + (size_t)(c + kWPrefetch) * 32);  \
+        if (lane == 1 && c + 2 * kWPrefetch < c1) prefetch_l2(cunit + 2 * (size_t)(c + 2 * kWPrefetch)); \
+        issue(c + 2, e2, u2, up, sS + (SI) * kStage, 4u);                               \
+        compute(sS + (SC) * kStage);                                                   \
+        kinds >>= 1; rows >>= 1;                                                       \
+        up = u2; e2 = e3; u2 = u3; ie += 32;                                           \
+        if (++c >= c1) break;                                                          \
+    }
+    for (;;) {
+        QNB_WSTEP(0, 2)
+        QNB_WSTEP(1, 0)
+        QNB_WSTEP(2, 1)
+    }
+#undef QNB_WSTEP
     flush();
 }
 
@@ -322,7 +356,7 @@ k_solute_rows(RowPar P, const int *__restrict__ upk, const int *__restrict__ nq_
                 const int pt = pi0 + min(t, nt - 1);
                 const float4 o = rec_f[pt];
                 ox[t] = -o.x; oy[t] = -o.y; oz[t] = -o.z; q[t] = t < nt ? o.w : 0.f;
-                ct[t] = rec_i[pt].w;
+                ct[t] = rec_i[pt].w & 0xff;
             }
 #pragma unroll
             for (int h = 0; h < 2; h++) {
@@ -348,7 +382,7 @@ k_solute_rows(RowPar P, const int *__restrict__ upk, const int *__restrict__ nq_
             for (int t = 0; t < 4; t++) {
                 const unsigned sb = (spec >> (3 * t)) & 7u;
                 const bool i14 = (sb & 2u) != 0, skip = (sb & 1u) != 0 || t >= nt;
-                const float2 l = ljp[(i14 ? plane : 0) + ct[t] * P.nct + rj.w];
+                const float2 l = ljp[(i14 ? plane : 0) + ct[t] * P.nct + (rj.w & 0xff)];
                 A12[t] = skip ? 0.f : l.x; B6[t] = skip ? 0.f : l.y;
                 qs[t] = skip ? 0.f : (i14 ? oj.w * P.el14 : oj.w);
             }
@@ -393,7 +427,7 @@ k_solute_rows(RowPar P, const int *__restrict__ upk, const int *__restrict__ nq_
 
 // ------------------------------------------------------------------------------------------------
 // Energies: one thread per listed pair (the reference's own list: each pair once), FP64.
-//   ww_pairs {wi, wj}: water numbers (0-based) of the two molecules            (E%ww, nonbond_ww(_spc)(_box))
+//   ww_pairs {pi, pj}: packed indices of the two oxygens                      (E%ww, nonbond_ww(_spc)(_box))
 //   pp_pairs {pi, pj | img << 24 | 1-4 << 30 | skip << 31}: packed atoms      (E%pp, nonbond_pp(_box))
 //   pw_pairs {pi, pj | img << 24}: packed solute atom, packed water oxygen    (E%pw, nonbond_pw(_box))
 // 1/r: MUFU.RSQ64H seed y0 (relative error e ~ 2^-21) and one Newton step, y = y0 (3/2 - r2 y0^2 / 2), error 3/2 e^2.
@@ -437,18 +471,40 @@ k_pair_energy(EnergyPar P, int n_ww, const int2 *__restrict__ ww_pairs, int n_pp
         const bool classes = P.spc && P.wwQ[1] == P.wwQ[2] && P.wwQ[1] == P.wwQ[3] && P.wwQ[1] == P.wwQ[6] && P.wwQ[4] == P.wwQ[5] &&
                              P.wwQ[4] == P.wwQ[7] && P.wwQ[4] == P.wwQ[8];
         double s1[3] = {0, 0, 0}, s2[3] = {0, 0, 0};
+        // Two dependent gathers per pair (its index, then 160 bytes of sites) against ~300 cycles of FP64 work: the
+        // partner's sites of the thread's NEXT pair are copied to shared memory with cp.async while the current pair is
+        // computed (the own molecule is shared by neighbouring threads of the flat list and stays an L1-hit load), and
+        // the pair index is read two pairs ahead.
+        __shared__ double2 Wst[2][5][128];
+        const unsigned sW = smem_addr(&Wst[0][0][threadIdx.x]);
+        constexpr unsigned kWPart = 128 * 16, kWStage = 5 * kWPart;
+        auto stage_partner = [&](int pj, unsigned dst) {
+            const double2 *src = wd + 2 * (size_t)pj;
+#pragma unroll
+            for (int k = 0; k < 5; k++) cp_async16(dst + k * kWPart, src + k, 16u);
+        };
+        int2 pr = make_int2(0, 0), pr_next = make_int2(0, 0);
+        if (tid < n_ww) { pr = ww_pairs[tid]; stage_partner(pr.y, sW); }
+        cp_async_commit();
+        if (tid + nthr < n_ww) pr_next = ww_pairs[tid + nthr];
+        unsigned st = 0;
         for (int t = tid; t < n_ww; t += nthr) {
-            const int2 pr = ww_pairs[t];
+            const int2 pr_nn = (t + 2 * nthr < n_ww) ? ww_pairs[t + 2 * nthr] : make_int2(0, 0);
+            if (t + nthr < n_ww) stage_partner(pr_next.y, sW + (st ^ 1u) * kWStage);
+            cp_async_commit();
             double xi[3][3], xj[3][3];
             {
-                const double2 *wi = wd + 5 * (size_t)pr.x, *wj = wd + 5 * (size_t)pr.y;
+                const double2 *wi = wd + 2 * (size_t)pr.x;
                 const double2 a0 = wi[0], a1 = wi[1], a2 = wi[2], a3 = wi[3], a4 = wi[4];
-                const double2 b0 = wj[0], b1 = wj[1], b2 = wj[2], b3 = wj[3], b4 = wj[4];
+                cp_async_wait<1>();
+                const double2 *wj = &Wst[st][0][threadIdx.x];
+                const double2 b0 = wj[0], b1 = wj[128], b2 = wj[256], b3 = wj[384], b4 = wj[512];
                 xi[0][0] = a0.x; xi[0][1] = a0.y; xi[0][2] = a1.x; xi[1][0] = a1.y; xi[1][1] = a2.x; xi[1][2] = a2.y;
                 xi[2][0] = a3.x; xi[2][1] = a3.y; xi[2][2] = a4.x;
                 xj[0][0] = b0.x; xj[0][1] = b0.y; xj[0][2] = b1.x; xj[1][0] = b1.y; xj[1][1] = b2.x; xj[1][2] = b2.y;
                 xj[2][0] = b3.x; xj[2][1] = b3.y; xj[2][2] = b4.x;
             }
+            pr = pr_next; pr_next = pr_nn; st ^= 1u;
             if (PBC) {
                 // one shift per molecule pair from the O-O vector (nonbond_ww_spc_box L6016-6017, nonbond_ww_box); rint
                 // instead of nint: they differ only for a pair exactly half a box apart, which no list holds
@@ -580,8 +636,7 @@ k_energy_fill(Dev D, const int *__restrict__ counts, const int *__restrict__ row
     const int pi0 = upk[u];
     if (u >= D.ncgp_solute) {
         int2 *dst = ww_pairs + off_ww[u - D.ncgp_solute];
-        for (int k = lane; k < own; k += 32)
-            dst[k] = make_int2(u - D.ncgp_solute, (pk_atom[r[k] & kIdMask] - D.nat_solute) / 3);
+        for (int k = lane; k < own; k += 32) dst[k] = make_int2(pi0, (int)(r[k] & kIdMask));
         return;
     }
     const int nq = D.nq_off[u + 1] - D.nq_off[u];

@@ -131,6 +131,10 @@ def load_library(path: str = LIB_PATH):
     lib.qnb_nonbond.restype = C.c_int
     # per-step call: raw addresses (array.ctypes costs microseconds per argument)
     lib.qnb_nonbond.argtypes = [H, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.qnb_build_lists_batch.restype = C.c_int
+    lib.qnb_build_lists_batch.argtypes = [C.c_int, C.c_void_p, C.c_void_p] + [C.c_double] * 7 + [C.c_void_p]
+    lib.qnb_nonbond_batch.restype = C.c_int
+    lib.qnb_nonbond_batch.argtypes = [C.c_int] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 3
     lib.qnb_list_count.restype = C.c_int
     lib.qnb_list_count.argtypes = [H, C.c_int, C.c_int, _PL]
     lib.qnb_export_list.restype = C.c_int
@@ -145,6 +149,10 @@ def load_library(path: str = LIB_PATH):
     lib.qnb_bench_nonbond.argtypes = [H, _PD, C.c_int, C.c_int, C.c_int, _PF]
     lib.qnb_bench_build_lists.restype = C.c_int
     lib.qnb_bench_build_lists.argtypes = [H, C.c_int, _PF]
+    lib.qnb_bench_allreduce.restype = C.c_int
+    lib.qnb_bench_allreduce.argtypes = [H, C.c_int, _PF]
+    lib.qnb_bench_last_build_timing.restype = C.c_int
+    lib.qnb_bench_last_build_timing.argtypes = [H, _PF]
     lib.qnb_bench_md.restype = C.c_int
     lib.qnb_bench_md.argtypes = [H, _PD, C.c_int, C.c_int, C.c_int, _PF]
     lib.qnb_bench_peak.restype = C.c_int
@@ -372,6 +380,17 @@ class Qnb:
         self._check(self.lib.qnb_bench_build_lists(self.h, reps, C.byref(ms)))
         return ms.value
 
+    def bench_allreduce(self, reps: int) -> float:
+        ms = C.c_float()
+        self._check(self.lib.qnb_bench_allreduce(self.h, reps, C.byref(ms)))
+        return ms.value
+
+    def last_build_timing(self) -> dict:
+        """ms per build of the parts timed by the last bench_build_lists: LRF accumulation, row scan passes."""
+        t = (C.c_float * 3)()
+        self._check(self.lib.qnb_bench_last_build_timing(self.h, t))
+        return dict(zip(("lrf_ms", "rows_count_ms", "rows_fill_ms"), [float(v) for v in t]))
+
     def bench_kernels(self, lambdas, reps: int, md=True, qq=True, flush_l2=False, restraints=False) -> dict:
         lam = np.ascontiguousarray(lambdas, dtype=np.float64)
         names = C.create_string_buffer(4096)
@@ -395,6 +414,57 @@ class Qnb:
         a, b = C.c_int64(), C.c_int64()
         self._check(self.lib.qnb_last_copy_bytes(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+
+class QnbBatch:
+    """Independent systems of one process (the lambda windows of a FEP farm, EVB frames) advanced together on one GPU
+    through qnb_build_lists_batch / qnb_nonbond_batch: same arguments and results as the single-system calls, one list
+    entry per system.  The pointer tables are built once; the arrays they point to are reused every step."""
+
+    def __init__(self, handles):
+        assert handles and len({id(g) for g in handles}) == len(handles)
+        self.g = list(handles)
+        self.lib = self.g[0].lib
+        n = self.n = len(self.g)
+        self._h = (C.c_void_p * n)(*[g.h for g in self.g])
+        self.x = [np.zeros(3 * g.sys.natom) for g in self.g]
+        self.lam = [np.zeros(g.sys.nstates) for g in self.g]
+        self.d = [np.zeros((g.sys.natom, 3)) for g in self.g]
+        self.E = [np.zeros(E_COUNT) for _ in self.g]
+        self.EQ = [np.zeros((g.sys.nstates, EQ_STRIDE)) for g in self.g]
+        tab = lambda arrs: (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+        self._x, self._lam, self._d, self._E, self._EQ = tab(self.x), tab(self.lam), tab(self.d), tab(self.E), tab(self.EQ)
+
+    def _check(self, rc):
+        if rc:
+            raise QnbError(self.lib.qnb_last_error().decode())
+
+    def make_pair_lists(self, xs, Rq, Rcq2, RcLRF2, Rcpp2, Rcpw2, Rcww2, RcLRF=None, counts=False):
+        for k, xk in enumerate(xs):
+            self.x[k][:] = np.asarray(xk, dtype=np.float64).reshape(-1)
+        if RcLRF is None:
+            RcLRF = float(np.sqrt(RcLRF2)) if RcLRF2 >= 0 else -1.0
+        out = np.zeros((self.n, 8), np.int64) if counts else None
+        self._check(self.lib.qnb_build_lists_batch(self.n, self._h, self._x, Rq, Rcq2, RcLRF2, Rcpp2, Rcpw2, Rcww2, RcLRF,
+                                                   out.ctypes.data if counts else None))
+        return out
+
+    def pot_energy_nonbonds(self, xs=None, lambdas=None, md=True, qq=True, zero_d=True):
+        """One step of every system; xs / lambdas (lists) are copied into the batch's own arrays when given.  Returns the
+        batch's (d, E, EQ) lists: d[k] is ADDED to unless zero_d."""
+        if xs is not None:
+            for k, xk in enumerate(xs):
+                self.x[k][:] = np.asarray(xk, dtype=np.float64).reshape(-1)
+        if lambdas is not None:
+            for k, lk in enumerate(lambdas):
+                self.lam[k][:] = lk
+        if zero_d:
+            for dk in self.d:
+                dk[:] = 0.0
+        flags = (QNB_FLAG_MD if md else 0) | (QNB_FLAG_QQ if qq else 0)
+        if self.lib.qnb_nonbond_batch(self.n, self._h, self._x, self._lam, flags, self._d, self._E, self._EQ):
+            self._check(1)
+        return self.d, self.E, self.EQ
 
 
 def bench_peak(which: int, device: int = 0) -> float:

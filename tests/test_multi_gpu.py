@@ -12,8 +12,8 @@ pytestmark = pytest.mark.gpu
 
 
 def _worker(rank, world, port, q_path, out_path, cuts, lam, shard_rows=False):
-    if shard_rows:
-        os.environ["QNB_SHARD_ROWS"] = "1"      # read by qnb_init
+    if not shard_rows:
+        os.environ["QNB_SHARD_PAIRS"] = "1"     # read by qnb_init: the reference's pair partition instead of the row partition
     import torch
     import torch.distributed as dist
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -363,3 +363,47 @@ def test_solvent_restraints(case):
     finally:
         g.close()
         o.close()
+
+
+def test_batched_windows_equal_single_calls():
+    """qnb_build_lists_batch / qnb_nonbond_batch over W lambda windows of one FEP system (own coordinates and lambda per
+    window, run_excl_test.sh:92-125) == W single-system calls: same list counts, gradients to FP64 summation-order noise,
+    energies likewise; every window also checked against the oracle."""
+    from oracle.pyoracle import Oracle
+    from q6_b200 import synth
+    from q6_b200.engine import Qnb, QnbBatch
+    q = synth.solvated_sphere(14.0, 0.0, 14, 2, 97, fep="annihilate")
+    cuts = common.sph_cuts(8.0)
+    W = 5
+    rng = np.random.default_rng(5)
+    xs = [q.xtop + rng.normal(0.0, 0.02, q.xtop.shape) for _ in range(W)]
+    lams = [np.array([1.0 - 0.2 * k, 0.2 * k]) for k in range(W)]
+    hs = [Qnb(q) for _ in range(W)]
+    b = QnbBatch(hs)
+    cb = b.make_pair_lists(xs, **cuts, counts=True)
+    d, E, EQ = b.pot_energy_nonbonds(xs, lams)
+    d = [v.copy() for v in d]; E = [v.copy() for v in E]; EQ = [v.copy() for v in EQ]
+    # a second batched step on the same inputs adds to d unless zeroed (pot_energy adds to d)
+    d2, _, _ = b.pot_energy_nonbonds(zero_d=False)
+    for k in range(W):
+        assert np.allclose(d2[k], 2.0 * d[k], rtol=1e-9, atol=1e-9)
+    o = Oracle(q)
+    for k in range(W):
+        g = Qnb(q)
+        c1 = g.make_pair_lists(xs[k], **cuts)
+        d1, E1, EQ1 = g.pot_energy_nonbonds(xs[k], lams[k])
+        assert np.array_equal(cb[k][:5], c1[:5])
+        assert common.rel_rms(d[k], d1) <= 1e-12
+        assert np.allclose(E[k], E1, rtol=1e-11, atol=1e-9) and np.allclose(EQ[k], EQ1, rtol=1e-11, atol=1e-9)
+        co = o.make_pair_lists(xs[k], **cuts)
+        do, Eo, EQo = o.pot_energy_nonbonds(xs[k], lams[k])
+        assert np.array_equal(c1[:5], co[:5])
+        assert common.rel_rms(d[k], do) <= common.FORCE_REL_RMS
+        common.assert_energy("E", E[k], Eo)
+        common.assert_energy("EQ", EQ[k], EQo)
+        g.close()
+    # errors: a handle given twice is refused
+    with pytest.raises(Exception):
+        QnbBatch([hs[0], hs[0]])
+    for g in hs:
+        g.close()

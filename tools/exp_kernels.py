@@ -13,7 +13,8 @@ step = g.bench_nonbond(lam, 400) / 400 * 1e3
 noe = g.bench_nonbond(lam, 400, energies=False) / 400 * 1e3
 build = g.bench_build_lists(5) / 5
 kt = g.bench_kernels(lam, 20, flush_l2=len(sys.argv) > 2)
-print(w, "counts", [int(v) for v in c[:5]], "step us %.2f  (no pp/pw/ww energies %.2f)  build ms %.3f" % (step, noe, build))
+print(w, "counts", [int(v) for v in c[:5]], "step us %.2f  (no pp/pw/ww energies %.2f)  build ms %.3f" % (step, noe, build),
+      {k: round(v, 3) for k, v in g.last_build_timing().items()})
 print("   kernels us:", {k: round(v * 1e3, 2) for k, v in kt.items()})
 nww = c[2] / 9.0
 fl_w = nww * 209 + 0.5 * c[1] * 33
