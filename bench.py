@@ -356,9 +356,7 @@ def sharded_c5(job, steps, warmup, repeats):
     g1.close()
     # ---- sharded
     g = Qnb(shard_system(q, job.rank, job.world), device=job.dev)
-    uid = [g.unique_id() if job.rank == 0 else None]
-    job.dist.broadcast_object_list(uid, src=0)
-    g.comm_init(job.rank, job.world, uid[0])
+    comm = g.comm_connect(job.rank, job.world, job.dist, os.environ.get("QNB_COMM", "auto"))
     cl = g.make_pair_lists(x, **cuts)
     tot = job.reduce(float(cl[2]), "sum")
     g.bench_md(lam, max(warmup, NBCYCLE), NBCYCLE)
@@ -372,11 +370,12 @@ def sharded_c5(job, steps, warmup, repeats):
     ar = job.reduce(g.bench_allreduce(50))
     e2e = float(np.median(timed_e2e(job, g, q, x, lam, cuts, steps, 3))) / steps
     kt = g.bench_kernels(lam, 10, flush_l2=True)
+    g.comm_status()
     g.close()
     return {"workload": WORKLOADS["C5"], "natom": int(q.natom), "partition": "pairs" if os.environ.get("QNB_SHARD_PAIRS") else "rows",
             "pairs_per_step": npairs, "list_entries_all_ranks": int(tot),
             "ms_per_step": tN_md, "value": npairs / (tN_md * 1e-3), "unit": "pairs/s", "device_step_ms": tN_step,
-            "list_build_ms": tN_build, "allreduce_ms": ar, "allreduce_bytes": int((3 * q.natom + 7 + 6 * q.nstates) * 8),
+            "list_build_ms": tN_build, "comm": comm, "allreduce_ms": ar, "allreduce_bytes": int((3 * q.natom + 7 + 6 * q.nstates) * 8),
             "e2e": {"ms_per_step": e2e * 1e3, "value": npairs / e2e, "unit": "pairs/s"},
             "n1": {"ms_per_step": t1_md, "device_step_ms": t1_step, "list_build_ms": t1_build},
             "efficiency_vs_n1": t1_md / (job.world * tN_md), "efficiency_device_step_vs_n1": t1_step / (job.world * tN_step),
@@ -384,8 +383,9 @@ def sharded_c5(job, steps, warmup, repeats):
             "scaling": "strong",
             "note": "ms_per_step = device-resident MD loop (one evaluation + all-reduce per step, list build + LRF all-reduce "
                     f"every {NBCYCLE} steps), CUDA events, max over ranks, median of {repeats} windows; n1 = the unsharded "
-                    "system on one GPU in the same run; the all-reduce is NCCL over NVLink issued eagerly after the step's "
-                    "kernels (not captured in the step graph: capture hung on this NCCL, profiles/r02d)"}
+                    "system on one GPU in the same run; comm p2p = one kernel per rank over CUDA-IPC peer memory (owner of a "
+                    "slice sums it over the ranks and writes the sum into every rank's buffer), captured in the step's CUDA "
+                    "graph; comm nccl = ncclAllReduce issued eagerly after the step's kernels (QNB_COMM=nccl)"}
 
 
 def main():
@@ -459,10 +459,8 @@ def main():
         # distribute_nonbonds (nonbondene.f90:80-505): contiguous i-ranges per rank, everything else replicated
         from q6_b200.system import shard_system
         g = Qnb(shard_system(q, rank, world), device=dev)
-        uid = [g.unique_id() if rank == 0 else None]
-        job.dist.broadcast_object_list(uid, src=0)
-        g.comm_init(rank, world, uid[0])
-        config["replicas"] = f"one system, pair lists sharded over {world} GPUs, NCCL all-reduce of [d|E|EQ] per step"
+        comm = g.comm_connect(rank, world, job.dist, os.environ.get("QNB_COMM", "auto"))
+        config["replicas"] = f"one system, rows of the pair lists sharded over {world} GPUs, all-reduce of [d|E|EQ] per step ({comm})"
     else:
         g = Qnb(q, device=dev)
     x = q.xtop.copy()

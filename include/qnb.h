@@ -292,6 +292,19 @@ int qnb_export_lrf(qnb_handle *h, double *lrf);
 int qnb_comm_unique_id(void *id128);
 int qnb_comm_init(qnb_handle *h, int rank, int nranks, const void *id128);
 
+/*
+ * The same sums over peer memory instead of NCCL, for ranks on one NVLink / NVSwitch node: every rank exports a
+ * QNB_IPC_BLOB-byte descriptor of its device buffers, the host gathers them (MPI_Allgather / torch.distributed) and every
+ * rank attaches all of them.  From then on the per-step sum of [d | E | EQ] and the per-build sum of the LRF moments are
+ * one kernel per rank that reads and writes the peers' buffers directly (captured in the step's CUDA graph); qnb_comm_init
+ * is not needed.  Fails (use qnb_comm_init) when the devices cannot access each other.
+ */
+#define QNB_IPC_BLOB 128
+int qnb_comm_ipc_export(qnb_handle *h, void *blob /* QNB_IPC_BLOB bytes */);
+int qnb_comm_ipc_attach(qnb_handle *h, int rank, int nranks, const void *blobs /* nranks * QNB_IPC_BLOB bytes, by rank */);
+/* 0, or non-zero (qnb_last_error) when a rank missed a barrier of the peer-memory all-reduce (it gives up after ~4 s). */
+int qnb_comm_status(qnb_handle *h);
+
 /* ---- measurement hooks (bench.py); device-resident, no host copies ---- */
 /* Re-run the last qnb_nonbond `steps` times on the coordinates already in HBM;
  * ms_out = CUDA-event time of the whole loop on the handle's stream. */

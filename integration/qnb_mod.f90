@@ -188,6 +188,26 @@ interface
         character(kind=c_char), intent(in) :: id128(128)
         integer(c_int) :: rc
     end function
+    ! the same sums over peer memory (NVLink / NVSwitch) instead of NCCL: every rank exports a 128-byte descriptor, the
+    ! host gathers them with MPI_Allgather and every rank attaches all of them (qnb_comm_init is then not needed)
+    function qnb_comm_ipc_export(handle, blob) bind(c, name='qnb_comm_ipc_export') result(rc)
+        import :: c_int, c_ptr, c_char
+        type(c_ptr), value :: handle
+        character(kind=c_char), intent(out) :: blob(128)
+        integer(c_int) :: rc
+    end function
+    function qnb_comm_status(handle) bind(c, name='qnb_comm_status') result(rc)
+        import :: c_int, c_ptr
+        type(c_ptr), value :: handle
+        integer(c_int) :: rc
+    end function
+    function qnb_comm_ipc_attach(handle, rank, nranks, blobs) bind(c, name='qnb_comm_ipc_attach') result(rc)
+        import :: c_int, c_ptr, c_char
+        type(c_ptr), value :: handle
+        integer(c_int), value :: rank, nranks
+        character(kind=c_char), intent(in) :: blobs(*)    ! 128 * nranks, by rank
+        integer(c_int) :: rc
+    end function
     function qnb_finalize(handle) bind(c, name='qnb_finalize') result(rc)
         import :: c_int, c_ptr
         type(c_ptr), value :: handle

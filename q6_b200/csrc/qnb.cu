@@ -9,6 +9,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -72,8 +75,11 @@ template <typename T>
 struct DBuf {   // device buffer that only grows
     T *p = nullptr;
     size_t cap = 0;
+    bool view = false;   // points into another allocation (the arena shared with peer GPUs): never freed or regrown here
+    void alias(T *q, size_t n) { p = q; cap = n; view = true; }
     int ensure(size_t n) {
         if (n <= cap) return 0;
+        if (view) return fail("internal: a view buffer cannot grow (%zu > %zu)", n, cap);
         if (p) cudaFree(p);
         p = nullptr;
         size_t want = n + n / 4 + 256;
@@ -82,7 +88,7 @@ struct DBuf {   // device buffer that only grows
         cap = want;
         return 0;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() { if (p && !view) cudaFree(p); p = nullptr; cap = 0; view = false; }
 };
 
 template <typename T>
@@ -137,7 +143,7 @@ struct qnb_handle {
         qp_shift_atom;
     DBuf<uint32_t> rows;
     DBuf<double4> item_pos, src;
-    DBuf<float4> item_posf, item_scr;
+    DBuf<float4> item_posf, item_scr, srcf;
     DBuf<int> cell_unsorted, item_nq, src_off, pk_atom, pk_ct;
     DBuf<float> pk_q;
     DBuf<double> pk_qd, px, py, pz;
@@ -194,6 +200,12 @@ struct qnb_handle {
     // comm
     ncclCommT comm = nullptr;
     int rank = 0, nranks = 1;
+    // peer-memory all-reduce (qnb_comm_ipc_export / qnb_comm_ipc_attach): [out | lrf | control words] live in ONE
+    // allocation that the other ranks of the node map through CUDA IPC
+    double *arena = nullptr;
+    size_t arena_doubles = 0, arena_lrf_off = 0, arena_ctl_off = 0;
+    P2PComm p2p{};
+    void *peer_base[kMaxPeers] = {};
     // stats
     int64_t launches = 0, last_h2d = 0, last_d2h = 0;
     double t_stage_in = 0, t_issue = 0, t_wait = 0, t_add_out = 0;   // host-side seconds of the last qnb_nonbond
@@ -359,10 +371,22 @@ static int init_device(qnb_handle *h) {
     const size_t n3 = 3 * (size_t)s.natom;
     h->nE = QNB_E_COUNT + QNB_EQ_STRIDE * s.nstates;
     h->nout = n3 + (size_t)kESlots * h->nE + kRstOut;   // [gradient | energy slots | restraint results]
-    if (h->x.ensure(n3 + kMaxStates) || h->out.ensure(h->nout) ||
-        h->lrf.ensure((size_t)QNB_LRF_STRIDE * std::max(s.ncgp, 1)))
-        return 1;
-    CU(cudaMemset(h->lrf.p, 0, sizeof(double) * QNB_LRF_STRIDE * std::max(s.ncgp, 1)));
+    if (h->x.ensure(n3 + kMaxStates)) return 1;
+    {
+        // one allocation of whole 2 MiB pages for everything other ranks read or write (a cudaMalloc of this size is never
+        // a sub-allocation of a driver slab, so the IPC handle of its base maps exactly these bytes in the peers)
+        const size_t nlrf = (size_t)QNB_LRF_STRIDE * std::max(s.ncgp, 1);
+        const size_t a16 = 16;   // doubles: keep every part 128-byte aligned
+        h->arena_lrf_off = (h->nout + a16 - 1) / a16 * a16;
+        h->arena_ctl_off = h->arena_lrf_off + (nlrf + a16 - 1) / a16 * a16;
+        const size_t bytes = ((h->arena_ctl_off + 512) * sizeof(double) + ((size_t)2 << 20) - 1) / ((size_t)2 << 20) * ((size_t)2 << 20);
+        cudaError_t e = cudaMalloc(&h->arena, bytes);
+        if (e != cudaSuccess) return fail("cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString(e));
+        h->arena_doubles = bytes / sizeof(double);
+        CU(cudaMemset(h->arena, 0, bytes));
+        h->out.alias(h->arena, h->nout);
+        h->lrf.alias(h->arena + h->arena_lrf_off, nlrf);
+    }
     CU(cudaMallocHost(&h->hx, (n3 + kMaxStates) * sizeof(double)));
     h->hlam = h->hx + n3;
     for (int k = 0; k < kMaxStates; k++) h->hlam[k] = 0.0;
@@ -395,6 +419,22 @@ static int init_device(qnb_handle *h) {
     if (const char *e = getenv("QNB_ONE_STREAM")) h->multi_stream = !(e[0] == '1');
     if (const char *e = getenv("QNB_WATER_BLOCKS")) h->water_blocks = std::max(0, atoi(e));
     if (const char *e = getenv("QNB_SOLUTE_BLOCKS")) h->solute_blocks = std::max(0, atoi(e));
+    return 0;
+}
+
+// Sum of a part of the arena over the ranks, in place on every rank: the kernel over peer memory when the ranks have
+// attached each other's arenas (graph-capturable: a plain kernel), else NCCL.
+static bool p2p_ready(const qnb_handle *h) { return h->p2p.n > 1; }
+static int allreduce_arena(qnb_handle *h, size_t off, size_t count, cudaStream_t st) {
+    if (p2p_ready(h)) {
+        const int blocks = std::max(1, std::min(h->nsm, (int)((count / 2 + 255) / 256)));
+        LAUNCH_ON(h, st, k_p2p_allreduce, blocks, 256, 0, h->p2p, off, count,
+                  reinterpret_cast<unsigned *>(h->arena + h->arena_ctl_off));
+        return 0;
+    }
+    if (!h->comm) return 0;
+    int rc = g_nccl.AllReduce(h->arena + off, h->arena + off, count, kNcclDouble, kNcclSum, h->comm, st);
+    if (rc) return fail("ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
     return 0;
 }
 
@@ -507,7 +547,7 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
         h->flag.ensure(std::max({D.natom, D.nwat, 1}) + 1) || h->pos.ensure(std::max({D.natom, D.nwat, 1}) + 2) ||
         h->qp_list.ensure(std::max(D.nat_solute, 1)) || h->qw_list.ensure(std::max(D.nwat, 1)) ||
         h->qp_shift_atom.ensure(std::max(D.ncgp_solute, 1)) || h->item_pos.ensure(std::max(nu, 1)) || h->item_posf.ensure(std::max(nu, 1)) || h->item_scr.ensure(std::max(nu, 1)) ||
-        h->src.ensure(std::max(D.natom, 1)) || h->cell_unsorted.ensure(std::max(nu, 1)) ||
+        h->src.ensure(std::max(D.natom, 1)) || h->srcf.ensure(std::max(D.natom, 1)) || h->cell_unsorted.ensure(std::max(nu, 1)) ||
         h->item_nq.ensure(std::max(nu, 1) + 1) || h->src_off.ensure(std::max(nu, 1) + 2) ||
         h->pk_atom.ensure(D.natom + 4) || h->pk_ct.ensure(D.natom + 4) || h->pk_q.ensure(D.natom + 4) ||
         h->pk_qd.ensure(D.natom + 4) || h->px.ensure(D.natom + 4) || h->py.ensure(D.natom + 4) ||   // +4: the force kernels always fetch three sites
@@ -530,7 +570,7 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
         if (h->time_build) cudaEventRecord(h->ev_bt[0], ls);
         LAUNCH_ON(h, ls, k_cgp_centers, cdiv(D.ncgp, 128), 128, 0, D, h->x.p, h->lrf.p);
         if (nu > 0) {
-            LAUNCH_ON(h, ls, k_pack_sources, cdiv(D.natom, 256), 256, 0, h->src_off.p + nu, h->pk_atom.p, h->x.p, h->crg.p, h->src.p);
+            LAUNCH_ON(h, ls, k_pack_sources, cdiv(D.natom, 256), 256, 0, h->src_off.p + nu, h->pk_atom.p, h->x.p, h->crg.p, h->src.p, h->srcf.p);
             // compaction pays when the LRF shell holds a small part of the scanned cells (boxes, short RcLRF)
             const double rl = std::sqrt(std::max(h->cut.rclrf2, 0.0));
             const bool all = h->cut.lrf_all[0] || h->cut.lrf_all[1] || h->cut.lrf_all[2];
@@ -547,16 +587,16 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
             for (int gn : h->T.g_n) gmax = std::max(gmax, gn);
             bool allpairs = !G.periodic && !general && gmax <= kLrfTileAtoms && !getenv("QNB_LRF_GENERAL");
             for (int d = 0; d < 3; d++) allpairs = allpairs && rr[d] >= G.n[d];
-            if (allpairs && !h->lrf_mom.ensure((size_t)20 * nu)) {
-                cudaMemsetAsync(h->lrf_mom.p, 0, sizeof(double) * 20 * (size_t)nu, ls);
+            if (allpairs && !h->lrf_mom.ensure((size_t)kLrfRaw * nu)) {
+                cudaMemsetAsync(h->lrf_mom.p, 0, sizeof(double) * kLrfRaw * (size_t)nu, ls);
                 const int tb = cdiv(nu, 128);
-                const int slices = std::max(1, std::min(cdiv(nu, kLrfTileItems), cdiv(4 * h->nsm, tb)));
+                const int slices = std::max(1, std::min(cdiv(nu, kLrfTileItems), cdiv(6 * h->nsm, tb)));
                 LAUNCH_ON(h, ls, k_lrf_allpairs, dim3(tb, slices), 128, 0, D, h->cut, h->x.p, h->upos.p, h->item_pos.p, h->item_posf.p,
                           h->src_off.p, h->src.p, h->lrf.p, h->lrf_mom.p);
                 LAUNCH_ON(h, ls, k_lrf_expand, cdiv(nu * 40, 256), 256, 0, D, h->lrf_mom.p, h->lrf.p);
             } else
 #define LRFCASE(CP, RS, GN) LAUNCH_ON(h, ls, (k_lrf_accumulate<CP, RS, GN>), nu, 32 * kRowWarps, 0, D, h->cut, G, h->lrf_reach, h->x.p, h->upos.p, \
-                                      h->cell_of.p, h->cell_start.p, h->item_pos.p, h->item_posf.p, h->src_off.p, h->src.p, h->lrf.p)
+                                      h->cell_of.p, h->cell_start.p, h->item_pos.p, h->item_posf.p, h->src_off.p, h->src.p, h->srcf.p, h->lrf.p)
             if (rowshift) { if (general) LRFCASE(true, true, true); else LRFCASE(true, true, false); }
             else if (compact) { if (general) LRFCASE(true, false, true); else LRFCASE(true, false, false); }
             else { if (general) LRFCASE(false, false, true); else LRFCASE(false, false, false); }
@@ -637,12 +677,16 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
         if (h->n_ww_e + h->n_pp_e + h->n_pw_e > 0)
             LAUNCH(h, k_energy_fill, cdiv(nu * 32, 256), 256, 0, D, h->counts.p, h->row_off.p, h->rows.p, h->upk.p, h->pk_atom.p, eo_ww, eo_pp,
                    eo_pw, h->ww_pairs.p, h->pp_pairs.p, h->pw_pairs.p);
+        // the all-zero records behind the last packed atom: what the padding lanes of the water-row chunks load
+        CU(cudaMemsetAsync(h->wT.p + npk, 0, 3 * sizeof(float4), h->st));
+        CU(cudaMemsetAsync(h->rec_i.p + npk, 0, sizeof(int4), h->st));
+        CU(cudaMemsetAsync(h->rec_f.p + npk, 0, sizeof(float4), h->st));
         if (h->nwchunk > 0)
             LAUNCH(h, k_chunk_fill, cdiv(nwat * 32, 256), 256, 0, D, nsol, nwat, 0, h->counts.p, h->row_off.p, h->rows.p, off_w,
-                   h->wdesc.p, h->wrow.p, h->pk_atom.p, (uint16_t *)nullptr, new_rows);
+                   h->wdesc.p, h->wrow.p, h->pk_atom.p, (uint16_t *)nullptr, new_rows, (uint32_t)npk);
         if (h->nschunk > 0)
             LAUNCH(h, k_chunk_fill, cdiv(nsol * 32, 256), 256, 0, D, 0, nsol, kITile, h->counts.p, h->row_off.p, h->rows.p, off_s,
-                   h->sdesc.p, h->srow.p, h->pk_atom.p, h->sspec.p, false);
+                   h->sdesc.p, h->srow.p, h->pk_atom.p, h->sspec.p, false, 0u);
         // one resident wave per kernel, every warp an equal share of the estimated work
         const int occw = new_rows ? h->occ_wr : h->occ_w, occs = new_rows ? h->occ_sr : h->occ_s;
         const int min_chunks = new_rows ? 2 : 4;   // chunks per warp below which more blocks only add launch overhead
@@ -680,12 +724,10 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
     // LRF: the moments were started on the side stream after the cell tables (see above); join, then the exchange
     if (D.use_LRF && D.ncgp > 0 && !h->restoring) {
         if (lrf_forked) CU(cudaStreamWaitEvent(h->st, h->ev_join[kLrfStream], 0));
-        if (h->comm) {
-            // lrf_gather (nonbondene.f90:616-623): sum the moments, keep cgp_cent (identical on every rank).
-            // cgp_cent is divided by nranks after the sum so one all-reduce serves both.
-            int rc = g_nccl.AllReduce(h->lrf.p, h->lrf.p, (size_t)QNB_LRF_STRIDE * D.ncgp, kNcclDouble, kNcclSum, h->comm, h->st);
-            if (rc) return fail("ncclAllReduce(lrf): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
-            // restore the centres (recomputed: bit-identical to the single-rank value)
+        if (h->comm || p2p_ready(h)) {
+            // lrf_gather (nonbondene.f90:616-623): sum the moments over the ranks; the centres (identical on every rank)
+            // are summed along and recomputed afterwards: bit-identical to the single-rank value
+            if (allreduce_arena(h, h->arena_lrf_off, (size_t)QNB_LRF_STRIDE * D.ncgp, h->st)) return 1;
             LAUNCH(h, k_cgp_centers_only, cdiv(D.ncgp, 128), 128, 0, D, h->x.p, h->lrf.p);
         }
     }
@@ -885,7 +927,7 @@ static int step_device(qnb_handle *h, int flags, bool with_copies = false) {
     // sharded step: the all-reduce is issued eagerly after the kernels unless QNB_SHARD_GRAPH=1 asks for it to be captured
     // with them (NCCL >= 2.9 supports capture once the communicator has been used; not yet run on hardware)
     static const bool shard_graph = getenv("QNB_SHARD_GRAPH") != nullptr;
-    const bool graphable = h->use_graph && (!h->comm || shard_graph);
+    const bool graphable = h->use_graph && (!h->comm || shard_graph || p2p_ready(h));
     flags &= (QNB_FLAG_MD | QNB_FLAG_QQ | QNB_FLAG_NO_ENERGY | QNB_FLAG_SOLVENT_RESTRAINTS);
     const int gi = (flags & 7) | ((flags & QNB_FLAG_SOLVENT_RESTRAINTS) ? 8 : 0);
     if (graphable) {
@@ -910,7 +952,7 @@ static int step_device(qnb_handle *h, int flags, bool with_copies = false) {
                 if (cleared) rc |= cudaStreamWaitEvent(h->st, h->ev_join[4], 0) != cudaSuccess;
             }
             rc |= issue_step(h, flags, cleared);
-            if (h->comm) rc |= g_nccl.AllReduce(h->out.p, h->out.p, h->nout, kNcclDouble, kNcclSum, h->comm, h->st) != 0;
+            rc |= allreduce_arena(h, 0, h->nout, h->st);
             if (with_copies) rc |= cudaMemcpyAsync(h->hout, h->out.p, h->nout * sizeof(double), cudaMemcpyDeviceToHost, h->st) != cudaSuccess;
             cudaError_t ce = cudaStreamEndCapture(h->st, &g);
             h->graph_launches[with_copies ? 1 : 0][gi] = (int)(h->launches - l0);
@@ -935,11 +977,8 @@ static int step_device(qnb_handle *h, int flags, bool with_copies = false) {
         CU(cudaMemcpyAsync(h->x.p, h->hx, (n3 + kMaxStates) * sizeof(double), cudaMemcpyHostToDevice, h->st));
     }
     if (issue_step(h, flags)) return 1;
-    if (h->comm) {
-        // gather_nonbond + serial sum on the master (potene.f90:195-222) as one all-reduce over [d | E | EQ]
-        int rc = g_nccl.AllReduce(h->out.p, h->out.p, h->nout, kNcclDouble, kNcclSum, h->comm, h->st);
-        if (rc) return fail("ncclAllReduce(forces): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
-    }
+    // gather_nonbond + serial sum on the master (potene.f90:195-222) as one all-reduce over [d | E | EQ]
+    if (allreduce_arena(h, 0, h->nout, h->st)) return 1;
     if (with_copies) CU(cudaMemcpyAsync(h->hout, h->out.p, h->nout * sizeof(double), cudaMemcpyDeviceToHost, h->st));
     return 0;
 }
@@ -1296,6 +1335,58 @@ int qnb_nonbond(qnb_handle *h, const double *x, const double *lambda, int flags,
 // Independent systems of one process (FEP lambda windows, EVB frames, replicas) advanced together: the step of every
 // handle is in flight on its own streams before the first result is awaited, so the kernels of the windows fill the SMs
 // side by side and the staging of window k+1 overlaps the device work of window k.  Same results as n qnb_nonbond calls.
+// Host-side workers of qnb_nonbond_batch: staging x into pinned memory, launching the graph and adding the gradient out
+// are ~25 us of host work per window (C2), serial in the caller's thread they would bound a batch of 7 at ~180 us.  A
+// small persistent pool (created on first use) shares the windows; the calling thread works too.
+namespace {
+struct BatchPool {
+    std::mutex mu;
+    std::condition_variable cv_go, cv_done;
+    std::vector<std::thread> th;
+    std::function<void(int)> job;   // job(worker index 1..nworker)
+    unsigned long long gen = 0;
+    int pending = 0;
+    bool stop = false;
+    ~BatchPool() {
+        { std::lock_guard<std::mutex> l(mu); stop = true; gen++; }
+        cv_go.notify_all();
+        for (auto &t : th) t.join();
+    }
+    void ensure(int nworker) {
+        while ((int)th.size() < nworker) {
+            const int id = (int)th.size() + 1;
+            const unsigned long long start_gen = gen;
+            th.emplace_back([this, id, start_gen] {
+                unsigned long long seen = start_gen;
+                for (;;) {
+                    std::function<void(int)> f;
+                    {
+                        std::unique_lock<std::mutex> l(mu);
+                        cv_go.wait(l, [&] { return gen != seen; });
+                        seen = gen;
+                        if (stop) return;
+                        f = job;
+                    }
+                    if (f) f(id);
+                    { std::lock_guard<std::mutex> l(mu); if (--pending == 0) cv_done.notify_one(); }
+                }
+            });
+        }
+    }
+    // run f(0) here and f(1..nworker) on the pool; returns when all are done
+    void run(int nworker, const std::function<void(int)> &f) {
+        ensure(nworker);
+        { std::lock_guard<std::mutex> l(mu); job = [f, nworker](int id) { if (id <= nworker) f(id); }; pending = (int)th.size(); gen++; }
+        cv_go.notify_all();
+        f(0);
+        std::unique_lock<std::mutex> l(mu);
+        cv_done.wait(l, [&] { return pending == 0; });
+    }
+};
+BatchPool g_pool;
+std::mutex g_pool_use;
+}  // namespace
+
 int qnb_nonbond_batch(int n, qnb_handle *const *hs, const double *const *x, const double *const *lambda, int flags,
                       double *const *d, double *const *E_out, double *const *EQ_out) {
     if (n < 0 || (n > 0 && (!hs || !x || !lambda || !d || !E_out || !EQ_out))) return fail("qnb_nonbond_batch: null argument");
@@ -1304,14 +1395,25 @@ int qnb_nonbond_batch(int n, qnb_handle *const *hs, const double *const *x, cons
         if (!hs[k]->lists_built) return fail("qnb_nonbond_batch: pair lists of system %d have not been built", k);
         for (int j = 0; j < k; j++) if (hs[j] == hs[k]) return fail("qnb_nonbond_batch: handle %d given twice", k);
     }
-    int started = 0, rc = 0;
-    for (; started < n; started++)
-        if (nonbond_begin(hs[started], x[started], lambda[started], flags)) { rc = 1; break; }
-    const std::string err = rc ? g_err : std::string();
-    for (int k = 0; k < started; k++)
-        if (nonbond_end(hs[k], d[k], E_out[k], EQ_out[k]) && !rc) rc = 1;
-    if (!err.empty()) g_err = err;
-    return rc;
+    static const int max_workers = [] { const char *e = getenv("QNB_BATCH_THREADS"); return e ? std::max(1, atoi(e)) : 4; }();
+    const int nw = std::max(1, std::min(max_workers, n));   // threads incl. the caller
+    std::vector<int> rc(nw, 0);
+    std::vector<std::string> err(nw);
+    // thread w takes windows w, w + nw, ...: all of its steps are in flight before it waits for the first result
+    auto work = [&](int w) {
+        int started = 0;
+        for (int k = w; k < n; k += nw, started++)
+            if (nonbond_begin(hs[k], x[k], lambda[k], flags)) { rc[w] = 1; err[w] = g_err; break; }
+        for (int k = w, j = 0; j < started; k += nw, j++)
+            if (nonbond_end(hs[k], d[k], E_out[k], EQ_out[k]) && !rc[w]) { rc[w] = 1; err[w] = g_err; }
+    };
+    if (nw == 1) work(0);
+    else {
+        std::lock_guard<std::mutex> use(g_pool_use);
+        g_pool.run(nw - 1, work);
+    }
+    for (int w = 0; w < nw; w++) if (rc[w]) return fail("%s", err[w].c_str());
+    return 0;
 }
 
 int qnb_last_timing(qnb_handle *h, double out[4]) {
@@ -1458,6 +1560,58 @@ int qnb_comm_init(qnb_handle *h, int rank, int nranks, const void *id128) {
     int rc = g_nccl.CommInitRank(&h->comm, nranks, id, rank);
     if (rc) return fail("ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
     h->rank = rank; h->nranks = nranks;
+    return 0;
+}
+
+// ---- all-reduce over peer memory (NVLink / NVSwitch): the ranks of one node map each other's arenas through CUDA IPC
+struct IpcBlob { cudaIpcMemHandle_t mem; int32_t device; int32_t pad; uint64_t doubles, lrf_off, ctl_off; };
+static_assert(sizeof(IpcBlob) <= QNB_IPC_BLOB, "IPC blob");
+
+int qnb_comm_ipc_export(qnb_handle *h, void *blob) {
+    if (!h || !blob) return fail("null argument");
+    CU(cudaSetDevice(h->device));
+    IpcBlob b{};
+    CU(cudaIpcGetMemHandle(&b.mem, h->arena));
+    b.device = h->device; b.doubles = h->arena_doubles; b.lrf_off = h->arena_lrf_off; b.ctl_off = h->arena_ctl_off;
+    memset(blob, 0, QNB_IPC_BLOB);
+    memcpy(blob, &b, sizeof b);
+    return 0;
+}
+
+int qnb_comm_ipc_attach(qnb_handle *h, int rank, int nranks, const void *blobs) {
+    if (!h || !blobs) return fail("null argument");
+    if (nranks < 1 || nranks > kMaxPeers || rank < 0 || rank >= nranks) return fail("qnb_comm_ipc_attach: rank %d of %d (at most %d ranks)", rank, nranks, kMaxPeers);
+    CU(cudaSetDevice(h->device));
+    P2PComm c{};
+    c.rank = rank; c.n = nranks; c.ctl_off = h->arena_ctl_off;
+    for (int p = 0; p < nranks; p++) {
+        IpcBlob b;
+        memcpy(&b, (const char *)blobs + (size_t)p * QNB_IPC_BLOB, sizeof b);
+        if (b.doubles != h->arena_doubles || b.lrf_off != h->arena_lrf_off || b.ctl_off != h->arena_ctl_off)
+            return fail("qnb_comm_ipc_attach: rank %d holds a different system (arena layout differs)", p);
+        if (p == rank) { c.base[p] = h->arena; continue; }
+        int can = 0;
+        CU(cudaDeviceCanAccessPeer(&can, h->device, b.device));
+        if (!can) return fail("qnb_comm_ipc_attach: device %d cannot access device %d of rank %d (no NVLink / P2P): use qnb_comm_init (NCCL)", h->device, b.device, p);
+        void *q = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&q, b.mem, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return fail("cudaIpcOpenMemHandle(rank %d): %s", p, cudaGetErrorString(e));
+        h->peer_base[p] = q;
+        c.base[p] = (double *)q;
+    }
+    h->p2p = c;
+    h->rank = rank; h->nranks = nranks;
+    drop_graphs(h);
+    return 0;
+}
+
+int qnb_comm_status(qnb_handle *h) {
+    if (!h) return fail("null handle");
+    if (!p2p_ready(h)) return 0;
+    CU(cudaSetDevice(h->device));
+    unsigned ctl[3] = {0, 0, 0};
+    CU(cudaMemcpy(ctl, h->arena + h->arena_ctl_off, sizeof ctl, cudaMemcpyDeviceToHost));
+    if (ctl[2]) return fail("peer-memory all-reduce: a rank did not arrive at a barrier within 4 s (epoch %u)", ctl[0]);
     return 0;
 }
 
@@ -1627,12 +1781,11 @@ int qnb_bench_kernels(qnb_handle *h, const double *lambda, int flags, int reps, 
 // the all-reduce of [d | E | EQ] alone (gather_nonbond + master sum), on the handle's stream
 int qnb_bench_allreduce(qnb_handle *h, int reps, float *ms_out) {
     if (!h || !ms_out) return fail("null argument");
-    if (!h->comm) return fail("qnb_bench_allreduce: no communicator (qnb_comm_init)");
+    if (!h->comm && !p2p_ready(h)) return fail("qnb_bench_allreduce: no communicator (qnb_comm_init / qnb_comm_ipc_attach)");
     CU(cudaSetDevice(h->device));
     for (int k = 0; k < reps + 2; k++) {
         if (k == 2) CU(cudaEventRecord(h->ev0, h->st));
-        int rc = g_nccl.AllReduce(h->out.p, h->out.p, h->nout, kNcclDouble, kNcclSum, h->comm, h->st);
-        if (rc) return fail("ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
+        if (allreduce_arena(h, 0, h->nout, h->st)) return 1;
     }
     CU(cudaEventRecord(h->ev1, h->st));
     CU(cudaEventSynchronize(h->ev1));
@@ -1674,10 +1827,12 @@ int qnb_finalize(qnb_handle *h) {
     h->shk_first.release(); h->shk_ij.release(); h->shk_d2.release(); h->shk_winv.release(); h->shk_x.release();
     h->shk_xx.release(); h->shk_iter.release();
     h->bead_atoms.release(); h->bead_base.release(); h->bead_disp.release(); h->bead_eq.release();
-    h->item_posf.release(); h->item_scr.release();
+    h->item_posf.release(); h->item_scr.release(); h->srcf.release();
     h->upk.release(); h->pk_sw.release(); h->e_cnt.release(); h->e_off.release(); h->rec_i.release(); h->rec_f.release(); h->wT.release(); h->wown.release(); h->wd.release();
     h->pw12.release(); h->ljp.release(); h->pw0.release(); h->ww_pairs.release(); h->pp_pairs.release(); h->pw_pairs.release();
     h->item_pos.release(); h->src.release(); h->cell_unsorted.release(); h->item_nq.release(); h->src_off.release();
+    for (int k = 0; k < kMaxPeers; k++) if (h->peer_base[k]) cudaIpcCloseMemHandle(h->peer_base[k]);
+    if (h->arena) cudaFree(h->arena);
     if (h->hx) cudaFreeHost(h->hx);
     if (h->hout) cudaFreeHost(h->hout);
     if (h->ev0) cudaEventDestroy(h->ev0);

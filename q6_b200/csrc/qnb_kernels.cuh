@@ -102,6 +102,81 @@ struct Cut {
     __host__ __device__ int lrf_all_of(int cls) const { return cls == 0 ? lrf_all[0] : cls == 1 ? lrf_all[1] : lrf_all[2]; }
 };
 
+// ------------------------------------------------------------------ all-reduce over peer memory
+// The ranks of one node (one process per GPU) map each other's arena [out | lrf | control] through CUDA IPC; NVSwitch
+// gives every GPU full bandwidth to every peer, so the sum is ONE kernel per rank: the owner of slice r (1/n of the
+// elements) reads that slice from every rank, adds the n values in rank order and writes the sum back into EVERY
+// rank's buffer -- 2 (n-1)/n of the buffer crosses NVLink per rank, nothing is staged, every rank ends up with
+// bit-identical sums.  Two flag barriers in peer memory bracket it (all partial results complete / all sums delivered and
+// nobody still reading); the epoch lives in device memory, so the kernel can sit in a CUDA graph.
+constexpr int kMaxPeers = 8;
+struct P2PComm {
+    double *base[kMaxPeers];   // arena of every rank as mapped in THIS process (base[rank] = own)
+    size_t ctl_off;            // doubles from the arena base to the control words
+    int rank, n;
+};
+// control words (unsigned) of a rank: [0] epoch, [1] blocks finished, [2] error, [16 + p] "rank p has arrived", [32 + p]
+// "rank p is done"
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// wait until *p >= target (wrap-safe); gives up after ~4 s of GPU clock and flags the error instead of hanging the device
+__device__ __forceinline__ bool spin_until(const unsigned *p, unsigned target, unsigned *err) {
+    const long long t0 = clock64();
+    while ((int)(ld_acquire_sys(p) - target) < 0) {
+        // a barrier that failed once fails fast from then on (qnb_comm_status reports it)
+        if (*(volatile unsigned *)err || clock64() - t0 > 8000000000ll) { atomicExch(err, 1u); return false; }
+        __nanosleep(64);
+    }
+    return true;
+}
+__global__ void __launch_bounds__(256)
+k_p2p_allreduce(P2PComm C, size_t off, size_t count, unsigned *ctl) {
+    const unsigned epoch = ld_acquire_sys(ctl) + 1u;
+    // ---- everybody's partial results are complete (this kernel follows the rank's step kernels in stream order)
+    if (blockIdx.x == 0 && threadIdx.x < C.n) {
+        unsigned *peer = reinterpret_cast<unsigned *>(C.base[threadIdx.x] + C.ctl_off);
+        __threadfence_system();
+        st_release_sys(peer + 16 + C.rank, epoch);
+    }
+    if (threadIdx.x < C.n) spin_until(ctl + 16 + threadIdx.x, epoch, ctl + 2);
+    __syncthreads();
+    // ---- own slice: sum over the ranks in rank order, deliver to every rank (16-byte accesses)
+    const size_t n2 = (count + 1) / 2;                       // double2 elements (the arena parts are padded)
+    const size_t per = (n2 + C.n - 1) / C.n;
+    const size_t lo = per * C.rank, hi = lo + per < n2 ? lo + per : n2;
+    for (size_t i = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (size_t)gridDim.x * blockDim.x) {
+        double2 s = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int p = 0; p < kMaxPeers; p++)
+            if (p < C.n) {
+                const double2 v = reinterpret_cast<const double2 *>(C.base[p] + off)[i];
+                s.x += v.x; s.y += v.y;
+            }
+#pragma unroll
+        for (int p = 0; p < kMaxPeers; p++)
+            if (p < C.n) reinterpret_cast<double2 *>(C.base[p] + off)[i] = s;
+    }
+    // ---- the last block of this rank tells everybody, waits for everybody, and opens the next epoch
+    __threadfence_system();
+    __syncthreads();
+    __shared__ unsigned last;
+    if (threadIdx.x == 0) last = atomicAdd(ctl + 1, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence_system();   // the other blocks' deliveries (fenced before their count) precede the "done" below
+    if (threadIdx.x < C.n) {
+        unsigned *peer = reinterpret_cast<unsigned *>(C.base[threadIdx.x] + C.ctl_off);
+        st_release_sys(peer + 32 + C.rank, epoch);
+        spin_until(ctl + 32 + threadIdx.x, epoch, ctl + 2);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { ctl[1] = 0u; __threadfence(); st_release_sys(ctl, epoch); }
+}
+
 // ------------------------------------------------------------------ small device helpers
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

@@ -134,11 +134,13 @@ __global__ void k_pack_atoms(Dev D, const int *__restrict__ cell_items, const in
 }
 // per list build: LRF source records (x,y,z,q) in packed order
 __global__ void k_pack_sources(const int *__restrict__ npk, const int *__restrict__ pk_atom, const double *__restrict__ x,
-                               const double *__restrict__ crg, double4 *__restrict__ src) {
+                               const double *__restrict__ crg, double4 *__restrict__ src, float4 *__restrict__ srcf) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= *npk) return;   // number of packed atoms, still on the device when this is launched
     const int i = pk_atom[p];
-    src[p] = make_double4(x[3 * i], x[3 * i + 1], x[3 * i + 2], crg[i]);
+    const double4 v = make_double4(x[3 * i], x[3 * i + 1], x[3 * i + 2], crg[i]);
+    src[p] = v;
+    srcf[p] = make_float4((float)v.x, (float)v.y, (float)v.z, (float)v.w);   // phi3 path and rsqrt seed of lrf_atom
 }
 // per step: coordinates in packed order, structure of arrays
 __global__ void k_pack_coords(int npk, const int *__restrict__ pk_atom, const double *__restrict__ x,
@@ -564,7 +566,7 @@ __global__ void k_warp_starts(Dev D, int u0, int n, int tile_atoms, bool new_row
 __global__ void k_chunk_fill(Dev D, int u0, int n, int tile_atoms, const int *__restrict__ counts,
                              const int *__restrict__ row_off, const uint32_t *__restrict__ rows,
                              const int *__restrict__ choff, int2 *__restrict__ cdesc, uint32_t *__restrict__ crow,
-                             const int *__restrict__ pk_atom, uint16_t *__restrict__ cspec, bool mark_kind) {
+                             const int *__restrict__ pk_atom, uint16_t *__restrict__ cspec, bool mark_kind, uint32_t pad_id) {
     const int lane = threadIdx.x & 31;
     const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (k >= n) return;
@@ -580,8 +582,12 @@ __global__ void k_chunk_fill(Dev D, int u0, int n, int tile_atoms, const int *__
                 if (lane == 0) cdesc[c] = make_int2(k, seg | (tile << 8));
                 uint32_t e = (b + lane < m) ? rows[base + b + lane] : 0xffffffffu;
                 // water rows of the pipelined kernel (k_water_rows): bit 30 of EVERY lane names the chunk's kind, so the
-                // gathers of a chunk can be issued from its entries alone; a padding lane is one whose id field is all ones
-                if (mark_kind) e = seg == 0 ? (e & ~kSpecialBit) : (e | kSpecialBit);
+                // loads of a chunk can be issued from its entries alone; a padding lane names the all-zero record kept
+                // behind the last packed atom (pad_id), so that it needs no test before the load
+                if (mark_kind) {
+                    if (e == 0xffffffffu) e = pad_id;
+                    e = seg == 0 ? (e & ~kSpecialBit) : (e | kSpecialBit);
+                }
                 crow[(size_t)c * 32 + lane] = e;
                 if (cspec) {
                     // solute tiles: resolve the special pairs (exclusion lists, 1-4 neighbours, own group) of this
@@ -742,6 +748,57 @@ __constant__ int kLrfExpand[40] = {0, 1, 2, 3,
                                    11, 13, 14, 13, 16, 17, 14, 17, 18,    // n = y
                                    12, 14, 15, 14, 17, 18, 15, 18, 19};   // n = z
 
+// ---- lrf_update of one source atom (nonbondene.f90:656-719) in RAW moments: the traceless combinations the reference
+// adds atom by atom (phi2 = f1 dr dr - f0 I, phi3 = 5 f2 dr dr dr - f2 r^2 (...)) are linear in the sums
+//   m[0] = S q/r            m[1..3] = S f0 dr          m[4..9] = S (f0/r^2) dr dr (xx xy xz yy yz zz)   m[10] = S f0
+//   h[0..9] = S (q/r^7) dr dr dr (xxx xxy xxz xyy xyz xzz yyy yyz yzz zzz)                h[10..12] = S (q/r^5) dr
+// with f0 = q/r^3, so the atom loop is 29 FP64 + 34 FP32 operations instead of 32 + 49 and lrf_finish() forms
+// phi0, phi1 = -m[1..3], phi2 = 3 m[4..9] - m[10] I, phi3 = -15 h[0..9] + {9, 3} h[10..12] once per target.
+// phi0-phi2 FP64 (FP32 phi2 was measured to move E%LRF by 1.1e-6 relative); phi3 enters only the field, as
+// 1/2 dr.phi3.dr with |dr| ~ 1 A against r >= Rc: a (dr/r)^2 ~ 1e-2 correction to phi1, summed in FP32.
+// d: displacement in FP64, f: the same in FP32 (phi3 path and rsqrt seed; its 1e-6 error is cubed away by the Halley step)
+__device__ __forceinline__ void lrf_atom(double (&m)[11], float (&h)[13], double dx, double dy, double dz, double q,
+                                         float fx, float fy, float fz, float qf) {
+    const double r2 = dx * dx + dy * dy + dz * dz;
+    const float rif = rsqrt_fast(fmaf(fx, fx, fmaf(fy, fy, fz * fz)));
+    const double ri = rsqrt_refine(r2, rif), ri2 = ri * ri;
+    const double qri = q * ri, f0 = qri * ri2, f1 = f0 * ri2;
+    m[0] += qri;
+    m[10] += f0;
+    m[1] += dx * f0; m[2] += dy * f0; m[3] += dz * f0;
+    const double tx = f1 * dx, ty = f1 * dy, tz = f1 * dz;
+    m[4] += tx * dx; m[5] += tx * dy; m[6] += tx * dz; m[7] += ty * dy; m[8] += ty * dz; m[9] += tz * dz;
+    const float rif2 = rif * rif, p5 = qf * rif * rif2 * rif2, p7 = p5 * rif2;
+    h[10] += p5 * fx; h[11] += p5 * fy; h[12] += p5 * fz;
+    const float ax = p7 * fx, ay = p7 * fy, az = p7 * fz;
+    const float axx = ax * fx, axy = ax * fy, axz = ax * fz, ayy = ay * fy, ayz = ay * fz, azz = az * fz;
+    h[0] += axx * fx; h[1] += axx * fy; h[2] += axx * fz; h[3] += axy * fy; h[4] += axy * fz; h[5] += axz * fz;
+    h[6] += ayy * fy; h[7] += ayy * fz; h[8] += ayz * fz; h[9] += azz * fz;
+}
+// raw sums (24 values: m[0..10], h[0..12] as doubles) -> the 20 unique moments in kLrfExpand's order
+__device__ __forceinline__ double lrf_finish(const double *raw, int k) {
+    const double *m = raw, *h = raw + 11;
+    if (k == 0) return m[0];
+    if (k <= 3) return -m[k];
+    if (k <= 9) return 3.0 * m[k] - ((k == 4 || k == 7 || k == 9) ? m[10] : 0.0);
+    // phi3, unique index k-10: xxx xxy xxz xyy xyz xzz yyy yyz yzz zzz; trace part -(-3 q/r^5) (...): 3x for aaa, 1x for aab
+    const int u = k - 10;
+    const double t = -15.0 * h[u];
+    switch (u) {
+    case 0: return t + 9.0 * h[10];   // xxx
+    case 1: return t + 3.0 * h[11];   // xxy
+    case 2: return t + 3.0 * h[12];   // xxz
+    case 3: return t + 3.0 * h[10];   // xyy
+    case 4: return t;                 // xyz
+    case 5: return t + 3.0 * h[10];   // xzz
+    case 6: return t + 9.0 * h[11];   // yyy
+    case 7: return t + 3.0 * h[12];   // yyz
+    case 8: return t + 3.0 * h[11];   // yzz
+    default: return t + 9.0 * h[12];  // zzz
+    }
+}
+constexpr int kLrfRaw = 24;
+
 // lrf_update (nonbondene.f90:628-725), gathered per TARGET group: the warp of target unit t sums the
 // contribution of every source atom whose unit pair (t,s) the reference sends through the LRF branch
 // (outside the class cut-off, inside RcLRF, pair owned by this shard).  20 unique moments are
@@ -757,12 +814,13 @@ __global__ void __launch_bounds__(32 * kRowWarps)
 k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x, const double *__restrict__ upos,
                  const int *__restrict__ cell_of, const int *__restrict__ cell_start,
                  const double4 *__restrict__ item_pos, const float4 *__restrict__ item_posf,
-                 const int *__restrict__ src_off, const double4 *__restrict__ src, double *__restrict__ lrf) {
+                 const int *__restrict__ src_off, const double4 *__restrict__ src, const float4 *__restrict__ srcf,
+                 double *__restrict__ lrf) {
     // one block (kRowWarps warps) per target unit; the cell rows inside the LRF reach are dealt to the warps.
     // Candidates are first screened (FP32 distance with a safety band, exact FP64 test inside the band) and the
     // accepted ones compacted into a per-warp queue, so that the expensive accumulation always runs on full warps
     // even when only a few percent of the scanned cells' units lie inside the LRF shell (periodic boxes).
-    __shared__ double red[kRowWarps][20];
+    __shared__ double red[kRowWarps][kLrfRaw];
     __shared__ int queue[kRowWarps][64];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int t = blockIdx.x;
@@ -780,10 +838,12 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
     // phi0, phi1, phi2 in FP64 (FP32 phi2 was measured to move E%LRF by 1.1e-6 relative).  phi3 enters only the field,
     // as 1/2 dr.phi3.dr with |dr| ~ 1 A (atom to group centre) against r >= Rc: a (dr/r)^2 ~ 1e-2 correction to
     // phi1, so it is formed and summed in FP32 (relative error ~1e-6 of itself).
-    double m[10];
-    float h[10];
+    double m[11];
+    float h[13];
 #pragma unroll
-    for (int k = 0; k < 10; k++) { m[k] = 0.0; h[k] = 0.f; }
+    for (int k = 0; k < 11; k++) m[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 13; k++) h[k] = 0.f;
 
     auto accumulate = [&](int idx) {
         // lrf_update(group1 = source unit of item idx, group2 = target): dr = x(i) - cgp_cent(target) - shift
@@ -796,40 +856,13 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
             oy += pshift(ip.y - cy_, D.box[1], D.inv_box[1]);
             oz += pshift(ip.z - cz_, D.box[2], D.inv_box[2]);
         }
+        const float oxf = (float)ox, oyf = (float)oy, ozf = (float)oz;
         const int a0 = src_off[idx], a1 = src_off[idx + 1];
 #pragma unroll 3
         for (int k = a0; k < a1; k++) {
             const double4 sa = src[k];
-            const double dx = sa.x - ox, dy = sa.y - oy, dz = sa.z - oz;
-            const double r2 = dx * dx + dy * dy + dz * dz;
-            const float rif = rsqrt_fast((float)r2);
-            const double ri = rsqrt_refine(r2, rif), ri2 = ri * ri;
-            const double f0 = sa.w * ri * ri2;      // field0 = q/r^3
-            m[0] += sa.w * ri;                      // phi0 += field0*r2
-            m[1] -= dx * f0; m[2] -= dy * f0; m[3] -= dz * f0;
-            // phi2: field1 = 3 field0/r^2; xx xy xz yy yz zz
-            const double f1 = 3.0 * f0 * ri2;
-            const double tx = f1 * dx, ty = f1 * dy, tz = f1 * dz;
-            m[4] += tx * dx - f0; m[5] += tx * dy; m[6] += tx * dz;
-            m[7] += ty * dy - f0; m[8] += ty * dz; m[9] += tz * dz - f0;
-            // phi3 (FP32): field2 = -field1/r^2 = -3 q/r^7; xxx xxy xxz xyy xyz xzz yyy yyz yzz zzz
-            const float fx = (float)dx, fy = (float)dy, fz = (float)dz;
-            const float rif2 = rif * rif;
-            const float f2 = -3.0f * (float)sa.w * rif * rif2 * rif2 * rif2;
-            const float g5 = 5.0f * f2, gr = f2 * (fx * fx + fy * fy + fz * fz);
-            const float ax = g5 * fx, ay = g5 * fy, az = g5 * fz;
-            const float axx = ax * fx, axy = ax * fy, axz = ax * fz, ayy = ay * fy, ayz = ay * fz, azz = az * fz;
-            const float gx = gr * fx, gy = gr * fy, gz = gr * fz;
-            h[0] += axx * fx - 3.0f * gx;
-            h[1] += axx * fy - gy;
-            h[2] += axx * fz - gz;
-            h[3] += axy * fy - gx;
-            h[4] += axy * fz;
-            h[5] += axz * fz - gx;
-            h[6] += ayy * fy - 3.0f * gy;
-            h[7] += ayy * fz - gz;
-            h[8] += ayz * fz - gy;
-            h[9] += azz * fz - 3.0f * gz;
+            const float4 sf = srcf[k];
+            lrf_atom(m, h, sa.x - ox, sa.y - oy, sa.z - oz, sa.w, sf.x - oxf, sf.y - oyf, sf.z - ozf, sf.w);
         }
     };
 
@@ -977,13 +1010,18 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
     if (lane < qn) accumulate(queue[wid][lane]);
     __syncwarp();
 #pragma unroll
-    for (int k = 0; k < 10; k++) {
-        const double a = warp_sum(m[k]), b3 = warp_sum((double)h[k]);
-        if (lane == 0) { red[wid][k] = a; red[wid][10 + k] = b3; }
+    for (int k = 0; k < 11; k++) {
+        const double a = warp_sum(m[k]);
+        if (lane == 0) red[wid][k] = a;
+    }
+#pragma unroll
+    for (int k = 0; k < 13; k++) {
+        const double a = warp_sum((double)h[k]);
+        if (lane == 0) red[wid][11 + k] = a;
     }
     __syncthreads();
-    __shared__ double mm[20];
-    if (threadIdx.x < 20) {
+    __shared__ double mm[kLrfRaw];
+    if (threadIdx.x < kLrfRaw) {
         double a = 0;
 #pragma unroll
         for (int k = 0; k < kRowWarps; k++) a += red[k][threadIdx.x];
@@ -992,7 +1030,7 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
     __syncthreads();
     if (threadIdx.x < 40) {
         // LRF_TYPE order after cgp_cent: phi0, phi1(3), phi2(a)%b (9), phi3(3*(n-1)+j)%k (27) from the unique moments
-        lt[3 + threadIdx.x] = mm[kLrfExpand[threadIdx.x]];
+        lt[3 + threadIdx.x] = lrf_finish(mm, kLrfExpand[threadIdx.x]);
     }
 }
 
@@ -1006,7 +1044,7 @@ constexpr int kLrfTileItems = 64, kLrfTileAtoms = 320;
 __global__ void __launch_bounds__(128)
 k_lrf_allpairs(Dev D, Cut C, const double *__restrict__ x, const double *__restrict__ upos, const double4 *__restrict__ item_pos,
                const float4 *__restrict__ item_posf, const int *__restrict__ src_off, const double4 *__restrict__ src,
-               const double *__restrict__ lrf, double *__restrict__ mom /* [nunit][20] */) {
+               const double *__restrict__ lrf, double *__restrict__ mom /* [nunit][kLrfRaw] raw sums */) {
     __shared__ float4 s_pos[kLrfTileItems];
     __shared__ int s_a0[kLrfTileItems + 1];
     __shared__ double4 s_atom[kLrfTileAtoms];
@@ -1028,10 +1066,12 @@ k_lrf_allpairs(Dev D, Cut C, const double *__restrict__ x, const double *__restr
     const float in_lo_s = lo_of(C.rc2_of(cls_s)), in_hi_s = hi_of(C.rc2_of(cls_s));
     const float in_lo_w = lo_of(C.rc2_of(cls_w)), in_hi_w = hi_of(C.rc2_of(cls_w));
     const float out_lo = lo_of(C.rclrf2), out_hi = hi_of(C.rclrf2);
-    double m[10];
-    float h[10];
+    double m[11];
+    float h[13];
 #pragma unroll
-    for (int k = 0; k < 10; k++) { m[k] = 0.0; h[k] = 0.f; }
+    for (int k = 0; k < 11; k++) m[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 13; k++) h[k] = 0.f;
     // this block's slice of the items
     const int per = (D.nunit + gridDim.y - 1) / gridDim.y;
     const int lo = blockIdx.y * per, hi = min(D.nunit, lo + per);
@@ -1077,57 +1117,31 @@ k_lrf_allpairs(Dev D, Cut C, const double *__restrict__ x, const double *__restr
                 }
                 if (zone != 1) continue;
                 for (int k = s_a0[it]; k < s_a0[it + 1]; k++) {
-                    // lrf_update (nonbondene.f90:656-719), see k_lrf_accumulate
+                    // lrf_update (nonbondene.f90:656-719), see lrf_atom; FP32 displacement from FP32 copies
+                    // (|x| ~ 30 A: 2e-6 A, the phi3 path is FP32 anyway)
                     const double4 sa = s_atom[k];
-                    const double ddx = sa.x - cx_, ddy = sa.y - cy_, ddz = sa.z - cz_;
-                    const double r2 = ddx * ddx + ddy * ddy + ddz * ddz;
-                    // FP32 displacement from FP32 copies (|x| ~ 30 A: 2e-6 A, the phi3 path is FP32 anyway; as the
-                    // rsqrt seed its 1e-6 error is cubed away by the Halley step)
                     const float4 af = s_atomf[k];
-                    const float fx = af.x - cxf, fy = af.y - cyf, fz = af.z - czf;
-                    const float rif = rsqrt_fast(fmaf(fx, fx, fmaf(fy, fy, fz * fz)));
-                    const double ri = rsqrt_refine(r2, rif), ri2 = ri * ri;
-                    const double f0 = sa.w * ri * ri2;
-                    m[0] += sa.w * ri;
-                    m[1] -= ddx * f0; m[2] -= ddy * f0; m[3] -= ddz * f0;
-                    const double f1 = 3.0 * f0 * ri2;
-                    const double tx = f1 * ddx, ty = f1 * ddy, tz = f1 * ddz;
-                    m[4] += tx * ddx - f0; m[5] += tx * ddy; m[6] += tx * ddz;
-                    m[7] += ty * ddy - f0; m[8] += ty * ddz; m[9] += tz * ddz - f0;
-                    const float rif2 = rif * rif;
-                    const float f2 = -3.0f * af.w * rif * rif2 * rif2 * rif2;
-                    const float g5 = 5.0f * f2, gr = f2 * (fx * fx + fy * fy + fz * fz);
-                    const float ax = g5 * fx, ay = g5 * fy, az = g5 * fz;
-                    const float axx = ax * fx, axy = ax * fy, axz = ax * fz, ayy = ay * fy, ayz = ay * fz, azz = az * fz;
-                    const float gx = gr * fx, gy = gr * fy, gz = gr * fz;
-                    h[0] += axx * fx - 3.0f * gx;
-                    h[1] += axx * fy - gy;
-                    h[2] += axx * fz - gz;
-                    h[3] += axy * fy - gx;
-                    h[4] += axy * fz;
-                    h[5] += axz * fz - gx;
-                    h[6] += ayy * fy - 3.0f * gy;
-                    h[7] += ayy * fz - gz;
-                    h[8] += ayz * fz - gy;
-                    h[9] += azz * fz - 3.0f * gz;
+                    lrf_atom(m, h, sa.x - cx_, sa.y - cy_, sa.z - cz_, sa.w, af.x - cxf, af.y - cyf, af.z - czf, af.w);
                 }
             }
         }
         base = tend;
     }
     if (live) {
-        double *mt = mom + (size_t)20 * t;
+        double *mt = mom + (size_t)kLrfRaw * t;
 #pragma unroll
-        for (int k = 0; k < 10; k++) { atomicAdd(&mt[k], m[k]); atomicAdd(&mt[10 + k], (double)h[k]); }
+        for (int k = 0; k < 11; k++) atomicAdd(&mt[k], m[k]);
+#pragma unroll
+        for (int k = 0; k < 13; k++) atomicAdd(&mt[11 + k], (double)h[k]);
     }
 }
-// unique moments -> LRF_TYPE (phi0, phi1(3), phi2(3x3), phi3(9x3)) of the unit's charge group
+// raw sums -> LRF_TYPE (phi0, phi1(3), phi2(3x3), phi3(9x3)) of the unit's charge group
 __global__ void k_lrf_expand(Dev D, const double *__restrict__ mom, double *__restrict__ lrf) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= D.nunit * 40) return;
     const int t = i / 40, k = i - 40 * t;
     if (D.u_excl[t]) return;
-    lrf[(size_t)QNB_LRF_STRIDE * D.u_grp[t] + 3 + k] = mom[(size_t)20 * t + kLrfExpand[k]];
+    lrf[(size_t)QNB_LRF_STRIDE * D.u_grp[t] + 3 + k] = lrf_finish(mom + (size_t)kLrfRaw * t, kLrfExpand[k]);
 }
 
 }  // namespace qnb

@@ -121,15 +121,16 @@ __device__ __forceinline__ f2 len2(f2 dx, f2 dy, f2 dz) { return fma2(dx, dx, fm
 // One warp streams a contiguous range of 32-entry chunks (k_warp_starts); lanes = partners of the row's water.
 //
 // The partners' records are gathers (cell-ordered, so neighbouring lanes hit neighbouring records, but still one L1/L2
-// round trip per chunk): r02c measured 60 % of the stall samples on their first consumers at 20 warps per SM.  They
-// are therefore staged through shared memory with cp.async (LDGSTS), three chunks deep: every lane copies the records
-// of ITS partner of chunk c+2 into its own 48-byte slot while chunk c is computed, so no registers are held by loads
-// in flight and no lane ever reads another lane's slot (no barrier).  The own molecule's record of the next row
-// travels the same way (lanes 0-2, a ring of four slots).  Entries and chunk descriptors are plain coalesced loads, three ahead.
+// round trip per chunk): r02c measured 60 % of the stall samples on their first consumers.  What was tried:
+//  * r02e-r02g: every lane copies its partner's record into its own shared-memory slot with cp.async, three chunks deep.
+//    Latency stalls fell (long scoreboard 7.9 -> 2.6 per issue) but the time only went 63 -> 55 us whatever the occupancy
+//    (4, 5, 6 blocks per SM): a GATHERED cp.async writes its sectors to shared memory as they arrive, ~11 data-pipe
+//    wavefronts per instruction, and l1tex__data_pipe_lsu_wavefronts sat at 81 % of peak;
+//  * now: the records of chunk c+1 are loaded into registers (three LDG.128) while chunk c is computed -- two register
+//    sets that swap roles in a loop unrolled twice -- entries three chunks ahead, and cp.async only where it is cheap:
+//    the own molecule's record of the next row (lanes 0-2, a ring of four slots).
 constexpr uint32_t kKindBit = kSpecialBit;   // water-row chunk entries: set in every lane of a B chunk (k_chunk_fill)
-constexpr int kWStages = 3;
 __device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-// 16-byte asynchronous copy global -> shared; nbytes = 0 fills the destination with zeros (padding lanes)
 __device__ __forceinline__ void cp_async16(unsigned dst, const void *gsrc, unsigned nbytes) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gsrc), "r"(nbytes) : "memory");
 }
@@ -137,7 +138,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 // the chunk entries stream from DRAM (21 MB per step on the 98 k-atom box): their lines are pulled into L2 kWPrefetch
-// chunks ahead, so that the register prefetch one step ahead only has to cover an L2 hit
+// chunks ahead, so that the register prefetch only has to cover an L2 hit
 constexpr int kWPrefetch = 10;
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ float4 lds128(unsigned addr) {
@@ -145,22 +146,21 @@ __device__ __forceinline__ float4 lds128(unsigned addr) {
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
 }
+struct WRec { float4 a, b, c; };   // a partner's record: water {wT[p], wT[p+1], wT[p+2]}, solute atom {rec_i[p], rec_f[p], -}
 
-// MINB: resident blocks per SM the register allocation aims at (5: 95 registers, 6: 79; QNB_WROWS_MINB selects at run time)
+// MINB: resident blocks per SM the register allocation aims at (QNB_WROWS_MINB selects at run time)
 template <bool SPC, int MINB>
 __global__ void __launch_bounds__(128, MINB)
 k_water_rows(RowPar P, const int4 *__restrict__ rec_i, const float4 *__restrict__ rec_f, const float4 *__restrict__ wT,
              const float4 *__restrict__ own, const float2 *__restrict__ pw0, const float4 *__restrict__ pw12,
              const int *__restrict__ wstart, const int2 *__restrict__ cdesc, const uint32_t *__restrict__ crow,
              int i0_water /* nat_solute */, double *__restrict__ grad) {
-    __shared__ float4 S[4][kWStages][3][32];   // [warp][stage][record part][lane]
     __shared__ float4 Own[4][4][4];            // [warp][slot][record part]; the issue side runs at most three row changes ahead
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int c0 = wstart[gw], c1 = wstart[gw + 1];
     if (c0 >= c1) return;
-    const unsigned sS = smem_addr(&S[wib][0][0][lane]), sOwn = smem_addr(&Own[wib][0][0]);
-    constexpr unsigned kPart = 32 * 16, kStage = 3 * kPart;
+    const unsigned sOwn = smem_addr(&Own[wib][0][0]);
     int cur_w = -1;
     int Pix = 0, Piy = 0, Piz = 0;
     f2 nSx = mk2(0, 0), nSy = nSx, nSz = nSx;                 // minus the own hydrogens' offsets {s1, s2}
@@ -179,34 +179,40 @@ k_water_rows(RowPar P, const int4 *__restrict__ rec_i, const float4 *__restrict_
         if (slot >= 0) atomicAdd(&grad[3 * (size_t)(i0_water + 3 * cur_w) + slot], (double)mine);
     };
     const int *__restrict__ cunit = reinterpret_cast<const int *>(cdesc);
-    // Pipeline state.  e2/u2: entry and unit of the chunk whose gathers are issued next (c+2), e3/u3: those of c+3, in
-    // flight; up: unit of chunk c+1.  kinds/rows: one bit per chunk in flight (bit k = chunk c+k): B chunk / first chunk
-    // of a row, so that the compute side needs neither the entries nor the descriptors again.
-    uint32_t e2, e3 = 0xffffffffu;
-    int u2, u3 = -1, up;
+    // Pipeline state.  e1: entry of chunk c+1 (its records are loaded while chunk c is computed); e2, e3: entries of
+    // c+2, c+3 in flight; u1, u2, u3: units of c+1, c+2, c+3.  kinds/rows: one bit per chunk ahead (bit k = chunk c+k):
+    // B chunk / first chunk of a row.
+    uint32_t e1, e2, e3 = 0xffffffffu;
+    int u1, u2, u3 = -1;
     unsigned kinds = 0, rows = 0, islot = 0, cslot = 0;
     int ie = (c0 + 3) * 32 + lane;   // entry index of chunk c+3
-    auto issue = [&](int cc, uint32_t e, int u, int uprev, unsigned dst, unsigned bit) {
-        if (cc < c1) {
-            const bool valid = (e & kIdMask) != kIdMask;
-            const int p = valid ? (int)(e & kIdMask) : 0;
-            const unsigned nb = valid ? 16u : 0u;
-            if (!__any_sync(kFull, (e & kKindBit) != 0)) {
-                const float4 *src = wT + p;
-                cp_async16(dst, src, nb); cp_async16(dst + kPart, src + 1, nb); cp_async16(dst + 2 * kPart, src + 2, nb);
-            } else {
-                cp_async16(dst, rec_i + p, nb); cp_async16(dst + kPart, rec_f + p, nb);
-                kinds |= bit;
-            }
-            if (u != uprev) {
-                if (lane < 3) cp_async16(sOwn + islot * 64 + lane * 16, own + 3 * (size_t)u + lane, 16u);
-                islot = (islot + 1) & 3;
-                rows |= bit;
-            }
+    // records of the partner named by entry e; a padding lane names the all-zero record behind the last packed atom
+    // (b.y / a.w mark real records), so the loads need no test
+    auto load_rec = [&](uint32_t e, unsigned bit) -> WRec {
+        WRec r;
+        const int p = (int)(e & kIdMask);
+        if (!__any_sync(kFull, (e & kKindBit) != 0)) {
+            const float4 *src = wT + p;
+            r.a = src[0]; r.b = src[1]; r.c = src[2];
+        } else {
+            const int4 ri = rec_i[p];
+            r.a = make_float4(__int_as_float(ri.x), __int_as_float(ri.y), __int_as_float(ri.z), __int_as_float(ri.w));
+            r.b = rec_f[p];
+            r.c = r.b;
+            kinds |= bit;
+        }
+        return r;
+    };
+    // own record of the row that starts with chunk cc (unit u, previous chunk's unit uprev): lanes 0-2, asynchronous
+    auto own_prefetch = [&](int cc, int u, int uprev, unsigned bit) {
+        if (cc < c1 && u != uprev) {
+            if (lane < 3) cp_async16(sOwn + islot * 64 + lane * 16, own + 3 * (size_t)u + lane, 16u);
+            islot = (islot + 1) & 3;
+            rows |= bit;
         }
         cp_async_commit();
     };
-    auto compute = [&](unsigned src) {
+    auto compute = [&](const WRec &R) {
         cp_async_wait<2>();
         if (rows & 1u) {
             flush();
@@ -221,10 +227,10 @@ k_water_rows(RowPar P, const int4 *__restrict__ rec_i, const float4 *__restrict_
             G12x = G12y = G12z = G21x = G21y = G21z = G0x = G0y = G0z = mk2(0.f, 0.f);
             g0x = g0y = g0z = 0.f;
         }
-        const float4 r0 = lds128(src), r1 = lds128(src + kPart);
+        const float4 r0 = R.a, r1 = R.b;
         if (!(kinds & 1u)) {
-            const float4 r2 = lds128(src + 2 * kPart);
-            // vector from the own oxygen to the partner's; a padding lane (zero-filled record) is sent to 1e18 A, where
+            const float4 r2 = R.c;
+            // vector from the own oxygen to the partner's; a padding lane (zero record) is sent to 1e18 A, where
             // every r^-3 and r^-6 below flushes to zero
             float Rx = (float)(__float_as_int(r0.x) - Pix) * P.scale[0];
             const float Ry = (float)(__float_as_int(r0.y) - Piy) * P.scale[1], Rz = (float)(__float_as_int(r1.x) - Piz) * P.scale[2];
@@ -268,33 +274,34 @@ k_water_rows(RowPar P, const int4 *__restrict__ rec_i, const float4 *__restrict_
             g0x = fmaf(ex, c0q, g0x); g0y = fmaf(ey, c0q, g0y); g0z = fmaf(ez, c0q, g0z);
         }
     };
+    WRec RA, RB;
     {
         const uint32_t e0 = crow[(size_t)c0 * 32 + lane];
-        const uint32_t e1 = c0 + 1 < c1 ? crow[(size_t)(c0 + 1) * 32 + lane] : 0xffffffffu;
+        e1 = c0 + 1 < c1 ? crow[(size_t)(c0 + 1) * 32 + lane] : 0xffffffffu;
         e2 = c0 + 2 < c1 ? crow[(size_t)(c0 + 2) * 32 + lane] : 0xffffffffu;
-        const int u0 = cunit[2 * (size_t)c0], u1 = c0 + 1 < c1 ? cunit[2 * (size_t)(c0 + 1)] : -1;
+        const int u0 = cunit[2 * (size_t)c0];
+        u1 = c0 + 1 < c1 ? cunit[2 * (size_t)(c0 + 1)] : -1;
         u2 = c0 + 2 < c1 ? cunit[2 * (size_t)(c0 + 2)] : -1;
-        issue(c0, e0, u0, -1, sS, 1u);
-        issue(c0 + 1, e1, u1, u0, sS + kStage, 2u);
-        up = u1;
+        own_prefetch(c0, u0, -1, 1u);
+        own_prefetch(c0 + 1, u1, u0, 2u);
+        RA = load_rec(e0, 1u);
     }
     int c = c0;
-    // one step: prefetch entry/unit of chunk c+3, issue the gathers of chunk c+2 (stage SI), compute chunk c (stage SC)
-#define QNB_WSTEP(SC, SI)                                                              \
-    {                                                                                  \
-        if (c + 3 < c1) { e3 = crow[ie]; u3 = cunit[2 * (size_t)(c + 3)]; }             \
-        if (lane == 0 && c + kWPrefetch < c1) prefetch_l2(crow + (size_t)(c + kWPrefetch) * 32);  \
-        if (lane == 1 && c + 2 * kWPrefetch < c1) prefetch_l2(cunit + 2 * (size_t)(c + 2 * kWPrefetch)); \
-        issue(c + 2, e2, u2, up, sS + (SI) * kStage, 4u);                               \
-        compute(sS + (SC) * kStage);                                                   \
-        kinds >>= 1; rows >>= 1;                                                       \
-        up = u2; e2 = e3; u2 = u3; ie += 32;                                           \
-        if (++c >= c1) break;                                                          \
+    // one step: records of chunk c+1 into NXT, entry/unit of chunk c+3, own record of chunk c+2's row, compute chunk c
+#define QNB_WSTEP(CUR, NXT, PF)                                                                           \
+    {                                                                                                   \
+        if (c + 1 < c1) NXT = load_rec(e1, 2u);                                                         \
+        if (c + 3 < c1) { e3 = crow[ie]; u3 = cunit[2 * (size_t)(c + 3)]; }                             \
+        if (PF && lane == 0 && c + kWPrefetch < c1) { prefetch_l2(crow + (size_t)(c + kWPrefetch) * 32); prefetch_l2(crow + (size_t)(c + kWPrefetch) * 32 + 32); } \
+        own_prefetch(c + 2, u2, u1, 4u);                                                                \
+        compute(CUR);                                                                                   \
+        kinds >>= 1; rows >>= 1;                                                                        \
+        e1 = e2; e2 = e3; u1 = u2; u2 = u3; ie += 32;                                                   \
+        if (++c >= c1) break;                                                                           \
     }
     for (;;) {
-        QNB_WSTEP(0, 2)
-        QNB_WSTEP(1, 0)
-        QNB_WSTEP(2, 1)
+        QNB_WSTEP(RA, RB, true)
+        QNB_WSTEP(RB, RA, false)
     }
 #undef QNB_WSTEP
     flush();
@@ -471,40 +478,20 @@ k_pair_energy(EnergyPar P, int n_ww, const int2 *__restrict__ ww_pairs, int n_pp
         const bool classes = P.spc && P.wwQ[1] == P.wwQ[2] && P.wwQ[1] == P.wwQ[3] && P.wwQ[1] == P.wwQ[6] && P.wwQ[4] == P.wwQ[5] &&
                              P.wwQ[4] == P.wwQ[7] && P.wwQ[4] == P.wwQ[8];
         double s1[3] = {0, 0, 0}, s2[3] = {0, 0, 0};
-        // Two dependent gathers per pair (its index, then 160 bytes of sites) against ~300 cycles of FP64 work: the
-        // partner's sites of the thread's NEXT pair are copied to shared memory with cp.async while the current pair is
-        // computed (the own molecule is shared by neighbouring threads of the flat list and stays an L1-hit load), and
-        // the pair index is read two pairs ahead.
-        __shared__ double2 Wst[2][5][128];
-        const unsigned sW = smem_addr(&Wst[0][0][threadIdx.x]);
-        constexpr unsigned kWPart = 128 * 16, kWStage = 5 * kWPart;
-        auto stage_partner = [&](int pj, unsigned dst) {
-            const double2 *src = wd + 2 * (size_t)pj;
-#pragma unroll
-            for (int k = 0; k < 5; k++) cp_async16(dst + k * kWPart, src + k, 16u);
-        };
-        int2 pr = make_int2(0, 0), pr_next = make_int2(0, 0);
-        if (tid < n_ww) { pr = ww_pairs[tid]; stage_partner(pr.y, sW); }
-        cp_async_commit();
-        if (tid + nthr < n_ww) pr_next = ww_pairs[tid + nthr];
-        unsigned st = 0;
         for (int t = tid; t < n_ww; t += nthr) {
-            const int2 pr_nn = (t + 2 * nthr < n_ww) ? ww_pairs[t + 2 * nthr] : make_int2(0, 0);
-            if (t + nthr < n_ww) stage_partner(pr_next.y, sW + (st ^ 1u) * kWStage);
-            cp_async_commit();
+            const int2 pr = ww_pairs[t];
             double xi[3][3], xj[3][3];
             {
-                const double2 *wi = wd + 2 * (size_t)pr.x;
+                // (staging the partner's sites through shared memory with cp.async was measured slower, r02h: 64 vs 43 us
+                // on the 98 k-atom box -- a gathered cp.async costs ~11 L1 data-pipe wavefronts per instruction)
+                const double2 *wi = wd + 2 * (size_t)pr.x, *wj = wd + 2 * (size_t)pr.y;
                 const double2 a0 = wi[0], a1 = wi[1], a2 = wi[2], a3 = wi[3], a4 = wi[4];
-                cp_async_wait<1>();
-                const double2 *wj = &Wst[st][0][threadIdx.x];
-                const double2 b0 = wj[0], b1 = wj[128], b2 = wj[256], b3 = wj[384], b4 = wj[512];
+                const double2 b0 = wj[0], b1 = wj[1], b2 = wj[2], b3 = wj[3], b4 = wj[4];
                 xi[0][0] = a0.x; xi[0][1] = a0.y; xi[0][2] = a1.x; xi[1][0] = a1.y; xi[1][1] = a2.x; xi[1][2] = a2.y;
                 xi[2][0] = a3.x; xi[2][1] = a3.y; xi[2][2] = a4.x;
                 xj[0][0] = b0.x; xj[0][1] = b0.y; xj[0][2] = b1.x; xj[1][0] = b1.y; xj[1][1] = b2.x; xj[1][2] = b2.y;
                 xj[2][0] = b3.x; xj[2][1] = b3.y; xj[2][2] = b4.x;
             }
-            pr = pr_next; pr_next = pr_nn; st ^= 1u;
             if (PBC) {
                 // one shift per molecule pair from the O-O vector (nonbond_ww_spc_box L6016-6017, nonbond_ww_box); rint
                 // instead of nint: they differ only for a pair exactly half a box apart, which no list holds

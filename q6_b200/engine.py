@@ -67,6 +67,7 @@ def wat_shells(xwcent, rwat, fk_wsphere=60.0, Dwmz=None, awmz=None, Tfree=300.0,
     return p
 LIST_PP, LIST_PW, LIST_WW, LIST_QP, LIST_QW, LIST_QQ, LIST_QQP = range(7)
 LRF_STRIDE = 43
+IPC_BLOB = 128
 E_COUNT = 7
 EQ_STRIDE = 6
 E_NAMES = ("pp.el", "pp.vdw", "pw.el", "pw.vdw", "ww.el", "ww.vdw", "LRF")
@@ -145,6 +146,12 @@ def load_library(path: str = LIB_PATH):
     lib.qnb_comm_unique_id.argtypes = [C.c_void_p]
     lib.qnb_comm_init.restype = C.c_int
     lib.qnb_comm_init.argtypes = [H, C.c_int, C.c_int, C.c_void_p]
+    lib.qnb_comm_ipc_export.restype = C.c_int
+    lib.qnb_comm_ipc_export.argtypes = [H, C.c_void_p]
+    lib.qnb_comm_status.restype = C.c_int
+    lib.qnb_comm_status.argtypes = [H]
+    lib.qnb_comm_ipc_attach.restype = C.c_int
+    lib.qnb_comm_ipc_attach.argtypes = [H, C.c_int, C.c_int, C.c_void_p]
     lib.qnb_bench_nonbond.restype = C.c_int
     lib.qnb_bench_nonbond.argtypes = [H, _PD, C.c_int, C.c_int, C.c_int, _PF]
     lib.qnb_bench_build_lists.restype = C.c_int
@@ -358,6 +365,46 @@ class Qnb:
 
     def comm_init(self, rank: int, nranks: int, uid: bytes):
         self._check(self.lib.qnb_comm_init(self.h, rank, nranks, C.c_char_p(uid)))
+
+    def ipc_export(self) -> bytes:
+        """Descriptor of this rank's device buffers for the peer-memory all-reduce (qnb_comm_ipc_export)."""
+        buf = C.create_string_buffer(IPC_BLOB)
+        self._check(self.lib.qnb_comm_ipc_export(self.h, buf))
+        return buf.raw
+
+    def ipc_attach(self, rank: int, nranks: int, blobs):
+        """Map the buffers of all ranks (their ipc_export() blobs, by rank): sums go over peer memory from now on."""
+        raw = b"".join(blobs)
+        assert len(raw) == nranks * IPC_BLOB
+        self._check(self.lib.qnb_comm_ipc_attach(self.h, rank, nranks, C.c_char_p(raw)))
+
+    def comm_status(self):
+        self._check(self.lib.qnb_comm_status(self.h))
+
+    def comm_connect(self, rank: int, nranks: int, dist, mode: str = "auto"):
+        """What the host does once per run: exchange the descriptors (or the NCCL id) over its own process group
+        (MPI_Allgather / MPI_Bcast in the Fortran host, torch.distributed here).  mode: 'p2p' (peer memory), 'nccl',
+        'auto' (peer memory when the GPUs can reach each other, else NCCL).  Returns the mode in use."""
+        if mode in ("p2p", "auto"):
+            blobs = [None] * nranks
+            dist.all_gather_object(blobs, self.ipc_export())
+            try:
+                self.ipc_attach(rank, nranks, blobs)
+                ok = 1
+            except QnbError:
+                if mode == "p2p":
+                    raise
+                ok = 0
+            oks = [None] * nranks
+            dist.all_gather_object(oks, ok)
+            if all(oks):
+                return "p2p"
+            if mode == "p2p":
+                raise QnbError("peer-memory attach failed on another rank")
+        uid = [self.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        self.comm_init(rank, nranks, uid[0])
+        return "nccl"
 
     # -- measurement
     def bench_nonbond(self, lambdas, steps: int, md=True, qq=True, flush_l2=False, energies=True, restraints=False) -> float:

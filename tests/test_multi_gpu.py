@@ -11,7 +11,7 @@ import common
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, q_path, out_path, cuts, lam, shard_rows=False):
+def _worker(rank, world, port, q_path, out_path, cuts, lam, shard_rows=False, comm="nccl"):
     if not shard_rows:
         os.environ["QNB_SHARD_PAIRS"] = "1"     # read by qnb_init: the reference's pair partition instead of the row partition
     import torch
@@ -22,11 +22,14 @@ def _worker(rank, world, port, q_path, out_path, cuts, lam, shard_rows=False):
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     q = QSystem.load(q_path)
     g = Qnb(shard_system(q, rank, world), device=rank)
-    uid = [g.unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(uid, src=0)          # MPI_Bcast of the 128-byte id in the Fortran host
-    g.comm_init(rank, world, uid[0])
+    # MPI_Bcast of the 128-byte NCCL id / MPI_Allgather of the IPC descriptors in the Fortran host
+    assert g.comm_connect(rank, world, dist, comm) == comm
     counts = g.make_pair_lists(q.xtop, **cuts)
     d, E, EQ = g.pot_energy_nonbonds(q.xtop, lam)
+    for _ in range(3):      # the step's graph (it holds the peer-memory all-reduce) is replayed: same sums every time
+        d2, E2, _ = g.pot_energy_nonbonds(q.xtop, lam)
+        assert np.allclose(d2, d, rtol=1e-9, atol=1e-9) and np.allclose(E2, E, rtol=1e-9, atol=1e-9)
+    g.comm_status()
     cnt = torch.from_numpy(counts.copy())
     dist.all_reduce(cnt)
     np.savez(out_path + f".{rank}.npz", d=d, E=E, EQ=EQ, cnt=cnt.numpy(), lrf=g.export_lrf())
@@ -34,9 +37,10 @@ def _worker(rank, world, port, q_path, out_path, cuts, lam, shard_rows=False):
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("comm", ["nccl", "p2p"])
 @pytest.mark.parametrize("shard_rows", [False, True], ids=["pair_partition", "row_partition"])
 @pytest.mark.parametrize("case", ["sphere_q", "water_box"])
-def test_sharded_allreduce_matches_oracle(case, shard_rows, tmp_path):
+def test_sharded_allreduce_matches_oracle(case, shard_rows, comm, tmp_path):
     import torch
     import torch.multiprocessing as mp
     from oracle.pyoracle import Oracle
@@ -54,8 +58,8 @@ def test_sharded_allreduce_matches_oracle(case, shard_rows, tmp_path):
     q_path, out_path = str(tmp_path / "q.npz"), str(tmp_path / "out")
     q.save(q_path)
     port = 29600 + (os.getpid() % 2000)
-    port += 7 if shard_rows else 0
-    mp.spawn(_worker, args=(world, port, q_path, out_path, cuts, lam, shard_rows), nprocs=world, join=True)
+    port += (7 if shard_rows else 0) + (13 if comm == "p2p" else 0)
+    mp.spawn(_worker, args=(world, port, q_path, out_path, cuts, lam, shard_rows, comm), nprocs=world, join=True)
     o = Oracle(q)
     counts = o.make_pair_lists(q.xtop, **cuts)
     d, E, EQ = o.pot_energy_nonbonds(q.xtop, lam)
