@@ -240,6 +240,9 @@ def timed_md(job, g, lam, steps, repeats):
 
 def timed_e2e(job, g, q, x, lam, cuts, steps, repeats):
     d = np.zeros((q.natom, 3))
+    # what the Fortran host does once at set-up for its module arrays x and d (qnb_register_host_buffers)
+    g.release_host_buffers()
+    g.register_host_buffers(x.reshape(-1), d.reshape(-1))
     out = []
     for _ in range(repeats):
         job.barrier()
@@ -247,8 +250,8 @@ def timed_e2e(job, g, q, x, lam, cuts, steps, repeats):
         for k in range(steps):
             if k % NBCYCLE == 0:
                 g.make_pair_lists(x, **cuts, counts=False)
-            d[:] = 0
-            g.pot_energy_nonbonds(x, lam, d=d)
+            d[:] = 0                                           # d(:) = zero, potene.f90:109
+            g.pot_energy_nonbonds(x, lam, d=d, d_is_zero=True)
         job.barrier()
         out.append(job.reduce(time.perf_counter() - t0))
     return out
@@ -264,13 +267,19 @@ def batched_windows(job, q, cuts, lam, nwin, steps, warmup, npairs, flop_step, f
     xs = [q.xtop + rng.normal(0.0, 0.01, q.xtop.shape) for _ in range(nwin)]
     lams = [lam for _ in range(nwin)]
 
+    tb = [0.0, 0]
+
     def run(n):
         for k in range(n):
             if k % NBCYCLE == 0:
+                t0 = time.perf_counter()
                 b.make_pair_lists(xs, **cuts)
+                tb[0] += time.perf_counter() - t0
+                tb[1] += 1
             b.pot_energy_nonbonds(xs if k == 0 else None, lams if k == 0 else None)
 
     run(max(warmup, NBCYCLE + 1))
+    tb[0], tb[1] = 0.0, 0
     times = []
     for _ in range(3):
         job.barrier()
@@ -278,6 +287,7 @@ def batched_windows(job, q, cuts, lam, nwin, steps, warmup, npairs, flop_step, f
         run(steps)
         job.barrier()
         times.append(job.reduce(time.perf_counter() - t0))
+    host = b.last_timing()
     for g in hs:
         g.close()
     t = float(np.median(times)) / steps          # seconds per batched step (nwin windows advance one step each)
@@ -286,7 +296,8 @@ def batched_windows(job, q, cuts, lam, nwin, steps, warmup, npairs, flop_step, f
             "value": agg, "unit": "pairs/s", "steps_per_s": job.world * nwin / t,
             "fep_windows_per_hour": 3600.0 * job.world * nwin / (STEPS_PER_WINDOW * t),
             "roofline_frac_fp32_e2e": nwin * flop_step / t / 1e12 / fp32_peak,
-            "spread_s": spread(times),
+            "spread_s": spread(times), "list_build_ms_per_batched_call": tb[0] / max(tb[1], 1) * 1e3,
+            "host_breakdown_last_call_us": {k: round(v * 1e6, 1) for k, v in host.items()},
             "note": "qnb_build_lists_batch + qnb_nonbond_batch: one C-ABI call per step for all windows of the GPU, host "
                     f"buffers, own coordinates per window, list build every {NBCYCLE} steps; roofline_frac = algorithmic "
                     "flop of all step kernels of all windows / wall time / FP32 peak"}
@@ -304,8 +315,12 @@ def fep_farm(job, steps_per_window, batch):
     hs = [Qnb(q, device=job.dev) for _ in range(nb)]
     rng = np.random.default_rng(100 + job.rank)
 
+    batches = {}
+
     def advance(ws, nsteps):
-        b = QnbBatch(hs[:len(ws)])
+        if len(ws) not in batches:
+            batches[len(ws)] = QnbBatch(hs[:len(ws)])
+        b = batches[len(ws)]
         xs = [q.xtop + rng.normal(0.0, 0.01, q.xtop.shape) for _ in ws]
         lams = [np.array([1.0 - 0.02 * w, 0.02 * w]) for w in ws]
         for k in range(nsteps):

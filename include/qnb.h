@@ -47,6 +47,10 @@ extern "C" {
  * energies of this step -- md.f90 reads E only when mod(istep, iout_cycle / iene_cycle / itemp_cycle) == 0 -- so the
  * row kernels skip their FP64 energy code.  E_out[pp,pw,ww] return 0; gradient, LRF and every Q term are unchanged. */
 #define QNB_FLAG_NO_ENERGY 4
+/* d is zero on entry -- pot_energy clears it right before the nonbonded terms (d(:) = zero, potene.f90:109; they are the
+ * first contribution) -- so the gradient may be written instead of added: with a registered d
+ * (qnb_register_host_buffers) the result is copied straight into it, no read of d and no host loop. */
+#define QNB_FLAG_D_IS_ZERO 8
 
 /* which list for qnb_list_count / qnb_export_list */
 #define QNB_LIST_PP 0  /* nbpp  (globals.f90:415) */
@@ -262,6 +266,16 @@ int qnb_build_lists(qnb_handle *h, const double *x, double Rq, double Rcq2, doub
  */
 int qnb_nonbond(qnb_handle *h, const double *x, const double *lambda, int flags, double *d,
                 double *E_out, double *EQ_out);
+/*
+ * Optional, once after qnb_init: page-lock (cudaHostRegister) the host's coordinate and gradient arrays -- Q6's x and d are
+ * module arrays that live as long as the run (md.f90) -- so that qnb_nonbond / qnb_nonbond_batch calls made with exactly
+ * these addresses upload x without a staging copy and let the device add the gradient into d (no host loop, no second
+ * copy).  Calls with other addresses keep staging through the library's own pinned buffers.  Either pointer may be NULL.
+ * The arrays stay registered until qnb_finalize; a host that frees or reallocates them earlier releases them first.
+ * QNB_NO_HOST_REGISTER=1 in the environment turns both calls into no-ops.
+ */
+int qnb_register_host_buffers(qnb_handle *h, const double *x, double *d);
+int qnb_release_host_buffers(qnb_handle *h);
 
 /*
  * Several independent systems of one process -- FEP lambda windows (tests/exclude_tests/run_excl_test.sh:92-125 runs 51
@@ -323,6 +337,9 @@ int qnb_bench_peak(int device, int which, float *tflops_out);
  * names_out: '\n'-separated list; returns number of kernels. */
 int qnb_bench_kernels(qnb_handle *h, const double *lambda, int flags, int reps, int flush_l2,
                       char *names_out, int names_cap, float *ms_out, int ms_cap);
+/* Host seconds of the last qnb_nonbond_batch in the calling thread: issuing (staging + graph launches), waiting for the
+ * device, adding the gradients out. */
+int qnb_bench_last_batch_timing(double out[3]);
 /* ms per all-reduce of [d | E | EQ] alone (sharded handles; the collective that replaces gather_nonbond). */
 int qnb_bench_allreduce(qnb_handle *h, int reps, float *ms_out);
 /* Kernel launches issued by this handle since creation. */

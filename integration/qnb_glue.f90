@@ -137,6 +137,9 @@ subroutine qnb_setup
   s%is_master = merge(1, 0, nodeid == 0)
 
   if (qnb_init(s, mod(nodeid, ngpu), qnb_handle) /= 0) call die('qnb_init: '//qnb_message())
+  ! x and d are module arrays allocated once (md.f90): page-locked, so that every step uploads x without a staging copy
+  ! and the device adds the gradient into d; a failure only means the staged path is used
+  if (qnb_register_host_buffers(qnb_handle, x, d) /= 0) write(*,'(a)') 'qnb: x / d not page-locked: '//qnb_message()
   if (use_PBC) then
      bl = (/ boxlength%x, boxlength%y, boxlength%z /); ibl = (/ inv_boxl%x, inv_boxl%y, inv_boxl%z /)
      if (qnb_update_box(qnb_handle, bl, ibl) /= 0) call die('qnb_update_box: '//qnb_message())

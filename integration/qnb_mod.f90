@@ -135,6 +135,19 @@ interface
         real(c_double), intent(out) :: E_out(7), EQ_out(*) ! 6*nstates
         integer(c_int) :: rc
     end function
+    ! page-lock x and d (module arrays of md.f90) once: no staging copy of x, the device adds the gradient into d
+    function qnb_register_host_buffers(handle, x, d) bind(c, name='qnb_register_host_buffers') result(rc)
+        import :: c_int, c_ptr
+        type(c_ptr), value :: handle
+        type(*), dimension(*), intent(in) :: x            ! TYPE(qr_vec) x(natom)
+        type(*), dimension(*), intent(inout) :: d         ! TYPE(qr_vec) d(natom)
+        integer(c_int) :: rc
+    end function
+    function qnb_release_host_buffers(handle) bind(c, name='qnb_release_host_buffers') result(rc)
+        import :: c_int, c_ptr
+        type(c_ptr), value :: handle
+        integer(c_int) :: rc
+    end function
     ! several independent systems of one process (lambda windows of a FEP farm, EVB frames) advanced together on one
     ! GPU: arrays of n handles / c_loc addresses, one entry per system; results are those of n single calls
     function qnb_build_lists_batch(n, handles, x, Rq, Rcq2, RcLRF2, Rcpp2, Rcpw2, Rcww2, RcLRF, counts) &

@@ -206,6 +206,19 @@ struct qnb_handle {
     size_t arena_doubles = 0, arena_lrf_off = 0, arena_ctl_off = 0;
     P2PComm p2p{};
     void *peer_base[kMaxPeers] = {};
+    // caller buffers used directly by the step's copies (page-locked on first sight, cudaHostRegister): no staging copy of
+    // x, and the gradient is added into the caller's d by the device (k_add_out over mapped host memory)
+    struct HostReg { const void *p; size_t bytes; void *dev; };
+    std::vector<HostReg> hostregs;
+    bool host_direct = true;
+    const double *x_direct = nullptr;      // this call's registered x (nullptr: staged through hx)
+    double *d_direct = nullptr;            // device alias of this call's registered d (nullptr: added on the host)
+    const double *graph_x[16] = {};        // what the with-copies graphs were captured with
+    double *graph_d[16] = {};
+    bool d_overwrite = false, graph_dow[16] = {};   // QNB_FLAG_D_IS_ZERO: copy into the registered d instead of adding
+    double *d_host = nullptr;              // the caller's registered d itself (host address), target of that copy
+    int share = 1;                         // systems that advance together on this GPU (qnb_build_lists_batch): grids are sized
+                                           // for 1/share of the SMs so that the kernels of the systems run side by side
     // stats
     int64_t launches = 0, last_h2d = 0, last_d2h = 0;
     double t_stage_in = 0, t_issue = 0, t_wait = 0, t_add_out = 0;   // host-side seconds of the last qnb_nonbond
@@ -415,6 +428,7 @@ static int init_device(qnb_handle *h) {
     CU(cudaEventCreate(&h->ev0));
     CU(cudaEventCreate(&h->ev1));
     for (int k = 0; k < 6; k++) CU(cudaEventCreate(&h->ev_bt[k]));
+    if (const char *e = getenv("QNB_NO_HOST_REGISTER")) h->host_direct = !(e[0] == '1');
     if (const char *e = getenv("QNB_NO_GRAPH")) h->use_graph = !(e[0] == '1');
     if (const char *e = getenv("QNB_ONE_STREAM")) h->multi_stream = !(e[0] == '1');
     if (const char *e = getenv("QNB_WATER_BLOCKS")) h->water_blocks = std::max(0, atoi(e));
@@ -595,8 +609,8 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
                           h->src_off.p, h->src.p, h->lrf.p, h->lrf_mom.p);
                 LAUNCH_ON(h, ls, k_lrf_expand, cdiv(nu * 40, 256), 256, 0, D, h->lrf_mom.p, h->lrf.p);
             } else
-#define LRFCASE(CP, RS, GN) LAUNCH_ON(h, ls, (k_lrf_accumulate<CP, RS, GN>), nu, 32 * kRowWarps, 0, D, h->cut, G, h->lrf_reach, h->x.p, h->upos.p, \
-                                      h->cell_of.p, h->cell_start.p, h->item_pos.p, h->item_posf.p, h->src_off.p, h->src.p, h->srcf.p, h->lrf.p)
+#define LRFCASE(CP, RS, GN) LAUNCH_ON(h, ls, (k_lrf_accumulate<CP, RS, GN>), cdiv(nu, kRowWarps), 32 * kRowWarps, 0, D, h->cut, G, h->lrf_reach, h->x.p, h->upos.p, \
+                                      h->cell_of.p, h->cell_start.p, h->cell_items.p, h->item_pos.p, h->item_posf.p, h->src_off.p, h->src.p, h->srcf.p, h->lrf.p)
             if (rowshift) { if (general) LRFCASE(true, true, true); else LRFCASE(true, true, false); }
             else if (compact) { if (general) LRFCASE(true, false, true); else LRFCASE(true, false, false); }
             else { if (general) LRFCASE(false, false, true); else LRFCASE(false, false, false); }
@@ -690,8 +704,9 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
         // one resident wave per kernel, every warp an equal share of the estimated work
         const int occw = new_rows ? h->occ_wr : h->occ_w, occs = new_rows ? h->occ_sr : h->occ_s;
         const int min_chunks = new_rows ? 2 : 4;   // chunks per warp below which more blocks only add launch overhead
-        h->wgrid = std::max(1, std::min((h->water_blocks ? h->water_blocks : std::max(occw, 1)) * h->nsm, cdiv(h->nwchunk, 4 * min_chunks)));
-        h->sgrid = std::max(1, std::min((h->solute_blocks ? h->solute_blocks : std::max(occs, 1)) * h->nsm, cdiv(h->nschunk, 4 * min_chunks)));
+        const int sh = std::max(1, h->share);
+        h->wgrid = std::max(1, std::min(cdiv((h->water_blocks ? h->water_blocks : std::max(occw, 1)) * h->nsm, sh), cdiv(h->nwchunk, 4 * min_chunks)));
+        h->sgrid = std::max(1, std::min(cdiv((h->solute_blocks ? h->solute_blocks : std::max(occs, 1)) * h->nsm, sh), cdiv(h->nschunk, 4 * min_chunks)));
         if (h->wstart_w.ensure(4 * h->wgrid + 2) || h->wstart_s.ensure(4 * h->sgrid + 2)) return 1;
         if (h->nwchunk > 0)
             LAUNCH(h, k_warp_starts, cdiv(4 * h->wgrid + 1, 128), 128, 0, D, nsol, nwat, 0, new_rows, h->counts.p, off_w, co_w, 4 * h->wgrid, h->wstart_w.p);
@@ -742,7 +757,7 @@ enum StepKernel { K_WATER = 0, K_SOLUTE, K_QPARTNER, K_QATOM, K_QSTATIC, K_LRF, 
 static const char *kStepKernelNames[K_COUNT] = {"k_water_rows", "k_solute_rows", "k_q_partner", "k_q_atom",
                                                 "k_qq_static", "k_lrf_taylor", "k_solvent_restraints", "k_pair_energy"};
 
-constexpr int kFlagEnergiesOnly = 8;   // internal (QCP beads): no kernel whose only product is a gradient
+constexpr int kFlagEnergiesOnly = 64;   // internal (QCP beads): no kernel whose only product is a gradient
 
 static bool step_kernel_active(const qnb_handle *h, int k, int flags) {
     const Dev &D = h->D;
@@ -865,7 +880,7 @@ static void launch_step_kernel(qnb_handle *h, int k, cudaStream_t cs, int flags)
         break;
     case K_ENERGY: {
         const int n = h->n_ww_e + h->n_pp_e + h->n_pw_e;
-        const int grid = std::max(1, std::min(cdiv(n, 128), 8 * h->nsm));
+        const int grid = std::max(1, std::min(cdiv(n, 128), cdiv(8 * h->nsm, std::max(1, h->share))));
         if (pbc) LAUNCH_ON(h, cs, k_pair_energy<true>, grid, 128, 0, h->epar, h->n_ww_e, h->ww_pairs.p, h->n_pp_e, h->pp_pairs.p, h->n_pw_e,
                            h->pw_pairs.p, h->px.p, h->py.p, h->pz.p, h->pk_qd.p, h->pk_ct.p, h->pk_sw.p, h->x.p, h->wd.p, h->ljd.p, h->ljcode.p, E, nE);
         else LAUNCH_ON(h, cs, k_pair_energy<false>, grid, 128, 0, h->epar, h->n_ww_e, h->ww_pairs.p, h->n_pp_e, h->pp_pairs.p, h->n_pw_e,
@@ -920,6 +935,50 @@ static int issue_step(qnb_handle *h, int flags, bool out_cleared = false) {
     return 0;
 }
 
+// d(host, mapped) += gradient: the last node of an end-to-end step when the caller's d is page-locked
+__global__ void __launch_bounds__(256) k_add_out(size_t n, const double *__restrict__ grad, double *__restrict__ d_host) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((reinterpret_cast<uintptr_t>(d_host) & 15u) == 0) {
+        const size_t n2 = n / 2;
+        if (i < n2) {
+            double2 v = reinterpret_cast<double2 *>(d_host)[i];
+            const double2 g = reinterpret_cast<const double2 *>(grad)[i];
+            v.x += g.x; v.y += g.y;
+            reinterpret_cast<double2 *>(d_host)[i] = v;
+        }
+        if (i == 0 && (n & 1)) d_host[n - 1] += grad[n - 1];
+    } else {
+        for (size_t k = 2 * i; k < 2 * i + 2 && k < n; k++) d_host[k] += grad[k];
+    }
+}
+
+// Device alias of a caller buffer that qnb_register_host_buffers page-locked (kept until qnb_finalize /
+// qnb_release_host_buffers); nullptr for any other buffer (the call then stages through the handle's own pinned memory).
+static void *host_alias(qnb_handle *h, const void *p, size_t bytes, bool may_register = false) {
+    if (!h->host_direct || !p) return nullptr;
+    for (const auto &r : h->hostregs)
+        if (r.p == p && (r.bytes >= bytes || r.bytes == 0)) return r.dev;
+    if (!may_register || h->hostregs.size() >= 32) return nullptr;
+    qnb_handle::HostReg r{p, bytes, nullptr};
+    cudaError_t e = cudaHostRegister(const_cast<void *>(p), bytes, cudaHostRegisterMapped | cudaHostRegisterPortable);
+    if (e == cudaSuccess || e == cudaErrorHostMemoryAlreadyRegistered) {
+        if (e != cudaSuccess) cudaGetLastError();
+        void *dev = nullptr;
+        if (cudaHostGetDevicePointer(&dev, const_cast<void *>(p), 0) == cudaSuccess) r.dev = dev;
+        else { cudaGetLastError(); if (e == cudaSuccess) cudaHostUnregister(const_cast<void *>(p)); }
+        if (e != cudaSuccess && r.dev) r.bytes = 0;   // somebody else's registration: never unregistered here
+    } else cudaGetLastError();
+    h->hostregs.push_back(r);
+    return r.dev;
+}
+static void release_host_buffers(qnb_handle *h) {
+    for (const auto &r : h->hostregs)
+        if (r.dev && r.bytes) cudaHostUnregister(const_cast<void *>(r.p));
+    cudaGetLastError();
+    h->hostregs.clear();
+    h->x_direct = nullptr; h->d_direct = nullptr;
+}
+
 // One evaluation on the device.  with_copies: pinned x -> device before, [grad|E|EQ] -> pinned after.
 // Captured once per list build into a CUDA graph (one launch per MD step instead of ~10 API calls).
 static int step_device(qnb_handle *h, int flags, bool with_copies = false) {
@@ -930,9 +989,32 @@ static int step_device(qnb_handle *h, int flags, bool with_copies = false) {
     const bool graphable = h->use_graph && (!h->comm || shard_graph || p2p_ready(h));
     flags &= (QNB_FLAG_MD | QNB_FLAG_QQ | QNB_FLAG_NO_ENERGY | QNB_FLAG_SOLVENT_RESTRAINTS);
     const int gi = (flags & 7) | ((flags & QNB_FLAG_SOLVENT_RESTRAINTS) ? 8 : 0);
+    // the copies of an end-to-end step: x from the caller's page-locked array (else from the staging copy), lambda from
+    // the staging tail; afterwards either [grad|E|EQ] -> pinned (added on the host) or d += grad by the device and only
+    // the energy tail -> pinned
+    auto copy_in = [&]() -> int {
+        int rc = 0;
+        if (h->x_direct) {
+            rc |= cudaMemcpyAsync(h->x.p, h->x_direct, n3 * sizeof(double), cudaMemcpyHostToDevice, h->st) != cudaSuccess;
+            rc |= cudaMemcpyAsync(h->lam_dev, h->hlam, kMaxStates * sizeof(double), cudaMemcpyHostToDevice, h->st) != cudaSuccess;
+        } else
+            rc |= cudaMemcpyAsync(h->x.p, h->hx, (n3 + kMaxStates) * sizeof(double), cudaMemcpyHostToDevice, h->st) != cudaSuccess;
+        return rc;
+    };
+    auto copy_out = [&]() -> int {
+        int rc = 0;
+        if (h->d_direct) {
+            if (h->d_overwrite) rc |= cudaMemcpyAsync(h->d_host, h->out.p, n3 * sizeof(double), cudaMemcpyDeviceToHost, h->st) != cudaSuccess;
+            else LAUNCH(h, k_add_out, cdiv((int)((n3 + 1) / 2), 256), 256, 0, n3, h->out.p, h->d_direct);
+            rc |= cudaMemcpyAsync(h->hout + n3, h->out.p + n3, (h->nout - n3) * sizeof(double), cudaMemcpyDeviceToHost, h->st) != cudaSuccess;
+        } else
+            rc |= cudaMemcpyAsync(h->hout, h->out.p, h->nout * sizeof(double), cudaMemcpyDeviceToHost, h->st) != cudaSuccess;
+        return rc;
+    };
     if (graphable) {
         cudaGraphExec_t &ge = h->graph[with_copies ? 1 : 0][gi];
         bool &dirty = h->graph_dirty[with_copies ? 1 : 0][gi];
+        if (with_copies && (h->graph_x[gi] != h->x_direct || h->graph_d[gi] != h->d_direct || h->graph_dow[gi] != h->d_overwrite)) dirty = true;   // baked pointers
         if (!ge || dirty) {
             cudaGraph_t g = nullptr;
             const int64_t l0 = h->launches;
@@ -948,12 +1030,12 @@ static int step_device(qnb_handle *h, int flags, bool with_copies = false) {
                     rc |= cudaEventRecord(h->ev_join[4], h->aux[4]) != cudaSuccess;
                     cleared = true;
                 }
-                rc |= cudaMemcpyAsync(h->x.p, h->hx, (n3 + kMaxStates) * sizeof(double), cudaMemcpyHostToDevice, h->st) != cudaSuccess;
+                rc |= copy_in();
                 if (cleared) rc |= cudaStreamWaitEvent(h->st, h->ev_join[4], 0) != cudaSuccess;
             }
             rc |= issue_step(h, flags, cleared);
             rc |= allreduce_arena(h, 0, h->nout, h->st);
-            if (with_copies) rc |= cudaMemcpyAsync(h->hout, h->out.p, h->nout * sizeof(double), cudaMemcpyDeviceToHost, h->st) != cudaSuccess;
+            if (with_copies) { rc |= copy_out(); h->graph_x[gi] = h->x_direct; h->graph_d[gi] = h->d_direct; h->graph_dow[gi] = h->d_overwrite; }
             cudaError_t ce = cudaStreamEndCapture(h->st, &g);
             h->graph_launches[with_copies ? 1 : 0][gi] = (int)(h->launches - l0);
             h->launches = l0;
@@ -973,13 +1055,11 @@ static int step_device(qnb_handle *h, int flags, bool with_copies = false) {
         h->launches += h->graph_launches[with_copies ? 1 : 0][gi];
         return 0;
     }
-    if (with_copies) {
-        CU(cudaMemcpyAsync(h->x.p, h->hx, (n3 + kMaxStates) * sizeof(double), cudaMemcpyHostToDevice, h->st));
-    }
+    if (with_copies && copy_in()) return fail("step: upload failed: %s", cudaGetErrorString(cudaGetLastError()));
     if (issue_step(h, flags)) return 1;
     // gather_nonbond + serial sum on the master (potene.f90:195-222) as one all-reduce over [d | E | EQ]
     if (allreduce_arena(h, 0, h->nout, h->st)) return 1;
-    if (with_copies) CU(cudaMemcpyAsync(h->hout, h->out.p, h->nout * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    if (with_copies && copy_out()) return fail("step: download failed: %s", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
 
@@ -1266,6 +1346,8 @@ int qnb_build_lists_batch(int n, qnb_handle *const *hs, const double *const *x, 
         if (!hs[k] || !x[k]) return fail("qnb_build_lists_batch: null argument for system %d", k);
         for (int j = 0; j < k; j++) if (hs[j] == hs[k]) return fail("qnb_build_lists_batch: handle %d given twice", k);
     }
+    static const int share_cap = [] { const char *e = getenv("QNB_BATCH_SHARE"); return e ? std::max(1, atoi(e)) : 4; }();
+    for (int k = 0; k < n; k++) hs[k]->share = std::min(n, share_cap);
     std::vector<int> rc(n, 0);
     std::vector<std::string> err(n);
     auto work = [&](int k) {
@@ -1281,13 +1363,17 @@ int qnb_build_lists_batch(int n, qnb_handle *const *hs, const double *const *x, 
 }
 
 // qnb_nonbond in two halves, so that several handles can be in flight at once (qnb_nonbond_batch)
-static int nonbond_begin(qnb_handle *h, const double *x, const double *lambda, int flags) {
+static int nonbond_begin(qnb_handle *h, const double *x, const double *lambda, int flags, double *d) {
     CU(cudaSetDevice(h->device));
     const qnb_system &s = h->T.s;
     const size_t n3 = 3 * (size_t)s.natom;
     using clk = std::chrono::steady_clock;
     const auto t0 = clk::now();
-    memcpy(h->hx, x, n3 * sizeof(double));
+    h->x_direct = host_alias(h, x, n3 * sizeof(double)) ? x : nullptr;
+    h->d_direct = static_cast<double *>(host_alias(h, d, n3 * sizeof(double)));
+    h->d_host = d;
+    h->d_overwrite = h->d_direct && (flags & QNB_FLAG_D_IS_ZERO);
+    if (!h->x_direct) memcpy(h->hx, x, n3 * sizeof(double));
     for (int k = 0; k < s.nstates; k++) h->hlam[k] = lambda[k];
     h->last_flags = flags;
     const auto t1 = clk::now();
@@ -1303,8 +1389,10 @@ static int nonbond_end(qnb_handle *h, double *d, double *E_out, double *EQ_out) 
     CU(cudaGetLastError());
     h->last_h2d = (int64_t)((n3 + s.nstates) * sizeof(double));
     h->last_d2h = (int64_t)(h->nout * sizeof(double));
-    const double *__restrict__ g = h->hout;
-    for (size_t k = 0; k < n3; k++) d[k] += g[k];
+    if (!h->d_direct) {
+        const double *__restrict__ g = h->hout;
+        for (size_t k = 0; k < n3; k++) d[k] += g[k];
+    }
     for (int k = 0; k < h->nE; k++) {
         double e = 0;   // fixed-order sum of the partial accumulators
         for (int sl = 0; sl < kESlots; sl++) e += h->hout[n3 + (size_t)sl * h->nE + k];
@@ -1320,7 +1408,7 @@ int qnb_nonbond(qnb_handle *h, const double *x, const double *lambda, int flags,
     if (!h->lists_built) return fail("qnb_nonbond: pair lists have not been built (call qnb_build_lists)");
     using clk = std::chrono::steady_clock;
     const auto t0 = clk::now();
-    if (nonbond_begin(h, x, lambda, flags)) return 1;
+    if (nonbond_begin(h, x, lambda, flags, d)) return 1;
     const auto t2 = clk::now();
     CU(cudaStreamSynchronize(h->st));
     const auto t3 = clk::now();
@@ -1385,7 +1473,14 @@ struct BatchPool {
 };
 BatchPool g_pool;
 std::mutex g_pool_use;
+double g_batch_t[3] = {0, 0, 0};   // calling thread, last batch: issuing (staging + launches), waiting for the device, adding out
 }  // namespace
+
+int qnb_bench_last_batch_timing(double out[3]) {
+    if (!out) return fail("null argument");
+    for (int k = 0; k < 3; k++) out[k] = g_batch_t[k];
+    return 0;
+}
 
 int qnb_nonbond_batch(int n, qnb_handle *const *hs, const double *const *x, const double *const *lambda, int flags,
                       double *const *d, double *const *E_out, double *const *EQ_out) {
@@ -1395,17 +1490,32 @@ int qnb_nonbond_batch(int n, qnb_handle *const *hs, const double *const *x, cons
         if (!hs[k]->lists_built) return fail("qnb_nonbond_batch: pair lists of system %d have not been built", k);
         for (int j = 0; j < k; j++) if (hs[j] == hs[k]) return fail("qnb_nonbond_batch: handle %d given twice", k);
     }
-    static const int max_workers = [] { const char *e = getenv("QNB_BATCH_THREADS"); return e ? std::max(1, atoi(e)) : 4; }();
+    // measured (r02l, C2 x 7): 4 host threads made the batched step SLOWER (0.74 vs 0.52 ms; the CUDA runtime serialises
+    // the launches and the wake-ups cost more than the copies they spread), so one thread is the default
+    static const int max_workers = [] { const char *e = getenv("QNB_BATCH_THREADS"); return e ? std::max(1, atoi(e)) : 1; }();
     const int nw = std::max(1, std::min(max_workers, n));   // threads incl. the caller
     std::vector<int> rc(nw, 0);
     std::vector<std::string> err(nw);
     // thread w takes windows w, w + nw, ...: all of its steps are in flight before it waits for the first result
+    using clk = std::chrono::steady_clock;
     auto work = [&](int w) {
         int started = 0;
+        const auto t0 = clk::now();
         for (int k = w; k < n; k += nw, started++)
-            if (nonbond_begin(hs[k], x[k], lambda[k], flags)) { rc[w] = 1; err[w] = g_err; break; }
-        for (int k = w, j = 0; j < started; k += nw, j++)
+            if (nonbond_begin(hs[k], x[k], lambda[k], flags, d[k])) { rc[w] = 1; err[w] = g_err; break; }
+        const auto t1 = clk::now();
+        double wait = 0.0;
+        for (int k = w, j = 0; j < started; k += nw, j++) {
+            const auto a = clk::now();
+            cudaStreamSynchronize(hs[k]->st);
+            wait += std::chrono::duration<double>(clk::now() - a).count();
             if (nonbond_end(hs[k], d[k], E_out[k], EQ_out[k]) && !rc[w]) { rc[w] = 1; err[w] = g_err; }
+        }
+        if (w == 0) {
+            g_batch_t[0] = std::chrono::duration<double>(t1 - t0).count();
+            g_batch_t[1] = wait;
+            g_batch_t[2] = std::chrono::duration<double>(clk::now() - t1).count() - wait;
+        }
     };
     if (nw == 1) work(0);
     else {
@@ -1413,6 +1523,23 @@ int qnb_nonbond_batch(int n, qnb_handle *const *hs, const double *const *x, cons
         g_pool.run(nw - 1, work);
     }
     for (int w = 0; w < nw; w++) if (rc[w]) return fail("%s", err[w].c_str());
+    return 0;
+}
+
+int qnb_register_host_buffers(qnb_handle *h, const double *x, double *d) {
+    if (!h) return fail("null handle");
+    CU(cudaSetDevice(h->device));
+    const size_t bytes = 3 * (size_t)h->T.s.natom * sizeof(double);
+    if (x && !host_alias(h, x, bytes, true) && h->host_direct) return fail("qnb_register_host_buffers: cudaHostRegister(x) failed");
+    if (d && !host_alias(h, d, bytes, true) && h->host_direct) return fail("qnb_register_host_buffers: cudaHostRegister(d) failed");
+    return 0;
+}
+
+int qnb_release_host_buffers(qnb_handle *h) {
+    if (!h) return fail("null handle");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->st));
+    release_host_buffers(h);
     return 0;
 }
 
@@ -1831,6 +1958,7 @@ int qnb_finalize(qnb_handle *h) {
     h->upk.release(); h->pk_sw.release(); h->e_cnt.release(); h->e_off.release(); h->rec_i.release(); h->rec_f.release(); h->wT.release(); h->wown.release(); h->wd.release();
     h->pw12.release(); h->ljp.release(); h->pw0.release(); h->ww_pairs.release(); h->pp_pairs.release(); h->pw_pairs.release();
     h->item_pos.release(); h->src.release(); h->cell_unsorted.release(); h->item_nq.release(); h->src_off.release();
+    release_host_buffers(h);
     for (int k = 0; k < kMaxPeers; k++) if (h->peer_base[k]) cudaIpcCloseMemHandle(h->peer_base[k]);
     if (h->arena) cudaFree(h->arena);
     if (h->hx) cudaFreeHost(h->hx);

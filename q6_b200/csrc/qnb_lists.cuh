@@ -812,19 +812,23 @@ struct LrfSeg { int lo, hi; float tx, ty, tz; };
 template <bool COMPACT, bool ROWSHIFT, bool GENERAL>
 __global__ void __launch_bounds__(32 * kRowWarps)
 k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x, const double *__restrict__ upos,
-                 const int *__restrict__ cell_of, const int *__restrict__ cell_start,
+                 const int *__restrict__ cell_of, const int *__restrict__ cell_start, const int *__restrict__ cell_items,
                  const double4 *__restrict__ item_pos, const float4 *__restrict__ item_posf,
                  const int *__restrict__ src_off, const double4 *__restrict__ src, const float4 *__restrict__ srcf,
                  double *__restrict__ lrf) {
-    // one block (kRowWarps warps) per target unit; the cell rows inside the LRF reach are dealt to the warps.
+    // One WARP per target unit, the kRowWarps targets of a block being neighbours in cell order: they scan (nearly) the
+    // same cells at the same time, so the source records one warp pulls through L1 serve the others (r02e: one block per
+    // target with its warps on different cell rows, 49 % L1 hit rate, 258 KB of source records per target through L2).
     // Candidates are first screened (FP32 distance with a safety band, exact FP64 test inside the band) and the
     // accepted ones compacted into a per-warp queue, so that the expensive accumulation always runs on full warps
     // even when only a few percent of the scanned cells' units lie inside the LRF shell (periodic boxes).
     __shared__ double red[kRowWarps][kLrfRaw];
     __shared__ int queue[kRowWarps][64];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int t = blockIdx.x;
-    if (D.u_excl[t]) return;   // block-uniform
+    const int titem = blockIdx.x * kRowWarps + wid;
+    if (titem >= D.nunit) return;   // warp-uniform; no block-wide barrier below
+    const int t = cell_items[titem];
+    if (D.u_excl[t]) return;
     if (GENERAL && D.sharded && D.shard_rows && !row_in_any_shard(D, t)) return;   // another rank's target: stays zero, summed later
     const int ns = D.ncgp_solute;
     const int gt = D.u_grp[t];
@@ -889,21 +893,22 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
     if (G.periodic)
         for (int d = 0; d < 3; d++) ptw[d] -= D.box[d] * floor(ptw[d] * D.inv_box[d]);
     const float ptf[3] = {(float)ptw[0], (float)ptw[1], (float)ptw[2]};
-    __shared__ LrfSeg seg[kLrfSegBatch];   // item ranges [lo,hi) of the cell rows (+ target image), computed once per block
-    __shared__ int seg_n, seg_next;        // non-empty segments of the batch; next one to hand out
+    __shared__ LrfSeg seg_all[kRowWarps][kLrfSegBatch];   // item ranges [lo,hi) of the cell rows (+ target image) of this warp's target
+    LrfSeg *seg = seg_all[wid];
     int qn = 0;   // entries waiting in this warp's queue (warp-uniform)
     for (int r0 = 0; r0 < nrow; r0 += kLrfSegBatch) {
-        __syncthreads();
-        if (threadIdx.x == 0) { seg_n = 0; seg_next = 0; }
-        __syncthreads();
-        if (whole) { if (threadIdx.x == 0) { seg[0] = LrfSeg{0, D.nunit, ptf[0], ptf[1], ptf[2]}; seg_n = 1; } }
-        else for (int r = r0 + threadIdx.x; r < min(nrow, r0 + kLrfSegBatch); r += blockDim.x) {
+        __syncwarp();
+        int nseg = 0;
+        if (whole) { if (lane == 0) seg[0] = LrfSeg{0, D.nunit, ptf[0], ptf[1], ptf[2]}; nseg = 1; }
+        else for (int rb = r0; rb < min(nrow, r0 + kLrfSegBatch); rb += 32) {
+            const int r = rb + lane;
+            LrfSeg sg{0, 0, ptf[0], ptf[1], ptf[2]};
+            if (r < min(nrow, r0 + kLrfSegBatch)) {
             const int nxs = ROWSHIFT ? 2 : xs.n;
             const int sgi = r % nxs, iy = (r / nxs) % ry.count, iz = r / (nxs * ry.count);
             const int zu = rz.start + iz, yu = ry.start + iy;           // unwrapped cell indices of the row
             const int z = (zu % G.n[2] + G.n[2]) % G.n[2], y = (yu % G.n[1] + G.n[1]) % G.n[1];
             const int rowbase = (z * G.n[1] + y) * G.n[0];
-            LrfSeg sg{0, 0, ptf[0], ptf[1], ptf[2]};
             if (!ROWSHIFT) {
                 sg.lo = cell_start[rowbase + (sgi == 0 ? xs.lo[0] : xs.lo[1])];
                 sg.hi = cell_start[rowbase + (sgi == 0 ? xs.hi[0] : xs.hi[1])];
@@ -934,23 +939,17 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
                     }
                 }
             }
-            if (sg.hi > sg.lo) seg[atomicAdd(&seg_n, 1)] = sg;   // only rows that hold candidates
-        }
-        __syncthreads();
-        const int nseg = seg_n;
-        // few long segments: all warps share each segment, striding by kRowWarps*32; else the warps draw segments from
-        // a shared counter (rows differ in length after trimming: a fixed deal leaves warps idle at the barrier)
-        const bool share = nseg < kRowWarps;
-        for (int r = 0;;) {
-            if (share) { if (r >= nseg) break; }
-            else {
-                if (lane == 0) r = atomicAdd(&seg_next, 1);
-                r = __shfl_sync(kFull, r, 0);
-                if (r >= nseg) break;
             }
+            // only rows that hold candidates, appended in lane order
+            const unsigned keep = __ballot_sync(kFull, sg.hi > sg.lo);
+            if (sg.hi > sg.lo) seg[nseg + __popc(keep & ((1u << lane) - 1u))] = sg;
+            nseg += __popc(keep);
+        }
+        __syncwarp();
+        for (int r = 0; r < nseg; r++) {
             const LrfSeg sg = seg[r];
-            const int lo = sg.lo + (share ? 32 * wid : 0), hi = sg.hi;
-            for (int base = lo; base < hi; base += share ? 32 * kRowWarps : 32) {
+            const int lo = sg.lo, hi = sg.hi;
+            for (int base = lo; base < hi; base += 32) {
                 const int idx = base + lane;
                 bool accept = false;
                 if (idx < hi) {
@@ -1003,7 +1002,6 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
                     qn = rest;
                 }
             }
-            if (share) r++;
         }
     }
     __syncwarp();
@@ -1019,19 +1017,9 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
         const double a = warp_sum((double)h[k]);
         if (lane == 0) red[wid][11 + k] = a;
     }
-    __syncthreads();
-    __shared__ double mm[kLrfRaw];
-    if (threadIdx.x < kLrfRaw) {
-        double a = 0;
-#pragma unroll
-        for (int k = 0; k < kRowWarps; k++) a += red[k][threadIdx.x];
-        mm[threadIdx.x] = a;
-    }
-    __syncthreads();
-    if (threadIdx.x < 40) {
-        // LRF_TYPE order after cgp_cent: phi0, phi1(3), phi2(a)%b (9), phi3(3*(n-1)+j)%k (27) from the unique moments
-        lt[3 + threadIdx.x] = lrf_finish(mm, kLrfExpand[threadIdx.x]);
-    }
+    __syncwarp();
+    // LRF_TYPE order after cgp_cent: phi0, phi1(3), phi2(a)%b (9), phi3(3*(n-1)+j)%k (27) from the unique moments
+    for (int k = lane; k < 40; k += 32) lt[3 + k] = lrf_finish(red[wid], kLrfExpand[k]);
 }
 
 // ---------------------------------------------------------------- LRF, sphere with the LRF cut-off spanning it

@@ -21,6 +21,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libqnb.so")
 QNB_FLAG_MD = 1
 QNB_FLAG_QQ = 2
 QNB_FLAG_NO_ENERGY = 4
+QNB_FLAG_D_IS_ZERO = 8
 QNB_FLAG_SOLVENT_RESTRAINTS = 16
 MAX_SHELLS = 8
 
@@ -136,6 +137,10 @@ def load_library(path: str = LIB_PATH):
     lib.qnb_build_lists_batch.argtypes = [C.c_int, C.c_void_p, C.c_void_p] + [C.c_double] * 7 + [C.c_void_p]
     lib.qnb_nonbond_batch.restype = C.c_int
     lib.qnb_nonbond_batch.argtypes = [C.c_int] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 3
+    lib.qnb_register_host_buffers.restype = C.c_int
+    lib.qnb_register_host_buffers.argtypes = [H, C.c_void_p, C.c_void_p]
+    lib.qnb_release_host_buffers.restype = C.c_int
+    lib.qnb_release_host_buffers.argtypes = [H]
     lib.qnb_list_count.restype = C.c_int
     lib.qnb_list_count.argtypes = [H, C.c_int, C.c_int, _PL]
     lib.qnb_export_list.restype = C.c_int
@@ -156,6 +161,8 @@ def load_library(path: str = LIB_PATH):
     lib.qnb_bench_nonbond.argtypes = [H, _PD, C.c_int, C.c_int, C.c_int, _PF]
     lib.qnb_bench_build_lists.restype = C.c_int
     lib.qnb_bench_build_lists.argtypes = [H, C.c_int, _PF]
+    lib.qnb_bench_last_batch_timing.restype = C.c_int
+    lib.qnb_bench_last_batch_timing.argtypes = [_PD]
     lib.qnb_bench_allreduce.restype = C.c_int
     lib.qnb_bench_allreduce.argtypes = [H, C.c_int, _PF]
     lib.qnb_bench_last_build_timing.restype = C.c_int
@@ -215,6 +222,19 @@ class Qnb:
     def _check(self, rc: int):
         if rc != 0:
             raise QnbError(self.lib.qnb_last_error().decode())
+
+    def register_host_buffers(self, x=None, d=None):
+        """Page-lock the caller's persistent x / d arrays (qnb_register_host_buffers): later steps given exactly these
+        arrays skip the staging copy of x and have the gradient added into d by the device.  The caller keeps the arrays
+        alive until close() / release_host_buffers()."""
+        for a in (x, d):
+            assert a is None or (a.dtype == np.float64 and a.flags.c_contiguous and a.size == 3 * self.sys.natom)
+        self._registered = (x, d)     # keep them alive as long as the handle
+        self._check(self.lib.qnb_register_host_buffers(self.h, None if x is None else x.ctypes.data, None if d is None else d.ctypes.data))
+
+    def release_host_buffers(self):
+        self._check(self.lib.qnb_release_host_buffers(self.h))
+        self._registered = None
 
     def close(self):
         if getattr(self, "h", None):
@@ -277,7 +297,7 @@ class Qnb:
         k = getattr(self, "_nshell", 0)
         return E, ts[:k], ns[:k]
 
-    def pot_energy_nonbonds(self, x, lambdas, md=True, qq=True, d=None, energies=True, restraints=False):
+    def pot_energy_nonbonds(self, x, lambdas, md=True, qq=True, d=None, energies=True, restraints=False, d_is_zero=False):
         """pot_energy_nonbonds(E,EQ,md) (+ nonbond_qq/nonbond_qqp when qq): returns (d, E[7], EQ[nstates][6]).
         energies=False (extension, QNB_FLAG_NO_ENERGY): the pp/pw/ww energies of this step are not needed."""
         x = _f64(x)
@@ -290,7 +310,7 @@ class Qnb:
         E = np.empty(E_COUNT)
         EQ = np.empty((self.sys.nstates, EQ_STRIDE))
         flags = ((QNB_FLAG_MD if md else 0) | (QNB_FLAG_QQ if qq else 0) | (0 if energies else QNB_FLAG_NO_ENERGY)
-                 | (QNB_FLAG_SOLVENT_RESTRAINTS if restraints else 0))
+                 | (QNB_FLAG_SOLVENT_RESTRAINTS if restraints else 0) | (QNB_FLAG_D_IS_ZERO if d_is_zero else 0))
         if self.lib.qnb_nonbond(self.h, _addr(x), _addr(lam), flags, _addr(d), _addr(E), _addr(EQ)):
             self._check(1)
         return d.reshape(-1, 3), E, EQ
@@ -479,6 +499,9 @@ class QnbBatch:
         self.d = [np.zeros((g.sys.natom, 3)) for g in self.g]
         self.E = [np.zeros(E_COUNT) for _ in self.g]
         self.EQ = [np.zeros((g.sys.nstates, EQ_STRIDE)) for g in self.g]
+        for g, xk, dk in zip(self.g, self.x, self.d):
+            g.release_host_buffers()
+            g.register_host_buffers(xk.reshape(-1), dk.reshape(-1))     # the batch owns these arrays for its lifetime
         tab = lambda arrs: (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
         self._x, self._lam, self._d, self._E, self._EQ = tab(self.x), tab(self.lam), tab(self.d), tab(self.E), tab(self.EQ)
 
@@ -505,13 +528,17 @@ class QnbBatch:
         if lambdas is not None:
             for k, lk in enumerate(lambdas):
                 self.lam[k][:] = lk
-        if zero_d:
-            for dk in self.d:
-                dk[:] = 0.0
-        flags = (QNB_FLAG_MD if md else 0) | (QNB_FLAG_QQ if qq else 0)
+        # zero_d: d(:) = zero of pot_energy (potene.f90:109) -- the library is told (QNB_FLAG_D_IS_ZERO) and writes the
+        # gradient into the registered arrays, so the clearing itself is not needed
+        flags = (QNB_FLAG_MD if md else 0) | (QNB_FLAG_QQ if qq else 0) | (QNB_FLAG_D_IS_ZERO if zero_d else 0)
         if self.lib.qnb_nonbond_batch(self.n, self._h, self._x, self._lam, flags, self._d, self._E, self._EQ):
             self._check(1)
         return self.d, self.E, self.EQ
+
+    def last_timing(self) -> dict:
+        t = np.zeros(3)
+        self._check(self.lib.qnb_bench_last_batch_timing(_dp(t)))
+        return dict(zip(("issue_s", "device_wait_s", "add_out_s"), t.tolist()))
 
 
 def bench_peak(which: int, device: int = 0) -> float:

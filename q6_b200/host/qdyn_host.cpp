@@ -1197,6 +1197,9 @@ Nonbonded::Nonbonded(System &sys, int device) : sys_(sys) {
     x.assign(3 * (size_t)s->natom, 0.0);
     d.assign(3 * (size_t)s->natom, 0.0);
     if (qnb_init(s, device, &h_) != 0) throw Die(std::string("qnb_init: ") + qnb_last_error());
+    // x and d live as long as this object (md.f90's module arrays): page-locked once, so that every step uploads x without
+    // a staging copy and the device adds the gradient into d
+    if (qnb_register_host_buffers(h_, x.data(), d.data()) != 0) throw Die(std::string("qnb_register_host_buffers: ") + qnb_last_error());
     if (s->use_PBC) update_box(sys_.boxlength);
 }
 

@@ -383,10 +383,13 @@ def test_batched_windows_equal_single_calls():
     cb = b.make_pair_lists(xs, **cuts, counts=True)
     d, E, EQ = b.pot_energy_nonbonds(xs, lams)
     d = [v.copy() for v in d]; E = [v.copy() for v in E]; EQ = [v.copy() for v in EQ]
-    # a second batched step on the same inputs adds to d unless zeroed (pot_energy adds to d)
+    # a second batched step on the same inputs adds to d unless the caller says d is zero (pot_energy adds to d)
     d2, _, _ = b.pot_energy_nonbonds(zero_d=False)
     for k in range(W):
         assert np.allclose(d2[k], 2.0 * d[k], rtol=1e-9, atol=1e-9)
+    d3, _, _ = b.pot_energy_nonbonds()          # QNB_FLAG_D_IS_ZERO: written, whatever the arrays held
+    for k in range(W):
+        assert np.allclose(d3[k], d[k], rtol=1e-9, atol=1e-9)
     o = Oracle(q)
     for k in range(W):
         g = Qnb(q)
@@ -407,3 +410,31 @@ def test_batched_windows_equal_single_calls():
         QnbBatch([hs[0], hs[0]])
     for g in hs:
         g.close()
+
+
+def test_registered_host_buffers_same_results():
+    """qnb_register_host_buffers (x uploaded without staging, gradient added into d by the device) gives what the staged
+    path gives: d is ADDED to (potene.f90:109 zeroes it, bonded terms may already be in it), other arrays still work."""
+    from q6_b200 import synth
+    from q6_b200.engine import Qnb
+    q = synth.solvated_sphere(14.0, 7.0, 10, 2, 41, fep="evb")
+    cuts, lam = common.sph_cuts(8.0), np.array([0.3, 0.7])
+    g = Qnb(q)
+    x = q.xtop.copy()
+    g.make_pair_lists(x, **cuts)
+    d0, E0, EQ0 = g.pot_energy_nonbonds(x, lam)
+    d0 = d0.copy()
+    d = np.full((q.natom, 3), 0.25)            # pre-loaded, e.g. with bonded terms
+    g.register_host_buffers(x.reshape(-1), d.reshape(-1))
+    _, E1, EQ1 = g.pot_energy_nonbonds(x, lam, d=d)
+    assert rel_rms(d - 0.25, d0) <= 1e-12 and np.allclose(E1, E0, rtol=1e-11, atol=1e-9) and np.allclose(EQ1, EQ0, rtol=1e-11, atol=1e-9)
+    x[:] = x + 0.01                            # the registered array is read anew every step
+    d[:] = 0.0
+    g.pot_energy_nonbonds(x, lam, d=d)
+    d2, _, _ = g.pot_energy_nonbonds(x.copy(), lam)      # unregistered arrays: the staged path
+    assert rel_rms(d, d2) <= 1e-12
+    g.release_host_buffers()
+    d[:] = 0.0
+    g.pot_energy_nonbonds(x, lam, d=d)
+    assert rel_rms(d, d2) <= 1e-12
+    g.close()
