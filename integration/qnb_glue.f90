@@ -173,7 +173,8 @@ subroutine qnb_glue_nonbond(E_loc,EQ_loc,md)
   integer :: flags, is
   lam = 0
   lam(1:nstates) = EQ_loc(1:nstates)%lambda
-  flags = QNB_FLAG_QQ
+  ! pot_energy has just cleared d (d(:) = zero, potene.f90:109) and the nonbonded terms are its first contribution
+  flags = QNB_FLAG_QQ + QNB_FLAG_D_IS_ZERO
   if (md) flags = flags + QNB_FLAG_MD
   if (qnb_nonbond(qnb_handle, x, lam, flags, d, En, qnb_EQ) /= 0) call die('pot_energy_nonbonds: '//qnb_message())
   E_loc%pp%el = E_loc%pp%el + En(1); E_loc%pp%vdw = E_loc%pp%vdw + En(2)

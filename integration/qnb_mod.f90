@@ -11,7 +11,8 @@ use, intrinsic :: iso_c_binding
 implicit none
 
 integer(c_int), parameter :: QNB_ABI_VERSION = 1
-integer(c_int), parameter :: QNB_FLAG_MD = 1, QNB_FLAG_QQ = 2
+integer(c_int), parameter :: QNB_FLAG_MD = 1, QNB_FLAG_QQ = 2, QNB_FLAG_NO_ENERGY = 4, QNB_FLAG_D_IS_ZERO = 8, &
+                             QNB_FLAG_SOLVENT_RESTRAINTS = 16
 
 ! struct qnb_system (include/qnb.h) -- field order and types must match exactly
 type, bind(c) :: qnb_system
