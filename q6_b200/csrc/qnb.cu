@@ -139,7 +139,7 @@ struct qnb_handle {
     Grid grid{};
     bool have_grid = false;
     DBuf<double> upos;
-    DBuf<int> cell_of, cell_count, cell_start, cell_items, counts, row_tot, row_off, flag, pos, qp_list, qw_list,
+    DBuf<int> cell_of, cell_count, cell_start, cell_items, counts, row_tot, row_off, flag, pos, flag2, pos2, qp_list, qw_list,
         qp_shift_atom;
     DBuf<uint32_t> rows;
     DBuf<double4> item_pos, src;
@@ -543,6 +543,30 @@ static int run_exclusive_scan(qnb_handle *h, const int *in, int *out, int n) {
     return 0;
 }
 
+// nbqplist / nbqwlist: flags -> scan -> compaction, the counts copied back asynchronously (the caller synchronises)
+static int launch_q_lists(qnb_handle *h) {
+    const Dev &D = h->D;
+    if (D.nqat <= 0) return 0;
+    const double rex2 = h->T.s.rexcl_o * h->T.s.rexcl_o;
+    const bool skip_qp = h->qp_done && (D.use_PBC ? (h->cut.Rq < 0.0) : (h->cut.rcq2 > rex2));
+    const bool skip_qw = h->qw_done && (D.use_PBC ? (h->cut.Rq < 0.0) : (h->cut.rcq2 > rex2));
+    if (!skip_qp && D.ncgp_solute > 0) {
+        LAUNCH(h, k_qp_flags, cdiv(D.ncgp_solute, 128), 128, 0, D, h->cut, h->x.p, h->flag.p, h->qp_shift_atom.p);
+        LAUNCH(h, k_exclusive_scan, 1, 1024, 0, h->flag.p, h->pos.p, D.nat_solute);
+        LAUNCH(h, k_compact, cdiv(D.nat_solute, 256), 256, 0, D.nat_solute, h->flag.p, h->pos.p, h->qp_list.p);
+        CU(cudaMemcpyAsync(&h->nqp, h->pos.p + D.nat_solute, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+        h->qp_done = true;
+    }
+    if (!skip_qw && D.nwat > 0) {
+        LAUNCH(h, k_qw_flags, cdiv(D.nwat, 128), 128, 0, D, h->cut, h->x.p, h->flag2.p);
+        LAUNCH(h, k_exclusive_scan, 1, 1024, 0, h->flag2.p, h->pos2.p, D.nwat);
+        LAUNCH(h, k_compact, cdiv(D.nwat, 256), 256, 0, D.nwat, h->flag2.p, h->pos2.p, h->qw_list.p);
+        CU(cudaMemcpyAsync(&h->nqw, h->pos2.p + D.nwat, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+        h->qw_done = true;
+    }
+    return 0;
+}
+
 static int build_device(qnb_handle *h, const double *hx_for_grid) {
     const Dev &D = h->D;
     drop_graphs(h);   // row pointers, counts and list sizes are baked into the captured launches
@@ -559,6 +583,7 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
         h->counts.ensure(3 * (size_t)std::max(nu, 1)) || h->row_tot.ensure(std::max(nu, 1) + 1) ||
         h->row_off.ensure(std::max(nu, 1) + 2) ||
         h->flag.ensure(std::max({D.natom, D.nwat, 1}) + 1) || h->pos.ensure(std::max({D.natom, D.nwat, 1}) + 2) ||
+        h->flag2.ensure(std::max(D.nwat, 1) + 1) || h->pos2.ensure(std::max(D.nwat, 1) + 2) ||
         h->qp_list.ensure(std::max(D.nat_solute, 1)) || h->qw_list.ensure(std::max(D.nwat, 1)) ||
         h->qp_shift_atom.ensure(std::max(D.ncgp_solute, 1)) || h->item_pos.ensure(std::max(nu, 1)) || h->item_posf.ensure(std::max(nu, 1)) || h->item_scr.ensure(std::max(nu, 1)) ||
         h->src.ensure(std::max(D.natom, 1)) || h->srcf.ensure(std::max(D.natom, 1)) || h->cell_unsorted.ensure(std::max(nu, 1)) ||
@@ -604,9 +629,26 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
             if (allpairs && !h->lrf_mom.ensure((size_t)kLrfRaw * nu)) {
                 cudaMemsetAsync(h->lrf_mom.p, 0, sizeof(double) * kLrfRaw * (size_t)nu, ls);
                 const int tb = cdiv(nu, 128);
-                const int slices = std::max(1, std::min(cdiv(nu, kLrfTileItems), cdiv(6 * h->nsm, tb)));
-                LAUNCH_ON(h, ls, k_lrf_allpairs, dim3(tb, slices), 128, 0, D, h->cut, h->x.p, h->upos.p, h->item_pos.p, h->item_posf.p,
-                          h->src_off.p, h->src.p, h->lrf.p, h->lrf_mom.p);
+                // one resident wave of equal slices (r02o: 896 blocks on 740 slots = 1.2 waves, the second a fifth full)
+                static const int ap_minb = [] { const char *e = getenv("QNB_LRFAP_MINB"); return e && atoi(e) == 5 ? 5 : 6; }();
+                static int occ_ap = 0;
+                if (!occ_ap) {
+                    if (ap_minb == 5) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ap, k_lrf_allpairs<5>, 128, 0);
+                    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ap, k_lrf_allpairs<6>, 128, 0);
+                    occ_ap = std::max(occ_ap, 1);
+                }
+                // QNB_LRFAP_BLOCKS=n (< occupancy): leave SM room for the row scan and chunk kernels that run next to it (unused
+                // dynamic shared memory caps the resident blocks)
+                static const int ap_blocks = [] { const char *e = getenv("QNB_LRFAP_BLOCKS"); return e ? std::max(1, atoi(e)) : 0; }();
+                const int nres = ap_blocks > 0 ? std::min(ap_blocks, occ_ap) : occ_ap;
+                const size_t pad = nres < occ_ap ? (size_t)(228 * 1024 / (nres + 1) + 1024 > 17 * 1024 ? 228 * 1024 / (nres + 1) + 1024 - 17 * 1024 : 0) : 0;
+                const int slices = std::max(1, std::min(cdiv(nu, kLrfTileItems), (nres * h->nsm) / tb));
+                if (ap_minb == 5)
+                    LAUNCH_ON(h, ls, k_lrf_allpairs<5>, dim3(tb, slices), 128, std::min<size_t>(pad, 30 * 1024), D, h->cut, h->x.p, h->upos.p, h->item_pos.p, h->item_posf.p,
+                              h->src_off.p, h->src.p, h->lrf.p, h->lrf_mom.p);
+                else
+                    LAUNCH_ON(h, ls, k_lrf_allpairs<6>, dim3(tb, slices), 128, 0, D, h->cut, h->x.p, h->upos.p, h->item_pos.p, h->item_posf.p,
+                              h->src_off.p, h->src.p, h->lrf.p, h->lrf_mom.p);
                 LAUNCH_ON(h, ls, k_lrf_expand, cdiv(nu * 40, 256), 256, 0, D, h->lrf_mom.p, h->lrf.p);
             } else
 #define LRFCASE(CP, RS, GN) LAUNCH_ON(h, ls, (k_lrf_accumulate<CP, RS, GN>), cdiv(nu, kRowWarps), 32 * kRowWarps, 0, D, h->cut, G, h->lrf_reach, h->x.p, h->upos.p, \
@@ -672,6 +714,9 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
         CU(cudaMemcpyAsync(&h->n_ww_e, eo_ww + nwat, sizeof(int), cudaMemcpyDeviceToHost, h->st));
         CU(cudaMemcpyAsync(&h->n_pp_e, eo_pp + nsol, sizeof(int), cudaMemcpyDeviceToHost, h->st));
         CU(cudaMemcpyAsync(&h->n_pw_e, eo_pw + nsol, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+        // Q-atom partner lists: built once when the cut-off covers everything (nbqplist L3678, nbqwlist L3889,
+        // nbqplist_box L3780, nbqwlist_box L3972); their counts ride on the same host round trip as the row sizes
+        if (launch_q_lists(h)) return 1;
         CU(cudaStreamSynchronize(h->st));   // the only host round trip of the build: sizes for the allocations
         h->total_rows = total;
         h->npk = npk;
@@ -713,29 +758,7 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
         if (h->nschunk > 0)
             LAUNCH(h, k_warp_starts, cdiv(4 * h->sgrid + 1, 128), 128, 0, D, 0, nsol, kITile, new_rows, h->counts.p, off_s, co_s, 4 * h->sgrid, h->wstart_s.p);
     }
-    // Q-atom partner lists: built once when the cut-off covers everything (nbqplist L3678, nbqwlist L3889,
-    // nbqplist_box L3780, nbqwlist_box L3972)
-    const double rex2 = h->T.s.rexcl_o * h->T.s.rexcl_o;
-    if (D.nqat > 0) {
-        const bool skip_qp = h->qp_done && (D.use_PBC ? (h->cut.Rq < 0.0) : (h->cut.rcq2 > rex2));
-        const bool skip_qw = h->qw_done && (D.use_PBC ? (h->cut.Rq < 0.0) : (h->cut.rcq2 > rex2));
-        if (!skip_qp && D.ncgp_solute > 0) {
-            LAUNCH(h, k_qp_flags, cdiv(D.ncgp_solute, 128), 128, 0, D, h->cut, h->x.p, h->flag.p, h->qp_shift_atom.p);
-            run_exclusive_scan(h, h->flag.p, h->pos.p, D.nat_solute);
-            LAUNCH(h, k_compact, cdiv(D.nat_solute, 256), 256, 0, D.nat_solute, h->flag.p, h->pos.p, h->qp_list.p);
-            CU(cudaMemcpyAsync(&h->nqp, h->pos.p + D.nat_solute, sizeof(int), cudaMemcpyDeviceToHost, h->st));
-            CU(cudaStreamSynchronize(h->st));
-            h->qp_done = true;
-        }
-        if (!skip_qw && D.nwat > 0) {
-            LAUNCH(h, k_qw_flags, cdiv(D.nwat, 128), 128, 0, D, h->cut, h->x.p, h->flag.p);
-            run_exclusive_scan(h, h->flag.p, h->pos.p, D.nwat);
-            LAUNCH(h, k_compact, cdiv(D.nwat, 256), 256, 0, D.nwat, h->flag.p, h->pos.p, h->qw_list.p);
-            CU(cudaMemcpyAsync(&h->nqw, h->pos.p + D.nwat, sizeof(int), cudaMemcpyDeviceToHost, h->st));
-            CU(cudaStreamSynchronize(h->st));
-            h->qw_done = true;
-        }
-    }
+    if (!(nu > 0 && md_lists)) { if (launch_q_lists(h)) return 1; }
     // LRF: the moments were started on the side stream after the cell tables (see above); join, then the exchange
     if (D.use_LRF && D.ncgp > 0 && !h->restoring) {
         if (lrf_forked) CU(cudaStreamWaitEvent(h->st, h->ev_join[kLrfStream], 0));
@@ -1785,8 +1808,7 @@ int qnb_bench_md(qnb_handle *h, const double *lambda, int flags, int steps, int 
     CU(cudaEventRecord(h->ev0, h->st));
     for (int k = 0; k < steps; k++) {
         if (nbcycle > 0 && k % nbcycle == 0) {
-            h->qp_done = h->qw_done = false;
-            if (build_device(h, h->hx)) return 1;
+            if (build_device(h, h->hx)) return 1;   // as qnb_build_lists: Q partner lists only when the cut-offs ask for it
         }
         if (step_device(h, flags)) return 1;
     }
@@ -1844,7 +1866,6 @@ int qnb_bench_build_lists(qnb_handle *h, int reps, float *ms_out) {
     h->time_build = true;
     for (int k = 0; k < 3; k++) h->build_ms[k] = 0.f;
     for (int k = 0; k < reps; k++) {
-        h->qp_done = h->qw_done = false;
         CU(cudaEventRecord(h->ev0, h->st));
         if (build_device(h, h->hx)) { h->time_build = false; return 1; }
         CU(cudaEventRecord(h->ev1, h->st));
@@ -1947,7 +1968,7 @@ int qnb_finalize(qnb_handle *h) {
     h->u_excl.release(); h->ljcode.release(); h->sp_code.release(); h->qp_tab.release(); h->qw_tab.release(); h->qp_tabf.release(); h->qw_tabf.release();
     h->qstatic.release(); h->x.release(); h->out.release(); h->lrf.release(); h->upos.release();
     h->cell_of.release(); h->cell_count.release(); h->cell_start.release(); h->cell_items.release(); h->counts.release();
-    h->row_tot.release(); h->row_off.release(); h->flag.release(); h->pos.release(); h->qp_list.release();
+    h->row_tot.release(); h->row_off.release(); h->flag.release(); h->pos.release(); h->flag2.release(); h->pos2.release(); h->qp_list.release();
     h->qw_list.release(); h->qp_shift_atom.release(); h->rows.release(); h->flush.release();
     h->pk_atom.release(); h->pk_ct.release(); h->pk_q.release(); h->pk_qd.release(); h->px.release(); h->py.release(); h->pz.release();
     h->nch.release(); h->choff.release(); h->ucost.release(); h->cost_off.release(); h->wstart_w.release(); h->wstart_s.release(); h->wdesc.release(); h->wrow.release(); h->sdesc.release(); h->srow.release(); h->sspec.release(); h->x_saved.release(); h->lrf_saved.release(); h->wp_theta.release(); h->wp_shell_n.release(); h->wp_shell_list.release(); h->wp_shell_theta.release(); h->lrf_mom.release();

@@ -217,6 +217,14 @@ __device__ __forceinline__ int split_slot(int lane, int base = 0, int count = N)
         return split_slot<H, MASK / 2>(lane, up ? base + H : base, up ? count - H : min(count, H));
     }
 }
+// double -> float ONCE: nvcc rematerialises a plain (float) cast of a loop-invariant double inside the loop to save a
+// register (r02o: 4.7 F2F per interaction in k_lrf_allpairs, the 16-lane XU pipe 31 % busy with them); a volatile asm
+// cannot be duplicated, so the converted value stays in its register
+__device__ __forceinline__ float f32_once(double v) {
+    float r;
+    asm volatile("cvt.rn.f32.f64 %0, %1;" : "=f"(r) : "d"(v));
+    return r;
+}
 // MUFU.RSQ alone (rsqrtf() wraps it in denormal scaling: three more instructions per pair)
 __device__ __forceinline__ float rsqrt_fast(float v) {
     float r;

@@ -356,12 +356,12 @@ k_rows_scan(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x, cons
         for (int d = 0; d < 3; d++) {
             double w = pu[d];
             if (D.use_PBC) w -= D.box[d] * floor(w * D.inv_box[d]);   // as the records are stored (k_pack_items)
-            puf[d] = (float)w;
+            puf[d] = f32_once(w);
         }
-        const float bx = (float)D.box[0], by = (float)D.box[1], bz = (float)D.box[2];
-        const float ibx = (float)D.inv_box[0], iby = (float)D.inv_box[1], ibz = (float)D.inv_box[2];
+        const float bx = f32_once(D.box[0]), by = f32_once(D.box[1]), bz = f32_once(D.box[2]);
+        const float ibx = f32_once(D.inv_box[0]), iby = f32_once(D.inv_box[1]), ibz = f32_once(D.inv_box[2]);
         // screening thresholds by the partner's kind (see screen_r2)
-        const float rc_s = (float)C.rc2_of(u_sol ? 0 : 1), rc_w = (float)C.rc2_of(u_sol ? 1 : 2);
+        const float rc_s = f32_once(C.rc2_of(u_sol ? 0 : 1)), rc_w = f32_once(C.rc2_of(u_sol ? 1 : 2));
         const float lo_s = rc_s * (1.0f - 1e-3f) - 0.05f, hi_s = rc_s * (1.0f + 1e-3f) + 0.05f;
         const float lo_w = rc_w * (1.0f - 1e-3f) - 0.05f, hi_w = rc_w * (1.0f + 1e-3f) + 0.05f;
         const int cu = cell_of[u];
@@ -809,8 +809,11 @@ constexpr int kLrfRaw = 24;
 // cannot reach the LRF shell are skipped and the x-range of the others is trimmed to the shell's chord, so the
 // per-candidate screening is nine FP32 instructions.  GENERAL adds what any-atom cut-offs and sharded builds need.
 struct LrfSeg { int lo, hi; float tx, ty, tz; };
+#ifndef QNB_LRF_MINB
+#define QNB_LRF_MINB 4
+#endif
 template <bool COMPACT, bool ROWSHIFT, bool GENERAL>
-__global__ void __launch_bounds__(32 * kRowWarps)
+__global__ void __launch_bounds__(32 * kRowWarps, QNB_LRF_MINB)
 k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x, const double *__restrict__ upos,
                  const int *__restrict__ cell_of, const int *__restrict__ cell_start, const int *__restrict__ cell_items,
                  const double4 *__restrict__ item_pos, const float4 *__restrict__ item_posf,
@@ -836,7 +839,7 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
     const double cx_ = lt[0], cy_ = lt[1], cz_ = lt[2];
     const double pt[3] = {upos[3 * t], upos[3 * t + 1], upos[3 * t + 2]};
     // any-atom mode: the deciding atoms sit up to rmax2/2 from either switch atom
-    const float rl = sqrtf(fmaxf((float)C.rclrf2, 0.f)) + (D.any_atom ? (float)C.rmax2 : 0.f);
+    const float rl = sqrtf(fmaxf(f32_once(C.rclrf2), 0.f)) + (D.any_atom ? f32_once(C.rmax2) : 0.f);
     const float hi_band = rl * rl * (1.0f + 1e-3f) + 0.05f;   // surely outside the LRF shell above this
     const bool any_all = C.lrf_all[0] || C.lrf_all[1] || C.lrf_all[2] || (D.any_atom && D.use_PBC && C.rclrf2 == -1.0);
     // phi0, phi1, phi2 in FP64 (FP32 phi2 was measured to move E%LRF by 1.1e-6 relative).  phi3 enters only the field,
@@ -880,19 +883,19 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
     // screening thresholds of this target against solute / water sources (FP32, see screen_r2)
     const bool t_sol = t < ns;
     const int cls_s = t_sol ? 0 : 1, cls_w = t_sol ? 1 : 2;     // class with a solute / a water source
-    auto lo_of = [](double c2) { return (float)c2 * (1.0f - 1e-3f) - 0.05f; };
-    auto hi_of = [](double c2) { return (float)c2 * (1.0f + 1e-3f) + 0.05f; };
+    auto lo_of = [](double c2) { return f32_once(c2) * (1.0f - 1e-3f) - 0.05f; };
+    auto hi_of = [](double c2) { return f32_once(c2) * (1.0f + 1e-3f) + 0.05f; };
     const float in_lo_s = lo_of(C.rc2_of(cls_s)), in_hi_s = hi_of(C.rc2_of(cls_s));
     const float in_lo_w = lo_of(C.rc2_of(cls_w)), in_hi_w = hi_of(C.rc2_of(cls_w));
     const float out_lo = lo_of(C.rclrf2), out_hi = hi_of(C.rclrf2);
     const bool all_s = C.lrf_all_of(cls_s), all_w = C.lrf_all_of(cls_w);
-    const float bx = (float)D.box[0], by = (float)D.box[1], bz = (float)D.box[2];
-    const float ibx = (float)D.inv_box[0], iby = (float)D.inv_box[1], ibz = (float)D.inv_box[2];
+    const float bx = f32_once(D.box[0]), by = f32_once(D.box[1]), bz = f32_once(D.box[2]);
+    const float ibx = f32_once(D.inv_box[0]), iby = f32_once(D.inv_box[1]), ibz = f32_once(D.inv_box[2]);
     // target position as the candidates are stored: wrapped into the box when periodic (k_pack_items)
     double ptw[3] = {pt[0], pt[1], pt[2]};
     if (G.periodic)
         for (int d = 0; d < 3; d++) ptw[d] -= D.box[d] * floor(ptw[d] * D.inv_box[d]);
-    const float ptf[3] = {(float)ptw[0], (float)ptw[1], (float)ptw[2]};
+    const float ptf[3] = {f32_once(ptw[0]), f32_once(ptw[1]), f32_once(ptw[2])};
     __shared__ LrfSeg seg_all[kRowWarps][kLrfSegBatch];   // item ranges [lo,hi) of the cell rows (+ target image) of this warp's target
     LrfSeg *seg = seg_all[wid];
     int qn = 0;   // entries waiting in this warp's queue (warp-uniform)
@@ -1029,7 +1032,8 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
 // and the moments of the slice are added to an unexpanded [nunit][20] buffer that k_lrf_expand turns into LRF_TYPE.
 // Switching-atom lists, unsharded, non-periodic only (the general kernel above serves everything else).
 constexpr int kLrfTileItems = 64, kLrfTileAtoms = 320;
-__global__ void __launch_bounds__(128)
+template <int MINB>   // resident blocks per SM the register allocation aims at (5: 96 registers, 6: 80)
+__global__ void __launch_bounds__(128, MINB)
 k_lrf_allpairs(Dev D, Cut C, const double *__restrict__ x, const double *__restrict__ upos, const double4 *__restrict__ item_pos,
                const float4 *__restrict__ item_posf, const int *__restrict__ src_off, const double4 *__restrict__ src,
                const double *__restrict__ lrf, double *__restrict__ mom /* [nunit][kLrfRaw] raw sums */) {
@@ -1045,12 +1049,12 @@ k_lrf_allpairs(Dev D, Cut C, const double *__restrict__ x, const double *__restr
     const int gt = D.u_grp[tt];
     const double cx_ = lrf[(size_t)QNB_LRF_STRIDE * gt], cy_ = lrf[(size_t)QNB_LRF_STRIDE * gt + 1], cz_ = lrf[(size_t)QNB_LRF_STRIDE * gt + 2];
     const double pt[3] = {upos[3 * tt], upos[3 * tt + 1], upos[3 * tt + 2]};
-    const float ptf[3] = {(float)pt[0], (float)pt[1], (float)pt[2]};
-    const float cxf = (float)cx_, cyf = (float)cy_, czf = (float)cz_;
+    const float ptf[3] = {f32_once(pt[0]), f32_once(pt[1]), f32_once(pt[2])};
+    const float cxf = f32_once(cx_), cyf = f32_once(cy_), czf = f32_once(cz_);
     const bool t_sol = tt < ns;
     const int cls_s = t_sol ? 0 : 1, cls_w = t_sol ? 1 : 2;
-    auto lo_of = [](double c2) { return (float)c2 * (1.0f - 1e-3f) - 0.05f; };
-    auto hi_of = [](double c2) { return (float)c2 * (1.0f + 1e-3f) + 0.05f; };
+    auto lo_of = [](double c2) { return f32_once(c2) * (1.0f - 1e-3f) - 0.05f; };
+    auto hi_of = [](double c2) { return f32_once(c2) * (1.0f + 1e-3f) + 0.05f; };
     const float in_lo_s = lo_of(C.rc2_of(cls_s)), in_hi_s = hi_of(C.rc2_of(cls_s));
     const float in_lo_w = lo_of(C.rc2_of(cls_w)), in_hi_w = hi_of(C.rc2_of(cls_w));
     const float out_lo = lo_of(C.rclrf2), out_hi = hi_of(C.rclrf2);
