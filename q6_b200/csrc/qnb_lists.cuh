@@ -865,12 +865,19 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
         }
         const float oxf = (float)ox, oyf = (float)oy, ozf = (float)oz;
         const int a0 = src_off[idx], a1 = src_off[idx + 1];
-#pragma unroll 3
-        for (int k = a0; k < a1; k++) {
-            const double4 sa = src[k];
-            const float4 sf = srcf[k];
-            lrf_atom(m, h, sa.x - ox, sa.y - oy, sa.z - oz, sa.w, sf.x - oxf, sf.y - oyf, sf.z - ozf, sf.w);
-        }
+        if (a1 - a0 == 3) {
+            // three-atom unit (every water, most solute groups): all nine loads in flight before the first use
+            const double4 s0 = src[a0], s1 = src[a0 + 1], s2 = src[a0 + 2];
+            const float4 f0 = srcf[a0], f1 = srcf[a0 + 1], f2 = srcf[a0 + 2];
+            lrf_atom(m, h, s0.x - ox, s0.y - oy, s0.z - oz, s0.w, f0.x - oxf, f0.y - oyf, f0.z - ozf, f0.w);
+            lrf_atom(m, h, s1.x - ox, s1.y - oy, s1.z - oz, s1.w, f1.x - oxf, f1.y - oyf, f1.z - ozf, f1.w);
+            lrf_atom(m, h, s2.x - ox, s2.y - oy, s2.z - oz, s2.w, f2.x - oxf, f2.y - oyf, f2.z - ozf, f2.w);
+        } else
+            for (int k = a0; k < a1; k++) {
+                const double4 sa = src[k];
+                const float4 sf = srcf[k];
+                lrf_atom(m, h, sa.x - ox, sa.y - oy, sa.z - oz, sa.w, sf.x - oxf, sf.y - oyf, sf.z - ozf, sf.w);
+            }
     };
 
     const int cu = cell_of[t];
@@ -949,14 +956,29 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
             nseg += __popc(keep);
         }
         __syncwarp();
-        for (int r = 0; r < nseg; r++) {
-            const LrfSeg sg = seg[r];
-            const int lo = sg.lo, hi = sg.hi;
-            for (int base = lo; base < hi; base += 32) {
+        // The candidates of all segments are walked as one sequence of 32-wide steps; the screening record of the NEXT step
+        // (possibly the first of the next segment) is loaded before the current one is processed: with one warp per target
+        // the load -> test -> queue chain of a step is otherwise fully exposed (segments hold one or two steps each).
+        if (nseg > 0) {
+            int r = 0;
+            LrfSeg sg = seg[0];
+            int base = sg.lo;
+            float4 pf_cur = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (base + lane < sg.hi) pf_cur = item_posf[base + lane];
+            while (r < nseg) {
+                int nr = r, nbase = base + 32;
+                LrfSeg nsg = sg;
+                if (nbase >= sg.hi) {
+                    nr = r + 1;
+                    if (nr < nseg) { nsg = seg[nr]; nbase = nsg.lo; }
+                }
+                float4 pf_next = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (nr < nseg && nbase + lane < nsg.hi) pf_next = item_posf[nbase + lane];
+                const int hi = sg.hi;
                 const int idx = base + lane;
                 bool accept = false;
                 if (idx < hi) {
-                    const float4 pf = item_posf[idx];
+                    const float4 pf = pf_cur;
                     const int s = __float_as_int(pf.w);
                     float dx = pf.x - sg.tx, dy = pf.y - sg.ty, dz = pf.z - sg.tz;
                     if (!ROWSHIFT && D.use_PBC) { dx -= bx * rintf(dx * ibx); dy -= by * rintf(dy * iby); dz -= bz * rintf(dz * ibz); }
@@ -989,8 +1011,7 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
                 if (!COMPACT) {
                     // nearly every scanned unit is a source (sphere with RcLRF covering it): no queueing needed
                     if (accept) accumulate(idx);
-                    continue;
-                }
+                } else {
                 const unsigned mask = __ballot_sync(kFull, accept);
                 if (accept) queue[wid][qn + __popc(mask & ((1u << lane) - 1u))] = idx;
                 qn += __popc(mask);
@@ -1004,6 +1025,8 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
                     if (lane < rest) queue[wid][lane] = moved;
                     qn = rest;
                 }
+                }   // end of the step (COMPACT path falls through, !COMPACT path jumps here)
+                r = nr; base = nbase; sg = nsg; pf_cur = pf_next;
             }
         }
     }
