@@ -625,10 +625,9 @@ __device__ __forceinline__ void q_shift(const Dev &D, const double *__restrict__
 // the other gradient paths: FP64 only to form coordinates relative to a local origin (the Q switch atom; periodic
 // shift folded in), FP32 pair arithmetic with FP32 parameter tables.
 template <bool PBC>
-__global__ void __launch_bounds__(128)
-k_q_partner(Dev D, const double *__restrict__ x, const double *__restrict__ lambda, int nqp,
-            const int *__restrict__ qp_list, const int *__restrict__ qp_shift_atom, int nqw,
-            const int *__restrict__ qw_list, double *__restrict__ grad) {
+struct QPartnerBody {
+    // BX, NBX, BY, NBY: block index and grid size (the batched launch passes those of the window, k_batched)
+    static __device__ __forceinline__ void run(const Dev &D, const double *__restrict__ x, const double *__restrict__ lambda, int nqp, const int *__restrict__ qp_list, const int *__restrict__ qp_shift_atom, int nqw, const int *__restrict__ qw_list, double *__restrict__ grad, const int BX, const int NBX, const int BY, const int NBY) {
     extern __shared__ float shq[];
     float *xq = shq;                 // [nqat][3] relative to the origin
     float *lam = shq + 3 * D.nqat;   // [nstates]
@@ -640,7 +639,7 @@ k_q_partner(Dev D, const double *__restrict__ x, const double *__restrict__ lamb
     }
     for (int k = threadIdx.x; k < D.nstates; k += blockDim.x) lam[k] = (float)lambda[k];
     __syncthreads();
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = BX * blockDim.x + threadIdx.x;
     if (p >= nqp + 3 * nqw) return;
     const int nst = D.nstates;
     const QSite s = q_site(D, p, nqp, qp_list, qw_list);
@@ -651,9 +650,9 @@ k_q_partner(Dev D, const double *__restrict__ x, const double *__restrict__ lamb
                 jz = (float)((x[3 * s.atom + 2] - oz) + shf[2]);
     const bool coul_only = s.water && D.spc_water && s.site > 0;   // nbe_qspc
     float gx = 0.f, gy = 0.f, gz = 0.f;
-    // the Q-atoms are dealt to gridDim.y blocks so that the few thousand partner sites still fill the machine
-    const int qchunk = (D.nqat + gridDim.y - 1) / gridDim.y;
-    const int q0 = blockIdx.y * qchunk, q1 = min(D.nqat, q0 + qchunk);
+    // the Q-atoms are dealt to NBY blocks so that the few thousand partner sites still fill the machine
+    const int qchunk = (D.nqat + NBY - 1) / NBY;
+    const int q0 = BY * qchunk, q1 = min(D.nqat, q0 + qchunk);
 #pragma unroll 2
     for (int q = q0; q < q1; q++) {
         const float vx = jx - xq[3 * q], vy = jy - xq[3 * q + 1], vz = jz - xq[3 * q + 2];
@@ -677,17 +676,24 @@ k_q_partner(Dev D, const double *__restrict__ x, const double *__restrict__ lamb
     }
     atomicAdd(&grad[3 * s.atom], (double)gx); atomicAdd(&grad[3 * s.atom + 1], (double)gy); atomicAdd(&grad[3 * s.atom + 2], (double)gz);
 }
+};
+template <bool PBC>
+__global__ void __launch_bounds__(128)
+k_q_partner(Dev D, const double *__restrict__ x, const double *__restrict__ lambda, int nqp,
+            const int *__restrict__ qp_list, const int *__restrict__ qp_shift_atom, int nqw,
+            const int *__restrict__ qw_list, double *__restrict__ grad) {
+    QPartnerBody<PBC>::run(D, x, lambda, nqp, qp_list, qp_shift_atom, nqw, qw_list, grad, blockIdx.x, gridDim.x, blockIdx.y, gridDim.y);
+}
 
 // Gradient on the Q-atoms and the per-state energies EQ(:)%qp, EQ(:)%qw.  Block (q, slice): the partner sites
 // are dealt round-robin to gridDim.y slices so that a few dozen Q-atoms still fill the machine.
 template <bool PBC, int NS>
-__global__ void __launch_bounds__(128)
-k_q_atom(Dev D, const double *__restrict__ x, const double *__restrict__ lambda, int nqp,
-         const int *__restrict__ qp_list, const int *__restrict__ qp_shift_atom, int nqw,
-         const int *__restrict__ qw_list, double *__restrict__ grad, double *__restrict__ Eslots, int nE) {
+struct QAtomBody {
+    // BX, NBX, BY, NBY: block index and grid size (the batched launch passes those of the window, k_batched)
+    static __device__ __forceinline__ void run(const Dev &D, const double *__restrict__ x, const double *__restrict__ lambda, int nqp, const int *__restrict__ qp_list, const int *__restrict__ qp_shift_atom, int nqw, const int *__restrict__ qw_list, double *__restrict__ grad, double *__restrict__ Eslots, int nE, const int BX, const int NBX, const int BY, const int NBY) {
     __shared__ double red[4][3 + 4 * NS];
-    double *EQ = Eslots + (size_t)((blockIdx.x + blockIdx.y) & (kESlots - 1)) * nE + QNB_E_COUNT;
-    const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    double *EQ = Eslots + (size_t)((BX + BY) & (kESlots - 1)) * nE + QNB_E_COUNT;
+    const int q = BX, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int nst = D.nstates;
     const int iat = D.iqseq[q];
     const double qx = x[3 * iat], qy = x[3 * iat + 1], qz = x[3 * iat + 2];
@@ -696,7 +702,7 @@ k_q_atom(Dev D, const double *__restrict__ x, const double *__restrict__ lambda,
     for (int s = 0; s < NS; s++) { lam[s] = s < nst ? lambda[s] : 0.0; eel[s] = evdw[s] = wel[s] = wvdw[s] = 0.0; }
     double gx = 0, gy = 0, gz = 0;
     const int nsite = nqp + 3 * nqw;
-    for (int p = blockIdx.y * blockDim.x + tid; p < nsite; p += gridDim.y * blockDim.x) {
+    for (int p = BY * blockDim.x + tid; p < nsite; p += NBY * blockDim.x) {
         const QSite s = q_site(D, p, nqp, qp_list, qw_list);
         double shf[3];
         q_shift<PBC>(D, x, s, qp_shift_atom, shf);
@@ -742,12 +748,21 @@ k_q_atom(Dev D, const double *__restrict__ x, const double *__restrict__ lambda,
         }
     }
 }
+};
+template <bool PBC, int NS>
+__global__ void __launch_bounds__(128)
+k_q_atom(Dev D, const double *__restrict__ x, const double *__restrict__ lambda, int nqp,
+         const int *__restrict__ qp_list, const int *__restrict__ qp_shift_atom, int nqw,
+         const int *__restrict__ qw_list, double *__restrict__ grad, double *__restrict__ Eslots, int nE) {
+    QAtomBody<PBC, NS>::run(D, x, lambda, nqp, qp_list, qp_shift_atom, nqw, qw_list, grad, Eslots, nE, blockIdx.x, gridDim.x, blockIdx.y, gridDim.y);
+}
 
 // Static lists nbqq / nbqqp (nonbond_qq L5013, nonbond_qqp L5085): one thread per (pair,state) entry.
 struct QStatic { int i, j, state, soft; QPar4 p; };
-__global__ void k_qq_static(int n, int nqq, const QStatic *__restrict__ lst, const double *__restrict__ x,
-                            const double *__restrict__ lambda, double *__restrict__ grad, double *__restrict__ Eslots, int nE) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+struct QqStaticBody {
+    // BX, NBX, BY, NBY: block index and grid size (the batched launch passes those of the window, k_batched)
+    static __device__ __forceinline__ void run(int n, int nqq, const QStatic *__restrict__ lst, const double *__restrict__ x, const double *__restrict__ lambda, double *__restrict__ grad, double *__restrict__ Eslots, int nE, const int BX, const int NBX, const int BY, const int NBY) {
+    const int k = BX * blockDim.x + threadIdx.x;
     double *EQ = Eslots + (size_t)(k & (kESlots - 1)) * nE + QNB_E_COUNT;
     if (k >= n) return;
     const QStatic e = lst[k];
@@ -772,12 +787,19 @@ __global__ void k_qq_static(int n, int nqq, const QStatic *__restrict__ lst, con
     atomicAdd(&EQ[QNB_EQ_STRIDE * e.state + o], vel);
     atomicAdd(&EQ[QNB_EQ_STRIDE * e.state + o + 1], vvdw);
 }
+};
+__global__ void
+k_qq_static(int n, int nqq, const QStatic *__restrict__ lst, const double *__restrict__ x,
+                            const double *__restrict__ lambda, double *__restrict__ grad, double *__restrict__ Eslots, int nE) {
+    QqStaticBody::run(n, nqq, lst, x, lambda, grad, Eslots, nE, blockIdx.x, gridDim.x, blockIdx.y, gridDim.y);
+}
 
 // lrf_taylor (nonbondene.f90:507-571)
-__global__ void k_lrf_taylor(Dev D, const double *__restrict__ x, const double *__restrict__ lrf,
-                             double *__restrict__ grad, double *__restrict__ Eslots, int nE) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    double *E = Eslots + (size_t)(blockIdx.x & (kESlots - 1)) * nE;
+struct LrfTaylorBody {
+    // BX, NBX, BY, NBY: block index and grid size (the batched launch passes those of the window, k_batched)
+    static __device__ __forceinline__ void run(const Dev &D, const double *__restrict__ x, const double *__restrict__ lrf, double *__restrict__ grad, double *__restrict__ Eslots, int nE, const int BX, const int NBX, const int BY, const int NBY) {
+    const int i = BX * blockDim.x + threadIdx.x;
+    double *E = Eslots + (size_t)(BX & (kESlots - 1)) * nE;
     double e = 0.0;
     if (i < D.natom && i + 1 >= D.at_s && i + 1 <= D.at_e && !D.is_q[i] && (D.use_PBC || !D.excl[i])) {
         const double *l = lrf + (size_t)QNB_LRF_STRIDE * D.grp_of_atom[i];
@@ -805,6 +827,12 @@ __global__ void k_lrf_taylor(Dev D, const double *__restrict__ x, const double *
     }
     e = warp_sum(e);
     if ((threadIdx.x & 31) == 0 && e != 0.0) atomicAdd(&E[QNB_E_LRF], e);
+}
+};
+__global__ void
+k_lrf_taylor(Dev D, const double *__restrict__ x, const double *__restrict__ lrf,
+                             double *__restrict__ grad, double *__restrict__ Eslots, int nE) {
+    LrfTaylorBody::run(D, x, lrf, grad, Eslots, nE, blockIdx.x, gridDim.x, blockIdx.y, gridDim.y);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -17,6 +17,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cuda/std/tuple>
 
 namespace qnb {
 
@@ -101,6 +102,28 @@ struct Cut {
     __host__ __device__ double rc2_of(int cls) const { return cls == 0 ? rc2[0] : cls == 1 ? rc2[1] : rc2[2]; }
     __host__ __device__ int lrf_all_of(int cls) const { return cls == 0 ? lrf_all[0] : cls == 1 ? lrf_all[1] : lrf_all[2]; }
 };
+
+// ------------------------------------------------------------------ one launch for several systems
+// The step kernels are written as Body functors (struct XBody { static __device__ void run(args..., BX, NBX, BY, NBY) })
+// with a thin __global__ wrapper each.  k_batched runs the same body for W systems (lambda windows of a FEP farm) in ONE
+// launch: blockIdx.z names the system, its argument tuple lies in device memory and is copied to shared memory first,
+// its own grid size comes from `grids` (blocks beyond it leave at once).  A 12 k-atom system cannot fill 148 SMs with a
+// single wave of any kernel; seven of them per launch amortise the launch, the ramp and the tail.
+template <class Body, int THREADS, int MINB, class... P>
+__global__ void __launch_bounds__(THREADS, MINB) k_batched(const cuda::std::tuple<P...> *__restrict__ args, const int2 *__restrict__ grids) {
+    using T = cuda::std::tuple<P...>;
+    __shared__ alignas(16) unsigned char raw[sizeof(T)];
+    const int2 g = grids[blockIdx.z];
+    if ((int)blockIdx.x >= g.x || (int)blockIdx.y >= g.y) return;
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(args + blockIdx.z);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(raw);
+        for (int i = threadIdx.x; i < (int)(sizeof(T) / 4); i += THREADS) dst[i] = src[i];
+    }
+    __syncthreads();
+    const T &t = *reinterpret_cast<const T *>(raw);
+    cuda::std::apply([&](const P &...p) { Body::run(p..., (int)blockIdx.x, g.x, (int)blockIdx.y, g.y); }, t);
+}
 
 // ------------------------------------------------------------------ all-reduce over peer memory
 // The ranks of one node (one process per GPU) map each other's arena [out | lrf | control] through CUDA IPC; NVSwitch

@@ -159,12 +159,19 @@ __global__ void k_set_bead(int natq, const int *__restrict__ atoms0, const doubl
     x[3 * atoms0[k / 3] + k % 3] = base[k] + disp[k];
 }
 // fixed-order sum of the replicated energy slots: dst[k] = sum_s E[s][k]
-__global__ void k_collect_energies(int nE, int nslot, const double *__restrict__ E, double *__restrict__ dst) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+struct CollectEnergiesBody {
+    // BX, NBX, BY, NBY: block index and grid size (the batched launch passes those of the window, k_batched)
+    static __device__ __forceinline__ void run(int nE, int nslot, const double *__restrict__ E, double *__restrict__ dst, const int BX, const int NBX, const int BY, const int NBY) {
+    const int k = BX * blockDim.x + threadIdx.x;
     if (k >= nE) return;
     double e = 0;
     for (int s = 0; s < nslot; s++) e += E[(size_t)s * nE + k];
     dst[k] = e;
+}
+};
+__global__ void
+k_collect_energies(int nE, int nslot, const double *__restrict__ E, double *__restrict__ dst) {
+    CollectEnergiesBody::run(nE, nslot, E, dst, blockIdx.x, gridDim.x, blockIdx.y, gridDim.y);
 }
 
 // range of cells along one dimension around c with reach m

@@ -54,12 +54,14 @@ __device__ __forceinline__ f2 rsq2(f2 a) { return mk2(rsqrt_fast(a.x), rsqrt_fas
 //   own   = the same three float4 per water, indexed by water number (the own molecule of a water row), the water
 //           number in the third one's .z
 // and px/py/pz: FP64 coordinates in packed order (energy kernel)
-__global__ void __launch_bounds__(256)
-k_pack_step(int npk, FixFrame F, int nat_solute, const int *__restrict__ pk_atom, const int *__restrict__ pk_sw,
-            const float *__restrict__ pk_q, const int *__restrict__ pk_ct, const double *__restrict__ x,
-            double *__restrict__ px, double *__restrict__ py, double *__restrict__ pz, int4 *__restrict__ rec_i,
-            float4 *__restrict__ rec_f, float4 *__restrict__ wT, float4 *__restrict__ own, double2 *__restrict__ wd) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+struct PackStepBody {
+    // BX, NBX, BY, NBY: block index and grid size (the batched launch passes those of the window, k_batched)
+    static __device__ __forceinline__ void run(int npk, const FixFrame &F, int nat_solute, const int *__restrict__ pk_atom, const int *__restrict__ pk_sw, const float *__restrict__ pk_q, const int *__restrict__ pk_ct, const double *__restrict__ x, double *__restrict__ px, double *__restrict__ py, double *__restrict__ pz, int4 *__restrict__ rec_i, float4 *__restrict__ rec_f, float4 *__restrict__ wT, float4 *__restrict__ own, double2 *__restrict__ wd, double *__restrict__ zero_out, int nzero, const double *__restrict__ lam_src, double *__restrict__ lam_dst, int nlam, const int BX, const int NBX, const int BY, const int NBY) {
+    const int p = BX * blockDim.x + threadIdx.x;
+    // batched steps fold the clearing of the output buffer and the upload of lambda into this kernel (two graph nodes less
+    // per window); single steps pass null pointers
+    if (zero_out) for (int i = p; i < nzero; i += NBX * blockDim.x) zero_out[i] = 0.0;
+    if (lam_src && p < nlam) lam_dst[p] = lam_src[p];
     if (p >= npk) return;
     const int i = pk_atom[p], sw = pk_sw[p];
     const double xi = x[3 * i], yi = x[3 * i + 1], zi = x[3 * i + 2];
@@ -85,6 +87,15 @@ k_pack_step(int npk, FixFrame F, int nat_solute, const int *__restrict__ pk_atom
         o[0] = make_double2(xi, yi); o[1] = make_double2(zi, x[3 * i + 3]); o[2] = make_double2(x[3 * i + 4], x[3 * i + 5]);
         o[3] = make_double2(x[3 * i + 6], x[3 * i + 7]); o[4] = make_double2(x[3 * i + 8], 0.0);
     }
+}
+};
+__global__ void __launch_bounds__(256)
+k_pack_step(int npk, FixFrame F, int nat_solute, const int *__restrict__ pk_atom, const int *__restrict__ pk_sw,
+            const float *__restrict__ pk_q, const int *__restrict__ pk_ct, const double *__restrict__ x,
+            double *__restrict__ px, double *__restrict__ py, double *__restrict__ pz, int4 *__restrict__ rec_i,
+            float4 *__restrict__ rec_f, float4 *__restrict__ wT, float4 *__restrict__ own, double2 *__restrict__ wd,
+            double *__restrict__ zero_out, int nzero, const double *__restrict__ lam_src, double *__restrict__ lam_dst, int nlam) {
+    PackStepBody::run(npk, F, nat_solute, pk_atom, pk_sw, pk_q, pk_ct, x, px, py, pz, rec_i, rec_f, wT, own, wd, zero_out, nzero, lam_src, lam_dst, nlam, blockIdx.x, gridDim.x, blockIdx.y, gridDim.y);
 }
 
 // FP32 parameters of the row kernels (kernel argument, constant bank)
@@ -150,14 +161,12 @@ struct WRec { float4 a, b, c; };   // a partner's record: water {wT[p], wT[p+1],
 
 // MINB: resident blocks per SM the register allocation aims at (QNB_WROWS_MINB selects at run time)
 template <bool SPC, int MINB>
-__global__ void __launch_bounds__(128, MINB)
-k_water_rows(RowPar P, const int4 *__restrict__ rec_i, const float4 *__restrict__ rec_f, const float4 *__restrict__ wT,
-             const float4 *__restrict__ own, const float2 *__restrict__ pw0, const float4 *__restrict__ pw12,
-             const int *__restrict__ wstart, const int2 *__restrict__ cdesc, const uint32_t *__restrict__ crow,
-             int i0_water /* nat_solute */, double *__restrict__ grad) {
+struct WaterRowsBody {
+    // BX, NBX, BY, NBY: block index and grid size (the batched launch passes those of the window, k_batched)
+    static __device__ __forceinline__ void run(const RowPar &P, const int4 *__restrict__ rec_i, const float4 *__restrict__ rec_f, const float4 *__restrict__ wT, const float4 *__restrict__ own, const float2 *__restrict__ pw0, const float4 *__restrict__ pw12, const int *__restrict__ wstart, const int2 *__restrict__ cdesc, const uint32_t *__restrict__ crow, int i0_water, double *__restrict__ grad, const int BX, const int NBX, const int BY, const int NBY) {
     __shared__ float4 Own[4][4][4];            // [warp][slot][record part]; the issue side runs at most three row changes ahead
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int gw = (BX * blockDim.x + threadIdx.x) >> 5;
     const int c0 = wstart[gw], c1 = wstart[gw + 1];
     if (c0 >= c1) return;
     const unsigned sOwn = smem_addr(&Own[wib][0][0]);
@@ -306,6 +315,15 @@ k_water_rows(RowPar P, const int4 *__restrict__ rec_i, const float4 *__restrict_
 #undef QNB_WSTEP
     flush();
 }
+};
+template <bool SPC, int MINB>
+__global__ void __launch_bounds__(128, MINB)
+k_water_rows(RowPar P, const int4 *__restrict__ rec_i, const float4 *__restrict__ rec_f, const float4 *__restrict__ wT,
+             const float4 *__restrict__ own, const float2 *__restrict__ pw0, const float4 *__restrict__ pw12,
+             const int *__restrict__ wstart, const int2 *__restrict__ cdesc, const uint32_t *__restrict__ crow,
+             int i0_water /* nat_solute */, double *__restrict__ grad) {
+    WaterRowsBody<SPC, MINB>::run(P, rec_i, rec_f, wT, own, pw0, pw12, wstart, cdesc, crow, i0_water, grad, blockIdx.x, gridDim.x, blockIdx.y, gridDim.y);
+}
 
 // ------------------------------------------------------------------------------------------------
 // Solute rows, gradient only: pp (both sides) + the solute side of pw.  A chunk belongs to one (charge group, tile of
@@ -316,14 +334,11 @@ k_water_rows(RowPar P, const int4 *__restrict__ rec_i, const float4 *__restrict_
 #define QNB_SROWS_MINB 4
 #endif
 template <bool HLJ /* solvent hydrogens carry LJ against some solute type */>
-__global__ void __launch_bounds__(128, QNB_SROWS_MINB)
-k_solute_rows(RowPar P, const int *__restrict__ upk, const int *__restrict__ nq_off, const int4 *__restrict__ rec_i,
-              const float4 *__restrict__ rec_f, const float4 *__restrict__ wT, const float2 *__restrict__ ljp,
-              const float2 *__restrict__ pw0, const float4 *__restrict__ pw12, const int *__restrict__ wstart,
-              const int2 *__restrict__ cdesc, const uint32_t *__restrict__ crow, const uint16_t *__restrict__ cspec,
-              const int *__restrict__ pk_atom, double *__restrict__ grad) {
+struct SoluteRowsBody {
+    // BX, NBX, BY, NBY: block index and grid size (the batched launch passes those of the window, k_batched)
+    static __device__ __forceinline__ void run(const RowPar &P, const int *__restrict__ upk, const int *__restrict__ nq_off, const int4 *__restrict__ rec_i, const float4 *__restrict__ rec_f, const float4 *__restrict__ wT, const float2 *__restrict__ ljp, const float2 *__restrict__ pw0, const float4 *__restrict__ pw12, const int *__restrict__ wstart, const int2 *__restrict__ cdesc, const uint32_t *__restrict__ crow, const uint16_t *__restrict__ cspec, const int *__restrict__ pk_atom, double *__restrict__ grad, const int BX, const int NBX, const int BY, const int NBY) {
     const int lane = threadIdx.x & 31;
-    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int gw = (BX * blockDim.x + threadIdx.x) >> 5;
     const int c0 = wstart[gw], c1 = wstart[gw + 1];
     if (c0 >= c1) return;
     int cur_key = -1, nt = 0, pi0 = 0;
@@ -431,6 +446,16 @@ k_solute_rows(RowPar P, const int *__restrict__ upk, const int *__restrict__ nq_
     }
     flush();
 }
+};
+template <bool HLJ /* solvent hydrogens carry LJ against some solute type */>
+__global__ void __launch_bounds__(128, QNB_SROWS_MINB)
+k_solute_rows(RowPar P, const int *__restrict__ upk, const int *__restrict__ nq_off, const int4 *__restrict__ rec_i,
+              const float4 *__restrict__ rec_f, const float4 *__restrict__ wT, const float2 *__restrict__ ljp,
+              const float2 *__restrict__ pw0, const float4 *__restrict__ pw12, const int *__restrict__ wstart,
+              const int2 *__restrict__ cdesc, const uint32_t *__restrict__ crow, const uint16_t *__restrict__ cspec,
+              const int *__restrict__ pk_atom, double *__restrict__ grad) {
+    SoluteRowsBody<HLJ>::run(P, upk, nq_off, rec_i, rec_f, wT, ljp, pw0, pw12, wstart, cdesc, crow, cspec, pk_atom, grad, blockIdx.x, gridDim.x, blockIdx.y, gridDim.y);
+}
 
 // ------------------------------------------------------------------------------------------------
 // Energies: one thread per listed pair (the reference's own list: each pair once), FP64.
@@ -464,13 +489,10 @@ __device__ __forceinline__ void lj_f64(const EnergyPar &P, const double *__restr
 }
 
 template <bool PBC>
-__global__ void __launch_bounds__(128)
-k_pair_energy(EnergyPar P, int n_ww, const int2 *__restrict__ ww_pairs, int n_pp, const int2 *__restrict__ pp_pairs,
-              int n_pw, const int2 *__restrict__ pw_pairs, const double *__restrict__ px, const double *__restrict__ py,
-              const double *__restrict__ pz, const double *__restrict__ pk_qd, const int *__restrict__ pk_ct,
-              const int *__restrict__ pk_sw, const double *__restrict__ x, const double2 *__restrict__ wd,
-              const double *__restrict__ ljd, const uint8_t *__restrict__ ljcode, double *__restrict__ Eslots, int nE) {
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+struct PairEnergyBody {
+    // BX, NBX, BY, NBY: block index and grid size (the batched launch passes those of the window, k_batched)
+    static __device__ __forceinline__ void run(const EnergyPar &P, int n_ww, const int2 *__restrict__ ww_pairs, int n_pp, const int2 *__restrict__ pp_pairs, int n_pw, const int2 *__restrict__ pw_pairs, const double *__restrict__ px, const double *__restrict__ py, const double *__restrict__ pz, const double *__restrict__ pk_qd, const int *__restrict__ pk_ct, const int *__restrict__ pk_sw, const double *__restrict__ x, const double2 *__restrict__ wd, const double *__restrict__ ljd, const uint8_t *__restrict__ ljcode, double *__restrict__ Eslots, int nE, const int BX, const int NBX, const int BY, const int NBY) {
+    const int tid = BX * blockDim.x + threadIdx.x, nthr = NBX * blockDim.x;
     double e_ww_el = 0.0, e_ww_vdw = 0.0, e_pp_el = 0.0, e_pp_vdw = 0.0, e_pw_el = 0.0, e_pw_vdw = 0.0;
     // ---- water-water
     {
@@ -593,8 +615,18 @@ k_pair_energy(EnergyPar P, int n_ww, const int2 *__restrict__ ww_pairs, int n_pp
     __syncthreads();
     if (threadIdx.x < 6) {
         const double s = (red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x]);
-        if (s != 0.0) atomicAdd(&Eslots[(size_t)(blockIdx.x & (kESlots - 1)) * nE + threadIdx.x], s);
+        if (s != 0.0) atomicAdd(&Eslots[(size_t)(BX & (kESlots - 1)) * nE + threadIdx.x], s);
     }
+}
+};
+template <bool PBC>
+__global__ void __launch_bounds__(128)
+k_pair_energy(EnergyPar P, int n_ww, const int2 *__restrict__ ww_pairs, int n_pp, const int2 *__restrict__ pp_pairs,
+              int n_pw, const int2 *__restrict__ pw_pairs, const double *__restrict__ px, const double *__restrict__ py,
+              const double *__restrict__ pz, const double *__restrict__ pk_qd, const int *__restrict__ pk_ct,
+              const int *__restrict__ pk_sw, const double *__restrict__ x, const double2 *__restrict__ wd,
+              const double *__restrict__ ljd, const uint8_t *__restrict__ ljcode, double *__restrict__ Eslots, int nE) {
+    PairEnergyBody<PBC>::run(P, n_ww, ww_pairs, n_pp, pp_pairs, n_pw, pw_pairs, px, py, pz, pk_qd, pk_ct, pk_sw, x, wd, ljd, ljcode, Eslots, nE, blockIdx.x, gridDim.x, blockIdx.y, gridDim.y);
 }
 
 // ---- flat pair lists of the energy kernel, written at list-build time (one warp per unit)

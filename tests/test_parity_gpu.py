@@ -365,13 +365,16 @@ def test_solvent_restraints(case):
         o.close()
 
 
-def test_batched_windows_equal_single_calls():
+@pytest.mark.parametrize("one_graph", [False, True], ids=["graph_per_window", "one_graph"])
+def test_batched_windows_equal_single_calls(one_graph, monkeypatch):
     """qnb_build_lists_batch / qnb_nonbond_batch over W lambda windows of one FEP system (own coordinates and lambda per
     window, run_excl_test.sh:92-125) == W single-system calls: same list counts, gradients to FP64 summation-order noise,
     energies likewise; every window also checked against the oracle."""
     from oracle.pyoracle import Oracle
     from q6_b200 import synth
     from q6_b200.engine import Qnb, QnbBatch
+    if one_graph:
+        monkeypatch.setenv("QNB_BATCH_GRAPH", "1")      # one launch per kernel type for all windows (k_batched)
     q = synth.solvated_sphere(14.0, 0.0, 14, 2, 97, fep="annihilate")
     cuts = common.sph_cuts(8.0)
     W = 5
