@@ -206,6 +206,18 @@ class Job:
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
             self.dist = dist
         self.dev = self.local_rank if self.world > 1 else 0
+        # one slice of the host cores per rank (all GPUs of the box hang off the same NUMA node, `nvidia-smi topo -m`): eight
+        # Python ranks and the clock sampler otherwise migrate over each other's cores (r01: e2e efficiency 0.88 at N=8)
+        self.cores = None
+        if self.world > 1 and hasattr(os, "sched_setaffinity"):
+            try:
+                avail = sorted(os.sched_getaffinity(0))
+                per = max(1, len(avail) // self.world)
+                mine = avail[self.local_rank * per:(self.local_rank + 1) * per] or avail
+                os.sched_setaffinity(0, mine)
+                self.cores = [mine[0], mine[-1]]
+            except OSError:
+                pass
 
     def barrier(self):
         self.torch.cuda.synchronize()
@@ -427,7 +439,8 @@ def main():
     q, cuts, lam = synth.config(args.workload)
     config = {"workload": WORKLOADS[args.workload], "natom": int(q.natom), "nat_solute": int(q.nat_solute), "nwat": int(q.nwat),
               "nqat": int(q.nqat), "nstates": int(q.nstates), "nbcycle": NBCYCLE,
-              "replicas": "one independent system (lambda window) per GPU" if world > 1 else "single system",
+              "replicas": "one independent system (lambda window) per GPU, each rank pinned to its own slice of the host cores"
+                          if world > 1 else "single system",
               "cache": "coordinates, rows and gradient (< 3 MB) are L2-resident by nature of the workload; "
                        "per-kernel times in roofline are taken with an L2 flush before every launch"}
 

@@ -484,7 +484,9 @@ static int init_device(qnb_handle *h) {
 static bool p2p_ready(const qnb_handle *h) { return h->p2p.n > 1; }
 static int allreduce_arena(qnb_handle *h, size_t off, size_t count, cudaStream_t st) {
     if (p2p_ready(h)) {
-        const int blocks = std::max(1, std::min(h->nsm, (int)((count / 2 + 255) / 256)));
+        // blocks for this rank's slice (1/n of the elements), two 16-byte elements per thread at most
+        const size_t slice2 = ((count + 1) / 2 + h->p2p.n - 1) / h->p2p.n;
+        const int blocks = std::max(1, std::min(h->nsm, (int)((slice2 + 511) / 512)));
         LAUNCH_ON(h, st, k_p2p_allreduce, blocks, 256, 0, h->p2p, off, count,
                   reinterpret_cast<unsigned *>(h->arena + h->arena_ctl_off));
         return 0;
@@ -934,7 +936,8 @@ static void launch_step_kernel(qnb_handle *h, int k, cudaStream_t cs, int flags)
     }
     case K_QATOM: {
         const int nsite = h->nqp + 3 * h->nqw;
-        const int slices = std::max(1, std::min(cdiv(nsite, 128), cdiv(cdiv(4 * 148, std::max(1, h->share)), std::max(D.nqat, 1))));
+        static const int qa_mult = [] { const char *e = getenv("QNB_QATOM_BLOCKS_PER_SM"); return e ? std::max(1, atoi(e)) : 4; }();
+        const int slices = std::max(1, std::min(cdiv(nsite, 128), cdiv(cdiv(qa_mult * 148, std::max(1, h->share)), std::max(D.nqat, 1))));
         const dim3 qgrid(D.nqat, slices);
 #define QCASE(P, N)                                                                                                           \
     do {                                                                                                                      \
@@ -988,10 +991,13 @@ static void launch_step_kernel(qnb_handle *h, int k, cudaStream_t cs, int flags)
 static const int kStreamOf[K_COUNT] = {0, 1, 2, 3, 4, -1, 4, 5};   // aux stream index, -1 = main stream
 
 static int issue_step(qnb_handle *h, int flags, bool out_cleared = false) {
-    if (!out_cleared) CU(cudaMemsetAsync(h->out.p, 0, h->nout * sizeof(double), h->st));
-    if ((flags & QNB_FLAG_MD) && h->npk > 0)
+    // the output buffer is cleared by the packing kernel when there is one (one graph node less on the critical path)
+    const bool pack = (flags & QNB_FLAG_MD) && h->npk > 0;
+    if (!out_cleared && !pack) CU(cudaMemsetAsync(h->out.p, 0, h->nout * sizeof(double), h->st));
+    if (pack)
         LAUNCH(h, k_pack_step, cdiv(h->npk, 256), 256, 0, h->npk, h->fix, h->D.nat_solute, h->pk_atom.p, h->pk_sw.p, h->pk_q.p, h->pk_ct.p,
-               h->x.p, h->px.p, h->py.p, h->pz.p, h->rec_i.p, h->rec_f.p, h->wT.p, h->wown.p, h->wd.p, (double *)nullptr, 0, (const double *)nullptr, (double *)nullptr, 0);
+               h->x.p, h->px.p, h->py.p, h->pz.p, h->rec_i.p, h->rec_f.p, h->wT.p, h->wown.p, h->wd.p, out_cleared ? (double *)nullptr : h->out.p,
+               (int)h->nout, (const double *)nullptr, (double *)nullptr, 0);
     CU(cudaEventRecord(h->ev_fork, h->st));
     bool used[kAux] = {};
     static const int kOrder[K_COUNT] = {K_RST, K_QSTATIC, K_SOLUTE, K_QATOM, K_QPARTNER, K_WATER, K_ENERGY, K_LRF};

@@ -183,11 +183,15 @@ k_p2p_allreduce(P2PComm C, size_t off, size_t count, unsigned *ctl) {
         for (int p = 0; p < kMaxPeers; p++)
             if (p < C.n) reinterpret_cast<double2 *>(C.base[p] + off)[i] = s;
     }
-    // ---- the last block of this rank tells everybody, waits for everybody, and opens the next epoch
-    __threadfence_system();
+    // ---- the last block of this rank tells everybody, waits for everybody, and opens the next epoch.  One system-scope
+    // fence per block, by its leader after the block barrier (the pattern of a grid-wide sync): a fence in every thread
+    // put ~18 k membar.sys on the memory system at once
     __syncthreads();
     __shared__ unsigned last;
-    if (threadIdx.x == 0) last = atomicAdd(ctl + 1, 1u) == gridDim.x - 1;
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        last = atomicAdd(ctl + 1, 1u) == gridDim.x - 1;
+    }
     __syncthreads();
     if (!last) return;
     __threadfence_system();   // the other blocks' deliveries (fenced before their count) precede the "done" below
