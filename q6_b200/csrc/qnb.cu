@@ -878,6 +878,21 @@ static void query_occupancy(qnb_handle *h) {
     cudaGetLastError();
 }
 
+// grids of the Q and energy kernels (shared by the single launches and the fused step kernels)
+static dim3 q_partner_grid(const qnb_handle *h) {
+    const int n = h->nqp + 3 * h->nqw;
+    return dim3(cdiv(n, 128), std::max(1, std::min(h->D.nqat, cdiv(cdiv(6 * 148, std::max(1, h->share)), cdiv(n, 128)))));
+}
+static dim3 q_atom_grid(const qnb_handle *h) {
+    static const int qa_mult = [] { const char *e = getenv("QNB_QATOM_BLOCKS_PER_SM"); return e ? std::max(1, atoi(e)) : 4; }();
+    const int nsite = h->nqp + 3 * h->nqw;
+    return dim3(h->D.nqat, std::max(1, std::min(cdiv(nsite, 128), cdiv(cdiv(qa_mult * 148, std::max(1, h->share)), std::max(h->D.nqat, 1)))));
+}
+static int energy_grid(const qnb_handle *h) {
+    const int n = h->n_ww_e + h->n_pp_e + h->n_pw_e;
+    return std::max(1, std::min(cdiv(n, 128), cdiv(8 * h->nsm, std::max(1, h->share))));
+}
+
 static void launch_step_kernel(qnb_handle *h, int k, cudaStream_t cs, int flags) {
     const Dev &D = h->D;
     double *grad = h->out.p, *E = h->out.p + 3 * (size_t)D.natom;
@@ -927,18 +942,14 @@ static void launch_step_kernel(qnb_handle *h, int k, cudaStream_t cs, int flags)
         break;
     }
     case K_QPARTNER: {
-        const int n = h->nqp + 3 * h->nqw;
         const size_t sm = sizeof(float) * (3 * (size_t)D.nqat + D.nstates);
-        const dim3 pgrid(cdiv(n, 128), std::max(1, std::min(D.nqat, cdiv(cdiv(6 * 148, std::max(1, h->share)), cdiv(n, 128)))));
+        const dim3 pgrid = q_partner_grid(h);
         if (pbc) STEP_LAUNCH(h, cs, QPartnerBody<true>, 128, 6, k_q_partner<true>, pgrid, sm, D, h->x.p, h->lam_dev, h->nqp, h->qp_list.p, h->qp_shift_atom.p, h->nqw, h->qw_list.p, grad);
         else STEP_LAUNCH(h, cs, QPartnerBody<false>, 128, 6, k_q_partner<false>, pgrid, sm, D, h->x.p, h->lam_dev, h->nqp, h->qp_list.p, h->qp_shift_atom.p, h->nqw, h->qw_list.p, grad);
         break;
     }
     case K_QATOM: {
-        const int nsite = h->nqp + 3 * h->nqw;
-        static const int qa_mult = [] { const char *e = getenv("QNB_QATOM_BLOCKS_PER_SM"); return e ? std::max(1, atoi(e)) : 4; }();
-        const int slices = std::max(1, std::min(cdiv(nsite, 128), cdiv(cdiv(qa_mult * 148, std::max(1, h->share)), std::max(D.nqat, 1))));
-        const dim3 qgrid(D.nqat, slices);
+        const dim3 qgrid = q_atom_grid(h);
 #define QCASE(P, N)                                                                                                           \
     do {                                                                                                                      \
         using B_ = QAtomBody<P, N>;                                                                                           \
@@ -958,8 +969,7 @@ static void launch_step_kernel(qnb_handle *h, int k, cudaStream_t cs, int flags)
         STEP_LAUNCH(h, cs, LrfTaylorBody, 128, 6, k_lrf_taylor, cdiv(D.natom, 128), 0, D, h->x.p, h->lrf.p, grad, E, nE);
         break;
     case K_ENERGY: {
-        const int n = h->n_ww_e + h->n_pp_e + h->n_pw_e;
-        const int grid = std::max(1, std::min(cdiv(n, 128), cdiv(8 * h->nsm, std::max(1, h->share))));
+        const int grid = energy_grid(h);
         if (pbc) STEP_LAUNCH(h, cs, PairEnergyBody<true>, 128, 7, k_pair_energy<true>, grid, 0, h->epar, h->n_ww_e, h->ww_pairs.p, h->n_pp_e, h->pp_pairs.p, h->n_pw_e,
                            h->pw_pairs.p, h->px.p, h->py.p, h->pz.p, h->pk_qd.p, h->pk_ct.p, h->pk_sw.p, h->x.p, h->wd.p, h->ljd.p, h->ljcode.p, E, nE);
         else STEP_LAUNCH(h, cs, PairEnergyBody<false>, 128, 7, k_pair_energy<false>, grid, 0, h->epar, h->n_ww_e, h->ww_pairs.p, h->n_pp_e, h->pp_pairs.p, h->n_pw_e,
@@ -986,6 +996,78 @@ static void launch_step_kernel(qnb_handle *h, int k, cudaStream_t cs, int flags)
     }
 }
 
+// ---- the fused step: the row kernels in one launch, everything else in a second one (k_uber, qnb_kernels.cuh)
+using URowsSolute = SoluteRowsBody<false>;
+using URowsWater = WaterRowsBody<true, 5>;
+static bool uber_ok(const qnb_handle *h, int flags) {
+    // Opt-in (QNB_UBER=1).  Measured r03g: the step takes the same time with three launches as with nine (C2 32.8 vs 32.4 us,
+    // C3 22.5, C5 87.1) -- the graph's node count is not what bounds it; the two row kernels each need the whole machine for
+    // their single wave (solute 10.3 + water 11.6 us) and follow the pack kernel (4.5 us).
+    static const bool on = getenv("QNB_UBER") != nullptr;
+    const Dev &D = h->D;
+    return on && !h->collect && h->multi_stream && !h->legacy_rows && (D.spc_water || D.nwat == 0) && !h->pw_hlj && D.nstates <= 2 &&
+           !(flags & QNB_FLAG_SOLVENT_RESTRAINTS);
+}
+template <bool PBC, int NS>
+static void launch_uber_rest(qnb_handle *h, cudaStream_t cs, int flags) {
+    const Dev &D = h->D;
+    double *grad = h->out.p, *E = h->out.p + 3 * (size_t)D.natom;
+    USlot<QAtomBody<PBC, NS>> qa{};
+    USlot<QPartnerBody<PBC>> qp{};
+    USlot<PairEnergyBody<PBC>> en{};
+    USlot<LrfTaylorBody> lt{};
+    USlot<QqStaticBody> qs{};
+    size_t sm = 0;
+    if (step_kernel_active(h, K_QATOM, flags)) {
+        const dim3 g = q_atom_grid(h);
+        qa.a = body_args_t<QAtomBody<PBC, NS>>(D, h->x.p, h->lam_dev, h->nqp, h->qp_list.p, h->qp_shift_atom.p, h->nqw, h->qw_list.p, grad, E, h->nE);
+        qa.gx = (int)g.x; qa.gy = (int)g.y;
+    }
+    if (step_kernel_active(h, K_QPARTNER, flags)) {
+        const dim3 g = q_partner_grid(h);
+        qp.a = body_args_t<QPartnerBody<PBC>>(D, h->x.p, h->lam_dev, h->nqp, h->qp_list.p, h->qp_shift_atom.p, h->nqw, h->qw_list.p, grad);
+        qp.gx = (int)g.x; qp.gy = (int)g.y;
+        sm = sizeof(float) * (3 * (size_t)D.nqat + D.nstates);
+    }
+    if (step_kernel_active(h, K_ENERGY, flags)) {
+        en.a = body_args_t<PairEnergyBody<PBC>>(h->epar, h->n_ww_e, h->ww_pairs.p, h->n_pp_e, h->pp_pairs.p, h->n_pw_e, h->pw_pairs.p, h->px.p, h->py.p,
+                                                h->pz.p, h->pk_qd.p, h->pk_ct.p, h->pk_sw.p, h->x.p, h->wd.p, h->ljd.p, h->ljcode.p, E, h->nE);
+        en.gx = energy_grid(h); en.gy = 1;
+    }
+    if (step_kernel_active(h, K_LRF, flags)) {
+        lt.a = body_args_t<LrfTaylorBody>(D, h->x.p, h->lrf.p, grad, E, h->nE);
+        lt.gx = cdiv(D.natom, 128); lt.gy = 1;
+    }
+    if (step_kernel_active(h, K_QSTATIC, flags)) {
+        qs.a = body_args_t<QqStaticBody>(h->n_qstatic, h->n_qq, h->qstatic.p, h->x.p, h->lam_dev, grad, E, h->nE);
+        qs.gx = cdiv(h->n_qstatic, 128); qs.gy = 1;
+    }
+    const int nb = qa.gx * qa.gy + qp.gx * qp.gy + en.gx * en.gy + lt.gx * lt.gy + qs.gx * qs.gy;
+    if (nb <= 0) return;
+    k_uber<6, QAtomBody<PBC, NS>, QPartnerBody<PBC>, PairEnergyBody<PBC>, LrfTaylorBody, QqStaticBody><<<nb, 128, sm, cs>>>(qa, qp, en, lt, qs);
+    h->launches++;
+}
+static void launch_uber_rows(qnb_handle *h, cudaStream_t cs, int flags) {
+    const Dev &D = h->D;
+    double *grad = h->out.p;
+    USlot<URowsSolute> so{};
+    USlot<URowsWater> wa{};
+    if (step_kernel_active(h, K_SOLUTE, flags)) {
+        so.a = body_args_t<URowsSolute>(h->rowpar, h->upk.p, h->nq_off.p, h->rec_i.p, h->rec_f.p, h->wT.p, h->ljp.p, h->pw0.p, h->pw12.p, h->wstart_s.p,
+                                        h->sdesc.p, h->srow.p, h->sspec.p, h->pk_atom.p, grad);
+        so.gx = h->sgrid; so.gy = 1;
+    }
+    if (step_kernel_active(h, K_WATER, flags)) {
+        wa.a = body_args_t<URowsWater>(h->rowpar, h->rec_i.p, h->rec_f.p, h->wT.p, h->wown.p, h->pw0.p, h->pw12.p, h->wstart_w.p, h->wdesc.p, h->wrow.p,
+                                       D.nat_solute, grad);
+        wa.gx = h->wgrid; wa.gy = 1;
+    }
+    const int nb = so.gx + wa.gx;
+    if (nb <= 0) return;
+    k_uber<4, URowsSolute, URowsWater><<<nb, 128, 0, cs>>>(so, wa);
+    h->launches++;
+}
+
 // The kernels of one evaluation are independent (they only meet in atomicAdd on grad/E), so they are issued on
 // four streams between a fork and a join event: at 12k atoms no single kernel fills 148 SMs.
 static const int kStreamOf[K_COUNT] = {0, 1, 2, 3, 4, -1, 4, 5};   // aux stream index, -1 = main stream
@@ -1000,6 +1082,24 @@ static int issue_step(qnb_handle *h, int flags, bool out_cleared = false) {
                (int)h->nout, (const double *)nullptr, (double *)nullptr, 0);
     CU(cudaEventRecord(h->ev_fork, h->st));
     bool used[kAux] = {};
+    if (uber_ok(h, flags)) {
+        // two launches instead of seven: [solute rows | water rows] and [Q atoms | Q partners | energies | LRF Taylor | static Q lists]
+        const bool rows = step_kernel_active(h, K_SOLUTE, flags) || step_kernel_active(h, K_WATER, flags);
+        if (rows) {
+            CU(cudaStreamWaitEvent(h->aux[1], h->ev_fork, 0)); used[1] = true;
+            launch_uber_rows(h, h->aux[1], flags);
+        }
+        CU(cudaStreamWaitEvent(h->aux[3], h->ev_fork, 0)); used[3] = true;
+        const bool pbc = h->D.use_PBC;
+        if (h->D.nstates <= 1) { if (pbc) launch_uber_rest<true, 1>(h, h->aux[3], flags); else launch_uber_rest<false, 1>(h, h->aux[3], flags); }
+        else { if (pbc) launch_uber_rest<true, 2>(h, h->aux[3], flags); else launch_uber_rest<false, 2>(h, h->aux[3], flags); }
+        for (int k = 0; k < kAux; k++)
+            if (used[k]) {
+                CU(cudaEventRecord(h->ev_join[k], h->aux[k]));
+                CU(cudaStreamWaitEvent(h->st, h->ev_join[k], 0));
+            }
+        return 0;
+    }
     static const int kOrder[K_COUNT] = {K_RST, K_QSTATIC, K_SOLUTE, K_QATOM, K_QPARTNER, K_WATER, K_ENERGY, K_LRF};
     for (int o = 0; o < K_COUNT; o++) {
         const int k = kOrder[o];

@@ -125,6 +125,37 @@ __global__ void __launch_bounds__(THREADS, MINB) k_batched(const cuda::std::tupl
     cuda::std::apply([&](const P &...p) { Body::run(p..., (int)blockIdx.x, g.x, (int)blockIdx.y, g.y); }, t);
 }
 
+// ------------------------------------------------------------------ several kernels in one launch
+// A CUDA graph pays ~2.5 us of front-end time per kernel node: the step of a 12 k-atom system (pack + seven kernels of
+// 8-14 us each on their own streams) took 32 us whatever the grids (r03f) and 25 us even for 600 atoms (r02y).  k_uber
+// runs several Body functors in ONE launch: the grid is the concatenation of the bodies' grids, a block looks up which
+// body owns its index.  Arguments travel by value (constant bank), exactly as in the single kernels.
+template <class F> struct BodyRunArgs;
+template <class... P> struct BodyRunArgs<void (*)(P...)> { using type = cuda::std::tuple<cuda::std::decay_t<P>...>; };
+template <class Tup, size_t... I>
+cuda::std::tuple<cuda::std::tuple_element_t<I, Tup>...> body_args_head(cuda::std::index_sequence<I...>);
+// the argument tuple of Body::run without its trailing (BX, NBX, BY, NBY)
+template <class Body>
+using body_args_t = decltype(body_args_head<typename BodyRunArgs<decltype(&Body::run)>::type>(
+    cuda::std::make_index_sequence<cuda::std::tuple_size<typename BodyRunArgs<decltype(&Body::run)>::type>::value - 4>{}));
+template <class Body> struct USlot { body_args_t<Body> a; int gx, gy; };   // gx * gy blocks; gx == 0: body absent this step
+template <class Body>
+__device__ __forceinline__ bool uber_try(const USlot<Body> &s, int &b) {
+    const int n = s.gx * s.gy;
+    if (b < n) {
+        const int bx = b % s.gx, by = b / s.gx;
+        cuda::std::apply([&](const auto &...p) { Body::run(p..., bx, s.gx, by, s.gy); }, s.a);
+        return true;
+    }
+    b -= n;
+    return false;
+}
+template <int MINB, class... Body>
+__global__ void __launch_bounds__(128, MINB) k_uber(const __grid_constant__ USlot<Body>... s) {
+    int b = blockIdx.x;
+    (void)(uber_try(s, b) || ...);   // the first body whose block range holds b runs
+}
+
 // ------------------------------------------------------------------ all-reduce over peer memory
 // The ranks of one node (one process per GPU) map each other's arena [out | lrf | control] through CUDA IPC; NVSwitch
 // gives every GPU full bandwidth to every peer, so the sum is ONE kernel per rank: the owner of slice r (1/n of the
