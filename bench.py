@@ -5,8 +5,9 @@
 
 A "step" is one MD step's share of the hot path on one synthetic system: one nonbonded evaluation
 (qnb_nonbond) plus a pair-list rebuild every NBcycle = 25 steps, as md_run does (md.f90:1661,1742).
-`value`  = pair interactions/s with coordinates already resident in HBM (CUDA events, max over ranks, median of
-           `--repeats` windows of K steps each);
+`value`  = pair interactions/s with coordinates already resident in HBM (CUDA events, max over ranks, mean of
+           `--repeats` windows of exactly K steps each; the MD step counter -- list build every 25 steps -- runs on
+           across the windows);
 `e2e`    = the same through the C ABI with HOST buffers (x up, d + energies down inside the timed region).
 N > 1    = one independent replica / lambda window per GPU, no data-path collective (weak scaling); the same line
            carries `sharded_c5` (ONE 98k-atom periodic system, rows sharded over the N GPUs, NCCL all-reduce of
@@ -200,10 +201,17 @@ class Job:
         import torch
         self.torch = torch
         self.dist = None
+        self.ctl = None
         if self.world > 1:
             import torch.distributed as dist
             torch.cuda.set_device(self.local_rank)
-            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            # NCCL is the job's process group (created on first use: the sharded block's QNB_COMM=nccl variant and the
+            # object broadcasts); barriers and the max over ranks of the timed windows go through a gloo group on the host, so
+            # that no NCCL communicator -- with its proxy and watchdog threads polling the driver -- exists while the
+            # per-rank loops are timed (r03i: 0.058 ms per step per rank at N=2 and N=8 against 0.046 at N=1)
+            dist.init_process_group("nccl")
+            if os.environ.get("QNB_BENCH_CONTROL", "gloo") == "gloo":
+                self.ctl = dist.new_group(backend="gloo")
             self.dist = dist
         self.dev = self.local_rank if self.world > 1 else 0
         # one slice of the host cores per rank (all GPUs of the box hang off the same NUMA node, `nvidia-smi topo -m`): eight
@@ -222,19 +230,32 @@ class Job:
     def barrier(self):
         self.torch.cuda.synchronize()
         if self.dist is not None:
-            self.dist.barrier()
+            if self.ctl is not None:
+                self.dist.barrier(group=self.ctl)
+            else:
+                self.dist.barrier()
             self.torch.cuda.synchronize()
 
     def reduce(self, v, op="max"):
         if self.dist is None:
             return v
-        t = self.torch.tensor([v], dtype=self.torch.float64, device="cuda")
-        self.dist.all_reduce(t, op={"max": self.dist.ReduceOp.MAX, "sum": self.dist.ReduceOp.SUM}[op])
+        rop = {"max": self.dist.ReduceOp.MAX, "sum": self.dist.ReduceOp.SUM}[op]
+        if self.ctl is not None:
+            t = self.torch.tensor([v], dtype=self.torch.float64)
+            self.dist.all_reduce(t, op=rop, group=self.ctl)
+        else:
+            t = self.torch.tensor([v], dtype=self.torch.float64, device="cuda")
+            self.dist.all_reduce(t, op=rop)
         return float(t.item())
+
+    def gather_objects(self, obj):
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj, group=self.ctl)
+        return out
 
     def close(self):
         if self.dist is not None:
-            self.dist.barrier()
+            self.barrier()
             self.dist.destroy_process_group()
 
 
@@ -250,7 +271,10 @@ def timed_md(job, g, lam, steps, repeats):
     return out
 
 
-def timed_e2e(job, g, q, x, lam, cuts, steps, repeats):
+def timed_e2e(job, g, q, x, lam, cuts, steps, repeats, phase=None):
+    """`repeats` windows of `steps` end-to-end steps; the MD step counter (list build when it hits a multiple of NBCYCLE) runs
+    on across the windows, as md_run's does."""
+    phase = phase if phase is not None else [0]
     d = np.zeros((q.natom, 3))
     # what the Fortran host does once at set-up for its module arrays x and d (qnb_register_host_buffers)
     g.release_host_buffers()
@@ -260,8 +284,9 @@ def timed_e2e(job, g, q, x, lam, cuts, steps, repeats):
         job.barrier()
         t0 = time.perf_counter()
         for k in range(steps):
-            if k % NBCYCLE == 0:
+            if phase[0] % NBCYCLE == 0:
                 g.make_pair_lists(x, **cuts, counts=False)
+            phase[0] += 1
             d[:] = 0                                           # d(:) = zero, potene.f90:109
             g.pot_energy_nonbonds(x, lam, d=d, d_is_zero=True)
         job.barrier()
@@ -281,19 +306,22 @@ def batched_windows(job, q, cuts, lam, nwin, steps, warmup, npairs, flop_step, f
 
     tb = [0.0, 0]
 
+    phase = [0]
+
     def run(n):
         for k in range(n):
-            if k % NBCYCLE == 0:
+            if phase[0] % NBCYCLE == 0:
                 t0 = time.perf_counter()
                 b.make_pair_lists(xs, **cuts)
                 tb[0] += time.perf_counter() - t0
                 tb[1] += 1
+            phase[0] += 1
             b.pot_energy_nonbonds(xs if k == 0 else None, lams if k == 0 else None)
 
     run(max(warmup, NBCYCLE + 1))
     tb[0], tb[1] = 0.0, 0
     times = []
-    for _ in range(3):
+    for _ in range(5):
         job.barrier()
         t0 = time.perf_counter()
         run(steps)
@@ -302,7 +330,7 @@ def batched_windows(job, q, cuts, lam, nwin, steps, warmup, npairs, flop_step, f
     host = b.last_timing()
     for g in hs:
         g.close()
-    t = float(np.median(times)) / steps          # seconds per batched step (nwin windows advance one step each)
+    t = float(np.mean(times)) / steps            # seconds per batched step (nwin windows advance one step each)
     agg = job.world * nwin * npairs / t
     return {"windows_per_gpu": nwin, "ms_per_batched_step": t * 1e3, "ms_per_window_step": t / nwin * 1e3,
             "value": agg, "unit": "pairs/s", "steps_per_s": job.world * nwin / t,
@@ -376,7 +404,7 @@ def sharded_c5(job, steps, warmup, repeats):
     c1 = g1.make_pair_lists(x, **cuts)
     npairs = pairs_per_step(c1, q.nstates, 0)
     g1.bench_md(lam, max(warmup, NBCYCLE), NBCYCLE)
-    t1_md = float(np.median(timed_md(job, g1, lam, steps, repeats))) / steps
+    t1_md = float(np.mean(timed_md(job, g1, lam, steps, repeats))) / steps
     job.barrier()
     t1_step = job.reduce(g1.bench_nonbond(lam, 100) / 100)
     t1_build = job.reduce(g1.bench_build_lists(3) / 3)
@@ -388,14 +416,14 @@ def sharded_c5(job, steps, warmup, repeats):
     tot = job.reduce(float(cl[2]), "sum")
     g.bench_md(lam, max(warmup, NBCYCLE), NBCYCLE)
     md = timed_md(job, g, lam, steps, repeats)
-    tN_md = float(np.median(md)) / steps
+    tN_md = float(np.mean(md)) / steps
     job.barrier()
     tN_step = job.reduce(g.bench_nonbond(lam, 100) / 100)
     job.barrier()
     tN_build = job.reduce(g.bench_build_lists(3) / 3)
     job.barrier()
     ar = job.reduce(g.bench_allreduce(50))
-    e2e = float(np.median(timed_e2e(job, g, q, x, lam, cuts, steps, 3))) / steps
+    e2e = float(np.mean(timed_e2e(job, g, q, x, lam, cuts, steps, 3))) / steps
     kt = g.bench_kernels(lam, 10, flush_l2=True)
     g.comm_status()
     g.close()
@@ -409,7 +437,7 @@ def sharded_c5(job, steps, warmup, repeats):
             "speedup_vs_n1": t1_md / tN_md, "kernels_ms_rank0_l2_flushed": kt, "spread_ms_per_window": spread(md),
             "scaling": "strong",
             "note": "ms_per_step = device-resident MD loop (one evaluation + all-reduce per step, list build + LRF all-reduce "
-                    f"every {NBCYCLE} steps), CUDA events, max over ranks, median of {repeats} windows; n1 = the unsharded "
+                    f"every {NBCYCLE} steps), CUDA events, max over ranks, mean of {repeats} windows; n1 = the unsharded "
                     "system on one GPU in the same run; comm p2p = one kernel per rank over CUDA-IPC peer memory (owner of a "
                     "slice sums it over the ranks and writes the sum into every rank's buffer), captured in the step's CUDA "
                     "graph; comm nccl = ncclAllReduce issued eagerly after the step's kernels (QNB_COMM=nccl)"}
@@ -422,7 +450,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=25)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C2", choices=list(WORKLOADS))
-    ap.add_argument("--repeats", type=int, default=25, help="timed windows of --steps steps each (median reported)")
+    ap.add_argument("--repeats", type=int, default=25, help="timed windows of --steps steps each (mean reported, min / median / max under `repeats`)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sharded", action="store_true",
                     help="N>1: ONE system as the HEADLINE, rows of the pair lists sharded over the GPUs, NCCL all-reduce of forces "
@@ -509,11 +537,13 @@ def main():
     l0 = g.launch_count()
     md = timed_md(job, g, lam, steps, repeats)
     launches = (g.launch_count() - l0) // repeats
-    t_step = float(np.median(md)) * 1e-3 / steps
+    # mean over the windows: the list build falls into 4 of 5 windows of 20 steps, the mean weighs it as the MD loop does
+    t_step = float(np.mean(md)) * 1e-3 / steps
     # ---- end to end through the C ABI with host buffers
-    timed_e2e(job, g, q, x, lam, cuts, max(warmup, NBCYCLE + 1), 1)
-    e2e_runs = timed_e2e(job, g, q, x, lam, cuts, steps, 5)
-    e2e_step = float(np.median(e2e_runs)) / steps
+    e2e_phase = [0]
+    timed_e2e(job, g, q, x, lam, cuts, max(warmup, NBCYCLE + 1), 1, e2e_phase)
+    e2e_runs = timed_e2e(job, g, q, x, lam, cuts, steps, 10, e2e_phase)
+    e2e_step = float(np.mean(e2e_runs)) / steps
     host_breakdown = g.last_timing()
     h2d, d2h = g.last_copy_bytes()
     h2d_step = h2d + (3 * q.natom * 8) / NBCYCLE   # + the list build's coordinate upload, amortised
@@ -628,8 +658,9 @@ def main():
                 "dtype": "f32 pair math, f64 accumulation and energies",
                 "data": "synthetic", "config": config, "pairs_per_step": npairs,
                 "repeats": {"windows": repeats, "steps_per_window": steps, "ms_per_window": spread(md),
-                            "note": "ms_per_step = median window / steps; every window is bracketed by barrier + synchronize and "
-                                    "reduced with max over ranks"},
+                            "note": "ms_per_step = mean window / steps (the MD step counter runs on across the windows, so the list "
+                                    f"build every {NBCYCLE} steps falls into some windows and not others: min / median / max show it); every "
+                                    "window is bracketed by barrier + synchronize and reduced with max over ranks"},
                 "ns_per_day": 86400.0 / e2e_step * DT_FS * 1e-6,
                 "ns_per_day_device_resident": 86400.0 / t_step * DT_FS * 1e-6,
                 "fep_windows_per_hour": nsys * 3600.0 / (STEPS_PER_WINDOW * e2e_step),

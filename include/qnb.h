@@ -327,8 +327,8 @@ int qnb_bench_build_lists(qnb_handle *h, int reps, float *ms_out);
 /* Parts of the builds timed by the last qnb_bench_build_lists, ms per build (CUDA events on the streams the kernels
  * run on): LRF accumulation (lrf_update, on its side stream), row scan count pass, row scan fill pass. */
 int qnb_bench_last_build_timing(qnb_handle *h, float out[3]);
-/* md_run's loop on device-resident coordinates: a list rebuild every nbcycle steps (md.f90:1661) plus one
- * nonbonded evaluation per step; ms_out = CUDA-event time of the loop. */
+/* md_run's loop on device-resident coordinates: a list rebuild every nbcycle steps (md.f90:1661; the step counter runs
+ * on across calls) plus one nonbonded evaluation per step; ms_out = CUDA-event time of the loop. */
 int qnb_bench_md(qnb_handle *h, const double *lambda, int flags, int steps, int nbcycle, float *ms_out);
 /* Sustained FMA throughput of the FP32 (which=0) / FP64 (which=1) pipe in TFLOP/s: the measured roofline
  * denominator of the force kernels (MEASURED_PEAKS.json holds only HBM and bf16 tensor figures). */
@@ -342,6 +342,9 @@ int qnb_bench_kernels(qnb_handle *h, const double *lambda, int flags, int reps, 
 int qnb_bench_last_batch_timing(double out[3]);
 /* ms per all-reduce of [d | E | EQ] alone (sharded handles; the collective that replaces gather_nonbond). */
 int qnb_bench_allreduce(qnb_handle *h, int reps, float *ms_out);
+/* Phases of the last peer-memory all-reduce on this rank, us (%globaltimer): waiting for all ranks to arrive, summing and
+ * delivering the own slice, waiting for all ranks to finish. */
+int qnb_bench_allreduce_phases(qnb_handle *h, double out[3]);
 /* Kernel launches issued by this handle since creation. */
 int64_t qnb_launch_count(qnb_handle *h);
 /* Host-side seconds of the last qnb_nonbond: staging x into pinned memory, issuing the step (graph launch),

@@ -221,6 +221,7 @@ struct qnb_handle {
     int share = 1;                         // systems that advance together on this GPU (qnb_build_lists_batch): grids are sized
                                            // for 1/share of the SMs so that the kernels of the systems run side by side
     qnb::BatchSlot *collect = nullptr;     // set while a batch plan records this handle's launch arguments
+    int64_t md_phase = 0;                  // qnb_bench_md: MD step counter, runs on across calls
     uint64_t build_serial = 0;             // counts list builds and box changes: batch plans bake row pointers and sizes
     // stats
     int64_t launches = 0, last_h2d = 0, last_d2h = 0;
@@ -2145,7 +2146,9 @@ int qnb_bench_md(qnb_handle *h, const double *lambda, int flags, int steps, int 
     CU(cudaStreamSynchronize(h->st));
     CU(cudaEventRecord(h->ev0, h->st));
     for (int k = 0; k < steps; k++) {
-        if (nbcycle > 0 && k % nbcycle == 0) {
+        // the step counter runs on across calls (md.f90:1661, mod(istep, NBcycle) == 0): a timed window of 20 steps holds
+        // 0.8 list builds on average, not one
+        if (nbcycle > 0 && h->md_phase++ % nbcycle == 0) {
             if (build_device(h, h->hx)) return 1;   // as qnb_build_lists: Q partner lists only when the cut-offs ask for it
         }
         if (step_device(h, flags)) return 1;
@@ -2277,6 +2280,18 @@ int qnb_bench_allreduce(qnb_handle *h, int reps, float *ms_out) {
     CU(cudaEventSynchronize(h->ev1));
     CU(cudaEventElapsedTime(ms_out, h->ev0, h->ev1));
     *ms_out /= (float)std::max(reps, 1);
+    return 0;
+}
+
+// phases of the last peer-memory all-reduce on this rank, microseconds: waiting for all ranks, summing and delivering the own
+// slice, waiting for all ranks to finish
+int qnb_bench_allreduce_phases(qnb_handle *h, double out[3]) {
+    if (!h || !out) return fail("null argument");
+    if (!p2p_ready(h)) return fail("qnb_bench_allreduce_phases: peer-memory all-reduce not attached");
+    CU(cudaSetDevice(h->device));
+    unsigned long long st[4];
+    CU(cudaMemcpy(st, reinterpret_cast<unsigned *>(h->arena + h->arena_ctl_off) + 64, sizeof st, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 3; k++) out[k] = (double)(st[k + 1] - st[k]) * 1e-3;
     return 0;
 }
 

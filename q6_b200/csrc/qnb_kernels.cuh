@@ -187,8 +187,17 @@ __device__ __forceinline__ bool spin_until(const unsigned *p, unsigned target, u
     }
     return true;
 }
+__device__ __forceinline__ unsigned long long gtime_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// phase stamps of the last call (ns, %globaltimer), control words 64..71 as u64[4]: entry, all ranks arrived, own slice
+// delivered (block 0), all ranks done -- read by qnb_bench_allreduce_phases
 __global__ void __launch_bounds__(256)
 k_p2p_allreduce(P2PComm C, size_t off, size_t count, unsigned *ctl) {
+    unsigned long long *stamp = reinterpret_cast<unsigned long long *>(ctl + 64);
+    if (blockIdx.x == 0 && threadIdx.x == 0) stamp[0] = gtime_ns();
     const unsigned epoch = ld_acquire_sys(ctl) + 1u;
     // ---- everybody's partial results are complete (this kernel follows the rank's step kernels in stream order)
     if (blockIdx.x == 0 && threadIdx.x < C.n) {
@@ -198,6 +207,7 @@ k_p2p_allreduce(P2PComm C, size_t off, size_t count, unsigned *ctl) {
     }
     if (threadIdx.x < C.n) spin_until(ctl + 16 + threadIdx.x, epoch, ctl + 2);
     __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0) stamp[1] = gtime_ns();
     // ---- own slice: sum over the ranks in rank order, deliver to every rank (16-byte accesses)
     const size_t n2 = (count + 1) / 2;                       // double2 elements (the arena parts are padded)
     const size_t per = (n2 + C.n - 1) / C.n;
@@ -218,6 +228,7 @@ k_p2p_allreduce(P2PComm C, size_t off, size_t count, unsigned *ctl) {
     // fence per block, by its leader after the block barrier (the pattern of a grid-wide sync): a fence in every thread
     // put ~18 k membar.sys on the memory system at once
     __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0) stamp[2] = gtime_ns();
     __shared__ unsigned last;
     if (threadIdx.x == 0) {
         __threadfence_system();
@@ -232,7 +243,7 @@ k_p2p_allreduce(P2PComm C, size_t off, size_t count, unsigned *ctl) {
         spin_until(ctl + 32 + threadIdx.x, epoch, ctl + 2);
     }
     __syncthreads();
-    if (threadIdx.x == 0) { ctl[1] = 0u; __threadfence(); st_release_sys(ctl, epoch); }
+    if (threadIdx.x == 0) { stamp[3] = gtime_ns(); ctl[1] = 0u; __threadfence(); st_release_sys(ctl, epoch); }
 }
 
 // ------------------------------------------------------------------ small device helpers

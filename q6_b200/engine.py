@@ -163,6 +163,8 @@ def load_library(path: str = LIB_PATH):
     lib.qnb_bench_build_lists.argtypes = [H, C.c_int, _PF]
     lib.qnb_bench_last_batch_timing.restype = C.c_int
     lib.qnb_bench_last_batch_timing.argtypes = [_PD]
+    lib.qnb_bench_allreduce_phases.restype = C.c_int
+    lib.qnb_bench_allreduce_phases.argtypes = [H, _PD]
     lib.qnb_bench_allreduce.restype = C.c_int
     lib.qnb_bench_allreduce.argtypes = [H, C.c_int, _PF]
     lib.qnb_bench_last_build_timing.restype = C.c_int
@@ -451,6 +453,11 @@ class Qnb:
         ms = C.c_float()
         self._check(self.lib.qnb_bench_allreduce(self.h, reps, C.byref(ms)))
         return ms.value
+
+    def allreduce_phases(self) -> dict:
+        t = np.zeros(3)
+        self._check(self.lib.qnb_bench_allreduce_phases(self.h, _dp(t)))
+        return dict(zip(("wait_arrive_us", "sum_deliver_us", "wait_done_us"), t.tolist()))
 
     def last_build_timing(self) -> dict:
         """ms per build of the parts timed by the last bench_build_lists: LRF accumulation, row scan passes."""

@@ -24,6 +24,11 @@ for mode in (sys.argv[1:] or ["p2p", "nccl"]):
     g.comm_status()
     t = torch.tensor([ar * 1e3, step, build], device="cuda", dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if m == "p2p":
+        dist.barrier()
+        g.bench_allreduce(20)       # every rank takes part
+    if rank == 0 and m == "p2p":
+        print("   phases of the last all-reduce on rank 0:", {k: round(v, 1) for k, v in g.allreduce_phases().items()}, flush=True)
     if rank == 0:
         print(f"N={world} {m}: allreduce {t[0].item():.1f} us, sharded step {t[1].item():.1f} us, build {t[2].item():.3f} ms", flush=True)
     g.close()

@@ -5,7 +5,7 @@ OUT=gpurun_out
 mkdir -p $OUT
 (NCCL_DEBUG=WARN timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
     bench.py --gpus $N --steps 20 --warmup 3) > $OUT/bench_${TAG}_n$N.json 2> $OUT/bench_${TAG}_n$N.err
-(timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 tools/exp_allreduce.py 2>&1 | grep "N=\|rror") > $OUT/allreduce_${TAG}_n$N.txt
+(timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 tools/exp_allreduce.py 2>&1 | grep "N=\|rror\|phases") > $OUT/allreduce_${TAG}_n$N.txt
 cat $OUT/allreduce_${TAG}_n$N.txt
 python - <<PY
 import json
