@@ -368,12 +368,13 @@ def fep_farm(job, steps_per_window, batch):
                 b.make_pair_lists(xs, **cuts)
             b.pot_energy_nonbonds(xs if k == 0 else None, lams if k == 0 else None)
 
-    if mine:
-        advance(mine[:nb], NBCYCLE + 3)     # warm-up: allocations, graph instantiation
+    groups = [mine[i:i + nb] for i in range(0, len(mine), nb)]
+    for size in sorted({len(gr) for gr in groups}):
+        advance(mine[:size], NBCYCLE + 3)   # warm-up of every batch size that will occur: allocations, page-locking, graphs
     job.barrier()
     t0 = time.perf_counter()
-    for i in range(0, len(mine), nb):
-        advance(mine[i:i + nb], steps_per_window)
+    for gr in groups:
+        advance(gr, steps_per_window)
     job.torch.cuda.synchronize()
     t_rank = time.perf_counter() - t0
     job.barrier()
