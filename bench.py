@@ -579,7 +579,14 @@ def main():
         dom = max((k for k in kt if alg.get(k, 0.0) > 0.0), key=lambda k: kt[k])
         ach = alg[dom] / (kt[dom] * 1e-3) / 1e12
         nlrf = lrf_interactions(q, cuts) if q.use_LRF else None
-        roof = {"bound": "fp32", "kernel": dom, "achieved": ach, "peak": fp32_meas, "unit": "TFLOP/s", "frac": ach / fp32_meas,
+        # the pipe a kernel computes on: the row and Q-partner gradient kernels are FP32, the Q-atom / static-list / LRF Taylor
+        # kernels FP64 throughout (FEP observables)
+        fp64_kernels = {"k_q_atom", "k_qq_static", "k_lrf_taylor"}
+        dom_peak = fp64_meas if dom in fp64_kernels else fp32_meas
+        roof = {"bound": "fp64" if dom in fp64_kernels else "fp32", "kernel": dom, "achieved": ach, "peak": dom_peak, "unit": "TFLOP/s",
+                "frac": ach / dom_peak,
+                "dominant_by": "largest CUDA-event time of one launch with the L2 flushed; at 12 k atoms every step kernel is a "
+                               "single latency-bound wave of 8-17 us, see roofline.step for the whole evaluation and the MD loop",
                 "traffic": traffic.get(dom),
                 "traffic_source": f"archived: ncu --set full capture {traffic_src} (dram__bytes_read.sum + dram__bytes_write.sum per "
                                   "launch), not measured in this run",
