@@ -279,6 +279,8 @@ def timed_e2e(job, g, q, x, lam, cuts, steps, repeats, phase=None):
     # what the Fortran host does once at set-up for its module arrays x and d (qnb_register_host_buffers)
     g.release_host_buffers()
     g.register_host_buffers(x.reshape(-1), d.reshape(-1))
+    lam = np.ascontiguousarray(lam, dtype=np.float64)
+    step, _, _ = g.bind_step(x.reshape(-1), lam, d.reshape(-1), d_is_zero=True)   # pointers held once, as a compiled host does
     out = []
     for _ in range(repeats):
         job.barrier()
@@ -288,7 +290,7 @@ def timed_e2e(job, g, q, x, lam, cuts, steps, repeats, phase=None):
                 g.make_pair_lists(x, **cuts, counts=False)
             phase[0] += 1
             d[:] = 0                                           # d(:) = zero, potene.f90:109
-            g.pot_energy_nonbonds(x, lam, d=d, d_is_zero=True)
+            step()
         job.barrier()
         out.append(job.reduce(time.perf_counter() - t0))
     return out

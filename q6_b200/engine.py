@@ -317,6 +317,25 @@ class Qnb:
             self._check(1)
         return d.reshape(-1, 3), E, EQ
 
+    def bind_step(self, x, lambdas, d, md=True, qq=True, d_is_zero=False):
+        """The per-step call with everything bound once, for hosts whose x, lambda and d arrays live as long as the run (what a
+        compiled host does by holding the pointers): returns (step, E, EQ) where step() runs qnb_nonbond on the CURRENT
+        contents of x / lambdas, adds the gradient to d (or writes it: d_is_zero) and refreshes E[7], EQ[nstates][6]."""
+        for a in (x, d):
+            assert a.dtype == np.float64 and a.flags.c_contiguous and a.size == 3 * self.sys.natom
+        assert lambdas.dtype == np.float64 and lambdas.size == self.sys.nstates
+        E = np.empty(E_COUNT)
+        EQ = np.empty((self.sys.nstates, EQ_STRIDE))
+        flags = (QNB_FLAG_MD if md else 0) | (QNB_FLAG_QQ if qq else 0) | (QNB_FLAG_D_IS_ZERO if d_is_zero else 0)
+        fn, h, args = self.lib.qnb_nonbond, self.h, (_addr(x), _addr(lambdas), flags, _addr(d), _addr(E), _addr(EQ))
+        keep = (x, lambdas, d, E, EQ)
+
+        def step(_keep=keep):
+            if fn(h, *args):
+                self._check(1)
+
+        return step, E, EQ
+
     def qcp_beads(self, x_save, atoms, coord, lambdas):
         """qcp_run's bead loop (qcp.f90:319-372): for every bead, x(atoms) = x_save(atoms) + coord[bead] and
         pot_energy(..., .false.); returns EQ[nbeads][nstates][6] (nonbonded Q terms).  atoms are 1-based."""

@@ -441,3 +441,25 @@ def test_registered_host_buffers_same_results():
     g.pot_energy_nonbonds(x, lam, d=d)
     assert rel_rms(d, d2) <= 1e-12
     g.close()
+
+
+def test_bound_step_equals_the_plain_call():
+    """Qnb.bind_step (pointers held once) == pot_energy_nonbonds on the same arrays, and follows changes of x and lambda."""
+    from q6_b200 import synth
+    from q6_b200.engine import Qnb
+    q = synth.solvated_sphere(14.0, 7.0, 10, 2, 43, fep="evb")
+    cuts = common.sph_cuts(8.0)
+    g = Qnb(q)
+    x = q.xtop.copy()
+    lam = np.array([0.6, 0.4])
+    d = np.zeros((q.natom, 3))
+    g.make_pair_lists(x, **cuts)
+    step, E, EQ = g.bind_step(x.reshape(-1), lam, d.reshape(-1))
+    step()
+    d1, E1, EQ1 = g.pot_energy_nonbonds(x, lam)
+    assert rel_rms(d, d1) <= 1e-12 and np.allclose(E, E1, rtol=1e-11, atol=1e-9) and np.allclose(EQ, EQ1, rtol=1e-11, atol=1e-9)
+    x += 0.01; lam[:] = (0.2, 0.8); d[:] = 0.0
+    step()
+    d2, E2, EQ2 = g.pot_energy_nonbonds(x, lam)
+    assert rel_rms(d, d2) <= 1e-12 and np.allclose(E, E2, rtol=1e-11, atol=1e-9) and np.allclose(EQ, EQ2, rtol=1e-11, atol=1e-9)
+    g.close()
