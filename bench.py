@@ -211,7 +211,10 @@ class Job:
             # per-rank loops are timed (r03i: 0.058 ms per step per rank at N=2 and N=8 against 0.046 at N=1)
             dist.init_process_group("nccl")
             if os.environ.get("QNB_BENCH_CONTROL", "gloo") == "gloo":
-                self.ctl = dist.new_group(backend="gloo")
+                try:
+                    self.ctl = dist.new_group(backend="gloo")
+                except Exception:      # no usable host interface for gloo: the NCCL group serves the barriers as well
+                    self.ctl = None
             self.dist = dist
         self.dev = self.local_rank if self.world > 1 else 0
         # one slice of the host cores per rank (all GPUs of the box hang off the same NUMA node, `nvidia-smi topo -m`): eight
