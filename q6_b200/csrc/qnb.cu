@@ -1164,7 +1164,7 @@ static void release_host_buffers(qnb_handle *h) {
 
 // One evaluation on the device.  with_copies: pinned x -> device before, [grad|E|EQ] -> pinned after.
 // Captured once per list build into a CUDA graph (one launch per MD step instead of ~10 API calls).
-static int step_device(qnb_handle *h, int flags, bool with_copies = false) {
+static int step_device(qnb_handle *h, int flags, bool with_copies = false, cudaGraph_t *graph_out = nullptr, int *nodes_out = nullptr) {
     const size_t n3 = 3 * (size_t)h->T.s.natom;
     // sharded step: the all-reduce is issued eagerly after the kernels unless QNB_SHARD_GRAPH=1 asks for it to be captured
     // with them (NCCL >= 2.9 supports capture once the communicator has been used; not yet run on hardware)
@@ -1198,7 +1198,7 @@ static int step_device(qnb_handle *h, int flags, bool with_copies = false) {
         cudaGraphExec_t &ge = h->graph[with_copies ? 1 : 0][gi];
         bool &dirty = h->graph_dirty[with_copies ? 1 : 0][gi];
         if (with_copies && (h->graph_x[gi] != h->x_direct || h->graph_d[gi] != h->d_direct || h->graph_dow[gi] != h->d_overwrite)) dirty = true;   // baked pointers
-        if (!ge || dirty) {
+        if (!ge || dirty || graph_out) {
             cudaGraph_t g = nullptr;
             const int64_t l0 = h->launches;
             CU(cudaStreamBeginCapture(h->st, cudaStreamCaptureModeThreadLocal));
@@ -1223,6 +1223,12 @@ static int step_device(qnb_handle *h, int flags, bool with_copies = false) {
             h->graph_launches[with_copies ? 1 : 0][gi] = (int)(h->launches - l0);
             h->launches = l0;
             if (rc || ce != cudaSuccess || !g) return fail("CUDA graph capture of the step failed: %s", cudaGetErrorString(ce));
+            if (graph_out) {   // the caller (batched step) makes this graph a child of its own; this handle's own graph stays as it was
+                *graph_out = g;
+                if (nodes_out) *nodes_out = h->graph_launches[with_copies ? 1 : 0][gi];
+                dirty = true;   // the pointers recorded above belong to the caller's graph now
+                return 0;
+            }
             bool updated = false;
             if (ge) {
                 cudaGraphExecUpdateResultInfo info;
@@ -1238,6 +1244,7 @@ static int step_device(qnb_handle *h, int flags, bool with_copies = false) {
         h->launches += h->graph_launches[with_copies ? 1 : 0][gi];
         return 0;
     }
+    if (graph_out) return fail("internal: this handle's step cannot be captured into a graph");
     if (with_copies && copy_in()) return fail("step: upload failed: %s", cudaGetErrorString(cudaGetLastError()));
     if (issue_step(h, flags)) return 1;
     // gather_nonbond + serial sum on the master (potene.f90:195-222) as one all-reduce over [d | E | EQ]
@@ -1665,6 +1672,96 @@ int qnb_bench_last_batch_timing(double out[3]) {
     return 0;
 }
 
+// ---- the batched step as a parent graph whose children are the windows' own step graphs
+namespace {
+struct ParentPlan {
+    std::vector<qnb_handle *> hs;
+    std::vector<uint64_t> serial;
+    std::vector<const double *> xptr;
+    std::vector<double *> dptr;
+    std::vector<char> dow;
+    int flags = -1, nodes = 0;
+    cudaGraphExec_t ge = nullptr;
+    bool valid = false;
+};
+ParentPlan g_parent;
+}  // namespace
+
+namespace qnb {
+// returns 0 / 1 like qnb_nonbond_batch, or -1 when the batch has to take the per-window path
+static int batch_parent_run(int n, qnb_handle *const *hs, const double *const *x, const double *const *lambda, int flags,
+                            double *const *d, double *const *E_out, double *const *EQ_out) {
+    ParentPlan &B = g_parent;
+    using clk = std::chrono::steady_clock;
+    const auto t0 = clk::now();
+    if (cudaSetDevice(hs[0]->device) != cudaSuccess) return -1;
+    const int kflags = flags & (QNB_FLAG_MD | QNB_FLAG_QQ | QNB_FLAG_NO_ENERGY | QNB_FLAG_SOLVENT_RESTRAINTS);
+    // stage what nonbond_begin stages, without launching
+    for (int w = 0; w < n; w++) {
+        qnb_handle *h = hs[w];
+        const size_t n3 = 3 * (size_t)h->T.s.natom;
+        h->x_direct = host_alias(h, x[w], n3 * sizeof(double)) ? x[w] : nullptr;
+        h->d_direct = static_cast<double *>(host_alias(h, d[w], n3 * sizeof(double)));
+        h->d_host = d[w];
+        h->d_overwrite = h->d_direct && (flags & QNB_FLAG_D_IS_ZERO);
+        if (!h->x_direct) memcpy(h->hx, x[w], n3 * sizeof(double));
+        for (int k = 0; k < h->T.s.nstates; k++) h->hlam[k] = lambda[w][k];
+        h->last_flags = flags;
+    }
+    bool same = B.valid && (int)B.hs.size() == n && B.flags == kflags;
+    for (int w = 0; same && w < n; w++)
+        same = B.hs[w] == hs[w] && B.serial[w] == hs[w]->build_serial && B.xptr[w] == hs[w]->x_direct && B.dptr[w] == hs[w]->d_direct &&
+               (bool)B.dow[w] == hs[w]->d_overwrite;
+    if (!same) {
+        B.valid = false;
+        cudaGraph_t parent = nullptr;
+        if (cudaGraphCreate(&parent, 0) != cudaSuccess) { cudaGetLastError(); return -1; }
+        int nodes = 0;
+        bool ok = true;
+        std::vector<cudaGraph_t> kids;
+        for (int w = 0; w < n && ok; w++) {
+            cudaGraph_t g = nullptr;
+            int nn = 0;
+            if (step_device(hs[w], kflags, true, &g, &nn) || !g) { ok = false; break; }
+            kids.push_back(g);
+            cudaGraphNode_t node;
+            ok = cudaGraphAddChildGraphNode(&node, parent, nullptr, 0, g) == cudaSuccess;   // no dependencies: the windows run side by side
+            nodes += nn;
+        }
+        if (ok) {
+            bool updated = false;
+            if (B.ge && (int)B.hs.size() == n) {
+                cudaGraphExecUpdateResultInfo info;
+                updated = cudaGraphExecUpdate(B.ge, parent, &info) == cudaSuccess;
+                if (!updated) cudaGetLastError();
+            }
+            if (!updated) {
+                if (B.ge) { cudaGraphExecDestroy(B.ge); B.ge = nullptr; }
+                ok = cudaGraphInstantiate(&B.ge, parent, 0) == cudaSuccess;
+            }
+        }
+        for (cudaGraph_t g : kids) cudaGraphDestroy(g);
+        cudaGraphDestroy(parent);
+        if (!ok) { cudaGetLastError(); if (B.ge) { cudaGraphExecDestroy(B.ge); B.ge = nullptr; } B.hs.clear(); return -1; }
+        B.hs.assign(hs, hs + n); B.serial.resize(n); B.xptr.resize(n); B.dptr.resize(n); B.dow.resize(n);
+        for (int w = 0; w < n; w++) { B.serial[w] = hs[w]->build_serial; B.xptr[w] = hs[w]->x_direct; B.dptr[w] = hs[w]->d_direct; B.dow[w] = hs[w]->d_overwrite; }
+        B.flags = kflags; B.nodes = nodes; B.valid = true;
+    }
+    CU(cudaGraphLaunch(B.ge, hs[0]->st));
+    hs[0]->launches += B.nodes;
+    const auto t1 = clk::now();
+    CU(cudaStreamSynchronize(hs[0]->st));
+    const auto t2 = clk::now();
+    int rc = 0;
+    for (int w = 0; w < n; w++)
+        if (nonbond_end(hs[w], d[w], E_out[w], EQ_out[w])) rc = 1;
+    g_batch_t[0] = std::chrono::duration<double>(t1 - t0).count();
+    g_batch_t[1] = std::chrono::duration<double>(t2 - t1).count();
+    g_batch_t[2] = std::chrono::duration<double>(clk::now() - t2).count();
+    return rc;
+}
+}  // namespace qnb
+
 // ---- the batched step as ONE graph: every kernel type launched once for all windows (k_batched, blockIdx.z = window)
 namespace {
 constexpr int kSlotPack = qnb::K_COUNT, kSlotCollect = qnb::K_COUNT + 1, kSlots = qnb::K_COUNT + 2;
@@ -1853,6 +1950,19 @@ int qnb_nonbond_batch(int n, qnb_handle *const *hs, const double *const *x, cons
     {
         std::lock_guard<std::mutex> lock(g_plan_mu);
         if (qnb::batch_plan_ready(n, hs, x, flags, d)) return qnb::batch_plan_run(n, hs, lambda, flags, E_out, EQ_out);
+    }
+    // ---- opt-in (QNB_BATCH_PARENT=1): the windows' step graphs as children of ONE parent graph, one launch instead of n.
+    // Measured r03o (7 windows): no gain -- launching the parent costs what its ~85 nodes cost (49 us against 50-58 us for
+    // seven launches), C3 176 vs 167 us per batched step, C2 241 vs 236.
+    const bool use_parent = getenv("QNB_BATCH_PARENT") != nullptr;
+    if (use_parent && n >= 2) {
+        bool ok = true;
+        for (int k = 0; k < n && ok; k++) ok = hs[k]->use_graph && !hs[k]->comm && hs[k]->device == hs[0]->device;
+        if (ok) {
+            std::lock_guard<std::mutex> lock(g_plan_mu);
+            const int rc = qnb::batch_parent_run(n, hs, x, lambda, flags, d, E_out, EQ_out);
+            if (rc >= 0) return rc;   // -1: not applicable, fall through to the per-window launches
+        }
     }
     static const int max_workers = [] { const char *e = getenv("QNB_BATCH_THREADS"); return e ? std::max(1, atoi(e)) : 1; }();
     const int nw = std::max(1, std::min(max_workers, n));   // threads incl. the caller
@@ -2309,6 +2419,7 @@ int qnb_finalize(qnb_handle *h) {
     {
         std::lock_guard<std::mutex> lock(g_plan_mu);   // a cached batch plan must not outlive one of its handles
         for (qnb_handle *p : g_plan.hs) if (p == h) { g_plan.valid = false; g_plan.hs.clear(); break; }
+        for (qnb_handle *p : g_parent.hs) if (p == h) { g_parent.valid = false; g_parent.hs.clear(); break; }
     }
     cudaSetDevice(h->device);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);

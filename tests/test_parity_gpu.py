@@ -365,7 +365,7 @@ def test_solvent_restraints(case):
         o.close()
 
 
-@pytest.mark.parametrize("one_graph", [False, True], ids=["graph_per_window", "one_graph"])
+@pytest.mark.parametrize("one_graph", [False, True, "parent"], ids=["graph_per_window", "one_graph", "parent_graph"])
 def test_batched_windows_equal_single_calls(one_graph, monkeypatch):
     """qnb_build_lists_batch / qnb_nonbond_batch over W lambda windows of one FEP system (own coordinates and lambda per
     window, run_excl_test.sh:92-125) == W single-system calls: same list counts, gradients to FP64 summation-order noise,
@@ -373,7 +373,9 @@ def test_batched_windows_equal_single_calls(one_graph, monkeypatch):
     from oracle.pyoracle import Oracle
     from q6_b200 import synth
     from q6_b200.engine import Qnb, QnbBatch
-    if one_graph:
+    if one_graph == "parent":
+        monkeypatch.setenv("QNB_BATCH_PARENT", "1")     # the windows' step graphs as children of one parent graph
+    elif one_graph:
         monkeypatch.setenv("QNB_BATCH_GRAPH", "1")      # one launch per kernel type for all windows (k_batched)
     q = synth.solvated_sphere(14.0, 0.0, 14, 2, 97, fep="annihilate")
     cuts = common.sph_cuts(8.0)
