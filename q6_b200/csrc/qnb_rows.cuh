@@ -11,9 +11,13 @@
 // Here the two jobs are separate kernels that run concurrently and use different pipes:
 //   k_water_rows / k_solute_rows  gradient only, pure FP32, packed FFMA2/FMUL2/FADD2 (sm_100) for two site pairs per
 //                                 instruction, coordinates as 32-bit fixed point so that i-j differences are exact
-//                                 and periodic images come from integer wrap-around;
+//                                 and periodic images come from integer wrap-around; partner records of the next
+//                                 chunk loaded into registers while the current one is computed;
 //   k_pair_energy                 energies only, pure FP64, one thread per listed pair (owner side), MUFU.RSQ64H seed +
 //                                 one Newton step folded into two running sums per charge class.
+// The step kernels are written as Body functors (struct XBody { static __device__ void run(args..., BX, NBX, BY, NBY) })
+// with a thin __global__ wrapper each, so that the same body can also run inside k_batched (one launch for all windows
+// of a batch) and k_uber (several bodies in one launch), qnb_kernels.cuh.
 // Each pair's gradient is still evaluated from both sides (full rows, gather only).  Measured alternative
 // (tools/microbench2.cu, profiles/r02a_microbench2.txt): returning the partner's nine gradient components through
 // warp-coalesced RED.F64 costs 10-16 SM clocks per RED instruction, 90-140 per 32-pair chunk, against ~31 SM clocks to
