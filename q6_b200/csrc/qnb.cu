@@ -144,6 +144,7 @@ struct qnb_handle {
         qp_shift_atom;
     DBuf<uint32_t> rows;
     DBuf<double4> item_pos, src;
+    DBuf<char> lrf_planes;   // the LRF sources in planes per 32 items (k_pack_lrf_planes)
     DBuf<float4> item_posf, item_scr, srcf;
     DBuf<int> cell_unsorted, item_nq, src_off, pk_atom, pk_ct;
     DBuf<float> pk_q;
@@ -634,6 +635,7 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
         h->qp_list.ensure(std::max(D.nat_solute, 1)) || h->qw_list.ensure(std::max(D.nwat, 1)) ||
         h->qp_shift_atom.ensure(std::max(D.ncgp_solute, 1)) || h->item_pos.ensure(std::max(nu, 1)) || h->item_posf.ensure(std::max(nu, 1)) || h->item_scr.ensure(std::max(nu, 1)) ||
         h->src.ensure(std::max(D.natom, 1)) || h->srcf.ensure(std::max(D.natom, 1)) || h->cell_unsorted.ensure(std::max(nu, 1)) ||
+        h->lrf_planes.ensure((size_t)cdiv(std::max(nu, 1), 32) * kLrfPlaneBytes) ||
         h->item_nq.ensure(std::max(nu, 1) + 1) || h->src_off.ensure(std::max(nu, 1) + 2) ||
         h->pk_atom.ensure(D.natom + 4) || h->pk_ct.ensure(D.natom + 4) || h->pk_q.ensure(D.natom + 4) ||
         h->pk_qd.ensure(D.natom + 4) || h->px.ensure(D.natom + 4) || h->py.ensure(D.natom + 4) ||   // +4: the force kernels always fetch three sites
@@ -697,13 +699,15 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
                     LAUNCH_ON(h, ls, k_lrf_allpairs<6>, dim3(tb, slices), 128, 0, D, h->cut, h->x.p, h->upos.p, h->item_pos.p, h->item_posf.p,
                               h->src_off.p, h->src.p, h->lrf.p, h->lrf_mom.p);
                 LAUNCH_ON(h, ls, k_lrf_expand, cdiv(nu * 40, 256), 256, 0, D, h->lrf_mom.p, h->lrf.p);
-            } else
+            } else {
+                LAUNCH_ON(h, ls, k_pack_lrf_planes, cdiv(nu, 128), 128, 0, D, nu, h->item_pos.p, h->src_off.p, h->src.p, h->lrf_planes.p);
 #define LRFCASE(CP, RS, GN) LAUNCH_ON(h, ls, (k_lrf_accumulate<CP, RS, GN>), cdiv(nu, kRowWarps), 32 * kRowWarps, 0, D, h->cut, G, h->lrf_reach, h->x.p, h->upos.p, \
-                                      h->cell_of.p, h->cell_start.p, h->cell_items.p, h->item_pos.p, h->item_posf.p, h->src_off.p, h->src.p, h->srcf.p, h->lrf.p)
+                                      h->cell_of.p, h->cell_start.p, h->cell_items.p, h->item_pos.p, h->item_posf.p, h->src_off.p, h->src.p, h->srcf.p, h->lrf_planes.p, h->lrf.p)
             if (rowshift) { if (general) LRFCASE(true, true, true); else LRFCASE(true, true, false); }
             else if (compact) { if (general) LRFCASE(true, false, true); else LRFCASE(true, false, false); }
             else { if (general) LRFCASE(false, false, true); else LRFCASE(false, false, false); }
 #undef LRFCASE
+            }
         }
         if (h->time_build) cudaEventRecord(h->ev_bt[1], ls);
         if (h->multi_stream) { cudaEventRecord(h->ev_join[kLrfStream], ls); lrf_forked = true; }
@@ -2443,7 +2447,7 @@ int qnb_finalize(qnb_handle *h) {
     h->shk_first.release(); h->shk_ij.release(); h->shk_d2.release(); h->shk_winv.release(); h->shk_x.release();
     h->shk_xx.release(); h->shk_iter.release();
     h->bead_atoms.release(); h->bead_base.release(); h->bead_disp.release(); h->bead_eq.release();
-    h->item_posf.release(); h->item_scr.release(); h->srcf.release();
+    h->item_posf.release(); h->item_scr.release(); h->srcf.release(); h->lrf_planes.release();
     h->upk.release(); h->pk_sw.release(); h->e_cnt.release(); h->e_off.release(); h->rec_i.release(); h->rec_f.release(); h->wT.release(); h->wown.release(); h->wd.release();
     h->pw12.release(); h->ljp.release(); h->pw0.release(); h->ww_pairs.release(); h->pp_pairs.release(); h->pw_pairs.release();
     h->item_pos.release(); h->src.release(); h->cell_unsorted.release(); h->item_nq.release(); h->src_off.release();

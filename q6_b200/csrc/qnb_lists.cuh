@@ -142,6 +142,37 @@ __global__ void k_pack_sources(const int *__restrict__ npk, const int *__restric
     src[p] = v;
     srcf[p] = make_float4((float)v.x, (float)v.y, (float)v.z, (float)v.w);   // phi3 path and rsqrt seed of lrf_atom
 }
+// per list build: the LRF sources once more, laid out for the shell kernel.  Its warps take 32 accepted items at a time, one
+// unit per lane, mostly RUNS of consecutive items (cell order): from the per-atom records above a lane's 144 bytes sit 96
+// bytes from its neighbour's and one batch costs ~200 L1 wavefronts (r04c: the kernel ran at the same 2.1 ms with 12 or 16
+// warps per SM and 12 % fewer instructions - bound by the L1 tag pipe).  Here blocks of 32 items hold PLANES: 12 x 32
+// doubles {x,y,z,q of the unit's first three source atoms}, 3 x 32 floats (the charges once more), 32 atom counts
+// (kLrfPlaneBytes per block), so the lanes of a run read consecutive words.  Units with fewer than three source atoms are padded with copies
+// of the first one carrying no charge (an exact zero contribution); the atoms after the third stay in `src`.  Periodic
+// boxes: the unit is moved as a whole by the image that takes its switch atom into the box (the position it is binned and
+// screened at), so that the image of the scanned cell row is the pair's shift (k_lrf_accumulate).
+constexpr int kLrfPlaneQf = 12 * 32 * 8, kLrfPlaneCnt = kLrfPlaneQf + 3 * 32 * 4, kLrfPlaneBytes = kLrfPlaneCnt + 32 * 4;   // 3584
+__global__ void k_pack_lrf_planes(Dev D, int nunit, const double4 *__restrict__ item_pos, const int *__restrict__ src_off,
+                                  const double4 *__restrict__ src, char *__restrict__ planes) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nunit) return;
+    char *blk = planes + (size_t)(idx >> 5) * kLrfPlaneBytes;
+    double *pd = reinterpret_cast<double *>(blk) + (idx & 31);
+    float *pf = reinterpret_cast<float *>(blk + kLrfPlaneQf) + (idx & 31);
+    const int a0 = src_off[idx], n = src_off[idx + 1] - a0;
+    reinterpret_cast<int *>(blk + kLrfPlaneCnt)[idx & 31] = n;
+    double sh[3] = {0.0, 0.0, 0.0};
+    if (D.use_PBC) {
+        const double4 ip = item_pos[idx];
+        sh[0] = D.box[0] * floor(ip.x * D.inv_box[0]); sh[1] = D.box[1] * floor(ip.y * D.inv_box[1]); sh[2] = D.box[2] * floor(ip.z * D.inv_box[2]);
+    }
+    for (int k = 0; k < 3; k++) {
+        double4 v = make_double4(0.0, 0.0, 0.0, 0.0);
+        if (n > 0) { v = src[a0 + min(k, n - 1)]; if (k >= n) v.w = 0.0; }
+        pd[(4 * k + 0) * 32] = v.x - sh[0]; pd[(4 * k + 1) * 32] = v.y - sh[1]; pd[(4 * k + 2) * 32] = v.z - sh[2]; pd[(4 * k + 3) * 32] = v.w;
+        pf[k * 32] = (float)v.w;
+    }
+}
 // per step: coordinates in packed order, structure of arrays
 __global__ void k_pack_coords(int npk, const int *__restrict__ pk_atom, const double *__restrict__ x,
                               double *__restrict__ px, double *__restrict__ py, double *__restrict__ pz) {
@@ -748,7 +779,8 @@ __global__ void k_cgp_centers_only(Dev D, const double *__restrict__ x, double *
     l[0] = cx / n; l[1] = cy / n; l[2] = cz / n;
 }
 
-constexpr int kLrfSegBatch = 256;
+constexpr int kLrfSegBatch = 128;
+constexpr int kLrfStepsPerLane = 4;   // steps of one segment per pass of the step table (32 segments -> <= 128 steps)
 __constant__ int kLrfExpand[40] = {0, 1, 2, 3,
                                    4, 5, 6, 5, 7, 8, 6, 8, 9,
                                    10, 11, 12, 11, 13, 14, 12, 14, 15,    // n = x: (xx*, xy*, xz*)
@@ -805,6 +837,10 @@ __device__ __forceinline__ double lrf_finish(const double *raw, int k) {
     }
 }
 constexpr int kLrfRaw = 24;
+// the same with the FP32 displacement rounded from the FP64 one (plane records carry no FP32 coordinates)
+__device__ __forceinline__ void lrf_atom_d(double (&m)[11], float (&h)[13], double dx, double dy, double dz, double q, float qf) {
+    lrf_atom(m, h, dx, dy, dz, q, (float)dx, (float)dy, (float)dz, qf);
+}
 
 // lrf_update (nonbondene.f90:628-725), gathered per TARGET group: the warp of target unit t sums the
 // contribution of every source atom whose unit pair (t,s) the reference sends through the LRF branch
@@ -815,9 +851,12 @@ constexpr int kLrfRaw = 24;
 // offset, 2(m+1) <= n in every dimension): the periodic image is applied once per cell row to the TARGET, rows that
 // cannot reach the LRF shell are skipped and the x-range of the others is trimmed to the shell's chord, so the
 // per-candidate screening is nine FP32 instructions.  GENERAL adds what any-atom cut-offs and sharded builds need.
-struct LrfSeg { int lo, hi; float tx, ty, tz; };
+struct LrfSeg { int lo, hi; float tx, ty, tz; int img; };   // img: periodic image of the row, (ix+1) | (iy+1) << 2 | (iz+1) << 4
 #ifndef QNB_LRF_MINB
 #define QNB_LRF_MINB 4
+#endif
+#ifndef QNB_LRF_DEPTH
+#define QNB_LRF_DEPTH 2
 #endif
 template <bool COMPACT, bool ROWSHIFT, bool GENERAL>
 __global__ void __launch_bounds__(32 * kRowWarps, QNB_LRF_MINB)
@@ -825,16 +864,26 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
                  const int *__restrict__ cell_of, const int *__restrict__ cell_start, const int *__restrict__ cell_items,
                  const double4 *__restrict__ item_pos, const float4 *__restrict__ item_posf,
                  const int *__restrict__ src_off, const double4 *__restrict__ src, const float4 *__restrict__ srcf,
-                 double *__restrict__ lrf) {
+                 const char *__restrict__ planes, double *__restrict__ lrf) {
     // One WARP per target unit, the kRowWarps targets of a block being neighbours in cell order: they scan (nearly) the
     // same cells at the same time, so the source records one warp pulls through L1 serve the others (r02e: one block per
     // target with its warps on different cell rows, 49 % L1 hit rate, 258 KB of source records per target through L2).
     // Candidates are first screened (FP32 distance with a safety band, exact FP64 test inside the band) and the
     // accepted ones compacted into a per-warp queue, so that the expensive accumulation always runs on full warps
     // even when only a few percent of the scanned cells' units lie inside the LRF shell (periodic boxes).
-    __shared__ double red[kRowWarps][kLrfRaw];
-    __shared__ int queue[kRowWarps][64];
+    // everything a warp keeps in shared memory behind ONE base address (r04e: five separate per-warp arrays had their
+    // addresses rebuilt from threadIdx in every step, 39 of ~110 instructions per step)
+    struct WarpSm {
+        float4 steps[32 * kLrfStepsPerLane];   // {target image x, y, z, first item << 5 | items - 1} of a 32-wide step
+        float4 thr[2];                         // screening thresholds by source kind
+        LrfSeg seg[kLrfSegBatch];              // item ranges [lo,hi) of the cell rows (+ target image) of this warp's target
+        int simg[32 * kLrfStepsPerLane];       // image code of the step's row, in place for the queue entry
+        int queue[64];
+        double red[kLrfRaw];
+    };
+    __shared__ WarpSm wsm[kRowWarps];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    WarpSm &W = wsm[wid];
     const int titem = blockIdx.x * kRowWarps + wid;
     if (titem >= D.nunit) return;   // warp-uniform; no block-wide barrier below
     const int t = cell_items[titem];
@@ -859,32 +908,82 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
 #pragma unroll
     for (int k = 0; k < 13; k++) h[k] = 0.f;
 
-    auto accumulate = [&](int idx) {
-        // lrf_update(group1 = source unit of item idx, group2 = target): dr = x(i) - cgp_cent(target) - shift
-        double ox = cx_, oy = cy_, oz = cz_;
-        if (D.use_PBC) {
-            // shift = boxlength*nint((x(cgp(group1)%iswitch) - lrf(group2)%cgp_cent)*inv_boxl); the group's switch
-            // atom is the unit's binned position (checked at init: g_switch[u_grp[u]] == u_sw[u])
-            const double4 ip = item_pos[idx];
-            ox += pshift(ip.x - cx_, D.box[0], D.inv_box[0]);
-            oy += pshift(ip.y - cy_, D.box[1], D.inv_box[1]);
-            oz += pshift(ip.z - cz_, D.box[2], D.inv_box[2]);
+    // target centre in the frame the plane records are stored in (k_pack_lrf_planes): moved by the image that takes the
+    // target's own binned position into the box
+    double cw[3] = {cx_, cy_, cz_};
+    if (ROWSHIFT)
+        for (int d = 0; d < 3; d++) cw[d] -= D.box[d] * floor(pt[d] * D.inv_box[d]);
+    // e = item index | image code of the scanned cell row << 26 (ROWSHIFT).  The plane records of a batch are LOADED when
+    // the queue fills and USED at the next flush (r04e: 19 % of the stall samples sat on the first use of these loads),
+    // the screening steps in between cover their latency.
+    double P[12];
+    float PQ[3];
+    int pend_e = 0, pend_n = 0;
+    bool pend = false;   // warp-uniform
+    auto plane_load = [&](int e) {
+        const int idx = e & 0x3ffffff;
+        const char *blk = planes + (size_t)(idx >> 5) * kLrfPlaneBytes;
+        const double *pd = reinterpret_cast<const double *>(blk) + (idx & 31);
+        const float *pf = reinterpret_cast<const float *>(blk + kLrfPlaneQf) + (idx & 31);
+#pragma unroll
+        for (int k = 0; k < 12; k++) P[k] = pd[32 * k];   // a run of items reads consecutive words of every plane
+#pragma unroll
+        for (int k = 0; k < 3; k++) PQ[k] = pf[32 * k];
+        pend_n = reinterpret_cast<const int *>(blk + kLrfPlaneCnt)[idx & 31];
+        pend_e = e;
+    };
+    // lrf_update(group1 = source unit of the item, group2 = target): dr = x(i) - cgp_cent(target) - shift
+    auto plane_compute = [&]() {
+        double ox = cw[0], oy = cw[1], oz = cw[2];
+        if (ROWSHIFT) {
+            // shift = boxlength*nint((x(cgp(group1)%iswitch) - lrf(group2)%cgp_cent)*inv_boxl): with both ends taken into
+            // the box it is minus the image the row was scanned at (|delta| < box/2 for every scanned cell, see qnb.cu)
+            const int code = (int)((unsigned)pend_e >> 26);
+            ox -= (double)((code & 3) - 1) * D.box[0];
+            oy -= (double)(((code >> 2) & 3) - 1) * D.box[1];
+            oz -= (double)(((code >> 4) & 3) - 1) * D.box[2];
         }
+        lrf_atom_d(m, h, P[0] - ox, P[1] - oy, P[2] - oz, P[3], PQ[0]);
+        lrf_atom_d(m, h, P[4] - ox, P[5] - oy, P[6] - oz, P[7], PQ[1]);
+        lrf_atom_d(m, h, P[8] - ox, P[9] - oy, P[10] - oz, P[11], PQ[2]);
+        if (pend_n > 3) {
+            // the rest of a larger solute group from the per-atom records (stored unmoved)
+            const int idx = pend_e & 0x3ffffff;
+            if (ROWSHIFT) {
+                const double4 ip = item_pos[idx];
+                ox += D.box[0] * floor(ip.x * D.inv_box[0]); oy += D.box[1] * floor(ip.y * D.inv_box[1]); oz += D.box[2] * floor(ip.z * D.inv_box[2]);
+            }
+            const int a0 = src_off[idx];
+            for (int k = a0 + 3; k < a0 + pend_n; k++) {
+                const double4 sa = src[k];
+                lrf_atom_d(m, h, sa.x - ox, sa.y - oy, sa.z - oz, sa.w, (float)sa.w);
+            }
+        }
+    };
+    auto accumulate = [&](int e) {
+        if (ROWSHIFT || !D.use_PBC) { plane_load(e); plane_compute(); return; }
+        // small periodic boxes: the shift from the pair itself; the group's switch atom is the unit's binned position
+        // (checked at init: g_switch[u_grp[u]] == u_sw[u])
+        const int idx = e & 0x3ffffff;
+        const double4 ip = item_pos[idx];
+        const double ox = cx_ + pshift(ip.x - cx_, D.box[0], D.inv_box[0]);
+        const double oy = cy_ + pshift(ip.y - cy_, D.box[1], D.inv_box[1]);
+        const double oz = cz_ + pshift(ip.z - cz_, D.box[2], D.inv_box[2]);
         const float oxf = (float)ox, oyf = (float)oy, ozf = (float)oz;
         const int a0 = src_off[idx], a1 = src_off[idx + 1];
-        if (a1 - a0 == 3) {
-            // three-atom unit (every water, most solute groups): all nine loads in flight before the first use
-            const double4 s0 = src[a0], s1 = src[a0 + 1], s2 = src[a0 + 2];
-            const float4 f0 = srcf[a0], f1 = srcf[a0 + 1], f2 = srcf[a0 + 2];
-            lrf_atom(m, h, s0.x - ox, s0.y - oy, s0.z - oz, s0.w, f0.x - oxf, f0.y - oyf, f0.z - ozf, f0.w);
-            lrf_atom(m, h, s1.x - ox, s1.y - oy, s1.z - oz, s1.w, f1.x - oxf, f1.y - oyf, f1.z - ozf, f1.w);
-            lrf_atom(m, h, s2.x - ox, s2.y - oy, s2.z - oz, s2.w, f2.x - oxf, f2.y - oyf, f2.z - ozf, f2.w);
-        } else
-            for (int k = a0; k < a1; k++) {
-                const double4 sa = src[k];
-                const float4 sf = srcf[k];
-                lrf_atom(m, h, sa.x - ox, sa.y - oy, sa.z - oz, sa.w, sf.x - oxf, sf.y - oyf, sf.z - ozf, sf.w);
-            }
+        for (int k = a0; k < a1; k++) {
+            const double4 sa = src[k];
+            const float4 sf = srcf[k];
+            lrf_atom(m, h, sa.x - ox, sa.y - oy, sa.z - oz, sa.w, sf.x - oxf, sf.y - oyf, sf.z - ozf, sf.w);
+        }
+    };
+    // a full batch from the queue: the pending one is summed, this one becomes pending
+    auto flush = [&](int e) {
+        if (ROWSHIFT || !D.use_PBC) {
+            if (pend) plane_compute();
+            plane_load(e);
+            pend = true;
+        } else accumulate(e);
     };
 
     const int cu = cell_of[t];
@@ -902,7 +1001,14 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
     const float in_lo_s = lo_of(C.rc2_of(cls_s)), in_hi_s = hi_of(C.rc2_of(cls_s));
     const float in_lo_w = lo_of(C.rc2_of(cls_w)), in_hi_w = hi_of(C.rc2_of(cls_w));
     const float out_lo = lo_of(C.rclrf2), out_hi = hi_of(C.rclrf2);
-    const bool all_s = C.lrf_all_of(cls_s), all_w = C.lrf_all_of(cls_w);
+    // screening thresholds by source kind in shared memory (one 16-byte load per step instead of eight registers)
+    float4 *thr = W.thr;
+    if (lane == 0) {
+        const float kInf = __int_as_float(0x7f800000);
+        thr[0] = make_float4(in_lo_w, in_hi_w, C.lrf_all_of(cls_w) ? kInf : out_hi, C.lrf_all_of(cls_w) ? kInf : out_lo);
+        thr[1] = make_float4(in_lo_s, in_hi_s, C.lrf_all_of(cls_s) ? kInf : out_hi, C.lrf_all_of(cls_s) ? kInf : out_lo);
+    }
+    __syncwarp();
     const float bx = f32_once(D.box[0]), by = f32_once(D.box[1]), bz = f32_once(D.box[2]);
     const float ibx = f32_once(D.inv_box[0]), iby = f32_once(D.inv_box[1]), ibz = f32_once(D.inv_box[2]);
     // target position as the candidates are stored: wrapped into the box when periodic (k_pack_items)
@@ -910,16 +1016,76 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
     if (G.periodic)
         for (int d = 0; d < 3; d++) ptw[d] -= D.box[d] * floor(ptw[d] * D.inv_box[d]);
     const float ptf[3] = {f32_once(ptw[0]), f32_once(ptw[1]), f32_once(ptw[2])};
-    __shared__ LrfSeg seg_all[kRowWarps][kLrfSegBatch];   // item ranges [lo,hi) of the cell rows (+ target image) of this warp's target
-    LrfSeg *seg = seg_all[wid];
+    LrfSeg *seg = W.seg;
+    float4 *steps = W.steps;
+    int *simg = W.simg;
+    int *myq = W.queue;
+    const unsigned lt_mask = (1u << lane) - 1u;
     int qn = 0;   // entries waiting in this warp's queue (warp-uniform)
+    // screening record of one step; lanes past the step's last item get the "no source" id
+    auto fetch = [&](int sidx, float4 &pf) {
+        const int code = __float_as_int(steps[sidx].w);
+        pf = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+        if (lane <= (code & 31)) pf = item_posf[(code >> 5) + lane];
+    };
+    // one 32-wide step: FP32 screening of the candidates against the target image of the step, the FP64 test for the
+    // few inside the safety band, accepted items to the queue (or straight to the accumulation)
+    auto process = [&](int sidx, const float4 &pf) {
+        const float4 st = steps[sidx];
+        const int idx = (__float_as_int(st.w) >> 5) + lane;
+        const int ent = ROWSHIFT ? (idx | simg[sidx]) : idx;
+        const int s = __float_as_int(pf.w);
+        float dx = pf.x - st.x, dy = pf.y - st.y, dz = pf.z - st.z;
+        if (!ROWSHIFT && D.use_PBC) { dx -= bx * rintf(dx * ibx); dy -= by * rintf(dy * iby); dz -= bz * rintf(dz * ibz); }
+        const float r2f = dx * dx + dy * dy + dz * dz;
+        const bool s_sol = s < ns;
+        // "no LRF cut-off" classes carry infinite outer thresholds
+        const float4 th = thr[s_sol ? 1 : 0];     // {in_lo, in_hi, out_hi, out_lo} of the source's kind
+        bool rej = r2f < th.x || r2f > th.z;      // listed, or outside the shell
+        bool sure = r2f > th.y && r2f < th.w;     // surely inside the shell; neither: the FP64 test decides
+        if (GENERAL && D.any_atom && (t_sol || s_sol)) { rej = !any_all && r2f > hi_band; sure = false; }
+        rej = rej || s < 0 || s == t;
+        bool accept = sure && !rej;
+        const bool slow = !rej && ((GENERAL && D.sharded) || !sure);
+        if (__any_sync(kFull, slow)) {
+            if (slow) {
+                bool owner_is_t;
+                const int cls = pair_class(t, s, ns, owner_is_t);
+                if (GENERAL && D.sharded && !(D.shard_rows ? row_in_shard(D, cls, t) : in_shard(D, cls, owner_is_t ? t : s))) accept = false;
+                else if (!sure) {
+                    const double4 ip = item_pos[idx];
+                    const double ps[3] = {ip.x, ip.y, ip.z};
+                    // outside the class cut-off (else: a listed pair) and inside the LRF cut-off
+                    accept = (owner_is_t ? unit_pair_test(D, C, x, cls, t, s, pt, ps) : unit_pair_test(D, C, x, cls, s, t, ps, pt)).lrf;
+                }
+            }
+        }
+        if (!COMPACT) {
+            // nearly every scanned unit is a source (sphere with RcLRF covering it): no queueing needed
+            if (accept) accumulate(ent);
+        } else {
+            const unsigned mask = __ballot_sync(kFull, accept);
+            if (accept) myq[qn + __popc(mask & lt_mask)] = ent;
+            qn += __popc(mask);
+            if (qn >= 32) {
+                __syncwarp();
+                flush(myq[lane]);
+                const int rest = qn - 32;
+                int moved = 0;
+                if (lane < rest) moved = myq[32 + lane];
+                __syncwarp();
+                if (lane < rest) myq[lane] = moved;
+                qn = rest;
+            }
+        }
+    };
     for (int r0 = 0; r0 < nrow; r0 += kLrfSegBatch) {
         __syncwarp();
         int nseg = 0;
-        if (whole) { if (lane == 0) seg[0] = LrfSeg{0, D.nunit, ptf[0], ptf[1], ptf[2]}; nseg = 1; }
+        if (whole) { if (lane == 0) seg[0] = LrfSeg{0, D.nunit, ptf[0], ptf[1], ptf[2], 0}; nseg = 1; }
         else for (int rb = r0; rb < min(nrow, r0 + kLrfSegBatch); rb += 32) {
             const int r = rb + lane;
-            LrfSeg sg{0, 0, ptf[0], ptf[1], ptf[2]};
+            LrfSeg sg{0, 0, ptf[0], ptf[1], ptf[2], 0};
             if (r < min(nrow, r0 + kLrfSegBatch)) {
             const int nxs = ROWSHIFT ? 2 : xs.n;
             const int sgi = r % nxs, iy = (r / nxs) % ry.count, iz = r / (nxs * ry.count);
@@ -953,6 +1119,7 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
                         const int izg = (zu >= 0 ? zu / G.n[2] : -((-zu + G.n[2] - 1) / G.n[2]));
                         // candidate image = stored position + img*box: subtract it from the target instead
                         sg.tx = ptf[0] - (float)img * bx; sg.ty = ptf[1] - (float)iyg * by; sg.tz = ptf[2] - (float)izg * bz;
+                        sg.img = (img + 1) | ((iyg + 1) << 2) | ((izg + 1) << 4);
                     }
                 }
             }
@@ -963,96 +1130,84 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
             nseg += __popc(keep);
         }
         __syncwarp();
-        // The candidates of all segments are walked as one sequence of 32-wide steps; the screening record of the NEXT step
-        // (possibly the first of the next segment) is loaded before the current one is processed: with one warp per target
-        // the load -> test -> queue chain of a step is otherwise fully exposed (segments hold one or two steps each).
-        if (nseg > 0) {
-            int r = 0;
-            LrfSeg sg = seg[0];
-            int base = sg.lo;
-            float4 pf_cur = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (base + lane < sg.hi) pf_cur = item_posf[base + lane];
-            while (r < nseg) {
-                int nr = r, nbase = base + 32;
-                LrfSeg nsg = sg;
-                if (nbase >= sg.hi) {
-                    nr = r + 1;
-                    if (nr < nseg) { nsg = seg[nr]; nbase = nsg.lo; }
+        // The segments are expanded, 32 at a time, into a table of 32-wide STEPS {target image, first item << 5 | items - 1}
+        // (one 16-byte broadcast load per step); the walk over the table carries no segment logic and loads the screening
+        // record of the next step before the current one is tested.  r03h: the walk over the segment table itself cost
+        // 118 warp instructions per step (segment switches, rematerialised lane masks), half of the kernel.
+        for (int g0 = 0; g0 < nseg; g0 += 32) {
+            LrfSeg ms{0, 0, 0.f, 0.f, 0.f, 0};
+            if (g0 + lane < nseg) ms = seg[g0 + lane];
+            int lo = ms.lo;
+            for (;;) {
+                const int n = max(0, min(kLrfStepsPerLane, (ms.hi - lo + 31) >> 5));   // steps this lane adds in this pass
+                int incl = n;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(kFull, incl, o);
+                    if (lane >= o) incl += v;
                 }
-                float4 pf_next = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (nr < nseg && nbase + lane < nsg.hi) pf_next = item_posf[nbase + lane];
-                const int hi = sg.hi;
-                const int idx = base + lane;
-                bool accept = false;
-                if (idx < hi) {
-                    const float4 pf = pf_cur;
-                    const int s = __float_as_int(pf.w);
-                    float dx = pf.x - sg.tx, dy = pf.y - sg.ty, dz = pf.z - sg.tz;
-                    if (!ROWSHIFT && D.use_PBC) { dx -= bx * rintf(dx * ibx); dy -= by * rintf(dy * iby); dz -= bz * rintf(dz * ibz); }
-                    const float r2f = dx * dx + dy * dy + dz * dz;
-                    const bool s_sol = s < ns;
-                    // zones: 0 listed or outside the shell, 1 surely inside it, 2 the FP64 test decides
-                    int zone;
-                    if (GENERAL && D.any_atom && (t_sol || s_sol)) zone = (!any_all && r2f > hi_band) ? 0 : 2;
-                    else {
-                        const float il = s_sol ? in_lo_s : in_lo_w, ih = s_sol ? in_hi_s : in_hi_w;
-                        const bool all = s_sol ? all_s : all_w;
-                        zone = (r2f < il || (!all && r2f > out_hi)) ? 0 : (r2f > ih && (all || r2f < out_lo)) ? 1 : 2;
-                    }
-                    if (s < 0 || s == t) zone = 0;
-                    if (zone != 0 && ((GENERAL && D.sharded) || zone == 2)) {
-                        bool owner_is_t;
-                        const int cls = pair_class(t, s, ns, owner_is_t);
-                        if (GENERAL && D.sharded && !(D.shard_rows ? row_in_shard(D, cls, t) : in_shard(D, cls, owner_is_t ? t : s))) zone = 0;
-                        else if (zone == 2) {
-                            const double4 ip = item_pos[idx];
-                            const double ps[3] = {ip.x, ip.y, ip.z};
-                            // outside the class cut-off (else: a listed pair) and inside the LRF cut-off
-                            const bool lrf = (owner_is_t ? unit_pair_test(D, C, x, cls, t, s, pt, ps)
-                                                         : unit_pair_test(D, C, x, cls, s, t, ps, pt)).lrf;
-                            zone = lrf ? 1 : 0;
-                        }
-                    }
-                    accept = zone == 1;
+                const int total = __shfl_sync(kFull, incl, 31);
+                if (total == 0) break;
+                __syncwarp();   // the previous pass has been read
+                for (int k = 0; k < n; k++) {
+                    const int b = lo + 32 * k;
+                    steps[incl - n + k] = make_float4(ms.tx, ms.ty, ms.tz, __int_as_float((b << 5) | (min(32, ms.hi - b) - 1)));
+                    if (ROWSHIFT) simg[incl - n + k] = ms.img << 26;
                 }
-                if (!COMPACT) {
-                    // nearly every scanned unit is a source (sphere with RcLRF covering it): no queueing needed
-                    if (accept) accumulate(idx);
-                } else {
-                const unsigned mask = __ballot_sync(kFull, accept);
-                if (accept) queue[wid][qn + __popc(mask & ((1u << lane) - 1u))] = idx;
-                qn += __popc(mask);
-                if (qn >= 32) {
-                    __syncwarp();
-                    accumulate(queue[wid][lane]);
-                    const int rest = qn - 32;
-                    int moved = 0;
-                    if (lane < rest) moved = queue[wid][32 + lane];
-                    __syncwarp();
-                    if (lane < rest) queue[wid][lane] = moved;
-                    qn = rest;
+                lo += 32 * n;
+                __syncwarp();
+#if QNB_LRF_DEPTH == 4
+                // records of four steps in flight, four register sets
+                float4 p0, p1, p2, p3;
+                fetch(0, p0);
+                if (1 < total) fetch(1, p1);
+                if (2 < total) fetch(2, p2);
+                if (3 < total) fetch(3, p3);
+                for (int sidx = 0; sidx < total; sidx += 4) {
+                    process(sidx, p0);
+                    if (sidx + 4 < total) fetch(sidx + 4, p0);
+                    if (sidx + 1 >= total) break;
+                    process(sidx + 1, p1);
+                    if (sidx + 5 < total) fetch(sidx + 5, p1);
+                    if (sidx + 2 >= total) break;
+                    process(sidx + 2, p2);
+                    if (sidx + 6 < total) fetch(sidx + 6, p2);
+                    if (sidx + 3 >= total) break;
+                    process(sidx + 3, p3);
+                    if (sidx + 7 < total) fetch(sidx + 7, p3);
                 }
-                }   // end of the step (COMPACT path falls through, !COMPACT path jumps here)
-                r = nr; base = nbase; sg = nsg; pf_cur = pf_next;
+#else
+                // the record of the next step is loaded before the current one is tested; two register sets: no copies
+                float4 p0, p1;
+                fetch(0, p0);
+                for (int sidx = 0; sidx < total; sidx += 2) {
+                    if (sidx + 1 < total) fetch(sidx + 1, p1);
+                    process(sidx, p0);
+                    if (sidx + 1 >= total) break;
+                    if (sidx + 2 < total) fetch(sidx + 2, p0);
+                    process(sidx + 1, p1);
+                }
+#endif
             }
         }
     }
     __syncwarp();
-    if (lane < qn) accumulate(queue[wid][lane]);
+    if (pend) plane_compute();
+    if (lane < qn) accumulate(myq[lane]);
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < 11; k++) {
         const double a = warp_sum(m[k]);
-        if (lane == 0) red[wid][k] = a;
+        if (lane == 0) W.red[k] = a;
     }
 #pragma unroll
     for (int k = 0; k < 13; k++) {
         const double a = warp_sum((double)h[k]);
-        if (lane == 0) red[wid][11 + k] = a;
+        if (lane == 0) W.red[11 + k] = a;
     }
     __syncwarp();
     // LRF_TYPE order after cgp_cent: phi0, phi1(3), phi2(a)%b (9), phi3(3*(n-1)+j)%k (27) from the unique moments
-    for (int k = lane; k < 40; k += 32) lt[3 + k] = lrf_finish(red[wid], kLrfExpand[k]);
+    for (int k = lane; k < 40; k += 32) lt[3 + k] = lrf_finish(W.red, kLrfExpand[k]);
 }
 
 // ---------------------------------------------------------------- LRF, sphere with the LRF cut-off spanning it
