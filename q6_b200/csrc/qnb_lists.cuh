@@ -780,7 +780,6 @@ __global__ void k_cgp_centers_only(Dev D, const double *__restrict__ x, double *
 }
 
 constexpr int kLrfSegBatch = 128;
-constexpr int kLrfStepsPerLane = 4;   // steps of one segment per pass of the step table (32 segments -> <= 128 steps)
 __constant__ int kLrfExpand[40] = {0, 1, 2, 3,
                                    4, 5, 6, 5, 7, 8, 6, 8, 9,
                                    10, 11, 12, 11, 13, 14, 12, 14, 15,    // n = x: (xx*, xy*, xz*)
@@ -855,9 +854,6 @@ struct LrfSeg { int lo, hi; float tx, ty, tz; int img; };   // img: periodic ima
 #ifndef QNB_LRF_MINB
 #define QNB_LRF_MINB 4
 #endif
-#ifndef QNB_LRF_DEPTH
-#define QNB_LRF_DEPTH 2
-#endif
 template <bool COMPACT, bool ROWSHIFT, bool GENERAL>
 __global__ void __launch_bounds__(32 * kRowWarps, QNB_LRF_MINB)
 k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x, const double *__restrict__ upos,
@@ -874,16 +870,20 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
     // everything a warp keeps in shared memory behind ONE base address (r04e: five separate per-warp arrays had their
     // addresses rebuilt from threadIdx in every step, 39 of ~110 instructions per step)
     struct WarpSm {
-        float4 steps[32 * kLrfStepsPerLane];   // {target image x, y, z, first item << 5 | items - 1} of a 32-wide step
-        float4 thr[2];                         // screening thresholds by source kind
-        LrfSeg seg[kLrfSegBatch];              // item ranges [lo,hi) of the cell rows (+ target image) of this warp's target
-        int simg[32 * kLrfStepsPerLane];       // image code of the step's row, in place for the queue entry
+        float4 segA[kLrfSegBatch + 1];   // per segment: target image x, y, z and (first item - flat position of its first candidate)
+        float4 thr[2];                   // screening thresholds by source kind
+        LrfSeg seg[kLrfSegBatch];        // item ranges [lo,hi) of the cell rows (+ target image) of this warp's target, as built
+        int segI[kLrfSegBatch + 1];      // image code of the segment's row, in place for the queue entry
+        int cumE[kLrfSegBatch + 32];     // flat position one past the segment's last candidate
         int queue[64];
         double red[kLrfRaw];
     };
     __shared__ WarpSm wsm[kRowWarps];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    WarpSm &W = wsm[wid];
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int wbase = wid * (int)sizeof(WarpSm);
+    // opaque to the compiler: it otherwise rebuilds both from %tid wherever they are used (17 S2R sites in the r04f build)
+    asm volatile("" : "+r"(lane), "+r"(wbase));
+    WarpSm &W = *reinterpret_cast<WarpSm *>(reinterpret_cast<char *>(wsm) + wbase);
     const int titem = blockIdx.x * kRowWarps + wid;
     if (titem >= D.nunit) return;   // warp-uniform; no block-wide barrier below
     const int t = cell_items[titem];
@@ -1017,23 +1017,35 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
         for (int d = 0; d < 3; d++) ptw[d] -= D.box[d] * floor(ptw[d] * D.inv_box[d]);
     const float ptf[3] = {f32_once(ptw[0]), f32_once(ptw[1]), f32_once(ptw[2])};
     LrfSeg *seg = W.seg;
-    float4 *steps = W.steps;
-    int *simg = W.simg;
     int *myq = W.queue;
     const unsigned lt_mask = (1u << lane) - 1u;
     int qn = 0;   // entries waiting in this warp's queue (warp-uniform)
-    // screening record of one step; lanes past the step's last item get the "no source" id
-    auto fetch = [&](int sidx, float4 &pf) {
-        const int code = __float_as_int(steps[sidx].w);
-        pf = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-        if (lane <= (code & 31)) pf = item_posf[(code >> 5) + lane];
+    // The candidates of all segments of a batch of rows are walked as ONE sequence of 32-wide steps (r04f: with steps cut at
+    // the segment ends 43 % of the lanes were idle, a segment holds ~30 candidates).  The lanes of a step find their
+    // segment from the segment ends: lane j looks at the end of segment kmin + j, the ends that fall inside the step are
+    // OR-ed into a bit mask and a lane's segment is kmin + the number of ends at or before its position.
+    struct StepRegs { float4 pf; float tx, ty, tz; int ent; };
+    int kmin = 0, flat_total = 0;
+    auto fetch = [&](int sidx, StepRegs &r) {
+        const int f0 = 32 * sidx;
+        const int rel = W.cumE[kmin + lane] - f0;
+        const unsigned mask = __reduce_or_sync(kFull, (rel >= 1 && rel <= 31) ? (1u << rel) : 0u);
+        const int k = kmin + __popc(mask & (0xffffffffu >> (31 - lane)));
+        kmin += __popc(mask) + (__any_sync(kFull, rel == 32) ? 1 : 0);
+        const float4 a = W.segA[k];
+        r.tx = a.x; r.ty = a.y; r.tz = a.z;
+        const int idx = f0 + lane + __float_as_int(a.w);
+        r.ent = -1;
+        r.pf = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));   // lanes past the last candidate: the "no source" id
+        if (f0 + lane < flat_total) { r.ent = idx | W.segI[k]; r.pf = item_posf[idx]; }
     };
-    // one 32-wide step: FP32 screening of the candidates against the target image of the step, the FP64 test for the
+    // one 32-wide step: FP32 screening of the candidates against the target image of their rows, the FP64 test for the
     // few inside the safety band, accepted items to the queue (or straight to the accumulation)
-    auto process = [&](int sidx, const float4 &pf) {
-        const float4 st = steps[sidx];
-        const int idx = (__float_as_int(st.w) >> 5) + lane;
-        const int ent = ROWSHIFT ? (idx | simg[sidx]) : idx;
+    auto process = [&](const StepRegs &r) {
+        const float4 pf = r.pf;
+        const float4 st = make_float4(r.tx, r.ty, r.tz, 0.f);
+        const int ent = r.ent;
+        const int idx = ent & 0x3ffffff;
         const int s = __float_as_int(pf.w);
         float dx = pf.x - st.x, dy = pf.y - st.y, dz = pf.z - st.z;
         if (!ROWSHIFT && D.use_PBC) { dx -= bx * rintf(dx * ibx); dy -= by * rintf(dy * iby); dz -= bz * rintf(dz * ibz); }
@@ -1130,64 +1142,43 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
             nseg += __popc(keep);
         }
         __syncwarp();
-        // The segments are expanded, 32 at a time, into a table of 32-wide STEPS {target image, first item << 5 | items - 1}
-        // (one 16-byte broadcast load per step); the walk over the table carries no segment logic and loads the screening
-        // record of the next step before the current one is tested.  r03h: the walk over the segment table itself cost
-        // 118 warp instructions per step (segment switches, rematerialised lane masks), half of the kernel.
+        // flat positions of the segments' candidates (exclusive scan of the lengths)
+        int carry = 0;
         for (int g0 = 0; g0 < nseg; g0 += 32) {
+            const int k = g0 + lane;
             LrfSeg ms{0, 0, 0.f, 0.f, 0.f, 0};
-            if (g0 + lane < nseg) ms = seg[g0 + lane];
-            int lo = ms.lo;
-            for (;;) {
-                const int n = max(0, min(kLrfStepsPerLane, (ms.hi - lo + 31) >> 5));   // steps this lane adds in this pass
-                int incl = n;
+            if (k < nseg) ms = seg[k];
+            const int len = ms.hi - ms.lo;
+            int incl = len;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int v = __shfl_up_sync(kFull, incl, o);
-                    if (lane >= o) incl += v;
-                }
-                const int total = __shfl_sync(kFull, incl, 31);
-                if (total == 0) break;
-                __syncwarp();   // the previous pass has been read
-                for (int k = 0; k < n; k++) {
-                    const int b = lo + 32 * k;
-                    steps[incl - n + k] = make_float4(ms.tx, ms.ty, ms.tz, __int_as_float((b << 5) | (min(32, ms.hi - b) - 1)));
-                    if (ROWSHIFT) simg[incl - n + k] = ms.img << 26;
-                }
-                lo += 32 * n;
-                __syncwarp();
-#if QNB_LRF_DEPTH == 4
-                // records of four steps in flight, four register sets
-                float4 p0, p1, p2, p3;
-                fetch(0, p0);
-                if (1 < total) fetch(1, p1);
-                if (2 < total) fetch(2, p2);
-                if (3 < total) fetch(3, p3);
-                for (int sidx = 0; sidx < total; sidx += 4) {
-                    process(sidx, p0);
-                    if (sidx + 4 < total) fetch(sidx + 4, p0);
-                    if (sidx + 1 >= total) break;
-                    process(sidx + 1, p1);
-                    if (sidx + 5 < total) fetch(sidx + 5, p1);
-                    if (sidx + 2 >= total) break;
-                    process(sidx + 2, p2);
-                    if (sidx + 6 < total) fetch(sidx + 6, p2);
-                    if (sidx + 3 >= total) break;
-                    process(sidx + 3, p3);
-                    if (sidx + 7 < total) fetch(sidx + 7, p3);
-                }
-#else
-                // the record of the next step is loaded before the current one is tested; two register sets: no copies
-                float4 p0, p1;
-                fetch(0, p0);
-                for (int sidx = 0; sidx < total; sidx += 2) {
-                    if (sidx + 1 < total) fetch(sidx + 1, p1);
-                    process(sidx, p0);
-                    if (sidx + 1 >= total) break;
-                    if (sidx + 2 < total) fetch(sidx + 2, p0);
-                    process(sidx + 1, p1);
-                }
-#endif
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(kFull, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int end = carry + incl;
+            if (k < nseg) {
+                W.segA[k] = make_float4(ms.tx, ms.ty, ms.tz, __int_as_float(ms.lo - (end - len)));
+                W.segI[k] = ROWSHIFT ? (ms.img << 26) : 0;
+            }
+            W.cumE[k] = k < nseg ? end : 0x3fffffff;
+            carry = __shfl_sync(kFull, end, 31);
+        }
+        for (int k = ((nseg + 31) & ~31) + lane; k < nseg + 32; k += 32) W.cumE[k] = 0x3fffffff;
+        if (lane == 0) { W.segA[nseg] = make_float4(0.f, 0.f, 0.f, 0.f); W.segI[nseg] = 0; }
+        __syncwarp();
+        flat_total = carry;
+        kmin = 0;
+        const int nsteps = (flat_total + 31) >> 5;
+        if (nsteps > 0) {
+            // the record of the next step is loaded before the current one is tested; two register sets: no copies
+            StepRegs ra, rb;
+            fetch(0, ra);
+            for (int sidx = 0; sidx < nsteps; sidx += 2) {
+                if (sidx + 1 < nsteps) fetch(sidx + 1, rb);
+                process(ra);
+                if (sidx + 1 >= nsteps) break;
+                if (sidx + 2 < nsteps) fetch(sidx + 2, ra);
+                process(rb);
             }
         }
     }
