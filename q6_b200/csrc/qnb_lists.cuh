@@ -1024,7 +1024,7 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
     // the segment ends 43 % of the lanes were idle, a segment holds ~30 candidates).  The lanes of a step find their
     // segment from the segment ends: lane j looks at the end of segment kmin + j, the ends that fall inside the step are
     // OR-ed into a bit mask and a lane's segment is kmin + the number of ends at or before its position.
-    struct StepRegs { float4 pf; float tx, ty, tz; int ent; };
+    struct StepRegs { float4 pf; int k, ent; };   // screening record, segment, queue entry of a lane's candidate
     int kmin = 0, flat_total = 0;
     auto fetch = [&](int sidx, StepRegs &r) {
         const int f0 = 32 * sidx;
@@ -1032,9 +1032,8 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
         const unsigned mask = __reduce_or_sync(kFull, (rel >= 1 && rel <= 31) ? (1u << rel) : 0u);
         const int k = kmin + __popc(mask & (0xffffffffu >> (31 - lane)));
         kmin += __popc(mask) + (__any_sync(kFull, rel == 32) ? 1 : 0);
-        const float4 a = W.segA[k];
-        r.tx = a.x; r.ty = a.y; r.tz = a.z;
-        const int idx = f0 + lane + __float_as_int(a.w);
+        const int idx = f0 + lane + __float_as_int(W.segA[k].w);
+        r.k = k;
         r.ent = -1;
         r.pf = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));   // lanes past the last candidate: the "no source" id
         if (f0 + lane < flat_total) { r.ent = idx | W.segI[k]; r.pf = item_posf[idx]; }
@@ -1043,7 +1042,7 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
     // few inside the safety band, accepted items to the queue (or straight to the accumulation)
     auto process = [&](const StepRegs &r) {
         const float4 pf = r.pf;
-        const float4 st = make_float4(r.tx, r.ty, r.tz, 0.f);
+        const float4 st = W.segA[r.k];
         const int ent = r.ent;
         const int idx = ent & 0x3ffffff;
         const int s = __float_as_int(pf.w);
@@ -1170,15 +1169,18 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
         kmin = 0;
         const int nsteps = (flat_total + 31) >> 5;
         if (nsteps > 0) {
-            // the record of the next step is loaded before the current one is tested; two register sets: no copies
-            StepRegs ra, rb;
-            fetch(0, ra);
-            for (int sidx = 0; sidx < nsteps; sidx += 2) {
-                if (sidx + 1 < nsteps) fetch(sidx + 1, rb);
-                process(ra);
-                if (sidx + 1 >= nsteps) break;
-                if (sidx + 2 < nsteps) fetch(sidx + 2, ra);
-                process(rb);
+            // the records of the next two steps are in flight while the current one is tested (r04g: with one step of lead
+            // and full steps the record gather was the largest stall); three register sets rotated by copies, one instance
+            // of the step body (four unrolled instances ran into instruction-cache misses, r04c)
+            StepRegs r0, r1, r2;
+            fetch(0, r0);
+            r1 = r0;
+            if (1 < nsteps) fetch(1, r1);
+            for (int sidx = 0; sidx < nsteps; sidx++) {
+                r2 = r1;
+                if (sidx + 2 < nsteps) fetch(sidx + 2, r2);
+                process(r0);
+                r0 = r1; r1 = r2;
             }
         }
     }
