@@ -854,6 +854,9 @@ struct LrfSeg { int lo, hi; float tx, ty, tz; int img; };   // img: periodic ima
 #ifndef QNB_LRF_MINB
 #define QNB_LRF_MINB 4
 #endif
+#ifndef QNB_LRF_DEPTH
+#define QNB_LRF_DEPTH 3   // register sets of the screening walk: records of DEPTH-1 steps in flight
+#endif
 template <bool COMPACT, bool ROWSHIFT, bool GENERAL>
 __global__ void __launch_bounds__(32 * kRowWarps, QNB_LRF_MINB)
 k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x, const double *__restrict__ upos,
@@ -1170,17 +1173,21 @@ k_lrf_accumulate(Dev D, Cut C, Grid G, int3 reach, const double *__restrict__ x,
         const int nsteps = (flat_total + 31) >> 5;
         if (nsteps > 0) {
             // the records of the next two steps are in flight while the current one is tested (r04g: with one step of lead
-            // and full steps the record gather was the largest stall); three register sets rotated by copies, one instance
+            // and full steps the record gather was the largest stall); QNB_LRF_DEPTH register sets rotated by copies, one instance
             // of the step body (four unrolled instances ran into instruction-cache misses, r04c)
-            StepRegs r0, r1, r2;
-            fetch(0, r0);
-            r1 = r0;
-            if (1 < nsteps) fetch(1, r1);
+            StepRegs r[QNB_LRF_DEPTH];
+            fetch(0, r[0]);
+#pragma unroll
+            for (int d = 1; d < QNB_LRF_DEPTH - 1; d++) {
+                r[d] = r[d - 1];
+                if (d < nsteps) fetch(d, r[d]);
+            }
             for (int sidx = 0; sidx < nsteps; sidx++) {
-                r2 = r1;
-                if (sidx + 2 < nsteps) fetch(sidx + 2, r2);
-                process(r0);
-                r0 = r1; r1 = r2;
+                r[QNB_LRF_DEPTH - 1] = r[QNB_LRF_DEPTH - 2];
+                if (sidx + QNB_LRF_DEPTH - 1 < nsteps) fetch(sidx + QNB_LRF_DEPTH - 1, r[QNB_LRF_DEPTH - 1]);
+                process(r[0]);
+#pragma unroll
+                for (int d = 0; d < QNB_LRF_DEPTH - 1; d++) r[d] = r[d + 1];
             }
         }
     }

@@ -149,6 +149,51 @@ def test_baseline_configs(name):
     _run_case(q, cuts, lam, check_lists=True)
 
 
+@pytest.mark.parametrize("shard_rows", [False, True], ids=["pair_partition", "row_partition"])
+@pytest.mark.parametrize("case", ["sphere_q", "water_box", "water_box_shell"])
+def test_shards_on_one_gpu_sum_to_the_whole(case, shard_rows, monkeypatch):
+    """The sharded list build (the GENERAL instantiations of the LRF kernels, the shard tests of the row scan) without a
+    second GPU: every rank's handle is built on cuda:0 with no communicator, so its pair counts and LRF moments stay
+    partial, and their sum over the ranks must be the reference's lists and lrf_update (what lrf_gather,
+    nonbondene.f90:616, produces).  The all-reduce itself needs >= 2 GPUs: test_multi_gpu.py."""
+    from oracle.pyoracle import Oracle
+    from q6_b200 import synth
+    from q6_b200.engine import Qnb
+    from q6_b200.system import shard_system
+    if shard_rows:
+        monkeypatch.delenv("QNB_SHARD_PAIRS", raising=False)
+    else:
+        monkeypatch.setenv("QNB_SHARD_PAIRS", "1")     # read by qnb_init: the reference's pair partition
+    if case == "sphere_q":
+        q = synth.solvated_sphere(16.0, 9.0, 20, 2, 61, fep="evb")
+        cuts = common.sph_cuts(8.0)
+    elif case == "water_box":
+        q = synth.water_box(10, 62)
+        cuts = dict(Rq=-1.0, Rcq2=1.0, RcLRF2=13.0 ** 2, Rcpp2=81.0, Rcpw2=81.0, Rcww2=81.0, RcLRF=13.0)
+    else:   # a box large enough for the row-image scan (2(m+1) <= n cells): the kernel the sharded C5 bench runs
+        q = synth.water_box(14, 63)
+        cuts = dict(Rq=-1.0, Rcq2=1.0, RcLRF2=11.0 ** 2, Rcpp2=49.0, Rcpw2=49.0, Rcww2=49.0, RcLRF=11.0)
+    o = Oracle(q)
+    want_counts = o.make_pair_lists(q.xtop, **cuts)
+    want = o.export_lrf()
+    for world in (2, 3):
+        counts = np.zeros(5, dtype=np.int64)
+        mom = np.zeros_like(want[:, 3:])
+        for rank in range(world):
+            g = Qnb(shard_system(q, rank, world), device=0)
+            try:
+                counts += np.asarray(g.make_pair_lists(q.xtop, **cuts))[:5]
+                lrf = g.export_lrf()
+                assert np.allclose(lrf[:, :3], want[:, :3], rtol=0, atol=1e-9)   # centres: complete on every rank
+                mom += lrf[:, 3:]
+            finally:
+                g.close()
+        assert np.array_equal(counts, np.asarray(want_counts)[:5])
+        scale = np.abs(want[:, 3:]).max(axis=0) + 1e-300
+        tol = np.where(np.arange(3, 43) < 16, 1e-9, 2e-5)
+        assert np.all(np.abs(mom - want[:, 3:]) <= tol * scale + 1e-12), (case, world)
+
+
 def test_list_rebuild_after_motion():
     """Lists rebuilt at moved coordinates equal the oracle's; once-only Q lists stay (nbqplist L3678)."""
     from oracle.pyoracle import Oracle
