@@ -619,6 +619,7 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
     const Dev &D = h->D;
     drop_graphs(h);   // row pointers, counts and list sizes are baked into the captured launches
     const int nu = D.nunit;
+    if (nu >= (1 << 26)) return fail("qnb_build_lists: %d charge groups + waters, the LRF queue entries hold 26 bits of item index", nu);
     if (!h->restoring) {   // what qnb_save_lists would have to remember
         h->hx_build.assign(hx_for_grid, hx_for_grid + 3 * (size_t)D.natom);
         h->cut_build = h->cut;
