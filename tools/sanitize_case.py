@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import common  # noqa: E402
 from q6_b200.engine import Qnb  # noqa: E402
 
-want = sys.argv[1:] or ["sph_evb2", "box_solute_q", "box_water", "box_anyatom"]
+want = sys.argv[1:] or ["sph_evb2", "sph_small_rcq", "box_solute_q", "box_water", "box_water_rowimage", "box_solute_rowimage", "box_anyatom"]
 for name, q, cuts, lam in common.small_systems():
     if name not in want and want != ["all"]:
         continue
