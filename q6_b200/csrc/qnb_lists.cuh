@@ -1293,13 +1293,23 @@ k_lrf_allpairs(Dev D, Cut C, const double *__restrict__ x, const double *__restr
                     zone = lrf_pair ? 1 : 0;
                 }
                 if (zone != 1) continue;
-                for (int k = s_a0[it]; k < s_a0[it + 1]; k++) {
-                    // lrf_update (nonbondene.f90:656-719), see lrf_atom; FP32 displacement from FP32 copies
-                    // (|x| ~ 30 A: 2e-6 A, the phi3 path is FP32 anyway)
-                    const double4 sa = s_atom[k];
-                    const float4 af = s_atomf[k];
-                    lrf_atom(m, h, sa.x - cx_, sa.y - cy_, sa.z - cz_, sa.w, af.x - cxf, af.y - cyf, af.z - czf, af.w);
-                }
+                // lrf_update (nonbondene.f90:656-719), see lrf_atom; FP32 displacement from FP32 copies
+                // (|x| ~ 30 A: 2e-6 A, the phi3 path is FP32 anyway)
+                const int k0 = s_a0[it], k1 = s_a0[it + 1];   // the same for every lane
+                if (k1 - k0 == 3) {
+                    // three-atom unit (every water, most solute groups): straight-line code, the three dependency chains
+                    // interleave (one atom at a time left ~2 cycles of fixed-latency stall per instruction, r03h)
+                    const double4 s0 = s_atom[k0], s1 = s_atom[k0 + 1], s2 = s_atom[k0 + 2];
+                    const float4 f0 = s_atomf[k0], f1 = s_atomf[k0 + 1], f2 = s_atomf[k0 + 2];
+                    lrf_atom(m, h, s0.x - cx_, s0.y - cy_, s0.z - cz_, s0.w, f0.x - cxf, f0.y - cyf, f0.z - czf, f0.w);
+                    lrf_atom(m, h, s1.x - cx_, s1.y - cy_, s1.z - cz_, s1.w, f1.x - cxf, f1.y - cyf, f1.z - czf, f1.w);
+                    lrf_atom(m, h, s2.x - cx_, s2.y - cy_, s2.z - cz_, s2.w, f2.x - cxf, f2.y - cyf, f2.z - czf, f2.w);
+                } else
+                    for (int k = k0; k < k1; k++) {
+                        const double4 sa = s_atom[k];
+                        const float4 af = s_atomf[k];
+                        lrf_atom(m, h, sa.x - cx_, sa.y - cy_, sa.z - cz_, sa.w, af.x - cxf, af.y - cyf, af.z - czf, af.w);
+                    }
             }
         }
         base = tend;
