@@ -51,15 +51,12 @@ subroutine qnb_setup
 
   ! The interfaces pass x, d and every real table as c_double: a Q6 built with -DQSINGLE / -DQUADRUPLE cannot use them.
   if (kind(1.0_prec) /= c_double) call die('USE_QNB needs the double-precision build of Q6 (-DQDOUBLE)')
-  ! Not wired up in this glue (each would be silently wrong otherwise, ADVICE r1):
+  ! Not wired up in this glue (it would be silently wrong otherwise, ADVICE r1):
   !  * Qdyn6p with several ranks: make_pair_lists returns before lrf_gather (nonbondene.f90:831) and gather_nonbond /
   !    the master sum (potene.f90:114-119, 195-222) would add the GPU's already complete d, E, EQ once per rank.  The
   !    multi-GPU route is qnb_comm_init on every rank (NCCL all-reduce inside qnb_build_lists / qnb_nonbond) WITH those
   !    two MPI steps removed; see INTEGRATION.md.
-  !  * MC_volume (constant_pressure, md.f90:1976-2284) needs qnb_save_lists before the trial move, qnb_update_box after
-  !    every change of boxlength and qnb_restore_lists on rejection; the patch does not add those hunks.
   if (numnodes > 1) call die('USE_QNB: run one rank per GPU only after wiring qnb_comm_init (INTEGRATION.md); this glue is serial')
-  if (use_PBC .and. constant_pressure) call die('USE_QNB: constant_pressure (MC_volume) is not hooked up in this glue')
   ngpu = qnb_device_count()
   if (ngpu < 1) call die('USE_QNB: no CUDA device: '//qnb_message())
 
@@ -163,6 +160,32 @@ subroutine qnb_glue_make_pair_lists(Rq,Rcq2,RcLRF2,Rcpp2,Rcpw2,Rcww2)
                       real(Rcpw2,c_double), real(Rcww2,c_double), real(RcLRF,c_double), c_null_ptr) /= 0) &
      call die('make_pair_lists: '//qnb_message())
 end subroutine qnb_glue_make_pair_lists
+
+! --- MC_volume (constant_pressure, md.f90:1976-2284) under USE_QNB: three calls added by the patch
+! next to "old_nbww = nbww ... old_lrf(:) = lrf(:)" (md.f90:2022-2058): the GPU remembers its last list build
+subroutine qnb_glue_save_lists
+  if (use_LRF) then
+     if (qnb_save_lists(qnb_handle) /= 0) call die('qnb_save_lists: '//qnb_message())
+  end if
+end subroutine qnb_glue_save_lists
+
+! after boxlength / inv_boxl changed (md.f90:2088-2090).  With LRF on the make_pair_lists that follows (md.f90:2170) sends
+! the box again, with LRF off the lists are kept and the trial pot_energy (md.f90:2177) must see the new box
+subroutine qnb_glue_update_box
+  real(c_double) :: bl(3), ibl(3)
+  if (.not. use_PBC) return
+  bl = (/ boxlength%x, boxlength%y, boxlength%z /); ibl = (/ inv_boxl%x, inv_boxl%y, inv_boxl%z /)
+  if (qnb_update_box(qnb_handle, bl, ibl) /= 0) call die('qnb_update_box: '//qnb_message())
+end subroutine qnb_glue_update_box
+
+! volume change rejected (md.f90:2203-2256), called after the host has put boxlength, lists and lrf(:) back
+subroutine qnb_glue_restore_lists
+  if (use_LRF) then        ! lists, LRF moments and the box of the saved build, bit for bit
+     if (qnb_restore_lists(qnb_handle) /= 0) call die('qnb_restore_lists: '//qnb_message())
+  else
+     call qnb_glue_update_box
+  end if
+end subroutine qnb_glue_restore_lists
 
 ! --- body of pot_energy_nonbonds (potene.f90:320) under USE_QNB; d was zeroed at potene.f90:109 and is added to
 subroutine qnb_glue_nonbond(E_loc,EQ_loc,md)

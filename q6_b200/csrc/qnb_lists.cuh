@@ -6,6 +6,10 @@
 // reference tests all ncgp^2 switch-atom pairs; here switch atoms are binned into cells of edge
 // >= the largest cut-off and only the 27 surrounding cells are tested -- with the reference's own
 // FP64 expression, so the resulting set of pairs is identical.
+//
+// LRF kernels: k_lrf_allpairs (sphere with the LRF cut-off spanning it: one thread per target, sources broadcast from
+// shared memory) and k_lrf_accumulate (everything else: one warp per target, flat walk over the candidates of the cell
+// rows in reach, FP32 screening, accepted items batched through a queue, sources read from k_pack_lrf_planes' records).
 #pragma once
 #include "qnb_kernels.cuh"
 

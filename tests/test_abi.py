@@ -103,19 +103,20 @@ def test_fortran_interface_module_matches_header():
 @pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference tree not mounted")
 def test_integration_patch_applies_to_the_reference(tmp_path):
     """integration/q6_qnb.patch (the #if defined(USE_QNB) branches of make_pair_lists, pot_energy_nonbonds, nonbond_qq,
-    nonbond_qqp and the two calls in qdyn.f90) applies cleanly to the reference sources, and every procedure it calls
+    nonbond_qqp, the two calls in qdyn.f90 and the three MC_volume hooks in md.f90) applies cleanly to the reference sources, and every procedure it calls
     exists in integration/qnb_glue.f90."""
     import shutil
     import subprocess
     src = tmp_path / "src"
     src.mkdir()
-    for f in ("nonbondene.f90", "potene.f90", "qdyn.f90"):
+    for f in ("md.f90", "nonbondene.f90", "potene.f90", "qdyn.f90"):
         shutil.copy(os.path.join("/root/reference/src", f), src / f)
     patch = os.path.join(ROOT, "integration", "q6_qnb.patch")
     out = subprocess.run(["patch", "-p1", "--dry-run", "-i", patch], cwd=tmp_path, capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     glue = open(os.path.join(ROOT, "integration", "qnb_glue.f90")).read().lower()
     called = set(re.findall(r"^\+\s*call (qnb_\w+)", open(patch).read(), flags=re.M))
-    assert called == {"qnb_glue_make_pair_lists", "qnb_glue_add_qq", "qnb_glue_nonbond", "qnb_setup", "qnb_shutdown"}
+    assert called == {"qnb_glue_make_pair_lists", "qnb_glue_add_qq", "qnb_glue_nonbond", "qnb_setup", "qnb_shutdown",
+                      "qnb_glue_save_lists", "qnb_glue_update_box", "qnb_glue_restore_lists"}
     for name in called:
         assert f"subroutine {name}" in glue, name
