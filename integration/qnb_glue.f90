@@ -51,12 +51,14 @@ subroutine qnb_setup
 
   ! The interfaces pass x, d and every real table as c_double: a Q6 built with -DQSINGLE / -DQUADRUPLE cannot use them.
   if (kind(1.0_prec) /= c_double) call die('USE_QNB needs the double-precision build of Q6 (-DQDOUBLE)')
-  ! Not wired up in this glue (it would be silently wrong otherwise, ADVICE r1):
-  !  * Qdyn6p with several ranks: make_pair_lists returns before lrf_gather (nonbondene.f90:831) and gather_nonbond /
-  !    the master sum (potene.f90:114-119, 195-222) would add the GPU's already complete d, E, EQ once per rank.  The
-  !    multi-GPU route is qnb_comm_init on every rank (NCCL all-reduce inside qnb_build_lists / qnb_nonbond) WITH those
-  !    two MPI steps removed; see INTEGRATION.md.
-  if (numnodes > 1) call die('USE_QNB: run one rank per GPU only after wiring qnb_comm_init (INTEGRATION.md); this glue is serial')
+  ! Qdyn6p (several MPI ranks, one GPU each): every rank evaluates its calculation_assignment share and the library sums
+  ! d, E, EQ (per step) and the LRF moments (per list build) over the ranks - qnb_connect_ranks below.  The patch takes
+  ! the reference's own exchange out of the USE_QNB build: make_pair_lists returns before lrf_gather
+  ! (nonbondene.f90:831), gather_nonbond (L6760) returns at once and the master's sum over d_recv / E_recv
+  ! (potene.f90:200-222) is compiled out, else the complete sums would be counted once per rank.
+  ! MC_volume's restore of a rejected move runs on the master only (md.f90:2203): not wired for several ranks.
+  if (numnodes > 1 .and. use_PBC .and. constant_pressure) &
+     call die('USE_QNB: constant_pressure (MC_volume) with several MPI ranks is not hooked up in this glue')
   ngpu = qnb_device_count()
   if (ngpu < 1) call die('USE_QNB: no CUDA device: '//qnb_message())
 
@@ -134,6 +136,7 @@ subroutine qnb_setup
   s%is_master = merge(1, 0, nodeid == 0)
 
   if (qnb_init(s, mod(nodeid, ngpu), qnb_handle) /= 0) call die('qnb_init: '//qnb_message())
+  if (numnodes > 1) call qnb_connect_ranks
   ! x and d are module arrays allocated once (md.f90): page-locked, so that every step uploads x without a staging copy
   ! and the device adds the gradient into d; a failure only means the staged path is used
   if (qnb_register_host_buffers(qnb_handle, x, d) /= 0) write(*,'(a)') 'qnb: x / d not page-locked: '//qnb_message()
@@ -147,6 +150,37 @@ subroutine qnb_setup
   deallocate(g_cgp, g_cgpatom, g_excl, g_iqatom, g_iqseq, g_iac, g_ljcod, g_listex, g_list14, g_exlong, g_14long, g_qiac, &
              g_iqexpnb, g_jqexpnb, g_els_i, g_els_j, g_qconn, g_crg, g_iaclib, g_qcrg, g_qavdw, g_qbvdw, g_sc, g_els)
 end subroutine qnb_setup
+
+! --- Qdyn6p: connect the GPUs of the ranks (once, from qnb_setup).  First choice is the all-reduce kernel over peer memory
+! (NVLink / NVSwitch, ranks of one node): every rank exports a CUDA IPC descriptor of its arena, MPI_Allgather hands all of
+! them to everybody, every rank maps its peers.  If any rank cannot (no peer access, ranks on several nodes) ALL ranks go
+! to NCCL: rank 0 draws the unique id, MPI_Bcast, qnb_comm_init (which also drops a peer mapping that did succeed here).
+subroutine qnb_connect_ranks
+#if defined (USE_MPI)
+  character(kind=c_char), target :: blob(QNB_IPC_BLOB), id(128)
+  character(kind=c_char), allocatable, target :: blobs(:)
+  integer :: ierr, ok, allok
+  allocate(blobs(QNB_IPC_BLOB*numnodes))
+  if (qnb_comm_ipc_export(qnb_handle, blob) /= 0) call die('qnb_comm_ipc_export: '//qnb_message())
+  call MPI_Allgather(blob, QNB_IPC_BLOB, MPI_BYTE, blobs, QNB_IPC_BLOB, MPI_BYTE, MPI_COMM_WORLD, ierr)
+  if (ierr /= 0) call die('qnb_connect_ranks/MPI_Allgather')
+  ok = merge(1, 0, qnb_comm_ipc_attach(qnb_handle, nodeid, numnodes, blobs) == 0)
+  call MPI_Allreduce(ok, allok, 1, MPI_INTEGER, MPI_MIN, MPI_COMM_WORLD, ierr)
+  if (ierr /= 0) call die('qnb_connect_ranks/MPI_Allreduce')
+  if (allok == 0) then
+     if (nodeid == 0) then
+        write(*,'(a)') 'qnb: no peer memory between all GPUs of the job, the sums over the ranks go through NCCL'
+        if (qnb_comm_unique_id(id) /= 0) call die('qnb_comm_unique_id: '//qnb_message())
+     end if
+     call MPI_Bcast(id, 128, MPI_BYTE, 0, MPI_COMM_WORLD, ierr)
+     if (ierr /= 0) call die('qnb_connect_ranks/MPI_Bcast')
+     if (qnb_comm_init(qnb_handle, nodeid, numnodes, id) /= 0) call die('qnb_comm_init: '//qnb_message())
+  end if
+  deallocate(blobs)
+#else
+  call die('USE_QNB: several ranks need the MPI build (-DUSE_MPI)')
+#endif
+end subroutine qnb_connect_ranks
 
 ! --- body of make_pair_lists (nonbondene.f90:749) under USE_QNB
 subroutine qnb_glue_make_pair_lists(Rq,Rcq2,RcLRF2,Rcpp2,Rcpw2,Rcww2)

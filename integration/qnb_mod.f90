@@ -11,6 +11,7 @@ use, intrinsic :: iso_c_binding
 implicit none
 
 integer(c_int), parameter :: QNB_ABI_VERSION = 1
+integer(c_int), parameter :: QNB_IPC_BLOB = 128       ! bytes of a qnb_comm_ipc_export descriptor
 integer(c_int), parameter :: QNB_FLAG_MD = 1, QNB_FLAG_QQ = 2, QNB_FLAG_NO_ENERGY = 4, QNB_FLAG_D_IS_ZERO = 8, &
                              QNB_FLAG_SOLVENT_RESTRAINTS = 16
 

@@ -2164,6 +2164,14 @@ int qnb_comm_init(qnb_handle *h, int rank, int nranks, const void *id128) {
     int rc = g_nccl.CommInitRank(&h->comm, nranks, id, rank);
     if (rc) return fail("ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
     h->rank = rank; h->nranks = nranks;
+    // NCCL takes over on EVERY rank: a peer-memory attach that succeeded here but failed on another rank (the host falls
+    // back to this call on all of them) must not leave this rank on the peer-memory kernel
+    if (h->p2p.n > 1) {
+        for (int k = 0; k < kMaxPeers; k++)
+            if (h->peer_base[k]) { cudaIpcCloseMemHandle(h->peer_base[k]); h->peer_base[k] = nullptr; }
+        h->p2p = P2PComm{};
+        drop_graphs(h);
+    }
     return 0;
 }
 

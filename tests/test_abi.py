@@ -103,7 +103,8 @@ def test_fortran_interface_module_matches_header():
 @pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference tree not mounted")
 def test_integration_patch_applies_to_the_reference(tmp_path):
     """integration/q6_qnb.patch (the #if defined(USE_QNB) branches of make_pair_lists, pot_energy_nonbonds, nonbond_qq,
-    nonbond_qqp, the two calls in qdyn.f90 and the three MC_volume hooks in md.f90) applies cleanly to the reference sources, and every procedure it calls
+    nonbond_qqp, the two calls in qdyn.f90, the three MC_volume hooks in md.f90 and the removal of gather_nonbond / the
+    master's sum for MPI runs) applies cleanly to the reference sources, and every procedure it calls
     exists in integration/qnb_glue.f90."""
     import shutil
     import subprocess
