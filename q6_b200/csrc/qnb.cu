@@ -109,7 +109,8 @@ struct qnb_handle {
     int device = 0, nsm = 148;
     HostTables T;
     Dev D{};
-    cudaStream_t st = nullptr, aux[kAux] = {};
+    cudaStream_t st = nullptr, aux[kAux] = {}, lrf_st = nullptr;
+    cudaEvent_t ev_lrf = nullptr;   // end of the LRF accumulation of a list build (lrf_st)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_pack = nullptr, ev_join[kAux] = {};
     cudaEvent_t ev_bt[6] = {};   // qnb_bench_build_lists: LRF kernels (0,1), row count pass (2,3), row fill pass (4,5)
     bool time_build = false;
@@ -455,7 +456,18 @@ static int init_device(qnb_handle *h) {
         CU(cudaGetDeviceProperties(&prop, h->device));
         h->nsm = prop.multiProcessorCount;
     }
-    CU(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+    {
+        // The main stream carries the chain of short list-build kernels with its host round trips (and the step's pack
+        // kernel): most urgent.  The LRF accumulation (1.5 ms on C5, thousands of blocks) runs next to that chain on a stream
+        // of its own at the lowest priority, so that the chain's blocks are placed first whenever an SM slot frees up
+        // (until r04 it ran on aux[4], a most-urgent stream, and the chain queued behind it).
+        int lo = 0, hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        const bool flat = getenv("QNB_NO_PRIORITY") != nullptr;
+        CU(cudaStreamCreateWithPriority(&h->st, cudaStreamNonBlocking, flat || getenv("QNB_ST_LOW") ? lo : hi));
+        CU(cudaStreamCreateWithPriority(&h->lrf_st, cudaStreamNonBlocking, flat || !getenv("QNB_LRF_HIGH") ? lo : hi));
+        CU(cudaEventCreateWithFlags(&h->ev_lrf, cudaEventDisableTiming));
+    }
     for (int k = 0; k < kAux; k++) {
     {
         // the longest kernel of a step is placed first: stream k carries kernel k (kStreamOf); the solute rows (stream 1)
@@ -647,11 +659,10 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
     // LRF: cgp_centers + lrf_update over every pair that falls in the LRF branch.  It needs the cell tables and the
     // packed atoms but not the rows, and it is the longest kernel of a build: it runs on a side stream next to the
     // row/chunk kernels (which are short, latency-bound and interrupted by the host round trip for the sizes).
-    constexpr int kLrfStream = 4;
     bool lrf_forked = false;
     auto launch_lrf = [&]() {
         if (!(D.use_LRF && D.ncgp > 0) || h->restoring) return;
-        cudaStream_t ls = h->multi_stream ? h->aux[kLrfStream] : h->st;
+        cudaStream_t ls = h->multi_stream ? h->lrf_st : h->st;
         if (h->multi_stream) {
             cudaEventRecord(h->ev_fork, h->st);
             cudaStreamWaitEvent(ls, h->ev_fork, 0);
@@ -711,7 +722,7 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
             }
         }
         if (h->time_build) cudaEventRecord(h->ev_bt[1], ls);
-        if (h->multi_stream) { cudaEventRecord(h->ev_join[kLrfStream], ls); lrf_forked = true; }
+        if (h->multi_stream) { cudaEventRecord(h->ev_lrf, ls); lrf_forked = true; }
     };
     const bool md_lists = true;
     if (nu > 0 && md_lists) {
@@ -813,7 +824,7 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
     if (!(nu > 0 && md_lists)) { if (launch_q_lists(h)) return 1; }
     // LRF: the moments were started on the side stream after the cell tables (see above); join, then the exchange
     if (D.use_LRF && D.ncgp > 0 && !h->restoring) {
-        if (lrf_forked) CU(cudaStreamWaitEvent(h->st, h->ev_join[kLrfStream], 0));
+        if (lrf_forked) CU(cudaStreamWaitEvent(h->st, h->ev_lrf, 0));
         if (h->comm || p2p_ready(h)) {
             // lrf_gather (nonbondene.f90:616-623): sum the moments over the ranks; the centres (identical on every rank)
             // are summed along and recomputed afterwards: bit-identical to the single-rank value
@@ -2439,6 +2450,8 @@ int qnb_finalize(qnb_handle *h) {
     if (h->st) cudaStreamSynchronize(h->st);
     drop_graphs(h, true);
     for (int k = 0; k < kAux; k++) { if (h->aux[k]) cudaStreamDestroy(h->aux[k]); if (h->ev_join[k]) cudaEventDestroy(h->ev_join[k]); }
+    if (h->lrf_st) cudaStreamDestroy(h->lrf_st);
+    if (h->ev_lrf) cudaEventDestroy(h->ev_lrf);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_pack) cudaEventDestroy(h->ev_pack);
     for (int k = 0; k < 6; k++) if (h->ev_bt[k]) cudaEventDestroy(h->ev_bt[k]);
