@@ -680,7 +680,10 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
             // periodic image by cell row when 2(m+1) <= n in every dimension (then |delta| < box/2 for every scanned cell)
             bool rowshift = G.periodic && !all;
             const int rr[3] = {h->lrf_reach.x, h->lrf_reach.y, h->lrf_reach.z};
-            for (int d = 0; d < 3; d++) rowshift = rowshift && 2 * (rr[d] + 1) <= G.n[d];
+            // One cell more than the scan itself needs (2(m+1) <= n): the kernel takes the pair's shift from the image of
+            // the scanned row, which equals nint((x_switch - cgp_cent)/L) as long as the target's group centre lies within
+            // the spare cell(s) of its switch atom - two cell edges with this margin.
+            for (int d = 0; d < 3; d++) rowshift = rowshift && 2 * (rr[d] + 2) <= G.n[d];
             const bool general = D.any_atom || D.sharded;
             // sphere, switching-atom lists, unsharded, every cell within the LRF reach: all-pairs tiling
             int gmax = 0;
