@@ -677,7 +677,7 @@ static int build_device(qnb_handle *h, const double *hx_for_grid) {
             double ext = 0;
             for (int d = 0; d < 3; d++) ext = std::max(ext, G.n[d] / G.inv_cell[d]);
             const bool compact = !all && rl < 0.9 * ext;
-            // periodic image by cell row when 2(m+1) <= n in every dimension (then |delta| < box/2 for every scanned cell)
+            // periodic image by cell row when the reach m leaves room in every dimension (|delta| < box/2 for every scanned cell needs 2(m+1) <= n)
             bool rowshift = G.periodic && !all;
             const int rr[3] = {h->lrf_reach.x, h->lrf_reach.y, h->lrf_reach.z};
             // One cell more than the scan itself needs (2(m+1) <= n): the kernel takes the pair's shift from the image of

@@ -851,7 +851,7 @@ __device__ __forceinline__ void lrf_atom_d(double (&m)[11], float (&h)[13], doub
 // accumulated (phi2 and phi3 are symmetric) and expanded on write.  FP64, no divisions:
 // field0 = q/r^3, field1 = 3 field0/r^2, field2 = -field1/r^2 from 1/r (rsqrt seed + Halley step).
 // Scan modes.  ROWSHIFT (periodic box, reach small enough that the image of a scanned cell row is known from its cell
-// offset, 2(m+1) <= n in every dimension): the periodic image is applied once per cell row to the TARGET, rows that
+// offset, 2(m+2) <= n in every dimension, see qnb.cu): the periodic image is applied once per cell row to the TARGET, rows that
 // cannot reach the LRF shell are skipped and the x-range of the others is trimmed to the shell's chord, so the
 // per-candidate screening is nine FP32 instructions.  GENERAL adds what any-atom cut-offs and sharded builds need.
 struct LrfSeg { int lo, hi; float tx, ty, tz; int img; };   // img: periodic image of the row, (ix+1) | (iy+1) << 2 | (iz+1) << 4
